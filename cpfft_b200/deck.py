@@ -1,0 +1,305 @@
+"""Reader for the reference's free-form input decks (examples/*.in), restricted to the
+keywords the shipped decks use.  Semantics follow src/FFT_finite_3d.f:14-160 (command loop),
+src/inmat.f:69-300, src/incrystal.f:33-998, src/inelem.f:33-106, src/inlodcase.f:24-146,
+src/inlod.f:26-109, src/indypm.f:26-68 and the scanner's conventions in src/scan.f:
+  * a line whose first column is ``c`` followed by a blank (or nothing) is a comment;
+  * a comma is a token; in the property readers a comma makes the reader fetch the NEXT line
+    (``readsc``), discarding whatever followed the comma on the current line
+    (incrystal.f:989-990, inmat.f:288-289) -- ``harden_n 5,48`` therefore reads 5;
+  * bilinear properties are parsed into REAL*4 (inmat.f:100-127).
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import List
+
+import numpy as np
+
+from .problem import Crystal, Material, Problem, SLIP_TYPES, ELASTIC_TYPES, COMPONENTS
+
+
+class DeckError(ValueError):
+    pass
+
+
+def _tokens(line: str) -> List[str]:
+    # quoted strings stay one token; commas are tokens
+    out = []
+    for m in re.finditer(r"'[^']*'|\"[^\"]*\"|,|[^\s,]+", line):
+        out.append(m.group(0))
+    return out
+
+
+def _is_comment(line: str) -> bool:
+    s = line.rstrip("\n")
+    return len(s) >= 1 and s[0] in "cC" and (len(s) == 1 or s[1] in " \t")
+
+
+def _int_list(tokens: List[str]) -> List[int]:
+    """Integer lists ``1-100``, ``2-10 by 2``, ``1 2 3`` (user_list.f:13, scan trlist)."""
+    vals: List[int] = []
+    i = 0
+    while i < len(tokens):
+        t = tokens[i]
+        m = re.fullmatch(r"(\d+)-(\d+)", t)
+        if m:
+            a, b, step = int(m.group(1)), int(m.group(2)), 1
+            if i + 2 < len(tokens) and tokens[i + 1].lower() == "by":
+                step = int(tokens[i + 2]); i += 2
+            vals.extend(range(a, b + 1, step))
+        elif re.fullmatch(r"\d+", t):
+            vals.append(int(t))
+        else:
+            break
+        i += 1
+    return vals
+
+
+class _Lines:
+    def __init__(self, text: str):
+        self.lines = [l for l in text.splitlines() if not _is_comment(l) and l.strip()]
+        self.pos = 0
+
+    def peek(self):
+        return self.lines[self.pos] if self.pos < len(self.lines) else None
+
+    def next(self):
+        l = self.peek()
+        self.pos += 1
+        return l
+
+
+def _property_tokens(lines: _Lines, first: List[str]) -> List[str]:
+    """Token stream of a ``properties`` card: a comma jumps to the next line."""
+    toks: List[str] = []
+    cur = first
+    while True:
+        if "," in cur:
+            toks.extend(cur[:cur.index(",")])
+            nxt = lines.next()
+            if nxt is None:
+                break
+            cur = _tokens(nxt)
+        else:
+            toks.extend(cur)
+            break
+    return toks
+
+
+_CRYSTAL_NUM = {
+    "e": "e", "nu": "nu", "mu": "mu", "harden_n": "harden_n", "theta_0": "theta_0",
+    "tau_y": "tau_y", "tau_v": "tau_v", "voche_m": "voche_m", "voce_m": "voche_m",
+    "iD_v": "iD_v", "eps_dot_0_y": "eps_dot_0_y", "gamma_bar": "eps_dot_0_y", "k_0": "k_0",
+    "b": "burgers", "atol": "atol", "atol1": "atol1", "rtol": "rtol", "rtol1": "rtol1",
+}
+
+
+def _read_crystal(lines: _Lines, toks: List[str], crystals: dict):
+    cnum = int(toks[1])
+    c = Crystal()
+    first = _tokens(lines.next())
+    if not first or not first[0].lower().startswith("prop"):
+        raise DeckError("crystal: expected 'properties'")
+    pt = _property_tokens(lines, first[1:])
+    i = 0
+    while i < len(pt):
+        k = pt[i]
+        if k == "slip_type":
+            v = pt[i + 1]
+            if v not in SLIP_TYPES:
+                raise DeckError(f"slip_type {v} not supported (fcc, bcc48)")
+            c.slip_type = SLIP_TYPES[v]; i += 2
+        elif k == "elastic_type":
+            c.elastic_type = ELASTIC_TYPES[pt[i + 1]]; i += 2
+        elif k == "hardening":
+            if pt[i + 1] not in ("voce", "voche"):
+                raise DeckError(f"hardening {pt[i + 1]} not supported (voce only)")
+            c.h_type = 1; i += 2
+        elif k == "alter_mode":
+            c.alter_mode = 1 if pt[i + 1].lower() in ("on", "true") else 0; i += 2
+        elif k == "miter":
+            c.miter = int(pt[i + 1]); i += 2
+        elif k == "solver":
+            if pt[i + 1] != "nr":
+                raise DeckError("only solver nr is supported")
+            i += 2
+        elif k in _CRYSTAL_NUM:
+            setattr(c, _CRYSTAL_NUM[k], float(pt[i + 1])); i += 2
+        else:
+            raise DeckError(f"crystal: unknown property {k}")
+    crystals[cnum] = c
+
+
+def _read_material(lines: _Lines, toks: List[str], materials: List[Material], base_dir: str):
+    m = Material(name=toks[1])
+    first = _tokens(lines.next())
+    if not first or not first[0].lower().startswith("prop"):
+        raise DeckError("material: expected 'properties'")
+    kind = first[1]
+    if kind == "bilinear":
+        m.type = 1
+        # inmat.f:97-133: a comma only continues when it ends the line
+        pt: List[str] = []
+        cur = first[2:]
+        while True:
+            ends_with_comma = bool(cur) and cur[-1] == ","
+            pt.extend(t for t in cur if t != ",")
+            if ends_with_comma:
+                cur = _tokens(lines.next())
+            else:
+                break
+        i = 0
+        while i < len(pt):
+            k = pt[i]
+            if k in ("e", "nu", "beta", "tan_e", "yld_pt"):
+                setattr(m, k, float(np.float32(float(pt[i + 1])))); i += 2
+            elif k in ("alpha", "rho"):
+                i += 2
+            else:
+                raise DeckError(f"bilinear: unknown property {k}")
+    elif kind == "cp":
+        m.type = 10
+        pt = _property_tokens(lines, first[2:])
+        i = 0
+        ncry = 1
+        while i < len(pt):
+            k = pt[i]
+            if k in ("rho", "alpha", "tolerance"):
+                i += 2
+            elif k == "angle_convention":
+                if pt[i + 1] != "kocks":
+                    raise DeckError("only kocks angles are supported")
+                i += 2
+            elif k == "angle_type":
+                if pt[i + 1] != "degrees":
+                    raise DeckError("only degrees are supported")
+                i += 2
+            elif k == "n_crystals":
+                ncry = int(pt[i + 1]); i += 2
+            elif k == "crystal_input":
+                if pt[i + 1] != "single":
+                    raise DeckError("only crystal_input single is supported")
+                i += 2
+            elif k == "crystal_type":
+                m.crystal = int(pt[i + 1]); i += 2
+            elif k == "orientation_input":
+                m.orientation_input = 1 if pt[i + 1] == "single" else 2; i += 2
+            elif k == "angles":
+                m.angles = (float(pt[i + 1]), float(pt[i + 2]), float(pt[i + 3])); i += 4
+            elif k == "filename":
+                m.orientation_file = os.path.join(base_dir, pt[i + 1].strip("'\"")); i += 2
+            elif k == "debug":
+                i += 2
+            else:
+                raise DeckError(f"cp: unknown property {k}")
+        if ncry != 1:
+            raise DeckError("n_crystals > 1 is not supported yet")
+    else:
+        raise DeckError(f"material model {kind} not supported (bilinear, cp)")
+    materials.append(m)
+
+
+def read_orientation_file(path: str, n3: int) -> np.ndarray:
+    """``elem, psi, theta, phi`` per line (mod_crystals.f:2233-2318, read sequentially)."""
+    ang = np.zeros((n3, 3))
+    with open(path) as f:
+        rows = [re.split(r"[,\s]+", l.strip()) for l in f if l.strip()]
+    for r in rows:
+        e = int(r[0])
+        ang[e - 1] = [float(r[1]), float(r[2]), float(r[3])]
+    return ang
+
+
+def read_deck(path: str) -> Problem:
+    base_dir = os.path.dirname(os.path.abspath(path))
+    with open(path) as f:
+        lines = _Lines(f.read())
+    N = None
+    materials: List[Material] = []
+    crystals: dict = {}
+    elem_mat = None
+    FP_max = np.zeros(9)
+    isNBC = np.zeros(9, dtype=np.int32)
+    mults: dict = {}
+    tolNR, tolPCG, maxIter, tstep = 1e-5, 1e-10, 10, 1.0
+    while True:
+        line = lines.next()
+        if line is None:
+            break
+        toks = _tokens(line)
+        key = toks[0].lower()
+        if key == "number":                                   # number of grid N
+            N = int(toks[-1])
+        elif key == "crystal":
+            _read_crystal(lines, toks, crystals)
+        elif key == "material":
+            _read_material(lines, toks, materials, base_dir)
+        elif key == "elements":
+            if N is None:
+                raise DeckError("'number of grid' must precede 'elements'")
+            elem_mat = np.zeros(N ** 3, dtype=np.int32)
+            names = [m.name for m in materials]
+            while lines.peek() is not None and re.match(r"\s*\d", lines.peek()):
+                t = _tokens(lines.next())
+                k = t.index("material")
+                ids = _int_list(t[:k])
+                elem_mat[np.asarray(ids) - 1] = names.index(t[k + 1]) + 1
+        elif key == "strains":
+            while lines.peek() is not None:
+                t = _tokens(lines.peek())
+                mm = re.fullmatch(r"([FP])_([xyz]{2})", t[0])
+                if not mm:
+                    break
+                lines.next()
+                idx = COMPONENTS.index(mm.group(2))
+                FP_max[idx] = float(t[1])
+                isNBC[idx] = 1 if mm.group(1) == "P" else 0
+        elif key == "loading":
+            while lines.peek() is not None and _tokens(lines.peek())[0].lower() == "step":
+                t = _tokens(lines.next())
+                k = [x.lower()[:6] for x in t].index("constr")
+                for s in _int_list(t[1:k]):
+                    mults[s] = float(t[k + 1])
+        elif key == "nonlinear":
+            while lines.peek() is not None:
+                t = _tokens(lines.peek())
+                k0 = t[0].lower()
+                if k0.startswith("maximum"):
+                    maxIter = int(t[-1])
+                elif k0.startswith("converge"):
+                    for j, x in enumerate(t):
+                        if x == "NR":
+                            tolNR = float(t[j + 1])
+                        if x == "CG":
+                            tolPCG = float(t[j + 1])
+                elif k0 == "time":
+                    tstep = float(t[-1])
+                else:
+                    break
+                lines.next()
+        elif key in ("project", "sizes", "blocking", "output", "compute"):
+            pass
+        elif key == "stop":
+            break
+        else:
+            raise DeckError(f"unknown command: {line.strip()}")
+    if N is None or elem_mat is None:
+        raise DeckError("deck lacks grid size or element list")
+    n3 = N ** 3
+    angles = np.zeros((n3, 3))
+    for im, m in enumerate(materials):
+        if m.type != 10:
+            continue
+        sel = elem_mat == im + 1
+        if m.orientation_input == 2:
+            angles[sel] = read_orientation_file(m.orientation_file, n3)[sel]
+        else:
+            angles[sel] = m.angles
+    ncry = max(crystals) if crystals else 0
+    cry_list = [crystals.get(i + 1, Crystal()) for i in range(ncry)]
+    nstep = max(mults) if mults else 0
+    mult_arr = np.array([mults.get(s + 1, 0.0) for s in range(nstep)])
+    return Problem(N=N, materials=materials, crystals=cry_list, matlist=elem_mat, angles=angles,
+                   FP_max=FP_max, isNBC=isNBC, mults=mult_arr, tolNR=tolNR, tolPCG=tolPCG,
+                   maxIter=maxIter, tstep=tstep)

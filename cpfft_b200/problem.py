@@ -1,0 +1,141 @@
+"""Plain-data description of a CPFFT analysis: grid, materials, crystal library, per-voxel
+material/orientation maps and the load table.  This mirrors what the reference keeps in
+module ``fft`` (src/mod_fft.f:13-79), ``crystal_data`` (src/mod_crystals.f:137-227) and the
+``matprp`` slots filled by src/inmat.f, i.e. everything the hot path reads after input.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+SLIP_TYPES = {"fcc": 1, "bcc48": 8}           # mod_crystals.f:164-172 (supported subset)
+ELASTIC_TYPES = {"isotropic": 1, "cubic": 2}  # mod_crystals.f:173-176
+COMPONENTS = ["xx", "xy", "xz", "yx", "yy", "yz", "zx", "zy", "zz"]  # inlodcase.f:29-139
+
+
+class CrystalPOD(C.Structure):
+    """C layout shared by ``cpfft_crystal`` (include/cpfft_b200.h) and the test oracle."""
+    _fields_ = [
+        ("slip_type", C.c_int32), ("elastic_type", C.c_int32), ("h_type", C.c_int32),
+        ("alter_mode", C.c_int32), ("miter", C.c_int32), ("pad_", C.c_int32),
+        ("e", C.c_double), ("nu", C.c_double), ("mu", C.c_double), ("harden_n", C.c_double),
+        ("theta_0", C.c_double), ("tau_y", C.c_double), ("tau_v", C.c_double),
+        ("voche_m", C.c_double), ("iD_v", C.c_double), ("eps_dot_0_y", C.c_double),
+        ("k_0", C.c_double), ("burgers", C.c_double),
+        ("atol", C.c_double), ("atol1", C.c_double), ("rtol", C.c_double), ("rtol1", C.c_double),
+    ]
+
+
+class MaterialPOD(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("crystal", C.c_int32),
+        ("e", C.c_float), ("nu", C.c_float), ("beta", C.c_float), ("tan_e", C.c_float),
+        ("yld_pt", C.c_float), ("pad_", C.c_float),
+    ]
+
+
+@dataclass
+class Crystal:
+    """Defaults are ``initialize_new_crystal`` (mod_crystals.f:231-410); the single-precision
+    literals there are promoted by ifort ``-fpconstant`` (src/makefile:20), so they are doubles."""
+    slip_type: int = 1
+    elastic_type: int = 1
+    h_type: int = 1
+    alter_mode: int = 0
+    miter: int = 30
+    e: float = 69000.0
+    nu: float = 0.33
+    mu: float = 69000.0 / 2.0 / 1.33
+    harden_n: float = 20.0
+    theta_0: float = 100.0
+    tau_y: float = 0.0
+    tau_v: float = 0.0
+    voche_m: float = 1.0
+    iD_v: float = 0.0
+    eps_dot_0_y: float = 1.0e10
+    k_0: float = 0.0
+    burgers: float = 2.87e-7
+    atol: float = 1.0e-5
+    atol1: float = 1.0e-5
+    rtol: float = 5.0e-5
+    rtol1: float = 1.0e-5
+
+    def pod(self) -> CrystalPOD:
+        p = CrystalPOD()
+        for name, _ in CrystalPOD._fields_:
+            if name != "pad_":
+                setattr(p, name, getattr(self, name))
+        return p
+
+
+@dataclass
+class Material:
+    """type 1 = bilinear (mm01), 10 = crystal plasticity (mm10).  The bilinear properties
+    live in REAL*4 ``matprp`` slots (mod_fft.f:20, inmat.f:100-127): kept as float32."""
+    name: str = "mat"
+    type: int = 1
+    crystal: int = 0          # cp: crystal_type (1-based), crystal_input single
+    e: float = 0.0
+    nu: float = 0.0
+    beta: float = 0.0
+    tan_e: float = 0.0
+    yld_pt: float = 0.0
+    orientation_file: str = ""
+    angles: tuple = (0.0, 0.0, 0.0)
+    orientation_input: int = 1  # 1 single, 2 file
+
+    def pod(self) -> MaterialPOD:
+        p = MaterialPOD()
+        p.type, p.crystal = self.type, self.crystal
+        p.e, p.nu, p.beta, p.tan_e, p.yld_pt = (np.float32(self.e), np.float32(self.nu),
+                                                 np.float32(self.beta), np.float32(self.tan_e),
+                                                 np.float32(self.yld_pt))
+        return p
+
+
+@dataclass
+class Problem:
+    N: int
+    materials: List[Material]
+    crystals: List[Crystal]
+    matlist: np.ndarray                      # (N3,) int32, 1-based material number per voxel
+    angles: np.ndarray                       # (N3,3) float64 Kocks degrees per voxel
+    FP_max: np.ndarray = field(default_factory=lambda: np.zeros(9))
+    isNBC: np.ndarray = field(default_factory=lambda: np.zeros(9, dtype=np.int32))
+    mults: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    tolNR: float = 1.0e-5
+    tolPCG: float = 1.0e-10
+    maxIter: int = 10
+    tstep: float = 1.0
+
+    @property
+    def N3(self) -> int:
+        return self.N ** 3
+
+    @property
+    def nstep(self) -> int:
+        return len(self.mults)
+
+    def BC_all(self) -> np.ndarray:
+        """Cumulative load table (inlod.f:57-63), shape (nstep, 9)."""
+        bc = np.cumsum(np.outer(self.mults, self.FP_max), axis=0)
+        for d in (0, 4, 8):
+            if not self.isNBC[d]:
+                bc[:, d] += 1.0
+        return np.ascontiguousarray(bc)
+
+    def material_pods(self):
+        arr = (MaterialPOD * len(self.materials))()
+        for i, m in enumerate(self.materials):
+            arr[i] = m.pod()
+        return arr
+
+    def crystal_pods(self):
+        n = max(1, len(self.crystals))
+        arr = (CrystalPOD * n)()
+        for i, c in enumerate(self.crystals):
+            arr[i] = c.pod()
+        return arr

@@ -1,0 +1,220 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.h).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def oracle_lib_path() -> str:
+    return os.path.join(_HERE, "build", "liboracle_cpfft.so")
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile the C++ restatement with the Makefile next to this file."""
+    path = oracle_lib_path()
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".h", ".inc"))]
+    stale = (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return path
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = oracle_lib_path()
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, ip, dp]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_hist_size.argtypes = [C.c_void_p]
+        for name in ("Fn", "Fn1", "Pn", "Pn1", "K4", "dFm", "b", "hist_n", "hist_n1", "urcs_n",
+                     "urcs_n1", "eps_n", "eps_n1", "rot_n1"):
+            f = getattr(L, "orc_" + name)
+            f.restype = dp
+            f.argtypes = [C.c_void_p]
+        L.orc_fail_flags.restype = ip
+        L.orc_fail_flags.argtypes = [C.c_void_p]
+        L.orc_local_iters.restype = ip
+        L.orc_local_iters.argtypes = [C.c_void_p]
+        L.orc_drive_eps_sig.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_G_K_dF.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_fftPcg.argtypes = [C.c_void_p, dp, dp, C.c_double, ip, dp]
+        L.orc_tangent_homo.argtypes = [C.c_void_p, dp]
+        L.orc_update.argtypes = [C.c_void_p]
+        L.orc_mean_P.argtypes = [C.c_void_p, dp]
+        L.orc_FFT_nr3.argtypes = [C.c_void_p, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp,
+                                  C.POINTER(C.c_int64)]
+        L.orc_rtcmp1.argtypes = [dp, dp]
+        L.orc_cep2A.argtypes = [dp, dp, dp, dp, dp]
+        L.orc_point_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
+        L.orc_formG_entry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_crystal_stiffness.argtypes = [C.c_void_p, dp]
+        L.orc_slip_table.argtypes = [C.c_int, ip, dp, dp]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Oracle:
+    """CPU restatement of the reference hot path for one ``Problem`` (cpfft_b200.problem)."""
+
+    CG_CAP = 64
+
+    def __init__(self, prob, threads: int = 0):
+        L = _lib()
+        self.L, self.prob = L, prob
+        if threads:
+            L.orc_set_threads(threads)
+        mats, crys = prob.material_pods(), prob.crystal_pods()
+        ml = np.ascontiguousarray(prob.matlist, dtype=np.int32)
+        ang = np.ascontiguousarray(prob.angles, dtype=np.float64)
+        self.h = L.orc_create(prob.N, len(prob.materials), C.addressof(mats), len(prob.crystals),
+                              C.addressof(crys), _ip(ml), _dp(ang))
+        L.orc_set_params(self.h, prob.tolNR, prob.tolPCG, prob.maxIter, prob.tstep)
+        self.N, self.N3 = prob.N, prob.N3
+        self.H = L.orc_hist_size(self.h)
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def _view(self, name, shape):
+        ptr = getattr(self.L, "orc_" + name)(self.h)
+        return np.ctypeslib.as_array(ptr, shape=shape)
+
+    # SoA fields: (ncomp, N3) views of the reference's column-major (N3, ncomp) arrays
+    @property
+    def Fn(self): return self._view("Fn", (9, self.N3))
+    @property
+    def Fn1(self): return self._view("Fn1", (9, self.N3))
+    @property
+    def Pn1(self): return self._view("Pn1", (9, self.N3))
+    @property
+    def K4(self): return self._view("K4", (81, self.N3))
+    @property
+    def dFm(self): return self._view("dFm", (9, self.N3))
+    @property
+    def hist_n(self): return self._view("hist_n", (self.N3, self.H))
+    @property
+    def hist_n1(self): return self._view("hist_n1", (self.N3, self.H))
+    @property
+    def urcs_n(self): return self._view("urcs_n", (self.N3, 9))
+    @property
+    def urcs_n1(self): return self._view("urcs_n1", (self.N3, 9))
+    @property
+    def eps_n1(self): return self._view("eps_n1", (self.N3, 6))
+    @property
+    def rot_n1(self): return self._view("rot_n1", (self.N3, 9))
+    @property
+    def local_iters(self):
+        return np.ctypeslib.as_array(self.L.orc_local_iters(self.h), shape=(self.N3, 2))
+
+    def drive_eps_sig(self, step, it):
+        return self.L.orc_drive_eps_sig(self.h, step, it)
+
+    def G_K_dF(self, F, flgK):
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        out = np.empty_like(F)
+        self.L.orc_G_K_dF(self.h, _dp(F), _dp(out), int(bool(flgK)))
+        return out
+
+    def fftPcg(self, b, tol):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros_like(b)
+        it = C.c_int32(0)
+        rr = C.c_double(0)
+        rc = self.L.orc_fftPcg(self.h, _dp(b), _dp(x), tol, C.byref(it), C.byref(rr))
+        return rc, x, it.value, rr.value
+
+    def tangent_homo(self):
+        Ch = np.zeros(81)
+        rc = self.L.orc_tangent_homo(self.h, _dp(Ch))
+        return rc, Ch
+
+    def update(self):
+        self.L.orc_update(self.h)
+
+    def mean_P(self):
+        p = np.zeros(9)
+        self.L.orc_mean_P(self.h, _dp(p))
+        return p
+
+    def FFT_nr3(self, nstep=None):
+        prob = self.prob
+        bc = prob.BC_all()
+        nstep = prob.nstep if nstep is None else nstep
+        bc = np.ascontiguousarray(bc[:nstep])
+        nbc = np.ascontiguousarray(prob.isNBC, dtype=np.int32)
+        nr = np.zeros(nstep, dtype=np.int32)
+        cg = np.full((nstep, self.CG_CAP), -1, dtype=np.int32)
+        pbar = np.zeros((nstep, 9))
+        buckets = np.zeros(3)
+        counters = np.zeros(3, dtype=np.int64)
+        rc = self.L.orc_FFT_nr3(self.h, nstep, _dp(bc), _ip(nbc), _ip(nr), _ip(cg), self.CG_CAP,
+                                _dp(pbar), _dp(buckets), counters.ctypes.data_as(C.POINTER(C.c_int64)))
+        cg_lists = [list(row[:list(row).index(-1)]) if -1 in row else list(row) for row in cg]
+        return dict(rc=rc, nr_iters=nr, cg_iters=cg_lists, Pbar=pbar, buckets=buckets,
+                    counters=counters)
+
+    # unit probes
+    @staticmethod
+    def rtcmp1(F):
+        F = np.ascontiguousarray(F, dtype=np.float64).reshape(9)
+        R = np.zeros(9)
+        _lib().orc_rtcmp1(_dp(F), _dp(R))
+        return R.reshape(3, 3)
+
+    @staticmethod
+    def cep2A(Fn, Fn1, t6, cep):
+        a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (Fn, Fn1, t6)]
+        c = np.asfortranarray(cep, dtype=np.float64).ravel(order="F").copy()
+        A = np.zeros(81)
+        _lib().orc_cep2A(_dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(c), _dp(A))
+        return A
+
+    def point_update(self, voxel, step, it, Fn, Fn1):
+        a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (Fn, Fn1)]
+        P, A = np.zeros(9), np.zeros(81)
+        self.L.orc_point_update(self.h, voxel, step, it, _dp(a[0]), _dp(a[1]), _dp(P), _dp(A))
+        return P, A
+
+    @staticmethod
+    def formG_entry(N, i, j, k):
+        G = np.zeros(81)
+        _lib().orc_formG_entry(N, i, j, k, _dp(G))
+        return G
+
+    @staticmethod
+    def crystal_stiffness(crystal):
+        pod = crystal.pod()
+        Cm = np.zeros(36)
+        _lib().orc_crystal_stiffness(C.addressof(pod), _dp(Cm))
+        return Cm.reshape(6, 6, order="F")
+
+    @staticmethod
+    def slip_table(slip_type):
+        n = C.c_int32(0)
+        b, nn = np.zeros(48 * 3), np.zeros(48 * 3)
+        _lib().orc_slip_table(slip_type, C.byref(n), _dp(b), _dp(nn))
+        return b[:3 * n.value].reshape(-1, 3), nn[:3 * n.value].reshape(-1, 3)
