@@ -1,0 +1,104 @@
+// cpfft_b200: shared declarations for the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/cpfft_b200.h"
+
+#define CPF_MAX_SLIP 48
+
+#define CPF_CUDA(call)                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      cpf_set_error(h, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+      return CPFFT_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+// mm10 history layout (offsets, 0-based) -- mm10_d.f:137-331
+struct CpfHistLayout {
+  int use_max, nslip, num_hard;
+  int cep, gradfe, R, work, slipsum;
+  int c_stress, c_euler, c_Rp, c_D, c_eps, c_slipinc, c_tt, c_u, c_ttrate, c_ep, c_ed;
+  int len_u, len_slip, total;
+};
+
+// per-material constants in device memory
+struct CpfMatDev {
+  int type, crystal;        // crystal: 0-based index into crystal table
+  double ym, nu, beta, tan_e, yld, hprime;  // mm01 (REAL*4 promoted, drive_eps_sig.f:486-521)
+};
+
+// per-crystal constants (Voce), device
+struct CpfCryDev {
+  int nslip, alter_mode, miter, rate_int;   // rate_int: harden_n-1 if small integer else -1
+  double rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, eps_dot_0_y, k_0, burgers;
+  double atol, atol1, rtol, rtol1;
+};
+
+// per-grain (unique crystal+orientation) table entry, device, doubles:
+//   [0..8] g (row-major), [9..44] rotated stiffness C (row-major 6x6),
+//   [45 + 9 s ..): ms0[6] (engineering-shear Schmid vector), qs0[3] (skew vector) of system s
+#define CPF_GRAIN_G 0
+#define CPF_GRAIN_C 9
+#define CPF_GRAIN_B 45
+#define CPF_GRAIN_STRIDE (45 + 9 * CPF_MAX_SLIP)
+
+struct cpfft_handle {
+  cpfft_config cfg;
+  int N, Nh;                 // Nh = N/2+1 (half spectrum along z)
+  int nxloc, x0;             // local slab
+  int64_t n3;                // local voxels
+  int H;                     // history comps
+  cudaStream_t stream;
+  std::string err;
+  int64_t launches;
+  // fields
+  double* field[CPFFT_NUM_FIELDS];
+  int ncomp[CPFFT_NUM_FIELDS];
+  // model
+  std::vector<cpfft_material> mats;
+  std::vector<cpfft_crystal> crys;
+  CpfMatDev* d_mats; CpfCryDev* d_crys;
+  int32_t* d_matidx;         // per voxel 0-based material
+  int32_t* d_grain;          // per voxel grain index
+  double* d_grains;          // grain table
+  int ngrains;
+  bool has_mm01, has_mm10;
+  CpfHistLayout L;
+  int32_t* d_fail; int32_t* d_liters;
+  // spectral work
+  double2* spec_a; double2* spec_b;      // half-spectrum buffers [9][nx][N][Nh]
+  double2* tw;                           // twiddles exp(-2 pi i k / N)
+  int radices[32]; int nrad;
+  int* d_radices;
+  double* work9;                         // 9*n3 scratch (K4:x)
+  // reductions
+  double* d_partials; double* d_scalars; double* h_scalars; int nblocks_red;
+  // step-loop state (FFT_nr3 locals that persist between calls)
+  double barF[9], barF_t[9], P_bar[9], C_homo[81];
+  bool have_chomo;
+  int next_step;
+  // stats
+  double t_pcg, t_sig; int64_t n_apply, n_sweep, n_cg;
+  // nccl
+  void* nccl_comm; void* nccl_lib;
+  double2* xchg_send; double2* xchg_recv;
+};
+
+void cpf_set_error(cpfft_handle* h, const std::string& s);
+
+// material.cu
+int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* angles);
+int cpf_launch_update(cpfft_handle* h, int step, int iter);
+CpfHistLayout cpf_hist_layout(int nslip, int num_hard);
+
+// spectral.cu
+int cpf_spectral_init(cpfft_handle* h);
+void cpf_spectral_free(cpfft_handle* h);
+int cpf_apply_G(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out);
+
+// reduce.cu helpers (solver.cu)
+int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out);

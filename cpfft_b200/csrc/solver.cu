@@ -1,0 +1,643 @@
+// cpfft_b200: handle life cycle, BLAS-1 style field kernels, conjugate gradients (fftPcg),
+// the Newton / stress-BC step loop (FFT_nr3), tangent_homo and the C ABI (include/cpfft_b200.h).
+#include "common.cuh"
+#include <dlfcn.h>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+static double wall_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void cpf_set_error(cpfft_handle* h, const std::string& s) { if (h) h->err = s; }
+
+// ------------------------------------------------------------------------------------------
+// field kernels (grid-stride, coalesced, grid = multiple of the SM count)
+#define VEC_THREADS 256
+static int g_num_sms = 148;
+static inline int vec_grid(int64_t n) {
+  int64_t b = (n + VEC_THREADS - 1) / VEC_THREADS;
+  int64_t cap = (int64_t)g_num_sms * 8;
+  return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+
+__global__ void k_fill9(double* y, int64_t n3, double c0, double c1, double c2, double c3, double c4, double c5,
+                        double c6, double c7, double c8) {
+  const double cv[9] = {c0, c1, c2, c3, c4, c5, c6, c7, c8};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 9 * n3; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = cv[i / n3];
+}
+__global__ void k_axpy(double* y, const double* x, double a, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+__global__ void k_xpby(double* p, const double* r, double beta, int64_t n) {  // p = r + beta p
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = r[i] + beta * p[i];
+}
+__global__ void k_add_diag(double* y, int64_t n3, int comp) {  // y(:,comp) += 1
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x)
+    y[comp * n3 + i] += 1.0;
+}
+__global__ void k_gather_k4_col(double* dst, const double* K4, int64_t n3, int col) {  // dst(:,j) = K4(:,9j+col)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 9 * n3; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / n3, e = i - j * n3;
+    dst[i] = K4[(9 * j + col) * n3 + e];
+  }
+}
+
+// deterministic two-stage reductions: per-block partials in a fixed order, then one block
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+__global__ void k_dot_partial(const double* x, const double* y, int64_t n, double* partials) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += x[i] * y[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// x += a p ; r -= a q ; partial of r.r
+__global__ void k_cg_update(double* x, double* r, const double* p, const double* q, double a, int64_t n, double* partials) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += a * p[i];
+    const double rv = r[i] - a * q[i];
+    r[i] = rv;
+    s += rv * rv;
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void k_sum_comp_partial(const double* x, int64_t n3, double* partials) {  // blockIdx.y = component
+  double s = 0.0;
+  const double* xc = x + blockIdx.y * n3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) s += xc[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+__global__ void k_final_sum(const double* partials, int nb, double* out) {  // blockIdx.x = slot
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partials[blockIdx.x * nb + i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+__global__ void k_or_flags(const int32_t* f, int64_t n, int* out) {
+  int v = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v |= f[i];
+  if (__syncthreads_or(v) && threadIdx.x == 0) atomicOr(out, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (the library is only needed for world > 1)
+typedef struct { char internal[128]; } cpf_ncclUniqueId;
+typedef void* cpf_ncclComm_t;
+struct NcclApi {
+  int (*GetUniqueId)(cpf_ncclUniqueId*);
+  int (*CommInitRank)(cpf_ncclComm_t*, int, cpf_ncclUniqueId, int);
+  int (*CommDestroy)(cpf_ncclComm_t);
+  int (*AllReduce)(const void*, void*, size_t, int, int, cpf_ncclComm_t, cudaStream_t);
+  int (*Send)(const void*, size_t, int, int, cpf_ncclComm_t, cudaStream_t);
+  int (*Recv)(void*, size_t, int, int, cpf_ncclComm_t, cudaStream_t);
+  int (*GroupStart)(); int (*GroupEnd)();
+  const char* (*GetErrorString)(int);
+  void* lib;
+};
+static NcclApi g_nccl = {};
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return 1;
+#define LD(name) *(void**)(&g_nccl.name) = dlsym(lib, "nccl" #name); if (!g_nccl.name) return 1;
+  LD(GetUniqueId) LD(CommInitRank) LD(CommDestroy) LD(AllReduce) LD(Send) LD(Recv) LD(GroupStart) LD(GroupEnd) LD(GetErrorString)
+#undef LD
+  g_nccl.lib = lib;
+  return 0;
+}
+#define CPF_NCCL(call)                                                                    \
+  do {                                                                                    \
+    int r_ = (call);                                                                      \
+    if (r_ != 0) { cpf_set_error(h, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); return CPFFT_ERR_NCCL; } \
+  } while (0)
+
+// slab <-> pencil transposes of the half spectrum (2 per G_K_dF application)
+__global__ void k_pack_fwd(const double2* a, double2* out, int P, int nx, int N, int Nh) {
+  const int ny = N / P;
+  const int64_t total = (int64_t)9 * nx * N * Nh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int kz = t % Nh; t /= Nh;
+    const int yl = t % ny; t /= ny;
+    const int xl = t % nx; t /= nx;
+    const int c = t % 9; const int p = (int)(t / 9);
+    out[i] = a[(((int64_t)c * nx + xl) * N + (p * ny + yl)) * Nh + kz];
+  }
+}
+__global__ void k_unpack_fwd(const double2* in, double2* b, int P, int nx, int N, int Nh) {
+  const int ny = N / P;
+  const int64_t total = (int64_t)9 * nx * N * Nh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int kz = t % Nh; t /= Nh;
+    const int yl = t % ny; t /= ny;
+    const int xl = t % nx; t /= nx;
+    const int c = t % 9; const int p = (int)(t / 9);
+    b[(((int64_t)c * N + (p * nx + xl)) * ny + yl) * Nh + kz] = in[i];
+  }
+}
+__global__ void k_pack_bwd(const double2* b, double2* out, int P, int nx, int N, int Nh) {
+  const int ny = N / P;
+  const int64_t total = (int64_t)9 * nx * N * Nh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int kz = t % Nh; t /= Nh;
+    const int yl = t % ny; t /= ny;
+    const int xl = t % nx; t /= nx;
+    const int c = t % 9; const int p = (int)(t / 9);
+    out[i] = b[(((int64_t)c * N + (p * nx + xl)) * ny + yl) * Nh + kz];
+  }
+}
+__global__ void k_unpack_bwd(const double2* in, double2* a, int P, int nx, int N, int Nh) {
+  const int ny = N / P;
+  const int64_t total = (int64_t)9 * nx * N * Nh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int kz = t % Nh; t /= Nh;
+    const int yl = t % ny; t /= ny;
+    const int xl = t % nx; t /= nx;
+    const int c = t % 9; const int p = (int)(t / 9);
+    a[(((int64_t)c * nx + xl) * N + (p * ny + yl)) * Nh + kz] = in[i];
+  }
+}
+static int all_to_all(cpfft_handle* h) {
+  const int P = h->cfg.world;
+  const size_t per_peer = (size_t)9 * h->nxloc * (h->N / P) * h->Nh * 2;  // doubles
+  CPF_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < P; ++p) {
+    CPF_NCCL(g_nccl.Send((const double*)h->xchg_send + p * per_peer, per_peer, 8, p, h->nccl_comm, h->stream));
+    CPF_NCCL(g_nccl.Recv((double*)h->xchg_recv + p * per_peer, per_peer, 8, p, h->nccl_comm, h->stream));
+  }
+  CPF_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+int cpf_exchange_fwd(cpfft_handle* h) {
+  const int64_t total = (int64_t)9 * h->nxloc * h->N * h->Nh;
+  k_pack_fwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->spec_a, h->xchg_send, h->cfg.world, h->nxloc, h->N, h->Nh);
+  int rc = all_to_all(h); if (rc) return rc;
+  k_unpack_fwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->xchg_recv, h->spec_b, h->cfg.world, h->nxloc, h->N, h->Nh);
+  h->launches += 2;
+  return 0;
+}
+int cpf_exchange_bwd(cpfft_handle* h) {
+  const int64_t total = (int64_t)9 * h->nxloc * h->N * h->Nh;
+  k_pack_bwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->spec_b, h->xchg_send, h->cfg.world, h->nxloc, h->N, h->Nh);
+  int rc = all_to_all(h); if (rc) return rc;
+  k_unpack_bwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->xchg_recv, h->spec_a, h->cfg.world, h->nxloc, h->N, h->Nh);
+  h->launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar read-back of `cnt` reduction slots (all-reduced over ranks when world > 1)
+static int fetch_scalars(cpfft_handle* h, int cnt, double* out) {
+  if (h->cfg.world > 1)
+    CPF_NCCL(g_nccl.AllReduce(h->d_scalars, h->d_scalars, cnt, 8, 0, h->nccl_comm, h->stream));
+  CPF_CUDA(cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < cnt; ++i) out[i] = h->h_scalars[i];
+  return 0;
+}
+int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out) {
+  const int nb = h->nblocks_red;
+  k_dot_partial<<<nb, VEC_THREADS, 0, h->stream>>>(x, y, n, h->d_partials);
+  k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, nb, h->d_scalars);
+  h->launches += 2;
+  return fetch_scalars(h, 1, out);
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
+  if (!cfg || !out) return CPFFT_ERR_USAGE;
+  *out = nullptr;
+  cpfft_handle* h = new cpfft_handle();
+  h->cfg = *cfg;
+  if (h->cfg.world < 1) h->cfg.world = 1;
+  h->N = cfg->N; h->Nh = cfg->N / 2 + 1;
+  h->err.clear(); h->launches = 0;
+  for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) { h->field[f] = nullptr; h->ncomp[f] = 0; }
+  h->d_mats = nullptr; h->d_crys = nullptr; h->d_matidx = nullptr; h->d_grain = nullptr; h->d_grains = nullptr;
+  h->d_fail = nullptr; h->d_liters = nullptr; h->spec_a = h->spec_b = nullptr; h->tw = nullptr; h->d_radices = nullptr;
+  h->work9 = nullptr; h->d_partials = nullptr; h->d_scalars = nullptr; h->h_scalars = nullptr;
+  h->nccl_comm = nullptr; h->nccl_lib = nullptr; h->xchg_send = h->xchg_recv = nullptr;
+  h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr;
+  *out = h;  // returned even on failure so that cpfft_last_error works; caller destroys it
+  if (cfg->N < 2) { cpf_set_error(h, "N must be >= 2"); return CPFFT_ERR_USAGE; }
+  if (h->cfg.world > 1 && (cfg->N % h->cfg.world) != 0) {
+    cpf_set_error(h, "slab decomposition needs N divisible by world"); return CPFFT_ERR_USAGE;
+  }
+  CPF_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CPF_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  g_num_sms = prop.multiProcessorCount;
+  CPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->nxloc = cfg->N / h->cfg.world; h->x0 = h->cfg.rank * h->nxloc;
+  h->n3 = (int64_t)h->nxloc * cfg->N * cfg->N;
+  const int nc[CPFFT_NUM_FIELDS] = {9, 9, 9, 9, 9, 9, 9, 9, 9, 81, 9, 9, 6, 6, 9, 0, 0, 36};
+  for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) {
+    h->ncomp[f] = nc[f];
+    if (nc[f] == 0) continue;
+    CPF_CUDA(cudaMalloc(&h->field[f], sizeof(double) * (size_t)nc[f] * h->n3));
+    CPF_CUDA(cudaMemsetAsync(h->field[f], 0, sizeof(double) * (size_t)nc[f] * h->n3, h->stream));
+  }
+  CPF_CUDA(cudaMalloc(&h->work9, sizeof(double) * 9 * h->n3));
+  CPF_CUDA(cudaMalloc(&h->d_fail, sizeof(int32_t) * h->n3));
+  CPF_CUDA(cudaMalloc(&h->d_liters, sizeof(int32_t) * 2 * h->n3));
+  CPF_CUDA(cudaMemsetAsync(h->d_fail, 0, sizeof(int32_t) * h->n3, h->stream));
+  CPF_CUDA(cudaMemsetAsync(h->d_liters, 0, sizeof(int32_t) * 2 * h->n3, h->stream));
+  h->nblocks_red = g_num_sms * 8;
+  CPF_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * 16 * h->nblocks_red));
+  CPF_CUDA(cudaMalloc(&h->d_scalars, sizeof(double) * 128));
+  CPF_CUDA(cudaMallocHost(&h->h_scalars, sizeof(double) * 128));
+  // Fn = Fn1 = I (FFT_init.f:157-161)
+  k_fill9<<<vec_grid(9 * h->n3), VEC_THREADS, 0, h->stream>>>(h->field[CPFFT_FN], h->n3, 1, 0, 0, 0, 1, 0, 0, 0, 1);
+  k_fill9<<<vec_grid(9 * h->n3), VEC_THREADS, 0, h->stream>>>(h->field[CPFFT_FN1], h->n3, 1, 0, 0, 0, 1, 0, 0, 0, 1);
+  int rc = cpf_spectral_init(h);
+  if (rc) return rc;
+  for (int i = 0; i < 9; ++i) { h->barF[i] = h->barF_t[i] = (i % 4 == 0) ? 1.0 : 0.0; h->P_bar[i] = 0.0; }
+  h->have_chomo = false; h->next_step = 1;
+  h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0;
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void cpfft_destroy(cpfft_handle* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) if (h->field[f]) cudaFree(h->field[f]);
+  void* ptrs[] = {h->d_mats, h->d_crys, h->d_matidx, h->d_grain, h->d_grains, h->d_fail, h->d_liters, h->work9,
+                  h->d_partials, h->d_scalars, h->xchg_send, h->xchg_recv};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  cpf_spectral_free(h);
+  if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* cpfft_last_error(const cpfft_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int cpfft_set_materials(cpfft_handle* h, int nmat, const cpfft_material* mats, int ncry, const cpfft_crystal* crys) {
+  if (!h || nmat < 1 || !mats) return CPFFT_ERR_USAGE;
+  h->mats.assign(mats, mats + nmat);
+  h->crys.assign(crys, crys + (crys ? ncry : 0));
+  return 0;
+}
+int cpfft_set_voxels(cpfft_handle* h, const int32_t* matlist, const double* angles) {
+  if (!h || !matlist || h->mats.empty()) { cpf_set_error(h, "set_materials must precede set_voxels"); return CPFFT_ERR_USAGE; }
+  std::vector<double> zeros;
+  if (!angles) { zeros.assign((size_t)3 * h->n3, 0.0); angles = zeros.data(); }
+  int rc = cpf_material_setup(h, matlist, angles);
+  if (rc) return rc;
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int cpfft_set_params(cpfft_handle* h, double tolNR, double tolPCG, int maxIter, double tstep) {
+  if (!h) return CPFFT_ERR_USAGE;
+  h->cfg.tolNR = tolNR; h->cfg.tolPCG = tolPCG; h->cfg.maxIter = maxIter; h->cfg.tstep = tstep;
+  return 0;
+}
+int cpfft_hist_size(const cpfft_handle* h) { return h ? h->H : 0; }
+int64_t cpfft_local_voxels(const cpfft_handle* h) { return h ? h->n3 : 0; }
+int cpfft_field_ncomp(const cpfft_handle* h, cpfft_field f) { return (h && f >= 0 && f < CPFFT_NUM_FIELDS) ? h->ncomp[f] : 0; }
+
+int cpfft_upload(cpfft_handle* h, cpfft_field f, const double* host, cpfft_layout layout) {
+  if (!h || f < 0 || f >= CPFFT_NUM_FIELDS || !h->field[f]) return CPFFT_ERR_USAGE;
+  const int nc = h->ncomp[f]; const int64_t n3 = h->n3;
+  if (layout == CPFFT_LAYOUT_SOA) {
+    CPF_CUDA(cudaMemcpyAsync(h->field[f], host, sizeof(double) * nc * n3, cudaMemcpyHostToDevice, h->stream));
+    CPF_CUDA(cudaStreamSynchronize(h->stream));
+  } else {
+    std::vector<double> t((size_t)nc * n3);
+    for (int64_t e = 0; e < n3; ++e) for (int c = 0; c < nc; ++c) t[(size_t)c * n3 + e] = host[(size_t)e * nc + c];
+    CPF_CUDA(cudaMemcpy(h->field[f], t.data(), sizeof(double) * nc * n3, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+int cpfft_download(cpfft_handle* h, cpfft_field f, double* host, cpfft_layout layout) {
+  if (!h || f < 0 || f >= CPFFT_NUM_FIELDS || !h->field[f]) return CPFFT_ERR_USAGE;
+  const int nc = h->ncomp[f]; const int64_t n3 = h->n3;
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  if (layout == CPFFT_LAYOUT_SOA) {
+    CPF_CUDA(cudaMemcpy(host, h->field[f], sizeof(double) * nc * n3, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<double> t((size_t)nc * n3);
+    CPF_CUDA(cudaMemcpy(t.data(), h->field[f], sizeof(double) * nc * n3, cudaMemcpyDeviceToHost));
+    for (int64_t e = 0; e < n3; ++e) for (int c = 0; c < nc; ++c) host[(size_t)e * nc + c] = t[(size_t)c * n3 + e];
+  }
+  return 0;
+}
+int cpfft_download_fail_flags(cpfft_handle* h, int32_t* flags) {
+  if (!h) return CPFFT_ERR_USAGE;
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  CPF_CUDA(cudaMemcpy(flags, h->d_fail, sizeof(int32_t) * h->n3, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int cpfft_download_local_iters(cpfft_handle* h, int32_t* it) {
+  if (!h) return CPFFT_ERR_USAGE;
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  CPF_CUDA(cudaMemcpy(it, h->d_liters, sizeof(int32_t) * 2 * h->n3, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cpfft_synchronize(cpfft_handle* h) { if (!h) return CPFFT_ERR_USAGE; CPF_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
+void* cpfft_stream(cpfft_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t cpfft_kernel_launches(const cpfft_handle* h) { return h ? h->launches : 0; }
+
+// ---- drive_eps_sig ----
+int cpfft_drive_eps_sig(cpfft_handle* h, int step, int iter) {
+  if (!h || !h->d_matidx) { cpf_set_error(h, "model not set"); return CPFFT_ERR_USAGE; }
+  const double t0 = wall_s();
+  int rc = cpf_launch_update(h, step, iter);
+  if (rc) return rc;
+  h->n_sweep++;
+  if (h->has_mm10) {  // material_cut_step -> fatal (mm10_a.f:2811)
+    int* flag = (int*)(h->d_scalars + 64);
+    CPF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    k_or_flags<<<vec_grid(h->n3), VEC_THREADS, 0, h->stream>>>(h->d_fail, h->n3, flag);
+    h->launches++;
+    int hf = 0;
+    CPF_CUDA(cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CPF_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->cfg.world > 1) {
+      // every rank must agree
+      double v = hf;
+      CPF_CUDA(cudaMemcpyAsync(h->d_scalars, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      double o; int r2 = 0;
+      { if (h->cfg.world > 1) { r2 = g_nccl.AllReduce(h->d_scalars, h->d_scalars, 1, 8, 0, h->nccl_comm, h->stream); } }
+      if (r2) { cpf_set_error(h, "ncclAllReduce failed"); return CPFFT_ERR_NCCL; }
+      CPF_CUDA(cudaMemcpyAsync(&o, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CPF_CUDA(cudaStreamSynchronize(h->stream));
+      hf = (o != 0.0);
+    }
+    h->t_sig += wall_s() - t0;
+    if (hf) { cpf_set_error(h, ">>> Warning: mm10 implicit solution failed."); return CPFFT_ERR_MATERIAL; }
+  } else {
+    CPF_CUDA(cudaStreamSynchronize(h->stream));
+    h->t_sig += wall_s() - t0;
+  }
+  return 0;
+}
+
+// ---- G_K_dF ----
+int cpfft_G_K_dF(cpfft_handle* h, cpfft_field src, cpfft_field dst, int flgK) {
+  if (!h || src < 0 || dst < 0 || src >= CPFFT_NUM_FIELDS || dst >= CPFFT_NUM_FIELDS || h->ncomp[src] != 9 ||
+      h->ncomp[dst] != 9) { cpf_set_error(h, "G_K_dF needs 9-component fields"); return CPFFT_ERR_USAGE; }
+  return cpf_apply_G(h, h->field[src], h->field[dst], flgK != 0, 1.0);
+}
+
+// ---- fftPcg (FFT_nr3.f:214-360) on device vectors; x and b are 9*n3 device pointers ----
+static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int* iters, double* relres) {
+  const double t0 = wall_s();
+  const int64_t n = 9 * h->n3;
+  const double eps = 2.220446049250313e-16;
+  const int maxIter = 1000;
+  double* p = h->field[CPFFT_CG_P]; double* q = h->field[CPFFT_CG_AP]; double* r = h->field[CPFFT_CG_R];
+  CPF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
+  if (iters) *iters = 0;
+  if (relres) *relres = 0.0;
+  double rr;
+  int rc = cpf_dot(h, b, b, n, &rr); if (rc) return rc;
+  const double n2b = sqrt(rr), tolb = tol * n2b;
+  if (tol <= eps || tol >= 1.0) { cpf_set_error(h, ">>> pcg: improper tolerance"); return CPFFT_ERR_TOL; }
+  if (n2b <= eps) { h->t_pcg += wall_s() - t0; return 0; }
+  CPF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+  double rr_old = 0.0, resnorm = n2b;
+  int it = 0;
+  for (;;) {
+    resnorm = sqrt(rr);
+    if (resnorm <= tolb || resnorm <= tol) break;
+    if (it >= maxIter) { cpf_set_error(h, ">>>fftPcg: fail to converge within 1000 iterations"); return CPFFT_ERR_CG; }
+    if (it == 0) CPF_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    else { k_xpby<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(p, r, rr / rr_old, n); h->launches++; }
+    rc = cpf_apply_G(h, p, q, true, 1.0); if (rc) return rc;
+    double pq;
+    rc = cpf_dot(h, p, q, n, &pq); if (rc) return rc;
+    const double alpha = rr / pq;
+    k_cg_update<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(x, r, p, q, alpha, n, h->d_partials);
+    k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, h->nblocks_red, h->d_scalars);
+    h->launches += 2;
+    rr_old = rr;
+    rc = fetch_scalars(h, 1, &rr); if (rc) return rc;
+    ++it;
+  }
+  if (iters) *iters = it;
+  if (relres) *relres = resnorm / n2b;
+  h->n_cg += it;
+  h->t_pcg += wall_s() - t0;
+  return 0;
+}
+
+int cpfft_fftPcg(cpfft_handle* h, cpfft_field b, cpfft_field x, double tol, int* iters, double* relres) {
+  if (!h || h->ncomp[b] != 9 || h->ncomp[x] != 9 || b == x) { cpf_set_error(h, "fftPcg needs two distinct 9-component fields"); return CPFFT_ERR_USAGE; }
+  if (b == CPFFT_CG_P || b == CPFFT_CG_AP || b == CPFFT_CG_R || x == CPFFT_CG_P || x == CPFFT_CG_AP || x == CPFFT_CG_R) {
+    cpf_set_error(h, "CG work fields cannot be operands"); return CPFFT_ERR_USAGE;
+  }
+  return pcg_dev(h, h->field[b], h->field[x], tol, iters, relres);
+}
+
+int cpfft_mean_P(cpfft_handle* h, double Pbar[9]) {
+  if (!h) return CPFFT_ERR_USAGE;
+  const int nb = h->nblocks_red;
+  dim3 g(nb, 9);
+  k_sum_comp_partial<<<g, VEC_THREADS, 0, h->stream>>>(h->field[CPFFT_PN1], h->n3, h->d_partials);
+  k_final_sum<<<9, VEC_THREADS, 0, h->stream>>>(h->d_partials, nb, h->d_scalars);
+  h->launches += 2;
+  double s[9];
+  int rc = fetch_scalars(h, 9, s); if (rc) return rc;
+  const double n3g = (double)h->N * (double)h->N * (double)h->N;
+  for (int i = 0; i < 9; ++i) Pbar[i] = s[i] / n3g;
+  return 0;
+}
+
+// ---- tangent_homo (tangent_homo.f:11-73) ----
+int cpfft_tangent_homo(cpfft_handle* h, double C_homo[81]) {
+  if (!h) return CPFFT_ERR_USAGE;
+  const int64_t n3 = h->n3, n = 9 * n3;
+  double* Cij = h->work9; double* b = h->field[CPFFT_B];
+  const double n3g = (double)h->N * (double)h->N * (double)h->N;
+  for (int i = 0; i < 9; ++i) {
+    k_gather_k4_col<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(Cij, h->field[CPFFT_K4], n3, i);
+    h->launches++;
+    int rc = cpf_apply_G(h, Cij, b, false, -1.0); if (rc) return rc;
+    int it;
+    rc = pcg_dev(h, b, Cij, h->cfg.tolPCG, &it, nullptr); if (rc) return rc;
+    k_add_diag<<<vec_grid(n3), VEC_THREADS, 0, h->stream>>>(Cij, n3, i);
+    h->launches++;
+    for (int j = 0; j < 9; ++j) {
+      double v;
+      rc = cpf_dot(h, h->field[CPFFT_K4] + (int64_t)(9 * j) * n3, Cij, n, &v); if (rc) return rc;
+      C_homo[9 * j + i] = v / n3g;
+    }
+  }
+  return 0;
+}
+
+int cpfft_update(cpfft_handle* h) {  // update.f:75-106 + FFT_nr3.f:174-175
+  if (!h) return CPFFT_ERR_USAGE;
+  const int64_t n3 = h->n3;
+  const int pairs[5][2] = {{CPFFT_FN, CPFFT_FN1}, {CPFFT_PN, CPFFT_PN1}, {CPFFT_HIST_N, CPFFT_HIST_N1},
+                           {CPFFT_EPS_N, CPFFT_EPS_N1}, {CPFFT_URCS_N, CPFFT_URCS_N1}};
+  for (auto& pr : pairs)
+    if (h->field[pr[0]])
+      CPF_CUDA(cudaMemcpyAsync(h->field[pr[0]], h->field[pr[1]], sizeof(double) * h->ncomp[pr[0]] * n3,
+                               cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+// NBC_update (FFT_nr3.f:375-433), host, 9x9
+static int nbc_update(const double* C_homo, double* DbarF, const double* P_bar, const double* PBC, const int32_t* isNBC) {
+  double A[81], bb[9];
+  for (int i = 0; i < 9; ++i) {
+    if (isNBC[i]) { for (int m = 0; m < 9; ++m) A[i * 9 + m] = C_homo[m + 9 * i]; bb[i] = PBC[i] - P_bar[i]; }
+    else { for (int m = 0; m < 9; ++m) A[i * 9 + m] = 0.0; A[i * 9 + i] = 1.0; bb[i] = DbarF[i]; }
+  }
+  for (int k = 0; k < 9; ++k) {
+    int piv = k; double best = std::fabs(A[k * 9 + k]);
+    for (int r = k + 1; r < 9; ++r) if (std::fabs(A[r * 9 + k]) > best) { best = std::fabs(A[r * 9 + k]); piv = r; }
+    if (best == 0.0) return 1;
+    if (piv != k) { for (int c = 0; c < 9; ++c) std::swap(A[k * 9 + c], A[piv * 9 + c]); std::swap(bb[k], bb[piv]); }
+    for (int r = k + 1; r < 9; ++r) {
+      const double l = A[r * 9 + k] / A[k * 9 + k];
+      for (int c = k; c < 9; ++c) A[r * 9 + c] -= l * A[k * 9 + c];
+      bb[r] -= l * bb[k];
+    }
+  }
+  for (int k = 8; k >= 0; --k) { double s = bb[k]; for (int c = k + 1; c < 9; ++c) s -= A[k * 9 + c] * bb[c]; bb[k] = s / A[k * 9 + k]; }
+  for (int i = 0; i < 9; ++i) DbarF[i] = bb[i];
+  return 0;
+}
+
+// ---- FFT_nr3 (FFT_nr3.f:14-200) ----
+int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_t* isNBC, int32_t* nr_iters,
+                  int32_t* cg_iters, int cg_cap, double* Pbar_out, double* seconds, int64_t* counters) {
+  if (!h || !BC_all || !isNBC || !h->d_matidx) { cpf_set_error(h, "FFT_nr3: model not set"); return CPFFT_ERR_USAGE; }
+  const int64_t n3 = h->n3, n = 9 * n3;
+  double* Fn1 = h->field[CPFFT_FN1]; double* dFm = h->field[CPFFT_DFM]; double* b = h->field[CPFFT_B];
+  bool existNBC = false;
+  for (int i = 0; i < 9; ++i) if (isNBC[i]) existNBC = true;
+  h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0;
+  const double t_start = wall_s();
+  int rc;
+  if (!h->have_chomo) {  // "initial homogenized tangent stiffness", always (FFT_nr3.f:47)
+    rc = cpfft_tangent_homo(h, h->C_homo); if (rc) return rc;
+    h->have_chomo = true;
+  }
+  double DbarF[9], PBC[9], FBC[9];
+  const double tolNR = h->cfg.tolNR, tolCG = h->cfg.tolPCG;
+  for (int s = 0; s < nstep; ++s) {
+    const int step = h->next_step;
+    int ncg = 0;
+    auto push_cg = [&](int it) { if (cg_iters && ncg < cg_cap - 1) cg_iters[(size_t)s * cg_cap + ncg++] = it; };
+    for (int i = 0; i < 9; ++i) {
+      PBC[i] = 0; FBC[i] = 0; DbarF[i] = 0;
+      if (isNBC[i]) PBC[i] = BC_all[(size_t)s * 9 + i];
+      else { FBC[i] = BC_all[(size_t)s * 9 + i]; DbarF[i] = FBC[i] - h->barF_t[i]; }
+    }
+    if (existNBC && nbc_update(h->C_homo, DbarF, h->P_bar, PBC, isNBC)) { cpf_set_error(h, ">>> Error: P_bar update failed"); return CPFFT_ERR_PBAR; }
+    for (int i = 0; i < 9; ++i) h->barF[i] = h->barF_t[i] + DbarF[i];
+    int iiter_NBC = 0, total_nr = 0;
+    for (;;) {
+      k_fill9<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(dFm, n3, DbarF[0], DbarF[1], DbarF[2], DbarF[3], DbarF[4], DbarF[5], DbarF[6], DbarF[7], DbarF[8]);
+      h->launches++;
+      double f2;
+      rc = cpf_dot(h, Fn1, Fn1, n, &f2); if (rc) return rc;
+      const double Fnorm = sqrt(f2);
+      k_axpy<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(Fn1, dFm, 1.0, n); h->launches++;
+      rc = cpf_apply_G(h, dFm, b, true, -1.0); if (rc) return rc;
+      int it;
+      rc = pcg_dev(h, b, dFm, tolCG, &it, nullptr); if (rc) return rc;
+      push_cg(it);
+      k_axpy<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(Fn1, dFm, 1.0, n); h->launches++;
+      double resfft = 1.0;
+      int iiter_EBC = 0;
+      while (resfft > tolNR) {
+        rc = cpfft_drive_eps_sig(h, step, iiter_EBC); if (rc) return rc;
+        rc = cpf_apply_G(h, h->field[CPFFT_PN1], b, false, -1.0); if (rc) return rc;
+        rc = pcg_dev(h, b, dFm, tolCG, &it, nullptr); if (rc) return rc;
+        push_cg(it);
+        k_axpy<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(Fn1, dFm, 1.0, n); h->launches++;
+        double d2;
+        rc = cpf_dot(h, dFm, dFm, n, &d2); if (rc) return rc;
+        resfft = sqrt(d2) / Fnorm;
+        if (iiter_EBC == h->cfg.maxIter) { cpf_set_error(h, ">> Error: Newton loop does not converge."); return CPFFT_ERR_NEWTON; }
+        iiter_EBC++;
+      }
+      total_nr += iiter_EBC;
+      rc = cpfft_drive_eps_sig(h, step, iiter_EBC); if (rc) return rc;
+      rc = cpfft_mean_P(h, h->P_bar); if (rc) return rc;
+      double r1 = 0, r2 = 0, r3;
+      for (int i = 0; i < 9; ++i) {
+        r2 += h->P_bar[i] * h->P_bar[i];
+        if (!isNBC[i]) continue;
+        r1 += (h->P_bar[i] - PBC[i]) * (h->P_bar[i] - PBC[i]);
+      }
+      r3 = (r2 < 1.0e-8) ? sqrt(r1) : sqrt(r1 / r2);
+      if (r3 <= tolNR) break;
+      if (iiter_NBC > h->cfg.maxIter) { cpf_set_error(h, ">> Error: Prescribed stress cannot be reached within given maximum iteration."); return CPFFT_ERR_STRESS_BC; }
+      rc = cpfft_tangent_homo(h, h->C_homo); if (rc) return rc;
+      for (int i = 0; i < 9; ++i) DbarF[i] = 0;
+      if (nbc_update(h->C_homo, DbarF, h->P_bar, PBC, isNBC)) { cpf_set_error(h, ">>> Error: P_bar update failed"); return CPFFT_ERR_PBAR; }
+      for (int i = 0; i < 9; ++i) h->barF[i] += DbarF[i];
+      iiter_NBC++;
+    }
+    for (int i = 0; i < 9; ++i) h->barF_t[i] = h->barF[i];
+    rc = cpfft_update(h); if (rc) return rc;
+    if (nr_iters) nr_iters[s] = total_nr;
+    if (cg_iters) cg_iters[(size_t)s * cg_cap + ncg] = -1;
+    if (Pbar_out) for (int i = 0; i < 9; ++i) Pbar_out[(size_t)s * 9 + i] = h->P_bar[i];
+    h->next_step++;
+  }
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  if (seconds) { seconds[0] = h->t_pcg; seconds[1] = h->t_sig; seconds[2] = wall_s() - t_start; }
+  if (counters) { counters[0] = h->n_apply; counters[1] = h->n_sweep; counters[2] = h->n_cg; }
+  return 0;
+}
+
+// ---- NCCL bootstrap ----
+int cpfft_nccl_unique_id(void* id128) {
+  if (nccl_load()) return CPFFT_ERR_NCCL;
+  return g_nccl.GetUniqueId((cpf_ncclUniqueId*)id128) ? CPFFT_ERR_NCCL : 0;
+}
+int cpfft_nccl_init(cpfft_handle* h, const void* id128) {
+  if (!h) return CPFFT_ERR_USAGE;
+  if (h->cfg.world <= 1) return 0;
+  if (nccl_load()) { cpf_set_error(h, "libnccl.so.2 not found"); return CPFFT_ERR_NCCL; }
+  cpf_ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  CPF_CUDA(cudaSetDevice(h->cfg.device));
+  CPF_NCCL(g_nccl.CommInitRank(&h->nccl_comm, h->cfg.world, id, h->cfg.rank));
+  const size_t spec_elems = (size_t)9 * h->nxloc * h->N * h->Nh;
+  CPF_CUDA(cudaMalloc(&h->spec_b, sizeof(double2) * spec_elems));
+  CPF_CUDA(cudaMalloc(&h->xchg_send, sizeof(double2) * spec_elems));
+  CPF_CUDA(cudaMalloc(&h->xchg_recv, sizeof(double2) * spec_elems));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+/*
+ * cpfft_b200 -- C ABI of the B200-native CPFFT hot path.
+ *
+ * The reference (maranGit/CPFFT) has no FFI: its "interface" is a set of fixed-form
+ * Fortran subroutines operating on module-global arrays.  Each export below replaces one
+ * of those entry points (file:line given) and keeps its argument meaning and error
+ * behaviour; all state lives on the GPU behind an opaque handle.  A Fortran host binds
+ * these through ISO_C_BINDING (see INTEGRATION.md and cpfft_b200/fortran/cpfft_iso_c.f90).
+ *
+ * Conventions
+ *   - every call returns int: 0 ok; >0 a reference-equivalent fatal condition (the reference
+ *     prints to unit `out` and stops, mpi_code.f:15-40); <0 a CUDA/NCCL/usage error.
+ *     cpfft_last_error() returns the text.
+ *   - voxel index e = x*N*N + y*N + z (0-based; FFT_init.f:311-318); 9-vectors are
+ *     11,12,13,21,..,33; 81-vectors are 27i+9j+3k+l (FFT_init.f:283-304).
+ *   - with world > 1 the grid is slab-decomposed along x: rank r owns
+ *     x in [r*N/world, (r+1)*N/world); host arrays passed in/out are the LOCAL slab.
+ *   - non re-entrant per handle, one host thread per GPU (the reference calls all of these
+ *     from its serial master thread).
+ */
+#ifndef CPFFT_B200_H
+#define CPFFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cpfft_handle cpfft_handle;
+
+/* error codes > 0: where the reference would `die_abort` */
+enum {
+  CPFFT_OK = 0,
+  CPFFT_ERR_NEWTON = 1,     /* FFT_nr3.f:116  Newton loop does not converge           */
+  CPFFT_ERR_CG = 2,         /* FFT_nr3.f:335  fftPcg failed to converge in 1000 its   */
+  CPFFT_ERR_TOL = 3,        /* FFT_nr3.f:248  improper CG tolerance                   */
+  CPFFT_ERR_STRESS_BC = 4,  /* FFT_nr3.f:153  prescribed stress cannot be reached     */
+  CPFFT_ERR_PBAR = 5,       /* FFT_nr3.f:418  P_bar update failed (singular 9x9)      */
+  CPFFT_ERR_MATERIAL = 6,   /* mm10_a.f:2811  mm10 implicit solution failed           */
+  CPFFT_ERR_CUDA = -1, CPFFT_ERR_USAGE = -2, CPFFT_ERR_NCCL = -3
+};
+
+/* crystal library entry, c_array(n) of mod_crystals.f:142-214 (Voce subset) */
+typedef struct {
+  int32_t slip_type;    /* 1 fcc, 8 bcc48 (mod_crystals.f:164-172)   */
+  int32_t elastic_type; /* 1 isotropic, 2 cubic (mod_crystals.f:173) */
+  int32_t h_type;       /* 1 voce                                    */
+  int32_t alter_mode;   /* mm10_a.f:2073                             */
+  int32_t miter;        /* mod_crystals.f:398                        */
+  int32_t pad_;
+  double e, nu, mu, harden_n, theta_0, tau_y, tau_v, voche_m, iD_v, eps_dot_0_y, k_0, burgers;
+  double atol, atol1, rtol, rtol1;
+} cpfft_crystal;
+
+/* material table entry: matprp slots of inmat.f:97-133 (REAL*4 on purpose) / :176-298 */
+typedef struct {
+  int32_t type;     /* 1 bilinear (mm01), 10 crystal plasticity (mm10) */
+  int32_t crystal;  /* cp: 1-based crystal number                      */
+  float e, nu, beta, tan_e, yld_pt, pad_;
+} cpfft_material;
+
+typedef struct {
+  int32_t N;        /* grid points per edge ("number of grid", FFT_finite_3d.f:88-93) */
+  int32_t device;   /* CUDA device ordinal                                            */
+  int32_t rank, world;
+  int32_t maxIter;  /* indypm.f:30-58 */
+  int32_t pad_;
+  double tolNR, tolPCG, tstep;
+} cpfft_config;
+
+/* device-resident fields addressable by id */
+typedef enum {
+  CPFFT_FN = 0, CPFFT_FN1, CPFFT_PN, CPFFT_PN1, CPFFT_DFM, CPFFT_B,   /* mod_fft.f:56-58, 9 comps */
+  CPFFT_CG_P, CPFFT_CG_AP, CPFFT_CG_R,                                /* tmpPcg cols 1-3          */
+  CPFFT_K4,                                                           /* 81 comps                  */
+  CPFFT_URCS_N, CPFFT_URCS_N1,                                        /* 9  (mod_eleblocks.f:60-94)*/
+  CPFFT_EPS_N, CPFFT_EPS_N1,                                          /* 6                         */
+  CPFFT_ROT_N1,                                                       /* 9                         */
+  CPFFT_HIST_N, CPFFT_HIST_N1,                                        /* cpfft_hist_size() comps   */
+  CPFFT_CEP,                                                          /* 36, [D] of last sweep     */
+  CPFFT_NUM_FIELDS
+} cpfft_field;
+
+typedef enum {
+  CPFFT_LAYOUT_SOA = 0,   /* (ncomp, N3loc): the reference's column-major (N3, ncomp)            */
+  CPFFT_LAYOUT_AOS = 1    /* (N3loc, ncomp): the per-block (nvals, ngp=1, span) storage, blocks
+                             concatenated in voxel order (mod_eleblocks.f:60-94, dupstr.f:326-349) */
+} cpfft_layout;
+
+/* ---- life cycle: FFT_init / fftAllocate (FFT_init.f:16-258) ---- */
+int  cpfft_create(const cpfft_config* cfg, cpfft_handle** out);
+void cpfft_destroy(cpfft_handle* h);
+const char* cpfft_last_error(const cpfft_handle* h);
+
+/* ---- model data: what inmat/incrystal/inelem leave in matprp, c_array, matList ---- */
+int cpfft_set_materials(cpfft_handle* h, int nmat, const cpfft_material* mats, int ncry,
+                        const cpfft_crystal* crys);
+/* matlist: 1-based material per local voxel; angles: (N3loc,3) Kocks degrees */
+int cpfft_set_voxels(cpfft_handle* h, const int32_t* matlist, const double* angles_deg);
+int cpfft_set_params(cpfft_handle* h, double tolNR, double tolPCG, int maxIter, double tstep);
+int cpfft_hist_size(const cpfft_handle* h);
+int64_t cpfft_local_voxels(const cpfft_handle* h);
+
+/* ---- hot path, one export per reference entry point ---- */
+int cpfft_drive_eps_sig(cpfft_handle* h, int step, int iter);          /* drive_eps_sig.f:16    */
+int cpfft_G_K_dF(cpfft_handle* h, cpfft_field src, cpfft_field dst, int flgK); /* G_K_dF.f:11   */
+int cpfft_fftPcg(cpfft_handle* h, cpfft_field b, cpfft_field x, double tol,
+                 int* iters, double* relres);                          /* FFT_nr3.f:214         */
+int cpfft_tangent_homo(cpfft_handle* h, double C_homo[81]);            /* tangent_homo.f:11     */
+int cpfft_mean_P(cpfft_handle* h, double Pbar[9]);                     /* FFT_nr3.f:127-134     */
+int cpfft_update(cpfft_handle* h);                  /* update.f:75-106 + dcopy FFT_nr3.f:174-175 */
+
+/* The whole step loop of FFT_nr3 (FFT_nr3.f:14-200) with zero host traffic inside:
+ * BC_all (nstep,9) row-major cumulative table (inlod.f:57-63), isNBC[9].
+ * Outputs (may be NULL): nr_iters[nstep] Newton iterations per step, cg_iters[nstep*cg_cap]
+ * CG iteration counts of the successive solves of the step (-1 terminated),
+ * Pbar[nstep*9], seconds[3] = {pcg bucket, sig-eps bucket, total} (thyme.f buckets 1,2),
+ * counters[3] = {G_K_dF applications, drive_eps_sig sweeps, CG iterations}.
+ * first_step > 1 continues a previous call (state is kept in the handle). */
+int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_t* isNBC,
+                  int32_t* nr_iters, int32_t* cg_iters, int cg_cap, double* Pbar,
+                  double* seconds, int64_t* counters);
+
+/* ---- host <-> device movement of whole fields ---- */
+int cpfft_field_ncomp(const cpfft_handle* h, cpfft_field f);
+int cpfft_upload(cpfft_handle* h, cpfft_field f, const double* host, cpfft_layout layout);
+int cpfft_download(cpfft_handle* h, cpfft_field f, double* host, cpfft_layout layout);
+int cpfft_download_fail_flags(cpfft_handle* h, int32_t* flags);   /* per voxel, mm10 local solve */
+int cpfft_download_local_iters(cpfft_handle* h, int32_t* iters2); /* (N3loc,2) predictor/update  */
+
+/* ---- multi-GPU (new; the reference's mpi_code.f is all stubs) ---- */
+int cpfft_nccl_unique_id(void* id128);                   /* rank 0: create, then broadcast */
+int cpfft_nccl_init(cpfft_handle* h, const void* id128); /* all ranks                       */
+
+/* ---- measurement helpers ---- */
+int cpfft_synchronize(cpfft_handle* h);
+void* cpfft_stream(cpfft_handle* h);                     /* cudaStream_t the kernels run on */
+int64_t cpfft_kernel_launches(const cpfft_handle* h);    /* launches since create           */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

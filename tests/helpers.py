@@ -1,0 +1,105 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+from cpfft_b200.deck import read_deck
+from cpfft_b200.problem import Problem, Material, Crystal
+
+DECKS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decks")
+
+# north_star tolerances: <= 1e-9 relative per voxel, <= 1e-10 on macroscopic averages
+TOL_VOXEL = 1.0e-9
+TOL_MACRO = 1.0e-10
+
+
+def deck(name):
+    return read_deck(os.path.join(DECKS, name))
+
+
+def relerr(a, b):
+    """max |a-b| scaled by the magnitude of the reference field (per-field scale)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+def mm10_variant(angle_file="angle2.in"):
+    """test_mm10.in with another orientation table."""
+    import tempfile
+    src = open(os.path.join(DECKS, "test_mm10.in")).read().replace("angle_bc.in", angle_file)
+    path = os.path.join(DECKS, "_tmp_variant.in")
+    with open(path, "w") as f:
+        f.write(src)
+    try:
+        return read_deck(path)
+    finally:
+        os.remove(path)
+
+
+def stress_bc_variant(prob):
+    """derived mixed deck: F_xx driven, P_yy = P_zz = 0."""
+    p = Problem(**{k: getattr(prob, k) for k in prob.__dataclass_fields__})
+    p.FP_max = prob.FP_max.copy(); p.isNBC = prob.isNBC.copy()
+    p.FP_max[4] = 0.0; p.FP_max[8] = 0.0
+    p.isNBC[4] = 1; p.isNBC[8] = 1
+    return p
+
+
+def mm10_layout(nslip, num_hard=1):
+    """0-based slot ranges of the mm10 history vector (mm10_d.f:137-331)."""
+    use_max = (num_hard == 48 or nslip == 48)
+    l5 = 48 if use_max else nslip
+    l6 = 48 if use_max else nslip
+    l7 = 48 if use_max else num_hard
+    l8 = 48 if use_max else 15
+    l9 = 48 if use_max else num_hard
+    names = [("cep", 36), ("gradfe", 27), ("R", 9), ("work", 3), ("slipsum", l5), ("stress", 6), ("euler", 3),
+             ("Rp", 9), ("D", 6), ("eps", 6), ("slipinc", l6), ("tau_tilde", l7), ("u", l8), ("tt_rate", l9),
+             ("ep", 6), ("ed", 6)]
+    out, pos = {}, 0
+    for n, l in names:
+        out[n] = (pos, pos + l)
+        pos += l
+    out["total"] = pos
+    return out
+
+
+def kocks_matrix(ang_deg):
+    """mm10_rotation_matrix (mm10_a.f:1329-1337), vectorised over rows of (psi,theta,phi)."""
+    a = np.deg2rad(np.asarray(ang_deg, float))
+    psi, th, phi = a[..., 0], a[..., 1], a[..., 2]
+    r = np.empty(a.shape[:-1] + (3, 3))
+    r[..., 0, 0] = -np.sin(psi) * np.sin(phi) - np.cos(psi) * np.cos(phi) * np.cos(th)
+    r[..., 0, 1] = np.cos(psi) * np.sin(phi) - np.sin(psi) * np.cos(phi) * np.cos(th)
+    r[..., 0, 2] = np.cos(phi) * np.sin(th)
+    r[..., 1, 0] = np.sin(psi) * np.cos(phi) - np.cos(psi) * np.sin(phi) * np.cos(th)
+    r[..., 1, 1] = -np.cos(psi) * np.cos(phi) - np.sin(psi) * np.sin(phi) * np.cos(th)
+    r[..., 1, 2] = np.sin(phi) * np.sin(th)
+    r[..., 2, 0] = np.cos(psi) * np.sin(th)
+    r[..., 2, 1] = np.sin(psi) * np.sin(th)
+    r[..., 2, 2] = np.cos(th)
+    return r
+
+
+def compare_mm10_history(hg, ho, nslip, tol=TOL_VOXEL):
+    """Group-wise comparison of (N3, H) mm10 histories.  Euler angles are compared through
+    the rotation matrix they define: at theta ~ 0 (gimbal lock) psi and phi are individually
+    undetermined (atan2 of round-off), only the rotation is meaningful."""
+    L = mm10_layout(nslip)
+    errs = {}
+    for name, rng in L.items():
+        if name == "total":
+            continue
+        a, b = hg[:, rng[0]:rng[1]], ho[:, rng[0]:rng[1]]
+        if name == "euler":
+            errs[name] = np.abs(kocks_matrix(a) - kocks_matrix(b)).max()
+        elif name == "u":
+            # u(12) = n_eff and u(14) = B_eff are ratios of increments; u(7), u(8) integers
+            sc = np.maximum(np.abs(b).max(axis=0), 1e-300)
+            errs[name] = (np.abs(a - b).max(axis=0) / sc).max()
+        else:
+            errs[name] = relerr(a, b) if np.abs(b).max() > 0 else np.abs(a).max()
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"mm10 history parity violated: {bad} (all: {errs})"
+    return errs

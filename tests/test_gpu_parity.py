@@ -1,0 +1,128 @@
+"""GPU <-> oracle parity through the C ABI on the reference's own decks (N = 7)."""
+import numpy as np
+import pytest
+
+from helpers import (deck, relerr, TOL_VOXEL, TOL_MACRO, mm10_variant, stress_bc_variant,
+                     compare_mm10_history)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs(oracle_built):
+    from cpfft_b200 import Solver
+    from oracle import Oracle
+    return Solver, Oracle
+
+
+def _compare_state(s, o, hist=True, tol=TOL_VOXEL):
+    errs = {
+        "Pn1": relerr(s.download("PN1"), o.Pn1),
+        "K4": relerr(s.download("K4"), o.K4),
+        "urcs_n1": relerr(s.download("URCS_N1", 1), o.urcs_n1),
+        "eps_n1": relerr(s.download("EPS_N1", 1), o.eps_n1),
+    }
+    if hist:
+        hg = s.download("HIST_N1", 1)[:, :o.H]
+        if any(m.type == 10 for m in o.prob.materials):
+            nslip = {1: 12, 8: 48}[o.prob.crystals[0].slip_type]
+            errs.update({"hist." + k: v for k, v in compare_mm10_history(hg, o.hist_n1, nslip, tol).items()})
+        else:
+            errs["hist_n1"] = relerr(hg, o.hist_n1)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"parity violated: {bad} (all: {errs})"
+    return errs
+
+
+@pytest.mark.parametrize("name", ["test_mm01.in", "test_mm10.in"])
+def test_initial_sweep(libs, name):
+    """drive_eps_sig(1,0) at F = I: P = 0, elastic K4 (FFT_finite_3d.f:145)."""
+    Solver, Oracle = libs
+    p = deck(name)
+    s, o = Solver(p), Oracle(p)
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    _compare_state(s, o)
+
+
+@pytest.mark.parametrize("name", ["test_mm01.in", "test_mm10.in"])
+def test_sweep_on_perturbed_F(libs, name):
+    """one nonlinear sweep (iter = 1) on a heterogeneous, finite deformation field."""
+    Solver, Oracle = libs
+    p = deck(name)
+    s, o = Solver(p), Oracle(p)
+    rng = np.random.default_rng(7)
+    amp = 0.05 if name == "test_mm01.in" else 0.004
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += amp * rng.standard_normal((9, p.N3))
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    s.upload("FN1", F); o.Fn1[:] = F
+    for it in (0, 1, 2):
+        s.drive_eps_sig(1, it); assert o.drive_eps_sig(1, it) == 0
+        _compare_state(s, o)
+    if name == "test_mm10.in":
+        assert np.array_equal(s.local_iters(), o.local_iters)
+
+
+@pytest.mark.parametrize("name", ["test_mm01.in", "test_mm10.in"])
+@pytest.mark.parametrize("flgK", [0, 1])
+def test_G_K_dF(libs, name, flgK):
+    Solver, Oracle = libs
+    p = deck(name)
+    s, o = Solver(p), Oracle(p)
+    rng = np.random.default_rng(11)
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += 0.01 * rng.standard_normal((9, p.N3))
+    s.upload("FN1", F); o.Fn1[:] = F
+    s.drive_eps_sig(1, 1); o.drive_eps_sig(1, 1)
+    x = rng.standard_normal((9, p.N3))
+    s.upload("DFM", x)
+    s.G_K_dF("DFM", "B", flgK)
+    ref = o.G_K_dF(x, flgK)
+    assert relerr(s.download("B"), ref) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["test_mm01.in", "test_mm10.in"])
+def test_full_deck(libs, name):
+    """whole FFT_nr3 step loop: identical Newton counts, stress-strain curve, final state."""
+    Solver, Oracle = libs
+    p = deck(name)
+    s, o = Solver(p), Oracle(p)
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    rs, ro = s.FFT_nr3(), o.FFT_nr3()
+    assert ro["rc"] == 0
+    assert list(rs["nr_iters"]) == list(ro["nr_iters"])
+    assert rs["cg_iters"] == [[int(v) for v in r] for r in ro["cg_iters"]]
+    scale = np.abs(ro["Pbar"]).max()
+    assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / scale <= TOL_MACRO
+    _compare_state(s, o)
+    assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
+    if name == "test_mm01.in":
+        assert relerr(s.download("HIST_N", 1)[:, :o.H], o.hist_n) <= TOL_VOXEL
+    else:
+        compare_mm10_history(s.download("HIST_N", 1)[:, :o.H], o.hist_n, 48)
+
+
+def test_homogeneous_single_crystal(libs):
+    """test_mm10.in with angle2.in: uniform fields, zero fluctuation."""
+    Solver, Oracle = libs
+    p = mm10_variant("angle2.in")
+    s, o = Solver(p), Oracle(p)
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    rs, ro = s.FFT_nr3(nstep=4), o.FFT_nr3(nstep=4)
+    assert list(rs["nr_iters"]) == list(ro["nr_iters"])
+    P = s.download("PN1")
+    assert np.abs(P - P.mean(axis=1, keepdims=True)).max() <= 1e-9 * np.abs(P).max()
+    assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / np.abs(ro["Pbar"]).max() <= TOL_MACRO
+
+
+def test_stress_bc_deck(libs):
+    """derived deck with P_yy = P_zz = 0: exercises tangent_homo + NBC_update."""
+    Solver, Oracle = libs
+    p = stress_bc_variant(deck("test_mm01.in"))
+    s, o = Solver(p), Oracle(p)
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    rs, ro = s.FFT_nr3(nstep=3), o.FFT_nr3(nstep=3)
+    assert ro["rc"] == 0
+    assert list(rs["nr_iters"]) == list(ro["nr_iters"])
+    assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / np.abs(ro["Pbar"]).max() <= 1e-9
+    assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
