@@ -47,8 +47,9 @@ EXPORTS = [
     "cpfft_set_params", "cpfft_hist_size", "cpfft_local_voxels", "cpfft_drive_eps_sig", "cpfft_G_K_dF",
     "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3",
     "cpfft_field_ncomp", "cpfft_upload", "cpfft_download", "cpfft_download_fail_flags",
-    "cpfft_download_local_iters", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_synchronize",
-    "cpfft_stream", "cpfft_kernel_launches",
+    "cpfft_download_local_iters", "cpfft_material_failures", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_synchronize",
+    "cpfft_stream", "cpfft_kernel_launches", "cpfft_profile_enable", "cpfft_profile_reset",
+    "cpfft_profile_classes", "cpfft_profile_name", "cpfft_profile_get",
 ]
 
 
@@ -89,6 +90,7 @@ def load_library():
     L.cpfft_download.argtypes = [vp, C.c_int, dp, C.c_int]
     L.cpfft_download_fail_flags.argtypes = [vp, ip]
     L.cpfft_download_local_iters.argtypes = [vp, ip]
+    L.cpfft_material_failures.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.cpfft_nccl_unique_id.argtypes = [vp]
     L.cpfft_nccl_init.argtypes = [vp, vp]
     L.cpfft_synchronize.argtypes = [vp]
@@ -96,6 +98,11 @@ def load_library():
     L.cpfft_stream.restype = vp
     L.cpfft_kernel_launches.argtypes = [vp]
     L.cpfft_kernel_launches.restype = C.c_int64
+    L.cpfft_profile_enable.argtypes = [vp, C.c_int]
+    L.cpfft_profile_reset.argtypes = [vp]
+    L.cpfft_profile_name.argtypes = [C.c_int]
+    L.cpfft_profile_name.restype = C.c_char_p
+    L.cpfft_profile_get.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64)]
     _LIB = L
     return L
 
@@ -113,7 +120,8 @@ class Solver:
 
     CG_CAP = 64
 
-    def __init__(self, prob: Problem, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None):
+    def __init__(self, prob: Problem, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None,
+                 local_slab: bool = False):
         self.L = load_library()
         self.prob = prob
         self.N, self.rank, self.world = prob.N, rank, world
@@ -126,7 +134,8 @@ class Solver:
         mats, crys = prob.material_pods(), prob.crystal_pods()
         self._check(self.L.cpfft_set_materials(self.h, len(prob.materials), C.addressof(mats),
                                                len(prob.crystals), C.addressof(crys)))
-        lo, hi = rank * self.n3, (rank + 1) * self.n3
+        lo, hi = (0, self.n3) if local_slab else (rank * self.n3, (rank + 1) * self.n3)
+        assert len(prob.matlist) >= hi, "matlist does not cover this rank's slab"
         ml = np.ascontiguousarray(prob.matlist[lo:hi], dtype=np.int32)
         ang = np.ascontiguousarray(prob.angles[lo:hi], dtype=np.float64)
         self._check(self.L.cpfft_set_voxels(self.h, _ip(ml), _dp(ang)))
@@ -188,6 +197,12 @@ class Solver:
         self._check(self.L.cpfft_download_local_iters(self.h, _ip(f)))
         return f
 
+    def material_failures(self):
+        """(total, last sweep) mm10 local-solver failures, summed over ranks"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.L.cpfft_material_failures(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- hot path, reference names ----
     def drive_eps_sig(self, step, iiter):
         self._check(self.L.cpfft_drive_eps_sig(self.h, step, iiter))
@@ -223,12 +238,34 @@ class Solver:
         cg = np.full((nstep, self.CG_CAP), -1, dtype=np.int32)
         pbar = np.zeros((nstep, 9))
         sec = np.zeros(3)
-        cnt = np.zeros(3, dtype=np.int64)
+        cnt = np.zeros(5, dtype=np.int64)
         rc = self.L.cpfft_FFT_nr3(self.h, nstep, _dp(bc), _ip(nbc), _ip(nr), _ip(cg), self.CG_CAP, _dp(pbar),
                                   _dp(sec), cnt.ctypes.data_as(C.POINTER(C.c_int64)))
         self._check(rc)
         cg_lists = [list(r[:list(r).index(-1)]) if -1 in r else list(r) for r in cg]
         return dict(rc=rc, nr_iters=nr, cg_iters=cg_lists, Pbar=pbar, buckets=sec, counters=cnt)
+
+    def profile(self, on=True):
+        self._check(self.L.cpfft_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._check(self.L.cpfft_profile_reset(self.h))
+
+    def profile_table(self):
+        """{kernel class: (total ms, launches)} from CUDA events on the launching stream."""
+        out = {}
+        for c in range(self.L.cpfft_profile_classes()):
+            ms, cnt = C.c_double(0), C.c_int64(0)
+            self._check(self.L.cpfft_profile_get(self.h, c, C.byref(ms), C.byref(cnt)))
+            out[self.L.cpfft_profile_name(c).decode()] = (ms.value, cnt.value)
+        return out
+
+    def upload_ptr(self, name, ptr, layout=SOA):
+        """upload from a raw host pointer (e.g. pinned memory)"""
+        self._check(self.L.cpfft_upload(self.h, FIELD_ID[name], C.cast(ptr, C.POINTER(C.c_double)), layout))
+
+    def download_ptr(self, name, ptr, layout=SOA):
+        self._check(self.L.cpfft_download(self.h, FIELD_ID[name], C.cast(ptr, C.POINTER(C.c_double)), layout))
 
     def synchronize(self):
         self._check(self.L.cpfft_synchronize(self.h))

@@ -40,14 +40,28 @@ struct CpfCryDev {
 
 // per-grain (unique crystal+orientation) table entry, device, doubles:
 //   [0..8] g (row-major), [9..44] rotated stiffness C (row-major 6x6),
-//   [45 + 9 s ..): ms0[6] (engineering-shear Schmid vector), qs0[3] (skew vector) of system s
+//   [45 + 9 s ..): ms0[6] (engineering-shear Schmid vector), qs0[3] (skew vector) of system s,
+//   [45 + 9*48 ..+3): the Kocks angles in degrees
 #define CPF_GRAIN_G 0
 #define CPF_GRAIN_C 9
 #define CPF_GRAIN_B 45
-#define CPF_GRAIN_STRIDE (45 + 9 * CPF_MAX_SLIP)
+#define CPF_GRAIN_ANG (45 + 9 * CPF_MAX_SLIP)   // Kocks angles (degrees) of the grain
+#define CPF_GRAIN_STRIDE (48 + 9 * CPF_MAX_SLIP)
+
+// kernel classes for the built-in CUDA-event profiler (cpfft_profile_*)
+enum CpfKernelClass {
+  CPF_K_UPDATE_MM01 = 0, CPF_K_UPDATE_MM10, CPF_K_PK1_TANGENT, CPF_K_FWD_Z, CPF_K_FWD_Z_K4, CPF_K_FFT_Y,
+  CPF_K_X_GREEN, CPF_K_INV_Z, CPF_K_VECTOR, CPF_K_EXCHANGE, CPF_K_NUM
+};
+struct CpfProfEvt { cudaEvent_t a, b; int cls; };
 
 struct cpfft_handle {
   cpfft_config cfg;
+  // profiler
+  bool prof_on;
+  std::vector<CpfProfEvt> prof_live;
+  std::vector<CpfProfEvt> prof_pool;
+  double prof_ms[CPF_K_NUM]; int64_t prof_cnt[CPF_K_NUM];
   int N, Nh;                 // Nh = N/2+1 (half spectrum along z)
   int nxloc, x0;             // local slab
   int64_t n3;                // local voxels
@@ -69,6 +83,8 @@ struct cpfft_handle {
   bool has_mm01, has_mm10;
   CpfHistLayout L;
   int32_t* d_fail; int32_t* d_liters;
+  int* d_failcnt;            // {mm10 local failures since reset, failures of the last sweep}
+  int64_t n_fail, n_fail_final;
   // spectral work
   double2* spec_a; double2* spec_b;      // half-spectrum buffers [9][nx][N][Nh]
   double2* tw;                           // twiddles exp(-2 pi i k / N)
@@ -89,6 +105,9 @@ struct cpfft_handle {
 };
 
 void cpf_set_error(cpfft_handle* h, const std::string& s);
+// CUDA-event bracket around one kernel launch (no-ops unless profiling is enabled)
+int cpf_prof_begin(cpfft_handle* h, int cls);
+void cpf_prof_end(cpfft_handle* h, int token);
 
 // material.cu
 int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* angles);

@@ -45,7 +45,7 @@ struct UpdArgs {
   double* cep;
   const int32_t* matidx; const int32_t* grain;
   const CpfMatDev* mats; const CpfCryDev* crys; const double* grains;
-  int32_t* fail; int32_t* liters;
+  int32_t* fail; int32_t* liters; int* failcnt;
   int64_t n3; int step, iter; double dt;
   CpfHistLayout L;
 };
@@ -245,20 +245,33 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm10(UpdArgs a) {
         }
     }
   }
-  if (fail) {  // reference: prints, leaves the block un-updated; here: flag + keep state finite
-    a.fail[e] = 1;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = c.sn[k];
-    x[6] = c.ttn;
-#pragma unroll
-    for (int k = 0; k < 36; ++k) tang[k] = __ldg(c.C + k);
-  } else a.fail[e] = 0;
-  a.liters[2 * e] = itp; a.liters[2 * e + 1] = itu;
-
   // ---- outputs: update_rotation + mm10_output (skipped on the elastic path, where the
   //      reference stores the zero-initialised np1 fields) ----
   double Rp1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, euler[3] = {0, 0, 0}, eps6[6] = {0, 0, 0, 0, 0, 0};
   double ep6[6] = {0, 0, 0, 0, 0, 0}, ed6[6] = {0, 0, 0, 0, 0, 0};
+  if (fail) {
+    // material_cut_step.  The reference prints a warning, resets stress / tau_tilde to the n
+    // state (mm10_a.f:2838-2841) and leaves the rest of the block un-updated (:125-127), i.e.
+    // undefined data.  Defined behaviour here (identical in the oracle): the point keeps its n
+    // state (stress, tau_tilde, Rp, Euler angles, lattice strain), no slip, elastic tangent;
+    // the sweep goes on and the failure is counted (cpfft_material_failures).
+    a.fail[e] = 1;
+    atomicAdd(a.failcnt, 1); atomicAdd(a.failcnt + 1, 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = c.sn[k];
+    x[6] = c.ttn;
+    tt_rate = 0.0;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) tang[k] = __ldg(c.C + k);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rp1[k] = Rpn[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      euler[k] = first ? __ldg(gt + CPF_GRAIN_ANG + k) : a.hist_n[(L.c_euler + k) * n3 + e];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) eps6[k] = first ? 0.0 : a.hist_n[(L.c_eps + k) * n3 + e];
+  } else a.fail[e] = 0;
+  a.liters[2 * e] = itp; a.liters[2 * e + 1] = itu;
   double u6 = 0, u7 = 0, u8 = 0, u11 = 0, u12 = 0, u13 = 0, u14 = 0, u15 = 0;
   double work_inc = 0, p_work_inc = 0, p_strain_inc = 0;
   const bool full = !elastic && !fail;
@@ -545,6 +558,7 @@ int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* an
     r[2][2] = std::cos(th);
     double tr[3][3];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { t[CPF_GRAIN_G + 3 * i + j] = r[i][j]; tr[i][j] = r[j][i]; }
+    for (int k = 0; k < 3; ++k) t[CPF_GRAIN_ANG + k] = key[1 + k];
     double Rs[6][6], tmp[6][6];
     host_rt2rve(tr, Rs);
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += stiff[ci][6 * i + k] * Rs[j][k]; tmp[i][j] = s; }
@@ -604,13 +618,23 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
   a.hist_n = h->field[CPFFT_HIST_N]; a.hist_n1 = h->field[CPFFT_HIST_N1];
   a.cep = h->field[CPFFT_CEP];
   a.matidx = h->d_matidx; a.grain = h->d_grain; a.mats = h->d_mats; a.crys = h->d_crys; a.grains = h->d_grains;
-  a.fail = h->d_fail; a.liters = h->d_liters;
+  a.fail = h->d_fail; a.liters = h->d_liters; a.failcnt = h->d_failcnt;
   a.n3 = h->n3; a.step = step; a.iter = iter; a.dt = h->cfg.tstep; a.L = h->L;
   const int64_t n3 = h->n3;
   const unsigned grid = (unsigned)((n3 + UPD_THREADS - 1) / UPD_THREADS);
-  if (h->has_mm01) { k_update_mm01<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++; }
-  if (h->has_mm10) { k_update_mm10<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++; }
+  if (h->has_mm01) {
+    const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM01);
+    k_update_mm01<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++;
+    cpf_prof_end(h, tk);
+  }
+  if (h->has_mm10) {
+    const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
+    k_update_mm10<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++;
+    cpf_prof_end(h, tk);
+  }
+  const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);
   k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
+  cpf_prof_end(h, tk);
   h->launches++;
   CPF_CUDA(cudaGetLastError());
   return 0;

@@ -13,6 +13,31 @@ static double wall_s() {
 }
 void cpf_set_error(cpfft_handle* h, const std::string& s) { if (h) h->err = s; }
 
+int cpf_prof_begin(cpfft_handle* h, int cls) {
+  if (!h->prof_on) return -1;
+  CpfProfEvt e;
+  if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+  else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
+  e.cls = cls;
+  cudaEventRecord(e.a, h->stream);
+  h->prof_live.push_back(e);
+  return (int)h->prof_live.size() - 1;
+}
+void cpf_prof_end(cpfft_handle* h, int token) {
+  if (token < 0) return;
+  cudaEventRecord(h->prof_live[token].b, h->stream);
+}
+static void prof_collect(cpfft_handle* h) {
+  if (h->prof_live.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  for (auto& e : h->prof_live) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { h->prof_ms[e.cls] += ms; h->prof_cnt[e.cls]++; }
+    h->prof_pool.push_back(e);
+  }
+  h->prof_live.clear();
+}
+
 // ------------------------------------------------------------------------------------------
 // field kernels (grid-stride, coalesced, grid = multiple of the SM count)
 #define VEC_THREADS 256
@@ -95,11 +120,6 @@ __global__ void k_final_sum(const double* partials, int nb, double* out) {  // b
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partials[blockIdx.x * nb + i];
   s = block_sum(s);
   if (threadIdx.x == 0) out[blockIdx.x] = s;
-}
-__global__ void k_or_flags(const int32_t* f, int64_t n, int* out) {
-  int v = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v |= f[i];
-  if (__syncthreads_or(v) && threadIdx.x == 0) atomicOr(out, 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -197,17 +217,21 @@ static int all_to_all(cpfft_handle* h) {
 }
 int cpf_exchange_fwd(cpfft_handle* h) {
   const int64_t total = (int64_t)9 * h->nxloc * h->N * h->Nh;
+  const int tk = cpf_prof_begin(h, CPF_K_EXCHANGE);
   k_pack_fwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->spec_a, h->xchg_send, h->cfg.world, h->nxloc, h->N, h->Nh);
   int rc = all_to_all(h); if (rc) return rc;
   k_unpack_fwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->xchg_recv, h->spec_b, h->cfg.world, h->nxloc, h->N, h->Nh);
+  cpf_prof_end(h, tk);
   h->launches += 2;
   return 0;
 }
 int cpf_exchange_bwd(cpfft_handle* h) {
   const int64_t total = (int64_t)9 * h->nxloc * h->N * h->Nh;
+  const int tk = cpf_prof_begin(h, CPF_K_EXCHANGE);
   k_pack_bwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->spec_b, h->xchg_send, h->cfg.world, h->nxloc, h->N, h->Nh);
   int rc = all_to_all(h); if (rc) return rc;
   k_unpack_bwd<<<vec_grid(total), VEC_THREADS, 0, h->stream>>>(h->xchg_recv, h->spec_a, h->cfg.world, h->nxloc, h->N, h->Nh);
+  cpf_prof_end(h, tk);
   h->launches += 2;
   return 0;
 }
@@ -224,8 +248,10 @@ static int fetch_scalars(cpfft_handle* h, int cnt, double* out) {
 }
 int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out) {
   const int nb = h->nblocks_red;
+  const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
   k_dot_partial<<<nb, VEC_THREADS, 0, h->stream>>>(x, y, n, h->d_partials);
   k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, nb, h->d_scalars);
+  cpf_prof_end(h, tk);
   h->launches += 2;
   return fetch_scalars(h, 1, out);
 }
@@ -241,9 +267,11 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   if (h->cfg.world < 1) h->cfg.world = 1;
   h->N = cfg->N; h->Nh = cfg->N / 2 + 1;
   h->err.clear(); h->launches = 0;
+  h->prof_on = false;
+  for (int i = 0; i < CPF_K_NUM; ++i) { h->prof_ms[i] = 0; h->prof_cnt[i] = 0; }
   for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) { h->field[f] = nullptr; h->ncomp[f] = 0; }
   h->d_mats = nullptr; h->d_crys = nullptr; h->d_matidx = nullptr; h->d_grain = nullptr; h->d_grains = nullptr;
-  h->d_fail = nullptr; h->d_liters = nullptr; h->spec_a = h->spec_b = nullptr; h->tw = nullptr; h->d_radices = nullptr;
+  h->d_fail = nullptr; h->d_liters = nullptr; h->d_failcnt = nullptr; h->n_fail = h->n_fail_final = 0; h->spec_a = h->spec_b = nullptr; h->tw = nullptr; h->d_radices = nullptr;
   h->work9 = nullptr; h->d_partials = nullptr; h->d_scalars = nullptr; h->h_scalars = nullptr;
   h->nccl_comm = nullptr; h->nccl_lib = nullptr; h->xchg_send = h->xchg_recv = nullptr;
   h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr;
@@ -270,6 +298,8 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   CPF_CUDA(cudaMalloc(&h->d_fail, sizeof(int32_t) * h->n3));
   CPF_CUDA(cudaMalloc(&h->d_liters, sizeof(int32_t) * 2 * h->n3));
   CPF_CUDA(cudaMemsetAsync(h->d_fail, 0, sizeof(int32_t) * h->n3, h->stream));
+  CPF_CUDA(cudaMalloc(&h->d_failcnt, sizeof(int) * 2));
+  CPF_CUDA(cudaMemsetAsync(h->d_failcnt, 0, sizeof(int) * 2, h->stream));
   CPF_CUDA(cudaMemsetAsync(h->d_liters, 0, sizeof(int32_t) * 2 * h->n3, h->stream));
   h->nblocks_red = g_num_sms * 8;
   CPF_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * 16 * h->nblocks_red));
@@ -290,8 +320,10 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
 void cpfft_destroy(cpfft_handle* h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  prof_collect(h);
+  for (auto& e : h->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) if (h->field[f]) cudaFree(h->field[f]);
-  void* ptrs[] = {h->d_mats, h->d_crys, h->d_matidx, h->d_grain, h->d_grains, h->d_fail, h->d_liters, h->work9,
+  void* ptrs[] = {h->d_mats, h->d_crys, h->d_matidx, h->d_grain, h->d_grains, h->d_fail, h->d_liters, h->d_failcnt, h->work9,
                   h->d_partials, h->d_scalars, h->xchg_send, h->xchg_recv};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -374,34 +406,33 @@ int64_t cpfft_kernel_launches(const cpfft_handle* h) { return h ? h->launches : 
 int cpfft_drive_eps_sig(cpfft_handle* h, int step, int iter) {
   if (!h || !h->d_matidx) { cpf_set_error(h, "model not set"); return CPFFT_ERR_USAGE; }
   const double t0 = wall_s();
+  if (h->has_mm10) CPF_CUDA(cudaMemsetAsync(h->d_failcnt + 1, 0, sizeof(int), h->stream));
   int rc = cpf_launch_update(h, step, iter);
   if (rc) return rc;
   h->n_sweep++;
-  if (h->has_mm10) {  // material_cut_step -> fatal (mm10_a.f:2811)
-    int* flag = (int*)(h->d_scalars + 64);
-    CPF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
-    k_or_flags<<<vec_grid(h->n3), VEC_THREADS, 0, h->stream>>>(h->d_fail, h->n3, flag);
-    h->launches++;
-    int hf = 0;
-    CPF_CUDA(cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CPF_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->cfg.world > 1) {
-      // every rank must agree
-      double v = hf;
-      CPF_CUDA(cudaMemcpyAsync(h->d_scalars, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      double o; int r2 = 0;
-      { if (h->cfg.world > 1) { r2 = g_nccl.AllReduce(h->d_scalars, h->d_scalars, 1, 8, 0, h->nccl_comm, h->stream); } }
-      if (r2) { cpf_set_error(h, "ncclAllReduce failed"); return CPFFT_ERR_NCCL; }
-      CPF_CUDA(cudaMemcpyAsync(&o, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      CPF_CUDA(cudaStreamSynchronize(h->stream));
-      hf = (o != 0.0);
-    }
-    h->t_sig += wall_s() - t0;
-    if (hf) { cpf_set_error(h, ">>> Warning: mm10 implicit solution failed."); return CPFFT_ERR_MATERIAL; }
-  } else {
-    CPF_CUDA(cudaStreamSynchronize(h->stream));
-    h->t_sig += wall_s() - t0;
+  // mm10 local failures of this sweep (material_cut_step, mm10_a.f:2811): counted, not fatal
+  // -- see the failure branch of k_update_mm10 for the defined behaviour
+  int cnt[2] = {0, 0};
+  if (h->has_mm10)
+    CPF_CUDA(cudaMemcpyAsync(cnt, h->d_failcnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_fail_final = cnt[1];
+  h->n_fail += cnt[1];
+  h->t_sig += wall_s() - t0;
+  return 0;
+}
+
+int cpfft_material_failures(cpfft_handle* h, int64_t* total, int64_t* last_sweep) {
+  if (!h) return CPFFT_ERR_USAGE;
+  int64_t v[2] = {h->n_fail, h->n_fail_final};
+  if (h->cfg.world > 1) {  // the counts of all slabs
+    double d[2] = {(double)v[0], (double)v[1]};
+    CPF_CUDA(cudaMemcpyAsync(h->d_scalars, d, sizeof(d), cudaMemcpyHostToDevice, h->stream));
+    int rc = fetch_scalars(h, 2, d); if (rc) return rc;
+    v[0] = (int64_t)d[0]; v[1] = (int64_t)d[1];
   }
+  if (total) *total = v[0];
+  if (last_sweep) *last_sweep = v[1];
   return 0;
 }
 
@@ -435,13 +466,19 @@ static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int*
     if (resnorm <= tolb || resnorm <= tol) break;
     if (it >= maxIter) { cpf_set_error(h, ">>>fftPcg: fail to converge within 1000 iterations"); return CPFFT_ERR_CG; }
     if (it == 0) CPF_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
-    else { k_xpby<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(p, r, rr / rr_old, n); h->launches++; }
+    else {
+      const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
+      k_xpby<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(p, r, rr / rr_old, n); h->launches++;
+      cpf_prof_end(h, tk);
+    }
     rc = cpf_apply_G(h, p, q, true, 1.0); if (rc) return rc;
     double pq;
     rc = cpf_dot(h, p, q, n, &pq); if (rc) return rc;
     const double alpha = rr / pq;
+    const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
     k_cg_update<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(x, r, p, q, alpha, n, h->d_partials);
     k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, h->nblocks_red, h->d_scalars);
+    cpf_prof_end(h, tk);
     h->launches += 2;
     rr_old = rr;
     rc = fetch_scalars(h, 1, &rr); if (rc) return rc;
@@ -542,7 +579,8 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
   double* Fn1 = h->field[CPFFT_FN1]; double* dFm = h->field[CPFFT_DFM]; double* b = h->field[CPFFT_B];
   bool existNBC = false;
   for (int i = 0; i < 9; ++i) if (isNBC[i]) existNBC = true;
-  h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0;
+  h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0; h->n_fail = 0;
+  int64_t fail_final_steps = 0;
   const double t_start = wall_s();
   int rc;
   if (!h->have_chomo) {  // "initial homogenized tangent stiffness", always (FFT_nr3.f:47)
@@ -591,6 +629,7 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
       }
       total_nr += iiter_EBC;
       rc = cpfft_drive_eps_sig(h, step, iiter_EBC); if (rc) return rc;
+      fail_final_steps += h->n_fail_final;
       rc = cpfft_mean_P(h, h->P_bar); if (rc) return rc;
       double r1 = 0, r2 = 0, r3;
       for (int i = 0; i < 9; ++i) {
@@ -616,7 +655,42 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
   }
   CPF_CUDA(cudaStreamSynchronize(h->stream));
   if (seconds) { seconds[0] = h->t_pcg; seconds[1] = h->t_sig; seconds[2] = wall_s() - t_start; }
-  if (counters) { counters[0] = h->n_apply; counters[1] = h->n_sweep; counters[2] = h->n_cg; }
+  if (counters) {
+    counters[0] = h->n_apply; counters[1] = h->n_sweep; counters[2] = h->n_cg;
+    int64_t tot = 0, last = 0;
+    const int64_t keep = h->n_fail_final;
+    h->n_fail_final = fail_final_steps;
+    rc = cpfft_material_failures(h, &tot, &last); if (rc) return rc;
+    h->n_fail_final = keep;
+    counters[3] = tot; counters[4] = last;
+  }
+  return 0;
+}
+
+// ---- built-in profiler: CUDA events on the launching stream around every kernel ----
+int cpfft_profile_enable(cpfft_handle* h, int on) {
+  if (!h) return CPFFT_ERR_USAGE;
+  prof_collect(h);
+  h->prof_on = (on != 0);
+  return 0;
+}
+int cpfft_profile_reset(cpfft_handle* h) {
+  if (!h) return CPFFT_ERR_USAGE;
+  prof_collect(h);
+  for (int i = 0; i < CPF_K_NUM; ++i) { h->prof_ms[i] = 0; h->prof_cnt[i] = 0; }
+  return 0;
+}
+int cpfft_profile_classes(void) { return CPF_K_NUM; }
+const char* cpfft_profile_name(int cls) {
+  static const char* names[CPF_K_NUM] = {"k_update_mm01", "k_update_mm10", "k_pk1_tangent", "k_fwd_z", "k_fwd_z_K4",
+                                          "k_fft_y", "k_x_green", "k_inv_z", "vector_ops", "exchange"};
+  return (cls >= 0 && cls < CPF_K_NUM) ? names[cls] : "?";
+}
+int cpfft_profile_get(cpfft_handle* h, int cls, double* ms, int64_t* count) {
+  if (!h || cls < 0 || cls >= CPF_K_NUM) return CPFFT_ERR_USAGE;
+  prof_collect(h);
+  if (ms) *ms = h->prof_ms[cls];
+  if (count) *count = h->prof_cnt[cls];
   return 0;
 }
 

@@ -287,30 +287,42 @@ int cpf_apply_G(cpfft_handle* h, const double* src, double* dst, bool flgK, doub
   g.N = N; g.Nh = Nh; g.nx = nx; g.x0 = h->x0; g.nrad = h->nrad; g.rad = h->d_radices; g.tw = h->tw; g.n3 = h->n3;
   const int threads = (N >= 256) ? 256 : ((N >= 64) ? 128 : 64);
   const size_t sm_z = (size_t)2 * 9 * N * sizeof(cplx);
+  int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
   k_fwd_z<<<nx * N, threads, sm_z, h->stream>>>(g, src, flgK ? h->field[CPFFT_K4] : nullptr, h->spec_a);
+  cpf_prof_end(h, tk);
   const int tzy = pick_tz(N, 1, Nh);
   dim3 gy(9 * nx, (Nh + tzy - 1) / tzy);
   const size_t sm_y = (size_t)2 * tzy * N * sizeof(cplx);
+  tk = cpf_prof_begin(h, CPF_K_FFT_Y);
   k_fft_y<<<gy, threads, sm_y, h->stream>>>(g, h->spec_a, tzy, -1);
+  cpf_prof_end(h, tk);
   const int tzx = pick_tz(N, 3, Nh);
   const size_t sm_x = (size_t)2 * 3 * tzx * N * sizeof(cplx);
   if (h->cfg.world == 1) {
     dim3 gx(N, (Nh + tzx - 1) / tzx, 3);
+    tk = cpf_prof_begin(h, CPF_K_X_GREEN);
     k_x_green<<<gx, threads, sm_x, h->stream>>>(g, h->spec_a, tzx, N, 0);
+    cpf_prof_end(h, tk);
     h->launches += 5;
   } else {
     int rc = cpf_exchange_fwd(h);   // spec_a (x-slabs) -> spec_b (y-slabs, full x)
     if (rc) return rc;
     const int ny = N / h->cfg.world;
     dim3 gx(ny, (Nh + tzx - 1) / tzx, 3);
+    tk = cpf_prof_begin(h, CPF_K_X_GREEN);
     k_x_green<<<gx, threads, sm_x, h->stream>>>(g, h->spec_b, tzx, ny, h->cfg.rank * ny);
+    cpf_prof_end(h, tk);
     rc = cpf_exchange_bwd(h);       // spec_b -> spec_a
     if (rc) return rc;
     h->launches += 5;
   }
+  tk = cpf_prof_begin(h, CPF_K_FFT_Y);
   k_fft_y<<<gy, threads, sm_y, h->stream>>>(g, h->spec_a, tzy, +1);
+  cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
+  tk = cpf_prof_begin(h, CPF_K_INV_Z);
   k_inv_z<<<nx * N, threads, sm_z, h->stream>>>(g, h->spec_a, dst, scale);
+  cpf_prof_end(h, tk);
   CPF_CUDA(cudaGetLastError());
   h->n_apply++;
   return 0;

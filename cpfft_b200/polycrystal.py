@@ -1,0 +1,58 @@
+"""Deterministic synthetic Voronoi polycrystal (BASELINE.json configs[3,4]).
+
+seed 20240607; G seeds uniform in [0,1)^3; periodic Voronoi tessellation evaluated at the voxel
+centres (i+1/2)/N; one orientation per grain, uniform on SO(3), given as Kocks angles in
+degrees (psi, phi uniform in [0,360), cos(theta) uniform in [-1,1]); voxel
+e = x*N*N + y*N + z.  One crystal-plasticity material: fcc, isotropic e 200000 nu 0.3, Voce
+harden_n 20 theta_0 100 voce_m 1 tau_v 100 tau_y 100, alter_mode off, time step 1.
+Loading (pure-strain variant): F_xx +1 %, F_yy = F_zz -0.3 % in 10 equal steps.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .problem import Crystal, Material, Problem
+
+SEED = 20240607
+
+
+def grain_map(N: int, ngrains: int = 1000, seed: int = SEED, x_range=None) -> np.ndarray:
+    """grain index per voxel (optionally only for the x-planes in ``x_range``)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    seeds = rng.random((ngrains, 3))
+    tree = cKDTree(seeds, boxsize=1.0)
+    x0, x1 = (0, N) if x_range is None else x_range
+    c = (np.arange(N) + 0.5) / N
+    out = np.empty((x1 - x0) * N * N, dtype=np.int32)
+    yy, zz = np.meshgrid(c, c, indexing="ij")
+    plane = np.stack([np.zeros(N * N), yy.ravel(), zz.ravel()], axis=1)
+    for ix in range(x0, x1):
+        plane[:, 0] = c[ix]
+        _, idx = tree.query(plane, workers=-1)
+        out[(ix - x0) * N * N:(ix - x0 + 1) * N * N] = idx
+    return out
+
+
+def grain_angles(ngrains: int = 1000, seed: int = SEED) -> np.ndarray:
+    rng = np.random.default_rng(seed + 1)
+    u = rng.random((ngrains, 3))
+    psi = 360.0 * u[:, 0]
+    theta = np.degrees(np.arccos(1.0 - 2.0 * u[:, 1]))
+    phi = 360.0 * u[:, 2]
+    return np.stack([psi, theta, phi], axis=1)
+
+
+def polycrystal(N: int, ngrains: int = 1000, seed: int = SEED, nstep: int = 10, slip_type: int = 1,
+                x_range=None) -> Problem:
+    gm = grain_map(N, ngrains, seed, x_range)
+    ang = grain_angles(ngrains, seed)[gm]
+    cry = Crystal(slip_type=slip_type, elastic_type=1, h_type=1, alter_mode=0, e=200000.0, nu=0.3,
+                  mu=200000.0 / 2.6, harden_n=20.0, theta_0=100.0, voche_m=1.0, tau_v=100.0, tau_y=100.0)
+    mat = Material(name="poly", type=10, crystal=1)
+    FP = np.zeros(9)
+    FP[0], FP[4], FP[8] = 0.01, -0.003, -0.003
+    p = Problem(N=N, materials=[mat], crystals=[cry], matlist=np.ones(len(gm), dtype=np.int32), angles=ang,
+                FP_max=FP, isNBC=np.zeros(9, dtype=np.int32), mults=np.full(nstep, 1.0 / nstep),
+                tolNR=1.0e-5, tolPCG=1.0e-10, maxIter=20, tstep=1.0)
+    return p

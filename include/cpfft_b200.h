@@ -37,7 +37,8 @@ enum {
   CPFFT_ERR_TOL = 3,        /* FFT_nr3.f:248  improper CG tolerance                   */
   CPFFT_ERR_STRESS_BC = 4,  /* FFT_nr3.f:153  prescribed stress cannot be reached     */
   CPFFT_ERR_PBAR = 5,       /* FFT_nr3.f:418  P_bar update failed (singular 9x9)      */
-  CPFFT_ERR_MATERIAL = 6,   /* mm10_a.f:2811  mm10 implicit solution failed           */
+  CPFFT_ERR_MATERIAL = 6,   /* mm10_a.f:2811  mm10 implicit solution failed (reserved: local
+                               failures are counted, see cpfft_material_failures)        */
   CPFFT_ERR_CUDA = -1, CPFFT_ERR_USAGE = -2, CPFFT_ERR_NCCL = -3
 };
 
@@ -116,7 +117,8 @@ int cpfft_update(cpfft_handle* h);                  /* update.f:75-106 + dcopy F
  * Outputs (may be NULL): nr_iters[nstep] Newton iterations per step, cg_iters[nstep*cg_cap]
  * CG iteration counts of the successive solves of the step (-1 terminated),
  * Pbar[nstep*9], seconds[3] = {pcg bucket, sig-eps bucket, total} (thyme.f buckets 1,2),
- * counters[3] = {G_K_dF applications, drive_eps_sig sweeps, CG iterations}.
+ * counters[5] = {G_K_dF applications, drive_eps_sig sweeps, CG iterations, mm10 local solver
+ * failures over all sweeps, failures in the final (converged) sweeps of the steps}.
  * first_step > 1 continues a previous call (state is kept in the handle). */
 int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_t* isNBC,
                   int32_t* nr_iters, int32_t* cg_iters, int cg_cap, double* Pbar,
@@ -128,6 +130,10 @@ int cpfft_upload(cpfft_handle* h, cpfft_field f, const double* host, cpfft_layou
 int cpfft_download(cpfft_handle* h, cpfft_field f, double* host, cpfft_layout layout);
 int cpfft_download_fail_flags(cpfft_handle* h, int32_t* flags);   /* per voxel, mm10 local solve */
 int cpfft_download_local_iters(cpfft_handle* h, int32_t* iters2); /* (N3loc,2) predictor/update  */
+/* mm10 material_cut_step events (mm10_a.f:2811 ">>> Warning: mm10 implicit solution failed"):
+ * the reference prints and carries on with an un-updated block; here the point keeps its n
+ * state with the elastic tangent, and the events are counted (summed over ranks). */
+int cpfft_material_failures(cpfft_handle* h, int64_t* total, int64_t* last_sweep);
 
 /* ---- multi-GPU (new; the reference's mpi_code.f is all stubs) ---- */
 int cpfft_nccl_unique_id(void* id128);                   /* rank 0: create, then broadcast */
@@ -137,6 +143,13 @@ int cpfft_nccl_init(cpfft_handle* h, const void* id128); /* all ranks           
 int cpfft_synchronize(cpfft_handle* h);
 void* cpfft_stream(cpfft_handle* h);                     /* cudaStream_t the kernels run on */
 int64_t cpfft_kernel_launches(const cpfft_handle* h);    /* launches since create           */
+/* CUDA events recorded on the launching stream around every kernel, summed per kernel class;
+ * the analogue of the reference's thyme() buckets (thyme.f:15-47) at kernel granularity */
+int cpfft_profile_enable(cpfft_handle* h, int on);
+int cpfft_profile_reset(cpfft_handle* h);
+int cpfft_profile_classes(void);
+const char* cpfft_profile_name(int cls);
+int cpfft_profile_get(cpfft_handle* h, int cls, double* ms, int64_t* count);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,8 @@ def _lib():
         L.orc_mean_P.argtypes = [C.c_void_p, dp]
         L.orc_FFT_nr3.argtypes = [C.c_void_p, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp,
                                   C.POINTER(C.c_int64)]
+        L.orc_FFT_nr3_from.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp,
+                                       C.POINTER(C.c_int64)]
         L.orc_rtcmp1.argtypes = [dp, dp]
         L.orc_cep2A.argtypes = [dp, dp, dp, dp, dp]
         L.orc_point_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
@@ -170,7 +172,7 @@ class Oracle:
         cg = np.full((nstep, self.CG_CAP), -1, dtype=np.int32)
         pbar = np.zeros((nstep, 9))
         buckets = np.zeros(3)
-        counters = np.zeros(3, dtype=np.int64)
+        counters = np.zeros(5, dtype=np.int64)
         rc = self.L.orc_FFT_nr3(self.h, nstep, _dp(bc), _ip(nbc), _ip(nr), _ip(cg), self.CG_CAP,
                                 _dp(pbar), _dp(buckets), counters.ctypes.data_as(C.POINTER(C.c_int64)))
         cg_lists = [list(row[:list(row).index(-1)]) if -1 in row else list(row) for row in cg]

@@ -95,7 +95,13 @@ void orc_mean_P(orc_model*, double* Pbar);
 int  orc_FFT_nr3(orc_model*, int nstep, const double* BC_all, const int32_t* isNBC,
                  int32_t* nr_iters, int32_t* cg_iters, int cg_cap, double* Pbar,
                  double* bucket_seconds /* [3]: pcg, sig-eps, total */,
-                 int64_t* counters /* [3]: G_K_dF applies, drive sweeps, cg iterations */);
+                 int64_t* counters /* [5]: G_K_dF applies, drive sweeps, cg iterations, local mm10 failures (all sweeps), failures in the last sweep */);
+
+/* same, continuing from load step `first_step` (1-based) with the state kept in the model;
+ * BC_all holds the rows of the steps to run */
+int  orc_FFT_nr3_from(orc_model*, int first_step, int nstep, const double* BC_all, const int32_t* isNBC,
+                      int32_t* nr_iters, int32_t* cg_iters, int cg_cap, double* Pbar,
+                      double* bucket_seconds, int64_t* counters);
 
 /* unit-level probes used by the pinning tests */
 void orc_rtcmp1(const double* F9_rowmajor, double* R9_rowmajor);

@@ -713,7 +713,26 @@ int mm10_point(int step, int iter, const CrystalLib& cry, const double* angles, 
     }
     bool anynan = std::isnan(tt);
     for (int k = 0; k < 6; ++k) anynan = anynan || std::isnan(stress[k]);
-    if (fail || anynan) return 1;  // material_cut_step: reference prints and leaves the block un-updated
+    if (fail || anynan) {
+      // material_cut_step.  The reference prints a warning, sets np1 stress / tau_tilde back to
+      // the n state (mm10_a.f:2838-2841), returns from mm10 and leaves the REST OF THE BLOCK
+      // un-updated (mm10_a.f:125-127) -- undefined data.  Defined behaviour of this project
+      // (oracle and GPU alike): the point keeps its n state (stress, tau_tilde, Rp, Euler
+      // angles, lattice strain), no slip, elastic tangent; the sweep goes on and the failure
+      // is counted.
+      for (int k = 0; k < 6; ++k) { h1[L.c_stress + k] = n.stress[k]; urcs_n1[k] = n.stress[k]; }
+      for (int k = 0; k < 3; ++k) h1[L.c_euler + k] = n.euler[k];
+      for (int k = 0; k < 9; ++k) h1[L.c_Rp + k] = hn[L.c_Rp + k];
+      for (int k = 0; k < 6; ++k) { h1[L.c_D + k] = np1.D[k]; h1[L.c_eps + k] = n.eps[k]; h1[L.c_ep + k] = 0.0; h1[L.c_ed + k] = 0.0; }
+      for (int k = 0; k < L.len_slip; ++k) { h1[L.c_slipinc + k] = 0.0; h1[L.slipsum + k] = hn[L.slipsum + k]; }
+      h1[L.c_tt] = n.tau_tilde; h1[L.c_ttrate] = 0.0;
+      for (int k = 0; k < 15; ++k) h1[L.c_u + k] = 0.0;
+      for (int k = 0; k < 9; ++k) h1[L.R + k] = rot9[k];
+      for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) h1[L.cep + 6 * j + i] = p.stiffness[i][j];
+      for (int k = 6; k < 9; ++k) urcs_n1[k] = urcs_n[k];
+      for (int k = 0; k < 3; ++k) h1[L.work + k] = hn[L.work + k];
+      return 1;
+    }
     curr_tt_rate = curr.tt_rate;
   }
   for (int k = 0; k < 6; ++k) np1.stress[k] = stress[k];

@@ -67,7 +67,9 @@ struct orc_model {
   std::vector<double> c1, c2;    // 1-D phase-ramp tables (phase separable in i+j+k)
   Fft1d fft;
   std::vector<cplx> work;        // 9 * N3 complex
-  double t_pcg, t_sig; int64_t n_apply, n_sweep, n_cg;
+  double t_pcg, t_sig; int64_t n_apply, n_sweep, n_cg, n_fail, n_fail_final;
+  // FFT_nr3 locals that persist across load steps (FFT_nr3.f:23-34)
+  double barF[9], barF_t[9], P_bar[9], C_homo[81]; bool have_chomo;
 };
 
 static int g_threads = 0;
@@ -123,7 +125,9 @@ extern "C" orc_model* orc_create(int N, int nmat, const orc_material* mats, int 
   for (int s = 0; s < 3 * N; ++s) { double t = NhN * (double)s; m->c1[s] = std::cos(t); m->c2[s] = -std::sin(t); }
   m->fft.init(N);
   m->work.resize(9 * n3);
-  m->t_pcg = m->t_sig = 0; m->n_apply = m->n_sweep = m->n_cg = 0;
+  m->t_pcg = m->t_sig = 0; m->n_apply = m->n_sweep = m->n_cg = 0; m->n_fail = m->n_fail_final = 0;
+  for (int i = 0; i < 9; ++i) { m->barF[i] = m->barF_t[i] = (i % 4 == 0) ? 1.0 : 0.0; m->P_bar[i] = 0.0; }
+  m->have_chomo = false;
   return m;
 }
 extern "C" void orc_destroy(orc_model* m) { delete m; }
@@ -456,24 +460,26 @@ static int nbc_update(const double* C_homo, double* DbarF, const double* P_bar, 
 // FFT_nr3 (FFT_nr3.f:14-200).  Error codes: 1 Newton not converged (:116), 2 CG not converged
 // (:335), 3 bad tolerance (:248), 4 stress BC not reached (:153), 5 P_bar update failed (:418),
 // 6 material model failure (mm10_a.f:2811).
-extern "C" int orc_FFT_nr3(orc_model* m, int nstep, const double* BC_all, const int32_t* isNBC, int32_t* nr_iters,
-                           int32_t* cg_iters, int cg_cap, double* Pbar_out, double* buckets, int64_t* counters) {
+extern "C" int orc_FFT_nr3_from(orc_model* m, int first_step, int nstep, const double* BC_all, const int32_t* isNBC,
+                                int32_t* nr_iters, int32_t* cg_iters, int cg_cap, double* Pbar_out, double* buckets,
+                                int64_t* counters) {
   const size_t n3 = m->N3, n = 9 * n3;
-  double barF[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, barF_t[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  double DbarF[9] = {0}, P_bar[9] = {0}, FBC[9], PBC[9], C_homo[81];
+  double* barF = m->barF; double* barF_t = m->barF_t; double* P_bar = m->P_bar; double* C_homo = m->C_homo;
+  double DbarF[9] = {0}, FBC[9], PBC[9];
   bool existNBC = false;
   for (int i = 0; i < 9; ++i) if (isNBC[i]) existNBC = true;
-  m->t_pcg = m->t_sig = 0; m->n_apply = m->n_sweep = m->n_cg = 0;
+  m->t_pcg = m->t_sig = 0; m->n_apply = m->n_sweep = m->n_cg = 0; m->n_fail = m->n_fail_final = 0;
   double t_start = now_s();
-  int rc = orc_tangent_homo(m, C_homo);
-  if (rc) return rc;
-  for (int step = 1; step <= nstep; ++step) {
+  int rc = 0;
+  if (!m->have_chomo) { rc = orc_tangent_homo(m, C_homo); if (rc) return rc; m->have_chomo = true; }
+  for (int sidx = 0; sidx < nstep; ++sidx) {
+    const int step = first_step + sidx;
     int ncg = 0;
-    auto push_cg = [&](int it) { if (ncg < cg_cap - 1) cg_iters[(size_t)(step - 1) * cg_cap + ncg++] = it; };
+    auto push_cg = [&](int it) { if (ncg < cg_cap - 1) cg_iters[(size_t)sidx * cg_cap + ncg++] = it; };
     for (int i = 0; i < 9; ++i) {
       PBC[i] = 0; FBC[i] = 0; DbarF[i] = 0;
-      if (isNBC[i]) PBC[i] = BC_all[(size_t)(step - 1) * 9 + i];
-      else { FBC[i] = BC_all[(size_t)(step - 1) * 9 + i]; DbarF[i] = FBC[i] - barF_t[i]; }
+      if (isNBC[i]) PBC[i] = BC_all[(size_t)sidx * 9 + i];
+      else { FBC[i] = BC_all[(size_t)sidx * 9 + i]; DbarF[i] = FBC[i] - barF_t[i]; }
     }
     if (existNBC) { if (nbc_update(C_homo, DbarF, P_bar, PBC, isNBC)) return 5; }
     for (int i = 0; i < 9; ++i) barF[i] = barF_t[i] + DbarF[i];
@@ -491,7 +497,7 @@ extern "C" int orc_FFT_nr3(orc_model* m, int nstep, const double* BC_all, const 
       double resfft = 1.0;
       int iiter_EBC = 0;
       while (resfft > m->tolNR) {
-        if (orc_drive_eps_sig(m, step, iiter_EBC)) return 6;
+        m->n_fail += orc_drive_eps_sig(m, step, iiter_EBC);  // local failures are counted, not fatal
         orc_G_K_dF(m, m->Pn1.data(), m->b.data(), 0);
         for (size_t k = 0; k < n; ++k) m->b[k] = -m->b[k];
         rc = orc_fftPcg(m, m->b.data(), m->dFm.data(), m->tolPCG, &it, nullptr);
@@ -503,7 +509,7 @@ extern "C" int orc_FFT_nr3(orc_model* m, int nstep, const double* BC_all, const 
         iiter_EBC++;
       }
       total_nr += iiter_EBC;
-      if (orc_drive_eps_sig(m, step, iiter_EBC)) return 6;
+      m->n_fail_final = orc_drive_eps_sig(m, step, iiter_EBC); m->n_fail += m->n_fail_final;
       double resP1 = 0, resP2 = 0, resP3;
       orc_mean_P(m, P_bar);
       for (int i = 0; i < 9; ++i) {
@@ -524,13 +530,20 @@ extern "C" int orc_FFT_nr3(orc_model* m, int nstep, const double* BC_all, const 
     for (int i = 0; i < 9; ++i) barF_t[i] = barF[i];
     m->Fn = m->Fn1; m->Pn = m->Pn1;
     orc_update(m);
-    nr_iters[step - 1] = total_nr;
-    cg_iters[(size_t)(step - 1) * cg_cap + ncg] = -1;
-    for (int i = 0; i < 9; ++i) Pbar_out[(size_t)(step - 1) * 9 + i] = P_bar[i];
+    nr_iters[sidx] = total_nr;
+    cg_iters[(size_t)sidx * cg_cap + ncg] = -1;
+    for (int i = 0; i < 9; ++i) Pbar_out[(size_t)sidx * 9 + i] = P_bar[i];
   }
   if (buckets) { buckets[0] = m->t_pcg; buckets[1] = m->t_sig; buckets[2] = now_s() - t_start; }
-  if (counters) { counters[0] = m->n_apply; counters[1] = m->n_sweep; counters[2] = m->n_cg; }
+  if (counters) { counters[0] = m->n_apply; counters[1] = m->n_sweep; counters[2] = m->n_cg; counters[3] = m->n_fail; counters[4] = m->n_fail_final; }
   return 0;
+}
+
+extern "C" int orc_FFT_nr3(orc_model* m, int nstep, const double* BC_all, const int32_t* isNBC, int32_t* nr_iters,
+                           int32_t* cg_iters, int cg_cap, double* Pbar_out, double* buckets, int64_t* counters) {
+  for (int i = 0; i < 9; ++i) { m->barF[i] = m->barF_t[i] = (i % 4 == 0) ? 1.0 : 0.0; m->P_bar[i] = 0.0; }
+  m->have_chomo = false;
+  return orc_FFT_nr3_from(m, 1, nstep, BC_all, isNBC, nr_iters, cg_iters, cg_cap, Pbar_out, buckets, counters);
 }
 
 // ---- unit probes ----

@@ -126,3 +126,45 @@ def test_stress_bc_deck(libs):
     assert list(rs["nr_iters"]) == list(ro["nr_iters"])
     assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / np.abs(ro["Pbar"]).max() <= 1e-9
     assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
+
+
+def test_mm10_local_failure_points(libs):
+    """Two voxels of the 256^3 polycrystal whose local Newton solve fails (sub-stepping
+    exhausted) at load step 2 / global iteration 4 -- captured on the GPU, stored in
+    tests/golden/mm10_fail_points.npz.  Oracle and GPU must fail on exactly the same points with
+    the same iteration counts and leave the same defined state (n state + elastic tangent)."""
+    import os
+    from cpfft_b200.polycrystal import polycrystal
+    Solver, Oracle = libs
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "mm10_fail_points.npz"))
+    nb = d["Fn"].shape[1]
+    p = polycrystal(2, ngrains=8)
+    p.angles[:nb] = d["angles"]
+    s, o = Solver(p), Oracle(p)
+    H = o.H
+    hist = np.zeros((H, p.N3)); urcs = np.zeros((9, p.N3)); eps = np.zeros((6, p.N3))
+    Fn = np.zeros((9, p.N3)); Fn[[0, 4, 8]] = 1.0
+    Fn1 = Fn.copy()
+    # the remaining 6 voxels: copies of point 0's state with a benign (small) increment
+    for v in range(p.N3):
+        src = v if v < nb else 0
+        hist[:, v] = d["hist_n"][:H, src]; urcs[:, v] = d["urcs_n"][:, src]; eps[:, v] = d["eps_n"][:, src]
+        Fn[:, v] = d["Fn"][:, src]
+        Fn1[:, v] = d["Fn1"][:, src] if v < nb else d["Fn"][:, src] + 0.05 * (d["Fn1"][:, src] - d["Fn"][:, src])
+    if nb < p.N3:
+        p.angles[nb:] = d["angles"][0]
+        s, o = Solver(p), Oracle(p)
+    for name, arr in (("HIST_N", hist), ("URCS_N", urcs), ("EPS_N", eps), ("FN", Fn), ("FN1", Fn1)):
+        s.upload(name, arr)
+    o.hist_n[:] = hist.T; o.urcs_n[:] = urcs.T; o._view("eps_n", (o.N3, 6))[:] = eps.T
+    o.Fn[:] = Fn; o.Fn1[:] = Fn1
+    step, it = int(d["step"]), int(d["iter"])
+    s.drive_eps_sig(step, it)
+    nfail = o.drive_eps_sig(step, it)
+    assert nfail == nb
+    flags = s.fail_flags()
+    assert flags.sum() == nb and flags[:nb].all()
+    assert s.material_failures() == (nb, nb)
+    assert np.array_equal(s.local_iters(), o.local_iters)
+    assert np.array_equal(s.local_iters()[:nb], d["liters"])
+    _compare_state(s, o)
