@@ -1,0 +1,73 @@
+"""The C-ABI boundary: libcpfft_b200.so loads here (no GPU), exports every symbol that
+include/cpfft_b200.h declares, and the product fails loudly -- never falls back -- without a
+CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cpfft_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cpfft_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cpfft_b200.build import build
+    build()
+    import cpfft_b200
+    return cpfft_b200.load_library()
+
+
+def test_header_and_python_mirror_agree():
+    import cpfft_b200
+    assert header_symbols() == sorted(cpfft_b200.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [s for s in header_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_no_torch_or_oracle_dependency(lib):
+    """plain C ABI: the shared object must not link libtorch, python or the oracle"""
+    import subprocess
+    import cpfft_b200
+    out = subprocess.run(["ldd", cpfft_b200.library_path()], capture_output=True, text=True).stdout
+    assert "torch" not in out and "python" not in out and "oracle" not in out
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "cpfft_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".f90")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt, f
+
+
+def test_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from helpers import deck
+    from cpfft_b200 import Solver, CpfftError
+    with pytest.raises(CpfftError) as ei:
+        Solver(deck("test_mm01.in"))
+    assert ei.value.code < 0          # CUDA error, no CPU fallback
+
+
+def test_usage_errors_without_device(lib):
+    assert lib.cpfft_hist_size(None) == 0
+    assert lib.cpfft_local_voxels(None) == 0
+    assert lib.cpfft_last_error(None) == b"null handle"
+    assert lib.cpfft_profile_classes() == 10
+    names = [lib.cpfft_profile_name(i).decode() for i in range(10)]
+    assert "k_x_green" in names and "k_update_mm10" in names

@@ -1,0 +1,73 @@
+"""The deck reader (cpfft_b200/deck.py) on the reference's shipped input decks
+(examples/*.in copied verbatim as fixtures into tests/golden/decks): what inmat / incrystal /
+inelem / inlodcase / inlod / indypm leave in the reference's modules."""
+import numpy as np
+import pytest
+
+from helpers import deck, stress_bc_variant
+from cpfft_b200.deck import _int_list, _tokens, _is_comment
+
+
+def test_scanner_conventions():
+    assert _is_comment("c this is a comment") and _is_comment("c") and not _is_comment("crystal 1")
+    assert _tokens("harden_n 5,48") == ["harden_n", "5", ",", "48"]
+    assert _int_list(["1-5"]) == [1, 2, 3, 4, 5]
+    assert _int_list(["2-10", "by", "2"]) == [2, 4, 6, 8, 10]
+    assert _int_list(["1", "2", "7-8", "material"]) == [1, 2, 7, 8]
+
+
+def test_mm01_deck():
+    p = deck("test_mm01.in")
+    assert p.N == 7 and p.N3 == 343
+    assert [m.type for m in p.materials] == [1, 1]
+    a, b = p.materials
+    # REAL*4 matprp slots (mod_fft.f:20, inmat.f:100-127)
+    assert a.e == 12000.0 and b.e == 24000.0
+    assert a.nu == float(np.float32(0.3)) and a.nu != 0.3
+    assert (a.yld_pt, b.yld_pt, a.tan_e, a.beta) == (100.0, 200.0, 1000.0, 0.5)
+    assert set(np.unique(p.matlist)) == {1, 2} and p.matlist.shape == (343,)
+    assert p.nstep == 10 and np.allclose(p.mults, 0.1)
+    assert np.allclose(p.FP_max, [0.3, 0, 0, 0, -0.1, 0, 0, 0, -0.1])
+    assert not p.isNBC.any()
+    assert (p.tolNR, p.tolPCG, p.maxIter, p.tstep) == (1e-5, 1e-10, 10, 10.0)
+    bc = p.BC_all()
+    assert bc.shape == (10, 9)
+    # cumulative + identity on the strain-controlled diagonal (inlod.f:57-63)
+    assert np.allclose(bc[-1], [1.3, 0, 0, 0, 0.9, 0, 0, 0, 0.9])
+    assert np.allclose(bc[0], [1.03, 0, 0, 0, 0.99, 0, 0, 0, 0.99])
+
+
+def test_mm10_deck():
+    p = deck("test_mm10.in")
+    assert p.N == 7 and len(p.materials) == 1 and p.materials[0].type == 10
+    c = p.crystals[0]
+    assert c.slip_type == 8 and c.elastic_type == 1 and c.h_type == 1 and c.alter_mode == 1
+    # `harden_n 5,48`: the comma makes the reader fetch the next line, 48 is discarded
+    # (incrystal.f:989-990)
+    assert c.harden_n == 5.0
+    assert (c.e, c.nu, c.theta_0, c.voche_m, c.tau_v, c.tau_y) == (200000.0, 0.3, 0.01, 1.0, 5000.0, 205.0)
+    assert c.eps_dot_0_y == 4e-5
+    # defaults of initialize_new_crystal (mod_crystals.f:392-403)
+    assert (c.atol, c.rtol, c.atol1, c.rtol1, c.miter) == (1e-5, 5e-5, 1e-5, 1e-5, 30)
+    # angle_bc.in: a bicrystal, 196 voxels at (0,0,0) and 147 at (45,0,0)
+    vals, counts = np.unique(p.angles, axis=0, return_counts=True)
+    assert vals.tolist() == [[0, 0, 0], [45, 0, 0]] and counts.tolist() == [196, 147]
+    assert np.allclose(p.FP_max, [0.03, 0, 0, 0, -0.01, 0, 0, 0, -0.01]) and p.tstep == 10.0
+
+
+def test_stress_bc_variant_table():
+    p = stress_bc_variant(deck("test_mm01.in"))
+    assert list(p.isNBC) == [0, 0, 0, 0, 1, 0, 0, 0, 1]
+    bc = p.BC_all()
+    # stress-controlled diagonals get no identity: the prescribed P is 0
+    assert np.allclose(bc[:, 4], 0) and np.allclose(bc[:, 8], 0) and np.allclose(bc[-1, 0], 1.3)
+
+
+def test_pod_layouts_match_header():
+    """ctypes mirrors of cpfft_crystal / cpfft_material / cpfft_config (include/cpfft_b200.h)."""
+    import ctypes as C
+    from cpfft_b200.problem import CrystalPOD, MaterialPOD
+    from cpfft_b200.api import Config
+    assert C.sizeof(CrystalPOD) == 6 * 4 + 16 * 8
+    assert C.sizeof(MaterialPOD) == 2 * 4 + 6 * 4
+    assert C.sizeof(Config) == 6 * 4 + 3 * 8

@@ -1,0 +1,150 @@
+"""Pinning the oracle's per-voxel update (oracle_kin.cpp, oracle_mm10.cpp) by derived identities
+(SURVEY.md 8c items 3-6): polar decomposition against scipy, the exact tangent dP/dF against
+central finite differences of P(F) (the reference's own claim, cep2A.f:9-10), the bilinear
+model against its closed form, crystal stiffness / slip-table invariants, history layout.
+"""
+import numpy as np
+import pytest
+
+from helpers import deck, mm10_layout
+
+
+@pytest.fixture(scope="module")
+def Oracle(oracle_built):
+    from oracle import Oracle
+    return Oracle
+
+
+def test_rtcmp1_matches_scipy_polar(Oracle):
+    from scipy.linalg import polar
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        F = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+        if np.linalg.det(F) <= 0.1:
+            continue
+        R = Oracle.rtcmp1(F)
+        Rs, _ = polar(F)
+        assert np.abs(R - Rs).max() <= 1e-12
+        assert np.abs(R @ R.T - np.eye(3)).max() <= 1e-12
+
+
+def _fd_tangent(o, voxel, step, it, Fn, Fn1, h=1e-5):
+    # h is large on purpose: the reference's closed-form (trigonometric) eigenvalues of C in
+    # the polar decomposition (polar.f:224-307) carry ~1e-8 relative noise near F = I, which a
+    # central difference divides by h
+    A = np.zeros((9, 9))
+    for kl in range(9):
+        d = np.zeros(9); d[kl] = h
+        Pp, _ = o.point_update(voxel, step, it, Fn, Fn1 + d)
+        Pm, _ = o.point_update(voxel, step, it, Fn, Fn1 - d)
+        A[:, kl] = (Pp - Pm) / (2 * h)
+    return A
+
+
+def test_cep2A_is_dPdF_for_mm01(Oracle):
+    """elastic and actively yielding points of the bilinear model: A = dP/dF to FD accuracy."""
+    p = deck("test_mm01.in")
+    o = Oracle(p)
+    rng = np.random.default_rng(2)
+    Fn = np.eye(3).ravel()
+    for amp, expect_plastic in ((1e-3, False), (0.03, True)):
+        Fn1 = Fn + amp * rng.standard_normal(9)
+        _, A = o.point_update(0, 1, 1, Fn, Fn1)
+        fd = _fd_tangent(o, 0, 1, 1, Fn, Fn1)
+        err = np.abs(A.reshape(9, 9) - fd).max() / np.abs(fd).max()
+        assert err <= 1e-5, (amp, err)
+
+
+def test_mm10_tangent_close_to_fd(Oracle):
+    """mm10: the stored tangent is built from the lagged (pre-update) Jacobian and symmetrised
+    (mm10_a.f:1137-1142), so A only approximates dP/dF; it must still be a good Newton
+    tangent.  At iter 0 the update is linear elastic and A is exact."""
+    p = deck("test_mm10.in")
+    o = Oracle(p)
+    rng = np.random.default_rng(4)
+    Fn = np.eye(3).ravel()
+    Fn1 = Fn + 1e-3 * rng.standard_normal(9)
+    _, A0 = o.point_update(3, 1, 0, Fn, Fn1)
+    fd0 = _fd_tangent(o, 3, 1, 0, Fn, Fn1)
+    assert np.abs(A0.reshape(9, 9) - fd0).max() / np.abs(fd0).max() <= 1e-5
+    Fn1 = Fn + 4e-3 * rng.standard_normal(9)
+    _, A = o.point_update(3, 1, 1, Fn, Fn1)
+    fd = _fd_tangent(o, 3, 1, 1, Fn, Fn1)
+    assert np.abs(A.reshape(9, 9) - fd).max() / np.abs(fd).max() <= 0.02
+
+
+def test_mm01_uniaxial_strain_closed_form(Oracle):
+    """homogeneous bilinear block in uniaxial strain: elastic slope lambda + 2 mu, then the
+    elastic-plastic slope K + 4 mu H' / (3 (3 mu + H')) (small-strain limit)."""
+    from cpfft_b200.problem import Problem, Material
+    N = 3
+    E, nu, Et, sy = np.float32(12000.0), np.float32(0.3), np.float32(1000.0), np.float32(100.0)
+    mat = Material(name="a", type=1, e=float(E), nu=float(nu), beta=0.5, tan_e=float(Et), yld_pt=float(sy))
+    FP = np.zeros(9); FP[0] = 4.0e-2
+    nstep = 40
+    p = Problem(N=N, materials=[mat], crystals=[], matlist=np.ones(N ** 3, np.int32), angles=np.zeros((N ** 3, 3)),
+                FP_max=FP, mults=np.full(nstep, 1.0 / nstep), tolNR=1e-8, tolPCG=1e-10, maxIter=20, tstep=1.0)
+    o = Oracle(p)
+    o.drive_eps_sig(1, 0)
+    r = o.FFT_nr3()
+    assert r["rc"] == 0
+    Ed, nud = float(E), float(nu)
+    mu, K = Ed / (2 * (1 + nud)), Ed / (3 * (1 - 2 * nud))
+    Hp = float(Et) * Ed / (Ed - float(Et))
+    eps = np.log(p.BC_all()[:, 0])                       # logarithmic strain of the stretch
+    sig = r["Pbar"][:, 0] / 1.0                          # lateral stretches are 1: P_xx = sigma_xx
+    # first step is elastic
+    assert abs(sig[0] / eps[0] - (K + 4 * mu / 3)) <= 2e-3 * (K + 4 * mu / 3)
+    slope = np.diff(sig[-10:]) / np.diff(eps[-10:])
+    want = K + 4 * mu * Hp / (3 * (3 * mu + Hp))
+    assert np.abs(slope / want - 1).max() <= 0.05      # finite-strain terms are O(strain) = 4 %
+    # every voxel identical (homogeneous), Newton converges immediately
+    assert np.abs(o.Pn1 - o.Pn1.mean(axis=1, keepdims=True)).max() <= 1e-9 * np.abs(o.Pn1).max()
+
+
+def test_crystal_stiffness_isotropic(Oracle):
+    from cpfft_b200.problem import Crystal
+    c = Crystal(e=200000.0, nu=0.3, mu=200000.0 / 2.6, elastic_type=1)
+    C = Oracle.crystal_stiffness(c)
+    lam = 200000.0 * 0.3 / (1.3 * 0.4); mu = 200000.0 / 2.6
+    want = np.zeros((6, 6)); want[:3, :3] = lam
+    want[np.arange(3), np.arange(3)] += 2 * mu
+    want[np.arange(3, 6), np.arange(3, 6)] = mu
+    assert np.abs(C - want).max() <= 1e-9 * lam
+
+
+@pytest.mark.parametrize("slip_type,nslip", [(1, 12), (8, 48)])
+def test_slip_tables(Oracle, slip_type, nslip):
+    """unit vectors, slip direction in the slip plane; fcc = {111}<110>."""
+    b, n = Oracle.slip_table(slip_type)
+    assert b.shape == (nslip, 3) and n.shape == (nslip, 3)
+    assert np.abs(np.linalg.norm(b, axis=1) - 1).max() <= 1e-14
+    assert np.abs(np.linalg.norm(n, axis=1) - 1).max() <= 1e-14
+    assert np.abs((b * n).sum(axis=1)).max() <= 1e-14
+    if slip_type == 1:
+        assert np.allclose(np.abs(n), 1 / np.sqrt(3))
+        assert np.allclose(np.sort(np.abs(b), axis=1), [0, 1 / np.sqrt(2), 1 / np.sqrt(2)])
+        assert len({tuple(np.round(np.r_[x, y], 6)) for x, y in zip(b, n)}) == 12
+
+
+def test_history_layout_sizes(Oracle):
+    """mm10_d.f:157-331: fcc/Voce = 158 doubles, bcc48 (use_max) = 357."""
+    assert mm10_layout(12)["total"] == 158
+    assert mm10_layout(48)["total"] == 357
+    assert Oracle(deck("test_mm10.in")).H == 357
+    assert Oracle(deck("test_mm01.in")).H == 11
+
+
+def test_homogeneous_single_crystal_is_uniform(Oracle):
+    """test_mm10.in with angle2.in (all orientations equal): no fluctuation, every voxel is the
+    same material-point integration."""
+    from helpers import mm10_variant
+    p = mm10_variant("angle2.in")
+    o = Oracle(p)
+    o.drive_eps_sig(1, 0)
+    r = o.FFT_nr3(nstep=3)
+    assert r["rc"] == 0
+    P = o.Pn1
+    assert np.abs(P - P.mean(axis=1, keepdims=True)).max() <= 1e-9 * np.abs(P).max()
+    F = o.Fn1
+    assert np.abs(F - F.mean(axis=1, keepdims=True)).max() <= 1e-12

@@ -1,0 +1,169 @@
+"""Pinning the oracle's spectral operator (oracle_solver.cpp: orc_G_K_dF, green_entry, phase
+ramp) without the reference binary:
+
+  * an INDEPENDENT numpy restatement that follows the reference literally -- stored Ghat4 table
+    (FFT_init.f:272-340), fftshift phase ramp coeffs1/2 (FFT_init.f:354-385), full complex 3-D
+    transforms with split re/im contraction and "keep the real part" (G_K_dF.f:11-227);
+  * the projection identities the Green operator must satisfy for odd N;
+  * the documented even-N convention (Nyquist planes zeroed; the reference itself is wrong
+    for even N).
+"""
+import numpy as np
+import pytest
+
+from helpers import deck
+
+
+@pytest.fixture(scope="module")
+def Oracle(oracle_built):
+    from oracle import Oracle
+    return Oracle
+
+
+# ---------------------------------------------------------------------------------------------
+# literal numpy restatement of the reference
+def ref_indices():
+    """indices(4,81) of formG: column m = 27 i + 9 j + 3 k + l (FFT_init.f:283-304)."""
+    m = np.arange(81)
+    return m // 27, (m // 9) % 3, (m // 3) % 3, m % 3
+
+
+def ref_formG(N):
+    Nhalf = (N + 1) // 2 if N % 2 == 1 else N // 2 + 1
+    r = np.arange(1, N + 1) - Nhalf
+    q = np.stack(np.meshgrid(r, r, r, indexing="ij"), axis=-1).reshape(-1, 3).astype(float)  # ii slowest, kk fastest
+    qq = (q * q).sum(axis=1)
+    G = np.zeros((N ** 3, 81))
+    i, j, k, l = ref_indices()
+    for m in range(81):
+        if i[m] == k[m]:
+            G[:, m] = q[:, j[m]] * q[:, l[m]]
+    zero = np.abs(qq) <= 1e-10
+    G[zero] = 0.0
+    G[~zero] /= qq[~zero, None]
+    return G
+
+
+def ref_shift(N):
+    Nhalf = (N + 1) // 2 if N % 2 == 1 else N // 2 + 1
+    NhN = Nhalf * 2.0 * np.pi / N
+    a = np.arange(N)
+    s = a[:, None, None] + a[None, :, None] + a[None, None, :]
+    return np.cos(NhN * s).ravel(), -np.sin(NhN * s).ravel()
+
+
+def ref_ddot42n(A4, B2):
+    """C2(:,i) = sum_j A4(:,9 i + j) B2(:,j) (G_K_dF.f:241-268); A4 (N3,81), B2 (N3,9)."""
+    return np.einsum("eij,ej->ei", A4.reshape(-1, 9, 9), B2)
+
+
+def ref_G_K_dF(N, F, K4=None):
+    """F (9,N3) -> (9,N3), exactly the data flow of G_K_dF.f:11-87."""
+    c1, c2 = ref_shift(N)
+    G = ref_formG(N)
+    x = F.T if K4 is None else ref_ddot42n(K4.T, F.T)         # (N3, 9)
+    re, im = np.empty_like(x), np.empty_like(x)
+    for c in range(9):                                         # fftfem3d
+        z = np.fft.fftn((x[:, c] * c1 + 1j * x[:, c] * c2).reshape(N, N, N))
+        re[:, c], im[:, c] = z.real.ravel(), z.imag.ravel()
+    gre, gim = ref_ddot42n(G, re), ref_ddot42n(G, im)          # Ghat is real
+    out = np.empty_like(x)
+    for c in range(9):                                         # ifftfem3d: re*c1 + im*c2
+        z = np.fft.ifftn((gre[:, c] + 1j * gim[:, c]).reshape(N, N, N))
+        out[:, c] = z.real.ravel() * c1 + z.imag.ravel() * c2
+    return out.T
+
+
+# ---------------------------------------------------------------------------------------------
+def _toy_problem(N):
+    from cpfft_b200.problem import Problem, Material
+    mats = [Material(name="a", type=1, e=12000.0, nu=0.3, beta=0.5, tan_e=1000.0, yld_pt=100.0),
+            Material(name="b", type=1, e=24000.0, nu=0.3, beta=0.5, tan_e=1000.0, yld_pt=200.0)]
+    rng = np.random.default_rng(N)
+    ml = rng.integers(1, 3, N ** 3).astype(np.int32)
+    return Problem(N=N, materials=mats, crystals=[], matlist=ml, angles=np.zeros((N ** 3, 3)),
+                   FP_max=np.zeros(9), mults=np.ones(1))
+
+
+@pytest.mark.parametrize("N", [3, 5, 7, 9])
+def test_formG_entries_match_reference_table(Oracle, N):
+    G = ref_formG(N)
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        ii, jj, kk = rng.integers(0, N, 3)
+        e = (ii * N + jj) * N + kk
+        assert np.array_equal(Oracle.formG_entry(N, int(ii), int(jj), int(kk)), G[e])
+
+
+@pytest.mark.parametrize("N", [5, 7])
+def test_G_K_dF_matches_numpy_restatement(Oracle, N):
+    p = _toy_problem(N)
+    o = Oracle(p)
+    rng = np.random.default_rng(3)
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += 0.02 * rng.standard_normal((9, p.N3))
+    o.Fn1[:] = F
+    o.drive_eps_sig(1, 1)                      # heterogeneous K4
+    x = rng.standard_normal((9, p.N3))
+    for flgK in (0, 1):
+        got = o.G_K_dF(x, flgK)
+        want = ref_G_K_dF(N, x, o.K4.copy() if flgK else None)
+        assert np.abs(got - want).max() <= 2e-13 * np.abs(want).max()
+
+
+def test_G_K_dF_on_shipped_deck(Oracle):
+    """N = 7 bicrystal of test_mm10.in, K4 from a real mm10 sweep."""
+    p = deck("test_mm10.in")
+    o = Oracle(p)
+    rng = np.random.default_rng(5)
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += 0.002 * rng.standard_normal((9, p.N3))
+    o.drive_eps_sig(1, 0)
+    o.Fn1[:] = F
+    assert o.drive_eps_sig(1, 1) == 0
+    x = rng.standard_normal((9, p.N3))
+    want = ref_G_K_dF(7, x, o.K4.copy())
+    assert np.abs(o.G_K_dF(x, 1) - want).max() <= 2e-13 * np.abs(want).max()
+
+
+def _grad_field(N, rng, kmax):
+    """gradient of a periodic, band-limited displacement field, F_ij = d u_i / d X_j"""
+    a = np.arange(N)
+    X = np.stack(np.meshgrid(a, a, a, indexing="ij"), axis=0).astype(float)  # X[0] = x index (slowest)
+    grad = np.zeros((3, 3, N, N, N))
+    for _ in range(6):
+        k = rng.integers(-kmax, kmax + 1, 3)
+        if not k.any():
+            continue
+        ph = 2 * np.pi * (k[0] * X[0] + k[1] * X[1] + k[2] * X[2]) / N + rng.uniform(0, 2 * np.pi)
+        amp = rng.standard_normal(3)
+        for i in range(3):
+            for j in range(3):
+                grad[i, j] += amp[i] * (2 * np.pi * k[j] / N) * np.cos(ph)
+    return grad.reshape(9, -1)
+
+
+@pytest.mark.parametrize("N", [5, 7, 6, 8])
+def test_green_projection_identities(Oracle, N):
+    """Ghat:grad(u) = grad(u), Ghat:const = 0, idempotence, self-adjointness.  For even N the
+    identities hold on fields without Nyquist content (documented convention)."""
+    o = Oracle(_toy_problem(N))
+    rng = np.random.default_rng(N)
+    g = _grad_field(N, rng, kmax=(N - 1) // 2)
+    assert np.abs(o.G_K_dF(g, 0) - g).max() <= 1e-12 * np.abs(g).max()
+    const = np.repeat(rng.standard_normal((9, 1)), N ** 3, axis=1)
+    assert np.abs(o.G_K_dF(const, 0)).max() <= 1e-12
+    x, y = rng.standard_normal((9, N ** 3)), rng.standard_normal((9, N ** 3))
+    Gx, Gy = o.G_K_dF(x, 0), o.G_K_dF(y, 0)
+    assert np.abs(o.G_K_dF(Gx, 0) - Gx).max() <= 1e-12 * np.abs(Gx).max()
+    assert abs((Gx * y).sum() - (x * Gy).sum()) <= 1e-11 * np.abs(x).max() * np.abs(y).max() * N ** 3
+
+
+def test_reference_table_is_broken_for_even_N():
+    """the literal reference operator is not a projection for even N, which
+    is why even grids use the corrected convention instead of the reference's table."""
+    rng = np.random.default_rng(0)
+    for N, ok in ((5, True), (6, False)):
+        g = _grad_field(N, rng, kmax=1)
+        err = np.abs(ref_G_K_dF(N, g) - g).max() / np.abs(g).max()
+        assert (err <= 1e-12) == ok
