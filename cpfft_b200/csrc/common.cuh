@@ -62,7 +62,8 @@ struct cpfft_handle {
   std::vector<CpfProfEvt> prof_live;
   std::vector<CpfProfEvt> prof_pool;
   double prof_ms[CPF_K_NUM]; int64_t prof_cnt[CPF_K_NUM];
-  int N, Nh;                 // Nh = N/2+1 (half spectrum along z)
+  int N, Nh;                 // Nh = stored kz bins: N/2+1, or N/2 on the power-of-two path
+  bool fast_pow2;            // spectral_pow2.cu handles this grid
   int nxloc, x0;             // local slab
   int64_t n3;                // local voxels
   int H;                     // history comps
@@ -118,6 +119,10 @@ CpfHistLayout cpf_hist_layout(int nslip, int num_hard);
 int cpf_spectral_init(cpfft_handle* h);
 void cpf_spectral_free(cpfft_handle* h);
 int cpf_apply_G(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out);
+// spectral_pow2.cu
+bool cpf_pow2_supported(int N);
+int cpf_pow2_init(cpfft_handle* h);
+int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out);
 
 // reduce.cu helpers (solver.cu)
 int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out);

@@ -1,0 +1,165 @@
+// cpfft_b200: register-resident radix-2/4/8/16 butterflies and in-place shared-memory FFT stages
+// for power-of-two line lengths (the 256^3 / 512^3 benchmark grids; everything else goes
+// through the generic Stockham path in spectral.cu).
+//
+// Decomposition of an N-point line, N = R1 R2 [R3]: decimation in frequency, every stage in
+// place.  Stage with current sub-transform length Ns and radix R, M = Ns / R: task (q, t)
+// (q-th sub-transform, t in [0, M)) owns the R elements  q Ns + m M + t, m = 0..R-1, replaces
+// them by their R-point DFT (index m -> output digit k) and multiplies output k by w_Ns^(t k).
+// After the last stage position p = k1 (N/R1) + k2 (N/(R1 R2)) + k3 holds X[k1 + R1 k2 + R1 R2 k3]
+// ("digit-reversed").  The inverse runs the transposed flow (conjugate twiddle, then the
+// conjugate butterfly, stages in reverse order) and takes digit-reversed input back to natural
+// order, so a forward -> pointwise -> inverse chain never reorders anything.
+//
+// The same source compiles for the host (tests/fft_core_host_test.cpp, plain g++) so the
+// index algebra is verified on the CPU build box.
+#pragma once
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define FHD __host__ __device__ __forceinline__
+#else
+#include <cmath>
+#define FHD inline
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+#endif
+
+typedef double2 cplx;
+
+FHD cplx c_add(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+FHD cplx c_sub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+FHD cplx c_mul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+FHD cplx c_mulc(cplx a, cplx b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a conj(b)
+FHD cplx c_conj(cplx a) { return make_double2(a.x, -a.y); }
+// multiply by -i (DIR = -1, forward) or +i (DIR = +1, inverse)
+template <int DIR> FHD cplx c_rot(cplx a) { return DIR < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x); }
+
+template <int R, int DIR> struct Dft;
+
+template <int DIR> struct Dft<1, DIR> { static FHD void run(cplx*) {} };
+template <int DIR> struct Dft<2, DIR> {
+  static FHD void run(cplx* v) { cplx a = v[0], b = v[1]; v[0] = c_add(a, b); v[1] = c_sub(a, b); }
+};
+template <int DIR> struct Dft<4, DIR> {
+  static FHD void run(cplx* v) {
+    const cplx t0 = c_add(v[0], v[2]), t1 = c_sub(v[0], v[2]), t2 = c_add(v[1], v[3]);
+    const cplx t3 = c_rot<DIR>(c_sub(v[1], v[3]));
+    v[0] = c_add(t0, t2); v[2] = c_sub(t0, t2); v[1] = c_add(t1, t3); v[3] = c_sub(t1, t3);
+  }
+};
+template <int DIR> struct Dft<8, DIR> {
+  static FHD void run(cplx* v) {
+    const double h = 0.70710678118654752440;
+    cplx e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4, DIR>::run(e); Dft<4, DIR>::run(o);
+    // w8^k o[k]: forward w8 = (1 - i)/sqrt2, inverse its conjugate
+    const cplx o1 = DIR < 0 ? make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x))
+                            : make_double2(h * (o[1].x - o[1].y), h * (o[1].y + o[1].x));
+    const cplx o2 = c_rot<DIR>(o[2]);
+    const cplx o3 = DIR < 0 ? make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y))
+                            : make_double2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y));
+    v[0] = c_add(e[0], o[0]); v[4] = c_sub(e[0], o[0]);
+    v[1] = c_add(e[1], o1);   v[5] = c_sub(e[1], o1);
+    v[2] = c_add(e[2], o2);   v[6] = c_sub(e[2], o2);
+    v[3] = c_add(e[3], o3);   v[7] = c_sub(e[3], o3);
+  }
+};
+template <int DIR> struct Dft<16, DIR> {
+  static FHD void run(cplx* v) {
+    // 4 x 4: n = 4 a + b, k = k1 + 4 k2
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    cplx y[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      cplx t[4] = {v[b], v[4 + b], v[8 + b], v[12 + b]};
+      Dft<4, DIR>::run(t);
+#pragma unroll
+      for (int k1 = 0; k1 < 4; ++k1) y[b][k1] = t[k1];
+    }
+    // twiddle w16^(b k1); w16^m = cos(m pi/8) -/+ i sin(m pi/8)
+    const double wr[10] = {1.0, c1, h, s1, 0.0, -s1, -h, -c1, -1.0, -c1};
+    const double wi[10] = {0.0, s1, h, c1, 1.0, c1, h, s1, 0.0, -s1};
+#pragma unroll
+    for (int b = 1; b < 4; ++b)
+#pragma unroll
+      for (int k1 = 1; k1 < 4; ++k1) {
+        const int m = b * k1;  // <= 9
+        const cplx w = make_double2(wr[m], DIR < 0 ? -wi[m] : wi[m]);
+        y[b][k1] = c_mul(y[b][k1], w);
+      }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+      cplx t[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+      Dft<4, DIR>::run(t);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = t[k2];
+    }
+  }
+};
+
+// compile-time plan of an N-point transform
+template <int N> struct FftPlan;
+template <> struct FftPlan<8>   { static constexpr int R1 = 8,  R2 = 1,  R3 = 1; };
+template <> struct FftPlan<16>  { static constexpr int R1 = 16, R2 = 1,  R3 = 1; };
+template <> struct FftPlan<32>  { static constexpr int R1 = 8,  R2 = 4,  R3 = 1; };
+template <> struct FftPlan<64>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct FftPlan<128> { static constexpr int R1 = 16, R2 = 8,  R3 = 1; };
+template <> struct FftPlan<256> { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
+template <> struct FftPlan<512> { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
+
+// position (after the forward stages) <-> natural frequency index
+template <int N> FHD int fft_natural(int p) {
+  typedef FftPlan<N> P;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  const int k1 = p / N1, r = p - k1 * N1;
+  const int k2 = r / N2, k3 = r - k2 * N2;
+  return k1 + P::R1 * (k2 + P::R2 * k3);
+}
+template <int N> FHD int fft_position(int k) {
+  typedef FftPlan<N> P;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  const int k1 = k % P::R1, r = k / P::R1;
+  const int k2 = r % P::R2, k3 = r / P::R2;
+  return k1 * N1 + k2 * N2 + k3;
+}
+
+// One task of a forward (DIF) stage.  A: element accessor with  cplx& A(int i)  semantics given
+// through load/store functors so that the first stage can read global memory and the last one
+// can write it.  tw[j] = exp(-2 pi i j / NT), TWS = NT / Ns (table stride of this stage).
+template <int Ns, int R, int DIR, int TWS, class LoadF, class StoreF>
+FHD void fft_stage_dif(int task, const cplx* tw, LoadF ld, StoreF st) {
+  constexpr int M = Ns / R;
+  const int q = task / M, t = task - q * M;
+  const int base = q * Ns + t;
+  cplx v[R];
+#pragma unroll
+  for (int m = 0; m < R; ++m) v[m] = ld(base + m * M);
+  Dft<R, DIR>::run(v);
+  if (M > 1) {
+#pragma unroll
+    for (int k = 1; k < R; ++k) {
+      const cplx w = tw[TWS * t * k];
+      v[k] = DIR < 0 ? c_mul(v[k], w) : c_mulc(v[k], w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) st(base + k * M, v[k]);
+}
+// One task of an inverse (DIT, transposed) stage: conjugate twiddle first, then the butterfly.
+template <int Ns, int R, int TWS, class LoadF, class StoreF>
+FHD void fft_stage_dit_inv(int task, const cplx* tw, LoadF ld, StoreF st) {
+  constexpr int M = Ns / R;
+  const int q = task / M, t = task - q * M;
+  const int base = q * Ns + t;
+  cplx v[R];
+#pragma unroll
+  for (int m = 0; m < R; ++m) v[m] = ld(base + m * M);
+  if (M > 1) {
+#pragma unroll
+    for (int k = 1; k < R; ++k) v[k] = c_mulc(v[k], tw[TWS * t * k]);
+  }
+  Dft<R, +1>::run(v);
+#pragma unroll
+  for (int k = 0; k < R; ++k) st(base + k * M, v[k]);
+}

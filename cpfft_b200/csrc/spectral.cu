@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 typedef double2 cplx;
 
@@ -245,6 +246,8 @@ static int pick_tz(int N, int lines_per_tz, int Nh) {
 
 int cpf_spectral_init(cpfft_handle* h) {
   const int N = h->N;
+  h->fast_pow2 = cpf_pow2_supported(N) && (getenv("CPFFT_GENERIC_FFT") == nullptr);
+  if (h->fast_pow2) h->Nh = N / 2;   // the Nyquist bin is never stored (Ghat = 0 there)
   choose_radices(N, h->radices, &h->nrad);
   std::vector<cplx> tw(N);
   for (int k = 0; k < N; ++k) {
@@ -266,6 +269,7 @@ int cpf_spectral_init(cpfft_handle* h) {
   CPF_CUDA(cudaFuncSetAttribute(k_inv_z, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CPF_CUDA(cudaFuncSetAttribute(k_fft_y, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CPF_CUDA(cudaFuncSetAttribute(k_x_green, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (h->fast_pow2) return cpf_pow2_init(h);
   return 0;
 }
 
@@ -282,6 +286,7 @@ int cpf_exchange_bwd(cpfft_handle* h);
 
 // dst = scale_out * IFFT3( Ghat : FFT3( flgK ? K4:src : src ) ) / N^3
 int cpf_apply_G(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out) {
+  if (h->fast_pow2) return cpf_apply_G_pow2(h, src, dst, flgK, scale_out);
   const int N = h->N, Nh = h->Nh, nx = h->nxloc;
   SpecArgs g;
   g.N = N; g.Nh = Nh; g.nx = nx; g.x0 = h->x0; g.nrad = h->nrad; g.rad = h->d_radices; g.tw = h->tw; g.n3 = h->n3;

@@ -1,0 +1,421 @@
+// cpfft_b200: fast path of the spectral operator G_K_dF (G_K_dF.f:11-87) for power-of-two grids
+// (N = 16 .. 512; the 256^3 / 512^3 benchmark grids).  Same mathematics as spectral.cu, built
+// from the register butterflies of fft_core.cuh:
+//
+//   k_fz  : [K4 : x contraction fused on load] two real z lines per CTA, each packed as an N/2
+//           complex line (even/odd samples), N/2-point FFT, untangled to bins kz = 0..N/2-1.
+//           The Nyquist bin is never stored: the even-N convention zeroes Ghat there.
+//   k_fy  : y lines (forward or inverse), tile of TZ consecutive kz per CTA; first stage loads
+//           from global memory, last stage stores to it, one shared-memory exchange between.
+//   k_fx  : x forward -> Ghat contraction from integer frequencies -> x inverse, one tensor row
+//           (3 components) x TZ kz per CTA; the spectrum stays digit-reversed in shared memory
+//           between the two transforms, so nothing is reordered.
+//   k_iz  : half-spectrum lines -> packed N/2 inverse transform -> two real samples per thread.
+//
+// Spectrum layout: spec[((c * NX + x) * NY + y) * NZ + kz], NZ = N/2, complex double.
+#include "common.cuh"
+#include "fft_core.cuh"
+
+struct Pow2Args {
+  int nx;        // local x planes (z / y passes)
+  int NY, y0;    // x pass: local y extent and its global offset (slab-transposed layout)
+  int64_t n3;    // local voxels
+  const cplx* tw;  // exp(-2 pi i k / N), k < N
+};
+
+template <int N> struct Pow2Cfg {
+  static constexpr int H = N / 2;
+  static constexpr int TZY = (H < 16 ? H : 16) < (4096 / N) ? (H < 16 ? H : 16) : (4096 / N);
+  static constexpr int TZX = (H < 8 ? H : 8) < (2048 / N) ? (H < 8 ? H : 8) : (2048 / N);
+};
+
+template <int N> __device__ __forceinline__ constexpr int last_radix() {
+  return FftPlan<N>::R3 > 1 ? FftPlan<N>::R3 : (FftPlan<N>::R2 > 1 ? FftPlan<N>::R2 : FftPlan<N>::R1);
+}
+
+// all stages of an in-place transform over `nlines` lines held in shared memory through the
+// accessor a(line, i); tasks are dealt round-robin to the CTA's threads
+// (TWM = twiddle table length / N)
+template <int N, int DIR, int TWM, class Acc>
+__device__ __forceinline__ void smem_fft_dif(int nlines, const cplx* tw, Acc a) {
+  typedef FftPlan<N> P;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  for (int task = threadIdx.x; task < nlines * (N / P::R1); task += blockDim.x) {
+    const int line = task / (N / P::R1), j = task - line * (N / P::R1);
+    fft_stage_dif<N, P::R1, DIR, TWM>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
+  }
+  __syncthreads();
+  if (P::R2 > 1) {
+    for (int task = threadIdx.x; task < nlines * (N / P::R2); task += blockDim.x) {
+      const int line = task / (N / P::R2), j = task - line * (N / P::R2);
+      fft_stage_dif<N1, P::R2, DIR, TWM * (N / N1)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
+    }
+    __syncthreads();
+  }
+  if (P::R3 > 1) {
+    for (int task = threadIdx.x; task < nlines * (N / P::R3); task += blockDim.x) {
+      const int line = task / (N / P::R3), j = task - line * (N / P::R3);
+      fft_stage_dif<N2, P::R3, DIR, TWM * (N / N2)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
+    }
+    __syncthreads();
+  }
+}
+template <int N, int TWM, class Acc>
+__device__ __forceinline__ void smem_fft_dit_inv(int nlines, const cplx* tw, Acc a) {
+  typedef FftPlan<N> P;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  if (P::R3 > 1) {
+    for (int task = threadIdx.x; task < nlines * (N / P::R3); task += blockDim.x) {
+      const int line = task / (N / P::R3), j = task - line * (N / P::R3);
+      fft_stage_dit_inv<N2, P::R3, TWM * (N / N2)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
+    }
+    __syncthreads();
+  }
+  if (P::R2 > 1) {
+    for (int task = threadIdx.x; task < nlines * (N / P::R2); task += blockDim.x) {
+      const int line = task / (N / P::R2), j = task - line * (N / P::R2);
+      fft_stage_dit_inv<N1, P::R2, TWM * (N / N1)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
+    }
+    __syncthreads();
+  }
+  for (int task = threadIdx.x; task < nlines * (N / P::R1); task += blockDim.x) {
+    const int line = task / (N / P::R1), j = task - line * (N / P::R1);
+    fft_stage_dit_inv<N, P::R1, TWM>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// z passes.  Shared memory: 18 packed lines (2 grid lines x 9 components) of H complex, padded
+// by one slot per `RL` (last radix) so that the stride-RL accesses of the last stage spread
+// over the banks; followed by the twiddle table of the FULL length N (the H-point transform
+// uses every second entry).
+template <int N> struct ZSmem {
+  static constexpr int H = N / 2;
+  static constexpr int RL = last_radix<H>();
+  static constexpr int HP = H + H / RL;
+  static __device__ __forceinline__ int pad(int i) { return i + i / RL; }
+  static constexpr size_t bytes = sizeof(cplx) * (18 * HP + N);
+};
+
+template <int N, bool WITH_K4>
+__global__ void __launch_bounds__(N) k_fz(Pow2Args g, const double* __restrict__ src, const double* __restrict__ K4,
+                                          cplx* __restrict__ spec) {
+  typedef ZSmem<N> Z;
+  constexpr int H = Z::H;
+  extern __shared__ cplx sm[];
+  cplx* zb = sm;
+  cplx* tw = sm + 18 * Z::HP;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  const int64_t n3 = g.n3;
+  const int l = threadIdx.x / H, t = threadIdx.x - l * H;
+  const int64_t L = (int64_t)2 * blockIdx.x + l;          // grid line x * N + y
+  const int64_t e0 = L * N + 2 * t;
+  {
+    double2 f[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) f[c] = *reinterpret_cast<const double2*>(src + c * n3 + e0);
+    if (WITH_K4) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        double2 a[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) a[j] = *reinterpret_cast<const double2*>(K4 + (int64_t)(9 * i + j) * n3 + e0);
+        double ta[9], tb[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { ta[j] = __dmul_rn(a[j].x, f[j].x); tb[j] = __dmul_rn(a[j].y, f[j].y); }
+        // ddot42n's summation tree (G_K_dF.f:258-264)
+        const double va = ta[0] + (((ta[1] + ta[5]) + (ta[3] + ta[7])) + ((ta[2] + ta[6]) + (ta[4] + ta[8])));
+        const double vb = tb[0] + (((tb[1] + tb[5]) + (tb[3] + tb[7])) + ((tb[2] + tb[6]) + (tb[4] + tb[8])));
+        zb[(l * 9 + i) * Z::HP + Z::pad(t)] = make_double2(va, vb);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) zb[(l * 9 + c) * Z::HP + Z::pad(t)] = f[c];
+    }
+  }
+  __syncthreads();
+  // the H-point transform uses w_H^j = w_N^(2j): table stride multiplier 2
+  smem_fft_dif<H, -1, 2>(18, tw, [&](int line, int i) -> cplx& { return zb[line * Z::HP + Z::pad(i)]; });
+  // untangle: X[k] = (E + w_N^k O), E = (Z[k] + conj Z[H-k]) / 2, O = (Z[k] - conj Z[H-k]) / (2 i)
+  const int64_t nxN = (int64_t)g.nx * N;
+  for (int idx = threadIdx.x; idx < 18 * H; idx += blockDim.x) {
+    const int lc = idx / H, k = idx - lc * H;
+    const int ll = lc / 9, c = lc - ll * 9;
+    const cplx* line = zb + lc * Z::HP;
+    const cplx Zk = line[Z::pad(fft_position<H>(k))];
+    const cplx Zm = c_conj(line[Z::pad(fft_position<H>((H - k) & (H - 1)))]);
+    const cplx E = c_add(Zk, Zm), D = c_sub(Zk, Zm);
+    const cplx O = c_mul(make_double2(D.y, -D.x), tw[k]);
+    spec[((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H + k] = make_double2(0.5 * (E.x + O.x), 0.5 * (E.y + O.y));
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale) {
+  typedef ZSmem<N> Z;
+  constexpr int H = Z::H;
+  extern __shared__ cplx sm[];
+  cplx* zb = sm;
+  cplx* tw = sm + 18 * Z::HP;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  __syncthreads();
+  const int64_t nxN = (int64_t)g.nx * N;
+  // tangle: Z'[k] = (X[k] + conj X[H-k]) + i w_N^-k (X[k] - conj X[H-k]), X[H] = 0, X[0] real
+  for (int idx = threadIdx.x; idx < 18 * H; idx += blockDim.x) {
+    const int lc = idx / H, k = idx - lc * H;
+    const int ll = lc / 9, c = lc - ll * 9;
+    const cplx* row = spec + ((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H;
+    cplx Xk = row[k], Xm;
+    if (k == 0) { Xk.y = 0.0; Xm = make_double2(0.0, 0.0); }
+    else Xm = c_conj(row[H - k]);
+    const cplx E = c_add(Xk, Xm), D = c_sub(Xk, Xm);
+    const cplx O = c_mulc(D, tw[k]);
+    zb[lc * Z::HP + Z::pad(fft_position<H>(k))] = make_double2(E.x - O.y, E.y + O.x);
+  }
+  __syncthreads();
+  smem_fft_dit_inv<H, 2>(18, tw, [&](int line, int i) -> cplx& { return zb[line * Z::HP + Z::pad(i)]; });
+  const int l = threadIdx.x / H, t = threadIdx.x - l * H;
+  const int64_t e0 = ((int64_t)2 * blockIdx.x + l) * N + 2 * t;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const cplx z = zb[(l * 9 + c) * Z::HP + Z::pad(t)];
+    *reinterpret_cast<double2*>(dst + c * g.n3 + e0) = make_double2(z.x * scale, z.y * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y pass, in place.  grid = (9 * nx, NZ / TZ).  Shared memory s[i * TZ + l] (+ twiddles).
+template <int N, int DIR>
+__global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec) {
+  typedef FftPlan<N> P;
+  constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZY;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  extern __shared__ cplx sm[];
+  cplx* s = sm;
+  cplx* tw = sm + N * TZ;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  __syncthreads();
+  cplx* G = spec + (int64_t)blockIdx.x * N * H + blockIdx.y * TZ;
+  constexpr bool single = (P::R2 == 1);
+  for (int task = threadIdx.x; task < TZ * (N / P::R1); task += blockDim.x) {
+    const int j = task / TZ, l = task - j * TZ;
+    if (single)
+      fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return G[(int64_t)i * H + l]; },
+                                      [&](int i, cplx v) { G[(int64_t)fft_natural<N>(i) * H + l] = v; });
+    else
+      fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return G[(int64_t)i * H + l]; },
+                                      [&](int i, cplx v) { s[i * TZ + l] = v; });
+  }
+  if (single) return;
+  __syncthreads();
+  constexpr bool two = (P::R3 == 1);
+  for (int task = threadIdx.x; task < TZ * (N / P::R2); task += blockDim.x) {
+    const int j = task / TZ, l = task - j * TZ;
+    if (two)
+      fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; },
+                                            [&](int i, cplx v) { G[(int64_t)fft_natural<N>(i) * H + l] = v; });
+    else
+      fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; },
+                                            [&](int i, cplx v) { s[i * TZ + l] = v; });
+  }
+  if (two) return;
+  __syncthreads();
+  for (int task = threadIdx.x; task < TZ * (N / P::R3); task += blockDim.x) {
+    const int j = task / TZ, l = task - j * TZ;
+    fft_stage_dif<N2, P::R3, DIR, N / N2>(j, tw, [&](int i) { return s[i * TZ + l]; },
+                                          [&](int i, cplx v) { G[(int64_t)fft_natural<N>(i) * H + l] = v; });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x pass: forward, Green operator, inverse.  grid = (NY, NZ / TZ, 3 tensor rows).
+// Shared memory s[(cl * N + i) * TZ + l], cl = component within the row.
+template <int N>
+__global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec) {
+  typedef FftPlan<N> P;
+  constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZX;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  extern __shared__ cplx sm[];
+  cplx* s = sm;
+  cplx* tw = sm + 3 * N * TZ;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  __syncthreads();
+  const int y = blockIdx.x, kz0 = blockIdx.y * TZ, row = blockIdx.z;
+  const int64_t xs = (int64_t)g.NY * H;                       // stride between x planes
+  cplx* G = spec + ((int64_t)(3 * row) * N * g.NY + y) * H + kz0;   // + (cl * N + x) * xs + l
+  // ---- forward: stage 1 from global memory ----
+  for (int task = threadIdx.x; task < 3 * TZ * (N / P::R1); task += blockDim.x) {
+    const int l = task % TZ, r = task / TZ;
+    const int j = r % (N / P::R1), cl = r / (N / P::R1);
+    cplx* sc = s + cl * N * TZ + l;
+    const cplx* gc = G + (int64_t)cl * N * xs + l;
+    fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return gc[(int64_t)i * xs]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+  }
+  __syncthreads();
+  if (P::R2 > 1) {
+    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R2); task += blockDim.x) {
+      const int l = task % TZ, r = task / TZ;
+      const int j = r % (N / P::R2), cl = r / (N / P::R2);
+      cplx* sc = s + cl * N * TZ + l;
+      fft_stage_dif<N1, P::R2, -1, N / N1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    }
+    __syncthreads();
+  }
+  if (P::R3 > 1) {
+    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R3); task += blockDim.x) {
+      const int l = task % TZ, r = task / TZ;
+      const int j = r % (N / P::R3), cl = r / (N / P::R3);
+      cplx* sc = s + cl * N * TZ + l;
+      fft_stage_dif<N2, P::R3, -1, N / N2>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    }
+    __syncthreads();
+  }
+  // ---- Green operator on the row: out_j = xi_j (sum_l tau_l xi_l) / |xi|^2 (FFT_init.f:321-335),
+  //      zero at xi = 0 and on the Nyquist planes (even-N convention) ----
+  {
+    const int ky = y + g.y0;
+    const double fy = (double)(ky < H ? ky : ky - N);
+    for (int idx = threadIdx.x; idx < N * TZ; idx += blockDim.x) {
+      const int l = idx % TZ, p = idx / TZ;
+      const int kx = fft_natural<N>(p);
+      const double fx = (double)(kx < H ? kx : kx - N), fz = (double)(kz0 + l);
+      const double qq = fx * fx + fy * fy + fz * fz;
+      const bool zero = (kx == H) || (ky == H) || (fabs(qq) <= 1e-10);
+      cplx* a = s + p * TZ + l;
+      const cplx t0 = a[0], t1 = a[N * TZ], t2 = a[2 * N * TZ];
+      double sr = 0.0, si = 0.0;
+      if (!zero) {
+        const double iq = 1.0 / qq;
+        sr = (t0.x * fx + t1.x * fy + t2.x * fz) * iq;
+        si = (t0.y * fx + t1.y * fy + t2.y * fz) * iq;
+      }
+      a[0] = make_double2(fx * sr, fx * si);
+      a[N * TZ] = make_double2(fy * sr, fy * si);
+      a[2 * N * TZ] = make_double2(fz * sr, fz * si);
+    }
+  }
+  __syncthreads();
+  // ---- inverse: transposed flow, last stage stores to global memory in natural order ----
+  if (P::R3 > 1) {
+    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R3); task += blockDim.x) {
+      const int l = task % TZ, r = task / TZ;
+      const int j = r % (N / P::R3), cl = r / (N / P::R3);
+      cplx* sc = s + cl * N * TZ + l;
+      fft_stage_dit_inv<N2, P::R3, N / N2>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    }
+    __syncthreads();
+  }
+  if (P::R2 > 1) {
+    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R2); task += blockDim.x) {
+      const int l = task % TZ, r = task / TZ;
+      const int j = r % (N / P::R2), cl = r / (N / P::R2);
+      cplx* sc = s + cl * N * TZ + l;
+      fft_stage_dit_inv<N1, P::R2, N / N1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    }
+    __syncthreads();
+  }
+  for (int task = threadIdx.x; task < 3 * TZ * (N / P::R1); task += blockDim.x) {
+    const int l = task % TZ, r = task / TZ;
+    const int j = r % (N / P::R1), cl = r / (N / P::R1);
+    cplx* sc = s + cl * N * TZ + l;
+    cplx* gc = G + (int64_t)cl * N * xs + l;
+    fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { gc[(int64_t)i * xs] = v; });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+int cpf_exchange_fwd(cpfft_handle* h);   // solver.cu (NCCL transposes)
+int cpf_exchange_bwd(cpfft_handle* h);
+
+template <int N>
+static int apply_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out) {
+  constexpr int H = N / 2, TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
+  typedef FftPlan<N> P;
+  const int nx = h->nxloc, world = h->cfg.world;
+  Pow2Args g;
+  g.nx = nx; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
+  const size_t sm_z = ZSmem<N>::bytes;
+  const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
+  const unsigned zgrid = (unsigned)(nx * N / 2);
+  int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
+  if (flgK) k_fz<N, true><<<zgrid, N, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a);
+  else k_fz<N, false><<<zgrid, N, sm_z, h->stream>>>(g, src, nullptr, h->spec_a);
+  cpf_prof_end(h, tk);
+  constexpr int RminY = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
+  constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
+  constexpr int thr_x = (3 * TZX * (N / RminY)) > 512 ? 512 : (3 * TZX * (N / RminY) < 32 ? 32 : 3 * TZX * (N / RminY));
+  const dim3 gy(9 * nx, H / TZY);
+  tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+  k_fy<N, -1><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a);
+  cpf_prof_end(h, tk);
+  if (world == 1) {
+    const dim3 gx(N, H / TZX, 3);
+    tk = cpf_prof_begin(h, CPF_K_X_GREEN);
+    k_fx<N><<<gx, thr_x, sm_x, h->stream>>>(g, h->spec_a);
+    cpf_prof_end(h, tk);
+  } else {
+    int rc = cpf_exchange_fwd(h);
+    if (rc) return rc;
+    const int ny = N / world;
+    Pow2Args gt = g;
+    gt.NY = ny; gt.y0 = h->cfg.rank * ny;
+    const dim3 gx(ny, H / TZX, 3);
+    tk = cpf_prof_begin(h, CPF_K_X_GREEN);
+    k_fx<N><<<gx, thr_x, sm_x, h->stream>>>(gt, h->spec_b);
+    cpf_prof_end(h, tk);
+    rc = cpf_exchange_bwd(h);
+    if (rc) return rc;
+  }
+  tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+  k_fy<N, +1><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a);
+  cpf_prof_end(h, tk);
+  const double scale = scale_out / ((double)N * (double)N * (double)N);
+  tk = cpf_prof_begin(h, CPF_K_INV_Z);
+  k_iz<N><<<zgrid, N, sm_z, h->stream>>>(g, h->spec_a, dst, scale);
+  cpf_prof_end(h, tk);
+  h->launches += 5;
+  CPF_CUDA(cudaGetLastError());
+  h->n_apply++;
+  return 0;
+}
+
+template <int N>
+static int init_pow2(cpfft_handle* h) {
+  constexpr int TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
+  const size_t sm_z = ZSmem<N>::bytes;
+  const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
+  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_iz<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
+  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
+  CPF_CUDA(cudaFuncSetAttribute(k_fx<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  return 0;
+}
+int cpf_pow2_init(cpfft_handle* h) {
+  switch (h->N) {
+    case 16: return init_pow2<16>(h);
+    case 32: return init_pow2<32>(h);
+    case 64: return init_pow2<64>(h);
+    case 128: return init_pow2<128>(h);
+    case 256: return init_pow2<256>(h);
+    case 512: return init_pow2<512>(h);
+  }
+  return CPFFT_ERR_USAGE;
+}
+
+bool cpf_pow2_supported(int N) { return N == 16 || N == 32 || N == 64 || N == 128 || N == 256 || N == 512; }
+
+int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out) {
+  switch (h->N) {
+    case 16: return apply_pow2<16>(h, src, dst, flgK, scale_out);
+    case 32: return apply_pow2<32>(h, src, dst, flgK, scale_out);
+    case 64: return apply_pow2<64>(h, src, dst, flgK, scale_out);
+    case 128: return apply_pow2<128>(h, src, dst, flgK, scale_out);
+    case 256: return apply_pow2<256>(h, src, dst, flgK, scale_out);
+    case 512: return apply_pow2<512>(h, src, dst, flgK, scale_out);
+  }
+  cpf_set_error(h, "power-of-two spectral path called with an unsupported N");
+  return CPFFT_ERR_USAGE;
+}

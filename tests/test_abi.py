@@ -71,3 +71,18 @@ def test_usage_errors_without_device(lib):
     assert lib.cpfft_profile_classes() == 10
     names = [lib.cpfft_profile_name(i).decode() for i in range(10)]
     assert "k_x_green" in names and "k_update_mm10" in names
+
+
+def test_fortran_module_binds_every_symbol():
+    """cpfft_b200/fortran/cpfft_iso_c.f90 (not compilable here: no Fortran compiler) must at
+    least declare a bind(c) interface for every export and the same field ids as the header."""
+    f90 = open(os.path.join(ROOT, "cpfft_b200", "fortran", "cpfft_iso_c.f90")).read()
+    bound = sorted(set(re.findall(r"name='(cpfft_[A-Za-z0-9_]+)'", f90)))
+    assert bound == header_symbols()
+    hdr = open(os.path.join(ROOT, "include", "cpfft_b200.h")).read()
+    enum = re.search(r"typedef enum \{(.*?)\} cpfft_field;", hdr, flags=re.S).group(1)
+    enum = re.sub(r"/\*.*?\*/", "", enum, flags=re.S)
+    names = [n.strip().split("=")[0].strip() for n in enum.split(",") if n.strip()]
+    names = [n for n in names if n != "CPFFT_NUM_FIELDS"]
+    for i, n in enumerate(names):
+        assert re.search(rf"\b{n} = {i}\b", f90), (n, i)
