@@ -123,6 +123,7 @@ int cpf_apply_G(cpfft_handle* h, const double* src, double* dst, bool flgK, doub
 bool cpf_pow2_supported(int N);
 int cpf_pow2_init(cpfft_handle* h);
 int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out);
+int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts);
 
 // reduce.cu helpers (solver.cu)
 int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out);

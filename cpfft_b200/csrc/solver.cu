@@ -96,8 +96,11 @@ __global__ void k_dot_partial(const double* x, const double* y, int64_t n, doubl
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
-// x += a p ; r -= a q ; partial of r.r
-__global__ void k_cg_update(double* x, double* r, const double* p, const double* q, double a, int64_t n, double* partials) {
+// x += a p ; r -= a q ; partial of r.r, with a = rr / (p.q) and p.q read from device memory
+// (it was reduced on the device by the previous kernels, no host round trip)
+__global__ void k_cg_update(double* x, double* r, const double* p, const double* q, double rr, const double* pq,
+                            int64_t n, double* partials) {
+  const double a = rr / *pq;
   double s = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     x[i] += a * p[i];
@@ -302,7 +305,10 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   CPF_CUDA(cudaMemsetAsync(h->d_failcnt, 0, sizeof(int) * 2, h->stream));
   CPF_CUDA(cudaMemsetAsync(h->d_liters, 0, sizeof(int32_t) * 2 * h->n3, h->stream));
   h->nblocks_red = g_num_sms * 8;
-  CPF_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * 16 * h->nblocks_red));
+  {  // per-block partial sums: vector kernels (16 slots x nblocks_red) or one per z-pass CTA
+    const size_t np = std::max<size_t>((size_t)16 * h->nblocks_red, (size_t)h->nxloc * cfg->N);
+    CPF_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * np));
+  }
   CPF_CUDA(cudaMalloc(&h->d_scalars, sizeof(double) * 128));
   CPF_CUDA(cudaMallocHost(&h->h_scalars, sizeof(double) * 128));
   // Fn = Fn1 = I (FFT_init.f:157-161)
@@ -465,18 +471,33 @@ static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int*
     resnorm = sqrt(rr);
     if (resnorm <= tolb || resnorm <= tol) break;
     if (it >= maxIter) { cpf_set_error(h, ">>>fftPcg: fail to converge within 1000 iterations"); return CPFFT_ERR_CG; }
-    if (it == 0) CPF_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
-    else {
+    double* pq_dev = h->d_scalars + 8;
+    if (h->fast_pow2) {
+      // p <- r + beta p and the partial sums of p.q are fused into the z passes of the operator
+      if (it == 0) CPF_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+      int nparts = 0;
+      rc = cpf_cg_apply_pow2(h, p, q, r, (it == 0) ? 0.0 : rr / rr_old, it > 0, &nparts); if (rc) return rc;
       const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
-      k_xpby<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(p, r, rr / rr_old, n); h->launches++;
+      k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, nparts, pq_dev);
       cpf_prof_end(h, tk);
+      h->launches++;
+    } else {
+      if (it == 0) CPF_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+      else {
+        const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
+        k_xpby<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(p, r, rr / rr_old, n); h->launches++;
+        cpf_prof_end(h, tk);
+      }
+      rc = cpf_apply_G(h, p, q, true, 1.0); if (rc) return rc;
+      const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
+      k_dot_partial<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(p, q, n, h->d_partials);
+      k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, h->nblocks_red, pq_dev);
+      cpf_prof_end(h, tk);
+      h->launches += 2;
     }
-    rc = cpf_apply_G(h, p, q, true, 1.0); if (rc) return rc;
-    double pq;
-    rc = cpf_dot(h, p, q, n, &pq); if (rc) return rc;
-    const double alpha = rr / pq;
+    if (h->cfg.world > 1) CPF_NCCL(g_nccl.AllReduce(pq_dev, pq_dev, 1, 8, 0, h->nccl_comm, h->stream));
     const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
-    k_cg_update<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(x, r, p, q, alpha, n, h->d_partials);
+    k_cg_update<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(x, r, p, q, rr, pq_dev, n, h->d_partials);
     k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, h->nblocks_red, h->d_scalars);
     cpf_prof_end(h, tk);
     h->launches += 2;

@@ -98,9 +98,12 @@ template <int N> struct ZSmem {
   static constexpr size_t bytes = sizeof(cplx) * (18 * HP + N);
 };
 
-template <int N, bool WITH_K4>
-__global__ void __launch_bounds__(N) k_fz(Pow2Args g, const double* __restrict__ src, const double* __restrict__ K4,
-                                          cplx* __restrict__ spec) {
+// MODE 0: transform src.  MODE 1: transform K4 : src (G_K_dF with flgK).  MODE 2: the CG
+// direction update p <- r + beta p (FFT_nr3.f:290, MKL dcg) fused in front of MODE 1: src is p
+// (read and written), rvec is the residual.
+template <int N, int MODE>
+__global__ void __launch_bounds__(N) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
+                                          cplx* __restrict__ spec, const double* __restrict__ rvec, double beta) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H;
   extern __shared__ cplx sm[];
@@ -115,7 +118,15 @@ __global__ void __launch_bounds__(N) k_fz(Pow2Args g, const double* __restrict__
     double2 f[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) f[c] = *reinterpret_cast<const double2*>(src + c * n3 + e0);
-    if (WITH_K4) {
+    if (MODE == 2) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const double2 r = *reinterpret_cast<const double2*>(rvec + c * n3 + e0);
+        f[c] = make_double2(r.x + beta * f[c].x, r.y + beta * f[c].y);
+        *reinterpret_cast<double2*>(src + c * n3 + e0) = f[c];
+      }
+    }
+    if (MODE >= 1) {
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         double2 a[9];
@@ -151,8 +162,11 @@ __global__ void __launch_bounds__(N) k_fz(Pow2Args g, const double* __restrict__
   }
 }
 
-template <int N>
-__global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale) {
+// DOT: also accumulate sum(dst * pvec) over the CTA's voxels (the p.Ap of CG) into
+// partials[blockIdx.x]; fixed summation order, no atomics.
+template <int N, bool DOT>
+__global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+                                          const double* __restrict__ pvec, double* __restrict__ partials) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H;
   extern __shared__ cplx sm[];
@@ -177,10 +191,29 @@ __global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ s
   smem_fft_dit_inv<H, 2>(18, tw, [&](int line, int i) -> cplx& { return zb[line * Z::HP + Z::pad(i)]; });
   const int l = threadIdx.x / H, t = threadIdx.x - l * H;
   const int64_t e0 = ((int64_t)2 * blockIdx.x + l) * N + 2 * t;
+  double acc = 0.0;
 #pragma unroll
   for (int c = 0; c < 9; ++c) {
     const cplx z = zb[(l * 9 + c) * Z::HP + Z::pad(t)];
-    *reinterpret_cast<double2*>(dst + c * g.n3 + e0) = make_double2(z.x * scale, z.y * scale);
+    const double2 o = make_double2(z.x * scale, z.y * scale);
+    *reinterpret_cast<double2*>(dst + c * g.n3 + e0) = o;
+    if (DOT) {
+      const double2 pv = *reinterpret_cast<const double2*>(pvec + c * g.n3 + e0);
+      acc += o.x * pv.x + o.y * pv.y;
+    }
+  }
+  if (DOT) {
+    __shared__ double red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int i = 0; i < (N + 31) / 32; ++i) sum += red[i];
+      partials[blockIdx.x] = sum;
+    }
   }
 }
 
@@ -328,8 +361,12 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec)
 int cpf_exchange_fwd(cpfft_handle* h);   // solver.cu (NCCL transposes)
 int cpf_exchange_bwd(cpfft_handle* h);
 
+// cg != nullptr: the operator application of one CG iteration, q = G K4 p, with the direction
+// update (update_p) and the p.q partial sums fused into the z passes.
+struct CgFuse { const double* r; double beta; bool update_p; };
+
 template <int N>
-static int apply_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out) {
+static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, double scale_out, const CgFuse* cg) {
   constexpr int H = N / 2, TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
   typedef FftPlan<N> P;
   const int nx = h->nxloc, world = h->cfg.world;
@@ -339,8 +376,9 @@ static int apply_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
   const unsigned zgrid = (unsigned)(nx * N / 2);
   int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
-  if (flgK) k_fz<N, true><<<zgrid, N, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a);
-  else k_fz<N, false><<<zgrid, N, sm_z, h->stream>>>(g, src, nullptr, h->spec_a);
+  if (cg && cg->update_p) k_fz<N, 2><<<zgrid, N, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta);
+  else if (flgK) k_fz<N, 1><<<zgrid, N, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0);
+  else k_fz<N, 0><<<zgrid, N, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0);
   cpf_prof_end(h, tk);
   constexpr int RminY = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
   constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
@@ -372,7 +410,8 @@ static int apply_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK
   cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
   tk = cpf_prof_begin(h, CPF_K_INV_Z);
-  k_iz<N><<<zgrid, N, sm_z, h->stream>>>(g, h->spec_a, dst, scale);
+  if (cg) k_iz<N, true><<<zgrid, N, sm_z, h->stream>>>(g, h->spec_a, dst, scale, src, h->d_partials);
+  else k_iz<N, false><<<zgrid, N, sm_z, h->stream>>>(g, h->spec_a, dst, scale, nullptr, nullptr);
   cpf_prof_end(h, tk);
   h->launches += 5;
   CPF_CUDA(cudaGetLastError());
@@ -385,9 +424,11 @@ static int init_pow2(cpfft_handle* h) {
   constexpr int TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
   const size_t sm_z = ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
-  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_iz<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_iz<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
+  CPF_CUDA(cudaFuncSetAttribute(k_iz<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
   CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
   CPF_CUDA(cudaFuncSetAttribute(k_fy<N, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
   CPF_CUDA(cudaFuncSetAttribute(k_fx<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
@@ -407,15 +448,32 @@ int cpf_pow2_init(cpfft_handle* h) {
 
 bool cpf_pow2_supported(int N) { return N == 16 || N == 32 || N == 64 || N == 128 || N == 256 || N == 512; }
 
-int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out) {
+template <int N> struct Tag {};
+template <class F> static int dispatch_pow2(cpfft_handle* h, F f) {
   switch (h->N) {
-    case 16: return apply_pow2<16>(h, src, dst, flgK, scale_out);
-    case 32: return apply_pow2<32>(h, src, dst, flgK, scale_out);
-    case 64: return apply_pow2<64>(h, src, dst, flgK, scale_out);
-    case 128: return apply_pow2<128>(h, src, dst, flgK, scale_out);
-    case 256: return apply_pow2<256>(h, src, dst, flgK, scale_out);
-    case 512: return apply_pow2<512>(h, src, dst, flgK, scale_out);
+    case 16: return f(Tag<16>());
+    case 32: return f(Tag<32>());
+    case 64: return f(Tag<64>());
+    case 128: return f(Tag<128>());
+    case 256: return f(Tag<256>());
+    case 512: return f(Tag<512>());
   }
   cpf_set_error(h, "power-of-two spectral path called with an unsupported N");
   return CPFFT_ERR_USAGE;
+}
+template <int N> static int call_apply(Tag<N>, cpfft_handle* h, double* src, double* dst, bool flgK, double sc, const CgFuse* cg) {
+  return apply_pow2<N>(h, src, dst, flgK, sc, cg);
+}
+
+int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out) {
+  return dispatch_pow2(h, [&](auto tag) { return call_apply(tag, h, const_cast<double*>(src), dst, flgK, scale_out, nullptr); });
+}
+
+// One CG operator application q = G K4 p with fused direction update and dot product:
+//   update_p: p <- r + beta p before the product;  on return d_partials[0 .. nparts) hold the
+//   per-CTA partial sums of p.q (nparts returned).
+int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts) {
+  CgFuse cg{r, beta, update_p};
+  *nparts = h->nxloc * h->N / 2;
+  return dispatch_pow2(h, [&](auto tag) { return call_apply(tag, h, p, q, true, 1.0, &cg); });
 }

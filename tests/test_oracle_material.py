@@ -148,3 +148,45 @@ def test_homogeneous_single_crystal_is_uniform(Oracle):
     assert np.abs(P - P.mean(axis=1, keepdims=True)).max() <= 1e-9 * np.abs(P).max()
     F = o.Fn1
     assert np.abs(F - F.mean(axis=1, keepdims=True)).max() <= 1e-12
+
+
+def test_stress_noise_floor_of_the_reference_polar_decomposition(oracle_built, tmp_path):
+    """Why the small-strain parity tolerance on P is 5e-8 and not 1e-9.
+
+    The reference gets R = F U^-1 from closed-form trigonometric eigenvalues of C = F^T F
+    (polar.f:224-307).  Its discriminant cancels catastrophically when the principal stretches
+    differ by less than ~3e-3, the angle phi becomes round-off noise, and the stress inherits a
+    noise of order strain^3 ~ 1e-9..1e-8 (relative).  Two builds of the SAME oracle source that
+    differ only in compiler flags (FMA contraction on/off) therefore disagree by ~1e-8 at
+    strain increments of 1e-3 and agree to <1e-9 only at increments >= 2e-2 -- an
+    implementation-independent 1e-9 per-voxel stress match is not defined below that."""
+    import ctypes as C
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    alt = str(tmp_path / "liboracle_alt.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=c++17", "-shared", "-o", alt] +
+                          [os.path.join(src, f) for f in ("oracle_kin.cpp", "oracle_mm10.cpp", "oracle_solver.cpp")])
+    dp = C.POINTER(C.c_double)
+    libs = []
+    for path in (oracle_built, alt):
+        L = C.CDLL(path)
+        L.orc_rtcmp1.argtypes = [dp, dp]
+        libs.append(L)
+
+    def maxdiff(amp, n=400):
+        rng = np.random.default_rng(1)
+        worst = 0.0
+        for _ in range(n):
+            F = np.eye(3).ravel() + amp * rng.standard_normal(9)
+            R = [np.zeros(9), np.zeros(9)]
+            for L, r in zip(libs, R):
+                L.orc_rtcmp1(F.ctypes.data_as(dp), r.ctypes.data_as(dp))
+            # sigma = R t R^T and d = Rh^T D Rh: a rotation error dR is a relative stress error ~ 2 dR
+            worst = max(worst, np.abs(R[0] - R[1]).max())
+        return worst
+
+    small, large = maxdiff(1e-3), maxdiff(5e-2)
+    assert small > 5e-10, small         # noise floor is real at 0.1 % strain increments ...
+    assert small < 5e-8, small          # ... and bounded
+    assert large < 1e-11, large         # well separated stretches: reproducible
