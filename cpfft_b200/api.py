@@ -47,14 +47,15 @@ EXPORTS = [
     "cpfft_set_params", "cpfft_hist_size", "cpfft_local_voxels", "cpfft_drive_eps_sig", "cpfft_G_K_dF",
     "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3",
     "cpfft_field_ncomp", "cpfft_upload", "cpfft_download", "cpfft_download_fail_flags",
-    "cpfft_download_local_iters", "cpfft_material_failures", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_synchronize",
+    "cpfft_download_local_iters", "cpfft_material_failures", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_exchange_mode", "cpfft_synchronize",
     "cpfft_stream", "cpfft_kernel_launches", "cpfft_profile_enable", "cpfft_profile_reset",
     "cpfft_profile_classes", "cpfft_profile_name", "cpfft_profile_get",
 ]
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libcpfft_b200.so")
+    # CPFFT_B200_LIB: development override (kernel-variant experiments); still a CUDA build
+    return os.environ.get("CPFFT_B200_LIB") or os.path.join(_HERE, "libcpfft_b200.so")
 
 
 def load_library():
@@ -93,6 +94,7 @@ def load_library():
     L.cpfft_material_failures.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.cpfft_nccl_unique_id.argtypes = [vp]
     L.cpfft_nccl_init.argtypes = [vp, vp]
+    L.cpfft_exchange_mode.argtypes = [vp]
     L.cpfft_synchronize.argtypes = [vp]
     L.cpfft_stream.argtypes = [vp]
     L.cpfft_stream.restype = vp
@@ -272,6 +274,10 @@ class Solver:
 
     def stream(self):
         return self.L.cpfft_stream(self.h)
+
+    def exchange_mode(self):
+        """0 single GPU, 1 NCCL send/recv transposes, 2 peer stores fused into the FFT kernels"""
+        return int(self.L.cpfft_exchange_mode(self.h))
 
     def kernel_launches(self):
         return int(self.L.cpfft_kernel_launches(self.h))

@@ -7,6 +7,7 @@
 #include "../../include/cpfft_b200.h"
 
 #define CPF_MAX_SLIP 48
+#define CPF_MAX_WORLD 8   // one NVSwitch domain
 
 #define CPF_CUDA(call)                                                                    \
   do {                                                                                    \
@@ -103,6 +104,9 @@ struct cpfft_handle {
   // nccl
   void* nccl_comm; void* nccl_lib;
   double2* xchg_send; double2* xchg_recv;
+  // peer-mapped spectrum buffers of every rank (CUDA IPC), own rank = local pointers
+  bool p2p;
+  double2* peer_spec_a[CPF_MAX_WORLD]; double2* peer_spec_b[CPF_MAX_WORLD];
 };
 
 void cpf_set_error(cpfft_handle* h, const std::string& s);

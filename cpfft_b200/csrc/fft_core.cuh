@@ -1,5 +1,5 @@
 // cpfft_b200: register-resident radix-2/4/8/16 butterflies and in-place shared-memory FFT stages
-// for power-of-two line lengths (the 256^3 / 512^3 benchmark grids; everything else goes
+// for power-of-two and a few 5-smooth line lengths (the benchmark grids; everything else goes
 // through the generic Stockham path in spectral.cu).
 //
 // Decomposition of an N-point line, N = R1 R2 [R3]: decimation in frequency, every stage in
@@ -46,6 +46,22 @@ template <int DIR> struct Dft<4, DIR> {
     const cplx t0 = c_add(v[0], v[2]), t1 = c_sub(v[0], v[2]), t2 = c_add(v[1], v[3]);
     const cplx t3 = c_rot<DIR>(c_sub(v[1], v[3]));
     v[0] = c_add(t0, t2); v[2] = c_sub(t0, t2); v[1] = c_add(t1, t3); v[3] = c_sub(t1, t3);
+  }
+};
+template <int DIR> struct Dft<5, DIR> {
+  static FHD void run(cplx* v) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2 pi/5), cos(4 pi/5)
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;    // sin(2 pi/5), sin(4 pi/5)
+    const cplx a = c_add(v[1], v[4]), b = c_add(v[2], v[3]), c = c_sub(v[1], v[4]), d = c_sub(v[2], v[3]);
+    const cplx x0 = v[0];
+    const cplx p1 = make_double2(x0.x + c1 * a.x + c2 * b.x, x0.y + c1 * a.y + c2 * b.y);
+    const cplx p2 = make_double2(x0.x + c2 * a.x + c1 * b.x, x0.y + c2 * a.y + c1 * b.y);
+    // forward: X1 = p1 - i q1, X4 = p1 + i q1, X2 = p2 - i q2, X3 = p2 + i q2
+    const cplx q1 = c_rot<DIR>(make_double2(s1 * c.x + s2 * d.x, s1 * c.y + s2 * d.y));
+    const cplx q2 = c_rot<DIR>(make_double2(s2 * c.x - s1 * d.x, s2 * c.y - s1 * d.y));
+    v[0] = make_double2(x0.x + a.x + b.x, x0.y + a.y + b.y);
+    v[1] = c_add(p1, q1); v[4] = c_sub(p1, q1);
+    v[2] = c_add(p2, q2); v[3] = c_sub(p2, q2);
   }
 };
 template <int DIR> struct Dft<8, DIR> {
@@ -107,6 +123,15 @@ template <> struct FftPlan<64>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 1;
 template <> struct FftPlan<128> { static constexpr int R1 = 16, R2 = 8,  R3 = 1; };
 template <> struct FftPlan<256> { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
 template <> struct FftPlan<512> { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
+// 5-smooth sizes of the weak-scaling grids (320^3 on 2 GPUs, 400^3 on 4)
+template <> struct FftPlan<20>  { static constexpr int R1 = 5,  R2 = 4,  R3 = 1; };
+template <> struct FftPlan<40>  { static constexpr int R1 = 5,  R2 = 8,  R3 = 1; };
+template <> struct FftPlan<80>  { static constexpr int R1 = 5,  R2 = 16, R3 = 1; };
+template <> struct FftPlan<100> { static constexpr int R1 = 5,  R2 = 5,  R3 = 4; };
+template <> struct FftPlan<160> { static constexpr int R1 = 5,  R2 = 8,  R3 = 4; };
+template <> struct FftPlan<200> { static constexpr int R1 = 5,  R2 = 5,  R3 = 8; };
+template <> struct FftPlan<320> { static constexpr int R1 = 5,  R2 = 8,  R3 = 8; };
+template <> struct FftPlan<400> { static constexpr int R1 = 5,  R2 = 5,  R3 = 16; };
 
 // position (after the forward stages) <-> natural frequency index
 template <int N> FHD int fft_natural(int p) {

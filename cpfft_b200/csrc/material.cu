@@ -7,8 +7,15 @@
 // All state is structure-of-arrays field[comp * n3 + voxel]; consecutive threads touch
 // consecutive voxels so every load/store is coalesced.
 #include "common.cuh"
+#ifndef UPD_THREADS
+#define UPD_THREADS 128
+#endif
+#ifndef MM10_MIN_CTAS
+#define MM10_MIN_CTAS 3
+#endif
 #include "kin.cuh"
 #include "mm01.cuh"
+#define MM10_THREADS UPD_THREADS
 #include "mm10.cuh"
 #include "slip_tables.cuh"
 #include <cmath>
@@ -16,7 +23,6 @@
 #include <array>
 #include <cstring>
 
-#define UPD_THREADS 128
 
 CpfHistLayout cpf_hist_layout(int nslip, int num_hard) {  // mm10_d.f:137-331
   CpfHistLayout L;
@@ -82,7 +88,9 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm01(UpdArgs a) {
   for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] = cep[k];
 }
 
-__global__ void __launch_bounds__(UPD_THREADS) k_update_mm10(UpdArgs a) {
+#define MM10_SMEM_DOUBLES (9 + 9 + 49)   // RWQ, RWR, lagged Jacobian per thread
+__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdArgs a) {
+  extern __shared__ double mm10_sm[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n3) return;
   const CpfMatDev mp = a.mats[a.matidx[e]];
@@ -127,6 +135,10 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm10(UpdArgs a) {
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) c.Q[3 * i + j] = Rpn[3 * j + i];
+  c.RWQ.p = mm10_sm + threadIdx.x;
+  c.RWR.p = mm10_sm + 9 * UPD_THREADS + threadIdx.x;
+  SArr J7;
+  J7.p = mm10_sm + 18 * UPD_THREADS + threadIdx.x;
   cpf_rvw(c.Q, c.RWQ);
   cpf_rvw(R, c.RWR);
   const double dt = a.dt;
@@ -189,7 +201,6 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm10(UpdArgs a) {
       for (int k = 3; k < 6; ++k) p2 += (d1[k] * s1) * (d2[k] * s2);
       cos_ang = fmax(p1 + p2, 0.0);
     }
-    double J7[49];
     double frac = 0.0, stp = 1.0, ox[7], h_last = c.ttn;
     int cuts = 0;
 #pragma unroll
@@ -628,8 +639,10 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
     cpf_prof_end(h, tk);
   }
   if (h->has_mm10) {
+    CPF_CUDA(cudaFuncSetAttribute(k_update_mm10, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS)));
     const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
-    k_update_mm10<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++;
+    k_update_mm10<<<grid, UPD_THREADS, sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS, h->stream>>>(a); h->launches++;
     cpf_prof_end(h, tk);
   }
   const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);

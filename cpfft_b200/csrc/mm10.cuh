@@ -43,13 +43,31 @@ CPF_DI void cpf_symsw(const double* s, const double* w, double* sw) {
   sw[4] = 0.5 * (w[0] * (s[1] - s[2]) + w[1] * s[3] + w[2] * s[5]);
   sw[5] = 0.5 * (w[1] * (s[0] - s[2]) + w[0] * s[3] - w[2] * s[4]);
 }
+// Per-thread array kept in shared memory, element k of thread t at p[k * blockDim + t]:
+// conflict-free, and it takes the lagged Jacobian and the two skew-rotation operators out of
+// the register budget of the Newton loops.
+#ifndef MM10_UNROLL
+#define MM10_UNROLL 1
+#endif
+#define MM10_PRAGMA_(x) _Pragma(#x)
+#define MM10_PRAGMA(x) MM10_PRAGMA_(x)
+#ifndef MM10_THREADS
+#define MM10_THREADS 128
+#endif
+struct SArr {
+  double* p;
+  CPF_DI double& operator[](int k) const { return p[k * MM10_THREADS]; }
+};
+
 // mm10_rt2rvw (mm10_a.f:1461-1479)
-CPF_DI void cpf_rvw(const double* rt, double* rv) {
+template <class Out>
+CPF_DI void cpf_rvw(const double* rt, Out rv) {
   rv[0] = rt[4] * rt[8] - rt[5] * rt[7]; rv[1] = rt[3] * rt[8] - rt[5] * rt[6]; rv[2] = rt[3] * rt[7] - rt[4] * rt[6];
   rv[3] = rt[1] * rt[8] - rt[2] * rt[7]; rv[4] = rt[0] * rt[8] - rt[2] * rt[6]; rv[5] = rt[0] * rt[7] - rt[1] * rt[6];
   rv[6] = rt[1] * rt[5] - rt[2] * rt[4]; rv[7] = rt[0] * rt[5] - rt[2] * rt[3]; rv[8] = rt[0] * rt[4] - rt[1] * rt[3];
 }
-CPF_DI void cpf_mv3(const double* M, const double* v, double* o) {
+template <class Mat>
+CPF_DI void cpf_mv3(const Mat& M, const double* v, double* o) {
   o[0] = M[0] * v[0] + M[1] * v[1] + M[2] * v[2];
   o[1] = M[3] * v[0] + M[4] * v[1] + M[5] * v[2];
   o[2] = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
@@ -106,8 +124,8 @@ struct Mm10Ctx {
   double rate_n, theta_0, tau_y, tau_v, voche_m, iD_v;
   double atol, atol1, rtol, rtol1;
   double Q[9];     // Rp_n^T
-  double RWQ[9];   // RW(Rp_n^T)
-  double RWR[9];   // RW(R)
+  SArr RWQ;        // RW(Rp_n^T), 9 entries (shared memory)
+  SArr RWR;        // RW(R), 9 entries (shared memory)
   double sn[6];    // stress at n
   double ttn;      // tau_tilde at n
   double D[6];     // strain increment of the (sub)step
@@ -155,6 +173,7 @@ CPF_DI double mm10_hfac(const Mm10Ctx& c, double tt, double* hterm_out) {
 CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double* R, bool want2, double* wq_out) {
   double dbarp[6] = {0, 0, 0, 0, 0, 0}, wq[3] = {0, 0, 0}, sabs = 0.0;
   const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v;
+  MM10_PRAGMA(unroll MM10_UNROLL)
   for (int s = 0; s < c.nslip; ++s) {
     double ms[6], qs[3];
     mm10_slip_geom(c, s, ms, qs);
@@ -192,8 +211,8 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
 }
 
 // Jacobian (mm10_formJ): J is NJ x NJ row-major, NJ = 6 (J11 only, predictor) or 7.
-template <int NJ>
-CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, double* J) {
+template <int NJ, class JT>
+CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, JT J) {
   double S[21], T[18], dps[6], wqs[3], wqf[3], es[6], sabs = 0.0, ssum = 0.0;
 #pragma unroll
   for (int k = 0; k < 21; ++k) S[k] = 0.0;
@@ -204,6 +223,7 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, double
 #pragma unroll
   for (int k = 0; k < 3; ++k) { wqs[k] = 0.0; wqf[k] = 0.0; }
   const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v, dgn = c.dg * c.rate_n / tt;
+  MM10_PRAGMA(unroll MM10_UNROLL)
   for (int s = 0; s < c.nslip; ++s) {
     double ms[6], qs[3];
     mm10_slip_geom(c, s, ms, qs);
@@ -295,7 +315,7 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, double
 // mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening, then
 // the coupled update.  x[7] in/out.  J7 receives the last Jacobian formed (lagged).
 // Returns true on failure.
-CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, double* J7, int* it_pred,
+CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, SArr J7, int* it_pred,
                        int* it_upd, double* h_last) {
   const double cc = 1.0e-4, red = 0.5;
   const int mls = 10, mmin = 1;
@@ -312,7 +332,7 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, do
     int iter = 0;
     while ((nR1 > c.atol1) && (nR1 / inR1 > c.rtol1)) {
       double J[36], mJ[36], dx[6], wv[6];
-      mm10_jacobian<6>(c, x1, x2, J);
+      mm10_jacobian<6, double*>(c, x1, x2, J);
 #pragma unroll
       for (int k = 0; k < 36; ++k) mJ[k] = -J[k];
 #pragma unroll
@@ -366,7 +386,7 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, do
     int iter = 0;
     while (((nR > c.atol) && (nR / inR > c.rtol)) || (iter < mmin)) {
       double mJ[49], dx[7], wv[7];
-      mm10_jacobian<7>(c, x, x[6], J7);
+      mm10_jacobian<7, SArr>(c, x, x[6], J7);
 #pragma unroll
       for (int k = 0; k < 49; ++k) mJ[k] = -J7[k];
       dot = 0.0;

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 
 static double wall_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -134,6 +135,7 @@ struct NcclApi {
   int (*CommInitRank)(cpf_ncclComm_t*, int, cpf_ncclUniqueId, int);
   int (*CommDestroy)(cpf_ncclComm_t);
   int (*AllReduce)(const void*, void*, size_t, int, int, cpf_ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void*, void*, size_t, int, cpf_ncclComm_t, cudaStream_t);
   int (*Send)(const void*, size_t, int, int, cpf_ncclComm_t, cudaStream_t);
   int (*Recv)(void*, size_t, int, int, cpf_ncclComm_t, cudaStream_t);
   int (*GroupStart)(); int (*GroupEnd)();
@@ -147,7 +149,7 @@ static int nccl_load() {
   if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) return 1;
 #define LD(name) *(void**)(&g_nccl.name) = dlsym(lib, "nccl" #name); if (!g_nccl.name) return 1;
-  LD(GetUniqueId) LD(CommInitRank) LD(CommDestroy) LD(AllReduce) LD(Send) LD(Recv) LD(GroupStart) LD(GroupEnd) LD(GetErrorString)
+  LD(GetUniqueId) LD(CommInitRank) LD(CommDestroy) LD(AllReduce) LD(AllGather) LD(Send) LD(Recv) LD(GroupStart) LD(GroupEnd) LD(GetErrorString)
 #undef LD
   g_nccl.lib = lib;
   return 0;
@@ -239,6 +241,14 @@ int cpf_exchange_bwd(cpfft_handle* h) {
   return 0;
 }
 
+// stream-ordered barrier over all ranks: every rank's work queued before it on the compute
+// stream (in particular its peer stores) has completed when work queued after it starts
+int cpf_rank_barrier(cpfft_handle* h) {
+  double* slot = h->d_scalars + 32;
+  CPF_NCCL(g_nccl.AllReduce(slot, slot, 1, 8, 0, h->nccl_comm, h->stream));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // scalar read-back of `cnt` reduction slots (all-reduced over ranks when world > 1)
 static int fetch_scalars(cpfft_handle* h, int cnt, double* out) {
@@ -277,6 +287,8 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   h->d_fail = nullptr; h->d_liters = nullptr; h->d_failcnt = nullptr; h->n_fail = h->n_fail_final = 0; h->spec_a = h->spec_b = nullptr; h->tw = nullptr; h->d_radices = nullptr;
   h->work9 = nullptr; h->d_partials = nullptr; h->d_scalars = nullptr; h->h_scalars = nullptr;
   h->nccl_comm = nullptr; h->nccl_lib = nullptr; h->xchg_send = h->xchg_recv = nullptr;
+  h->p2p = false;
+  for (int r = 0; r < CPF_MAX_WORLD; ++r) h->peer_spec_a[r] = h->peer_spec_b[r] = nullptr;
   h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr;
   *out = h;  // returned even on failure so that cpfft_last_error works; caller destroys it
   if (cfg->N < 2) { cpf_set_error(h, "N must be >= 2"); return CPFFT_ERR_USAGE; }
@@ -333,6 +345,12 @@ void cpfft_destroy(cpfft_handle* h) {
                   h->d_partials, h->d_scalars, h->xchg_send, h->xchg_recv};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->p2p)
+    for (int r = 0; r < h->cfg.world; ++r)
+      if (r != h->cfg.rank) {
+        if (h->peer_spec_a[r]) cudaIpcCloseMemHandle(h->peer_spec_a[r]);
+        if (h->peer_spec_b[r]) cudaIpcCloseMemHandle(h->peer_spec_b[r]);
+      }
   cpf_spectral_free(h);
   if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -730,9 +748,52 @@ int cpfft_nccl_init(cpfft_handle* h, const void* id128) {
   CPF_NCCL(g_nccl.CommInitRank(&h->nccl_comm, h->cfg.world, id, h->cfg.rank));
   const size_t spec_elems = (size_t)9 * h->nxloc * h->N * h->Nh;
   CPF_CUDA(cudaMalloc(&h->spec_b, sizeof(double2) * spec_elems));
-  CPF_CUDA(cudaMalloc(&h->xchg_send, sizeof(double2) * spec_elems));
-  CPF_CUDA(cudaMalloc(&h->xchg_recv, sizeof(double2) * spec_elems));
+  CPF_CUDA(cudaMemset(h->d_scalars, 0, sizeof(double) * 128));
+  // Peer mapping of the spectrum buffers (fast spectral path only): exchange CUDA IPC handles
+  // through the communicator and open every peer's spec_a / spec_b.  Any failure (no peer
+  // access, IPC not permitted) leaves the NCCL send/recv transposes in place.
+  bool want = h->fast_pow2 && h->cfg.world <= CPF_MAX_WORLD && getenv("CPFFT_NO_P2P") == nullptr;
+  int ok = want ? 1 : 0;
+  const int W = h->cfg.world;
+  std::vector<cudaIpcMemHandle_t> all((size_t)2 * W);
+  if (want) {
+    cudaIpcMemHandle_t mine[2];
+    if (cudaIpcGetMemHandle(&mine[0], h->spec_a) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], h->spec_b) != cudaSuccess) {
+      ok = 0; cudaGetLastError(); std::memset(mine, 0, sizeof(mine));
+    }
+    void* d_hand = nullptr;
+    CPF_CUDA(cudaMalloc(&d_hand, sizeof(mine) * (W + 1)));
+    CPF_CUDA(cudaMemcpy((char*)d_hand + sizeof(mine) * W, mine, sizeof(mine), cudaMemcpyHostToDevice));
+    CPF_NCCL(g_nccl.AllGather((char*)d_hand + sizeof(mine) * W, d_hand, sizeof(mine), 0 /* ncclChar */, h->nccl_comm, h->stream));
+    CPF_CUDA(cudaStreamSynchronize(h->stream));
+    CPF_CUDA(cudaMemcpy(all.data(), d_hand, sizeof(mine) * W, cudaMemcpyDeviceToHost));
+    cudaFree(d_hand);
+    if (ok) {
+      for (int r = 0; r < W && ok; ++r) {
+        if (r == h->cfg.rank) { h->peer_spec_a[r] = h->spec_a; h->peer_spec_b[r] = h->spec_b; continue; }
+        void *pa = nullptr, *pb = nullptr;
+        if (cudaIpcOpenMemHandle(&pa, all[2 * r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pb, all[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = 0; cudaGetLastError();
+        }
+        h->peer_spec_a[r] = (double2*)pa; h->peer_spec_b[r] = (double2*)pb;
+      }
+    }
+  }
+  // every rank must take the same path
+  double v = ok ? 0.0 : 1.0, bad = 0.0;
+  CPF_CUDA(cudaMemcpy(h->d_scalars + 33, &v, sizeof(double), cudaMemcpyHostToDevice));
+  CPF_NCCL(g_nccl.AllReduce(h->d_scalars + 33, h->d_scalars + 33, 1, 8, 0, h->nccl_comm, h->stream));
+  CPF_CUDA(cudaStreamSynchronize(h->stream));
+  CPF_CUDA(cudaMemcpy(&bad, h->d_scalars + 33, sizeof(double), cudaMemcpyDeviceToHost));
+  h->p2p = want && (bad == 0.0);
+  if (!h->p2p) {   // staging buffers of the NCCL send/recv transposes
+    CPF_CUDA(cudaMalloc(&h->xchg_send, sizeof(double2) * spec_elems));
+    CPF_CUDA(cudaMalloc(&h->xchg_recv, sizeof(double2) * spec_elems));
+  }
   return 0;
 }
+
+int cpfft_exchange_mode(const cpfft_handle* h) { return h ? (h->cfg.world <= 1 ? 0 : (h->p2p ? 2 : 1)) : -1; }
 
 }  // extern "C"

@@ -1,5 +1,5 @@
 // cpfft_b200: fast path of the spectral operator G_K_dF (G_K_dF.f:11-87) for power-of-two grids
-// (N = 16 .. 512; the 256^3 / 512^3 benchmark grids).  Same mathematics as spectral.cu, built
+// (N = 16 .. 512) and the 5-smooth weak-scaling grids 320 and 400.  Same mathematics as spectral.cu, built
 // from the register butterflies of fft_core.cuh:
 //
 //   k_fz  : [K4 : x contraction fused on load] two real z lines per CTA, each packed as an N/2
@@ -17,17 +17,31 @@
 #include "fft_core.cuh"
 
 struct Pow2Args {
-  int nx;        // local x planes (z / y passes)
+  int nx, x0;    // local x planes (z / y passes) and their global offset
   int NY, y0;    // x pass: local y extent and its global offset (slab-transposed layout)
   int64_t n3;    // local voxels
   const cplx* tw;  // exp(-2 pi i k / N), k < N
 };
 
+// kz tile sizes of the y and x passes (must divide N/2) and the CTA size of the z passes
+// Slab <-> pencil transposes fused into the FFT store stages (world > 1): every rank maps the
+// spectrum buffers of all ranks (CUDA IPC) and the last butterfly stage of the y pass / of the
+// inverse x pass stores each element straight into the rank that owns it -- NVLink stores in
+// 128..256-byte runs, no pack / unpack kernels, no staging buffers, the transfer overlaps
+// the transform.  peers[r] = base of rank r's destination buffer (own rank: local pointer).
+struct PeerPtrs { cplx* p[CPF_MAX_WORLD]; };
+
 template <int N> struct Pow2Cfg {
   static constexpr int H = N / 2;
   static constexpr int TZY = (H < 16 ? H : 16) < (4096 / N) ? (H < 16 ? H : 16) : (4096 / N);
   static constexpr int TZX = (H < 8 ? H : 8) < (2048 / N) ? (H < 8 ? H : 8) : (2048 / N);
+  static constexpr int ZT = (N + 31) / 32 * 32;     // threads of k_fz / k_iz (N of them work)
 };
+template <> struct Pow2Cfg<40> { static constexpr int H = 20, TZY = 10, TZX = 5, ZT = 64; };
+template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, ZT = 96; };
+template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 224; };
+template <> struct Pow2Cfg<320> { static constexpr int H = 160, TZY = 16, TZX = 8, ZT = 320; };
+template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8, ZT = 416; };
 
 template <int N> __device__ __forceinline__ constexpr int last_radix() {
   return FftPlan<N>::R3 > 1 ? FftPlan<N>::R3 : (FftPlan<N>::R2 > 1 ? FftPlan<N>::R2 : FftPlan<N>::R1);
@@ -102,7 +116,7 @@ template <int N> struct ZSmem {
 // direction update p <- r + beta p (FFT_nr3.f:290, MKL dcg) fused in front of MODE 1: src is p
 // (read and written), rvec is the residual.
 template <int N, int MODE>
-__global__ void __launch_bounds__(N) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
                                           cplx* __restrict__ spec, const double* __restrict__ rvec, double beta) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H;
@@ -114,7 +128,7 @@ __global__ void __launch_bounds__(N) k_fz(Pow2Args g, double* __restrict__ src, 
   const int l = threadIdx.x / H, t = threadIdx.x - l * H;
   const int64_t L = (int64_t)2 * blockIdx.x + l;          // grid line x * N + y
   const int64_t e0 = L * N + 2 * t;
-  {
+  if (threadIdx.x < N) {
     double2 f[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) f[c] = *reinterpret_cast<const double2*>(src + c * n3 + e0);
@@ -155,7 +169,7 @@ __global__ void __launch_bounds__(N) k_fz(Pow2Args g, double* __restrict__ src, 
     const int ll = lc / 9, c = lc - ll * 9;
     const cplx* line = zb + lc * Z::HP;
     const cplx Zk = line[Z::pad(fft_position<H>(k))];
-    const cplx Zm = c_conj(line[Z::pad(fft_position<H>((H - k) & (H - 1)))]);
+    const cplx Zm = c_conj(line[Z::pad(fft_position<H>((k == 0) ? 0 : H - k))]);
     const cplx E = c_add(Zk, Zm), D = c_sub(Zk, Zm);
     const cplx O = c_mul(make_double2(D.y, -D.x), tw[k]);
     spec[((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H + k] = make_double2(0.5 * (E.x + O.x), 0.5 * (E.y + O.y));
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__(N) k_fz(Pow2Args g, double* __restrict__ src, 
 // DOT: also accumulate sum(dst * pvec) over the CTA's voxels (the p.Ap of CG) into
 // partials[blockIdx.x]; fixed summation order, no atomics.
 template <int N, bool DOT>
-__global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                           const double* __restrict__ pvec, double* __restrict__ partials) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H;
@@ -192,6 +206,7 @@ __global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ s
   const int l = threadIdx.x / H, t = threadIdx.x - l * H;
   const int64_t e0 = ((int64_t)2 * blockIdx.x + l) * N + 2 * t;
   double acc = 0.0;
+  if (threadIdx.x < N) {
 #pragma unroll
   for (int c = 0; c < 9; ++c) {
     const cplx z = zb[(l * 9 + c) * Z::HP + Z::pad(t)];
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ s
       acc += o.x * pv.x + o.y * pv.y;
     }
   }
+  }
   if (DOT) {
     __shared__ double red[32];
 #pragma unroll
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ s
     __syncthreads();
     if (threadIdx.x == 0) {
       double sum = 0.0;
-      for (int i = 0; i < (N + 31) / 32; ++i) sum += red[i];
+      for (int i = 0; i < Pow2Cfg<N>::ZT / 32; ++i) sum += red[i];
       partials[blockIdx.x] = sum;
     }
   }
@@ -219,8 +235,10 @@ __global__ void __launch_bounds__(N) k_iz(Pow2Args g, const cplx* __restrict__ s
 
 // ---------------------------------------------------------------------------------------------
 // y pass, in place.  grid = (9 * nx, NZ / TZ).  Shared memory s[i * TZ + l] (+ twiddles).
-template <int N, int DIR>
-__global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec) {
+// SCATTER: the result line (natural y order) is written to the y-slab layout
+// [c][x global][y local][kz] of the rank that owns y (forward transpose fused into the store).
+template <int N, int DIR, bool SCATTER>
+__global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
   typedef FftPlan<N> P;
   constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZY;
   constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
@@ -230,12 +248,24 @@ __global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec)
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   __syncthreads();
   cplx* G = spec + (int64_t)blockIdx.x * N * H + blockIdx.y * TZ;
+  const int ny = g.NY;                                   // SCATTER: y planes per rank
+  const int cc = blockIdx.x / g.nx, xg = g.x0 + (blockIdx.x - cc * g.nx);
+  const int64_t sbase = ((int64_t)cc * N + xg) * ny * H + blockIdx.y * TZ;
+  auto out = [&](int i, int l, cplx v) {
+    const int y = fft_natural<N>(i);
+    if (SCATTER) {
+      const int pr = y / ny, yl = y - pr * ny;
+      peers.p[pr][sbase + (int64_t)yl * H + l] = v;
+    } else {
+      G[(int64_t)y * H + l] = v;
+    }
+  };
   constexpr bool single = (P::R2 == 1);
   for (int task = threadIdx.x; task < TZ * (N / P::R1); task += blockDim.x) {
     const int j = task / TZ, l = task - j * TZ;
     if (single)
       fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return G[(int64_t)i * H + l]; },
-                                      [&](int i, cplx v) { G[(int64_t)fft_natural<N>(i) * H + l] = v; });
+                                      [&](int i, cplx v) { out(i, l, v); });
     else
       fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return G[(int64_t)i * H + l]; },
                                       [&](int i, cplx v) { s[i * TZ + l] = v; });
@@ -247,7 +277,7 @@ __global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec)
     const int j = task / TZ, l = task - j * TZ;
     if (two)
       fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; },
-                                            [&](int i, cplx v) { G[(int64_t)fft_natural<N>(i) * H + l] = v; });
+                                            [&](int i, cplx v) { out(i, l, v); });
     else
       fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; },
                                             [&](int i, cplx v) { s[i * TZ + l] = v; });
@@ -257,15 +287,17 @@ __global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec)
   for (int task = threadIdx.x; task < TZ * (N / P::R3); task += blockDim.x) {
     const int j = task / TZ, l = task - j * TZ;
     fft_stage_dif<N2, P::R3, DIR, N / N2>(j, tw, [&](int i) { return s[i * TZ + l]; },
-                                          [&](int i, cplx v) { G[(int64_t)fft_natural<N>(i) * H + l] = v; });
+                                          [&](int i, cplx v) { out(i, l, v); });
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // x pass: forward, Green operator, inverse.  grid = (NY, NZ / TZ, 3 tensor rows).
 // Shared memory s[(cl * N + i) * TZ + l], cl = component within the row.
-template <int N>
-__global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec) {
+// SCATTER: the inverse-transformed line (natural x order) goes back to the x-slab layout
+// [c][x local][y global][kz] of the rank that owns x (backward transpose fused into the store).
+template <int N, bool SCATTER>
+__global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
   typedef FftPlan<N> P;
   constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZX;
   constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
@@ -353,12 +385,21 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec)
     const int j = r % (N / P::R1), cl = r / (N / P::R1);
     cplx* sc = s + cl * N * TZ + l;
     cplx* gc = G + (int64_t)cl * N * xs + l;
-    fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { gc[(int64_t)i * xs] = v; });
+    const int c = 3 * row + cl;
+    fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) {
+      if (SCATTER) {
+        const int q = i / g.nx, xl = i - q * g.nx;       // owner of x plane i
+        peers.p[q][(((int64_t)c * g.nx + xl) * N + (g.y0 + y)) * H + kz0 + l] = v;
+      } else {
+        gc[(int64_t)i * xs] = v;
+      }
+    });
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-int cpf_exchange_fwd(cpfft_handle* h);   // solver.cu (NCCL transposes)
+int cpf_exchange_fwd(cpfft_handle* h);   // solver.cu (NCCL transposes, fallback without peer mapping)
+int cpf_rank_barrier(cpfft_handle* h);   // solver.cu: stream-ordered barrier over all ranks
 int cpf_exchange_bwd(cpfft_handle* h);
 
 // cg != nullptr: the operator application of one CG iteration, q = G K4 p, with the direction
@@ -367,51 +408,71 @@ struct CgFuse { const double* r; double beta; bool update_p; };
 
 template <int N>
 static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, double scale_out, const CgFuse* cg) {
-  constexpr int H = N / 2, TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
+  constexpr int H = N / 2, TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX, ZT = Pow2Cfg<N>::ZT;
   typedef FftPlan<N> P;
   const int nx = h->nxloc, world = h->cfg.world;
   Pow2Args g;
-  g.nx = nx; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
+  g.nx = nx; g.x0 = h->x0; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
+  PeerPtrs none = {};
   const size_t sm_z = ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
   const unsigned zgrid = (unsigned)(nx * N / 2);
   int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
-  if (cg && cg->update_p) k_fz<N, 2><<<zgrid, N, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta);
-  else if (flgK) k_fz<N, 1><<<zgrid, N, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0);
-  else k_fz<N, 0><<<zgrid, N, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0);
+  if (cg && cg->update_p) k_fz<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta);
+  else if (flgK) k_fz<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0);
+  else k_fz<N, 0><<<zgrid, ZT, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0);
   cpf_prof_end(h, tk);
-  constexpr int RminY = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
+  constexpr int Rm12 = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
+  constexpr int RminY = P::R3 > 1 ? (Rm12 < P::R3 ? Rm12 : P::R3) : Rm12;
   constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
   constexpr int thr_x = (3 * TZX * (N / RminY)) > 512 ? 512 : (3 * TZX * (N / RminY) < 32 ? 32 : 3 * TZX * (N / RminY));
   const dim3 gy(9 * nx, H / TZY);
-  tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-  k_fy<N, -1><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a);
-  cpf_prof_end(h, tk);
   if (world == 1) {
+    tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+    k_fy<N, -1, false><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
+    cpf_prof_end(h, tk);
     const dim3 gx(N, H / TZX, 3);
     tk = cpf_prof_begin(h, CPF_K_X_GREEN);
-    k_fx<N><<<gx, thr_x, sm_x, h->stream>>>(g, h->spec_a);
+    k_fx<N, false><<<gx, thr_x, sm_x, h->stream>>>(g, h->spec_a, none);
     cpf_prof_end(h, tk);
   } else {
-    int rc = cpf_exchange_fwd(h);
-    if (rc) return rc;
     const int ny = N / world;
     Pow2Args gt = g;
     gt.NY = ny; gt.y0 = h->cfg.rank * ny;
     const dim3 gx(ny, H / TZX, 3);
-    tk = cpf_prof_begin(h, CPF_K_X_GREEN);
-    k_fx<N><<<gx, thr_x, sm_x, h->stream>>>(gt, h->spec_b);
-    cpf_prof_end(h, tk);
-    rc = cpf_exchange_bwd(h);
-    if (rc) return rc;
+    if (h->p2p) {
+      PeerPtrs pa, pb;
+      for (int r = 0; r < CPF_MAX_WORLD; ++r) { pa.p[r] = h->peer_spec_a[r]; pb.p[r] = h->peer_spec_b[r]; }
+      Pow2Args gs = g;
+      gs.NY = ny;                                  // y planes per rank, for the scatter
+      tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+      k_fy<N, -1, true><<<gy, thr_y, sm_y, h->stream>>>(gs, h->spec_a, pb);   // -> every rank's spec_b
+      cpf_prof_end(h, tk);
+      int rc = cpf_rank_barrier(h); if (rc) return rc;
+      tk = cpf_prof_begin(h, CPF_K_X_GREEN);
+      k_fx<N, true><<<gx, thr_x, sm_x, h->stream>>>(gt, h->spec_b, pa);        // -> every rank's spec_a
+      cpf_prof_end(h, tk);
+      rc = cpf_rank_barrier(h); if (rc) return rc;
+    } else {
+      tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+      k_fy<N, -1, false><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
+      cpf_prof_end(h, tk);
+      int rc = cpf_exchange_fwd(h);
+      if (rc) return rc;
+      tk = cpf_prof_begin(h, CPF_K_X_GREEN);
+      k_fx<N, false><<<gx, thr_x, sm_x, h->stream>>>(gt, h->spec_b, none);
+      cpf_prof_end(h, tk);
+      rc = cpf_exchange_bwd(h);
+      if (rc) return rc;
+    }
   }
   tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-  k_fy<N, +1><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a);
+  k_fy<N, +1, false><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
   cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
   tk = cpf_prof_begin(h, CPF_K_INV_Z);
-  if (cg) k_iz<N, true><<<zgrid, N, sm_z, h->stream>>>(g, h->spec_a, dst, scale, src, h->d_partials);
-  else k_iz<N, false><<<zgrid, N, sm_z, h->stream>>>(g, h->spec_a, dst, scale, nullptr, nullptr);
+  if (cg) k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, src, h->d_partials);
+  else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, nullptr, nullptr);
   cpf_prof_end(h, tk);
   h->launches += 5;
   CPF_CUDA(cudaGetLastError());
@@ -429,9 +490,11 @@ static int init_pow2(cpfft_handle* h) {
   CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
   CPF_CUDA(cudaFuncSetAttribute(k_iz<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
   CPF_CUDA(cudaFuncSetAttribute(k_iz<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
-  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
-  CPF_CUDA(cudaFuncSetAttribute(k_fx<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
+  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
+  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, +1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
+  CPF_CUDA(cudaFuncSetAttribute(k_fx<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  CPF_CUDA(cudaFuncSetAttribute(k_fx<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
   return 0;
 }
 int cpf_pow2_init(cpfft_handle* h) {
@@ -442,11 +505,18 @@ int cpf_pow2_init(cpfft_handle* h) {
     case 128: return init_pow2<128>(h);
     case 256: return init_pow2<256>(h);
     case 512: return init_pow2<512>(h);
+    case 40: return init_pow2<40>(h);
+    case 80: return init_pow2<80>(h);
+    case 200: return init_pow2<200>(h);
+    case 320: return init_pow2<320>(h);
+    case 400: return init_pow2<400>(h);
   }
   return CPFFT_ERR_USAGE;
 }
 
-bool cpf_pow2_supported(int N) { return N == 16 || N == 32 || N == 64 || N == 128 || N == 256 || N == 512; }
+bool cpf_pow2_supported(int N) {
+  return N == 16 || N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 320 || N == 400 || N == 40 || N == 80 || N == 200;
+}
 
 template <int N> struct Tag {};
 template <class F> static int dispatch_pow2(cpfft_handle* h, F f) {
@@ -457,6 +527,11 @@ template <class F> static int dispatch_pow2(cpfft_handle* h, F f) {
     case 128: return f(Tag<128>());
     case 256: return f(Tag<256>());
     case 512: return f(Tag<512>());
+    case 40: return f(Tag<40>());
+    case 80: return f(Tag<80>());
+    case 200: return f(Tag<200>());
+    case 320: return f(Tag<320>());
+    case 400: return f(Tag<400>());
   }
   cpf_set_error(h, "power-of-two spectral path called with an unsupported N");
   return CPFFT_ERR_USAGE;

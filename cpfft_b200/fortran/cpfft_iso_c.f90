@@ -163,6 +163,10 @@ module cpfft_iso_c
        type(c_ptr), value :: handle
        character(kind=c_char), intent(in) :: id128(128)
      end function
+     integer(c_int) function cpfft_exchange_mode(handle) bind(c, name='cpfft_exchange_mode')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: handle
+     end function
      integer(c_int) function cpfft_synchronize(handle) bind(c, name='cpfft_synchronize')
        import :: c_int, c_ptr
        type(c_ptr), value :: handle

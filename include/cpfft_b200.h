@@ -138,6 +138,9 @@ int cpfft_material_failures(cpfft_handle* h, int64_t* total, int64_t* last_sweep
 /* ---- multi-GPU (new; the reference's mpi_code.f is all stubs) ---- */
 int cpfft_nccl_unique_id(void* id128);                   /* rank 0: create, then broadcast */
 int cpfft_nccl_init(cpfft_handle* h, const void* id128); /* all ranks                       */
+/* how the slab <-> pencil transposes of G_K_dF run: 0 single GPU, 1 NCCL send/recv with
+ * pack/unpack kernels, 2 peer-mapped stores fused into the FFT store stages (CUDA IPC) */
+int cpfft_exchange_mode(const cpfft_handle* h);
 
 /* ---- measurement helpers ---- */
 int cpfft_synchronize(cpfft_handle* h);

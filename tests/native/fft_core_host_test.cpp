@@ -129,11 +129,11 @@ template <int N> static void test_real_pack() {
 
 int main() {
   srand48(12345);
-  test_dft<2>(); test_dft<4>(); test_dft<8>(); test_dft<16>();
+  test_dft<2>(); test_dft<4>(); test_dft<5>(); test_dft<8>(); test_dft<16>();
   printf("butterflies maxerr %.3e\n", maxerr);
-  test_line<8>(); test_line<16>(); test_line<32>(); test_line<64>(); test_line<128>(); test_line<256>(); test_line<512>();
+  test_line<8>(); test_line<16>(); test_line<32>(); test_line<64>(); test_line<128>(); test_line<256>(); test_line<512>(); test_line<20>(); test_line<40>(); test_line<80>(); test_line<100>(); test_line<160>(); test_line<200>(); test_line<320>(); test_line<400>();
   printf("lines maxerr %.3e\n", maxerr);
-  test_real_pack<16>(); test_real_pack<32>(); test_real_pack<64>(); test_real_pack<128>(); test_real_pack<256>(); test_real_pack<512>();
+  test_real_pack<16>(); test_real_pack<32>(); test_real_pack<64>(); test_real_pack<128>(); test_real_pack<256>(); test_real_pack<512>(); test_real_pack<40>(); test_real_pack<80>(); test_real_pack<200>(); test_real_pack<320>(); test_real_pack<400>();
   printf("real pack maxerr %.3e\n", maxerr);
   if (!(maxerr < 1e-13)) { printf("FAIL\n"); return 1; }
   printf("OK\n");
