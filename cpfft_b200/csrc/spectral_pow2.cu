@@ -37,6 +37,29 @@ template <int N> struct Pow2Cfg {
   static constexpr int TZX = (H < 8 ? H : 8) < (2048 / N) ? (H < 8 ? H : 8) : (2048 / N);
   static constexpr int ZT = (N + 31) / 32 * 32;     // threads of k_fz / k_iz (N of them work)
 };
+// resident CTAs per SM the z passes are compiled for (register budget 64K / (threads * CTAs))
+#ifndef CPF_ZMINB
+#define CPF_ZMINB 1
+#endif
+#ifndef CPF_CARVE_Z
+#define CPF_CARVE_Z 0
+#endif
+#ifndef CPF_CARVE_Y
+#define CPF_CARVE_Y 0
+#endif
+#ifndef CPF_CARVE_X
+#define CPF_CARVE_X 0
+#endif
+// measured at 256^3: k_iz gains from 3 resident CTAs (0.92 -> 0.78 ms), k_fz loses (1.91 -> 2.05 ms);
+// giving the whole L1 to shared memory (carveout) slows every pass down
+template <int N> struct ZOcc {
+  static constexpr int MINB_FZ = CPF_ZMINB;
+  static constexpr int MINB_IZ = Pow2Cfg<N>::ZT <= 256 ? 3 : 1;
+};
+#ifndef CPF_TZX256
+#define CPF_TZX256 4     // measured: k_fx 0.84 ms with 8 kz per CTA (1 CTA/SM), 0.75 ms with 4 (3 CTAs/SM)
+#endif
+template <> struct Pow2Cfg<256> { static constexpr int H = 128, TZY = 16, TZX = CPF_TZX256, ZT = 256; };
 template <> struct Pow2Cfg<40> { static constexpr int H = 20, TZY = 10, TZX = 5, ZT = 64; };
 template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, ZT = 96; };
 template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 224; };
@@ -116,7 +139,7 @@ template <int N> struct ZSmem {
 // direction update p <- r + beta p (FFT_nr3.f:290, MKL dcg) fused in front of MODE 1: src is p
 // (read and written), rvec is the residual.
 template <int N, int MODE>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB_FZ) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
                                           cplx* __restrict__ spec, const double* __restrict__ rvec, double beta) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H;
@@ -179,7 +202,7 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT) k_fz(Pow2Args g, double* __res
 // DOT: also accumulate sum(dst * pvec) over the CTA's voxels (the p.Ap of CG) into
 // partials[blockIdx.x]; fixed summation order, no atomics.
 template <int N, bool DOT>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB_IZ) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                           const double* __restrict__ pvec, double* __restrict__ partials) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H;
@@ -189,17 +212,39 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT) k_iz(Pow2Args g, const cplx* _
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   __syncthreads();
   const int64_t nxN = (int64_t)g.nx * N;
-  // tangle: Z'[k] = (X[k] + conj X[H-k]) + i w_N^-k (X[k] - conj X[H-k]), X[H] = 0, X[0] real
+  // stage the 18 half-spectrum rows at their digit-reversed positions (one coalesced read of
+  // every row), then tangle pairs (k, H-k) in place:
+  //   Z'[k] = (X[k] + conj X[H-k]) + i w_N^-k (X[k] - conj X[H-k]),  X[H] = 0,  X[0] real
   for (int idx = threadIdx.x; idx < 18 * H; idx += blockDim.x) {
     const int lc = idx / H, k = idx - lc * H;
     const int ll = lc / 9, c = lc - ll * 9;
-    const cplx* row = spec + ((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H;
-    cplx Xk = row[k], Xm;
-    if (k == 0) { Xk.y = 0.0; Xm = make_double2(0.0, 0.0); }
-    else Xm = c_conj(row[H - k]);
-    const cplx E = c_add(Xk, Xm), D = c_sub(Xk, Xm);
-    const cplx O = c_mulc(D, tw[k]);
-    zb[lc * Z::HP + Z::pad(fft_position<H>(k))] = make_double2(E.x - O.y, E.y + O.x);
+    zb[lc * Z::HP + Z::pad(fft_position<H>(k))] = spec[((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H + k];
+  }
+  __syncthreads();
+  constexpr int NP = H / 2 + 1;                 // pairs per row: k = 0 .. H/2 (0 and H/2 are self-paired)
+  for (int idx = threadIdx.x; idx < 18 * NP; idx += blockDim.x) {
+    const int lc = idx / NP, k = idx - lc * NP;
+    cplx* row = zb + lc * Z::HP;
+    const int pk = Z::pad(fft_position<H>(k));
+    if (k == 0) {
+      const double x0 = row[pk].x;
+      row[pk] = make_double2(x0, x0);           // X[0] real, X[H] = 0:  Z'[0] = X0 (1 + i)
+    } else {
+      const int pm = Z::pad(fft_position<H>(H - k));
+      const cplx Xk = row[pk], Xh = row[pm];
+      {
+        const cplx Xm = c_conj(Xh);
+        const cplx E = c_add(Xk, Xm), D = c_sub(Xk, Xm);
+        const cplx O = c_mulc(D, tw[k]);
+        row[pk] = make_double2(E.x - O.y, E.y + O.x);
+      }
+      if (2 * k != H) {
+        const cplx Xm = c_conj(Xk);
+        const cplx E = c_add(Xh, Xm), D = c_sub(Xh, Xm);
+        const cplx O = c_mulc(D, tw[H - k]);
+        row[pm] = make_double2(E.x - O.y, E.y + O.x);
+      }
+    }
   }
   __syncthreads();
   smem_fft_dit_inv<H, 2>(18, tw, [&](int line, int i) -> cplx& { return zb[line * Z::HP + Z::pad(i)]; });
@@ -485,16 +530,20 @@ static int init_pow2(cpfft_handle* h) {
   constexpr int TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
   const size_t sm_z = ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
-  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_fz<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_iz<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_iz<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_z));
-  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
-  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
-  CPF_CUDA(cudaFuncSetAttribute(k_fy<N, +1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_y));
-  CPF_CUDA(cudaFuncSetAttribute(k_fx<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
-  CPF_CUDA(cudaFuncSetAttribute(k_fx<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_x));
+  // let the SM give the whole unified L1/shared array to shared memory so that 2-4 CTAs fit
+#define CPF_SMEM_ATTR(kern, bytes, carve)                                                                 \
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
+  if (carve) CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CPF_SMEM_ATTR((k_fz<N, 0>), sm_z, CPF_CARVE_Z);
+  CPF_SMEM_ATTR((k_fz<N, 1>), sm_z, CPF_CARVE_Z);
+  CPF_SMEM_ATTR((k_fz<N, 2>), sm_z, CPF_CARVE_Z);
+  CPF_SMEM_ATTR((k_iz<N, true>), sm_z, CPF_CARVE_Z);
+  CPF_SMEM_ATTR((k_iz<N, false>), sm_z, CPF_CARVE_Z);
+  CPF_SMEM_ATTR((k_fy<N, -1, false>), sm_y, CPF_CARVE_Y);
+  CPF_SMEM_ATTR((k_fy<N, -1, true>), sm_y, CPF_CARVE_Y);
+  CPF_SMEM_ATTR((k_fy<N, +1, false>), sm_y, CPF_CARVE_Y);
+  CPF_SMEM_ATTR((k_fx<N, false>), sm_x, CPF_CARVE_X);
+  CPF_SMEM_ATTR((k_fx<N, true>), sm_x, CPF_CARVE_X);
   return 0;
 }
 int cpf_pow2_init(cpfft_handle* h) {
