@@ -11,7 +11,7 @@
 #define UPD_THREADS 128
 #endif
 #ifndef MM10_MIN_CTAS
-#define MM10_MIN_CTAS 3
+#define MM10_MIN_CTAS 2     // 255 registers; 3 CTAs (168 registers) spill and run 1.5x slower
 #endif
 #include "kin.cuh"
 #include "mm01.cuh"
@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm01(UpdArgs a) {
   for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] = cep[k];
 }
 
-#define MM10_SMEM_DOUBLES (9 + 9 + 49)   // RWQ, RWR, lagged Jacobian per thread
 __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdArgs a) {
   extern __shared__ double mm10_sm[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,10 +134,10 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) c.Q[3 * i + j] = Rpn[3 * j + i];
-  c.RWQ.p = mm10_sm + threadIdx.x;
-  c.RWR.p = mm10_sm + 9 * UPD_THREADS + threadIdx.x;
-  SArr J7;
-  J7.p = mm10_sm + 18 * UPD_THREADS + threadIdx.x;
+  c.J.p = mm10_sm + MM10_SM_J * UPD_THREADS + threadIdx.x;
+  c.RWQ.p = mm10_sm + MM10_SM_RWQ * UPD_THREADS + threadIdx.x;
+  c.RWR.p = mm10_sm + MM10_SM_RWR * UPD_THREADS + threadIdx.x;
+  c.acc.p = mm10_sm + MM10_SM_ACC * UPD_THREADS + threadIdx.x;
   cpf_rvw(c.Q, c.RWQ);
   cpf_rvw(R, c.RWR);
   const double dt = a.dt;
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
     for (int k = 0; k < 36; ++k) tang[k] = __ldg(c.C + k);
     if (!no_load) {
       double R1[7];
-      mm10_resid(c, x, x[6], R1, false, nullptr);
+      mm10_resid(c, x, x[6], R1, false);
 #pragma unroll
       for (int k = 0; k < 6; ++k) x[k] = x[k] - R1[k];
     }
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
       c.dg = cr.alter_mode ? cr.eps_dot_0_y * c.tinc : sqrt((2.0 / 3.0) * ((t1 * sc * sc) + 0.5 * (t2 * sc * sc)));
       if (!cr.alter_mode && sc == 1.0) c.dg = dg_full;
       x[6] = c.ttn;
-      fail = mm10_solve(c, x, cos_ang * ttrate_n * (dt * stp), J7, &itp, &itu, &h_last);
+      fail = mm10_solve(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
       if (fail) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) x[k] = ox[k];
@@ -236,17 +235,30 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
 #pragma unroll
       for (int k = 0; k < 6; ++k) c.D[k] = de[k];
       c.dg = dg_full; c.tinc = dt;
-      // mm10_tangent (Voce: ed = 0, dgammadd = 0): T = (J11 - J12 J21 / J22)^-1 C
-      double JJ[36];
+      // mm10_tangent (Voce: ed = 0, dgammadd = 0): T = (J11 - J12 J21 / J22)^-1 C.  The Schur
+      // complement replaces the lagged Jacobian in shared memory (padded to 7x7) and the six
+      // columns of C go through the kernel's single LU site one at a time.
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        const double beta = c.J[42 + j] / c.J[48];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const double beta = J7[42 + j] / J7[48];
-          JJ[6 * i + j] = J7[7 * i + j] - J7[7 * i + 6] * beta;
-          tang[6 * i + j] = __ldg(c.C + 6 * i + j);
-        }
-      cpf_lu_solve<6, 6>(JJ, tang);
+        for (int i = 0; i < 6; ++i) c.J[7 * i + j] = c.J[7 * i + j] - c.J[7 * i + 6] * beta;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { c.J[7 * k + 6] = 0.0; c.J[42 + k] = 0.0; }
+      c.J[48] = 1.0;
+#pragma unroll 1
+      for (int col = 0; col < 6; ++col) {
+        double b7[7];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) b7[k] = __ldg(c.C + 6 * k + col);
+        b7[6] = 0.0;
+        mm10_lu7(c.J.p, 1.0, b7);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c.acc[6 * k + col] = b7[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 36; ++k) tang[k] = c.acc[k];
 #pragma unroll
       for (int i = 0; i < 6; ++i)   // mm10_a_make_symm_1
 #pragma unroll
@@ -333,8 +345,8 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
       m3_mul_nt(Rp1, R, w1);
       m3_mul(g, w1, fr);
       const double PI = 3.141592653589793;
-      double psi = atan2(fr[7], fr[6]); if (psi < 0.0) psi += 2.0 * PI;
-      double phi = atan2(fr[5], fr[2]); if (phi < 0.0) phi += 2.0 * PI;
+      double psi = cpf_atan2(fr[7], fr[6]); if (psi < 0.0) psi += 2.0 * PI;
+      double phi = cpf_atan2(fr[5], fr[2]); if (phi < 0.0) phi += 2.0 * PI;
       double f33 = fr[8]; if (f33 > 1.0) f33 = 1.0;
       const double th = acos(f33);
       euler[0] = 180.0 / PI * psi; euler[1] = 180.0 / PI * th; euler[2] = 180.0 / PI * phi;
@@ -347,12 +359,18 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
     work_inc = x[0] * de[0] + x[1] * de[1] + x[2] * de[2] + x[3] * de[3] + x[4] * de[4] + x[5] * de[5];
     // lattice strain: ee = RE(R) (C^-1 sigma)
     {
-      double S[36], eu[6];
+      double eu[7];   // C^-1 sigma through the same LU site (C padded to 7x7 in shared memory)
 #pragma unroll
-      for (int k = 0; k < 36; ++k) S[k] = __ldg(c.C + k);
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) c.J[7 * i + j] = __ldg(c.C + 6 * i + j);
+        c.J[7 * i + 6] = 0.0; c.J[42 + i] = 0.0;
+      }
+      c.J[48] = 1.0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) eu[k] = x[k];
-      cpf_lu_solve<6, 1>(S, eu);
+      eu[6] = 0.0;
+      mm10_lu7(c.J.p, 1.0, eu);
       // ee = RT2RVE(R) eeunrot: the stress-type operator (mm10_a.f:3538-3539), i.e. R E~ R^T
       double E[9], T[9], S2[9];
       v6_to_m3(eu, E);
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
     }
     if (ec_dot < 1.e-100) u14 = 0.0;
     else if (n_eff > 100.0) u14 = -1.0;
-    else u14 = ec_dot / pow(u13, n_eff);
+    else u14 = ec_dot / cpf_pow(u13, n_eff);
   } else {
     for (int s = 0; s < nslip; ++s) {
       a.hist_n1[(L.c_slipinc + s) * n3 + e] = 0.0;

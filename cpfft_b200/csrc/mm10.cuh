@@ -20,14 +20,43 @@
 //    mm10_slipinc up to three times) and by repeated squaring when n-1 is a small integer.
 // Control flow that decides iteration counts (tolerances, Armijo test, at least one update
 // iteration, lagged Jacobian for the tangent, sub-stepping) follows the reference exactly.
+//
+// Code layout.  The first version of this kernel was instruction-fetch bound (17 k SASS
+// instructions, instruction-cache hit rate 56 %, "no instruction" the top stall reason in ncu).
+// Now the stress predictor (6 unknowns) and the coupled update (7 unknowns) of mm10_solve run
+// through ONE Newton state machine with one residual site, one Jacobian site and one
+// non-inlined 7x7 LU; the predictor pads its system with an identity row / column, which
+// leaves the arithmetic of the first six unknowns bit-identical.  The tangent (6 right-hand
+// sides) and the lattice-strain solve reuse the same LU.  Libm functions with long inline
+// expansions sit behind non-inlined wrappers.
 #pragma once
 #include "kin.cuh"
 #include "common.cuh"
 
+#ifndef MM10_THREADS
+#define MM10_THREADS 128
+#endif
+
+// Per-thread array kept in shared memory, element k of thread t at p[k * blockDim + t]:
+// conflict-free, and it takes the Jacobian and the skew-rotation operators out of the
+// register budget of the Newton loop.
+struct SArr {
+  double* p;
+  CPF_DI double& operator[](int k) const { return p[k * MM10_THREADS]; }
+};
+#define MM10_SM_J 0      // 49: Jacobian of the last Newton step (lagged for the tangent)
+#define MM10_SM_RWQ 49   // 9 : RW(Rp_n^T)
+#define MM10_SM_RWR 58   // 9 : RW(R)
+#define MM10_SM_ACC 67   // 39: S (21) and T (18) slip sums of the Jacobian
+#define MM10_SMEM_DOUBLES 106
+
+static __device__ __noinline__ double cpf_pow(double x, double y) { return pow(x, y); }
+static __device__ __noinline__ double cpf_atan2(double y, double x) { return atan2(y, x); }
+
 CPF_DI double cpf_sgn(double x) { return x >= 0.0 ? 1.0 : -1.0; }  // Fortran sign(one,x)
 
 CPF_DI double cpf_pow_abs(double x, int ie, double fe) {  // x >= 0
-  if (ie < 0) return pow(x, fe);
+  if (ie < 0) return cpf_pow(x, fe);
   double r = 1.0, b = x;
   int e = ie;
   while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
@@ -43,22 +72,6 @@ CPF_DI void cpf_symsw(const double* s, const double* w, double* sw) {
   sw[4] = 0.5 * (w[0] * (s[1] - s[2]) + w[1] * s[3] + w[2] * s[5]);
   sw[5] = 0.5 * (w[1] * (s[0] - s[2]) + w[0] * s[3] - w[2] * s[4]);
 }
-// Per-thread array kept in shared memory, element k of thread t at p[k * blockDim + t]:
-// conflict-free, and it takes the lagged Jacobian and the two skew-rotation operators out of
-// the register budget of the Newton loops.
-#ifndef MM10_UNROLL
-#define MM10_UNROLL 1
-#endif
-#define MM10_PRAGMA_(x) _Pragma(#x)
-#define MM10_PRAGMA(x) MM10_PRAGMA_(x)
-#ifndef MM10_THREADS
-#define MM10_THREADS 128
-#endif
-struct SArr {
-  double* p;
-  CPF_DI double& operator[](int k) const { return p[k * MM10_THREADS]; }
-};
-
 // mm10_rt2rvw (mm10_a.f:1461-1479)
 template <class Out>
 CPF_DI void cpf_rvw(const double* rt, Out rv) {
@@ -85,14 +98,31 @@ CPF_DI void cpf_lu_solve(double* A, double* B) {
       double v = fabs(A[i * N + k]);
       if (v > best) { best = v; piv = i; }
     }
+    // row interchange by value selects (an `if (i == piv) swap` chain is turned into run-time
+    // indexed accesses by the optimiser, which demotes the whole matrix to local memory)
 #pragma unroll
-    for (int i = k + 1; i < N; ++i) {
-      if (i == piv) {
+    for (int j = 0; j < N; ++j) {
+      const double top = A[k * N + j];
+      double pv = top;
 #pragma unroll
-        for (int j = 0; j < N; ++j) { double t = A[k * N + j]; A[k * N + j] = A[i * N + j]; A[i * N + j] = t; }
-#pragma unroll
-        for (int j = 0; j < NR; ++j) { double t = B[k * NR + j]; B[k * NR + j] = B[i * NR + j]; B[i * NR + j] = t; }
+      for (int i = k + 1; i < N; ++i) {
+        const double cur = A[i * N + j];
+        pv = (piv == i) ? cur : pv;
+        A[i * N + j] = (piv == i) ? top : cur;
       }
+      A[k * N + j] = pv;
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      const double top = B[k * NR + j];
+      double pv = top;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const double cur = B[i * NR + j];
+        pv = (piv == i) ? cur : pv;
+        B[i * NR + j] = (piv == i) ? top : cur;
+      }
+      B[k * NR + j] = pv;
     }
     const double inv = 1.0 / A[k * N + k];
 #pragma unroll
@@ -117,6 +147,26 @@ CPF_DI void cpf_lu_solve(double* A, double* B) {
   }
 }
 
+// The one LU site of the kernel: b <- (sign * J)^-1 b for the 7x7 matrix held in shared
+// memory (left untouched).  Systems of 6 unknowns are padded with an identity row / column.
+CPF_DI void mm10_lu7_inl(SArr J, double sign, double* b) {
+  double M[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) M[k] = sign * J[k];
+  cpf_lu_solve<7, 1>(M, b);
+}
+// out-of-line copy for the cold call sites (tangent columns, lattice strain): a call makes the
+// caller spill its live registers, which the Newton loop cannot afford but the epilogue can
+static __device__ __noinline__ void mm10_lu7(const double* Jp, double sign, double* b) {
+  SArr J; J.p = const_cast<double*>(Jp);
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = b[k];
+  mm10_lu7_inl(J, sign, x);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) b[k] = x[k];
+}
+
 struct Mm10Ctx {
   const double* __restrict__ ms0;    // grain table: per system ms0[6], qs0[3] (drive_eps_sig.f:975-986)
   const double* __restrict__ C;      // rotated stiffness, 36 row-major
@@ -126,6 +176,8 @@ struct Mm10Ctx {
   double Q[9];     // Rp_n^T
   SArr RWQ;        // RW(Rp_n^T), 9 entries (shared memory)
   SArr RWR;        // RW(R), 9 entries (shared memory)
+  SArr J;          // 7x7 Jacobian (shared memory)
+  SArr acc;        // 39 Jacobian slip sums (shared memory)
   double sn[6];    // stress at n
   double ttn;      // tau_tilde at n
   double D[6];     // strain increment of the (sub)step
@@ -163,17 +215,16 @@ CPF_DI double mm10_hfac(const Mm10Ctx& c, double tt, double* hterm_out) {
   const double hterm = 1.0 - (tt - c.tau_y) / c.tau_v + c.taul / (tt - c.tau_y);
   *hterm_out = hterm;
   const double ah = fabs(hterm);
-  const double pw = (c.voche_m == 1.0) ? ah : pow(ah, c.voche_m);
+  const double pw = (c.voche_m == 1.0) ? ah : cpf_pow(ah, c.voche_m);
   return pw * cpf_sgn(hterm);
 }
 
-// Residual (mm10_formR / formR1 / formR2).  R[0..5] = R1, R[6] = R2 (if want2); returns the
-// hardening target h (np1%tt_rate = (h - tt_n)/tinc).  wq_out: lattice-frame sum of
-// (slip + diffusion) * qs, i.e. wbarp.
-CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double* R, bool want2, double* wq_out) {
+// Residual (mm10_formR / formR1 / formR2).  R[0..5] = R1, R[6] = R2 (0 unless want2); returns
+// the hardening target h (np1%tt_rate = (h - tt_n)/tinc).
+CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double* R, bool want2) {
   double dbarp[6] = {0, 0, 0, 0, 0, 0}, wq[3] = {0, 0, 0}, sabs = 0.0;
   const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v;
-  MM10_PRAGMA(unroll MM10_UNROLL)
+#pragma unroll 1
   for (int s = 0; s < c.nslip; ++s) {
     double ms[6], qs[3];
     mm10_slip_geom(c, s, ms, qs);
@@ -199,8 +250,8 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
     for (int j = 0; j < 6; ++j) s += __ldg(c.C + 6 * i + j) * w1[j];
     R[i] = sig[i] - c.sn[i] - s + 2.0 * sw[i];
   }
-  if (wq_out) { wq_out[0] = wq[0]; wq_out[1] = wq[1]; wq_out[2] = wq[2]; }
   double h = 0.0;
+  R[6] = 0.0;
   if (want2) {
     double ht;
     const double hf = mm10_hfac(c, tt, &ht);
@@ -210,84 +261,97 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
   return h;
 }
 
-// Jacobian (mm10_formJ): J is NJ x NJ row-major, NJ = 6 (J11 only, predictor) or 7.
-template <int NJ, class JT>
-CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, JT J) {
-  double S[21], T[18], dps[6], wqs[3], wqf[3], es[6], sabs = 0.0, ssum = 0.0;
+// Jacobian (mm10_formJ) into c.J (7x7 row-major, shared memory).  full = false: J11 only
+// (stress predictor), padded with an identity row / column.
+CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool full) {
+  double dps[6], wqs[3], wqf[3], es[6], sabs = 0.0, ssum = 0.0;
+  {
+    double S[21], T[18];
 #pragma unroll
-  for (int k = 0; k < 21; ++k) S[k] = 0.0;
+    for (int k = 0; k < 21; ++k) S[k] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 18; ++k) T[k] = 0.0;
+    for (int k = 0; k < 18; ++k) T[k] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { dps[k] = 0.0; es[k] = 0.0; }
+    for (int k = 0; k < 6; ++k) { dps[k] = 0.0; es[k] = 0.0; }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { wqs[k] = 0.0; wqf[k] = 0.0; }
-  const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v, dgn = c.dg * c.rate_n / tt;
-  MM10_PRAGMA(unroll MM10_UNROLL)
-  for (int s = 0; s < c.nslip; ++s) {
-    double ms[6], qs[3];
-    mm10_slip_geom(c, s, ms, qs);
-    const double rs = sig[0] * ms[0] + sig[1] * ms[1] + sig[2] * ms[2] + sig[3] * ms[3] + sig[4] * ms[4] + sig[5] * ms[5];
-    const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
-    const double slip = dgtt * p * rs;
-    const double dgdt = dgn * p + dif;
-    const double f = rs * dif + slip;
-    int q = 0;
+    for (int k = 0; k < 3; ++k) { wqs[k] = 0.0; wqf[k] = 0.0; }
+    const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v, dgn = c.dg * c.rate_n / tt;
+#pragma unroll 1
+    for (int s = 0; s < c.nslip; ++s) {
+      double ms[6], qs[3];
+      mm10_slip_geom(c, s, ms, qs);
+      const double rs = sig[0] * ms[0] + sig[1] * ms[1] + sig[2] * ms[2] + sig[3] * ms[3] + sig[4] * ms[4] + sig[5] * ms[5];
+      const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
+      const double slip = dgtt * p * rs;
+      const double dgdt = dgn * p + dif;
+      const double f = rs * dif + slip;
+      int q = 0;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      const double da = dgdt * ms[a];
+      for (int a = 0; a < 6; ++a) {
+        const double da = dgdt * ms[a];
 #pragma unroll
-      for (int b = a; b < 6; ++b) S[q++] += da * ms[b];
-    }
+        for (int b = a; b < 6; ++b) S[q++] += da * ms[b];
+      }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double dk = dgdt * qs[k];
+      for (int k = 0; k < 3; ++k) {
+        const double dk = dgdt * qs[k];
 #pragma unroll
-      for (int b = 0; b < 6; ++b) T[6 * k + b] += dk * ms[b];
-      wqf[k] += f * qs[k];
-      if (NJ == 7) wqs[k] += slip * qs[k];
-    }
-    if (NJ == 7) {
+        for (int b = 0; b < 6; ++b) T[6 * k + b] += dk * ms[b];
+        wqf[k] += f * qs[k];
+        wqs[k] += slip * qs[k];
+      }
       const double sp = cpf_sgn(rs) * p;
 #pragma unroll
       for (int k = 0; k < 6; ++k) { dps[k] += slip * ms[k]; es[k] += sp * ms[k]; }
       sabs += fabs(slip); ssum += slip;
     }
+    // park the sums in shared memory so that the column loop below can index them at run
+    // time: acc[0..20] = S packed upper triangle by rows, acc[21 + 6 k + b] = T(k, b)
+#pragma unroll
+    for (int k = 0; k < 21; ++k) c.acc[k] = S[k];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) c.acc[21 + k] = T[k];
   }
-  // J11 = C S + 2 Lsig (RWR T) + IW(wp) + I
-  double Sf[36];
-  { int q = 0;
+  // J11 = C S + 2 Lsig (RWR T) + IW(wp) + I, one column per trip
+  double rwr[9];
 #pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = a; b < 6; ++b) { Sf[6 * a + b] = S[q]; Sf[6 * b + a] = S[q]; ++q; } }
-#pragma unroll
+  for (int k = 0; k < 9; ++k) rwr[k] = c.RWR[k];
+#pragma unroll 1
   for (int b = 0; b < 6; ++b) {
-    double tcol[3] = {T[b], T[6 + b], T[12 + b]}, tc[3], sw[6];
-    cpf_mv3(c.RWR, tcol, tc);
+    double scol[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const int lo = a < b ? a : b, hi = a < b ? b : a;   // S(a,b) = packed[(lo,hi)]
+      scol[a] = c.acc[lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)];
+    }
+    const double tcol[3] = {c.acc[21 + b], c.acc[27 + b], c.acc[33 + b]};
+    double tc[3], sw[6];
+    cpf_mv3(rwr, tcol, tc);
     cpf_symsw(sig, tc, sw);
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       double s = 2.0 * sw[a];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += __ldg(c.C + 6 * a + k) * Sf[6 * k + b];
-      J[NJ * a + b] = s;
+      for (int k = 0; k < 6; ++k) s += __ldg(c.C + 6 * a + k) * scol[k];
+      c.J[7 * a + b] = s;
     }
   }
-  double w[3];
-  cpf_mv3(c.RWR, wqf, w);
-  J[NJ * 0 + 3] += 2.0 * w[2]; J[NJ * 0 + 5] += -2.0 * w[1];
-  J[NJ * 1 + 3] += 2.0 * w[2]; J[NJ * 1 + 4] += -2.0 * w[0];
-  J[NJ * 2 + 4] += 2.0 * w[0]; J[NJ * 2 + 5] += 2.0 * w[1];
-  J[NJ * 3 + 0] += w[2]; J[NJ * 3 + 1] += -w[2]; J[NJ * 3 + 4] += -w[1]; J[NJ * 3 + 5] += w[0];
-  J[NJ * 4 + 1] += w[0]; J[NJ * 4 + 2] += -w[0]; J[NJ * 4 + 3] += w[1]; J[NJ * 4 + 5] += w[2];
-  J[NJ * 5 + 0] += w[1]; J[NJ * 5 + 2] += -w[1]; J[NJ * 5 + 3] += w[0]; J[NJ * 5 + 4] += -w[2];
+  {
+    double w[3];
+    cpf_mv3(rwr, wqf, w);
+    c.J[7 * 0 + 3] += 2.0 * w[2]; c.J[7 * 0 + 5] += -2.0 * w[1];
+    c.J[7 * 1 + 3] += 2.0 * w[2]; c.J[7 * 1 + 4] += -2.0 * w[0];
+    c.J[7 * 2 + 4] += 2.0 * w[0]; c.J[7 * 2 + 5] += 2.0 * w[1];
+    c.J[7 * 3 + 0] += w[2]; c.J[7 * 3 + 1] += -w[2]; c.J[7 * 3 + 4] += -w[1]; c.J[7 * 3 + 5] += w[0];
+    c.J[7 * 4 + 1] += w[0]; c.J[7 * 4 + 2] += -w[0]; c.J[7 * 4 + 3] += w[1]; c.J[7 * 4 + 5] += w[2];
+    c.J[7 * 5 + 0] += w[1]; c.J[7 * 5 + 2] += -w[1]; c.J[7 * 5 + 3] += w[0]; c.J[7 * 5 + 4] += -w[2];
 #pragma unroll
-  for (int a = 0; a < 6; ++a) J[NJ * a + a] += 1.0;
-  if (NJ == 7) {
+    for (int a = 0; a < 6; ++a) c.J[7 * a + a] += 1.0;
+  }
+  if (full) {
     // J12 = -(n/tt) [C dps + 2 symSW(sig, RWR wqs)]
     double wc[3], sw[6];
-    cpf_mv3(c.RWR, wqs, wc);
+    cpf_mv3(rwr, wqs, wc);
     cpf_symsw(sig, wc, sw);
     const double nt = -c.rate_n / tt;
 #pragma unroll
@@ -295,143 +359,113 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, JT J) 
       double s = 2.0 * sw[a];
 #pragma unroll
       for (int k = 0; k < 6; ++k) s += __ldg(c.C + 6 * a + k) * dps[k];
-      J[NJ * a + 6] = nt * s;
+      c.J[7 * a + 6] = nt * s;
     }
     // J21 = -theta0 dg n / tt * hfac * sum sgn(rs) |rs/tt|^(n-1) ms
     double ht;
     const double hf = mm10_hfac(c, tt, &ht);
+    const double dgn = c.dg * c.rate_n / tt;
     const double fac = c.theta_0 * dgn * hf;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) J[NJ * 6 + k] = -(fac * es[k]);
+    for (int k = 0; k < 6; ++k) c.J[42 + k] = -(fac * es[k]);
     // J22 (mm10_ehard_voche)
     const double ah = fabs(ht);
-    const double pw = (c.voche_m == 1.0) ? ah : pow(ah, c.voche_m);
+    const double pw = (c.voche_m == 1.0) ? ah : cpf_pow(ah, c.voche_m);
     const double A = -1.0 / c.tau_v - c.taul / ((tt - c.tau_y) * (tt - c.tau_y));
     const double etau = (c.voche_m * A * sabs / ah - ssum * c.rate_n / tt * cpf_sgn(ht)) * pw;
-    J[NJ * 6 + 6] = 1.0 - c.theta_0 * etau;
+    c.J[48] = 1.0 - c.theta_0 * etau;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { c.J[7 * k + 6] = 0.0; c.J[42 + k] = 0.0; }
+    c.J[48] = 1.0;
   }
 }
 
-// mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening, then
-// the coupled update.  x[7] in/out.  J7 receives the last Jacobian formed (lagged).
-// Returns true on failure.
-CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, SArr J7, int* it_pred,
-                       int* it_upd, double* h_last) {
+// mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening
+// (phase 0, 6 unknowns), then the coupled update (phase 1, 7 unknowns), as one state machine.
+// x[7] in/out.  c.J keeps the last Jacobian formed (lagged tangent).  Returns true on failure.
+CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, int* it_pred, int* it_upd,
+                       double* h_last) {
   const double cc = 1.0e-4, red = 0.5;
   const int mls = 10, mmin = 1;
-  bool fail = false;
-  double inR1;
-  {  // ---- predictor ----
-    double x1[6], R1[7];
+  double y[7], dx[7], R[7];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) x1[k] = x[k];
-    const double x2 = x[6] + cos_ang_ttrate_dt;
-    mm10_resid(c, x1, x2, R1, false, nullptr);
-    double nR1 = sqrt(R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] + R1[4] * R1[4] + R1[5] * R1[5]);
-    inR1 = nR1;
-    int iter = 0;
-    while ((nR1 > c.atol1) && (nR1 / inR1 > c.rtol1)) {
-      double J[36], mJ[36], dx[6], wv[6];
-      mm10_jacobian<6, double*>(c, x1, x2, J);
+  for (int k = 0; k < 6; ++k) { y[k] = x[k]; dx[k] = 0.0; R[k] = 0.0; }
+  y[6] = x[6] + cos_ang_ttrate_dt; dx[6] = 0.0; R[6] = 0.0;
+  int phase = 0, iter = 0, ls = 0;
+  bool init = true, fail = false, done = false;
+  double alpha = 0.0, ls1 = 0.0, ls2 = 0.0, nR = 0.0, inR = 0.0, inR1 = 0.0, h = 0.0;
+  // One loop, one back edge, warp-uniform trip count: lanes that are finished idle until the
+  // slowest lane of the warp is done, so the warp reconverges at the top of every trip (a
+  // loop with several `continue` edges made the lanes run the body one after another).
+  const unsigned lanes = __activemask();
+#pragma unroll 1
+  while (__any_sync(lanes, !done)) {
+    if (!done) {
+      double yt[7], Rt[7];
 #pragma unroll
-      for (int k = 0; k < 36; ++k) mJ[k] = -J[k];
+      for (int k = 0; k < 7; ++k) yt[k] = init ? y[k] : y[k] + alpha * dx[k];
+      h = mm10_resid(c, yt, yt[6], Rt, phase == 1);
+      double dot = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dx[k] = R1[k];
-      double dot = R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] + R1[4] * R1[4] + R1[5] * R1[5];
-      const double ls1 = 0.5 * dot;
+      for (int k = 0; k < 7; ++k) dot += Rt[k] * Rt[k];
+      const double nRt = sqrt(dot);
+      bool accepted = true;
+      if (init) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
-        wv[j] = J[j] * R1[0] + J[6 + j] * R1[1] + J[12 + j] * R1[2] + J[18 + j] * R1[3] + J[24 + j] * R1[4] + J[30 + j] * R1[5];
-      cpf_lu_solve<6, 1>(mJ, dx);
-      const double ls2 = cc * (dx[0] * wv[0] + dx[1] * wv[1] + dx[2] * wv[2] + dx[3] * wv[3] + dx[4] * wv[4] + dx[5] * wv[5]);
-      double alpha = 1.0;
-      int ls = 0;
-      for (;;) {
-        const double nlsx = ls1 + ls2 * alpha;
-        double xn[6];
+        for (int k = 0; k < 7; ++k) R[k] = Rt[k];
+        nR = nRt; inR = nRt; iter = 0;
+        if (phase == 0) inR1 = nRt;
+        else if (inR == 0.0) inR = inR1;
+        init = false;
+      } else if (!((0.5 * dot <= ls1 + ls2 * alpha) || (ls > mls))) {
+        alpha = red * alpha; ls = ls + 1;        // Armijo test failed: shorter step, same direction
+        accepted = false;
+      } else {
+        bool nan = false;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) xn[k] = x1[k] + alpha * dx[k];
-        mm10_resid(c, xn, x2, R1, false, nullptr);
-        dot = R1[0] * R1[0] + R1[1] * R1[1] + R1[2] * R1[2] + R1[3] * R1[3] + R1[4] * R1[4] + R1[5] * R1[5];
-        nR1 = sqrt(dot);
-        if ((0.5 * dot <= nlsx) || (ls > mls)) {
-#pragma unroll
-          for (int k = 0; k < 6; ++k) x1[k] = xn[k];
-          break;
-        }
-        alpha = red * alpha; ls = ls + 1;
+        for (int k = 0; k < 7; ++k) { y[k] = yt[k]; R[k] = Rt[k]; nan = nan || isnan(yt[k]); }
+        nR = nRt;
+        iter = iter + 1;
+        if ((iter > c.miter) || nan) { fail = true; done = true; }
       }
-      iter = iter + 1;
-      bool nan = false;
+      if (accepted && !done) {
+        const bool go = (phase == 0) ? ((nR > c.atol1) && (nR / inR > c.rtol1))
+                                     : (((nR > c.atol) && (nR / inR > c.rtol)) || (iter < mmin));
+        if (!go) {
+          if (phase == 0) { *it_pred += iter; phase = 1; init = true; }
+          else { *it_upd += iter; done = true; }
+        } else {
+          // Newton step: dx = -J^-1 R with the Armijo data of the line search
+          mm10_jacobian(c, y, y[6], phase == 1);
+          double wv[7];
+          dot = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) nan = nan || isnan(x1[k]);
-      if ((iter > c.miter) || nan) { fail = true; break; }
-    }
-    *it_pred += iter;
-    if (!fail) {
+          for (int k = 0; k < 7; ++k) { dx[k] = R[k]; dot += R[k] * R[k]; }
+          ls1 = 0.5 * dot;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) x[k] = x1[k];
-      x[6] = x2;
+          for (int j = 0; j < 7; ++j) {
+            double sj = 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) sj += c.J[7 * i + j] * R[i];
+            wv[j] = sj;
+          }
+          mm10_lu7_inl(c.J, -1.0, dx);
+          double d = 0.0;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) d += dx[k] * wv[k];
+          ls2 = cc * d;
+          alpha = 1.0; ls = 0;
+        }
+      }
     }
   }
-  if (fail) return true;  // reference still runs the update but discards its result (fail stays set)
-  {  // ---- coupled update ----
-    double R[7];
-    double h = mm10_resid(c, x, x[6], R, true, nullptr);
-    double dot = 0.0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) dot += R[k] * R[k];
-    double nR = sqrt(dot), inR = nR;
-    if (inR == 0.0) inR = inR1;
-    int iter = 0;
-    while (((nR > c.atol) && (nR / inR > c.rtol)) || (iter < mmin)) {
-      double mJ[49], dx[7], wv[7];
-      mm10_jacobian<7, SArr>(c, x, x[6], J7);
-#pragma unroll
-      for (int k = 0; k < 49; ++k) mJ[k] = -J7[k];
-      dot = 0.0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) { dx[k] = R[k]; dot += R[k] * R[k]; }
-      const double ls1 = 0.5 * dot;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) s += J7[7 * i + j] * R[i];
-        wv[j] = s;
-      }
-      cpf_lu_solve<7, 1>(mJ, dx);
-      double d = 0.0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) d += dx[k] * wv[k];
-      const double ls2 = cc * d;
-      double alpha = 1.0;
-      int ls = 0;
-      for (;;) {
-        const double nlsx = ls1 + ls2 * alpha;
-        double xn[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) xn[k] = x[k] + alpha * dx[k];
-        h = mm10_resid(c, xn, xn[6], R, true, nullptr);
-        dot = 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) dot += R[k] * R[k];
-        nR = sqrt(dot);
-        if ((0.5 * dot <= nlsx) || (ls > mls)) {
-#pragma unroll
-          for (int k = 0; k < 7; ++k) x[k] = xn[k];
-          break;
-        }
-        alpha = red * alpha; ls = ls + 1;
-      }
-      iter = iter + 1;
-      bool nan = false;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) nan = nan || isnan(x[k]);
-      if ((iter > c.miter) || nan) { fail = true; break; }
-    }
-    *it_upd += iter;
-    *h_last = h;
+  if (fail) {
+    if (phase == 0) *it_pred += iter; else *it_upd += iter;
+    return true;
   }
-  return fail;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = y[k];
+  *h_last = h;
+  return false;
 }
