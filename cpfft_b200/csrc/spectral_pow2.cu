@@ -34,8 +34,8 @@ struct PeerPtrs { cplx* p[CPF_MAX_WORLD]; };
 template <int N> struct Pow2Cfg {
   static constexpr int H = N / 2;
   static constexpr int TZY = (H < 16 ? H : 16) < (4096 / N) ? (H < 16 ? H : 16) : (4096 / N);
-  static constexpr int TZX = (H < 8 ? H : 8) < (2048 / N) ? (H < 8 ? H : 8) : (2048 / N);
-  static constexpr int ZT = (N + 31) / 32 * 32;     // threads of k_fz / k_iz (N of them work)
+  static constexpr int TZX = (H < 8 ? H : 8) < (2048 / N) ? (H < 8 ? H : 8) : (2048 / N);   // 512: 4
+  static constexpr int ZT = (N / 2 + 31) / 32 * 32;   // threads of k_fz / k_iz (N/2 of them work)
 };
 // resident CTAs per SM the z passes are compiled for (register budget 64K / (threads * CTAs))
 #ifndef CPF_ZMINB
@@ -52,106 +52,114 @@ template <int N> struct Pow2Cfg {
 #endif
 // measured at 256^3: k_iz gains from 3 resident CTAs (0.92 -> 0.78 ms), k_fz loses (1.91 -> 2.05 ms);
 // giving the whole L1 to shared memory (carveout) slows every pass down
-template <int N> struct ZOcc {
-  static constexpr int MINB_FZ = CPF_ZMINB;
-  static constexpr int MINB_IZ = Pow2Cfg<N>::ZT <= 256 ? 3 : 1;
-};
+// keep >= 512 threads resident per SM: without a floor the compiler spends 254 registers per
+// thread on k_fz and a single CTA fits (measured at 320^3: occupancy 7.6 %, 56 % of HBM)
+template <int N> struct ZOcc { static constexpr int MINB = (512 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT; };
 #ifndef CPF_TZX256
-#define CPF_TZX256 4     // measured: k_fx 0.84 ms with 8 kz per CTA (1 CTA/SM), 0.75 ms with 4 (3 CTAs/SM)
+#define CPF_TZX256 8     // two-line x pass: 2 * 256 * 8 * 16 B = 64 KB per CTA, 3 CTAs/SM, 128-byte runs
 #endif
-template <> struct Pow2Cfg<256> { static constexpr int H = 128, TZY = 16, TZX = CPF_TZX256, ZT = 256; };
-template <> struct Pow2Cfg<40> { static constexpr int H = 20, TZY = 10, TZX = 5, ZT = 64; };
-template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, ZT = 96; };
-template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 224; };
-template <> struct Pow2Cfg<320> { static constexpr int H = 160, TZY = 16, TZX = 8, ZT = 320; };
-template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8, ZT = 416; };
-
-template <int N> __device__ __forceinline__ constexpr int last_radix() {
-  return FftPlan<N>::R3 > 1 ? FftPlan<N>::R3 : (FftPlan<N>::R2 > 1 ? FftPlan<N>::R2 : FftPlan<N>::R1);
-}
-
-// all stages of an in-place transform over `nlines` lines held in shared memory through the
-// accessor a(line, i); tasks are dealt round-robin to the CTA's threads
-// (TWM = twiddle table length / N)
-template <int N, int DIR, int TWM, class Acc>
-__device__ __forceinline__ void smem_fft_dif(int nlines, const cplx* tw, Acc a) {
-  typedef FftPlan<N> P;
-  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
-  for (int task = threadIdx.x; task < nlines * (N / P::R1); task += blockDim.x) {
-    const int line = task / (N / P::R1), j = task - line * (N / P::R1);
-    fft_stage_dif<N, P::R1, DIR, TWM>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
-  }
-  __syncthreads();
-  if (P::R2 > 1) {
-    for (int task = threadIdx.x; task < nlines * (N / P::R2); task += blockDim.x) {
-      const int line = task / (N / P::R2), j = task - line * (N / P::R2);
-      fft_stage_dif<N1, P::R2, DIR, TWM * (N / N1)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
-    }
-    __syncthreads();
-  }
-  if (P::R3 > 1) {
-    for (int task = threadIdx.x; task < nlines * (N / P::R3); task += blockDim.x) {
-      const int line = task / (N / P::R3), j = task - line * (N / P::R3);
-      fft_stage_dif<N2, P::R3, DIR, TWM * (N / N2)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
-    }
-    __syncthreads();
-  }
-}
-template <int N, int TWM, class Acc>
-__device__ __forceinline__ void smem_fft_dit_inv(int nlines, const cplx* tw, Acc a) {
-  typedef FftPlan<N> P;
-  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
-  if (P::R3 > 1) {
-    for (int task = threadIdx.x; task < nlines * (N / P::R3); task += blockDim.x) {
-      const int line = task / (N / P::R3), j = task - line * (N / P::R3);
-      fft_stage_dit_inv<N2, P::R3, TWM * (N / N2)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
-    }
-    __syncthreads();
-  }
-  if (P::R2 > 1) {
-    for (int task = threadIdx.x; task < nlines * (N / P::R2); task += blockDim.x) {
-      const int line = task / (N / P::R2), j = task - line * (N / P::R2);
-      fft_stage_dit_inv<N1, P::R2, TWM * (N / N1)>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
-    }
-    __syncthreads();
-  }
-  for (int task = threadIdx.x; task < nlines * (N / P::R1); task += blockDim.x) {
-    const int line = task / (N / P::R1), j = task - line * (N / P::R1);
-    fft_stage_dit_inv<N, P::R1, TWM>(j, tw, [&](int i) { return a(line, i); }, [&](int i, cplx v) { a(line, i) = v; });
-  }
-  __syncthreads();
-}
+template <> struct Pow2Cfg<256> { static constexpr int H = 128, TZY = 16, TZX = CPF_TZX256, ZT = 128; };
+template <> struct Pow2Cfg<40> { static constexpr int H = 20, TZY = 10, TZX = 5, ZT = 32; };
+template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, ZT = 64; };
+template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 128; };
+template <> struct Pow2Cfg<320> { static constexpr int H = 160, TZY = 16, TZX = 8, ZT = 160; };
+template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8, ZT = 224; };
 
 // ---------------------------------------------------------------------------------------------
-// z passes.  Shared memory: 18 packed lines (2 grid lines x 9 components) of H complex, padded
-// by one slot per `RL` (last radix) so that the stride-RL accesses of the last stage spread
-// over the banks; followed by the twiddle table of the FULL length N (the H-point transform
-// uses every second entry).
+// z passes: one grid line (x, y) and its 9 components per CTA, H = N/2 threads, two voxels
+// (one packed complex sample) per thread.
+//
+// Shared memory, both conflict-free for every radix plan:
+//   A[i * 9 + c]      the 9 packed lines, component fastest; the in-place FFT stages run on it
+//                     with the component as the fastest task index (a quarter warp touches
+//                     8-9 consecutive slots of one element index);
+//   B[c * HB + k]     natural-order spectrum rows with an odd pitch HB, used for the
+//                     (k, H-k) tangling next to the global rows;
+//   tw[N]             the twiddle table of the FULL length N (the H-point transform uses
+//                     every second entry).
+// The last forward stage writes A -> B (digit-reversed position -> natural bin), the first
+// inverse stage reads B -> A, so neither side needs a separate reordering pass.
 template <int N> struct ZSmem {
   static constexpr int H = N / 2;
-  static constexpr int RL = last_radix<H>();
-  static constexpr int HP = H + H / RL;
-  static __device__ __forceinline__ int pad(int i) { return i + i / RL; }
-  static constexpr size_t bytes = sizeof(cplx) * (18 * HP + N);
+  static constexpr int HB = H + 1 + (H & 1);           // odd pitch of the B rows
+  static constexpr size_t bytes = sizeof(cplx) * (9 * H + 9 * HB + N);
 };
+
+// all stages but the last of the forward transform, in place on A (task = j * 9 + c)
+template <int H, class StoreLast>
+__device__ __forceinline__ void z_fft_fwd(cplx* A, const cplx* tw, StoreLast store_last) {
+  typedef FftPlan<H> P;
+  constexpr int N1 = H / P::R1, N2 = N1 / P::R2;
+  constexpr bool one = (P::R2 == 1), two = (P::R3 == 1);
+  for (int task = threadIdx.x; task < 9 * (H / P::R1); task += blockDim.x) {
+    const int j = task / 9, c = task - j * 9;
+    if (one) fft_stage_dif<H, P::R1, -1, 2>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { store_last(c, i, v); });
+    else fft_stage_dif<H, P::R1, -1, 2>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+  }
+  __syncthreads();
+  if constexpr (!one) {
+    for (int task = threadIdx.x; task < 9 * (H / P::R2); task += blockDim.x) {
+      const int j = task / 9, c = task - j * 9;
+      if (two) fft_stage_dif<N1, P::R2, -1, 2 * (H / N1)>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { store_last(c, i, v); });
+      else fft_stage_dif<N1, P::R2, -1, 2 * (H / N1)>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+    }
+    __syncthreads();
+  }
+  if constexpr (!two) {
+    for (int task = threadIdx.x; task < 9 * (H / P::R3); task += blockDim.x) {
+      const int j = task / 9, c = task - j * 9;
+      fft_stage_dif<N2, P::R3, -1, 2 * (H / N2)>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { store_last(c, i, v); });
+    }
+    __syncthreads();
+  }
+}
+// inverse (transposed) transform: the first stage loads through load_first(c, position)
+template <int H, class LoadFirst>
+__device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst load_first) {
+  typedef FftPlan<H> P;
+  constexpr int N1 = H / P::R1, N2 = N1 / P::R2;
+  constexpr bool one = (P::R2 == 1), two = (P::R3 == 1);
+  if (!two) {
+    for (int task = threadIdx.x; task < 9 * (H / P::R3); task += blockDim.x) {
+      const int j = task / 9, c = task - j * 9;
+      fft_stage_dit_inv<N2, P::R3, 2 * (H / N2)>(j, tw, [&](int i) { return load_first(c, i); }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+    }
+    __syncthreads();
+  }
+  if (!one) {
+    for (int task = threadIdx.x; task < 9 * (H / P::R2); task += blockDim.x) {
+      const int j = task / 9, c = task - j * 9;
+      if (two) fft_stage_dit_inv<N1, P::R2, 2 * (H / N1)>(j, tw, [&](int i) { return load_first(c, i); }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+      else fft_stage_dit_inv<N1, P::R2, 2 * (H / N1)>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+    }
+    __syncthreads();
+  }
+  for (int task = threadIdx.x; task < 9 * (H / P::R1); task += blockDim.x) {
+    const int j = task / 9, c = task - j * 9;
+    if (one) fft_stage_dit_inv<H, P::R1, 2>(j, tw, [&](int i) { return load_first(c, i); }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+    else fft_stage_dit_inv<H, P::R1, 2>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { A[i * 9 + c] = v; });
+  }
+  __syncthreads();
+}
 
 // MODE 0: transform src.  MODE 1: transform K4 : src (G_K_dF with flgK).  MODE 2: the CG
 // direction update p <- r + beta p (FFT_nr3.f:290, MKL dcg) fused in front of MODE 1: src is p
 // (read and written), rvec is the residual.
 template <int N, int MODE>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB_FZ) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
                                           cplx* __restrict__ spec, const double* __restrict__ rvec, double beta) {
   typedef ZSmem<N> Z;
-  constexpr int H = Z::H;
+  constexpr int H = Z::H, HB = Z::HB;
   extern __shared__ cplx sm[];
-  cplx* zb = sm;
-  cplx* tw = sm + 18 * Z::HP;
+  cplx* A = sm;
+  cplx* B = sm + 9 * H;
+  cplx* tw = B + 9 * HB;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   const int64_t n3 = g.n3;
-  const int l = threadIdx.x / H, t = threadIdx.x - l * H;
-  const int64_t L = (int64_t)2 * blockIdx.x + l;          // grid line x * N + y
+  const int t = threadIdx.x;
+  const int64_t L = blockIdx.x;                         // grid line x * N + y
   const int64_t e0 = L * N + 2 * t;
-  if (threadIdx.x < N) {
+  if (t < H) {
     double2 f[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) f[c] = *reinterpret_cast<const double2*>(src + c * n3 + e0);
@@ -175,93 +183,88 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB_FZ) k_fz(Pow2Arg
         // ddot42n's summation tree (G_K_dF.f:258-264)
         const double va = ta[0] + (((ta[1] + ta[5]) + (ta[3] + ta[7])) + ((ta[2] + ta[6]) + (ta[4] + ta[8])));
         const double vb = tb[0] + (((tb[1] + tb[5]) + (tb[3] + tb[7])) + ((tb[2] + tb[6]) + (tb[4] + tb[8])));
-        zb[(l * 9 + i) * Z::HP + Z::pad(t)] = make_double2(va, vb);
+        A[t * 9 + i] = make_double2(va, vb);
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) zb[(l * 9 + c) * Z::HP + Z::pad(t)] = f[c];
+      for (int c = 0; c < 9; ++c) A[t * 9 + c] = f[c];
     }
   }
   __syncthreads();
-  // the H-point transform uses w_H^j = w_N^(2j): table stride multiplier 2
-  smem_fft_dif<H, -1, 2>(18, tw, [&](int line, int i) -> cplx& { return zb[line * Z::HP + Z::pad(i)]; });
+  z_fft_fwd<H>(A, tw, [&](int c, int p, cplx v) { B[c * HB + fft_natural<H>(p)] = v; });
   // untangle: X[k] = (E + w_N^k O), E = (Z[k] + conj Z[H-k]) / 2, O = (Z[k] - conj Z[H-k]) / (2 i)
   const int64_t nxN = (int64_t)g.nx * N;
-  for (int idx = threadIdx.x; idx < 18 * H; idx += blockDim.x) {
-    const int lc = idx / H, k = idx - lc * H;
-    const int ll = lc / 9, c = lc - ll * 9;
-    const cplx* line = zb + lc * Z::HP;
-    const cplx Zk = line[Z::pad(fft_position<H>(k))];
-    const cplx Zm = c_conj(line[Z::pad(fft_position<H>((k == 0) ? 0 : H - k))]);
+  for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
+    const int c = idx / H, k = idx - c * H;
+    const cplx* row = B + c * HB;
+    const cplx Zk = row[k];
+    const cplx Zm = c_conj(row[(k == 0) ? 0 : H - k]);
     const cplx E = c_add(Zk, Zm), D = c_sub(Zk, Zm);
     const cplx O = c_mul(make_double2(D.y, -D.x), tw[k]);
-    spec[((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H + k] = make_double2(0.5 * (E.x + O.x), 0.5 * (E.y + O.y));
+    spec[((int64_t)c * nxN + L) * H + k] = make_double2(0.5 * (E.x + O.x), 0.5 * (E.y + O.y));
   }
 }
 
 // DOT: also accumulate sum(dst * pvec) over the CTA's voxels (the p.Ap of CG) into
 // partials[blockIdx.x]; fixed summation order, no atomics.
 template <int N, bool DOT>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB_IZ) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                           const double* __restrict__ pvec, double* __restrict__ partials) {
   typedef ZSmem<N> Z;
-  constexpr int H = Z::H;
+  constexpr int H = Z::H, HB = Z::HB;
   extern __shared__ cplx sm[];
-  cplx* zb = sm;
-  cplx* tw = sm + 18 * Z::HP;
+  cplx* A = sm;
+  cplx* B = sm + 9 * H;
+  cplx* tw = B + 9 * HB;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
-  __syncthreads();
   const int64_t nxN = (int64_t)g.nx * N;
-  // stage the 18 half-spectrum rows at their digit-reversed positions (one coalesced read of
-  // every row), then tangle pairs (k, H-k) in place:
+  const int64_t L = blockIdx.x;
+  // stage the 9 half-spectrum rows (one coalesced read each), then tangle pairs (k, H-k) in place:
   //   Z'[k] = (X[k] + conj X[H-k]) + i w_N^-k (X[k] - conj X[H-k]),  X[H] = 0,  X[0] real
-  for (int idx = threadIdx.x; idx < 18 * H; idx += blockDim.x) {
-    const int lc = idx / H, k = idx - lc * H;
-    const int ll = lc / 9, c = lc - ll * 9;
-    zb[lc * Z::HP + Z::pad(fft_position<H>(k))] = spec[((int64_t)c * nxN + (2 * blockIdx.x + ll)) * H + k];
+  for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
+    const int c = idx / H, k = idx - c * H;
+    B[c * HB + k] = spec[((int64_t)c * nxN + L) * H + k];
   }
   __syncthreads();
   constexpr int NP = H / 2 + 1;                 // pairs per row: k = 0 .. H/2 (0 and H/2 are self-paired)
-  for (int idx = threadIdx.x; idx < 18 * NP; idx += blockDim.x) {
-    const int lc = idx / NP, k = idx - lc * NP;
-    cplx* row = zb + lc * Z::HP;
-    const int pk = Z::pad(fft_position<H>(k));
+  for (int idx = threadIdx.x; idx < 9 * NP; idx += blockDim.x) {
+    const int c = idx / NP, k = idx - c * NP;
+    cplx* row = B + c * HB;
     if (k == 0) {
-      const double x0 = row[pk].x;
-      row[pk] = make_double2(x0, x0);           // X[0] real, X[H] = 0:  Z'[0] = X0 (1 + i)
+      const double x0 = row[0].x;
+      row[0] = make_double2(x0, x0);            // X[0] real, X[H] = 0:  Z'[0] = X0 (1 + i)
     } else {
-      const int pm = Z::pad(fft_position<H>(H - k));
-      const cplx Xk = row[pk], Xh = row[pm];
+      const cplx Xk = row[k], Xh = row[H - k];
       {
         const cplx Xm = c_conj(Xh);
         const cplx E = c_add(Xk, Xm), D = c_sub(Xk, Xm);
         const cplx O = c_mulc(D, tw[k]);
-        row[pk] = make_double2(E.x - O.y, E.y + O.x);
+        row[k] = make_double2(E.x - O.y, E.y + O.x);
       }
       if (2 * k != H) {
         const cplx Xm = c_conj(Xk);
         const cplx E = c_add(Xh, Xm), D = c_sub(Xh, Xm);
         const cplx O = c_mulc(D, tw[H - k]);
-        row[pm] = make_double2(E.x - O.y, E.y + O.x);
+        row[H - k] = make_double2(E.x - O.y, E.y + O.x);
       }
     }
   }
   __syncthreads();
-  smem_fft_dit_inv<H, 2>(18, tw, [&](int line, int i) -> cplx& { return zb[line * Z::HP + Z::pad(i)]; });
-  const int l = threadIdx.x / H, t = threadIdx.x - l * H;
-  const int64_t e0 = ((int64_t)2 * blockIdx.x + l) * N + 2 * t;
+  z_fft_inv<H>(A, tw, [&](int c, int p) { return B[c * HB + fft_natural<H>(p)]; });
+  const int t = threadIdx.x;
+  const int64_t e0 = L * N + 2 * t;
   double acc = 0.0;
-  if (threadIdx.x < N) {
+  if (t < H) {
 #pragma unroll
-  for (int c = 0; c < 9; ++c) {
-    const cplx z = zb[(l * 9 + c) * Z::HP + Z::pad(t)];
-    const double2 o = make_double2(z.x * scale, z.y * scale);
-    *reinterpret_cast<double2*>(dst + c * g.n3 + e0) = o;
-    if (DOT) {
-      const double2 pv = *reinterpret_cast<const double2*>(pvec + c * g.n3 + e0);
-      acc += o.x * pv.x + o.y * pv.y;
+    for (int c = 0; c < 9; ++c) {
+      const cplx z = A[t * 9 + c];
+      const double2 o = make_double2(z.x * scale, z.y * scale);
+      *reinterpret_cast<double2*>(dst + c * g.n3 + e0) = o;
+      if (DOT) {
+        const double2 pv = *reinterpret_cast<const double2*>(pvec + c * g.n3 + e0);
+        acc += o.x * pv.x + o.y * pv.y;
+      }
     }
-  }
   }
   if (DOT) {
     __shared__ double red[32];
@@ -338,9 +341,16 @@ __global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec,
 
 // ---------------------------------------------------------------------------------------------
 // x pass: forward, Green operator, inverse.  grid = (NY, NZ / TZ, 3 tensor rows).
-// Shared memory s[(cl * N + i) * TZ + l], cl = component within the row.
-// SCATTER: the inverse-transformed line (natural x order) goes back to the x-slab layout
-// [c][x local][y global][kz] of the rank that owns x (backward transpose fused into the store).
+//
+// The Green operator of a tensor row is rank one, out_j = xi_j s with
+// s = (xi_x t0 + xi_y t1 + xi_z t2) / |xi|^2 (FFT_init.f:321-335), and xi_y, xi_z are constant
+// along an x line.  So only TWO lines per (y, kz) are transformed instead of three:
+//   forward :  A = FFTx(t0),  B = FFTx(xi_y t1 + xi_z t2)       (combined while loading)
+//   Green   :  s = (xi_x A + B) / |xi|^2;   A <- xi_x s,  B <- s
+//   inverse :  out0 = IFFTx(A),  out1 = xi_y IFFTx(B),  out2 = xi_z IFFTx(B)   (while storing)
+// Shared memory s[(line * N + i) * TZ + l].  The spectrum stays digit-reversed between the two
+// transforms.  SCATTER: the inverse-transformed lines (natural x order) go back to the x-slab
+// layout [c][x local][y global][kz] of the rank that owns x (backward transpose fused in).
 template <int N, bool SCATTER>
 __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
   typedef FftPlan<N> P;
@@ -348,97 +358,109 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec,
   constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
   extern __shared__ cplx sm[];
   cplx* s = sm;
-  cplx* tw = sm + 3 * N * TZ;
+  cplx* tw = sm + 2 * N * TZ;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   __syncthreads();
   const int y = blockIdx.x, kz0 = blockIdx.y * TZ, row = blockIdx.z;
   const int64_t xs = (int64_t)g.NY * H;                       // stride between x planes
-  cplx* G = spec + ((int64_t)(3 * row) * N * g.NY + y) * H + kz0;   // + (cl * N + x) * xs + l
+  const int64_t cs = (int64_t)N * xs;                         // stride between components
+  cplx* G = spec + ((int64_t)(3 * row) * N * g.NY + y) * H + kz0;   // + cl * cs + x * xs + l
+  const int ky = y + g.y0;
+  const double fy = (double)(ky < H ? ky : ky - N);
   // ---- forward: stage 1 from global memory ----
-  for (int task = threadIdx.x; task < 3 * TZ * (N / P::R1); task += blockDim.x) {
+  for (int task = threadIdx.x; task < 2 * TZ * (N / P::R1); task += blockDim.x) {
     const int l = task % TZ, r = task / TZ;
-    const int j = r % (N / P::R1), cl = r / (N / P::R1);
-    cplx* sc = s + cl * N * TZ + l;
-    const cplx* gc = G + (int64_t)cl * N * xs + l;
-    fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return gc[(int64_t)i * xs]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    const int j = r % (N / P::R1), ln = r / (N / P::R1);
+    cplx* sc = s + ln * N * TZ + l;
+    const cplx* gc = G + l;
+    const double fz = (double)(kz0 + l);
+    if (ln == 0)
+      fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return gc[(int64_t)i * xs]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    else
+      fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) {
+        const cplx a = gc[cs + (int64_t)i * xs], b = gc[2 * cs + (int64_t)i * xs];
+        return make_double2(fy * a.x + fz * b.x, fy * a.y + fz * b.y);
+      }, [&](int i, cplx v) { sc[i * TZ] = v; });
   }
   __syncthreads();
   if (P::R2 > 1) {
-    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R2); task += blockDim.x) {
+    for (int task = threadIdx.x; task < 2 * TZ * (N / P::R2); task += blockDim.x) {
       const int l = task % TZ, r = task / TZ;
-      const int j = r % (N / P::R2), cl = r / (N / P::R2);
-      cplx* sc = s + cl * N * TZ + l;
+      const int j = r % (N / P::R2), ln = r / (N / P::R2);
+      cplx* sc = s + ln * N * TZ + l;
       fft_stage_dif<N1, P::R2, -1, N / N1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
     }
     __syncthreads();
   }
   if (P::R3 > 1) {
-    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R3); task += blockDim.x) {
+    for (int task = threadIdx.x; task < 2 * TZ * (N / P::R3); task += blockDim.x) {
       const int l = task % TZ, r = task / TZ;
-      const int j = r % (N / P::R3), cl = r / (N / P::R3);
-      cplx* sc = s + cl * N * TZ + l;
+      const int j = r % (N / P::R3), ln = r / (N / P::R3);
+      cplx* sc = s + ln * N * TZ + l;
       fft_stage_dif<N2, P::R3, -1, N / N2>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
     }
     __syncthreads();
   }
-  // ---- Green operator on the row: out_j = xi_j (sum_l tau_l xi_l) / |xi|^2 (FFT_init.f:321-335),
-  //      zero at xi = 0 and on the Nyquist planes (even-N convention) ----
-  {
-    const int ky = y + g.y0;
-    const double fy = (double)(ky < H ? ky : ky - N);
-    for (int idx = threadIdx.x; idx < N * TZ; idx += blockDim.x) {
-      const int l = idx % TZ, p = idx / TZ;
-      const int kx = fft_natural<N>(p);
-      const double fx = (double)(kx < H ? kx : kx - N), fz = (double)(kz0 + l);
-      const double qq = fx * fx + fy * fy + fz * fz;
-      const bool zero = (kx == H) || (ky == H) || (fabs(qq) <= 1e-10);
-      cplx* a = s + p * TZ + l;
-      const cplx t0 = a[0], t1 = a[N * TZ], t2 = a[2 * N * TZ];
-      double sr = 0.0, si = 0.0;
-      if (!zero) {
-        const double iq = 1.0 / qq;
-        sr = (t0.x * fx + t1.x * fy + t2.x * fz) * iq;
-        si = (t0.y * fx + t1.y * fy + t2.y * fz) * iq;
-      }
-      a[0] = make_double2(fx * sr, fx * si);
-      a[N * TZ] = make_double2(fy * sr, fy * si);
-      a[2 * N * TZ] = make_double2(fz * sr, fz * si);
+  // ---- Green operator: zero at xi = 0 and on the Nyquist planes (even-N convention) ----
+  for (int idx = threadIdx.x; idx < N * TZ; idx += blockDim.x) {
+    const int l = idx % TZ, p = idx / TZ;
+    const int kx = fft_natural<N>(p);
+    const double fx = (double)(kx < H ? kx : kx - N), fz = (double)(kz0 + l);
+    const double qq = fx * fx + fy * fy + fz * fz;
+    const bool zero = (kx == H) || (ky == H) || (fabs(qq) <= 1e-10);
+    cplx* a = s + p * TZ + l;
+    const cplx A = a[0], B = a[N * TZ];
+    double sr = 0.0, si = 0.0;
+    if (!zero) {
+      const double iq = 1.0 / qq;
+      sr = (fx * A.x + B.x) * iq;
+      si = (fx * A.y + B.y) * iq;
     }
+    a[0] = make_double2(fx * sr, fx * si);
+    a[N * TZ] = make_double2(sr, si);
   }
   __syncthreads();
   // ---- inverse: transposed flow, last stage stores to global memory in natural order ----
   if (P::R3 > 1) {
-    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R3); task += blockDim.x) {
+    for (int task = threadIdx.x; task < 2 * TZ * (N / P::R3); task += blockDim.x) {
       const int l = task % TZ, r = task / TZ;
-      const int j = r % (N / P::R3), cl = r / (N / P::R3);
-      cplx* sc = s + cl * N * TZ + l;
+      const int j = r % (N / P::R3), ln = r / (N / P::R3);
+      cplx* sc = s + ln * N * TZ + l;
       fft_stage_dit_inv<N2, P::R3, N / N2>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
     }
     __syncthreads();
   }
   if (P::R2 > 1) {
-    for (int task = threadIdx.x; task < 3 * TZ * (N / P::R2); task += blockDim.x) {
+    for (int task = threadIdx.x; task < 2 * TZ * (N / P::R2); task += blockDim.x) {
       const int l = task % TZ, r = task / TZ;
-      const int j = r % (N / P::R2), cl = r / (N / P::R2);
-      cplx* sc = s + cl * N * TZ + l;
+      const int j = r % (N / P::R2), ln = r / (N / P::R2);
+      cplx* sc = s + ln * N * TZ + l;
       fft_stage_dit_inv<N1, P::R2, N / N1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
     }
     __syncthreads();
   }
-  for (int task = threadIdx.x; task < 3 * TZ * (N / P::R1); task += blockDim.x) {
+  for (int task = threadIdx.x; task < 2 * TZ * (N / P::R1); task += blockDim.x) {
     const int l = task % TZ, r = task / TZ;
-    const int j = r % (N / P::R1), cl = r / (N / P::R1);
-    cplx* sc = s + cl * N * TZ + l;
-    cplx* gc = G + (int64_t)cl * N * xs + l;
-    const int c = 3 * row + cl;
-    fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) {
+    const int j = r % (N / P::R1), ln = r / (N / P::R1);
+    cplx* sc = s + ln * N * TZ + l;
+    const double fz = (double)(kz0 + l);
+    const int c0 = 3 * row;
+    // destination of element (component c, x plane i) of this CTA's (y, kz0 + l)
+    auto put = [&](int c, int i, cplx v) {
       if (SCATTER) {
         const int q = i / g.nx, xl = i - q * g.nx;       // owner of x plane i
-        peers.p[q][(((int64_t)c * g.nx + xl) * N + (g.y0 + y)) * H + kz0 + l] = v;
+        peers.p[q][(((int64_t)c * g.nx + xl) * N + ky) * H + kz0 + l] = v;
       } else {
-        gc[(int64_t)i * xs] = v;
+        G[(int64_t)(c - c0) * cs + (int64_t)i * xs + l] = v;
       }
-    });
+    };
+    if (ln == 0)
+      fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { put(c0, i, v); });
+    else
+      fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) {
+        put(c0 + 1, i, make_double2(fy * v.x, fy * v.y));
+        put(c0 + 2, i, make_double2(fz * v.x, fz * v.y));
+      });
   }
 }
 
@@ -449,7 +471,7 @@ int cpf_exchange_bwd(cpfft_handle* h);
 
 // cg != nullptr: the operator application of one CG iteration, q = G K4 p, with the direction
 // update (update_p) and the p.q partial sums fused into the z passes.
-struct CgFuse { const double* r; double beta; bool update_p; };
+struct CgFuse { const double* r; double beta; bool update_p; int nparts; };
 
 template <int N>
 static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, double scale_out, const CgFuse* cg) {
@@ -460,8 +482,8 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   g.nx = nx; g.x0 = h->x0; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
   PeerPtrs none = {};
   const size_t sm_z = ZSmem<N>::bytes;
-  const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
-  const unsigned zgrid = (unsigned)(nx * N / 2);
+  const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
+  const unsigned zgrid = (unsigned)(nx * N);
   int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
   if (cg && cg->update_p) k_fz<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta);
   else if (flgK) k_fz<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0);
@@ -470,7 +492,7 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   constexpr int Rm12 = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
   constexpr int RminY = P::R3 > 1 ? (Rm12 < P::R3 ? Rm12 : P::R3) : Rm12;
   constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
-  constexpr int thr_x = (3 * TZX * (N / RminY)) > 512 ? 512 : (3 * TZX * (N / RminY) < 32 ? 32 : 3 * TZX * (N / RminY));
+  constexpr int thr_x = (2 * TZX * (N / RminY)) > 512 ? 512 : (2 * TZX * (N / RminY) < 32 ? 32 : 2 * TZX * (N / RminY));
   const dim3 gy(9 * nx, H / TZY);
   if (world == 1) {
     tk = cpf_prof_begin(h, CPF_K_FFT_Y);
@@ -516,7 +538,7 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
   tk = cpf_prof_begin(h, CPF_K_INV_Z);
-  if (cg) k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, src, h->d_partials);
+  if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
   else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, nullptr, nullptr);
   cpf_prof_end(h, tk);
   h->launches += 5;
@@ -529,7 +551,7 @@ template <int N>
 static int init_pow2(cpfft_handle* h) {
   constexpr int TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
   const size_t sm_z = ZSmem<N>::bytes;
-  const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (3 * N * TZX + N);
+  const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
   // let the SM give the whole unified L1/shared array to shared memory so that 2-4 CTAs fit
 #define CPF_SMEM_ATTR(kern, bytes, carve)                                                                 \
   CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
@@ -597,7 +619,9 @@ int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK,
 //   update_p: p <- r + beta p before the product;  on return d_partials[0 .. nparts) hold the
 //   per-CTA partial sums of p.q (nparts returned).
 int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts) {
-  CgFuse cg{r, beta, update_p};
-  *nparts = h->nxloc * h->N / 2;
-  return dispatch_pow2(h, [&](auto tag) { return call_apply(tag, h, p, q, true, 1.0, &cg); });
+  CgFuse cg{r, beta, update_p, 0};
+  *nparts = h->nxloc * h->N;   // upper bound; apply_pow2 reports the exact count of z-pass CTAs
+  const int rc = dispatch_pow2(h, [&](auto tag) { return call_apply(tag, h, p, q, true, 1.0, &cg); });
+  *nparts = cg.nparts;
+  return rc;
 }
