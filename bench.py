@@ -140,11 +140,22 @@ def _oracle_steps(o, bc_rows, first_step):
     return {"nr_iters": nr, "buckets": bk, "counters": cnt, "Pbar": pb}
 
 
+def ncu_profile_data():
+    """per-launch DRAM traffic / FP64 counts measured by `ncu --set full` (tools/ncu_full.sh,
+    tools/ncu_traffic.py), committed under profiles/; None when absent"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def algorithmic_bytes_per_voxel(cls, N):
     """SURVEY.md 8d per-unit figures (FP64, half spectrum, Ghat and phases recomputed)."""
     half = 16.0 * (N // 2 + 1) / N          # complex half-spectrum bytes per voxel-component
     return {
-        "k_fwd_z_K4": (81 + 9) * 8 + 9 * half,      # K4 + x in, 9 spectrum lines out
+        # K4 + p in, 9 spectrum lines out; inside CG the kernel also reads r and writes p (+144)
+        "k_fwd_z_K4": (81 + 9) * 8 + 9 * half,
         "k_fwd_z": 9 * 8 + 9 * half,
         "k_fft_y": 2 * 9 * half,
         "k_x_green": 2 * 9 * half,
@@ -215,11 +226,14 @@ def main():
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    applies = sweeps = cgits = 0
+    applies = sweeps = cgits = nfail = nfail_final = 0
+    t_pcg = t_sig = 0.0
     nr_hist = []
     for _ in range(K):
         r = s.FFT_nr3(nstep=1, first=step0); step0 += 1
         applies += int(r["counters"][0]); sweeps += int(r["counters"][1]); cgits += int(r["counters"][2])
+        nfail += int(r["counters"][3]); nfail_final += int(r["counters"][4])
+        t_pcg += float(r["buckets"][0]); t_sig += float(r["buckets"][1])
         nr_hist.append(int(r["nr_iters"][0]))
     ev1.record(stream)
     barrier()
@@ -233,6 +247,7 @@ def main():
     s.profile(False)
     nvox = float(N) ** 3
     value = nvox * applies / secs
+    fp64_peak = s.fp64_peak()
 
     # ---- end-to-end through the public C ABI with HOST buffers (pinned) ----
     e2e = None
@@ -279,13 +294,22 @@ def main():
             gbs = b * (s.n3) / (kms / cnt * 1e-3) / 1e9
             ent.update({"alg_bytes_per_voxel": b, "achieved_gbs": gbs, "frac_of_hbm": gbs / peak})
         stages[name] = ent
+    prof = ncu_profile_data()
+    if prof and prof.get("grid") == N and world == 1:
+        for name, ent in prof["kernels"].items():
+            if name in stages:
+                stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
+                if "fp64_flop" in ent:
+                    tf = ent["fp64_flop"] / (stages[name]["ms_per_launch"] * 1e-3) / 1e12
+                    stages[name].update({"fp64_flop_per_launch_ncu": ent["fp64_flop"], "fp64_tflops": tf,
+                                         "fp64_peak_tflops_measured": fp64_peak, "frac_of_fp64": tf / fp64_peak})
     cand = [k for k in stages if "achieved_gbs" in stages[k]]
     dom = max(cand, key=lambda k: stages[k]["ms_total"]) if cand else None
     roof = None
     if dom:
         d = stages[dom]
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["achieved_gbs"] / peak, "traffic": None, "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": d["achieved_gbs"] / peak, "traffic": d.get("ncu_dram_bytes_per_launch"), "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
                 "alg_bytes_per_launch": d["alg_bytes_per_voxel"] * s.n3, "ms_per_launch": d["ms_per_launch"]}
 
     cpu = None
@@ -308,6 +332,12 @@ def main():
                    "step": "one FFT_nr3 load step", "newton_iters_per_step": nr_hist,
                    "G_K_dF_applies": applies, "drive_eps_sig_sweeps": sweeps, "cg_iterations": cgits,
                    "newton_normalised_voxel_updates_per_s": nvox * sweeps / secs,
+                   # VG/s = voxels x G_K_dF applications / bucket 1 (pcg), VU/s = voxels x
+                   # drive_eps_sig sweeps / bucket 2 (sig-eps), the reference's own thyme() buckets
+                   "VG_per_s": nvox * applies / t_pcg if t_pcg > 0 else None,
+                   "VU_per_s": nvox * sweeps / t_sig if t_sig > 0 else None,
+                   "mm10_local_failures": {"all_sweeps": nfail, "final_sweeps": nfail_final},
+                   "exchange_mode": s.exchange_mode(), "fp64_peak_tflops_measured": fp64_peak,
                    "even_N_convention": "Nyquist planes of Ghat zeroed (reference is only valid for odd N)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "stages": stages,
         "cpu_baseline": cpu,

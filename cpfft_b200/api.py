@@ -49,7 +49,7 @@ EXPORTS = [
     "cpfft_field_ncomp", "cpfft_upload", "cpfft_download", "cpfft_download_fail_flags",
     "cpfft_download_local_iters", "cpfft_material_failures", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_exchange_mode", "cpfft_synchronize",
     "cpfft_stream", "cpfft_kernel_launches", "cpfft_profile_enable", "cpfft_profile_reset",
-    "cpfft_profile_classes", "cpfft_profile_name", "cpfft_profile_get",
+    "cpfft_profile_classes", "cpfft_profile_name", "cpfft_profile_get", "cpfft_fp64_peak",
 ]
 
 
@@ -105,6 +105,7 @@ def load_library():
     L.cpfft_profile_name.argtypes = [C.c_int]
     L.cpfft_profile_name.restype = C.c_char_p
     L.cpfft_profile_get.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64)]
+    L.cpfft_fp64_peak.argtypes = [vp, dp]
     _LIB = L
     return L
 
@@ -261,6 +262,12 @@ class Solver:
             self._check(self.L.cpfft_profile_get(self.h, c, C.byref(ms), C.byref(cnt)))
             out[self.L.cpfft_profile_name(c).decode()] = (ms.value, cnt.value)
         return out
+
+    def fp64_peak(self):
+        """measured FP64 FMA peak of this GPU in TFLOP/s"""
+        v = C.c_double(0)
+        self._check(self.L.cpfft_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     def upload_ptr(self, name, ptr, layout=SOA):
         """upload from a raw host pointer (e.g. pinned memory)"""

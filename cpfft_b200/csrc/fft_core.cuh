@@ -114,6 +114,48 @@ template <int DIR> struct Dft<16, DIR> {
   }
 };
 
+// Composite radices 10 = 5 x 2 and 20 = 5 x 4 (Cooley-Tukey inside the registers):
+// n = R2 a + b, k = k1 + R1 k2: R1-point transforms over a, twiddle w_R^(b k1), R2-point over b.
+template <int R1, int R2, int DIR> struct DftCT {
+  static FHD void run(cplx* v) {
+    constexpr int R = R1 * R2;
+    // cos / sin (2 pi m / 20), m = 0..19; w_R^m uses every (20 / R)-th entry
+    const double c20[20] = {1.0, 0.95105651629515357212, 0.8090169943749474241, 0.58778525229247312917, 0.3090169943749474241,
+                            0.0, -0.3090169943749474241, -0.58778525229247312917, -0.8090169943749474241, -0.95105651629515357212,
+                            -1.0, -0.95105651629515357212, -0.8090169943749474241, -0.58778525229247312917, -0.3090169943749474241,
+                            0.0, 0.3090169943749474241, 0.58778525229247312917, 0.8090169943749474241, 0.95105651629515357212};
+    const double s20[20] = {0.0, 0.3090169943749474241, 0.58778525229247312917, 0.8090169943749474241, 0.95105651629515357212,
+                            1.0, 0.95105651629515357212, 0.8090169943749474241, 0.58778525229247312917, 0.3090169943749474241,
+                            0.0, -0.3090169943749474241, -0.58778525229247312917, -0.8090169943749474241, -0.95105651629515357212,
+                            -1.0, -0.95105651629515357212, -0.8090169943749474241, -0.58778525229247312917, -0.3090169943749474241};
+    cplx y[R2][R1];
+#pragma unroll
+    for (int b = 0; b < R2; ++b) {
+      cplx t[R1];
+#pragma unroll
+      for (int a = 0; a < R1; ++a) t[a] = v[R2 * a + b];
+      Dft<R1, DIR>::run(t);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) {
+        const int m = (b * k1) % R * (20 / R);
+        const cplx w = make_double2(c20[m], DIR < 0 ? -s20[m] : s20[m]);
+        y[b][k1] = (b == 0 || k1 == 0) ? t[k1] : c_mul(t[k1], w);
+      }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      cplx t[R2];
+#pragma unroll
+      for (int b = 0; b < R2; ++b) t[b] = y[b][k1];
+      Dft<R2, DIR>::run(t);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = t[k2];
+    }
+  }
+};
+template <int DIR> struct Dft<10, DIR> { static FHD void run(cplx* v) { DftCT<5, 2, DIR>::run(v); } };
+template <int DIR> struct Dft<20, DIR> { static FHD void run(cplx* v) { DftCT<5, 4, DIR>::run(v); } };
+
 // compile-time plan of an N-point transform
 template <int N> struct FftPlan;
 template <> struct FftPlan<8>   { static constexpr int R1 = 8,  R2 = 1,  R3 = 1; };
@@ -124,13 +166,13 @@ template <> struct FftPlan<128> { static constexpr int R1 = 16, R2 = 8,  R3 = 1;
 template <> struct FftPlan<256> { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
 template <> struct FftPlan<512> { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
 // 5-smooth sizes of the weak-scaling grids (320^3 on 2 GPUs, 400^3 on 4)
-template <> struct FftPlan<20>  { static constexpr int R1 = 5,  R2 = 4,  R3 = 1; };
+template <> struct FftPlan<20>  { static constexpr int R1 = 20, R2 = 1,  R3 = 1; };
 template <> struct FftPlan<40>  { static constexpr int R1 = 5,  R2 = 8,  R3 = 1; };
 template <> struct FftPlan<80>  { static constexpr int R1 = 5,  R2 = 16, R3 = 1; };
-template <> struct FftPlan<100> { static constexpr int R1 = 5,  R2 = 5,  R3 = 4; };
-template <> struct FftPlan<160> { static constexpr int R1 = 5,  R2 = 8,  R3 = 4; };
+template <> struct FftPlan<100> { static constexpr int R1 = 10, R2 = 10, R3 = 1; };
+template <> struct FftPlan<160> { static constexpr int R1 = 10, R2 = 16, R3 = 1; };
 template <> struct FftPlan<200> { static constexpr int R1 = 5,  R2 = 5,  R3 = 8; };
-template <> struct FftPlan<320> { static constexpr int R1 = 5,  R2 = 8,  R3 = 8; };
+template <> struct FftPlan<320> { static constexpr int R1 = 5,  R2 = 8,  R3 = 8; };   // measured: radix 20 spills in the x / y passes
 template <> struct FftPlan<400> { static constexpr int R1 = 5,  R2 = 5,  R3 = 16; };
 
 // position (after the forward stages) <-> natural frequency index

@@ -126,6 +126,19 @@ __global__ void k_final_sum(const double* partials, int nb, double* out) {  // b
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread, enough CTAs to fill
+// the chip.  MEASURED_PEAKS.json carries no FP64 figure, so the roofline denominator of the
+// material-update kernels is measured here on the device the handle lives on.
+__global__ void k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 // ------------------------------------------------------------------------------------------
 // NCCL through dlopen (the library is only needed for world > 1)
 typedef struct { char internal[128]; } cpf_ncclUniqueId;
@@ -791,6 +804,28 @@ int cpfft_nccl_init(cpfft_handle* h, const void* id128) {
     CPF_CUDA(cudaMalloc(&h->xchg_send, sizeof(double2) * spec_elems));
     CPF_CUDA(cudaMalloc(&h->xchg_recv, sizeof(double2) * spec_elems));
   }
+  return 0;
+}
+
+int cpfft_fp64_peak(cpfft_handle* h, double* tflops) {
+  if (!h || !tflops) return CPFFT_ERR_USAGE;
+  const int blocks = g_num_sms * 8, threads = 256, iters = 1 << 14;
+  double* buf = nullptr;
+  CPF_CUDA(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CPF_CUDA(cudaEventCreate(&e0)); CPF_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up
+    CPF_CUDA(cudaEventRecord(e0, h->stream));
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(buf, iters, 0.999999, 1e-9);
+    CPF_CUDA(cudaEventRecord(e1, h->stream));
+    CPF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CPF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
   return 0;
 }
 

@@ -163,6 +163,11 @@ module cpfft_iso_c
        type(c_ptr), value :: handle
        character(kind=c_char), intent(in) :: id128(128)
      end function
+     integer(c_int) function cpfft_fp64_peak(handle, tflops) bind(c, name='cpfft_fp64_peak')
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: handle
+       real(c_double), intent(out) :: tflops
+     end function
      integer(c_int) function cpfft_exchange_mode(handle) bind(c, name='cpfft_exchange_mode')
        import :: c_int, c_ptr
        type(c_ptr), value :: handle

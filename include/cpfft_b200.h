@@ -153,6 +153,9 @@ int cpfft_profile_reset(cpfft_handle* h);
 int cpfft_profile_classes(void);
 const char* cpfft_profile_name(int cls);
 int cpfft_profile_get(cpfft_handle* h, int cls, double* ms, int64_t* count);
+/* measured FP64 FMA issue peak of the device (TFLOP/s): roofline denominator of the material
+ * update kernels (MEASURED_PEAKS.json has HBM and bf16 figures only) */
+int cpfft_fp64_peak(cpfft_handle* h, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -129,7 +129,7 @@ template <int N> static void test_real_pack() {
 
 int main() {
   srand48(12345);
-  test_dft<2>(); test_dft<4>(); test_dft<5>(); test_dft<8>(); test_dft<16>();
+  test_dft<2>(); test_dft<4>(); test_dft<5>(); test_dft<8>(); test_dft<10>(); test_dft<16>(); test_dft<20>();
   printf("butterflies maxerr %.3e\n", maxerr);
   test_line<8>(); test_line<16>(); test_line<32>(); test_line<64>(); test_line<128>(); test_line<256>(); test_line<512>(); test_line<20>(); test_line<40>(); test_line<80>(); test_line<100>(); test_line<160>(); test_line<200>(); test_line<320>(); test_line<400>();
   printf("lines maxerr %.3e\n", maxerr);
