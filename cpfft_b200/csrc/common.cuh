@@ -88,7 +88,8 @@ struct cpfft_handle {
   int* d_failcnt;            // {mm10 local failures since reset, failures of the last sweep}
   int64_t n_fail, n_fail_final;
   // spectral work
-  double2* spec_a; double2* spec_b;      // half-spectrum buffers [9][nx][N][Nh]
+  double2* spec_a; double2* spec_b;      // half-spectrum buffers [9][nx][N][Nh] (x slabs) / [9][N][ny][Nh] (y slabs)
+  double2* spec_c;                       // fast path: output of the inverse y pass, input of the inverse z pass
   double2* tw;                           // twiddles exp(-2 pi i k / N)
   int radices[32]; int nrad;
   int* d_radices;

@@ -260,7 +260,8 @@ int cpf_spectral_init(cpfft_handle* h) {
   CPF_CUDA(cudaMalloc(&h->d_radices, sizeof(int) * 32));
   CPF_CUDA(cudaMemcpy(h->d_radices, h->radices, sizeof(int) * 32, cudaMemcpyHostToDevice));
   CPF_CUDA(cudaMalloc(&h->spec_a, sizeof(cplx) * spec_elems));
-  h->spec_b = nullptr;
+  h->spec_b = nullptr; h->spec_c = nullptr;
+  if (h->fast_pow2) CPF_CUDA(cudaMalloc(&h->spec_c, sizeof(cplx) * (size_t)9 * h->nxloc * N * (N / 2)));
   if ((size_t)2 * 9 * N * sizeof(cplx) > 227 * 1024) {
     cpf_set_error(h, "grid edge too large for the shared-memory z pass (N <= 806)");
     return CPFFT_ERR_USAGE;
@@ -278,7 +279,8 @@ void cpf_spectral_free(cpfft_handle* h) {
   if (h->d_radices) cudaFree(h->d_radices);
   if (h->spec_a) cudaFree(h->spec_a);
   if (h->spec_b) cudaFree(h->spec_b);
-  h->tw = nullptr; h->d_radices = nullptr; h->spec_a = h->spec_b = nullptr;
+  if (h->spec_c) cudaFree(h->spec_c);
+  h->tw = nullptr; h->d_radices = nullptr; h->spec_a = h->spec_b = h->spec_c = nullptr;
 }
 
 int cpf_exchange_fwd(cpfft_handle* h);   // solver.cu (NCCL transposes)

@@ -282,61 +282,138 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g
 }
 
 // ---------------------------------------------------------------------------------------------
-// y pass, in place.  grid = (9 * nx, NZ / TZ).  Shared memory s[i * TZ + l] (+ twiddles).
-// SCATTER: the result line (natural y order) is written to the y-slab layout
-// [c][x global][y local][kz] of the rank that owns y (forward transpose fused into the store).
-template <int N, int DIR, bool SCATTER>
-__global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
+// y passes.  Shared memory s[i * TZ + l] (+ twiddles), tile of TZ consecutive kz per CTA.
+//
+// The Green operator of a tensor row r is rank one (see k_fx): the x pass needs only
+//   T0 = F(t_r0)   and   B = xi_y F(t_r1) + xi_z F(t_r2)
+// and returns only  U0 = IFFTx(xi_x s)  and  W = IFFTx(s)  (out_r1 = xi_y W, out_r2 = xi_z W).
+// So between the forward y pass and the inverse y pass the spectrum carries 6 lines instead of
+// 9 (slots 3r and 3r+1 of the 9-slot buffers; slot 3r+2 is unused): one third less HBM
+// traffic in those passes and one third less NVLink traffic in both slab transposes.
+
+// all stages of one y line tile; `ld(i, l)` supplies the input, `fin(it, cnt, i, l, v)` receives
+// the natural-order result of task iteration `it` (cnt-th output of that butterfly)
+template <int N, int DIR, class Ld, class Fin>
+__device__ __forceinline__ void y_line_fft(cplx* s, const cplx* tw, Ld ld, Fin fin) {
+  typedef FftPlan<N> P;
+  constexpr int TZ = Pow2Cfg<N>::TZY;
+  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  constexpr bool single = (P::R2 == 1), two = (P::R3 == 1);
+  constexpr int RL = single ? P::R1 : (two ? P::R2 : P::R3);
+  const int ntl = TZ * (N / RL);                       // tasks of the last stage
+  if constexpr (single) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int task = threadIdx.x + it * blockDim.x;
+      if (task < ntl) {
+        const int j = task / TZ, l = task - j * TZ;
+        int cnt = 0;
+        fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return ld(i, l); }, [&](int i, cplx v) { fin(it, cnt++, fft_natural<N>(i), l, v); });
+      }
+    }
+  } else {
+  for (int task = threadIdx.x; task < TZ * (N / P::R1); task += blockDim.x) {
+    const int j = task / TZ, l = task - j * TZ;
+    fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return ld(i, l); }, [&](int i, cplx v) { s[i * TZ + l] = v; });
+  }
+  __syncthreads();
+  if constexpr (!two) {
+    for (int task = threadIdx.x; task < TZ * (N / P::R2); task += blockDim.x) {
+      const int j = task / TZ, l = task - j * TZ;
+      fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; }, [&](int i, cplx v) { s[i * TZ + l] = v; });
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {                     // the launch guarantees ntl <= 2 * blockDim
+    const int task = threadIdx.x + it * blockDim.x;
+    if (task < ntl) {
+      const int j = task / TZ, l = task - j * TZ;
+      int cnt = 0;
+      if constexpr (two)
+        fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; }, [&](int i, cplx v) { fin(it, cnt++, fft_natural<N>(i), l, v); });
+      else
+        fft_stage_dif<N2, P::R3, DIR, N / N2>(j, tw, [&](int i) { return s[i * TZ + l]; }, [&](int i, cplx v) { fin(it, cnt++, fft_natural<N>(i), l, v); });
+    }
+  }
+  }
+}
+
+// forward y pass, grid = (6 * nx, NZ / TZ): line slot ls = blockIdx.x / nx, row r = ls / 2.
+//   ls even: component 3r   -> slot 3r
+//   ls odd : components 3r+1 and 3r+2 -> slot 3r+1 = xi_y(ky) F(t_r1) + xi_z(kz) F(t_r2)
+// in place in spec (x-slab layout), or SCATTER: to the y-slab layout [slot][x global][y local][kz]
+// of the rank that owns y (forward slab transpose fused into the store).
+template <int N, bool SCATTER>
+__global__ void __launch_bounds__(512) k_fyf(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
   typedef FftPlan<N> P;
   constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZY;
-  constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
+  constexpr int RL = (P::R2 == 1) ? P::R1 : ((P::R3 == 1) ? P::R2 : P::R3);
   extern __shared__ cplx sm[];
   cplx* s = sm;
   cplx* tw = sm + N * TZ;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   __syncthreads();
-  cplx* G = spec + (int64_t)blockIdx.x * N * H + blockIdx.y * TZ;
+  const int ls = blockIdx.x / g.nx, xl = blockIdx.x - ls * g.nx;
+  const int row = ls >> 1, kz0 = blockIdx.y * TZ;
+  const int slot = 3 * row + (ls & 1);
   const int ny = g.NY;                                   // SCATTER: y planes per rank
-  const int cc = blockIdx.x / g.nx, xg = g.x0 + (blockIdx.x - cc * g.nx);
-  const int64_t sbase = ((int64_t)cc * N + xg) * ny * H + blockIdx.y * TZ;
-  auto out = [&](int i, int l, cplx v) {
-    const int y = fft_natural<N>(i);
+  const int64_t plane = (int64_t)N * H;                  // one (component, x) plane of the x-slab layout
+  const cplx* G1 = spec + ((int64_t)slot * g.nx + xl) * plane + kz0;
+  cplx* Gout = spec + ((int64_t)slot * g.nx + xl) * plane + kz0;
+  const int64_t sbase = ((int64_t)slot * N + (g.x0 + xl)) * ny * H + kz0;
+  auto out = [&](int y, int l, cplx v) {
     if (SCATTER) {
       const int pr = y / ny, yl = y - pr * ny;
       peers.p[pr][sbase + (int64_t)yl * H + l] = v;
     } else {
-      G[(int64_t)y * H + l] = v;
+      Gout[(int64_t)y * H + l] = v;
     }
   };
-  constexpr bool single = (P::R2 == 1);
-  for (int task = threadIdx.x; task < TZ * (N / P::R1); task += blockDim.x) {
-    const int j = task / TZ, l = task - j * TZ;
-    if (single)
-      fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return G[(int64_t)i * H + l]; },
-                                      [&](int i, cplx v) { out(i, l, v); });
-    else
-      fft_stage_dif<N, P::R1, DIR, 1>(j, tw, [&](int i) { return G[(int64_t)i * H + l]; },
-                                      [&](int i, cplx v) { s[i * TZ + l] = v; });
+  if ((ls & 1) == 0) {
+    y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
+                      [&](int, int, int y, int l, cplx v) { out(y, l, v); });
+  } else {
+    cplx keep[2][RL];
+    y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
+                      [&](int it, int cnt, int y, int, cplx v) {
+                        const double fy = (double)(y < H ? y : y - N);
+                        keep[it][cnt] = make_double2(fy * v.x, fy * v.y);
+                      });
+    __syncthreads();                                     // the tile buffer is reused for component 3r+2
+    const cplx* G2 = G1 + (int64_t)g.nx * plane;
+    y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G2[(int64_t)i * H + l]; },
+                      [&](int it, int cnt, int y, int l, cplx v) {
+                        const double fz = (double)(kz0 + l);
+                        out(y, l, make_double2(keep[it][cnt].x + fz * v.x, keep[it][cnt].y + fz * v.y));
+                      });
   }
-  if (single) return;
+}
+
+// inverse y pass, grid = (9 * nx, NZ / TZ), out of place: component c = 3r + m reads line slot
+// 3r (m = 0) or 3r+1 scaled by xi_y(ky) (m = 1) / xi_z(kz) (m = 2) and writes component c of
+// `dst` (x-slab layout, all 9 components again).
+template <int N>
+__global__ void __launch_bounds__(512) k_fyi(Pow2Args g, const cplx* __restrict__ src, cplx* __restrict__ dst) {
+  constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZY;
+  extern __shared__ cplx sm[];
+  cplx* s = sm;
+  cplx* tw = sm + N * TZ;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   __syncthreads();
-  constexpr bool two = (P::R3 == 1);
-  for (int task = threadIdx.x; task < TZ * (N / P::R2); task += blockDim.x) {
-    const int j = task / TZ, l = task - j * TZ;
-    if (two)
-      fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; },
-                                            [&](int i, cplx v) { out(i, l, v); });
-    else
-      fft_stage_dif<N1, P::R2, DIR, N / N1>(j, tw, [&](int i) { return s[i * TZ + l]; },
-                                            [&](int i, cplx v) { s[i * TZ + l] = v; });
-  }
-  if (two) return;
-  __syncthreads();
-  for (int task = threadIdx.x; task < TZ * (N / P::R3); task += blockDim.x) {
-    const int j = task / TZ, l = task - j * TZ;
-    fft_stage_dif<N2, P::R3, DIR, N / N2>(j, tw, [&](int i) { return s[i * TZ + l]; },
-                                          [&](int i, cplx v) { out(i, l, v); });
-  }
+  const int c = blockIdx.x / g.nx, xl = blockIdx.x - c * g.nx;
+  const int row = c / 3, m = c - 3 * row, kz0 = blockIdx.y * TZ;
+  const int slot = 3 * row + (m ? 1 : 0);
+  const int64_t plane = (int64_t)N * H;
+  const cplx* Gin = src + ((int64_t)slot * g.nx + xl) * plane + kz0;
+  cplx* Gout = dst + ((int64_t)c * g.nx + xl) * plane + kz0;
+  y_line_fft<N, +1>(s, tw, [&](int i, int l) {
+                      const cplx v = Gin[(int64_t)i * H + l];
+                      if (m == 0) return v;
+                      const double f = (m == 1) ? (double)(i < H ? i : i - N) : (double)(kz0 + l);
+                      return make_double2(f * v.x, f * v.y);
+                    },
+                    [&](int, int, int y, int l, cplx v) { Gout[(int64_t)y * H + l] = v; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,9 +422,9 @@ __global__ void __launch_bounds__(512) k_fy(Pow2Args g, cplx* __restrict__ spec,
 // The Green operator of a tensor row is rank one, out_j = xi_j s with
 // s = (xi_x t0 + xi_y t1 + xi_z t2) / |xi|^2 (FFT_init.f:321-335), and xi_y, xi_z are constant
 // along an x line.  So only TWO lines per (y, kz) are transformed instead of three:
-//   forward :  A = FFTx(t0),  B = FFTx(xi_y t1 + xi_z t2)       (combined while loading)
+//   forward :  A = FFTx(T0),  B = FFTx(xi_y T1 + xi_z T2)    (line slots 3r, 3r+1 from k_fyf)
 //   Green   :  s = (xi_x A + B) / |xi|^2;   A <- xi_x s,  B <- s
-//   inverse :  out0 = IFFTx(A),  out1 = xi_y IFFTx(B),  out2 = xi_z IFFTx(B)   (while storing)
+//   inverse :  U0 = IFFTx(A) -> slot 3r,  W = IFFTx(B) -> slot 3r+1   (k_fyi expands W)
 // Shared memory s[(line * N + i) * TZ + l].  The spectrum stays digit-reversed between the two
 // transforms.  SCATTER: the inverse-transformed lines (natural x order) go back to the x-slab
 // layout [c][x local][y global][kz] of the rank that owns x (backward transpose fused in).
@@ -373,14 +450,8 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec,
     const int j = r % (N / P::R1), ln = r / (N / P::R1);
     cplx* sc = s + ln * N * TZ + l;
     const cplx* gc = G + l;
-    const double fz = (double)(kz0 + l);
-    if (ln == 0)
-      fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return gc[(int64_t)i * xs]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
-    else
-      fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) {
-        const cplx a = gc[cs + (int64_t)i * xs], b = gc[2 * cs + (int64_t)i * xs];
-        return make_double2(fy * a.x + fz * b.x, fy * a.y + fz * b.y);
-      }, [&](int i, cplx v) { sc[i * TZ] = v; });
+    const cplx* gl = gc + (int64_t)ln * cs;
+    fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return gl[(int64_t)i * xs]; }, [&](int i, cplx v) { sc[i * TZ] = v; });
   }
   __syncthreads();
   if (P::R2 > 1) {
@@ -443,7 +514,6 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec,
     const int l = task % TZ, r = task / TZ;
     const int j = r % (N / P::R1), ln = r / (N / P::R1);
     cplx* sc = s + ln * N * TZ + l;
-    const double fz = (double)(kz0 + l);
     const int c0 = 3 * row;
     // destination of element (component c, x plane i) of this CTA's (y, kz0 + l)
     auto put = [&](int c, int i, cplx v) {
@@ -454,13 +524,7 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec,
         G[(int64_t)(c - c0) * cs + (int64_t)i * xs + l] = v;
       }
     };
-    if (ln == 0)
-      fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { put(c0, i, v); });
-    else
-      fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) {
-        put(c0 + 1, i, make_double2(fy * v.x, fy * v.y));
-        put(c0 + 2, i, make_double2(fz * v.x, fz * v.y));
-      });
+    fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return sc[i * TZ]; }, [&](int i, cplx v) { put(c0 + ln, i, v); });
   }
 }
 
@@ -494,9 +558,10 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
   constexpr int thr_x = (2 * TZX * (N / RminY)) > 512 ? 512 : (2 * TZX * (N / RminY) < 32 ? 32 : 2 * TZX * (N / RminY));
   const dim3 gy(9 * nx, H / TZY);
+  const dim3 gyf(6 * nx, H / TZY);
   if (world == 1) {
     tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-    k_fy<N, -1, false><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
+    k_fyf<N, false><<<gyf, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
     cpf_prof_end(h, tk);
     const dim3 gx(N, H / TZX, 3);
     tk = cpf_prof_begin(h, CPF_K_X_GREEN);
@@ -513,7 +578,7 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
       Pow2Args gs = g;
       gs.NY = ny;                                  // y planes per rank, for the scatter
       tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-      k_fy<N, -1, true><<<gy, thr_y, sm_y, h->stream>>>(gs, h->spec_a, pb);   // -> every rank's spec_b
+      k_fyf<N, true><<<gyf, thr_y, sm_y, h->stream>>>(gs, h->spec_a, pb);     // -> every rank's spec_b
       cpf_prof_end(h, tk);
       int rc = cpf_rank_barrier(h); if (rc) return rc;
       tk = cpf_prof_begin(h, CPF_K_X_GREEN);
@@ -522,7 +587,7 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
       rc = cpf_rank_barrier(h); if (rc) return rc;
     } else {
       tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-      k_fy<N, -1, false><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
+      k_fyf<N, false><<<gyf, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
       cpf_prof_end(h, tk);
       int rc = cpf_exchange_fwd(h);
       if (rc) return rc;
@@ -534,12 +599,12 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
     }
   }
   tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-  k_fy<N, +1, false><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
+  k_fyi<N><<<gy, thr_y, sm_y, h->stream>>>(g, h->spec_a, h->spec_c);           // 6 line slots -> 9 components
   cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
   tk = cpf_prof_begin(h, CPF_K_INV_Z);
-  if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
-  else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_a, dst, scale, nullptr, nullptr);
+  if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
+  else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
   cpf_prof_end(h, tk);
   h->launches += 5;
   CPF_CUDA(cudaGetLastError());
@@ -561,9 +626,9 @@ static int init_pow2(cpfft_handle* h) {
   CPF_SMEM_ATTR((k_fz<N, 2>), sm_z, CPF_CARVE_Z);
   CPF_SMEM_ATTR((k_iz<N, true>), sm_z, CPF_CARVE_Z);
   CPF_SMEM_ATTR((k_iz<N, false>), sm_z, CPF_CARVE_Z);
-  CPF_SMEM_ATTR((k_fy<N, -1, false>), sm_y, CPF_CARVE_Y);
-  CPF_SMEM_ATTR((k_fy<N, -1, true>), sm_y, CPF_CARVE_Y);
-  CPF_SMEM_ATTR((k_fy<N, +1, false>), sm_y, CPF_CARVE_Y);
+  CPF_SMEM_ATTR((k_fyf<N, false>), sm_y, CPF_CARVE_Y);
+  CPF_SMEM_ATTR((k_fyf<N, true>), sm_y, CPF_CARVE_Y);
+  CPF_SMEM_ATTR((k_fyi<N>), sm_y, CPF_CARVE_Y);
   CPF_SMEM_ATTR((k_fx<N, false>), sm_x, CPF_CARVE_X);
   CPF_SMEM_ATTR((k_fx<N, true>), sm_x, CPF_CARVE_X);
   return 0;
