@@ -273,7 +273,8 @@ def main():
         if world > 1:
             dist.all_reduce(mse, op=dist.ReduceOp.MAX)
         e2e = {"value": nvox * app_e / (float(mse.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(9 * n3 * 8), "d2h_bytes_per_step": int(18 * n3 * 8), "steps": Ke,
+               "h2d_bytes_per_step": int(9 * n3 * 8) * world, "d2h_bytes_per_step": int(18 * n3 * 8) * world,   # all ranks
+               "steps": Ke,
                "check": float(hP.abs().max())}
 
     if rank != 0:
