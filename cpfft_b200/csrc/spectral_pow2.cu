@@ -23,7 +23,6 @@ struct Pow2Args {
   const cplx* tw;  // exp(-2 pi i k / N), k < N
 };
 
-// kz tile sizes of the y and x passes (must divide N/2) and the CTA size of the z passes
 // Slab <-> pencil transposes fused into the FFT store stages (world > 1): every rank maps the
 // spectrum buffers of all ranks (CUDA IPC) and the last butterfly stage of the y pass / of the
 // inverse x pass stores each element straight into the rank that owns it -- NVLink stores in
@@ -31,39 +30,28 @@ struct Pow2Args {
 // the transform.  peers[r] = base of rank r's destination buffer (own rank: local pointer).
 struct PeerPtrs { cplx* p[CPF_MAX_WORLD]; };
 
+// Per-grid tuning: kz tile sizes of the y and x passes (must divide N/2) and the CTA size of
+// the z passes.  Measured at 256^3 (tools/time_apply.py, A/B in one run):
+//   * x pass: 8 kz per CTA = 2 * 256 * 8 * 16 B = 64 KB, 3 CTAs/SM, 128-byte runs;
+//   * z passes: one grid line per CTA beats two (k_iz 0.78 -> 0.70 ms);
+//   * giving the whole L1 to shared memory (cudaSharedmemCarveoutMaxShared) slows every pass
+//     down (k_fz 1.9 -> 3.0 ms): the streaming loads want the L1.
 template <int N> struct Pow2Cfg {
   static constexpr int H = N / 2;
   static constexpr int TZY = (H < 16 ? H : 16) < (4096 / N) ? (H < 16 ? H : 16) : (4096 / N);
   static constexpr int TZX = (H < 8 ? H : 8) < (2048 / N) ? (H < 8 ? H : 8) : (2048 / N);   // 512: 4
   static constexpr int ZT = (N / 2 + 31) / 32 * 32;   // threads of k_fz / k_iz (N/2 of them work)
 };
-// resident CTAs per SM the z passes are compiled for (register budget 64K / (threads * CTAs))
-#ifndef CPF_ZMINB
-#define CPF_ZMINB 1
-#endif
-#ifndef CPF_CARVE_Z
-#define CPF_CARVE_Z 0
-#endif
-#ifndef CPF_CARVE_Y
-#define CPF_CARVE_Y 0
-#endif
-#ifndef CPF_CARVE_X
-#define CPF_CARVE_X 0
-#endif
-// measured at 256^3: k_iz gains from 3 resident CTAs (0.92 -> 0.78 ms), k_fz loses (1.91 -> 2.05 ms);
-// giving the whole L1 to shared memory (carveout) slows every pass down
-// keep >= 512 threads resident per SM: without a floor the compiler spends 254 registers per
-// thread on k_fz and a single CTA fits (measured at 320^3: occupancy 7.6 %, 56 % of HBM)
-template <int N> struct ZOcc { static constexpr int MINB = (512 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT; };
-#ifndef CPF_TZX256
-#define CPF_TZX256 8     // two-line x pass: 2 * 256 * 8 * 16 B = 64 KB per CTA, 3 CTAs/SM, 128-byte runs
-#endif
-template <> struct Pow2Cfg<256> { static constexpr int H = 128, TZY = 16, TZX = CPF_TZX256, ZT = 128; };
+template <> struct Pow2Cfg<256> { static constexpr int H = 128, TZY = 16, TZX = 8, ZT = 128; };
 template <> struct Pow2Cfg<40> { static constexpr int H = 20, TZY = 10, TZX = 5, ZT = 32; };
 template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, ZT = 64; };
 template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 128; };
 template <> struct Pow2Cfg<320> { static constexpr int H = 160, TZY = 16, TZX = 8, ZT = 160; };
 template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8, ZT = 224; };
+// Resident CTAs per SM the z passes are compiled for: keep >= 512 threads per SM.  Without a
+// floor the compiler spends 254 registers per thread on k_fz and a single CTA fits (measured
+// at 320^3: occupancy 7.6 %, 56 % of the HBM peak).
+template <int N> struct ZOcc { static constexpr int MINB = (512 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT; };
 
 // ---------------------------------------------------------------------------------------------
 // z passes: one grid line (x, y) and its 9 components per CTA, H = N/2 threads, two voxels
@@ -617,20 +605,18 @@ static int init_pow2(cpfft_handle* h) {
   constexpr int TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
   const size_t sm_z = ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
-  // let the SM give the whole unified L1/shared array to shared memory so that 2-4 CTAs fit
-#define CPF_SMEM_ATTR(kern, bytes, carve)                                                                 \
-  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
-  if (carve) CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CPF_SMEM_ATTR((k_fz<N, 0>), sm_z, CPF_CARVE_Z);
-  CPF_SMEM_ATTR((k_fz<N, 1>), sm_z, CPF_CARVE_Z);
-  CPF_SMEM_ATTR((k_fz<N, 2>), sm_z, CPF_CARVE_Z);
-  CPF_SMEM_ATTR((k_iz<N, true>), sm_z, CPF_CARVE_Z);
-  CPF_SMEM_ATTR((k_iz<N, false>), sm_z, CPF_CARVE_Z);
-  CPF_SMEM_ATTR((k_fyf<N, false>), sm_y, CPF_CARVE_Y);
-  CPF_SMEM_ATTR((k_fyf<N, true>), sm_y, CPF_CARVE_Y);
-  CPF_SMEM_ATTR((k_fyi<N>), sm_y, CPF_CARVE_Y);
-  CPF_SMEM_ATTR((k_fx<N, false>), sm_x, CPF_CARVE_X);
-  CPF_SMEM_ATTR((k_fx<N, true>), sm_x, CPF_CARVE_X);
+#define CPF_SMEM_ATTR(kern, bytes) \
+  CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));
+  CPF_SMEM_ATTR((k_fz<N, 0>), sm_z);
+  CPF_SMEM_ATTR((k_fz<N, 1>), sm_z);
+  CPF_SMEM_ATTR((k_fz<N, 2>), sm_z);
+  CPF_SMEM_ATTR((k_iz<N, true>), sm_z);
+  CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
+  CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
+  CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
+  CPF_SMEM_ATTR((k_fyi<N>), sm_y);
+  CPF_SMEM_ATTR((k_fx<N, false>), sm_x);
+  CPF_SMEM_ATTR((k_fx<N, true>), sm_x);
   return 0;
 }
 int cpf_pow2_init(cpfft_handle* h) {
