@@ -125,14 +125,17 @@ def compare_mm10_history(hg, ho, nslip, tol=TOL_VOXEL):
     return errs
 
 
-def assert_same_cg_counts(got, want):
+def assert_same_cg_counts(got, want, slack=0):
     """CG iteration counts must agree solve by solve, except degenerate solves whose right-hand
     side is at round-off level: there the reference's ABSOLUTE stop test (resnorm <= tol = 1e-10,
     FFT_nr3.f:305) is decided by the summation order of the norm -- the oracle itself returns 1
-    or 8 iterations for the last solve of test_mm10.in depending on its OpenMP thread count."""
+    or 8 iterations for the last solve of test_mm10.in depending on its OpenMP thread count.
+    ``slack``: stress-controlled runs only -- the last correction of the P_bar iteration has a
+    right-hand side proportional to the nearly cancelled residual P_bar - P_BC, so the same
+    absolute test moves by one iteration between implementations (38 vs 39 on the GPU)."""
     got = [[int(v) for v in r] for r in got]
     want = [[int(v) for v in r] for r in want]
     assert [len(r) for r in got] == [len(r) for r in want], (got, want)
     for a, b in zip(got, want):
         for x, y in zip(a, b):
-            assert x == y or min(x, y) <= 1, (got, want)
+            assert abs(x - y) <= slack or min(x, y) <= 1, (got, want)
