@@ -1,0 +1,45 @@
+"""Run one of the reference's input decks end to end on the GPU:
+
+    python -m cpfft_b200 examples/test_mm10.in [--outdir results] [--device 0]
+
+Mirrors `compute` of the reference's main program (FFT_finite_3d.f:138-147): the initial
+drive_eps_sig sweep, the FFT_nr3 step loop with the reference's log lines on stdout, and on the
+steps selected by `output results steps ...` the flat-text result files of ouresult.f
+(wes#####_text stresses, wee#####_text strains).  The CUDA library does all the work; this
+module is host glue (deck reader, printing, file writing)."""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+
+from . import Solver, read_deck
+from .results import write_step
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="python -m cpfft_b200")
+    ap.add_argument("deck")
+    ap.add_argument("--outdir", default=".")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=0, help="run only the first STEPS load steps")
+    args = ap.parse_args(argv)
+    prob = read_deck(args.deck)
+    nstep = args.steps or prob.nstep
+    print(f" >> deck {args.deck}: grid {prob.N}^3, {len(prob.materials)} material(s), {nstep} load step(s)")
+    s = Solver(prob, device=args.device)
+    t0 = time.time()
+    s.drive_eps_sig(1, 0)
+    for step in range(1, nstep + 1):
+        r = s.FFT_nr3(nstep=1, first=step - 1)
+        sys.stdout.write(r["log"])
+        if step in prob.out_steps:
+            write_step(args.outdir, step, s.download("URCS_N1", 1), s.download("EPS_N1", 1), prob.name, prob.N)
+            print(f"       results of step {step} written to {args.outdir}")
+    fails = s.material_failures()[0]
+    print(f"\n >> analysis done: {nstep} steps, {time.time() - t0:.2f} s, mm10 local failures {fails}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

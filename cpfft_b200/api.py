@@ -45,7 +45,7 @@ class Config(C.Structure):
 EXPORTS = [
     "cpfft_create", "cpfft_destroy", "cpfft_last_error", "cpfft_set_materials", "cpfft_set_voxels",
     "cpfft_set_params", "cpfft_hist_size", "cpfft_local_voxels", "cpfft_drive_eps_sig", "cpfft_G_K_dF",
-    "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3",
+    "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3", "cpfft_step_log",
     "cpfft_field_ncomp", "cpfft_upload", "cpfft_download", "cpfft_download_fail_flags",
     "cpfft_download_local_iters", "cpfft_material_failures", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_exchange_mode", "cpfft_synchronize",
     "cpfft_stream", "cpfft_kernel_launches", "cpfft_profile_enable", "cpfft_profile_reset",
@@ -86,6 +86,8 @@ def load_library():
     L.cpfft_mean_P.argtypes = [vp, dp]
     L.cpfft_update.argtypes = [vp]
     L.cpfft_FFT_nr3.argtypes = [vp, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp, C.POINTER(C.c_int64)]
+    L.cpfft_step_log.argtypes = [vp]
+    L.cpfft_step_log.restype = C.c_char_p
     L.cpfft_field_ncomp.argtypes = [vp, C.c_int]
     L.cpfft_upload.argtypes = [vp, C.c_int, dp, C.c_int]
     L.cpfft_download.argtypes = [vp, C.c_int, dp, C.c_int]
@@ -246,7 +248,8 @@ class Solver:
                                   _dp(sec), cnt.ctypes.data_as(C.POINTER(C.c_int64)))
         self._check(rc)
         cg_lists = [list(r[:list(r).index(-1)]) if -1 in r else list(r) for r in cg]
-        return dict(rc=rc, nr_iters=nr, cg_iters=cg_lists, Pbar=pbar, buckets=sec, counters=cnt)
+        return dict(rc=rc, nr_iters=nr, cg_iters=cg_lists, Pbar=pbar, buckets=sec, counters=cnt,
+                    log=self.L.cpfft_step_log(self.h).decode())
 
     def profile(self, on=True):
         self._check(self.L.cpfft_profile_enable(self.h, int(on)))

@@ -70,6 +70,7 @@ struct cpfft_handle {
   int H;                     // history comps
   cudaStream_t stream;
   std::string err;
+  std::string log;           // the reference's step / iteration lines of the last cpfft_FFT_nr3 call
   int64_t launches;
   // fields
   double* field[CPFFT_NUM_FIELDS];

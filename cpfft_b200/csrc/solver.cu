@@ -623,6 +623,20 @@ static int nbc_update(const double* C_homo, double* DbarF, const double* P_bar, 
   return 0;
 }
 
+// Fortran Dw.3 edit descriptor (FFT_nr3.f:195-199 formats 1001-1003): 0.123D-04, width 10
+static std::string fmt_d10_3(double x) {
+  char buf[64];
+  if (x == 0.0 || !std::isfinite(x)) { snprintf(buf, sizeof(buf), "%10s", std::isfinite(x) ? "0.000D+00" : "NaN"); return buf; }
+  int e = (int)std::floor(std::log10(std::fabs(x))) + 1;
+  double m = std::fabs(x) / std::pow(10.0, e);
+  long r = std::lround(m * 1000.0);
+  if (r >= 1000) { r = 100; e += 1; }
+  char body[48];
+  snprintf(body, sizeof(body), "%s0.%03ldD%c%02d", x < 0 ? "-" : "", r, e < 0 ? '-' : '+', std::abs(e));
+  snprintf(buf, sizeof(buf), "%10s", body);
+  return buf;
+}
+
 // ---- FFT_nr3 (FFT_nr3.f:14-200) ----
 int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_t* isNBC, int32_t* nr_iters,
                   int32_t* cg_iters, int cg_cap, double* Pbar_out, double* seconds, int64_t* counters) {
@@ -632,6 +646,7 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
   bool existNBC = false;
   for (int i = 0; i < 9; ++i) if (isNBC[i]) existNBC = true;
   h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0; h->n_fail = 0;
+  h->log.clear();
   int64_t fail_final_steps = 0;
   const double t_start = wall_s();
   int rc;
@@ -645,6 +660,11 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
     const int step = h->next_step;
     int ncg = 0;
     auto push_cg = [&](int it) { if (cg_iters && ncg < cg_cap - 1) cg_iters[(size_t)s * cg_cap + ncg++] = it; };
+    {  // format 1000
+      char hd[160];
+      snprintf(hd, sizeof(hd), "\n    -------------------------------------------------------------------------\n     Now starting step: %7d\n", step);
+      h->log += hd;
+    }
     for (int i = 0; i < 9; ++i) {
       PBC[i] = 0; FBC[i] = 0; DbarF[i] = 0;
       if (isNBC[i]) PBC[i] = BC_all[(size_t)s * 9 + i];
@@ -665,6 +685,11 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
       rc = pcg_dev(h, b, dFm, tolCG, &it, nullptr); if (rc) return rc;
       push_cg(it);
       k_axpy<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(Fn1, dFm, 1.0, n); h->launches++;
+      {  // format 1003: the residual of the first correction (printed, not used: FFT_nr3.f:100-103)
+        double d0;
+        rc = cpf_dot(h, dFm, dFm, n, &d0); if (rc) return rc;
+        h->log += "       Initial residual                 " + fmt_d10_3(sqrt(d0) / Fnorm) + "\n";
+      }
       double resfft = 1.0;
       int iiter_EBC = 0;
       while (resfft > tolNR) {
@@ -676,6 +701,11 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
         double d2;
         rc = cpf_dot(h, dFm, dFm, n, &d2); if (rc) return rc;
         resfft = sqrt(d2) / Fnorm;
+        {  // format 1001
+          char ln[96];
+          snprintf(ln, sizeof(ln), "       Iteration %5d         residual %s\n", iiter_EBC, fmt_d10_3(resfft).c_str());
+          h->log += ln;
+        }
         if (iiter_EBC == h->cfg.maxIter) { cpf_set_error(h, ">> Error: Newton loop does not converge."); return CPFFT_ERR_NEWTON; }
         iiter_EBC++;
       }
@@ -690,6 +720,11 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
         r1 += (h->P_bar[i] - PBC[i]) * (h->P_bar[i] - PBC[i]);
       }
       r3 = (r2 < 1.0e-8) ? sqrt(r1) : sqrt(r1 / r2);
+      if (existNBC) {  // format 1002
+        char ln[96];
+        snprintf(ln, sizeof(ln), "       Stress iteration %5d  residual %s\n", iiter_NBC, fmt_d10_3(r3).c_str());
+        h->log += ln;
+      }
       if (r3 <= tolNR) break;
       if (iiter_NBC > h->cfg.maxIter) { cpf_set_error(h, ">> Error: Prescribed stress cannot be reached within given maximum iteration."); return CPFFT_ERR_STRESS_BC; }
       rc = cpfft_tangent_homo(h, h->C_homo); if (rc) return rc;
@@ -806,6 +841,8 @@ int cpfft_nccl_init(cpfft_handle* h, const void* id128) {
   }
   return 0;
 }
+
+const char* cpfft_step_log(const cpfft_handle* h) { return h ? h->log.c_str() : ""; }
 
 int cpfft_fp64_peak(cpfft_handle* h, double* tflops) {
   if (!h || !tflops) return CPFFT_ERR_USAGE;

@@ -223,6 +223,7 @@ def read_deck(path: str) -> Problem:
     isNBC = np.zeros(9, dtype=np.int32)
     mults: dict = {}
     tolNR, tolPCG, maxIter, tstep = 1e-5, 1e-10, 10, 1.0
+    name, out_steps = "", ()
     while True:
         line = lines.next()
         if line is None:
@@ -278,7 +279,15 @@ def read_deck(path: str) -> Problem:
                 else:
                     break
                 lines.next()
-        elif key in ("project", "sizes", "blocking", "output", "compute"):
+        elif key == "project":
+            name = toks[1] if len(toks) > 1 else ""
+        elif key == "output":
+            # `output results steps <integer list>` selects the steps written by ouresult;
+            # `output model ...` (mesh files) is not part of the hot path
+            low = [t.lower() for t in toks]
+            if len(low) > 2 and low[1].startswith("result") and low[2].startswith("step"):
+                out_steps = tuple(_int_list(toks[3:]))
+        elif key in ("sizes", "blocking", "compute"):
             pass
         elif key == "stop":
             break
@@ -302,4 +311,4 @@ def read_deck(path: str) -> Problem:
     mult_arr = np.array([mults.get(s + 1, 0.0) for s in range(nstep)])
     return Problem(N=N, materials=materials, crystals=cry_list, matlist=elem_mat, angles=angles,
                    FP_max=FP_max, isNBC=isNBC, mults=mult_arr, tolNR=tolNR, tolPCG=tolPCG,
-                   maxIter=maxIter, tstep=tstep)
+                   maxIter=maxIter, tstep=tstep, name=name, out_steps=out_steps)

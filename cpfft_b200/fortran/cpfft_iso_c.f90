@@ -121,6 +121,10 @@ module cpfft_iso_c
        real(c_double), intent(out) :: Pbar(9, *), seconds(3)
        integer(c_int64_t), intent(out) :: counters(5)
      end function
+     type(c_ptr) function cpfft_step_log(handle) bind(c, name='cpfft_step_log')
+       import :: c_ptr
+       type(c_ptr), value :: handle
+     end function
      integer(c_int) function cpfft_field_ncomp(handle, f) bind(c, name='cpfft_field_ncomp')
        import :: c_int, c_ptr
        type(c_ptr), value :: handle

@@ -110,6 +110,8 @@ class Problem:
     tolPCG: float = 1.0e-10
     maxIter: int = 10
     tstep: float = 1.0
+    name: str = ""                           # `project` card (stname)
+    out_steps: tuple = ()                    # `output results steps <list>` (oudriv.f:82-166)
 
     @property
     def N3(self) -> int:

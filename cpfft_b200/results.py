@@ -1,0 +1,60 @@
+"""Result files in the reference's flat-text format (src/ouresult.f): per output step one
+``wes#####_text`` (unrotated Cauchy stresses) and one ``wee#####_text`` (strains) file with the
+``ouddpa_flat_header`` header (ouresult.f:335-398) and one ``30e15.6`` record per element
+(ouresult.f:296-298; 11 + 15 values per stress record, 7 + 15 per strain record, of which the
+first 6 carry data -- the reference zero-fills the rest, ouresult.f:170-172, 208-215)."""
+from __future__ import annotations
+
+import math
+import os
+import time
+
+import numpy as np
+
+
+def fortran_e(x: float, width: int = 15, digits: int = 6) -> str:
+    """Fortran ``Ew.d`` edit descriptor: 0.123457E+03 right-justified in ``width``."""
+    if abs(x) < 1.0e-30:            # "zero small values to prevent 3-digit exponents" (ouresult.f:289)
+        x = 0.0
+    if x == 0.0:
+        body = "0." + "0" * digits + "E+00"
+    else:
+        e = int(math.floor(math.log10(abs(x)))) + 1
+        m = abs(x) / 10.0 ** e
+        r = int(round(m * 10 ** digits))
+        if r >= 10 ** digits:
+            r //= 10
+            e += 1
+        body = ("-" if x < 0 else "") + "0." + f"{r:0{digits}d}" + "E" + ("-" if e < 0 else "+") + f"{abs(e):02d}"
+    return body.rjust(width)
+
+
+def flat_name(kind: str, step: int) -> str:
+    """``wes`` / ``wee`` + step (i5.5) + ``_text`` (ouresult.f:704-711)."""
+    return {"stresses": "wes", "strains": "wee"}[kind] + f"{step:05d}_text"
+
+
+def write_flat(path: str, kind: str, step: int, values: np.ndarray, structure: str = "", nnode: int = 0):
+    """values: (nelem, 6) in the reference's Voigt order xx, yy, zz, xy, yz, xz."""
+    nvals = {"stresses": 11 + 15, "strains": 7 + 15}[kind]
+    nelem = values.shape[0]
+    with open(path, "w") as f:
+        f.write("#\n")
+        f.write(f"#  WARP3D element results: {kind:<15s}\n")
+        f.write(f"#  Structure name: {structure[:8]:<8s}\n")
+        f.write(f"#  Model nodes, elements: {nnode:8d}{nelem:8d}\n")
+        f.write(f"#  {time.strftime('%a %b %d %H:%M:%S %Y'):<24s}\n")
+        f.write(f"#  Load(time) step: {step:8d}\n")
+        f.write("#\n")
+        zero = fortran_e(0.0)
+        pad = zero * (nvals - 6)
+        for row in values:
+            f.write("".join(fortran_e(float(v)) for v in row[:6]) + pad + "\n")
+
+
+def write_step(outdir: str, step: int, urcs_n1: np.ndarray, eps_n1: np.ndarray, structure: str = "", N: int = 0):
+    """urcs_n1 (nelem, >= 6), eps_n1 (nelem, 6): the AoS block order of the reference."""
+    os.makedirs(outdir, exist_ok=True)
+    nnode = (N + 1) ** 3 if N else 0
+    write_flat(os.path.join(outdir, flat_name("stresses", step)), "stresses", step, urcs_n1[:, :6], structure, nnode)
+    write_flat(os.path.join(outdir, flat_name("strains", step)), "strains", step, eps_n1[:, :6], structure, nnode)

@@ -124,6 +124,11 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
                   int32_t* nr_iters, int32_t* cg_iters, int cg_cap, double* Pbar,
                   double* seconds, int64_t* counters);
 
+/* The lines the reference prints to unit `out` during FFT_nr3 (formats 1000-1003,
+ * FFT_nr3.f:195-199: step banner, "Initial residual", "Iteration i residual", "Stress
+ * iteration"), for the steps of the last cpfft_FFT_nr3 call; the host prints them verbatim. */
+const char* cpfft_step_log(const cpfft_handle* h);
+
 /* ---- host <-> device movement of whole fields ---- */
 int cpfft_field_ncomp(const cpfft_handle* h, cpfft_field f);
 int cpfft_upload(cpfft_handle* h, cpfft_field f, const double* host, cpfft_layout layout);

@@ -71,3 +71,30 @@ def test_pod_layouts_match_header():
     assert C.sizeof(CrystalPOD) == 6 * 4 + 16 * 8
     assert C.sizeof(MaterialPOD) == 2 * 4 + 6 * 4
     assert C.sizeof(Config) == 6 * 4 + 3 * 8
+
+
+def test_output_cards_and_project_name():
+    p = deck("test_mm10.in")
+    assert p.name == "test"
+    assert p.out_steps == (2, 4, 6, 8, 10)           # `output results steps 2-10 by 2`
+
+
+def test_flat_result_writer(tmp_path):
+    """wes / wee flat text files of ouresult.f: header, 30e15.6 records, zero-filled tail."""
+    from cpfft_b200.results import write_step, fortran_e, flat_name
+    assert fortran_e(123.4567) == "   0.123457E+03" and fortran_e(-1.2345678e-4) == "  -0.123457E-03"
+    assert fortran_e(0.0) == "   0.000000E+00" and fortran_e(1e-31) == "   0.000000E+00"
+    assert fortran_e(9.9999996) == "   0.100000E+02"
+    assert flat_name("stresses", 4) == "wes00004_text" and flat_name("strains", 12) == "wee00012_text"
+    rng = np.random.default_rng(0)
+    urcs, eps = rng.standard_normal((343, 9)) * 100, rng.standard_normal((343, 6)) * 1e-3
+    write_step(str(tmp_path), 2, urcs, eps, "test", 7)
+    lines = open(tmp_path / "wes00002_text").read().splitlines()
+    assert lines[0] == "#" and lines[1].startswith("#  WARP3D element results: stresses")
+    assert lines[3] == "#  Model nodes, elements:      512     343" and lines[5] == "#  Load(time) step:        2"
+    rows = lines[7:]
+    assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
+    back = np.array([[float(r[15 * k:15 * k + 15]) for k in range(26)] for r in rows])
+    assert np.abs(back[:, :6] - urcs[:, :6]).max() <= 1e-6 * np.abs(urcs).max() * 10 and (back[:, 6:] == 0).all()
+    rows_e = open(tmp_path / "wee00002_text").read().splitlines()[7:]
+    assert all(len(r) == 22 * 15 for r in rows_e)

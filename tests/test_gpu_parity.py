@@ -168,3 +168,25 @@ def test_mm10_local_failure_points(libs):
     assert np.array_equal(s.local_iters(), o.local_iters)
     assert np.array_equal(s.local_iters()[:nb], d["liters"])
     _compare_state(s, o)
+
+
+def test_cli_runs_a_deck_end_to_end(tmp_path):
+    """python -m cpfft_b200 deck: the reference's log lines (FFT_nr3.f:195-199) on stdout and
+    its flat-text result files (ouresult.f) for the steps of `output results steps ...`."""
+    import os
+    import re
+    import subprocess
+    import sys
+    from helpers import DECKS
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "cpfft_b200", os.path.join(DECKS, "test_mm10.in"), "--outdir", str(tmp_path),
+                          "--steps", "4"], capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    txt = out.stdout
+    assert len(re.findall(r"^     Now starting step:\s+\d+$", txt, flags=re.M)) == 4
+    assert len(re.findall(r"^       Initial residual\s+[-0-9.]+D[+-]\d\d$", txt, flags=re.M)) == 4
+    its = re.findall(r"^       Iteration\s+(\d+)\s+residual\s+([-0-9.]+D[+-]\d\d)$", txt, flags=re.M)
+    assert len(its) == 1 + 1 + 3 + 3          # Newton iterations of steps 1-4 of test_mm10.in
+    assert sorted(os.listdir(tmp_path)) == ["wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text"]
+    rows = open(tmp_path / "wes00004_text").read().splitlines()[7:]
+    assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
