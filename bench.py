@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stress-bc", action="store_true",
+                    help="uniaxial tension with P_yy = P_zz = 0 (stress-BC loop, tangent_homo) instead of pure strain control")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -204,7 +206,8 @@ def main():
     N = args.grid or GRID_FOR_GPUS.get(world, 256)
     W, K = max(args.warmup, 0), max(args.steps, 1)
     nx = N // world
-    prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + 2 * K + 2), x_range=(rank * nx, (rank + 1) * nx))
+    prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + 2 * K + 2), x_range=(rank * nx, (rank + 1) * nx),
+                       stress_bc=args.stress_bc)
     s = Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=nccl_id, local_slab=True)
     stream = torch.cuda.ExternalStream(s.stream())
 
@@ -327,7 +330,8 @@ def main():
         "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal ({args.grains} random-orientation fcc grains, "
-                               "mm10/Voce), finite-strain uniaxial tension, strain-controlled, 0.1 % per load step",
+                               "mm10/Voce), finite-strain uniaxial tension, " +
+                               ("F_xx driven with P_yy = P_zz = 0" if args.stress_bc else "strain-controlled") + ", 0.1 % per load step",
                    "grid": N, "voxels": int(nvox), "voxels_per_gpu": int(s.n3), "parallelism": f"x-slabs x{world}",
                    "l2": "working set (>= 1.2 GB per field) far exceeds the 126 MB L2; no flush needed",
                    "step": "one FFT_nr3 load step", "newton_iters_per_step": nr_hist,

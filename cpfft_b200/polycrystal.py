@@ -5,7 +5,8 @@ centres (i+1/2)/N; one orientation per grain, uniform on SO(3), given as Kocks a
 degrees (psi, phi uniform in [0,360), cos(theta) uniform in [-1,1]); voxel
 e = x*N*N + y*N + z.  One crystal-plasticity material: fcc, isotropic e 200000 nu 0.3, Voce
 harden_n 20 theta_0 100 voce_m 1 tau_v 100 tau_y 100, alter_mode off, time step 1.
-Loading (pure-strain variant): F_xx +1 %, F_yy = F_zz -0.3 % in 10 equal steps.
+Loading: F_xx +1 %, F_yy = F_zz -0.3 % in 10 equal steps (pure-strain variant, the benchmark), or
+with ``stress_bc`` uniaxial tension F_xx +1 %, P_yy = P_zz = 0 (tangent_homo + NBC_update path).
 """
 from __future__ import annotations
 
@@ -44,7 +45,7 @@ def grain_angles(ngrains: int = 1000, seed: int = SEED) -> np.ndarray:
 
 
 def polycrystal(N: int, ngrains: int = 1000, seed: int = SEED, nstep: int = 10, slip_type: int = 1,
-                x_range=None) -> Problem:
+                x_range=None, stress_bc: bool = False) -> Problem:
     gm = grain_map(N, ngrains, seed, x_range)
     ang = grain_angles(ngrains, seed)[gm]
     cry = Crystal(slip_type=slip_type, elastic_type=1, h_type=1, alter_mode=0, e=200000.0, nu=0.3,
@@ -52,7 +53,11 @@ def polycrystal(N: int, ngrains: int = 1000, seed: int = SEED, nstep: int = 10, 
     mat = Material(name="poly", type=10, crystal=1)
     FP = np.zeros(9)
     FP[0], FP[4], FP[8] = 0.01, -0.003, -0.003
+    nbc = np.zeros(9, dtype=np.int32)
+    if stress_bc:                 # uniaxial tension: F_xx driven, P_yy = P_zz = 0
+        FP[4] = FP[8] = 0.0
+        nbc[4] = nbc[8] = 1
     p = Problem(N=N, materials=[mat], crystals=[cry], matlist=np.ones(len(gm), dtype=np.int32), angles=ang,
-                FP_max=FP, isNBC=np.zeros(9, dtype=np.int32), mults=np.full(nstep, 1.0 / nstep),
+                FP_max=FP, isNBC=nbc, mults=np.full(nstep, 1.0 / nstep),
                 tolNR=1.0e-5, tolPCG=1.0e-10, maxIter=20, tstep=1.0)
     return p

@@ -134,3 +134,21 @@ def test_polycrystal_steps_match_oracle(libs, N, grains):
     assert errs["F"] <= TOL_VOXEL, errs
     assert errs["P"] <= 5e-8, errs
     compare_mm10_history(s.download("HIST_N", 1)[:, :o.H], o.hist_n, 12, tol=5e-8)
+
+
+def test_polycrystal_stress_bc_matches_oracle(libs):
+    """uniaxial tension with P_yy = P_zz = 0 on the benchmark polycrystal (N = 16): the
+    stress-BC loop, tangent_homo (9 CG solves through the fused fast path) and NBC_update."""
+    from cpfft_b200.polycrystal import polycrystal
+    Solver, Oracle = libs
+    p = polycrystal(16, ngrains=20, stress_bc=True)
+    s, o = Solver(p), Oracle(p, threads=8)
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    rs, ro = s.FFT_nr3(nstep=3), o.FFT_nr3(nstep=3)
+    assert ro["rc"] == 0
+    assert list(rs["nr_iters"]) == list(ro["nr_iters"])
+    assert_same_cg_counts(rs["cg_iters"], ro["cg_iters"], slack=1)
+    scale = np.abs(ro["Pbar"]).max()
+    assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / scale <= 1e-9
+    assert np.abs(rs["Pbar"][:, [4, 8]]).max() <= 1e-5 * scale      # the prescribed stresses are met
+    assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
