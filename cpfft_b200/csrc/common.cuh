@@ -5,8 +5,8 @@
 #include <string>
 #include <vector>
 #include "../../include/cpfft_b200.h"
+#include "material_types.h"
 
-#define CPF_MAX_SLIP 48
 #define CPF_MAX_WORLD 8   // one NVSwitch domain
 
 #define CPF_CUDA(call)                                                                    \
@@ -17,37 +17,6 @@
       return CPFFT_ERR_CUDA;                                                              \
     }                                                                                     \
   } while (0)
-
-// mm10 history layout (offsets, 0-based) -- mm10_d.f:137-331
-struct CpfHistLayout {
-  int use_max, nslip, num_hard;
-  int cep, gradfe, R, work, slipsum;
-  int c_stress, c_euler, c_Rp, c_D, c_eps, c_slipinc, c_tt, c_u, c_ttrate, c_ep, c_ed;
-  int len_u, len_slip, total;
-};
-
-// per-material constants in device memory
-struct CpfMatDev {
-  int type, crystal;        // crystal: 0-based index into crystal table
-  double ym, nu, beta, tan_e, yld, hprime;  // mm01 (REAL*4 promoted, drive_eps_sig.f:486-521)
-};
-
-// per-crystal constants (Voce), device
-struct CpfCryDev {
-  int nslip, alter_mode, miter, rate_int;   // rate_int: harden_n-1 if small integer else -1
-  double rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, eps_dot_0_y, k_0, burgers;
-  double atol, atol1, rtol, rtol1;
-};
-
-// per-grain (unique crystal+orientation) table entry, device, doubles:
-//   [0..8] g (row-major), [9..44] rotated stiffness C (row-major 6x6),
-//   [45 + 9 s ..): ms0[6] (engineering-shear Schmid vector), qs0[3] (skew vector) of system s,
-//   [45 + 9*48 ..+3): the Kocks angles in degrees
-#define CPF_GRAIN_G 0
-#define CPF_GRAIN_C 9
-#define CPF_GRAIN_B 45
-#define CPF_GRAIN_ANG (45 + 9 * CPF_MAX_SLIP)   // Kocks angles (degrees) of the grain
-#define CPF_GRAIN_STRIDE (48 + 9 * CPF_MAX_SLIP)
 
 // kernel classes for the built-in CUDA-event profiler (cpfft_profile_*)
 enum CpfKernelClass {
@@ -119,7 +88,6 @@ void cpf_prof_end(cpfft_handle* h, int token);
 // material.cu
 int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* angles);
 int cpf_launch_update(cpfft_handle* h, int step, int iter);
-CpfHistLayout cpf_hist_layout(int nslip, int num_hard);
 
 // spectral.cu
 int cpf_spectral_init(cpfft_handle* h);

@@ -3,9 +3,7 @@
 // getrm1+qmply1 (polar.f:680-802, qmply1.f), inv33/mul33/cs2p (drive_eps_sig.f:1017-1224)
 // and cep2A_a (cep2A.f:86-284).  3x3 matrices are row-major double[9].
 #pragma once
-#include <cuda_runtime.h>
-
-#define CPF_DI __device__ __forceinline__
+#include "compat.cuh"
 
 CPF_DI void m3_mul(const double* A, const double* B, double* C) {  // C = A B
 #pragma unroll

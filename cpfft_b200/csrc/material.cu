@@ -13,605 +13,40 @@
 #ifndef MM10_MIN_CTAS
 #define MM10_MIN_CTAS 2     // 255 registers; 3 CTAs (168 registers) spill and run 1.5x slower
 #endif
-#include "kin.cuh"
-#include "mm01.cuh"
 #define MM10_THREADS UPD_THREADS
-#include "mm10.cuh"
-#include "slip_tables.cuh"
-#include <cmath>
-#include <map>
-#include <array>
-#include <cstring>
+#include "update.cuh"
+#include "material_tables.hpp"
 
-
-CpfHistLayout cpf_hist_layout(int nslip, int num_hard) {  // mm10_d.f:137-331
-  CpfHistLayout L;
-  L.use_max = (num_hard == 48 || nslip == 48) ? 1 : 0;
-  L.nslip = nslip; L.num_hard = num_hard;
-  const int lc5 = L.use_max ? 48 : nslip;
-  L.cep = 0; L.gradfe = 36; L.R = 63; L.work = 72; L.slipsum = 75;
-  const int common = 75 + lc5;
-  const int l6 = L.use_max ? 48 : nslip, l7 = L.use_max ? 48 : num_hard, l8 = L.use_max ? 48 : 15,
-            l9 = L.use_max ? 48 : num_hard;
-  L.len_slip = l6; L.len_u = l8;
-  L.c_stress = common; L.c_euler = L.c_stress + 6; L.c_Rp = L.c_euler + 3; L.c_D = L.c_Rp + 9;
-  L.c_eps = L.c_D + 6; L.c_slipinc = L.c_eps + 6; L.c_tt = L.c_slipinc + l6; L.c_u = L.c_tt + l7;
-  L.c_ttrate = L.c_u + l8; L.c_ep = L.c_ttrate + l9; L.c_ed = L.c_ep + 6;
-  L.total = L.c_ed + 6;
-  return L;
-}
-
-// ------------------------------------------------------------------------------------------
-struct UpdArgs {
-  const double* Fn; const double* Fn1;
-  const double* urcs_n; double* urcs_n1;
-  const double* eps_n; double* eps_n1;
-  double* rot_n1;
-  const double* hist_n; double* hist_n1;
-  double* cep;
-  const int32_t* matidx; const int32_t* grain;
-  const CpfMatDev* mats; const CpfCryDev* crys; const double* grains;
-  int32_t* fail; int32_t* liters; int* failcnt;
-  int64_t n3; int step, iter; double dt;
-  CpfHistLayout L;
-};
 
 __global__ void __launch_bounds__(UPD_THREADS) k_update_mm01(UpdArgs a) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n3) return;
-  const CpfMatDev mp = a.mats[a.matidx[e]];
-  if (mp.type != 1) return;
-  const int64_t n3 = a.n3;
-  double fn[9], fn1[9], Rh[9], R[9], fhinv[9], detFh, de[6];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) { fn[k] = a.Fn[k * n3 + e]; fn1[k] = a.Fn1[k * n3 + e]; }
-  voxel_kinematics(fn, fn1, Rh, R, fhinv, &detFh, de);
-  double hn[11], sn[9], s1[9], h1[11], cep[36];
-#pragma unroll
-  for (int k = 0; k < 11; ++k) hn[k] = a.hist_n[k * n3 + e];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) sn[k] = a.urcs_n[k * n3 + e];
-  mm01_update(a.step, mp, hn, sn, de, s1, h1, cep);
-#pragma unroll
-  for (int k = 0; k < 9; ++k) a.urcs_n1[k * n3 + e] = s1[k];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) a.eps_n1[k * n3 + e] = a.eps_n[k * n3 + e] + de[k];
-  if (a.iter > 0) {  // rplstr.f:74-85
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) a.rot_n1[(3 * j + i) * n3 + e] = R[3 * i + j];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) a.hist_n1[k * n3 + e] = h1[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] = cep[k];
+  upd_mm01_voxel(a, e);
 }
 
 __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdArgs a) {
   extern __shared__ double mm10_sm[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n3) return;
-  const CpfMatDev mp = a.mats[a.matidx[e]];
-  if (mp.type != 10) return;
-  const int64_t n3 = a.n3;
-  const CpfHistLayout& L = a.L;
-  const CpfCryDev cr = a.crys[mp.crystal];
-  const double* gt = a.grains + (int64_t)a.grain[e] * CPF_GRAIN_STRIDE;
-  const int nslip = cr.nslip;
-  double R[9], de[6];
-  {
-    double fn[9], fn1[9], Rh[9], fhinv[9], detFh;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { fn[k] = a.Fn[k * n3 + e]; fn1[k] = a.Fn1[k * n3 + e]; }
-    voxel_kinematics(fn, fn1, Rh, R, fhinv, &detFh, de);
-  }
-  Mm10Ctx c;
-  c.ms0 = gt + CPF_GRAIN_B; c.C = gt + CPF_GRAIN_C;
-  c.nslip = nslip; c.rate_int = cr.rate_int; c.miter = cr.miter;
-  c.rate_n = cr.rate_n; c.theta_0 = cr.theta_0; c.tau_y = cr.tau_y; c.tau_v = cr.tau_v;
-  c.voche_m = cr.voche_m; c.iD_v = cr.iD_v;
-  c.atol = cr.atol; c.atol1 = cr.atol1; c.rtol = cr.rtol; c.rtol1 = cr.rtol1;
-  // ---- state at n (mm10_copy_cc_hist), or the step-1 initial state (mm10_a.f:92-97,220-227)
-  double Rpn[9], Dn[6], ttrate_n, work_n[3];
-  const bool first = (a.step == 1);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    c.sn[k] = first ? a.urcs_n[k * n3 + e] : a.hist_n[(L.c_stress + k) * n3 + e];
-    Dn[k] = first ? 0.0 : a.hist_n[(L.c_D + k) * n3 + e];
-  }
-#pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      Rpn[3 * i + j] = first ? ((i == j) ? 1.0 : 0.0) : a.hist_n[(L.c_Rp + 3 * j + i) * n3 + e];
-  c.ttn = first ? (cr.tau_y + 1.0e-5) : a.hist_n[L.c_tt * n3 + e];
-  ttrate_n = first ? 0.0 : a.hist_n[L.c_ttrate * n3 + e];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) work_n[k] = first ? 0.0 : a.hist_n[(L.work + k) * n3 + e];
-  // ---- mm10_setup: Q = Rp_n^T, RW(R), dg, tau_l ----
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) c.Q[3 * i + j] = Rpn[3 * j + i];
-  c.J.p = mm10_sm + MM10_SM_J * UPD_THREADS + threadIdx.x;
-  c.RWQ.p = mm10_sm + MM10_SM_RWQ * UPD_THREADS + threadIdx.x;
-  c.RWR.p = mm10_sm + MM10_SM_RWR * UPD_THREADS + threadIdx.x;
-  c.acc.p = mm10_sm + MM10_SM_ACC * UPD_THREADS + threadIdx.x;
-  cpf_rvw(c.Q, c.RWQ);
-  cpf_rvw(R, c.RWR);
-  const double dt = a.dt;
-  {
-    const double mu_h = __ldg(c.C + 35);
-    const double alpha = 1.0 / 3.0;
-    const double cst = cr.k_0 * cr.burgers * alpha * alpha * mu_h * mu_h / 2.0 / cr.theta_0;
-    c.taul = cst * 0.0;
-  }
-  const double t1 = de[0] * de[0] + de[1] * de[1] + de[2] * de[2];
-  const double t2 = de[3] * de[3] + de[4] * de[4] + de[5] * de[5];
-  const double dg_full = cr.alter_mode ? cr.eps_dot_0_y * dt : sqrt((2.0 / 3.0) * (t1 + 0.5 * t2));
-  double sn2 = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) sn2 += c.sn[k] * c.sn[k];
-  const bool no_load = (sn2 == 0.0) && ((t1 + t2) == 0.0);
-  const bool elastic = (a.iter == 0) || no_load;  // iter_0_extrapolate_off (rstgp1.f:870-877)
-
-  double x[7];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) x[k] = c.sn[k];
-  x[6] = c.ttn;
-  double tang[36];   // row-major
-  double tt_rate = 0.0;
-  int itp = 0, itu = 0;
-  bool fail = false;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) c.D[k] = de[k];
-  c.dg = dg_full; c.tinc = dt;
-  if (elastic) {
-#pragma unroll
-    for (int k = 0; k < 36; ++k) tang[k] = __ldg(c.C + k);
-    if (!no_load) {
-      double R1[7];
-      mm10_resid(c, x, x[6], R1, false);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) x[k] = x[k] - R1[k];
-    }
-  } else {
-    // cosine of the angle between the deviatoric strain increments (mm10_a.f:2993-3021)
-    double cos_ang;
-    {
-      double d1[6], d2[6];
-      double tr = (de[0] + de[1] + de[2]) / 3.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) d1[k] = de[k] - ((k < 3) ? tr : 0.0);
-      double a1 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], a2 = d1[3] * d1[3] + d1[4] * d1[4] + d1[5] * d1[5];
-      double s1 = (a1 + a2 == 0.0) ? 0.0 : 1.0 / sqrt(a1 + a2);
-      tr = (Dn[0] + Dn[1] + Dn[2]) / 3.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) d2[k] = Dn[k] - ((k < 3) ? tr : 0.0);
-      a1 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]; a2 = d2[3] * d2[3] + d2[4] * d2[4] + d2[5] * d2[5];
-      double s2 = (a1 + a2 == 0.0) ? 0.0 : 1.0 / sqrt(a1 + a2);
-      // the reference divides each vector by its norm, then takes the dot product; a
-      // uniform scaling of the sub-step strain does not change the direction
-      double p1 = 0.0, p2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) p1 += (d1[k] * s1) * (d2[k] * s2);
-#pragma unroll
-      for (int k = 3; k < 6; ++k) p2 += (d1[k] * s1) * (d2[k] * s2);
-      cos_ang = fmax(p1 + p2, 0.0);
-    }
-    double frac = 0.0, stp = 1.0, ox[7], h_last = c.ttn;
-    int cuts = 0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) ox[k] = x[k];
-    while (frac < 1.0) {  // mm10_solve_strup_iterate (mm10_a.f:2759-2843)
-      const double sc = stp + frac;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) c.D[k] = de[k] * sc;
-      c.tinc = dt * sc;
-      c.dg = cr.alter_mode ? cr.eps_dot_0_y * c.tinc : sqrt((2.0 / 3.0) * ((t1 * sc * sc) + 0.5 * (t2 * sc * sc)));
-      if (!cr.alter_mode && sc == 1.0) c.dg = dg_full;
-      x[6] = c.ttn;
-      fail = mm10_solve(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
-      if (fail) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) x[k] = ox[k];
-        stp = stp * 0.5; cuts = cuts + 1;
-        if (cuts > 4) break;
-        fail = false;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) ox[k] = x[k];
-        frac = frac + stp;
-      }
-    }
-    bool nan = false;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) nan = nan || isnan(x[k]);
-    fail = fail || nan;
-    tt_rate = (h_last - c.ttn) / c.tinc;
-    if (!fail) {
-      // restore the full-step context for tangent / rotation / output (np1, not curr)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) c.D[k] = de[k];
-      c.dg = dg_full; c.tinc = dt;
-      // mm10_tangent (Voce: ed = 0, dgammadd = 0): T = (J11 - J12 J21 / J22)^-1 C.  The Schur
-      // complement replaces the lagged Jacobian in shared memory (padded to 7x7) and the six
-      // columns of C go through the kernel's single LU site one at a time.
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const double beta = c.J[42 + j] / c.J[48];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) c.J[7 * i + j] = c.J[7 * i + j] - c.J[7 * i + 6] * beta;
-      }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { c.J[7 * k + 6] = 0.0; c.J[42 + k] = 0.0; }
-      c.J[48] = 1.0;
-#pragma unroll 1
-      for (int col = 0; col < 6; ++col) {
-        double b7[7];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) b7[k] = __ldg(c.C + 6 * k + col);
-        b7[6] = 0.0;
-        mm10_lu7(c.J.p, 1.0, b7);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) c.acc[6 * k + col] = b7[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 36; ++k) tang[k] = c.acc[k];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)   // mm10_a_make_symm_1
-#pragma unroll
-        for (int j = i + 1; j < 6; ++j) {
-          const double v = (tang[6 * i + j] + tang[6 * j + i]) * 0.5;
-          tang[6 * i + j] = v; tang[6 * j + i] = v;
-        }
-    }
-  }
-  // ---- outputs: update_rotation + mm10_output (skipped on the elastic path, where the
-  //      reference stores the zero-initialised np1 fields) ----
-  double Rp1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, euler[3] = {0, 0, 0}, eps6[6] = {0, 0, 0, 0, 0, 0};
-  double ep6[6] = {0, 0, 0, 0, 0, 0}, ed6[6] = {0, 0, 0, 0, 0, 0};
-  if (fail) {
-    // material_cut_step.  The reference prints a warning, resets stress / tau_tilde to the n
-    // state (mm10_a.f:2838-2841) and leaves the rest of the block un-updated (:125-127), i.e.
-    // undefined data.  Defined behaviour here (identical in the oracle): the point keeps its n
-    // state (stress, tau_tilde, Rp, Euler angles, lattice strain), no slip, elastic tangent;
-    // the sweep goes on and the failure is counted (cpfft_material_failures).
-    a.fail[e] = 1;
-    atomicAdd(a.failcnt, 1); atomicAdd(a.failcnt + 1, 1);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = c.sn[k];
-    x[6] = c.ttn;
-    tt_rate = 0.0;
-#pragma unroll
-    for (int k = 0; k < 36; ++k) tang[k] = __ldg(c.C + k);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Rp1[k] = Rpn[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      euler[k] = first ? __ldg(gt + CPF_GRAIN_ANG + k) : a.hist_n[(L.c_euler + k) * n3 + e];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) eps6[k] = first ? 0.0 : a.hist_n[(L.c_eps + k) * n3 + e];
-  } else a.fail[e] = 0;
-  a.liters[2 * e] = itp; a.liters[2 * e + 1] = itu;
-  double u6 = 0, u7 = 0, u8 = 0, u11 = 0, u12 = 0, u13 = 0, u14 = 0, u15 = 0;
-  double work_inc = 0, p_work_inc = 0, p_strain_inc = 0;
-  const bool full = !elastic && !fail;
-  if (full) {
-    double dbarp[6] = {0, 0, 0, 0, 0, 0}, wq[3] = {0, 0, 0}, edv[6] = {0, 0, 0, 0, 0, 0}, Nv[6] = {0, 0, 0, 0, 0, 0};
-    const double tt = x[6], itt = 1.0 / tt, dgtt = c.dg / tt, dif = dt * c.iD_v, dgn = c.dg * c.rate_n / tt;
-    double maxslip = 0.0; int sysID = 0;
-    for (int s = 0; s < nslip; ++s) {
-      double ms[6], qs[3];
-      mm10_slip_geom(c, s, ms, qs);
-      const double rs = x[0] * ms[0] + x[1] * ms[1] + x[2] * ms[2] + x[3] * ms[3] + x[4] * ms[4] + x[5] * ms[5];
-      const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
-      const double slip = dgtt * p * rs, dslp = rs * dif, dgdt = dgn * p + dif;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { dbarp[k] += slip * ms[k]; edv[k] += dslp * ms[k]; Nv[k] += (rs * dgdt) * ms[k]; }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) wq[k] += (slip + dslp) * qs[k];
-      const double tot = slip + dslp;
-      a.hist_n1[(L.c_slipinc + s) * n3 + e] = tot;
-      a.hist_n1[(L.slipsum + s) * n3 + e] = (first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e]) + tot;
-      if (fabs(tot) > maxslip) { maxslip = fabs(tot); sysID = s + 1; }
-    }
-    int numAct = 0;
-    for (int s = 0; s < nslip; ++s)
-      if (fabs(a.hist_n1[(L.c_slipinc + s) * n3 + e]) >= 0.1 * maxslip) numAct++;
-    u6 = maxslip / dt; u7 = (double)sysID; u8 = (double)numAct;
-    // plastic rotation update: Rp = exp(Wbar_p) Rp_n (mm10_a.f:3310-3414)
-    {
-      double W[9] = {0, wq[2], wq[1], -wq[2], 0, wq[0], -wq[1], -wq[0], 0}, ex[9], W2[9];
-      const double al = sqrt(W[5] * W[5] + W[2] * W[2] + W[1] * W[1]);
-      if (al < 1.0e-16) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) ex[k] = 0.0;
-      } else {
-        m3_mul(W, W, W2);
-        const double ca = (1.0 - cos(al)) / (al * al), cb = sin(al) / al;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) ex[k] = ca * W2[k] + cb * W[k];
-      }
-      ex[0] += 1.0; ex[4] += 1.0; ex[8] += 1.0;
-      m3_mul(ex, Rpn, Rp1);
-    }
-    // Euler angles (mm10_a.f:1171-1233)
-    {
-      double w1[9], fr[9], g[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) g[k] = __ldg(gt + CPF_GRAIN_G + k);
-      m3_mul_nt(Rp1, R, w1);
-      m3_mul(g, w1, fr);
-      const double PI = 3.141592653589793;
-      double psi = cpf_atan2(fr[7], fr[6]); if (psi < 0.0) psi += 2.0 * PI;
-      double phi = cpf_atan2(fr[5], fr[2]); if (phi < 0.0) phi += 2.0 * PI;
-      double f33 = fr[8]; if (f33 > 1.0) f33 = 1.0;
-      const double th = acos(f33);
-      euler[0] = 180.0 / PI * psi; euler[1] = 180.0 / PI * th; euler[2] = 180.0 / PI * phi;
-    }
-    // diffusion strain
-#pragma unroll
-    for (int k = 0; k < 6; ++k) ed6[k] = edv[k] / dt;
-    u15 = sqrt(2.0 / 3.0 * ((edv[0] * edv[0] + edv[1] * edv[1] + edv[2] * edv[2]) +
-                           0.5 * (edv[3] * edv[3] + edv[4] * edv[4] + edv[5] * edv[5]))) / dt;
-    work_inc = x[0] * de[0] + x[1] * de[1] + x[2] * de[2] + x[3] * de[3] + x[4] * de[4] + x[5] * de[5];
-    // lattice strain: ee = RE(R) (C^-1 sigma)
-    {
-      double eu[7];   // C^-1 sigma through the same LU site (C padded to 7x7 in shared memory)
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) c.J[7 * i + j] = __ldg(c.C + 6 * i + j);
-        c.J[7 * i + 6] = 0.0; c.J[42 + i] = 0.0;
-      }
-      c.J[48] = 1.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) eu[k] = x[k];
-      eu[6] = 0.0;
-      mm10_lu7(c.J.p, 1.0, eu);
-      // ee = RT2RVE(R) eeunrot: the stress-type operator (mm10_a.f:3538-3539), i.e. R E~ R^T
-      double E[9], T[9], S2[9];
-      v6_to_m3(eu, E);
-      m3_mul(R, E, T);
-      m3_mul_nt(T, R, S2);
-      eps6[0] = S2[0]; eps6[1] = S2[4]; eps6[2] = S2[8];
-      eps6[3] = S2[1]; eps6[4] = S2[5]; eps6[5] = S2[2];
-    }
-    double wp[3], ew[6], ep[6];
-    cpf_mv3(c.RWR, wq, wp);
-    cpf_symsw(eps6, wp, ew);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { ep[k] = dbarp[k] + ew[k]; ep6[k] = ep[k] / dt; }
-    u11 = sqrt(2.0 / 3.0 * ((ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2]) +
-                           0.5 * (ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5]))) / dt;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) ep[k] = ep[k] + edv[k];
-    p_strain_inc = sqrt(2.0 / 3.0 * ((ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2]) +
-                                    0.5 * (ep[3] * ep[3] + ep[4] * ep[4] + ep[5] * ep[5])));
-    p_work_inc = x[0] * ep[0] + x[1] * ep[1] + x[2] * ep[2] + x[3] * ep[3] + x[4] * ep[4] + x[5] * ep[5];
-    const double ec_dot = p_strain_inc / dt;
-    double n_eff;
-    if (ec_dot > 0.0) {
-      const double a1 = Nv[0] * ep[0] + Nv[1] * ep[1] + Nv[2] * ep[2];
-      const double a2 = Nv[3] * ep[3] + Nv[4] * ep[4] + Nv[5] * ep[5];
-      n_eff = (2.0 / 3.0) * ((a1 + 0.5 * a2) / dt) / ec_dot / ec_dot / dt;
-    } else n_eff = 1.0e10;
-    u12 = n_eff;
-    {
-      const double st = (x[0] + x[1] + x[2]) / 3.0;
-      const double s0 = x[0] - st, s1 = x[1] - st, s2 = x[2] - st;
-      u13 = sqrt(1.5 * ((s0 * s0 + s1 * s1 + s2 * s2) + 2.0 * (x[3] * x[3] + x[4] * x[4] + x[5] * x[5])));
-    }
-    if (ec_dot < 1.e-100) u14 = 0.0;
-    else if (n_eff > 100.0) u14 = -1.0;
-    else u14 = ec_dot / cpf_pow(u13, n_eff);
-  } else {
-    for (int s = 0; s < nslip; ++s) {
-      a.hist_n1[(L.c_slipinc + s) * n3 + e] = 0.0;
-      a.hist_n1[(L.slipsum + s) * n3 + e] = first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e];
-    }
-  }
-  // ---- scatter (mm10_store_cryhist, mm10_a_store_crystal, rplstr: mat 10 always saves hist1)
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    a.urcs_n1[k * n3 + e] = x[k];
-    a.hist_n1[(L.c_stress + k) * n3 + e] = x[k];
-    a.hist_n1[(L.c_D + k) * n3 + e] = de[k];
-    a.hist_n1[(L.c_eps + k) * n3 + e] = eps6[k];
-    a.hist_n1[(L.c_ep + k) * n3 + e] = ep6[k];
-    a.hist_n1[(L.c_ed + k) * n3 + e] = ed6[k];
-    a.eps_n1[k * n3 + e] = a.eps_n[k * n3 + e] + de[k];
-  }
-  a.urcs_n1[6 * n3 + e] = a.urcs_n[6 * n3 + e] + work_inc;
-  a.urcs_n1[7 * n3 + e] = a.urcs_n[7 * n3 + e] + p_work_inc;
-  a.urcs_n1[8 * n3 + e] = a.urcs_n[8 * n3 + e] + p_strain_inc;
-  a.hist_n1[(L.work + 0) * n3 + e] = work_n[0] + work_inc;
-  a.hist_n1[(L.work + 1) * n3 + e] = work_n[1] + p_work_inc;
-  a.hist_n1[(L.work + 2) * n3 + e] = work_n[2] + p_strain_inc;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) a.hist_n1[(L.c_euler + k) * n3 + e] = euler[k];
-#pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      a.hist_n1[(L.c_Rp + 3 * j + i) * n3 + e] = Rp1[3 * i + j];
-      a.hist_n1[(L.R + 3 * j + i) * n3 + e] = R[3 * i + j];
-      if (a.iter > 0) a.rot_n1[(3 * j + i) * n3 + e] = R[3 * i + j];
-    }
-  a.hist_n1[L.c_tt * n3 + e] = x[6];
-  a.hist_n1[L.c_ttrate * n3 + e] = tt_rate;
-  a.hist_n1[(L.c_u + 5) * n3 + e] = u6;
-  a.hist_n1[(L.c_u + 6) * n3 + e] = u7;
-  a.hist_n1[(L.c_u + 7) * n3 + e] = u8;
-  a.hist_n1[(L.c_u + 10) * n3 + e] = u11;
-  a.hist_n1[(L.c_u + 11) * n3 + e] = u12;
-  a.hist_n1[(L.c_u + 12) * n3 + e] = u13;
-  a.hist_n1[(L.c_u + 13) * n3 + e] = u14;
-  a.hist_n1[(L.c_u + 14) * n3 + e] = u15;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      a.hist_n1[(L.cep + 6 * j + i) * n3 + e] = tang[6 * i + j];  // column-major in history
-      a.cep[(6 * i + j) * n3 + e] = tang[6 * i + j];
-    }
+  upd_mm10_voxel(a, e, mm10_sm + threadIdx.x);
 }
 
-// P and K4 for every voxel from (Fn, Fn1, unrotated stress, [D])
 __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, const double* Fn1, const double* urcs_n1,
                                                               const double* cep, double* Pn1, double* K4, int64_t n3) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n3) return;
-  double fn[9], fn1[9], t6[6], C[36], P[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) { fn[k] = Fn[k * n3 + e]; fn1[k] = Fn1[k * n3 + e]; }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) t6[k] = urcs_n1[k * n3 + e];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) C[k] = cep[k * n3 + e];
-  pk1_and_tangent(fn, fn1, t6, C, P, nullptr, K4 + e, n3);
-#pragma unroll
-  for (int k = 0; k < 9; ++k) Pn1[k * n3 + e] = P[k];
+  upd_pk1_voxel(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
 }
 
 // ------------------------------------------------------------------------------------------
-// host side: per-grain table (setup_mm10_rknstr, drive_eps_sig.f:571-606, 975-986;
-// mm10_rotation_matrix mm10_a.f:1287-1345; mm10_RT2RVE mm10_a.f:1400-1447; crystal
-// stiffness finalize_new_crystal mod_crystals.f:1793-1931)
-static void host_rt2rve(const double rt[3][3], double rv[6][6]) {
-  const int a[6] = {0, 1, 2, 0, 1, 0}, b[6] = {0, 1, 2, 1, 2, 2};
-  // strain-type (engineering shear) rotation operator of the tensor map E -> rt E rt^T
-  for (int I = 0; I < 6; ++I)
-    for (int Jc = 0; Jc < 6; ++Jc) {
-      int i = a[I], j = b[I], k = a[Jc], l = b[Jc];
-      double v;
-      if (Jc < 3) v = rt[i][k] * rt[j][k];
-      else v = rt[i][k] * rt[j][l] + rt[i][l] * rt[j][k];
-      if (I < 3 && Jc >= 3) v = 2.0 * rt[i][k] * rt[i][l];
-      rv[I][Jc] = v;
-    }
-}
-static void host_inv6(const double in[6][6], double out[6][6]) {
-  double A[6][12];
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { A[i][j] = in[i][j]; A[i][6 + j] = (i == j); }
-  for (int k = 0; k < 6; ++k) {
-    int p = k;
-    for (int i = k + 1; i < 6; ++i) if (std::fabs(A[i][k]) > std::fabs(A[p][k])) p = i;
-    if (p != k) for (int j = 0; j < 12; ++j) std::swap(A[k][j], A[p][j]);
-    double inv = 1.0 / A[k][k];
-    for (int j = 0; j < 12; ++j) A[k][j] *= inv;
-    for (int i = 0; i < 6; ++i) if (i != k) { double l = A[i][k]; for (int j = 0; j < 12; ++j) A[i][j] -= l * A[k][j]; }
-  }
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[i][j] = A[i][6 + j];
-}
-
 int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* angles) {
   const int64_t n3 = h->n3;
-  const int nmat = (int)h->mats.size(), ncry = (int)h->crys.size();
-  std::vector<CpfMatDev> md(nmat);
-  h->has_mm01 = h->has_mm10 = false;
-  int nslip_max = 0;
-  for (int i = 0; i < nmat; ++i) {
-    const cpfft_material& m = h->mats[i];
-    md[i].type = m.type; md[i].crystal = m.crystal - 1;
-    md[i].ym = (double)m.e; md[i].nu = (double)m.nu; md[i].beta = (double)m.beta;
-    md[i].tan_e = (double)m.tan_e; md[i].yld = (double)m.yld_pt;
-    md[i].hprime = (m.type == 1) ? md[i].tan_e * md[i].ym / (md[i].ym - md[i].tan_e) : 0.0;
-    if (m.type == 1) h->has_mm01 = true;
-    else if (m.type == 10) {
-      h->has_mm10 = true;
-      if (m.crystal < 1 || m.crystal > ncry) { cpf_set_error(h, "material refers to an undefined crystal"); return CPFFT_ERR_USAGE; }
-    } else { cpf_set_error(h, "unsupported material type (1 = bilinear, 10 = cp)"); return CPFFT_ERR_USAGE; }
-  }
-  std::vector<CpfCryDev> cd(std::max(1, ncry));
-  std::vector<std::array<double, 36>> stiff(std::max(1, ncry));
-  std::vector<std::vector<double>> bi(std::max(1, ncry)), ni(std::max(1, ncry));
-  for (int i = 0; i < ncry; ++i) {
-    const cpfft_crystal& c = h->crys[i];
-    CpfCryDev& d = cd[i];
-    if (c.h_type != 1) { cpf_set_error(h, "only Voce hardening (h_type 1) is supported"); return CPFFT_ERR_USAGE; }
-    const signed char (*tb)[3]; const signed char (*tn)[3];
-    if (c.slip_type == 1) { d.nslip = 12; tb = CPF_FCC_B; tn = CPF_FCC_N; }
-    else if (c.slip_type == 8) { d.nslip = 48; tb = CPF_BCC48_B; tn = CPF_BCC48_N; }
-    else { cpf_set_error(h, "unsupported slip_type (1 = fcc, 8 = bcc48)"); return CPFFT_ERR_USAGE; }
-    nslip_max = std::max(nslip_max, d.nslip);
-    bi[i].resize(3 * d.nslip); ni[i].resize(3 * d.nslip);
-    for (int s = 0; s < d.nslip; ++s) {
-      double sb = 0, sn = 0;
-      for (int k = 0; k < 3; ++k) { sb += tb[s][k] * tb[s][k]; sn += tn[s][k] * tn[s][k]; }
-      for (int k = 0; k < 3; ++k) { bi[i][3 * s + k] = (double)tb[s][k] / std::sqrt(sb); ni[i][3 * s + k] = (double)tn[s][k] / std::sqrt(sn); }
-    }
-    d.alter_mode = c.alter_mode; d.miter = c.miter;
-    d.rate_n = c.harden_n; d.theta_0 = c.theta_0; d.tau_y = c.tau_y; d.tau_v = c.tau_v; d.voche_m = c.voche_m;
-    d.iD_v = c.iD_v; d.eps_dot_0_y = c.eps_dot_0_y; d.k_0 = c.k_0; d.burgers = c.burgers;
-    d.atol = c.atol; d.atol1 = c.atol1; d.rtol = c.rtol; d.rtol1 = c.rtol1;
-    const double em1 = c.harden_n - 1.0;
-    d.rate_int = (em1 >= 0.0 && em1 <= 64.0 && em1 == std::floor(em1)) ? (int)em1 : -1;
-    double flex[6][6] = {{0}}, st[6][6];
-    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) flex[a][b] = (a == b) ? 1 / c.e : -c.nu / c.e;
-    const double sh = (c.elastic_type == 1) ? 2 * (1 + c.nu) / c.e : 1 / c.mu;
-    flex[3][3] = flex[4][4] = flex[5][5] = sh;
-    host_inv6(flex, st);
-    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) stiff[i][6 * a + b] = 0.5 * (st[a][b] + st[b][a]);
-  }
-  // voxel -> material index, grain dedup
-  std::vector<int32_t> midx(n3), gidx(n3, 0);
-  std::map<std::array<double, 4>, int> gmap;
-  std::vector<double> gtab;
-  const double PI = 3.141592653589793;
-  for (int64_t e = 0; e < n3; ++e) {
-    const int m = matlist[e] - 1;
-    if (m < 0 || m >= nmat) { cpf_set_error(h, "matlist entry out of range"); return CPFFT_ERR_USAGE; }
-    midx[e] = m;
-    if (h->mats[m].type != 10) continue;
-    const int ci = h->mats[m].crystal - 1;
-    std::array<double, 4> key = {(double)ci, angles[3 * e], angles[3 * e + 1], angles[3 * e + 2]};
-    auto it = gmap.find(key);
-    if (it != gmap.end()) { gidx[e] = it->second; continue; }
-    const int g = (int)gmap.size();
-    gmap[key] = g; gidx[e] = g;
-    gtab.resize((size_t)(g + 1) * CPF_GRAIN_STRIDE, 0.0);
-    double* t = &gtab[(size_t)g * CPF_GRAIN_STRIDE];
-    const double psi = key[1] * PI / 180.0, th = key[2] * PI / 180.0, phi = key[3] * PI / 180.0;
-    double r[3][3];
-    r[0][0] = -std::sin(psi) * std::sin(phi) - std::cos(psi) * std::cos(phi) * std::cos(th);
-    r[0][1] = std::cos(psi) * std::sin(phi) - std::sin(psi) * std::cos(phi) * std::cos(th);
-    r[0][2] = std::cos(phi) * std::sin(th);
-    r[1][0] = std::sin(psi) * std::cos(phi) - std::cos(psi) * std::sin(phi) * std::cos(th);
-    r[1][1] = -std::cos(psi) * std::cos(phi) - std::sin(psi) * std::sin(phi) * std::cos(th);
-    r[1][2] = std::sin(phi) * std::sin(th);
-    r[2][0] = std::cos(psi) * std::sin(th);
-    r[2][1] = std::sin(psi) * std::sin(th);
-    r[2][2] = std::cos(th);
-    double tr[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { t[CPF_GRAIN_G + 3 * i + j] = r[i][j]; tr[i][j] = r[j][i]; }
-    for (int k = 0; k < 3; ++k) t[CPF_GRAIN_ANG + k] = key[1 + k];
-    double Rs[6][6], tmp[6][6];
-    host_rt2rve(tr, Rs);
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += stiff[ci][6 * i + k] * Rs[j][k]; tmp[i][j] = s; }
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double s = 0; for (int k = 0; k < 6; ++k) s += Rs[i][k] * tmp[k][j]; t[CPF_GRAIN_C + 6 * i + j] = s; }
-    const int ns = cd[ci].nslip;
-    for (int s = 0; s < ns; ++s) {
-      double vb[3], vn[3], A[3][3];
-      for (int i = 0; i < 3; ++i) {
-        vb[i] = tr[i][0] * bi[ci][3 * s] + tr[i][1] * bi[ci][3 * s + 1] + tr[i][2] * bi[ci][3 * s + 2];
-        vn[i] = tr[i][0] * ni[ci][3 * s] + tr[i][1] * ni[ci][3 * s + 1] + tr[i][2] * ni[ci][3 * s + 2];
-      }
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = vb[i] * vn[j];
-      double* o = t + CPF_GRAIN_B + 9 * s;
-      o[0] = 0.5 * (A[0][0] + A[0][0]); o[1] = 0.5 * (A[1][1] + A[1][1]); o[2] = 0.5 * (A[2][2] + A[2][2]);
-      o[3] = 2.0 * (0.5 * (A[0][1] + A[1][0])); o[4] = 2.0 * (0.5 * (A[1][2] + A[2][1])); o[5] = 2.0 * (0.5 * (A[0][2] + A[2][0]));
-      o[6] = 0.5 * (A[1][2] - A[2][1]); o[7] = 0.5 * (A[0][2] - A[2][0]); o[8] = 0.5 * (A[0][1] - A[1][0]);
-    }
-  }
-  h->ngrains = (int)gmap.size();
-  if (gtab.empty()) gtab.assign(CPF_GRAIN_STRIDE, 0.0);
-  // history layout / size
-  int H = 11;
-  if (h->has_mm10) { h->L = cpf_hist_layout(nslip_max, 1); H = std::max(H, h->L.total); }
-  else std::memset(&h->L, 0, sizeof(h->L));
+  CpfMatTables T;
+  std::string err;
+  const int rc = cpf_build_material_tables(h->mats, h->crys, matlist, angles, n3, T, err);
+  if (rc) { cpf_set_error(h, err); return rc; }
+  h->has_mm01 = T.has_mm01; h->has_mm10 = T.has_mm10; h->ngrains = T.ngrains; h->L = T.L;
+  const int H = T.H;
   // (re)allocate history fields
   for (int f : {CPFFT_HIST_N, CPFFT_HIST_N1}) {
     if (h->field[f]) cudaFree(h->field[f]);
@@ -627,11 +62,11 @@ int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* an
     if (cudaMalloc(dst, bytes) != cudaSuccess) return 1;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess;
   };
-  if (upload((void**)&h->d_mats, md.data(), sizeof(CpfMatDev) * nmat) ||
-      upload((void**)&h->d_crys, cd.data(), sizeof(CpfCryDev) * cd.size()) ||
-      upload((void**)&h->d_matidx, midx.data(), sizeof(int32_t) * n3) ||
-      upload((void**)&h->d_grain, gidx.data(), sizeof(int32_t) * n3) ||
-      upload((void**)&h->d_grains, gtab.data(), sizeof(double) * gtab.size())) {
+  if (upload((void**)&h->d_mats, T.md.data(), sizeof(CpfMatDev) * T.md.size()) ||
+      upload((void**)&h->d_crys, T.cd.data(), sizeof(CpfCryDev) * T.cd.size()) ||
+      upload((void**)&h->d_matidx, T.midx.data(), sizeof(int32_t) * n3) ||
+      upload((void**)&h->d_grain, T.gidx.data(), sizeof(int32_t) * n3) ||
+      upload((void**)&h->d_grains, T.gtab.data(), sizeof(double) * T.gtab.size())) {
     cpf_set_error(h, "device allocation failed in cpfft_set_voxels");
     return CPFFT_ERR_CUDA;
   }

@@ -5,10 +5,10 @@
 // The numerical constants are the reference's literals, including the truncated ones.
 #pragma once
 #include "kin.cuh"
-#include "common.cuh"
+#include "material_types.h"
 
-CPF_DI double mm01_state_word(int s) { return __longlong_as_double((long long)(unsigned)s); }
-CPF_DI int mm01_state_of(double d) { return (int)(__double_as_longlong(d) & 0xffffffffLL); }
+CPF_DI double mm01_state_word(int s) { return CPF_LL2D((long long)(unsigned)s); }
+CPF_DI int mm01_state_of(double d) { return (int)(CPF_D2LL(d) & 0xffffffffLL); }
 
 // hn[11]: history at n (re-initialised when step == 1, mm01.f:141-144); sn[9]: urcs at n;
 // de[6]: unrotated strain increment; outputs s1[9], h1[11], cep[36] (row-major, symmetric).

@@ -31,7 +31,7 @@
 // expansions sit behind non-inlined wrappers.
 #pragma once
 #include "kin.cuh"
-#include "common.cuh"
+#include "material_types.h"
 
 #ifndef MM10_THREADS
 #define MM10_THREADS 128
@@ -50,8 +50,8 @@ struct SArr {
 #define MM10_SM_ACC 67   // 39: S (21) and T (18) slip sums of the Jacobian
 #define MM10_SMEM_DOUBLES 106
 
-static __device__ __noinline__ double cpf_pow(double x, double y) { return pow(x, y); }
-static __device__ __noinline__ double cpf_atan2(double y, double x) { return atan2(y, x); }
+CPF_DNOINLINE double cpf_pow(double x, double y) { return pow(x, y); }
+CPF_DNOINLINE double cpf_atan2(double y, double x) { return atan2(y, x); }
 
 CPF_DI double cpf_sgn(double x) { return x >= 0.0 ? 1.0 : -1.0; }  // Fortran sign(one,x)
 
@@ -157,7 +157,7 @@ CPF_DI void mm10_lu7_inl(SArr J, double sign, double* b) {
 }
 // out-of-line copy for the cold call sites (tangent columns, lattice strain): a call makes the
 // caller spill its live registers, which the Newton loop cannot afford but the epilogue can
-static __device__ __noinline__ void mm10_lu7(const double* Jp, double sign, double* b) {
+CPF_DNOINLINE void mm10_lu7(const double* Jp, double sign, double* b) {
   SArr J; J.p = const_cast<double*>(Jp);
   double x[7];
 #pragma unroll
@@ -190,8 +190,8 @@ struct Mm10Ctx {
 // doubling) is ms0, Q = Rp_n^T; that is what is evaluated here (45 FMA, no 6x6 operator).
 CPF_DI void mm10_slip_geom(const Mm10Ctx& c, int s, double* ms, double* qs) {
   const double* t = c.ms0 + 9 * s;
-  const double m0 = __ldg(t), m1 = __ldg(t + 1), m2 = __ldg(t + 2), m3 = __ldg(t + 3), m4 = __ldg(t + 4), m5 = __ldg(t + 5);
-  const double w0 = __ldg(t + 6), w1 = __ldg(t + 7), w2 = __ldg(t + 8);
+  const double m0 = CPF_LDG(t), m1 = CPF_LDG(t + 1), m2 = CPF_LDG(t + 2), m3 = CPF_LDG(t + 3), m4 = CPF_LDG(t + 4), m5 = CPF_LDG(t + 5);
+  const double w0 = CPF_LDG(t + 6), w1 = CPF_LDG(t + 7), w2 = CPF_LDG(t + 8);
   double T[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -247,7 +247,7 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
   for (int i = 0; i < 6; ++i) {
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) s += __ldg(c.C + 6 * i + j) * w1[j];
+    for (int j = 0; j < 6; ++j) s += CPF_LDG(c.C + 6 * i + j) * w1[j];
     R[i] = sig[i] - c.sn[i] - s + 2.0 * sw[i];
   }
   double h = 0.0;
@@ -332,7 +332,7 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
     for (int a = 0; a < 6; ++a) {
       double s = 2.0 * sw[a];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += __ldg(c.C + 6 * a + k) * scol[k];
+      for (int k = 0; k < 6; ++k) s += CPF_LDG(c.C + 6 * a + k) * scol[k];
       c.J[7 * a + b] = s;
     }
   }
@@ -358,7 +358,7 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
     for (int a = 0; a < 6; ++a) {
       double s = 2.0 * sw[a];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += __ldg(c.C + 6 * a + k) * dps[k];
+      for (int k = 0; k < 6; ++k) s += CPF_LDG(c.C + 6 * a + k) * dps[k];
       c.J[7 * a + 6] = nt * s;
     }
     // J21 = -theta0 dg n / tt * hfac * sum sgn(rs) |rs/tt|^(n-1) ms
@@ -398,9 +398,9 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, in
   // One loop, one back edge, warp-uniform trip count: lanes that are finished idle until the
   // slowest lane of the warp is done, so the warp reconverges at the top of every trip (a
   // loop with several `continue` edges made the lanes run the body one after another).
-  const unsigned lanes = __activemask();
+  const unsigned lanes = CPF_ACTIVEMASK();
 #pragma unroll 1
-  while (__any_sync(lanes, !done)) {
+  while (CPF_ANY_SYNC(lanes, !done)) {
     if (!done) {
       double yt[7], Rt[7];
 #pragma unroll

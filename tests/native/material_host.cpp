@@ -1,0 +1,109 @@
+// Host build of the per-voxel material code of the CUDA library: the SAME source that nvcc
+// compiles into k_update_mm01 / k_update_mm10 / k_pk1_tangent (cpfft_b200/csrc/update.cuh,
+// mm10.cuh, mm01.cuh, kin.cuh, material_tables.hpp), compiled by plain g++ through the macros
+// of compat.cuh and run voxel by voxel.  TEST INFRASTRUCTURE ONLY: it lets the `-m "not gpu"`
+// suite check the kernels' arithmetic and control flow against the CPU oracle on the build
+// box; the product path never links it.  Built by tests/host_kernels.py.
+#define MM10_THREADS 1
+#include "../../cpfft_b200/csrc/update.cuh"
+#include "../../cpfft_b200/csrc/material_tables.hpp"
+
+#include <cstdio>
+#include <vector>
+
+struct mh_model {
+  CpfMatTables T;
+  std::string err;
+  int64_t n3;
+  double dt;
+  // SoA state, field[comp * n3 + voxel] as on the device
+  std::vector<double> Fn, Fn1, Pn1, K4, urcs_n, urcs_n1, eps_n, eps_n1, rot_n1, hist_n, hist_n1, cep;
+  std::vector<int32_t> fail, liters;
+  int failcnt[2];
+};
+
+extern "C" {
+
+mh_model* mh_create(int64_t n3, int nmat, const cpfft_material* mats, int ncry, const cpfft_crystal* crys,
+                    const int32_t* matlist, const double* angles, double dt) {
+  mh_model* m = new mh_model;
+  m->n3 = n3; m->dt = dt;
+  std::vector<cpfft_material> vm(mats, mats + nmat);
+  std::vector<cpfft_crystal> vc(crys, crys + ncry);
+  if (cpf_build_material_tables(vm, vc, matlist, angles, n3, m->T, m->err)) {
+    std::fprintf(stderr, "mh_create: %s\n", m->err.c_str());
+    delete m;
+    return nullptr;
+  }
+  const size_t n = (size_t)n3;
+  m->Fn.assign(9 * n, 0.0);
+  for (int d : {0, 4, 8}) for (size_t e = 0; e < n; ++e) m->Fn[d * n + e] = 1.0;   // FFT_init.f:157-161
+  m->Fn1 = m->Fn;
+  m->Pn1.assign(9 * n, 0.0); m->K4.assign(81 * n, 0.0);
+  m->urcs_n.assign(9 * n, 0.0); m->urcs_n1.assign(9 * n, 0.0);
+  m->eps_n.assign(6 * n, 0.0); m->eps_n1.assign(6 * n, 0.0);
+  m->rot_n1.assign(9 * n, 0.0);
+  for (int d : {0, 4, 8}) for (size_t e = 0; e < n; ++e) m->rot_n1[d * n + e] = 1.0;
+  m->hist_n.assign((size_t)m->T.H * n, 0.0); m->hist_n1.assign((size_t)m->T.H * n, 0.0);
+  m->cep.assign(36 * n, 0.0);
+  m->fail.assign(n, 0); m->liters.assign(2 * n, 0);
+  m->failcnt[0] = m->failcnt[1] = 0;
+  return m;
+}
+void mh_destroy(mh_model* m) { delete m; }
+int mh_hist_size(mh_model* m) { return m->T.H; }
+int mh_ngrains(mh_model* m) { return m->T.ngrains; }
+
+double* mh_field(mh_model* m, const char* name) {
+  const std::string s(name);
+  if (s == "Fn") return m->Fn.data();
+  if (s == "Fn1") return m->Fn1.data();
+  if (s == "Pn1") return m->Pn1.data();
+  if (s == "K4") return m->K4.data();
+  if (s == "urcs_n") return m->urcs_n.data();
+  if (s == "urcs_n1") return m->urcs_n1.data();
+  if (s == "eps_n") return m->eps_n.data();
+  if (s == "eps_n1") return m->eps_n1.data();
+  if (s == "rot_n1") return m->rot_n1.data();
+  if (s == "hist_n") return m->hist_n.data();
+  if (s == "hist_n1") return m->hist_n1.data();
+  if (s == "cep") return m->cep.data();
+  return nullptr;
+}
+int32_t* mh_fail_flags(mh_model* m) { return m->fail.data(); }
+int32_t* mh_local_iters(mh_model* m) { return m->liters.data(); }
+
+// one drive_eps_sig sweep: what cpf_launch_update launches, voxel by voxel
+int mh_drive_eps_sig(mh_model* m, int step, int iter) {
+  UpdArgs a;
+  a.Fn = m->Fn.data(); a.Fn1 = m->Fn1.data();
+  a.urcs_n = m->urcs_n.data(); a.urcs_n1 = m->urcs_n1.data();
+  a.eps_n = m->eps_n.data(); a.eps_n1 = m->eps_n1.data();
+  a.rot_n1 = m->rot_n1.data();
+  a.hist_n = m->hist_n.data(); a.hist_n1 = m->hist_n1.data();
+  a.cep = m->cep.data();
+  a.matidx = m->T.midx.data(); a.grain = m->T.gidx.data();
+  a.mats = m->T.md.data(); a.crys = m->T.cd.data(); a.grains = m->T.gtab.data();
+  a.fail = m->fail.data(); a.liters = m->liters.data(); a.failcnt = m->failcnt;
+  a.n3 = m->n3; a.step = step; a.iter = iter; a.dt = m->dt; a.L = m->T.L;
+  m->failcnt[1] = 0;
+  const int64_t n3 = m->n3;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t e = 0; e < n3; ++e) {
+    const CpfMatDev& mp = a.mats[a.matidx[e]];
+    if (mp.type == 1) upd_mm01_voxel(a, e);
+    else if (mp.type == 10) {
+      double sm[MM10_SMEM_DOUBLES];
+      upd_mm10_voxel(a, e, sm);
+    }
+    upd_pk1_voxel(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
+  }
+  return m->failcnt[1];
+}
+
+// update.f:75-106 (history, eps, urcs) -- on the device a pointer swap in cpfft_commit_step
+void mh_update(mh_model* m) {
+  m->hist_n = m->hist_n1; m->eps_n = m->eps_n1; m->urcs_n = m->urcs_n1;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""The CUDA library's per-voxel material code, compiled for the host (tests/host_kernels.py,
+tests/native/material_host.cpp), against the CPU oracle: the same comparisons the `-m gpu`
+suite makes through the C ABI (tests/test_gpu_parity.py), made on the build box.  What this
+cannot see is anything CUDA-specific (launch geometry, shared-memory addressing, FMA
+contraction) -- the GPU suite covers that."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import deck, relerr, TOL_VOXEL, compare_mm10_history
+
+# Small-strain tolerance: the reference's closed-form polar decomposition (polar.f:224-307) loses
+# digits when the principal stretches differ by < 3e-3; two builds of the SAME source then differ
+# by a few 1e-9 in R and in everything rotated by it (measured for the oracle itself in
+# tests/test_oracle_material.py::test_stress_noise_floor_..., bound 5e-8; the GPU polycrystal
+# test uses the same bound).  Local Newton iteration counts are compared exactly.
+TOL_SMALL_STRAIN = 5.0e-8
+
+
+@pytest.fixture(scope="module")
+def libs(oracle_built):
+    from host_kernels import HostKernels, build
+    from oracle import Oracle
+    build()
+    return HostKernels, Oracle
+
+
+def _compare_state(k, o, tol=TOL_VOXEL):
+    errs = {
+        "Pn1": relerr(k.Pn1, o.Pn1),
+        "K4": relerr(k.K4, o.K4),
+        "urcs_n1": relerr(k.urcs_n1.T, o.urcs_n1),
+        "eps_n1": relerr(k.eps_n1.T, o.eps_n1),
+    }
+    hk = k.hist_n1.T[:, :o.H]
+    if any(m.type == 10 for m in o.prob.materials):
+        nslip = {1: 12, 8: 48}[o.prob.crystals[0].slip_type]
+        errs.update({"hist." + n: v for n, v in compare_mm10_history(hk, o.hist_n1, nslip, tol).items()})
+    else:
+        errs["hist_n1"] = relerr(hk, o.hist_n1)
+    bad = {n: v for n, v in errs.items() if not v <= tol}
+    assert not bad, f"parity violated: {bad} (all: {errs})"
+    return errs
+
+
+@pytest.mark.parametrize("name", ["test_mm01.in", "test_mm10.in"])
+def test_initial_sweep(libs, name):
+    """drive_eps_sig(1,0) at F = I: P = 0, elastic K4 (FFT_finite_3d.f:145)."""
+    HostKernels, Oracle = libs
+    p = deck(name)
+    k, o = HostKernels(p), Oracle(p)
+    assert k.H == o.H
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    _compare_state(k, o)
+
+
+@pytest.mark.parametrize("name", ["test_mm01.in", "test_mm10.in"])
+def test_sweep_on_perturbed_F(libs, name):
+    """nonlinear sweeps (iter = 0, 1, 2) on a heterogeneous, finite deformation field."""
+    HostKernels, Oracle = libs
+    p = deck(name)
+    k, o = HostKernels(p), Oracle(p)
+    rng = np.random.default_rng(7)
+    amp = 0.05 if name == "test_mm01.in" else 0.004
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += amp * rng.standard_normal((9, p.N3))
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    k.Fn1[:] = F; o.Fn1[:] = F
+    for it in (0, 1, 2):
+        assert k.drive_eps_sig(1, it) == 0 and o.drive_eps_sig(1, it) == 0
+        _compare_state(k, o, TOL_VOXEL if name == "test_mm01.in" else TOL_SMALL_STRAIN)
+    if name == "test_mm10.in":
+        assert np.array_equal(k.local_iters, o.local_iters)
+
+
+@pytest.mark.parametrize("kind", ["fcc_polycrystal", "test_mm10.in", "test_mm01.in"])
+def test_load_path_with_commits(libs, kind):
+    """four load steps along a prescribed heterogeneous deformation path, two sweeps per step,
+    n <- n+1 commits in between (update.f:75-106): the history written by one step is the
+    input of the next, so layout or scatter mistakes accumulate and show."""
+    from cpfft_b200.polycrystal import polycrystal
+    HostKernels, Oracle = libs
+    p = polycrystal(6, ngrains=20) if kind == "fcc_polycrystal" else deck(kind)
+    k, o = HostKernels(p), Oracle(p)
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((9, p.N3))               # fixed direction of the fluctuation
+    G[[0, 4, 8]] -= G[[0, 4, 8]].mean(axis=0)        # roughly isochoric
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.45
+    amp = 0.01 if kind == "test_mm01.in" else 0.002
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    I = np.zeros((9, p.N3)); I[[0, 4, 8]] = 1.0
+    iters = []
+    for step in range(1, 5):
+        for it, frac in ((0, 0.9), (1, 1.0)):
+            F = I + amp * (step - 1 + frac) * (bar + 0.3 * G)
+            k.Fn1[:] = F; o.Fn1[:] = F
+            assert k.drive_eps_sig(step, it) == 0 and o.drive_eps_sig(step, it) == 0
+            _compare_state(k, o, TOL_SMALL_STRAIN)
+            if kind != "test_mm01.in":
+                assert np.array_equal(k.local_iters, o.local_iters)
+                iters.append(int(o.local_iters.sum()))
+        k.Fn[:] = k.Fn1; o.Fn[:] = o.Fn1
+        k.update(); o.update()
+        assert relerr(k.hist_n.T[:, :o.H], o.hist_n) <= TOL_SMALL_STRAIN
+    if kind != "test_mm01.in":
+        assert iters[-1] > 0                          # the path reaches the plastic regime
+
+
+def test_mm10_local_failure_points(libs):
+    """the captured failing points of the 256^3 polycrystal (tests/golden/mm10_fail_points.npz):
+    same failing set, same local iteration counts, same defined fallback state."""
+    from cpfft_b200.polycrystal import polycrystal
+    HostKernels, Oracle = libs
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "mm10_fail_points.npz"))
+    nb = d["Fn"].shape[1]
+    p = polycrystal(2, ngrains=8)
+    p.angles[:nb] = d["angles"]
+    p.angles[nb:] = d["angles"][0]
+    k, o = HostKernels(p), Oracle(p)
+    H = o.H
+    for v in range(p.N3):
+        src = v if v < nb else 0
+        k.hist_n[:H, v] = d["hist_n"][:H, src]; k.urcs_n[:, v] = d["urcs_n"][:, src]; k.eps_n[:, v] = d["eps_n"][:, src]
+        k.Fn[:, v] = d["Fn"][:, src]
+        k.Fn1[:, v] = d["Fn1"][:, src] if v < nb else d["Fn"][:, src] + 0.05 * (d["Fn1"][:, src] - d["Fn"][:, src])
+    o.hist_n[:] = k.hist_n.T[:, :H]; o.urcs_n[:] = k.urcs_n.T; o._view("eps_n", (o.N3, 6))[:] = k.eps_n.T
+    o.Fn[:] = k.Fn; o.Fn1[:] = k.Fn1
+    step, it = int(d["step"]), int(d["iter"])
+    assert k.drive_eps_sig(step, it) == nb
+    assert o.drive_eps_sig(step, it) == nb
+    assert k.fail_flags.sum() == nb and k.fail_flags[:nb].all()
+    assert np.array_equal(k.local_iters, o.local_iters)
+    assert np.array_equal(k.local_iters[:nb], d["liters"])
+    _compare_state(k, o)
