@@ -178,9 +178,9 @@ def _read_material(lines: _Lines, toks: List[str], materials: List[Material], ba
             elif k == "n_crystals":
                 ncry = int(pt[i + 1]); i += 2
             elif k == "crystal_input":
-                if pt[i + 1] != "single":
-                    raise DeckError("only crystal_input single is supported")
-                i += 2
+                if pt[i + 1] not in ("single", "file"):
+                    raise DeckError("crystal_input must be single or file (inmat.f:218-233)")
+                m.crystal_input = 1 if pt[i + 1] == "single" else 2; i += 2
             elif k == "crystal_type":
                 m.crystal = int(pt[i + 1]); i += 2
             elif k == "orientation_input":
@@ -193,8 +193,9 @@ def _read_material(lines: _Lines, toks: List[str], materials: List[Material], ba
                 i += 2
             else:
                 raise DeckError(f"cp: unknown property {k}")
-        if ncry != 1:
-            raise DeckError("n_crystals > 1 is not supported yet")
+        if ncry < 1:
+            raise DeckError("n_crystals must be >= 1")
+        m.n_crystals = ncry
     else:
         raise DeckError(f"material model {kind} not supported (bilinear, cp)")
     materials.append(m)
@@ -202,13 +203,36 @@ def _read_material(lines: _Lines, toks: List[str], materials: List[Material], ba
 
 def read_orientation_file(path: str, n3: int) -> np.ndarray:
     """``elem, psi, theta, phi`` per line (mod_crystals.f:2233-2318, read sequentially)."""
-    ang = np.zeros((n3, 3))
+    return read_crystal_file(path, n3, 1, True, False)[0][:, 0, :]
+
+
+def read_crystal_file(path: str, n3: int, ncry: int, with_angles: bool, with_crystals: bool):
+    """The flat file of ``read_defs`` (mod_crystals.f:2233-2318): ``ncry`` consecutive lines per
+    element, each ``elem [psi theta phi] [crystal]`` -- angles when ``orientation_input file``,
+    crystal numbers when ``crystal_input file``.  Returns (angles (n3,ncry,3), ids (n3,ncry));
+    elements absent from the file keep zeros (the reference aborts when it needs one)."""
+    ang = np.zeros((n3, ncry, 3))
+    ids = np.zeros((n3, ncry), dtype=np.int32)
+    seen = {}
     with open(path) as f:
         rows = [re.split(r"[,\s]+", l.strip()) for l in f if l.strip()]
     for r in rows:
         e = int(r[0])
-        ang[e - 1] = [float(r[1]), float(r[2]), float(r[3])]
-    return ang
+        if not 1 <= e <= n3:
+            continue
+        c = seen.get(e, 0)
+        if c >= ncry:
+            continue                      # read_defs stops after ncry lines of the element
+        seen[e] = c + 1
+        pos = 1
+        if with_angles:
+            ang[e - 1, c] = [float(r[1]), float(r[2]), float(r[3])]; pos = 4
+        if with_crystals:
+            ids[e - 1, c] = int(r[pos])
+    short = [e for e, c in seen.items() if c < ncry]
+    if short:
+        raise DeckError(f"{path}: insufficient data for element {short[0]} (mod_crystals.f:2310)")
+    return ang, ids
 
 
 def read_deck(path: str) -> Problem:
@@ -296,19 +320,30 @@ def read_deck(path: str) -> Problem:
     if N is None or elem_mat is None:
         raise DeckError("deck lacks grid size or element list")
     n3 = N ** 3
-    angles = np.zeros((n3, 3))
+    ncmax = max([m.n_crystals for m in materials if m.type == 10] or [1])
+    from_file = any(m.type == 10 and m.crystal_input == 2 for m in materials)
+    angles = np.zeros((n3, ncmax, 3))
+    crystal_ids = np.zeros((n3, ncmax), dtype=np.int32) if from_file else None
     for im, m in enumerate(materials):
         if m.type != 10:
             continue
         sel = elem_mat == im + 1
+        nc = m.n_crystals
+        if m.orientation_input == 2 or m.crystal_input == 2:
+            fa, fi = read_crystal_file(m.orientation_file, n3, nc, m.orientation_input == 2, m.crystal_input == 2)
         if m.orientation_input == 2:
-            angles[sel] = read_orientation_file(m.orientation_file, n3)[sel]
+            angles[sel, :nc] = fa[sel]
         else:
-            angles[sel] = m.angles
+            angles[sel, :nc] = m.angles
+        if crystal_ids is not None:
+            crystal_ids[sel, :nc] = fi[sel] if m.crystal_input == 2 else m.crystal
+    if ncmax == 1:
+        angles = angles[:, 0, :]
+        crystal_ids = None if crystal_ids is None else crystal_ids
     ncry = max(crystals) if crystals else 0
     cry_list = [crystals.get(i + 1, Crystal()) for i in range(ncry)]
     nstep = max(mults) if mults else 0
     mult_arr = np.array([mults.get(s + 1, 0.0) for s in range(nstep)])
     return Problem(N=N, materials=materials, crystals=cry_list, matlist=elem_mat, angles=angles,
                    FP_max=FP_max, isNBC=isNBC, mults=mult_arr, tolNR=tolNR, tolPCG=tolPCG,
-                   maxIter=maxIter, tstep=tstep, name=name, out_steps=out_steps)
+                   maxIter=maxIter, tstep=tstep, name=name, out_steps=out_steps, crystal_ids=crystal_ids)

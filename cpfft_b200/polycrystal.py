@@ -61,3 +61,26 @@ def polycrystal(N: int, ngrains: int = 1000, seed: int = SEED, nstep: int = 10, 
                 FP_max=FP, isNBC=nbc, mults=np.full(nstep, 1.0 / nstep),
                 tolNR=1.0e-5, tolPCG=1.0e-10, maxIter=20, tstep=1.0)
     return p
+
+
+def taylor_polycrystal(N: int, ncrystals: int = 4, ngrains: int = 1000, seed: int = SEED, nstep: int = 10,
+                       mixed: bool = False) -> Problem:
+    """Polycrystalline material points: every voxel carries ``ncrystals`` crystals whose stresses
+    and tangents are Taylor-averaged (mm10 with n_crystals > 1, mm10_a.f:112-197).  Crystal 0 of
+    a voxel has the orientation of its Voronoi grain, the others are further draws from the same
+    orientation table.  ``mixed``: odd crystals are bcc48 (crystal_input file), even ones fcc."""
+    p = polycrystal(N, ngrains, seed, nstep)
+    gm = grain_map(N, ngrains, seed)
+    table = grain_angles(ngrains + ncrystals, seed)
+    ang = np.stack([table[(gm + c * 7) % len(table)] for c in range(ncrystals)], axis=1)   # (N3, nc, 3)
+    p.angles = np.ascontiguousarray(ang)
+    p.materials[0].n_crystals = ncrystals
+    if mixed:
+        import copy
+        bcc = copy.copy(p.crystals[0]); bcc.slip_type = 8; bcc.tau_y = 120.0
+        p.crystals = [p.crystals[0], bcc]
+        p.materials[0].crystal_input = 2
+        ids = np.ones((len(gm), ncrystals), dtype=np.int32)
+        ids[:, 1::2] = 2
+        p.crystal_ids = ids
+    return p

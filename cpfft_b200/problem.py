@@ -33,7 +33,7 @@ class MaterialPOD(C.Structure):
     _fields_ = [
         ("type", C.c_int32), ("crystal", C.c_int32),
         ("e", C.c_float), ("nu", C.c_float), ("beta", C.c_float), ("tan_e", C.c_float),
-        ("yld_pt", C.c_float), ("pad_", C.c_float),
+        ("yld_pt", C.c_float), ("n_crystals", C.c_int32),
     ]
 
 
@@ -78,6 +78,8 @@ class Material:
     name: str = "mat"
     type: int = 1
     crystal: int = 0          # cp: crystal_type (1-based), crystal_input single
+    n_crystals: int = 1       # cp: crystals per material point, Taylor average (inmat.f:201-204)
+    crystal_input: int = 1    # 1 single (crystal_type), 2 file (per voxel and crystal)
     e: float = 0.0
     nu: float = 0.0
     beta: float = 0.0
@@ -89,7 +91,7 @@ class Material:
 
     def pod(self) -> MaterialPOD:
         p = MaterialPOD()
-        p.type, p.crystal = self.type, self.crystal
+        p.type, p.crystal, p.n_crystals = self.type, self.crystal, self.n_crystals
         p.e, p.nu, p.beta, p.tan_e, p.yld_pt = (np.float32(self.e), np.float32(self.nu),
                                                  np.float32(self.beta), np.float32(self.tan_e),
                                                  np.float32(self.yld_pt))
@@ -102,7 +104,7 @@ class Problem:
     materials: List[Material]
     crystals: List[Crystal]
     matlist: np.ndarray                      # (N3,) int32, 1-based material number per voxel
-    angles: np.ndarray                       # (N3,3) float64 Kocks degrees per voxel
+    angles: np.ndarray                       # (N3,3) Kocks degrees per voxel; (N3,ncmax,3) with n_crystals > 1
     FP_max: np.ndarray = field(default_factory=lambda: np.zeros(9))
     isNBC: np.ndarray = field(default_factory=lambda: np.zeros(9, dtype=np.int32))
     mults: np.ndarray = field(default_factory=lambda: np.zeros(0))
@@ -112,10 +114,28 @@ class Problem:
     tstep: float = 1.0
     name: str = ""                           # `project` card (stname)
     out_steps: tuple = ()                    # `output results steps <list>` (oudriv.f:82-166)
+    crystal_ids: np.ndarray = None           # (N3,ncmax) 1-based crystal numbers (crystal_input file) or None
 
     @property
     def N3(self) -> int:
         return self.N ** 3
+
+    @property
+    def ncmax(self) -> int:
+        """crystals per material point the per-voxel tables are sized for (1 = the classic case)"""
+        return 1 if np.ndim(self.angles) == 2 else int(np.shape(self.angles)[1])
+
+    @property
+    def taylor(self) -> bool:
+        return any(m.type == 10 and m.n_crystals > 1 for m in self.materials) or self.crystal_ids is not None
+
+    def taylor_tables(self):
+        """(ncmax, angles (N3,ncmax,3) float64, crystal_ids (N3,ncmax) int32 or None), C-contiguous"""
+        nc = self.ncmax
+        ang = np.ascontiguousarray(np.asarray(self.angles, dtype=np.float64).reshape(self.N3, nc, 3))
+        ids = None if self.crystal_ids is None else \
+            np.ascontiguousarray(np.asarray(self.crystal_ids, dtype=np.int32).reshape(self.N3, nc))
+        return nc, ang, ids
 
     @property
     def nstep(self) -> int:

@@ -36,6 +36,7 @@ def _lib():
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, ip, dp]
         L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_taylor.argtypes = [C.c_void_p, C.c_int, dp, ip]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_hist_size.argtypes = [C.c_void_p]
@@ -88,9 +89,14 @@ class Oracle:
             L.orc_set_threads(threads)
         mats, crys = prob.material_pods(), prob.crystal_pods()
         ml = np.ascontiguousarray(prob.matlist, dtype=np.int32)
-        ang = np.ascontiguousarray(prob.angles, dtype=np.float64)
+        nc, ang, ids = prob.taylor_tables()
+        ang1 = np.ascontiguousarray(ang[:, 0, :])
         self.h = L.orc_create(prob.N, len(prob.materials), C.addressof(mats), len(prob.crystals),
-                              C.addressof(crys), _ip(ml), _dp(ang))
+                              C.addressof(crys), _ip(ml), _dp(ang1))
+        if prob.taylor:
+            rc = L.orc_set_taylor(self.h, nc, _dp(ang), _ip(ids) if ids is not None else None)
+            if rc:
+                raise ValueError(f"orc_set_taylor: inconsistent crystal tables (code {rc})")
         L.orc_set_params(self.h, prob.tolNR, prob.tolPCG, prob.maxIter, prob.tstep)
         self.N, self.N3 = prob.N, prob.N3
         self.H = L.orc_hist_size(self.h)

@@ -32,6 +32,7 @@ extern "C" {
 #endif
 
 #define ORC_MAX_SLIP 48
+#define ORC_MAX_CRYSTALS_PER_POINT 64
 
 /* one entry of the crystal library c_array (mod_crystals.f:142-214), Voce subset */
 typedef struct {
@@ -54,7 +55,7 @@ typedef struct {
   int32_t type;      /* 1 = bilinear (mm01), 10 = crystal plasticity (mm10) */
   int32_t crystal;   /* cp: 1-based crystal number                          */
   float e, nu, beta, tan_e, yld_pt; /* REAL*4 matprp slots 1,2,3,4,5 (mod_fft.f:20) */
-  float pad_;
+  int32_t n_crystals; /* cp: crystals per material point, imatprp(101) (inmat.f:201-204); 0 = 1 */
 } orc_material;
 
 typedef struct orc_model orc_model;
@@ -64,6 +65,12 @@ typedef struct orc_model orc_model;
 orc_model* orc_create(int N, int nmat, const orc_material* mats, int ncry,
                       const orc_crystal* crys, const int32_t* matlist,
                       const double* angles);
+/* polycrystalline material points (n_crystals > 1, Taylor average mm10_a.f:112-197):
+ * angles (N3, ncmax, 3) and 1-based crystal numbers (N3, ncmax) of every crystal of every voxel
+ * (angle_input / crystal_input of read_crystal_data, mod_crystals.f:2111-2210); crystal_ids may
+ * be NULL = the material's own crystal (crystal_input single).  A voxel uses the first
+ * n_crystals entries of its material.  Resizes the history. */
+int orc_set_taylor(orc_model*, int ncmax, const double* angles, const int32_t* crystal_ids);
 void orc_destroy(orc_model*);
 void orc_set_params(orc_model*, double tolNR, double tolPCG, int maxIter, double tstep);
 void orc_set_threads(int nthreads);

@@ -30,7 +30,7 @@ void mm01_point(int step, const Mm01Props& p, double* history /*may be reset at 
                 double* cgn /*slots 8,9 reset at step 1*/, const double* deps, double* cgn1,
                 double* history1, M66 cep);
 
-// ---- mm10 (mm10_a.f / mm10_b.f), Voce, one crystal ----
+// ---- mm10 (mm10_a.f / mm10_b.f), Voce ----
 struct CrystalLib {
   orc_crystal in;
   int nslip;
@@ -47,10 +47,12 @@ struct HistLayout {                                    // mm10_d.f:25-360
 };
 HistLayout mm10_history_layout(int nslip_max, int num_hard_max);
 
-// returns 0 ok, 1 = material_cut_step (local solve failed)
-int mm10_point(int step, int iter, const CrystalLib& cry, const double* angles_deg,
+// one point with `ncrystals` crystals (Taylor average, mm10_a.f:112-197); crystals[c] and
+// angles_deg[3 c ..] describe crystal c; the history holds the common block followed by
+// ncrystals per-crystal blocks.  returns 0 ok, 1 = material_cut_step (a local solve failed)
+int mm10_point(int step, int iter, int ncrystals, const CrystalLib* const* crystals, const double* angles_deg,
                const HistLayout& L, double dt, const double* rot_n1_colmajor,
                const double* uddt, double* history_n, double* history_np1,
-               const double* urcs_n, double* urcs_n1, int* local_iters /*[2]*/);
+               const double* urcs_n, double* urcs_n1, int* local_iters /*[2], summed over crystals*/);
 
 } // namespace orc

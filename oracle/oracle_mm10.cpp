@@ -631,23 +631,22 @@ static void mm10_output(const Props& p, State& np1, const State& /*n*/) {
 }
 
 // ----------------------------------------------------------------------------
-// mm10 driver for one point / one crystal (mm10_a.f:29-355) incl. mm10_solve_crystal
-// (:1080-1157) and mm10_solve_strup (:2628-2845).
-int mm10_point(int step, int iter, const CrystalLib& cry, const double* angles, const HistLayout& L,
-               double dt, const double* rot9, const double* uddt, double* hn, double* h1,
-               const double* urcs_n, double* urcs_n1, int* local_iters) {
+// One crystal of one point: mm10_a_do_crystal (mm10_a.f:166-243) incl. mm10_solve_crystal
+// (:1080-1157), mm10_solve_strup (:2628-2845) and mm10_store_cryhist (:976-1055).
+// L carries the history offsets of THIS crystal (per-crystal terms already shifted).  The
+// crystal's contributions to the point averages come back in `out`.  Returns 1 when the local
+// solve failed (material_cut_step).
+struct CrystalOut { double stress[6], tangent[6][6], slip_incs[ORC_MAX_SLIP], work_inc, p_work_inc, p_strain_inc; };
+static int mm10_crystal(int step, int iter, const CrystalLib& cry, const double* angles, const HistLayout& L,
+                        double dt, const double* rot9, const double* uddt, double* hn, double* h1,
+                        const double* urcs_n, int* local_iters, CrystalOut& out) {
   const bool iter_0_extrapolate_off = (iter == 0);  // rstgp1.f:870-877
   static thread_local Props p;
   static thread_local State n, np1, curr;
   setup_props(cry, angles, p);
   const int nslip = p.nslip;
-  local_iters[0] = local_iters[1] = 0;
-  if (step == 1) {  // mm10_a.f:92-97, 220-227
-    for (int k = 0; k < 36; ++k) hn[L.cep + k] = 0.0;
-    for (int k = 0; k < 27; ++k) hn[L.gradfe + k] = 0.0;
-    for (int k = 0; k < 9; ++k) hn[L.R + k] = (k % 4 == 0) ? 1.0 : 0.0;
-    for (int k = 0; k < 3; ++k) hn[L.work + k] = 0.0;
-    for (int k = 0; k < L.len_slip; ++k) hn[L.slipsum + k] = 0.0;
+  std::memset(&out, 0, sizeof(out));
+  if (step == 1) {  // mm10_init_cc_hist0 (mm10_a.f:220-227)
     for (int k = 0; k < 6; ++k) hn[L.c_stress + k] = urcs_n[k];
     for (int k = 0; k < 3; ++k) hn[L.c_euler + k] = angles[k];
     for (int k = 0; k < 9; ++k) hn[L.c_Rp + k] = (k % 4 == 0) ? 1.0 : 0.0;
@@ -717,20 +716,17 @@ int mm10_point(int step, int iter, const CrystalLib& cry, const double* angles, 
       // material_cut_step.  The reference prints a warning, sets np1 stress / tau_tilde back to
       // the n state (mm10_a.f:2838-2841), returns from mm10 and leaves the REST OF THE BLOCK
       // un-updated (mm10_a.f:125-127) -- undefined data.  Defined behaviour of this project
-      // (oracle and GPU alike): the point keeps its n state (stress, tau_tilde, Rp, Euler
-      // angles, lattice strain), no slip, elastic tangent; the sweep goes on and the failure
-      // is counted.
-      for (int k = 0; k < 6; ++k) { h1[L.c_stress + k] = n.stress[k]; urcs_n1[k] = n.stress[k]; }
+      // (oracle and GPU alike): the crystal keeps its n state (stress, tau_tilde, Rp, Euler
+      // angles, lattice strain), no slip, elastic tangent; the other crystals of the point and
+      // the sweep go on and the failure is counted.
+      for (int k = 0; k < 6; ++k) { h1[L.c_stress + k] = n.stress[k]; out.stress[k] = n.stress[k]; }
       for (int k = 0; k < 3; ++k) h1[L.c_euler + k] = n.euler[k];
       for (int k = 0; k < 9; ++k) h1[L.c_Rp + k] = hn[L.c_Rp + k];
       for (int k = 0; k < 6; ++k) { h1[L.c_D + k] = np1.D[k]; h1[L.c_eps + k] = n.eps[k]; h1[L.c_ep + k] = 0.0; h1[L.c_ed + k] = 0.0; }
-      for (int k = 0; k < L.len_slip; ++k) { h1[L.c_slipinc + k] = 0.0; h1[L.slipsum + k] = hn[L.slipsum + k]; }
+      for (int k = 0; k < L.len_slip; ++k) h1[L.c_slipinc + k] = 0.0;
       h1[L.c_tt] = n.tau_tilde; h1[L.c_ttrate] = 0.0;
       for (int k = 0; k < 15; ++k) h1[L.c_u + k] = 0.0;
-      for (int k = 0; k < 9; ++k) h1[L.R + k] = rot9[k];
-      for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) h1[L.cep + 6 * j + i] = p.stiffness[i][j];
-      for (int k = 6; k < 9; ++k) urcs_n1[k] = urcs_n[k];
-      for (int k = 0; k < 3; ++k) h1[L.work + k] = hn[L.work + k];
+      for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) out.tangent[i][j] = p.stiffness[i][j];
       return 1;
     }
     curr_tt_rate = curr.tt_rate;
@@ -763,7 +759,7 @@ int mm10_point(int step, int iter, const CrystalLib& cry, const double* angles, 
     mat33(expw, n.Rp, np1.Rp);
     mm10_output(p, np1, n);
   }
-  // ---- mm10_store_cryhist (mm10_a.f:976-1055) + mm10_a_store_crystal (:285-318), ncrystals = 1 ----
+  // ---- mm10_store_cryhist (mm10_a.f:976-1055) ----
   for (int k = 0; k < 6; ++k) h1[L.c_stress + k] = np1.stress[k];
   for (int k = 0; k < 3; ++k) h1[L.c_euler + k] = np1.euler[k];
   for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) h1[L.c_Rp + 3 * j + i] = np1.Rp[i][j];
@@ -773,19 +769,67 @@ int mm10_point(int step, int iter, const CrystalLib& cry, const double* angles, 
   for (int k = 0; k < 15; ++k) h1[L.c_u + k] = np1.u[k];
   h1[L.c_ttrate] = np1.tt_rate;
   for (int k = 0; k < 6; ++k) { h1[L.c_ep + k] = np1.ep[k]; h1[L.c_ed + k] = np1.ed[k]; }
-  for (int k = 0; k < 6; ++k) urcs_n1[k] = np1.stress[k];
-  for (int k = 0; k < 9; ++k) h1[L.R + k] = rot9[k];
-  for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) h1[L.cep + 6 * j + i] = np1.tangent[i][j];
-  for (int k = 0; k < L.len_slip; ++k)
-    h1[L.slipsum + k] = hn[L.slipsum + k] + ((k < nslip) ? np1.slip_incs[k] : 0.0);
-  urcs_n1[6] = urcs_n[6] + np1.work_inc;
-  urcs_n1[7] = urcs_n[7] + np1.p_work_inc;
-  urcs_n1[8] = urcs_n[8] + np1.p_strain_inc;
-  h1[L.work + 0] = hn[L.work + 0] + np1.work_inc;
-  h1[L.work + 1] = hn[L.work + 1] + np1.p_work_inc;
-  h1[L.work + 2] = hn[L.work + 2] + np1.p_strain_inc;
-  (void)nslip;
+  // contributions to the point averages (mm10_a.f:228-238)
+  for (int k = 0; k < 6; ++k) out.stress[k] = np1.stress[k];
+  for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) out.tangent[i][j] = np1.tangent[i][j];
+  for (int k = 0; k < nslip; ++k) out.slip_incs[k] = np1.slip_incs[k];
+  out.work_inc = np1.work_inc; out.p_work_inc = np1.p_work_inc; out.p_strain_inc = np1.p_strain_inc;
   return 0;
+}
+
+// mm10 driver for one point (mm10_a.f:29-355): loop over the crystals of the point, Taylor
+// average of stress, tangent, slip and work increments (mm10_a_crystal_avgs :139-164), store
+// (mm10_a_store_crystal :285-318).  crystals[c] / angles[3 c ..] describe crystal c.
+int mm10_point(int step, int iter, int ncrystals, const CrystalLib* const* crystals, const double* angles,
+               const HistLayout& L, double dt, const double* rot9, const double* uddt, double* hn, double* h1,
+               const double* urcs_n, double* urcs_n1, int* local_iters) {
+  local_iters[0] = local_iters[1] = 0;
+  if (step == 1) {  // mm10_init_general_hist / uout / slip (mm10_a.f:92-97)
+    for (int k = 0; k < 36; ++k) hn[L.cep + k] = 0.0;
+    for (int k = 0; k < 27; ++k) hn[L.gradfe + k] = 0.0;
+    for (int k = 0; k < 9; ++k) hn[L.R + k] = (k % 4 == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < 3; ++k) hn[L.work + k] = 0.0;
+    for (int k = 0; k < L.len_slip; ++k) hn[L.slipsum + k] = 0.0;
+  }
+  double sig_avg[6] = {0, 0, 0, 0, 0, 0}, tang_avg[6][6], slip_avg[ORC_MAX_SLIP];
+  double t_work_inc = 0.0, p_work_inc = 0.0, p_strain_inc = 0.0;
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) tang_avg[i][j] = 0.0;
+  for (int k = 0; k < ORC_MAX_SLIP; ++k) slip_avg[k] = 0.0;
+  const int per = L.total - L.c_stress;    // one_crystal_hist_size
+  int failed = 0;
+  static thread_local CrystalOut out;
+  for (int c = 0; c < ncrystals; ++c) {
+    HistLayout Lc = L;
+    const int co = c * per;
+    Lc.c_stress += co; Lc.c_euler += co; Lc.c_Rp += co; Lc.c_D += co; Lc.c_eps += co; Lc.c_slipinc += co;
+    Lc.c_tt += co; Lc.c_u += co; Lc.c_ttrate += co; Lc.c_ep += co; Lc.c_ed += co;
+    int li[2] = {0, 0};
+    failed += mm10_crystal(step, iter, *crystals[c], angles + 3 * c, Lc, dt, rot9, uddt, hn, h1, urcs_n, li, out);
+    local_iters[0] += li[0]; local_iters[1] += li[1];
+    for (int k = 0; k < 6; ++k) sig_avg[k] = sig_avg[k] + out.stress[k];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) tang_avg[i][j] = tang_avg[i][j] + out.tangent[i][j];
+    for (int k = 0; k < L.len_slip && k < ORC_MAX_SLIP; ++k) slip_avg[k] = slip_avg[k] + out.slip_incs[k];
+    t_work_inc = t_work_inc + out.work_inc;
+    p_work_inc = p_work_inc + out.p_work_inc;
+    p_strain_inc = p_strain_inc + out.p_strain_inc;
+  }
+  const double rncry = (double)ncrystals;   // mm10_a_crystal_avgs
+  for (int k = 0; k < 6; ++k) sig_avg[k] = sig_avg[k] / rncry;
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) tang_avg[i][j] = tang_avg[i][j] / rncry;
+  for (int k = 0; k < ORC_MAX_SLIP; ++k) slip_avg[k] = slip_avg[k] / rncry;
+  t_work_inc = t_work_inc / rncry; p_work_inc = p_work_inc / rncry; p_strain_inc = p_strain_inc / rncry;
+  // mm10_a_store_crystal
+  for (int k = 0; k < 6; ++k) urcs_n1[k] = sig_avg[k];
+  for (int k = 0; k < 9; ++k) h1[L.R + k] = rot9[k];
+  for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) h1[L.cep + 6 * j + i] = tang_avg[i][j];
+  for (int k = 0; k < L.len_slip; ++k) h1[L.slipsum + k] = hn[L.slipsum + k] + ((k < ORC_MAX_SLIP) ? slip_avg[k] : 0.0);
+  urcs_n1[6] = urcs_n[6] + t_work_inc;
+  urcs_n1[7] = urcs_n[7] + p_work_inc;
+  urcs_n1[8] = urcs_n[8] + p_strain_inc;
+  h1[L.work + 0] = hn[L.work + 0] + t_work_inc;
+  h1[L.work + 1] = hn[L.work + 1] + p_work_inc;
+  h1[L.work + 2] = hn[L.work + 2] + p_strain_inc;
+  return failed ? 1 : 0;
 }
 
 } // namespace orc

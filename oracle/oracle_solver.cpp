@@ -58,6 +58,8 @@ struct orc_model {
   std::vector<CrystalLib> crys;
   std::vector<int32_t> matlist;
   std::vector<double> angles;
+  int ncmax;                          // crystals per voxel the tables below are sized for
+  std::vector<int32_t> cry_ids;       // (N3, ncmax) 1-based crystal numbers, empty = material's own
   HistLayout L; int H;
   double tolNR, tolPCG, tstep; int maxIter;
   std::vector<double> Fn, Fn1, Pn, Pn1, K4, dFm, b, tmp1, tmp2, tmp3;
@@ -97,6 +99,7 @@ extern "C" orc_model* orc_create(int N, int nmat, const orc_material* mats, int 
   for (int c = 0; c < ncry; ++c) { m->crys[c].in = crys[c]; finalize_crystal(m->crys[c]); }
   m->matlist.assign(matlist, matlist + m->N3);
   m->angles.assign(angles, angles + 3 * (size_t)m->N3);
+  m->ncmax = 1;
   for (int i = 0; i < nmat; ++i)
     if (mats[i].type == 10) {
       has_cp = true;
@@ -129,6 +132,33 @@ extern "C" orc_model* orc_create(int N, int nmat, const orc_material* mats, int 
   for (int i = 0; i < 9; ++i) { m->barF[i] = m->barF_t[i] = (i % 4 == 0) ? 1.0 : 0.0; m->P_bar[i] = 0.0; }
   m->have_chomo = false;
   return m;
+}
+extern "C" int orc_set_taylor(orc_model* m, int ncmax, const double* angles, const int32_t* crystal_ids) {
+  if (ncmax < 1 || ncmax > ORC_MAX_CRYSTALS_PER_POINT) return 1;
+  const size_t n3 = m->N3;
+  int nslip_max = 0, need = 1;
+  for (size_t e = 0; e < n3; ++e) {
+    const orc_material& mat = m->mats[m->matlist[e] - 1];
+    if (mat.type != 10) continue;
+    const int nc = std::max(1, (int)mat.n_crystals);
+    if (nc > ncmax) return 2;
+    need = std::max(need, nc);
+    for (int c = 0; c < nc; ++c) {
+      const int id = crystal_ids ? crystal_ids[e * ncmax + c] : mat.crystal;
+      if (id < 1 || id > (int)m->crys.size()) return 3;
+      nslip_max = std::max(nslip_max, m->crys[id - 1].nslip);
+    }
+  }
+  m->ncmax = ncmax;
+  m->angles.assign(angles, angles + 3 * n3 * (size_t)ncmax);
+  if (crystal_ids) m->cry_ids.assign(crystal_ids, crystal_ids + n3 * (size_t)ncmax); else m->cry_ids.clear();
+  if (nslip_max > 0) {
+    m->L = mm10_history_layout(nslip_max, 1);
+    const int per = m->L.total - m->L.c_stress;
+    m->H = std::max(11, m->L.c_stress + need * per);     // mm10_set_sizes_special (mm10_a.f:640-641)
+    m->hist_n.assign((size_t)m->H * n3, 0.0); m->hist_n1.assign((size_t)m->H * n3, 0.0);
+  }
+  return 0;
 }
 extern "C" void orc_destroy(orc_model* m) { delete m; }
 extern "C" void orc_set_params(orc_model* m, double tolNR, double tolPCG, int maxIter, double tstep) {
@@ -173,7 +203,8 @@ static int update_point(orc_model* m, size_t e, int step, int iter, const double
   getrm1(qnhalf, rnh, 1);
   qmply1(qnhalf, ddt, uddt);
   // gather n state (dupstr.f)
-  double hn[400], h1[400];
+  std::vector<double> hbuf(2 * (size_t)H);
+  double* hn = hbuf.data(); double* h1 = hn + H;
   for (int k = 0; k < H; ++k) { hn[k] = m->hist_n[e * H + k]; h1[k] = 0.0; }
   double urn[9], ur1[9] = {0}, eps1[6], rot9[9];
   for (int k = 0; k < 9; ++k) urn[k] = m->urcs_n[e * 9 + k];
@@ -190,10 +221,13 @@ static int update_point(orc_model* m, size_t e, int step, int iter, const double
     for (int k = 0; k < 11; ++k) h1[k] = m->hist_n1[e * H + k];  // not rewritten slots keep block values
     mm01_point(step, pr, hn, urn, uddt, ur1, h1, cep);
   } else {
-    const CrystalLib& cry = m->crys[mat.crystal - 1];
+    const int nc = std::min(m->ncmax, std::max(1, (int)mat.n_crystals));   // > 1 needs orc_set_taylor
+    const CrystalLib* cl[ORC_MAX_CRYSTALS_PER_POINT];
+    for (int c = 0; c < nc; ++c)
+      cl[c] = &m->crys[(m->cry_ids.empty() ? mat.crystal : m->cry_ids[e * m->ncmax + c]) - 1];
     for (int k = 0; k < H; ++k) h1[k] = m->hist_n1[e * H + k];
     int li[2];
-    rc = mm10_point(step, iter, cry, &m->angles[3 * e], m->L, m->tstep, rot9, uddt, hn, h1, urn, ur1, li);
+    rc = mm10_point(step, iter, nc, cl, &m->angles[3 * e * (size_t)m->ncmax], m->L, m->tstep, rot9, uddt, hn, h1, urn, ur1, li);
     if (scatter) { m->liters[2 * e] = li[0]; m->liters[2 * e + 1] = li[1]; }
     for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) cep[i][j] = h1[m->L.cep + 6 * j + i];
   }
