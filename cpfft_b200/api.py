@@ -44,6 +44,7 @@ class Config(C.Structure):
 
 EXPORTS = [
     "cpfft_create", "cpfft_destroy", "cpfft_last_error", "cpfft_set_materials", "cpfft_set_voxels",
+    "cpfft_set_voxels_taylor",
     "cpfft_set_params", "cpfft_hist_size", "cpfft_local_voxels", "cpfft_drive_eps_sig", "cpfft_G_K_dF",
     "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3", "cpfft_step_log",
     "cpfft_field_ncomp", "cpfft_upload", "cpfft_download", "cpfft_download_fail_flags",
@@ -75,6 +76,7 @@ def load_library():
     L.cpfft_last_error.restype = C.c_char_p
     L.cpfft_set_materials.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     L.cpfft_set_voxels.argtypes = [vp, ip, dp]
+    L.cpfft_set_voxels_taylor.argtypes = [vp, ip, C.c_int, dp, ip]
     L.cpfft_set_params.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_double]
     L.cpfft_hist_size.argtypes = [vp]
     L.cpfft_local_voxels.argtypes = [vp]
@@ -142,8 +144,15 @@ class Solver:
         lo, hi = (0, self.n3) if local_slab else (rank * self.n3, (rank + 1) * self.n3)
         assert len(prob.matlist) >= hi, "matlist does not cover this rank's slab"
         ml = np.ascontiguousarray(prob.matlist[lo:hi], dtype=np.int32)
-        ang = np.ascontiguousarray(prob.angles[lo:hi], dtype=np.float64)
-        self._check(self.L.cpfft_set_voxels(self.h, _ip(ml), _dp(ang)))
+        if prob.taylor:       # n_crystals > 1 per material point and / or crystal_input file
+            nc = prob.ncmax
+            ang = np.ascontiguousarray(np.asarray(prob.angles, dtype=np.float64).reshape(-1, nc, 3)[lo:hi])
+            ids = None if prob.crystal_ids is None else \
+                np.ascontiguousarray(np.asarray(prob.crystal_ids, dtype=np.int32).reshape(-1, nc)[lo:hi])
+            self._check(self.L.cpfft_set_voxels_taylor(self.h, _ip(ml), nc, _dp(ang), _ip(ids) if ids is not None else None))
+        else:
+            ang = np.ascontiguousarray(prob.angles[lo:hi], dtype=np.float64)
+            self._check(self.L.cpfft_set_voxels(self.h, _ip(ml), _dp(ang)))
         self.H = self.L.cpfft_hist_size(self.h)
         if world > 1:
             if nccl_id is None:

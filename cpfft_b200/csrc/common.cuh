@@ -49,10 +49,12 @@ struct cpfft_handle {
   std::vector<cpfft_crystal> crys;
   CpfMatDev* d_mats; CpfCryDev* d_crys;
   int32_t* d_matidx;         // per voxel 0-based material
-  int32_t* d_grain;          // per voxel grain index
+  int32_t* d_grain;          // (ncmax, n3) grain-table entry per voxel and crystal
+  int32_t* d_grain_cry;      // per grain-table entry: crystal library index
   double* d_grains;          // grain table
   int ngrains;
   bool has_mm01, has_mm10;
+  bool has_mm10_single, has_taylor;   // cp materials with one crystal / with n_crystals > 1 per point
   CpfHistLayout L;
   int32_t* d_fail; int32_t* d_liters;
   int* d_failcnt;            // {mm10 local failures since reset, failures of the last sweep}
@@ -86,7 +88,8 @@ int cpf_prof_begin(cpfft_handle* h, int cls);
 void cpf_prof_end(cpfft_handle* h, int token);
 
 // material.cu
-int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* angles);
+int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const double* angles,
+                       const int32_t* crystal_ids);
 int cpf_launch_update(cpfft_handle* h, int step, int iter);
 
 // spectral.cu

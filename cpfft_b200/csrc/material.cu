@@ -28,7 +28,15 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
   extern __shared__ double mm10_sm[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n3) return;
-  upd_mm10_voxel(a, e, mm10_sm + threadIdx.x);
+  upd_mm10_voxel<false>(a, e, mm10_sm + threadIdx.x);
+}
+
+// polycrystalline material points (n_crystals > 1): same per-crystal integration, Taylor average
+__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_taylor(UpdArgs a) {
+  extern __shared__ double mm10_sm[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n3) return;
+  upd_mm10_voxel<true>(a, e, mm10_sm + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, const double* Fn1, const double* urcs_n1,
@@ -39,13 +47,17 @@ __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, c
 }
 
 // ------------------------------------------------------------------------------------------
-int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* angles) {
+int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const double* angles,
+                       const int32_t* crystal_ids) {
   const int64_t n3 = h->n3;
   CpfMatTables T;
   std::string err;
-  const int rc = cpf_build_material_tables(h->mats, h->crys, matlist, angles, n3, T, err);
+  const int rc = cpf_build_material_tables(h->mats, h->crys, matlist, ncmax, angles, crystal_ids, n3, T, err);
   if (rc) { cpf_set_error(h, err); return rc; }
   h->has_mm01 = T.has_mm01; h->has_mm10 = T.has_mm10; h->ngrains = T.ngrains; h->L = T.L;
+  h->has_taylor = T.has_taylor;
+  h->has_mm10_single = false;
+  for (const CpfMatDev& m : T.md) if (m.type == 10 && m.ncry == 1) h->has_mm10_single = true;
   const int H = T.H;
   // (re)allocate history fields
   for (int f : {CPFFT_HIST_N, CPFFT_HIST_N1}) {
@@ -65,7 +77,8 @@ int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, const double* an
   if (upload((void**)&h->d_mats, T.md.data(), sizeof(CpfMatDev) * T.md.size()) ||
       upload((void**)&h->d_crys, T.cd.data(), sizeof(CpfCryDev) * T.cd.size()) ||
       upload((void**)&h->d_matidx, T.midx.data(), sizeof(int32_t) * n3) ||
-      upload((void**)&h->d_grain, T.gidx.data(), sizeof(int32_t) * n3) ||
+      upload((void**)&h->d_grain, T.gidx.data(), sizeof(int32_t) * T.gidx.size()) ||
+      upload((void**)&h->d_grain_cry, T.gcry.data(), sizeof(int32_t) * T.gcry.size()) ||
       upload((void**)&h->d_grains, T.gtab.data(), sizeof(double) * T.gtab.size())) {
     cpf_set_error(h, "device allocation failed in cpfft_set_voxels");
     return CPFFT_ERR_CUDA;
@@ -81,7 +94,7 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
   a.rot_n1 = h->field[CPFFT_ROT_N1];
   a.hist_n = h->field[CPFFT_HIST_N]; a.hist_n1 = h->field[CPFFT_HIST_N1];
   a.cep = h->field[CPFFT_CEP];
-  a.matidx = h->d_matidx; a.grain = h->d_grain; a.mats = h->d_mats; a.crys = h->d_crys; a.grains = h->d_grains;
+  a.matidx = h->d_matidx; a.grain = h->d_grain; a.grain_cry = h->d_grain_cry; a.mats = h->d_mats; a.crys = h->d_crys; a.grains = h->d_grains;
   a.fail = h->d_fail; a.liters = h->d_liters; a.failcnt = h->d_failcnt;
   a.n3 = h->n3; a.step = step; a.iter = iter; a.dt = h->cfg.tstep; a.L = h->L;
   const int64_t n3 = h->n3;
@@ -91,11 +104,18 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
     k_update_mm01<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++;
     cpf_prof_end(h, tk);
   }
-  if (h->has_mm10) {
+  if (h->has_mm10_single) {
     CPF_CUDA(cudaFuncSetAttribute(k_update_mm10, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS)));
     const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
     k_update_mm10<<<grid, UPD_THREADS, sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS, h->stream>>>(a); h->launches++;
+    cpf_prof_end(h, tk);
+  }
+  if (h->has_taylor) {
+    CPF_CUDA(cudaFuncSetAttribute(k_update_mm10_taylor, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS)));
+    const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
+    k_update_mm10_taylor<<<grid, UPD_THREADS, sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS, h->stream>>>(a); h->launches++;
     cpf_prof_end(h, tk);
   }
   const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);

@@ -19,7 +19,11 @@
 struct CpfMatTables {
   std::vector<CpfMatDev> md;
   std::vector<CpfCryDev> cd;
-  std::vector<int32_t> midx, gidx;   // per voxel: 0-based material, grain index
+  std::vector<int32_t> midx;         // per voxel: 0-based material
+  std::vector<int32_t> gidx;         // (ncmax, n3): grain-table entry of crystal ci of voxel e at [ci * n3 + e]
+  std::vector<int32_t> gcry;         // per grain-table entry: 0-based crystal library index
+  int ncmax = 1;                     // crystals per material point the tables are sized for
+  bool has_taylor = false;           // some cp material has n_crystals > 1
   std::vector<double> gtab;          // ngrains x CPF_GRAIN_STRIDE
   int ngrains = 0, nslip_max = 0;
   bool has_mm01 = false, has_mm10 = false;
@@ -55,8 +59,12 @@ static void host_inv6(const double in[6][6], double out[6][6]) {
 }
 
 // returns 0, or CPFFT_ERR_USAGE with the reason in `err`
+// angles: (n3, ncmax, 3) Kocks degrees; crystal_ids: (n3, ncmax) 1-based crystal numbers or
+// nullptr = the material's own crystal (crystal_input single); a voxel uses the first
+// n_crystals entries of its material (setup_mm10_rknstr case 2, drive_eps_sig.f:744-777).
 static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, const std::vector<cpfft_crystal>& crys,
-                                     const int32_t* matlist, const double* angles, int64_t n3,
+                                     const int32_t* matlist, int ncmax, const double* angles,
+                                     const int32_t* crystal_ids, int64_t n3,
                                      CpfMatTables& T, std::string& err) {
     const int nmat = (int)mats.size(), ncry = (int)crys.size();
   std::vector<CpfMatDev>& md = T.md; md.assign(nmat, CpfMatDev());
@@ -65,13 +73,16 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
   for (int i = 0; i < nmat; ++i) {
     const cpfft_material& m = mats[i];
     md[i].type = m.type; md[i].crystal = m.crystal - 1;
+    md[i].ncry = (m.type == 10 && m.n_crystals > 1) ? m.n_crystals : 1; md[i].pad_ = 0;
+    if (md[i].ncry > ncmax) { err = "n_crystals of a material exceeds the crystals per voxel of cpfft_set_voxels_taylor"; return CPFFT_ERR_USAGE; }
+    if (md[i].ncry > 1) T.has_taylor = true;
     md[i].ym = (double)m.e; md[i].nu = (double)m.nu; md[i].beta = (double)m.beta;
     md[i].tan_e = (double)m.tan_e; md[i].yld = (double)m.yld_pt;
     md[i].hprime = (m.type == 1) ? md[i].tan_e * md[i].ym / (md[i].ym - md[i].tan_e) : 0.0;
     if (m.type == 1) T.has_mm01 = true;
     else if (m.type == 10) {
       T.has_mm10 = true;
-      if (m.crystal < 1 || m.crystal > ncry) { err = "material refers to an undefined crystal"; return CPFFT_ERR_USAGE; }
+      if (!crystal_ids && (m.crystal < 1 || m.crystal > ncry)) { err = "material refers to an undefined crystal"; return CPFFT_ERR_USAGE; }
     } else { err = "unsupported material type (1 = bilinear, 10 = cp)"; return CPFFT_ERR_USAGE; }
   }
   std::vector<CpfCryDev>& cd = T.cd; cd.assign(std::max(1, ncry), CpfCryDev());
@@ -85,7 +96,6 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
     if (c.slip_type == 1) { d.nslip = 12; tb = CPF_FCC_B; tn = CPF_FCC_N; }
     else if (c.slip_type == 8) { d.nslip = 48; tb = CPF_BCC48_B; tn = CPF_BCC48_N; }
     else { err = "unsupported slip_type (1 = fcc, 8 = bcc48)"; return CPFFT_ERR_USAGE; }
-    nslip_max = std::max(nslip_max, d.nslip);
     bi[i].resize(3 * d.nslip); ni[i].resize(3 * d.nslip);
     for (int s = 0; s < d.nslip; ++s) {
       double sb = 0, sn = 0;
@@ -107,7 +117,8 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
   }
   // voxel -> material index, grain dedup
   std::vector<int32_t>& midx = T.midx; std::vector<int32_t>& gidx = T.gidx;
-  midx.assign(n3, 0); gidx.assign(n3, 0);
+  midx.assign(n3, 0); gidx.assign((size_t)n3 * ncmax, 0);
+  T.ncmax = ncmax; T.gcry.clear();
   std::map<std::array<double, 4>, int> gmap;
   std::vector<double>& gtab = T.gtab; gtab.clear();
   const double PI = 3.141592653589793;
@@ -116,12 +127,17 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
     if (m < 0 || m >= nmat) { err = "matlist entry out of range"; return CPFFT_ERR_USAGE; }
     midx[e] = m;
     if (mats[m].type != 10) continue;
-    const int ci = mats[m].crystal - 1;
-    std::array<double, 4> key = {(double)ci, angles[3 * e], angles[3 * e + 1], angles[3 * e + 2]};
+    for (int cc = 0; cc < md[m].ncry; ++cc) {
+    const int ci = (crystal_ids ? crystal_ids[(size_t)e * ncmax + cc] : mats[m].crystal) - 1;
+    if (ci < 0 || ci >= ncry) { err = "voxel refers to an undefined crystal"; return CPFFT_ERR_USAGE; }
+    nslip_max = std::max(nslip_max, cd[ci].nslip);       // over the crystals in use (mm10_d.f:85-110)
+    const double* av = angles + ((size_t)e * ncmax + cc) * 3;
+    std::array<double, 4> key = {(double)ci, av[0], av[1], av[2]};
     auto it = gmap.find(key);
-    if (it != gmap.end()) { gidx[e] = it->second; continue; }
+    if (it != gmap.end()) { gidx[(size_t)cc * n3 + e] = it->second; continue; }
     const int g = (int)gmap.size();
-    gmap[key] = g; gidx[e] = g;
+    gmap[key] = g; gidx[(size_t)cc * n3 + e] = g;
+    T.gcry.push_back(ci);
     gtab.resize((size_t)(g + 1) * CPF_GRAIN_STRIDE, 0.0);
     double* t = &gtab[(size_t)g * CPF_GRAIN_STRIDE];
     const double psi = key[1] * PI / 180.0, th = key[2] * PI / 180.0, phi = key[3] * PI / 180.0;
@@ -155,12 +171,19 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
       o[3] = 2.0 * (0.5 * (A[0][1] + A[1][0])); o[4] = 2.0 * (0.5 * (A[1][2] + A[2][1])); o[5] = 2.0 * (0.5 * (A[0][2] + A[2][0]));
       o[6] = 0.5 * (A[1][2] - A[2][1]); o[7] = 0.5 * (A[0][2] - A[2][0]); o[8] = 0.5 * (A[0][1] - A[1][0]);
     }
+    }   // crystals of the voxel
   }
   T.ngrains = (int)gmap.size();
-  if (gtab.empty()) gtab.assign(CPF_GRAIN_STRIDE, 0.0);
+  if (gtab.empty()) { gtab.assign(CPF_GRAIN_STRIDE, 0.0); T.gcry.assign(1, 0); }
   T.nslip_max = nslip_max;
   T.H = 11;
-  if (T.has_mm10) { T.L = cpf_hist_layout(nslip_max, 1); T.H = std::max(T.H, T.L.total); }
+  if (T.has_mm10) {
+    T.L = cpf_hist_layout(nslip_max, 1);
+    int need = 1;
+    for (int i = 0; i < nmat; ++i) if (md[i].type == 10) need = std::max(need, md[i].ncry);
+    // common block + n_crystals per-crystal blocks (mm10_set_sizes_special, mm10_a.f:640-641)
+    T.H = std::max(T.H, T.L.c_stress + need * (T.L.total - T.L.c_stress));
+  }
   else std::memset(&T.L, 0, sizeof(T.L));
   return 0;
 }

@@ -16,6 +16,7 @@ struct CpfHistLayout {
 // per-material constants in device memory
 struct CpfMatDev {
   int type, crystal;        // crystal: 0-based index into crystal table
+  int ncry, pad_;           // crystals per material point (imatprp(101)); > 1 = Taylor average
   double ym, nu, beta, tan_e, yld, hprime;  // mm01 (REAL*4 promoted, drive_eps_sig.f:486-521)
 };
 

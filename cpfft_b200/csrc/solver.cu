@@ -296,7 +296,8 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   h->prof_on = false;
   for (int i = 0; i < CPF_K_NUM; ++i) { h->prof_ms[i] = 0; h->prof_cnt[i] = 0; }
   for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) { h->field[f] = nullptr; h->ncomp[f] = 0; }
-  h->d_mats = nullptr; h->d_crys = nullptr; h->d_matidx = nullptr; h->d_grain = nullptr; h->d_grains = nullptr;
+  h->d_mats = nullptr; h->d_crys = nullptr; h->d_matidx = nullptr; h->d_grain = nullptr; h->d_grain_cry = nullptr; h->d_grains = nullptr;
+  h->has_mm10_single = h->has_taylor = false;
   h->d_fail = nullptr; h->d_liters = nullptr; h->d_failcnt = nullptr; h->n_fail = h->n_fail_final = 0; h->spec_a = h->spec_b = h->spec_c = nullptr; h->tw = nullptr; h->d_radices = nullptr;
   h->work9 = nullptr; h->d_partials = nullptr; h->d_scalars = nullptr; h->h_scalars = nullptr;
   h->nccl_comm = nullptr; h->nccl_lib = nullptr; h->xchg_send = h->xchg_recv = nullptr;
@@ -354,7 +355,7 @@ void cpfft_destroy(cpfft_handle* h) {
   prof_collect(h);
   for (auto& e : h->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) if (h->field[f]) cudaFree(h->field[f]);
-  void* ptrs[] = {h->d_mats, h->d_crys, h->d_matidx, h->d_grain, h->d_grains, h->d_fail, h->d_liters, h->d_failcnt, h->work9,
+  void* ptrs[] = {h->d_mats, h->d_crys, h->d_matidx, h->d_grain, h->d_grain_cry, h->d_grains, h->d_fail, h->d_liters, h->d_failcnt, h->work9,
                   h->d_partials, h->d_scalars, h->xchg_send, h->xchg_recv};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -378,14 +379,19 @@ int cpfft_set_materials(cpfft_handle* h, int nmat, const cpfft_material* mats, i
   h->crys.assign(crys, crys + (crys ? ncry : 0));
   return 0;
 }
-int cpfft_set_voxels(cpfft_handle* h, const int32_t* matlist, const double* angles) {
+int cpfft_set_voxels_taylor(cpfft_handle* h, const int32_t* matlist, int ncmax, const double* angles,
+                            const int32_t* crystal_ids) {
   if (!h || !matlist || h->mats.empty()) { cpf_set_error(h, "set_materials must precede set_voxels"); return CPFFT_ERR_USAGE; }
+  if (ncmax < 1) { cpf_set_error(h, "cpfft_set_voxels_taylor: ncmax must be >= 1"); return CPFFT_ERR_USAGE; }
   std::vector<double> zeros;
-  if (!angles) { zeros.assign((size_t)3 * h->n3, 0.0); angles = zeros.data(); }
-  int rc = cpf_material_setup(h, matlist, angles);
+  if (!angles) { zeros.assign((size_t)3 * ncmax * h->n3, 0.0); angles = zeros.data(); }
+  int rc = cpf_material_setup(h, matlist, ncmax, angles, crystal_ids);
   if (rc) return rc;
   CPF_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
+}
+int cpfft_set_voxels(cpfft_handle* h, const int32_t* matlist, const double* angles) {
+  return cpfft_set_voxels_taylor(h, matlist, 1, angles, nullptr);
 }
 int cpfft_set_params(cpfft_handle* h, double tolNR, double tolPCG, int maxIter, double tstep) {
   if (!h) return CPFFT_ERR_USAGE;

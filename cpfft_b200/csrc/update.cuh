@@ -21,7 +21,8 @@ struct UpdArgs {
   double* rot_n1;
   const double* hist_n; double* hist_n1;
   double* cep;
-  const int32_t* matidx; const int32_t* grain;
+  const int32_t* matidx; const int32_t* grain;   // grain: (ncmax, n3), crystal ci of voxel e at [ci * n3 + e]
+  const int32_t* grain_cry;                      // per grain-table entry: 0-based crystal library index
   const CpfMatDev* mats; const CpfCryDev* crys; const double* grains;
   int32_t* fail; int32_t* liters; int* failcnt;
   int64_t n3; int step, iter; double dt;
@@ -59,15 +60,21 @@ CPF_DI void upd_mm01_voxel(const UpdArgs& a, const int64_t e) {
   for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] = cep[k];
 }
 
-// sm: this thread's slice of the kernel's shared memory (element k at sm[k * MM10_THREADS])
+// sm: this thread's slice of the kernel's shared memory (element k at sm[k * MM10_THREADS]).
+// MULTI = false: one crystal per material point (every shipped deck, the benchmark).
+// MULTI = true : polycrystalline material points, n_crystals > 1 (mm10_a.f:112-197): the
+//   crystals of the point are integrated one after the other under the same R and D, each
+//   with its own history block (common block + ci * one_crystal_hist_size, mm10_a.f:640-641),
+//   and stress, tangent, slip and work increments are Taylor-averaged
+//   (mm10_a_crystal_avgs, mm10_a.f:139-164).  The sums of the 36 tangent entries and of the
+//   slip increments are kept in the voxel's own n+1 slots (a.cep, hist_n1 slip sums).
+template <bool MULTI>
 CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   const CpfMatDev mp = a.mats[a.matidx[e]];
   if (mp.type != 10) return;
+  if ((mp.ncry > 1) != MULTI) return;
   const int64_t n3 = a.n3;
   const CpfHistLayout& L = a.L;
-  const CpfCryDev cr = a.crys[mp.crystal];
-  const double* gt = a.grains + (int64_t)a.grain[e] * CPF_GRAIN_STRIDE;
-  const int nslip = cr.nslip;
   double R[9], de[6];
   {
     double fn[9], fn1[9], Rh[9], fhinv[9], detFh;
@@ -75,6 +82,23 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
     for (int k = 0; k < 9; ++k) { fn[k] = a.Fn[k * n3 + e]; fn1[k] = a.Fn1[k * n3 + e]; }
     voxel_kinematics(fn, fn1, Rh, R, fhinv, &detFh, de);
   }
+  // Taylor sums (MULTI only)
+  double sig_sum[6] = {0, 0, 0, 0, 0, 0}, winc_sum[3] = {0, 0, 0};
+  int fail_any = 0, itp_sum = 0, itu_sum = 0;
+  if (MULTI) {
+#pragma unroll 1
+    for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < L.len_slip; ++s) a.hist_n1[(L.slipsum + s) * n3 + e] = 0.0;
+  }
+  const int ncry = MULTI ? mp.ncry : 1;
+#pragma unroll 1
+  for (int ci = 0; ci < ncry; ++ci) {
+  const int co = MULTI ? ci * (L.total - L.c_stress) : 0;            // offset of this crystal's history block
+  const int gi = a.grain[(MULTI ? (int64_t)ci * n3 : (int64_t)0) + e];
+  const CpfCryDev cr = a.crys[MULTI ? a.grain_cry[gi] : mp.crystal];
+  const double* gt = a.grains + (int64_t)gi * CPF_GRAIN_STRIDE;
+  const int nslip = cr.nslip;
   Mm10Ctx c;
   c.ms0 = gt + CPF_GRAIN_B; c.C = gt + CPF_GRAIN_C;
   c.nslip = nslip; c.rate_int = cr.rate_int; c.miter = cr.miter;
@@ -86,16 +110,16 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   const bool first = (a.step == 1);
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    c.sn[k] = first ? a.urcs_n[k * n3 + e] : a.hist_n[(L.c_stress + k) * n3 + e];
-    Dn[k] = first ? 0.0 : a.hist_n[(L.c_D + k) * n3 + e];
+    c.sn[k] = first ? a.urcs_n[k * n3 + e] : a.hist_n[((L.c_stress + co) + k) * n3 + e];
+    Dn[k] = first ? 0.0 : a.hist_n[((L.c_D + co) + k) * n3 + e];
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-      Rpn[3 * i + j] = first ? ((i == j) ? 1.0 : 0.0) : a.hist_n[(L.c_Rp + 3 * j + i) * n3 + e];
-  c.ttn = first ? (cr.tau_y + 1.0e-5) : a.hist_n[L.c_tt * n3 + e];
-  ttrate_n = first ? 0.0 : a.hist_n[L.c_ttrate * n3 + e];
+      Rpn[3 * i + j] = first ? ((i == j) ? 1.0 : 0.0) : a.hist_n[((L.c_Rp + co) + 3 * j + i) * n3 + e];
+  c.ttn = first ? (cr.tau_y + 1.0e-5) : a.hist_n[(L.c_tt + co) * n3 + e];
+  ttrate_n = first ? 0.0 : a.hist_n[(L.c_ttrate + co) * n3 + e];
 #pragma unroll
   for (int k = 0; k < 3; ++k) work_n[k] = first ? 0.0 : a.hist_n[(L.work + k) * n3 + e];
   // ---- mm10_setup: Q = Rp_n^T, RW(R), dg, tau_l ----
@@ -247,8 +271,8 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
     // undefined data.  Defined behaviour here (identical in the oracle): the point keeps its n
     // state (stress, tau_tilde, Rp, Euler angles, lattice strain), no slip, elastic tangent;
     // the sweep goes on and the failure is counted (cpfft_material_failures).
-    a.fail[e] = 1;
-    CPF_ATOMIC_INC(a.failcnt); CPF_ATOMIC_INC(a.failcnt + 1);
+    if (MULTI) fail_any = 1;
+    else { a.fail[e] = 1; CPF_ATOMIC_INC(a.failcnt); CPF_ATOMIC_INC(a.failcnt + 1); }
 #pragma unroll
     for (int k = 0; k < 6; ++k) x[k] = c.sn[k];
     x[6] = c.ttn;
@@ -259,11 +283,12 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
     for (int k = 0; k < 9; ++k) Rp1[k] = Rpn[k];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      euler[k] = first ? CPF_LDG(gt + CPF_GRAIN_ANG + k) : a.hist_n[(L.c_euler + k) * n3 + e];
+      euler[k] = first ? CPF_LDG(gt + CPF_GRAIN_ANG + k) : a.hist_n[((L.c_euler + co) + k) * n3 + e];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) eps6[k] = first ? 0.0 : a.hist_n[(L.c_eps + k) * n3 + e];
-  } else a.fail[e] = 0;
-  a.liters[2 * e] = itp; a.liters[2 * e + 1] = itu;
+    for (int k = 0; k < 6; ++k) eps6[k] = first ? 0.0 : a.hist_n[((L.c_eps + co) + k) * n3 + e];
+  } else if (!MULTI) a.fail[e] = 0;
+  if (MULTI) { itp_sum += itp; itu_sum += itu; }
+  else { a.liters[2 * e] = itp; a.liters[2 * e + 1] = itu; }
   double u6 = 0, u7 = 0, u8 = 0, u11 = 0, u12 = 0, u13 = 0, u14 = 0, u15 = 0;
   double work_inc = 0, p_work_inc = 0, p_strain_inc = 0;
   const bool full = !elastic && !fail;
@@ -282,13 +307,14 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) wq[k] += (slip + dslp) * qs[k];
       const double tot = slip + dslp;
-      a.hist_n1[(L.c_slipinc + s) * n3 + e] = tot;
-      a.hist_n1[(L.slipsum + s) * n3 + e] = (first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e]) + tot;
+      a.hist_n1[((L.c_slipinc + co) + s) * n3 + e] = tot;
+      if (MULTI) a.hist_n1[(L.slipsum + s) * n3 + e] += tot;
+      else a.hist_n1[(L.slipsum + s) * n3 + e] = (first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e]) + tot;
       if (fabs(tot) > maxslip) { maxslip = fabs(tot); sysID = s + 1; }
     }
     int numAct = 0;
     for (int s = 0; s < nslip; ++s)
-      if (fabs(a.hist_n1[(L.c_slipinc + s) * n3 + e]) >= 0.1 * maxslip) numAct++;
+      if (fabs(a.hist_n1[((L.c_slipinc + co) + s) * n3 + e]) >= 0.1 * maxslip) numAct++;
     u6 = maxslip / dt; u7 = (double)sysID; u8 = (double)numAct;
     // plastic rotation update: Rp = exp(Wbar_p) Rp_n (mm10_a.f:3310-3414)
     {
@@ -378,54 +404,109 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
     else u14 = ec_dot / cpf_pow(u13, n_eff);
   } else {
     for (int s = 0; s < nslip; ++s) {
-      a.hist_n1[(L.c_slipinc + s) * n3 + e] = 0.0;
-      a.hist_n1[(L.slipsum + s) * n3 + e] = first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e];
+      a.hist_n1[((L.c_slipinc + co) + s) * n3 + e] = 0.0;
+      if (!MULTI) a.hist_n1[(L.slipsum + s) * n3 + e] = first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e];
     }
   }
-  // ---- scatter (mm10_store_cryhist, mm10_a_store_crystal, rplstr: mat 10 always saves hist1)
+  // ---- scatter of the crystal's history block (mm10_store_cryhist; rplstr: mat 10 always saves hist1)
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    a.urcs_n1[k * n3 + e] = x[k];
-    a.hist_n1[(L.c_stress + k) * n3 + e] = x[k];
-    a.hist_n1[(L.c_D + k) * n3 + e] = de[k];
-    a.hist_n1[(L.c_eps + k) * n3 + e] = eps6[k];
-    a.hist_n1[(L.c_ep + k) * n3 + e] = ep6[k];
-    a.hist_n1[(L.c_ed + k) * n3 + e] = ed6[k];
-    a.eps_n1[k * n3 + e] = a.eps_n[k * n3 + e] + de[k];
+    a.hist_n1[((L.c_stress + co) + k) * n3 + e] = x[k];
+    a.hist_n1[((L.c_D + co) + k) * n3 + e] = de[k];
+    a.hist_n1[((L.c_eps + co) + k) * n3 + e] = eps6[k];
+    a.hist_n1[((L.c_ep + co) + k) * n3 + e] = ep6[k];
+    a.hist_n1[((L.c_ed + co) + k) * n3 + e] = ed6[k];
   }
-  a.urcs_n1[6 * n3 + e] = a.urcs_n[6 * n3 + e] + work_inc;
-  a.urcs_n1[7 * n3 + e] = a.urcs_n[7 * n3 + e] + p_work_inc;
-  a.urcs_n1[8 * n3 + e] = a.urcs_n[8 * n3 + e] + p_strain_inc;
-  a.hist_n1[(L.work + 0) * n3 + e] = work_n[0] + work_inc;
-  a.hist_n1[(L.work + 1) * n3 + e] = work_n[1] + p_work_inc;
-  a.hist_n1[(L.work + 2) * n3 + e] = work_n[2] + p_strain_inc;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) a.hist_n1[(L.c_euler + k) * n3 + e] = euler[k];
+  for (int k = 0; k < 3; ++k) a.hist_n1[((L.c_euler + co) + k) * n3 + e] = euler[k];
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      a.hist_n1[(L.c_Rp + 3 * j + i) * n3 + e] = Rp1[3 * i + j];
-      a.hist_n1[(L.R + 3 * j + i) * n3 + e] = R[3 * i + j];
-      if (a.iter > 0) a.rot_n1[(3 * j + i) * n3 + e] = R[3 * i + j];
-    }
-  a.hist_n1[L.c_tt * n3 + e] = x[6];
-  a.hist_n1[L.c_ttrate * n3 + e] = tt_rate;
-  a.hist_n1[(L.c_u + 5) * n3 + e] = u6;
-  a.hist_n1[(L.c_u + 6) * n3 + e] = u7;
-  a.hist_n1[(L.c_u + 7) * n3 + e] = u8;
-  a.hist_n1[(L.c_u + 10) * n3 + e] = u11;
-  a.hist_n1[(L.c_u + 11) * n3 + e] = u12;
-  a.hist_n1[(L.c_u + 12) * n3 + e] = u13;
-  a.hist_n1[(L.c_u + 13) * n3 + e] = u14;
-  a.hist_n1[(L.c_u + 14) * n3 + e] = u15;
+    for (int i = 0; i < 3; ++i) a.hist_n1[((L.c_Rp + co) + 3 * j + i) * n3 + e] = Rp1[3 * i + j];
+  a.hist_n1[(L.c_tt + co) * n3 + e] = x[6];
+  a.hist_n1[(L.c_ttrate + co) * n3 + e] = tt_rate;
+  a.hist_n1[((L.c_u + co) + 5) * n3 + e] = u6;
+  a.hist_n1[((L.c_u + co) + 6) * n3 + e] = u7;
+  a.hist_n1[((L.c_u + co) + 7) * n3 + e] = u8;
+  a.hist_n1[((L.c_u + co) + 10) * n3 + e] = u11;
+  a.hist_n1[((L.c_u + co) + 11) * n3 + e] = u12;
+  a.hist_n1[((L.c_u + co) + 12) * n3 + e] = u13;
+  a.hist_n1[((L.c_u + co) + 13) * n3 + e] = u14;
+  a.hist_n1[((L.c_u + co) + 14) * n3 + e] = u15;
+  if (MULTI) {
+    // sums for the Taylor average (mm10_a.f:228-238)
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < 6; ++k) sig_sum[k] = sig_sum[k] + x[k];
+    winc_sum[0] = winc_sum[0] + work_inc; winc_sum[1] = winc_sum[1] + p_work_inc; winc_sum[2] = winc_sum[2] + p_strain_inc;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      a.hist_n1[(L.cep + 6 * j + i) * n3 + e] = tang[6 * i + j];  // column-major in history
-      a.cep[(6 * i + j) * n3 + e] = tang[6 * i + j];
+    for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] += tang[k];
+  } else {
+    // ---- point-level store for the single crystal (mm10_a_store_crystal) ----
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      a.urcs_n1[k * n3 + e] = x[k];
+      a.eps_n1[k * n3 + e] = a.eps_n[k * n3 + e] + de[k];
     }
+    a.urcs_n1[6 * n3 + e] = a.urcs_n[6 * n3 + e] + work_inc;
+    a.urcs_n1[7 * n3 + e] = a.urcs_n[7 * n3 + e] + p_work_inc;
+    a.urcs_n1[8 * n3 + e] = a.urcs_n[8 * n3 + e] + p_strain_inc;
+    a.hist_n1[(L.work + 0) * n3 + e] = work_n[0] + work_inc;
+    a.hist_n1[(L.work + 1) * n3 + e] = work_n[1] + p_work_inc;
+    a.hist_n1[(L.work + 2) * n3 + e] = work_n[2] + p_strain_inc;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        a.hist_n1[(L.R + 3 * j + i) * n3 + e] = R[3 * i + j];
+        if (a.iter > 0) a.rot_n1[(3 * j + i) * n3 + e] = R[3 * i + j];
+      }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        a.hist_n1[(L.cep + 6 * j + i) * n3 + e] = tang[6 * i + j];  // column-major in history
+        a.cep[(6 * i + j) * n3 + e] = tang[6 * i + j];
+      }
+  }
+  }   // crystals of the point
+  if (MULTI) {
+    // ---- mm10_a_crystal_avgs + mm10_a_store_crystal (mm10_a.f:139-164, 285-318) ----
+    const bool first = (a.step == 1);
+    const double rncry = (double)ncry;
+    a.fail[e] = fail_any;
+    if (fail_any) { CPF_ATOMIC_INC(a.failcnt); CPF_ATOMIC_INC(a.failcnt + 1); }
+    a.liters[2 * e] = itp_sum; a.liters[2 * e + 1] = itu_sum;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      a.urcs_n1[k * n3 + e] = sig_sum[k] / rncry;
+      a.eps_n1[k * n3 + e] = a.eps_n[k * n3 + e] + de[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double inc = winc_sum[k] / rncry;
+      a.urcs_n1[(6 + k) * n3 + e] = a.urcs_n[(6 + k) * n3 + e] + inc;
+      a.hist_n1[(L.work + k) * n3 + e] = (first ? 0.0 : a.hist_n[(L.work + k) * n3 + e]) + inc;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        a.hist_n1[(L.R + 3 * j + i) * n3 + e] = R[3 * i + j];
+        if (a.iter > 0) a.rot_n1[(3 * j + i) * n3 + e] = R[3 * i + j];
+      }
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i)
+#pragma unroll 1
+      for (int j = 0; j < 6; ++j) {
+        const double t = a.cep[(6 * i + j) * n3 + e] / rncry;
+        a.cep[(6 * i + j) * n3 + e] = t;
+        a.hist_n1[(L.cep + 6 * j + i) * n3 + e] = t;               // column-major in history
+      }
+#pragma unroll 1
+    for (int s = 0; s < L.len_slip; ++s)
+      a.hist_n1[(L.slipsum + s) * n3 + e] =
+          (first ? 0.0 : a.hist_n[(L.slipsum + s) * n3 + e]) + a.hist_n1[(L.slipsum + s) * n3 + e] / rncry;
+  }
 }
 
 // P and K4 of one voxel from (Fn, Fn1, unrotated stress, [D])

@@ -26,7 +26,8 @@ module cpfft_iso_c
 
   type, bind(c) :: cpfft_material          ! matprp slots, REAL*4 on purpose (mod_fft.f:20)
      integer(c_int32_t) :: type, crystal
-     real(c_float)      :: e, nu, beta, tan_e, yld_pt, pad_
+     real(c_float)      :: e, nu, beta, tan_e, yld_pt
+     integer(c_int32_t) :: n_crystals       ! imatprp(101): crystals per material point (inmat.f:201-204)
   end type cpfft_material
 
   type, bind(c) :: cpfft_crystal           ! c_array(n), Voce subset (mod_crystals.f:142-214)
@@ -62,6 +63,19 @@ module cpfft_iso_c
        type(c_ptr), value :: handle
        integer(c_int32_t), intent(in) :: matlist(*)
        real(c_double), intent(in) :: angles_deg(3, *)
+     end function
+     ! polycrystalline material points (n_crystals > 1): angle_input / crystal_input of
+     ! read_crystal_data (mod_crystals.f:2111-2210); Fortran shapes angle_input(3, ncmax, nvox),
+     ! crystal_input(ncmax, nvox); pass c_null_ptr-equivalent (an unallocated c_ptr) through
+     ! cpfft_set_voxels when every point has one crystal
+     integer(c_int) function cpfft_set_voxels_taylor(handle, matlist, ncmax, angles_deg, crystal_ids) &
+          bind(c, name='cpfft_set_voxels_taylor')
+       import :: c_int, c_ptr, c_int32_t, c_double
+       type(c_ptr), value :: handle
+       integer(c_int32_t), intent(in) :: matlist(*)
+       integer(c_int), value :: ncmax
+       real(c_double), intent(in) :: angles_deg(3, ncmax, *)
+       integer(c_int32_t), intent(in) :: crystal_ids(ncmax, *)
      end function
      integer(c_int) function cpfft_set_params(handle, tolNR, tolPCG, maxIter, tstep) &
           bind(c, name='cpfft_set_params')

@@ -58,7 +58,9 @@ typedef struct {
 typedef struct {
   int32_t type;     /* 1 bilinear (mm01), 10 crystal plasticity (mm10) */
   int32_t crystal;  /* cp: 1-based crystal number                      */
-  float e, nu, beta, tan_e, yld_pt, pad_;
+  float e, nu, beta, tan_e, yld_pt;
+  int32_t n_crystals; /* cp: crystals per material point, imatprp(101) (inmat.f:201-204);
+                         0 or 1 = one crystal, > 1 = Taylor average (mm10_a.f:112-197) */
 } cpfft_material;
 
 typedef struct {
@@ -99,6 +101,14 @@ int cpfft_set_materials(cpfft_handle* h, int nmat, const cpfft_material* mats, i
                         const cpfft_crystal* crys);
 /* matlist: 1-based material per local voxel; angles: (N3loc,3) Kocks degrees */
 int cpfft_set_voxels(cpfft_handle* h, const int32_t* matlist, const double* angles_deg);
+/* polycrystalline material points (materials with n_crystals > 1): what read_crystal_data
+ * leaves in angle_input / crystal_input (mod_crystals.f:2111-2210).  angles_deg (N3loc, ncmax, 3),
+ * crystal_ids (N3loc, ncmax) 1-based crystal numbers or NULL = the material's crystal_type
+ * (crystal_input single); a voxel uses the first n_crystals entries of its material.  The
+ * history then holds the common block followed by n_crystals per-crystal blocks
+ * (mm10_set_sizes_special, mm10_a.f:640-641). */
+int cpfft_set_voxels_taylor(cpfft_handle* h, const int32_t* matlist, int ncmax,
+                            const double* angles_deg, const int32_t* crystal_ids);
 int cpfft_set_params(cpfft_handle* h, double tolNR, double tolPCG, int maxIter, double tstep);
 int cpfft_hist_size(const cpfft_handle* h);
 int64_t cpfft_local_voxels(const cpfft_handle* h);

@@ -103,7 +103,9 @@ extern "C" orc_model* orc_create(int N, int nmat, const orc_material* mats, int 
   for (int i = 0; i < nmat; ++i)
     if (mats[i].type == 10) {
       has_cp = true;
-      nslip_max = std::max(nslip_max, m->crys[mats[i].crystal - 1].nslip);
+      // crystal_input file: the material names no crystal; orc_set_taylor sizes the history then
+      if (mats[i].crystal >= 1 && mats[i].crystal <= ncry) nslip_max = std::max(nslip_max, m->crys[mats[i].crystal - 1].nslip);
+      else nslip_max = std::max(nslip_max, 12);
       nhard_max = std::max(nhard_max, 1);
     }
   m->H = 11;

@@ -82,11 +82,19 @@ def kocks_matrix(ang_deg):
     return r
 
 
-def compare_mm10_history(hg, ho, nslip, tol=TOL_VOXEL):
-    """Group-wise comparison of (N3, H) mm10 histories.  Euler angles are compared through
+def compare_mm10_history(hg, ho, nslip, tol=TOL_VOXEL, ncrystals=1):
+    """Group-wise comparison of (N3, H) mm10 histories.  ncrystals > 1: the common block followed by
+    one block per crystal (mm10_a.f:640-641); every crystal block is compared like the single one.  Euler angles are compared through
     the rotation matrix they define: at theta ~ 0 (gimbal lock) psi and phi are individually
     undetermined (atan2 of round-off), only the rotation is meaningful."""
     L = mm10_layout(nslip)
+    if ncrystals > 1:
+        common, per = L["stress"][0], L["total"] - L["stress"][0]
+        out = {}
+        for c in range(ncrystals):
+            cols = list(range(common)) + list(range(common + c * per, common + (c + 1) * per))
+            out.update({f"c{c}.{k}": v for k, v in compare_mm10_history(hg[:, cols], ho[:, cols], nslip, tol).items()})
+        return out
     errs = {}
     for name, rng in L.items():
         if name == "total":

@@ -35,7 +35,7 @@ def _lib():
         L = C.CDLL(build())
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L.mh_create.restype = C.c_void_p
-        L.mh_create.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, ip, dp, C.c_double]
+        L.mh_create.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, ip, C.c_int, dp, ip, C.c_double]
         L.mh_destroy.argtypes = [C.c_void_p]
         L.mh_hist_size.argtypes = [C.c_void_p]
         L.mh_ngrains.argtypes = [C.c_void_p]
@@ -63,10 +63,11 @@ class HostKernels:
         self.L, self.prob, self.N3 = L, prob, prob.N3
         mats, crys = prob.material_pods(), prob.crystal_pods()
         ml = np.ascontiguousarray(prob.matlist, dtype=np.int32)
-        ang = np.ascontiguousarray(prob.angles, dtype=np.float64)
+        nc, ang, ids = prob.taylor_tables()
+        ip = C.POINTER(C.c_int32)
         self.h = L.mh_create(prob.N3, len(prob.materials), C.addressof(mats), len(prob.crystals), C.addressof(crys),
-                             ml.ctypes.data_as(C.POINTER(C.c_int32)), ang.ctypes.data_as(C.POINTER(C.c_double)),
-                             prob.tstep)
+                             ml.ctypes.data_as(ip), nc, ang.ctypes.data_as(C.POINTER(C.c_double)),
+                             ids.ctypes.data_as(ip) if ids is not None else None, prob.tstep)
         if not self.h:
             raise RuntimeError("mh_create failed")
         self.H = L.mh_hist_size(self.h)

@@ -25,12 +25,12 @@ struct mh_model {
 extern "C" {
 
 mh_model* mh_create(int64_t n3, int nmat, const cpfft_material* mats, int ncry, const cpfft_crystal* crys,
-                    const int32_t* matlist, const double* angles, double dt) {
+                    const int32_t* matlist, int ncmax, const double* angles, const int32_t* crystal_ids, double dt) {
   mh_model* m = new mh_model;
   m->n3 = n3; m->dt = dt;
   std::vector<cpfft_material> vm(mats, mats + nmat);
   std::vector<cpfft_crystal> vc(crys, crys + ncry);
-  if (cpf_build_material_tables(vm, vc, matlist, angles, n3, m->T, m->err)) {
+  if (cpf_build_material_tables(vm, vc, matlist, ncmax, angles, crystal_ids, n3, m->T, m->err)) {
     std::fprintf(stderr, "mh_create: %s\n", m->err.c_str());
     delete m;
     return nullptr;
@@ -82,7 +82,7 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
   a.rot_n1 = m->rot_n1.data();
   a.hist_n = m->hist_n.data(); a.hist_n1 = m->hist_n1.data();
   a.cep = m->cep.data();
-  a.matidx = m->T.midx.data(); a.grain = m->T.gidx.data();
+  a.matidx = m->T.midx.data(); a.grain = m->T.gidx.data(); a.grain_cry = m->T.gcry.data();
   a.mats = m->T.md.data(); a.crys = m->T.cd.data(); a.grains = m->T.gtab.data();
   a.fail = m->fail.data(); a.liters = m->liters.data(); a.failcnt = m->failcnt;
   a.n3 = m->n3; a.step = step; a.iter = iter; a.dt = m->dt; a.L = m->T.L;
@@ -94,7 +94,8 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
     if (mp.type == 1) upd_mm01_voxel(a, e);
     else if (mp.type == 10) {
       double sm[MM10_SMEM_DOUBLES];
-      upd_mm10_voxel(a, e, sm);
+      if (mp.ncry > 1) upd_mm10_voxel<true>(a, e, sm);
+      else upd_mm10_voxel<false>(a, e, sm);
     }
     upd_pk1_voxel(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
   }

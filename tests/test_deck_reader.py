@@ -4,7 +4,9 @@ inelem / inlodcase / inlod / indypm leave in the reference's modules (SURVEY.md 
 import numpy as np
 import pytest
 
-from helpers import deck, stress_bc_variant
+import os
+
+from helpers import deck, stress_bc_variant, DECKS
 from cpfft_b200.deck import _int_list, _tokens, _is_comment
 
 
@@ -98,3 +100,31 @@ def test_flat_result_writer(tmp_path):
     assert np.abs(back[:, :6] - urcs[:, :6]).max() <= 1e-6 * np.abs(urcs).max() * 10 and (back[:, 6:] == 0).all()
     rows_e = open(tmp_path / "wee00002_text").read().splitlines()[7:]
     assert all(len(r) == 22 * 15 for r in rows_e)
+
+
+def test_polycrystalline_points_from_a_crystal_file(tmp_path):
+    """n_crystals > 1 with `crystal_input file` / `orientation_input file`: ncry consecutive lines
+    per element, `elem psi theta phi crystal` (read_defs, mod_crystals.f:2233-2318)."""
+    from cpfft_b200.deck import read_deck, read_crystal_file, DeckError
+    p = read_deck(os.path.join(DECKS, "taylor_mm10.in"))
+    assert p.N == 5 and p.ncmax == 2 and p.taylor
+    assert p.materials[0].n_crystals == 2 and p.materials[0].crystal_input == 2
+    assert p.angles.shape == (125, 2, 3) and p.crystal_ids.shape == (125, 2)
+    rows = [l.split(",") for l in open(os.path.join(DECKS, "taylor_crystals.in")) if l.strip()]
+    for r in (0, 1, 100, 249):
+        e, c = int(rows[r][0]) - 1, r % 2
+        assert np.allclose(p.angles[e, c], [float(v) for v in rows[r][1:4]])
+        assert p.crystal_ids[e, c] == int(rows[r][4])
+    assert set(np.unique(p.crystal_ids)) == {1, 2} and len(p.crystals) == 2
+    assert p.crystals[0].slip_type == 8 and p.crystals[1].slip_type == 1
+    # angles only / crystals only variants of the same file format
+    f = tmp_path / "ang.in"
+    f.write_text("1 10 20 30\n1 40 50 60\n2 1 2 3\n2 4 5 6\n")
+    a, _ = read_crystal_file(str(f), 2, 2, True, False)
+    assert np.allclose(a[0], [[10, 20, 30], [40, 50, 60]]) and np.allclose(a[1], [[1, 2, 3], [4, 5, 6]])
+    f.write_text("1 2\n1 1\n2 1\n2 2\n")
+    _, ids = read_crystal_file(str(f), 2, 2, False, True)
+    assert ids.tolist() == [[2, 1], [1, 2]]
+    f.write_text("1 10 20 30\n2 1 2 3\n2 4 5 6\n")            # element 1 has one line, two are needed
+    with pytest.raises(DeckError):
+        read_crystal_file(str(f), 2, 2, True, False)

@@ -190,3 +190,42 @@ def test_cli_runs_a_deck_end_to_end(tmp_path):
     assert sorted(os.listdir(tmp_path)) == ["wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text"]
     rows = open(tmp_path / "wes00004_text").read().splitlines()[7:]
     assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_taylor_points(libs, mixed):
+    """polycrystalline material points (mm10 n_crystals = 3, Taylor average mm10_a.f:112-197;
+    `mixed`: fcc and bcc48 crystals in one point through crystal_input file): sweeps along a
+    prescribed heterogeneous path with commits, then a full FFT_nr3 solve."""
+    from cpfft_b200.polycrystal import taylor_polycrystal
+    Solver, Oracle = libs
+    p = taylor_polycrystal(5, ncrystals=3, ngrains=12, nstep=4, mixed=mixed)
+    s, o = Solver(p), Oracle(p)
+    assert s.H == o.H
+    nslip = 48 if mixed else 12
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((9, p.N3))
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.45
+    I = np.zeros((9, p.N3)); I[[0, 4, 8]] = 1.0
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    for step in (1, 2, 3):
+        for it, frac in ((0, 0.9), (1, 1.0)):
+            F = I + 0.002 * (step - 1 + frac) * (bar + 0.3 * G)
+            s.upload("FN1", F); o.Fn1[:] = F
+            s.drive_eps_sig(step, it); assert o.drive_eps_sig(step, it) == 0
+            assert np.array_equal(s.local_iters(), o.local_iters)
+            for name, ref in (("PN1", o.Pn1), ("K4", o.K4)):
+                assert relerr(s.download(name), ref) <= 5e-8       # small-strain polar noise floor
+            compare_mm10_history(s.download("HIST_N1", 1)[:, :o.H], o.hist_n1, nslip, 5e-8, ncrystals=3)
+        s.upload("FN", F); o.Fn[:] = F
+        s.update(); o.update()
+    assert o.local_iters.sum() > 0
+    # full solve from a fresh state
+    s, o = Solver(p), Oracle(p)
+    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    rs, ro = s.FFT_nr3(), o.FFT_nr3()
+    assert ro["rc"] == 0
+    assert list(rs["nr_iters"]) == list(ro["nr_iters"])
+    assert_same_cg_counts(rs["cg_iters"], ro["cg_iters"], slack=1)
+    assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / np.abs(ro["Pbar"]).max() <= TOL_MACRO
+    assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL

@@ -35,8 +35,9 @@ def _compare_state(k, o, tol=TOL_VOXEL):
     }
     hk = k.hist_n1.T[:, :o.H]
     if any(m.type == 10 for m in o.prob.materials):
-        nslip = {1: 12, 8: 48}[o.prob.crystals[0].slip_type]
-        errs.update({"hist." + n: v for n, v in compare_mm10_history(hk, o.hist_n1, nslip, tol).items()})
+        nslip = max({1: 12, 8: 48}[c.slip_type] for c in o.prob.crystals)
+        ncry = max(m.n_crystals for m in o.prob.materials if m.type == 10)
+        errs.update({"hist." + n: v for n, v in compare_mm10_history(hk, o.hist_n1, nslip, tol, ncry).items()})
     else:
         errs["hist_n1"] = relerr(hk, o.hist_n1)
     bad = {n: v for n, v in errs.items() if not v <= tol}
@@ -74,14 +75,19 @@ def test_sweep_on_perturbed_F(libs, name):
         assert np.array_equal(k.local_iters, o.local_iters)
 
 
-@pytest.mark.parametrize("kind", ["fcc_polycrystal", "test_mm10.in", "test_mm01.in"])
+@pytest.mark.parametrize("kind", ["fcc_polycrystal", "test_mm10.in", "test_mm01.in", "taylor_fcc", "taylor_mixed"])
 def test_load_path_with_commits(libs, kind):
     """four load steps along a prescribed heterogeneous deformation path, two sweeps per step,
     n <- n+1 commits in between (update.f:75-106): the history written by one step is the
     input of the next, so layout or scatter mistakes accumulate and show."""
-    from cpfft_b200.polycrystal import polycrystal
+    from cpfft_b200.polycrystal import polycrystal, taylor_polycrystal
     HostKernels, Oracle = libs
-    p = polycrystal(6, ngrains=20) if kind == "fcc_polycrystal" else deck(kind)
+    if kind == "fcc_polycrystal":
+        p = polycrystal(6, ngrains=20)
+    elif kind.startswith("taylor"):       # n_crystals = 3 per material point (mm10_a.f:112-197)
+        p = taylor_polycrystal(5, ncrystals=3, ngrains=12, mixed=(kind == "taylor_mixed"))
+    else:
+        p = deck(kind)
     k, o = HostKernels(p), Oracle(p)
     rng = np.random.default_rng(3)
     G = rng.standard_normal((9, p.N3))               # fixed direction of the fluctuation
