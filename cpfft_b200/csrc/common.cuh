@@ -34,6 +34,8 @@ struct cpfft_handle {
   double prof_ms[CPF_K_NUM]; int64_t prof_cnt[CPF_K_NUM];
   int N, Nh;                 // Nh = stored kz bins: N/2+1, or N/2 on the power-of-two path
   bool fast_pow2;            // spectral_pow2.cu handles this grid
+  int iz_lpc;                // grid lines per CTA of k_iz_pipe
+  int iz_pipe;               // inverse z pass: 0 k_iz, 1 / 2 software-pipelined k_iz_pipe with two / one spectrum buffers
   int nxloc, x0;             // local slab
   int64_t n3;                // local voxels
   int H;                     // history comps

@@ -102,8 +102,10 @@ __device__ __forceinline__ void z_fft_fwd(cplx* A, const cplx* tw, StoreLast sto
   }
 }
 // inverse (transposed) transform: the first stage loads through load_first(c, position)
-template <int H, class LoadFirst>
-__device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst load_first) {
+// `after_first()` runs once, right after the barrier that ends the stage reading through
+// load_first: from there on the source buffer is dead (k_iz_pipe refills it with the next line)
+template <int H, class LoadFirst, class AfterFirst>
+__device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst load_first, AfterFirst after_first) {
   typedef FftPlan<H> P;
   constexpr int N1 = H / P::R1, N2 = N1 / P::R2;
   constexpr bool one = (P::R2 == 1), two = (P::R3 == 1);
@@ -113,6 +115,7 @@ __device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst loa
       fft_stage_dit_inv<N2, P::R3, 2 * (H / N2)>(j, tw, [&](int i) { return load_first(c, i); }, [&](int i, cplx v) { A[i * 9 + c] = v; });
     }
     __syncthreads();
+    after_first();
   }
   if (!one) {
     for (int task = threadIdx.x; task < 9 * (H / P::R2); task += blockDim.x) {
@@ -121,6 +124,7 @@ __device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst loa
       else fft_stage_dit_inv<N1, P::R2, 2 * (H / N1)>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { A[i * 9 + c] = v; });
     }
     __syncthreads();
+    if (two) after_first();
   }
   for (int task = threadIdx.x; task < 9 * (H / P::R1); task += blockDim.x) {
     const int j = task / 9, c = task - j * 9;
@@ -128,6 +132,11 @@ __device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst loa
     else fft_stage_dit_inv<H, P::R1, 2>(j, tw, [&](int i) { return A[i * 9 + c]; }, [&](int i, cplx v) { A[i * 9 + c] = v; });
   }
   __syncthreads();
+  if (one) after_first();
+}
+template <int H, class LoadFirst>
+__device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst load_first) {
+  z_fft_inv<H>(A, tw, load_first, [] {});
 }
 
 // MODE 0: transform src.  MODE 1: transform K4 : src (G_K_dF with flgK).  MODE 2: the CG
@@ -266,6 +275,116 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g
       for (int i = 0; i < Pow2Cfg<N>::ZT / 32; ++i) sum += red[i];
       partials[blockIdx.x] = sum;
     }
+  }
+}
+
+// Software-pipelined inverse z pass.  k_iz is latency bound (0.42 of the HBM peak at 256^3): a
+// CTA loads its 18 KB of spectrum, waits, transforms, stores, and with 4-5 CTAs per SM there
+// are stretches where nothing is in flight.  Here a CTA walks `lpc` consecutive grid lines and
+// prefetches the half-spectrum rows of the next line with cp.async (16-byte LDGSTS, no
+// registers) while the current line is transformed and stored; the CG direction values of the
+// DOT variant are loaded into registers before the transform instead of after it.
+//   DB = true : two B buffers, line i+1 is requested before line i is touched (longest
+//               overlap, 1.45x the shared memory, one CTA per SM fewer);
+//   DB = false: one B buffer, line i+1 is requested as soon as the first butterfly stage has
+//               moved line i from B to A (shared memory and residency of k_iz).
+// Arithmetic, summation order and the per-line partial sums are those of k_iz, so results are
+// bit-identical.
+#include <cuda_pipeline.h>
+template <int N, bool DB> struct ZSmemPipe {
+  static constexpr int H = N / 2;
+  static constexpr int HB = ZSmem<N>::HB;
+  static constexpr size_t bytes = sizeof(cplx) * (9 * H + (DB ? 2 : 1) * 9 * HB + N);
+};
+template <int N, bool DB> struct ZOccPipe {   // resident CTAs the kernel is compiled for
+  static constexpr int BYSMEM = (int)((200 * 1024) / ZSmemPipe<N, DB>::bytes);
+  static constexpr int WANT = DB ? (384 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT : ZOcc<N>::MINB;
+  static constexpr int MINB = BYSMEM < 1 ? 1 : (WANT < BYSMEM ? WANT : BYSMEM);
+};
+template <int N, bool DOT, bool DB>
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOccPipe<N, DB>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+                                                                              const double* __restrict__ pvec, double* __restrict__ partials, int64_t nlines, int lpc) {
+  typedef ZSmem<N> Z;
+  constexpr int H = Z::H, HB = Z::HB;
+  extern __shared__ cplx sm[];
+  cplx* A = sm;
+  cplx* Bb = sm + 9 * H;             // one or two buffers of 9 * HB
+  cplx* tw = Bb + (DB ? 2 : 1) * 9 * HB;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  const int64_t nxN = (int64_t)g.nx * N;
+  const int64_t L0 = (int64_t)blockIdx.x * lpc;          // lpc consecutive grid lines per CTA
+  const int nl = (int)((nlines - L0) < lpc ? (nlines - L0) : lpc);
+  auto prefetch = [&](int64_t L, cplx* B) {
+    for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
+      const int c = idx / H, k = idx - c * H;
+      __pipeline_memcpy_async(B + c * HB + k, spec + ((int64_t)c * nxN + L) * H + k, sizeof(cplx));
+    }
+    __pipeline_commit();
+  };
+  prefetch(L0, Bb);
+  const int t = threadIdx.x;
+  constexpr int NP = H / 2 + 1;
+  for (int il = 0; il < nl; ++il) {
+    const int64_t L = L0 + il;
+    cplx* B = DB ? Bb + (il & 1) * 9 * HB : Bb;
+    if (DB && il + 1 < nl) { prefetch(L + 1, Bb + ((il + 1) & 1) * 9 * HB); __pipeline_wait_prior(1); }
+    else __pipeline_wait_prior(0);
+    __syncthreads();                                    // line L has landed for every thread (and tw on the first trip)
+    const int64_t e0 = L * N + 2 * t;
+    double2 pv[9];
+    if (DOT && t < H) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) pv[c] = *reinterpret_cast<const double2*>(pvec + c * g.n3 + e0);
+    }
+    for (int idx = threadIdx.x; idx < 9 * NP; idx += blockDim.x) {      // tangle, as in k_iz
+      const int c = idx / NP, k = idx - c * NP;
+      cplx* row = B + c * HB;
+      if (k == 0) {
+        const double x0 = row[0].x;
+        row[0] = make_double2(x0, x0);
+      } else {
+        const cplx Xk = row[k], Xh = row[H - k];
+        {
+          const cplx Xm = c_conj(Xh);
+          const cplx E = c_add(Xk, Xm), D = c_sub(Xk, Xm);
+          const cplx O = c_mulc(D, tw[k]);
+          row[k] = make_double2(E.x - O.y, E.y + O.x);
+        }
+        if (2 * k != H) {
+          const cplx Xm = c_conj(Xk);
+          const cplx E = c_add(Xh, Xm), D = c_sub(Xh, Xm);
+          const cplx O = c_mulc(D, tw[H - k]);
+          row[H - k] = make_double2(E.x - O.y, E.y + O.x);
+        }
+      }
+    }
+    __syncthreads();
+    z_fft_inv<H>(A, tw, [&](int c, int p) { return B[c * HB + fft_natural<H>(p)]; },
+                 [&] { if (!DB && il + 1 < nl) prefetch(L + 1, Bb); });
+    double acc = 0.0;
+    if (t < H) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const cplx z = A[t * 9 + c];
+        const double2 o = make_double2(z.x * scale, z.y * scale);
+        *reinterpret_cast<double2*>(dst + c * g.n3 + e0) = o;
+        if (DOT) acc += o.x * pv[c].x + o.y * pv[c].y;
+      }
+    }
+    if (DOT) {
+      __shared__ double red[32];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      if (lane == 0) red[w] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < Pow2Cfg<N>::ZT / 32; ++i) sum += red[i];
+        partials[L] = sum;
+      }
+    }
+    __syncthreads();                                    // A, red and the B buffer of line L are free again
   }
 }
 
@@ -591,7 +710,20 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
   tk = cpf_prof_begin(h, CPF_K_INV_Z);
-  if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
+  if (h->iz_pipe) {
+    const int lpc = h->iz_lpc;
+    const unsigned pgrid = (zgrid + lpc - 1) / lpc;
+    if (cg) const_cast<CgFuse*>(cg)->nparts = (int)zgrid;
+    if (h->iz_pipe == 1) {
+      const size_t sm_p = ZSmemPipe<N, true>::bytes;
+      if (cg) k_iz_pipe<N, true, true><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
+      else k_iz_pipe<N, false, true><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
+    } else {
+      const size_t sm_p = ZSmemPipe<N, false>::bytes;
+      if (cg) k_iz_pipe<N, true, false><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
+      else k_iz_pipe<N, false, false><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
+    }
+  } else if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
   else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
   cpf_prof_end(h, tk);
   h->launches += 5;
@@ -612,6 +744,10 @@ static int init_pow2(cpfft_handle* h) {
   CPF_SMEM_ATTR((k_fz<N, 2>), sm_z);
   CPF_SMEM_ATTR((k_iz<N, true>), sm_z);
   CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
+  CPF_SMEM_ATTR((k_iz_pipe<N, true, true>), (ZSmemPipe<N, true>::bytes));
+  CPF_SMEM_ATTR((k_iz_pipe<N, false, true>), (ZSmemPipe<N, true>::bytes));
+  CPF_SMEM_ATTR((k_iz_pipe<N, true, false>), (ZSmemPipe<N, false>::bytes));
+  CPF_SMEM_ATTR((k_iz_pipe<N, false, false>), (ZSmemPipe<N, false>::bytes));
   CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
   CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
   CPF_SMEM_ATTR((k_fyi<N>), sm_y);

@@ -152,3 +152,33 @@ def test_polycrystal_stress_bc_matches_oracle(libs):
     assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / scale <= 1e-9
     assert np.abs(rs["Pbar"][:, [4, 8]]).max() <= 1e-5 * scale      # the prescribed stresses are met
     assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
+
+
+@pytest.mark.parametrize("N", [16, 32, 40, 64, 80, 128])
+def test_inverse_z_pass_variants_are_bit_identical(libs, N, monkeypatch):
+    """k_iz and the two software-pipelined k_iz_pipe variants (CPFFT_IZ_PIPE = 0 / 1 / 2, read when
+    the handle is created) do the same arithmetic in the same order: G_K_dF and a CG solve
+    (p.Ap partial sums fused into the pass) must agree bit for bit."""
+    from test_oracle_spectral import _toy_problem
+    Solver, _ = libs
+    p = _toy_problem(N)
+    rng = np.random.default_rng(N)
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += 0.02 * rng.standard_normal((9, p.N3))
+    x = rng.standard_normal((9, p.N3))
+    res = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("CPFFT_IZ_PIPE", mode)
+        s = Solver(p)
+        s.upload("FN1", F)
+        s.drive_eps_sig(1, 1)
+        s.upload("DFM", x)
+        s.G_K_dF("DFM", "B", 1)
+        g = s.download("B")
+        it, rr = s.fftPcg("B", "DFM", 1e-8)
+        res.append((g, s.download("DFM"), it, rr))
+        del s
+    for g, sol, it, rr in res[1:]:
+        assert np.array_equal(g, res[0][0])
+        assert it == res[0][2] and rr == res[0][3]
+        assert np.array_equal(sol, res[0][1])
