@@ -34,8 +34,9 @@ struct cpfft_handle {
   double prof_ms[CPF_K_NUM]; int64_t prof_cnt[CPF_K_NUM];
   int N, Nh;                 // Nh = stored kz bins: N/2+1, or N/2 on the power-of-two path
   bool fast_pow2;            // spectral_pow2.cu handles this grid
+  bool cg_fuse_x;            // CG: solution update x += alpha p fused into the next forward z pass (k_fz MODE 3)
   int iz_lpc;                // grid lines per CTA of k_iz_pipe
-  int iz_pipe;               // inverse z pass: 0 k_iz, 1 / 2 software-pipelined k_iz_pipe with two / one spectrum buffers
+  int iz_pipe;               // inverse z pass: 1 software-pipelined k_iz_pipe (default), 0 k_iz (CPFFT_IZ_PIPE=0)
   int nxloc, x0;             // local slab
   int64_t n3;                // local voxels
   int H;                     // history comps
@@ -102,7 +103,8 @@ int cpf_apply_G(cpfft_handle* h, const double* src, double* dst, bool flgK, doub
 bool cpf_pow2_supported(int N);
 int cpf_pow2_init(cpfft_handle* h);
 int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK, double scale_out);
-int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts);
+int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts,
+                      double* x, double rr_alpha, const double* pq);
 
 // reduce.cu helpers (solver.cu)
 int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out);

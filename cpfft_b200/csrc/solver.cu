@@ -112,6 +112,25 @@ __global__ void k_cg_update(double* x, double* r, const double* p, const double*
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
+// fused-x variant of the CG update (k_fz MODE 3 applies x += a p in the next operator
+// application): r -= a q ; partial of r.r
+__global__ void k_cg_update_r(double* r, const double* q, double rr, const double* pq, int64_t n, double* partials) {
+  const double a = rr / *pq;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double rv = r[i] - a * q[i];
+    r[i] = rv;
+    s += rv * rv;
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// the solution update left pending when the CG loop stops: x += (rr / *pq) p
+__global__ void k_cg_flush_x(double* x, const double* p, double rr, const double* pq, int64_t n) {
+  const double a = rr / *pq;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] += a * p[i];
+}
 __global__ void k_sum_comp_partial(const double* x, int64_t n3, double* partials) {  // blockIdx.y = component
   double s = 0.0;
   const double* xc = x + blockIdx.y * n3;
@@ -504,6 +523,7 @@ static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int*
   CPF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
   double rr_old = 0.0, resnorm = n2b;
   int it = 0;
+  const bool fuse_x = h->fast_pow2 && h->cg_fuse_x;
   for (;;) {
     resnorm = sqrt(rr);
     if (resnorm <= tolb || resnorm <= tol) break;
@@ -513,7 +533,10 @@ static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int*
       // p <- r + beta p and the partial sums of p.q are fused into the z passes of the operator
       if (it == 0) CPF_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
       int nparts = 0;
-      rc = cpf_cg_apply_pow2(h, p, q, r, (it == 0) ? 0.0 : rr / rr_old, it > 0, &nparts); if (rc) return rc;
+      // fused-x: the solution update of iteration it-1, x += (rr_old / pq) p, is applied by this
+      // application's forward z pass (pq_dev still holds p.q of iteration it-1 at that point)
+      rc = cpf_cg_apply_pow2(h, p, q, r, (it == 0) ? 0.0 : rr / rr_old, it > 0, &nparts,
+                             (fuse_x && it > 0) ? x : nullptr, rr_old, pq_dev); if (rc) return rc;
       const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
       k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, nparts, pq_dev);
       cpf_prof_end(h, tk);
@@ -534,13 +557,19 @@ static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int*
     }
     if (h->cfg.world > 1) CPF_NCCL(g_nccl.AllReduce(pq_dev, pq_dev, 1, 8, 0, h->nccl_comm, h->stream));
     const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
-    k_cg_update<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(x, r, p, q, rr, pq_dev, n, h->d_partials);
+    if (fuse_x) k_cg_update_r<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(r, q, rr, pq_dev, n, h->d_partials);
+    else k_cg_update<<<h->nblocks_red, VEC_THREADS, 0, h->stream>>>(x, r, p, q, rr, pq_dev, n, h->d_partials);
     k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, h->nblocks_red, h->d_scalars);
     cpf_prof_end(h, tk);
     h->launches += 2;
     rr_old = rr;
     rc = fetch_scalars(h, 1, &rr); if (rc) return rc;
     ++it;
+  }
+  if (fuse_x && it > 0) {   // the update of the last iteration is still pending
+    const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
+    k_cg_flush_x<<<vec_grid(n), VEC_THREADS, 0, h->stream>>>(x, p, rr_old, h->d_scalars + 8, n); h->launches++;
+    cpf_prof_end(h, tk);
   }
   if (iters) *iters = it;
   if (relres) *relres = resnorm / n2b;

@@ -247,9 +247,11 @@ static int pick_tz(int N, int lines_per_tz, int Nh) {
 int cpf_spectral_init(cpfft_handle* h) {
   const int N = h->N;
   h->fast_pow2 = cpf_pow2_supported(N) && (getenv("CPFFT_GENERIC_FFT") == nullptr);
-  {  // development switch for the A/B measurement of the two inverse z passes (same results)
+  {  // development switches for A/B measurements; every setting gives bit-identical results
     const char* e = getenv("CPFFT_IZ_PIPE");
-    h->iz_pipe = e ? (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0)) : 0;
+    h->iz_pipe = e ? (e[0] != '0') : 1;
+    const char* fx = getenv("CPFFT_CG_FUSE_X");
+    h->cg_fuse_x = fx ? (fx[0] != '0') : true;
     const char* l = getenv("CPFFT_IZ_LPC");
     h->iz_lpc = l ? atoi(l) : 8;
     if (h->iz_lpc < 1) h->iz_lpc = 1;

@@ -141,10 +141,15 @@ __device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst loa
 
 // MODE 0: transform src.  MODE 1: transform K4 : src (G_K_dF with flgK).  MODE 2: the CG
 // direction update p <- r + beta p (FFT_nr3.f:290, MKL dcg) fused in front of MODE 1: src is p
-// (read and written), rvec is the residual.
+// (read and written), rvec is the residual.  MODE 3: MODE 2 plus the solution update of the
+// PREVIOUS iteration, x += alpha p_old with alpha = rr_alpha / *pq (the same expression and
+// operands k_cg_update uses), done while p_old is in registers anyway: the separate vector
+// pass then only updates the residual (one read of p and one read + write of x less per
+// iteration on balance: 72 B / voxel).
 template <int N, int MODE>
 __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
-                                          cplx* __restrict__ spec, const double* __restrict__ rvec, double beta) {
+                                          cplx* __restrict__ spec, const double* __restrict__ rvec, double beta,
+                                          double* __restrict__ xvec, double rr_alpha, const double* __restrict__ pq) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H, HB = Z::HB;
   extern __shared__ cplx sm[];
@@ -160,10 +165,17 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_fz(Pow2Args g
     double2 f[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) f[c] = *reinterpret_cast<const double2*>(src + c * n3 + e0);
-    if (MODE == 2) {
+    if (MODE >= 2) {
+      double alpha = 0.0;
+      if (MODE == 3) alpha = rr_alpha / *pq;
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         const double2 r = *reinterpret_cast<const double2*>(rvec + c * n3 + e0);
+        if (MODE == 3) {
+          double2 xv = *reinterpret_cast<const double2*>(xvec + c * n3 + e0);
+          xv.x += alpha * f[c].x; xv.y += alpha * f[c].y;
+          *reinterpret_cast<double2*>(xvec + c * n3 + e0) = xv;
+        }
         f[c] = make_double2(r.x + beta * f[c].x, r.y + beta * f[c].y);
         *reinterpret_cast<double2*>(src + c * n3 + e0) = f[c];
       }
@@ -281,54 +293,44 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g
 // Software-pipelined inverse z pass.  k_iz is latency bound (0.42 of the HBM peak at 256^3): a
 // CTA loads its 18 KB of spectrum, waits, transforms, stores, and with 4-5 CTAs per SM there
 // are stretches where nothing is in flight.  Here a CTA walks `lpc` consecutive grid lines and
-// prefetches the half-spectrum rows of the next line with cp.async (16-byte LDGSTS, no
-// registers) while the current line is transformed and stored; the CG direction values of the
-// DOT variant are loaded into registers before the transform instead of after it.
-//   DB = true : two B buffers, line i+1 is requested before line i is touched (longest
-//               overlap, 1.45x the shared memory, one CTA per SM fewer);
-//   DB = false: one B buffer, line i+1 is requested as soon as the first butterfly stage has
-//               moved line i from B to A (shared memory and residency of k_iz).
-// Arithmetic, summation order and the per-line partial sums are those of k_iz, so results are
-// bit-identical.
+// requests the half-spectrum rows of the next line with cp.async (16-byte LDGSTS, no
+// registers) as soon as the first butterfly stage has moved the current line from B to A, so
+// the loads fly during the remaining stages, the stores and the dot product; the CG direction
+// values of the DOT variant are loaded into registers before the transform instead of after
+// it.  Shared memory and residency are those of k_iz.  Arithmetic, summation order and the
+// per-line partial sums are those of k_iz too, so results are bit-identical
+// (tests/test_gpu_spectral.py::test_inverse_z_pass_variants_are_bit_identical).
+// Measured at 256^3 (tools/ab_iz.py, profiles/r01g_ab_iz_256.json): 0.724 -> 0.539 ms without
+// and 0.831 -> 0.661 ms with the fused dot product; a variant with two B buffers (next line
+// requested before the current one is touched, one CTA per SM fewer) measured 0.578 / 0.652 ms
+// and was dropped; 4, 8 or 16 lines per CTA make no difference.
 #include <cuda_pipeline.h>
-template <int N, bool DB> struct ZSmemPipe {
-  static constexpr int H = N / 2;
-  static constexpr int HB = ZSmem<N>::HB;
-  static constexpr size_t bytes = sizeof(cplx) * (9 * H + (DB ? 2 : 1) * 9 * HB + N);
-};
-template <int N, bool DB> struct ZOccPipe {   // resident CTAs the kernel is compiled for
-  static constexpr int BYSMEM = (int)((200 * 1024) / ZSmemPipe<N, DB>::bytes);
-  static constexpr int WANT = DB ? (384 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT : ZOcc<N>::MINB;
-  static constexpr int MINB = BYSMEM < 1 ? 1 : (WANT < BYSMEM ? WANT : BYSMEM);
-};
-template <int N, bool DOT, bool DB>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOccPipe<N, DB>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+template <int N, bool DOT>
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                                                               const double* __restrict__ pvec, double* __restrict__ partials, int64_t nlines, int lpc) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H, HB = Z::HB;
   extern __shared__ cplx sm[];
   cplx* A = sm;
-  cplx* Bb = sm + 9 * H;             // one or two buffers of 9 * HB
-  cplx* tw = Bb + (DB ? 2 : 1) * 9 * HB;
+  cplx* B = sm + 9 * H;
+  cplx* tw = B + 9 * HB;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   const int64_t nxN = (int64_t)g.nx * N;
   const int64_t L0 = (int64_t)blockIdx.x * lpc;          // lpc consecutive grid lines per CTA
   const int nl = (int)((nlines - L0) < lpc ? (nlines - L0) : lpc);
-  auto prefetch = [&](int64_t L, cplx* B) {
+  auto prefetch = [&](int64_t L) {
     for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
       const int c = idx / H, k = idx - c * H;
       __pipeline_memcpy_async(B + c * HB + k, spec + ((int64_t)c * nxN + L) * H + k, sizeof(cplx));
     }
     __pipeline_commit();
   };
-  prefetch(L0, Bb);
+  prefetch(L0);
   const int t = threadIdx.x;
   constexpr int NP = H / 2 + 1;
   for (int il = 0; il < nl; ++il) {
     const int64_t L = L0 + il;
-    cplx* B = DB ? Bb + (il & 1) * 9 * HB : Bb;
-    if (DB && il + 1 < nl) { prefetch(L + 1, Bb + ((il + 1) & 1) * 9 * HB); __pipeline_wait_prior(1); }
-    else __pipeline_wait_prior(0);
+    __pipeline_wait_prior(0);
     __syncthreads();                                    // line L has landed for every thread (and tw on the first trip)
     const int64_t e0 = L * N + 2 * t;
     double2 pv[9];
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOccPipe<N, DB>::MINB) k_iz_pi
     }
     __syncthreads();
     z_fft_inv<H>(A, tw, [&](int c, int p) { return B[c * HB + fft_natural<H>(p)]; },
-                 [&] { if (!DB && il + 1 < nl) prefetch(L + 1, Bb); });
+                 [&] { if (il + 1 < nl) prefetch(L + 1); });
     double acc = 0.0;
     if (t < H) {
 #pragma unroll
@@ -642,7 +644,8 @@ int cpf_exchange_bwd(cpfft_handle* h);
 
 // cg != nullptr: the operator application of one CG iteration, q = G K4 p, with the direction
 // update (update_p) and the p.q partial sums fused into the z passes.
-struct CgFuse { const double* r; double beta; bool update_p; int nparts; };
+// x != nullptr: also the pending solution update x += (rr_alpha / *pq) p_old (k_fz MODE 3).
+struct CgFuse { const double* r; double beta; bool update_p; int nparts; double* x; double rr_alpha; const double* pq; };
 
 template <int N>
 static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, double scale_out, const CgFuse* cg) {
@@ -656,9 +659,10 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
   const unsigned zgrid = (unsigned)(nx * N);
   int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
-  if (cg && cg->update_p) k_fz<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta);
-  else if (flgK) k_fz<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0);
-  else k_fz<N, 0><<<zgrid, ZT, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0);
+  if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
+  else if (cg && cg->update_p) k_fz<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
+  else if (flgK) k_fz<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+  else k_fz<N, 0><<<zgrid, ZT, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
   cpf_prof_end(h, tk);
   constexpr int Rm12 = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
   constexpr int RminY = P::R3 > 1 ? (Rm12 < P::R3 ? Rm12 : P::R3) : Rm12;
@@ -713,16 +717,8 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   if (h->iz_pipe) {
     const int lpc = h->iz_lpc;
     const unsigned pgrid = (zgrid + lpc - 1) / lpc;
-    if (cg) const_cast<CgFuse*>(cg)->nparts = (int)zgrid;
-    if (h->iz_pipe == 1) {
-      const size_t sm_p = ZSmemPipe<N, true>::bytes;
-      if (cg) k_iz_pipe<N, true, true><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
-      else k_iz_pipe<N, false, true><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
-    } else {
-      const size_t sm_p = ZSmemPipe<N, false>::bytes;
-      if (cg) k_iz_pipe<N, true, false><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
-      else k_iz_pipe<N, false, false><<<pgrid, ZT, sm_p, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
-    }
+    if (cg) { k_iz_pipe<N, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
+    else k_iz_pipe<N, false><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
   } else if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
   else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
   cpf_prof_end(h, tk);
@@ -742,12 +738,11 @@ static int init_pow2(cpfft_handle* h) {
   CPF_SMEM_ATTR((k_fz<N, 0>), sm_z);
   CPF_SMEM_ATTR((k_fz<N, 1>), sm_z);
   CPF_SMEM_ATTR((k_fz<N, 2>), sm_z);
+  CPF_SMEM_ATTR((k_fz<N, 3>), sm_z);
   CPF_SMEM_ATTR((k_iz<N, true>), sm_z);
   CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
-  CPF_SMEM_ATTR((k_iz_pipe<N, true, true>), (ZSmemPipe<N, true>::bytes));
-  CPF_SMEM_ATTR((k_iz_pipe<N, false, true>), (ZSmemPipe<N, true>::bytes));
-  CPF_SMEM_ATTR((k_iz_pipe<N, true, false>), (ZSmemPipe<N, false>::bytes));
-  CPF_SMEM_ATTR((k_iz_pipe<N, false, false>), (ZSmemPipe<N, false>::bytes));
+  CPF_SMEM_ATTR((k_iz_pipe<N, true>), sm_z);
+  CPF_SMEM_ATTR((k_iz_pipe<N, false>), sm_z);
   CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
   CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
   CPF_SMEM_ATTR((k_fyi<N>), sm_y);
@@ -805,8 +800,10 @@ int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK,
 // One CG operator application q = G K4 p with fused direction update and dot product:
 //   update_p: p <- r + beta p before the product;  on return d_partials[0 .. nparts) hold the
 //   per-CTA partial sums of p.q (nparts returned).
-int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts) {
-  CgFuse cg{r, beta, update_p, 0};
+//   x != nullptr (with update_p): the pending solution update x += (rr_alpha / *pq) p_old rides along.
+int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts,
+                      double* x, double rr_alpha, const double* pq) {
+  CgFuse cg{r, beta, update_p, 0, x, rr_alpha, pq};
   *nparts = h->nxloc * h->N;   // upper bound; apply_pow2 reports the exact count of z-pass CTAs
   const int rc = dispatch_pow2(h, [&](auto tag) { return call_apply(tag, h, p, q, true, 1.0, &cg); });
   *nparts = cg.nparts;

@@ -155,20 +155,22 @@ def test_polycrystal_stress_bc_matches_oracle(libs):
 
 
 @pytest.mark.parametrize("N", [16, 32, 40, 64, 80, 128])
-def test_inverse_z_pass_variants_are_bit_identical(libs, N, monkeypatch):
-    """k_iz and the two software-pipelined k_iz_pipe variants (CPFFT_IZ_PIPE = 0 / 1 / 2, read when
-    the handle is created) do the same arithmetic in the same order: G_K_dF and a CG solve
-    (p.Ap partial sums fused into the pass) must agree bit for bit."""
+def test_kernel_variants_are_bit_identical(libs, N, monkeypatch):
+    """The software-pipelined inverse z pass (k_iz_pipe, default) against k_iz (CPFFT_IZ_PIPE=0),
+    and the CG solution update fused into the next forward z pass (k_fz MODE 3, default) against the
+    separate vector pass (CPFFT_CG_FUSE_X=0): same arithmetic in the same order, so G_K_dF and a CG
+    solve must agree bit for bit.  The switches are read when the handle is created."""
     from test_oracle_spectral import _toy_problem
     Solver, _ = libs
     p = _toy_problem(N)
     rng = np.random.default_rng(N)
     F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
-    F += 0.02 * rng.standard_normal((9, p.N3))
+    F += 0.002 * rng.standard_normal((9, p.N3))        # elastic, heterogeneous: K4 stays positive definite
     x = rng.standard_normal((9, p.N3))
     res = []
-    for mode in ("0", "1", "2"):
-        monkeypatch.setenv("CPFFT_IZ_PIPE", mode)
+    for pipe, fuse in (("0", "0"), ("1", "0"), ("0", "1"), ("1", "1")):
+        monkeypatch.setenv("CPFFT_IZ_PIPE", pipe)
+        monkeypatch.setenv("CPFFT_CG_FUSE_X", fuse)
         s = Solver(p)
         s.upload("FN1", F)
         s.drive_eps_sig(1, 1)
@@ -178,6 +180,7 @@ def test_inverse_z_pass_variants_are_bit_identical(libs, N, monkeypatch):
         it, rr = s.fftPcg("B", "DFM", 1e-8)
         res.append((g, s.download("DFM"), it, rr))
         del s
+    assert 3 < res[0][2] < 200
     for g, sol, it, rr in res[1:]:
         assert np.array_equal(g, res[0][0])
         assert it == res[0][2] and rr == res[0][3]

@@ -1,5 +1,6 @@
-"""Development helper: A/B timing of the inverse z pass variants (CPFFT_IZ_PIPE = 0 k_iz, 1 / 2
-k_iz_pipe with two / one spectrum buffers) inside G_K_dF and inside a CG solve, one process, one
+"""Development helper: A/B timing of the kernel variants behind the development switches
+(CPFFT_IZ_PIPE = 0 k_iz / 1 k_iz_pipe; CPFFT_CG_FUSE_X = 0 separate CG update pass / 1 solution
+update fused into the next forward z pass) inside G_K_dF and inside a CG solve, one process, one
 grid.  CUDA events on the launching stream (the library's kernel-class profiler).
     python tools/ab_iz.py [N=256] [repeats=20]"""
 import json
@@ -19,8 +20,9 @@ p = _toy_problem(N)
 rng = np.random.default_rng(0)
 x = rng.standard_normal((9, p.N3))
 out = {"grid": N, "repeats": REP, "modes": {}}
-for mode, lpc in (("0", 8), ("1", 8), ("2", 8), ("1", 4), ("2", 4), ("1", 16), ("2", 16), ("0", 8)):   # baseline first and last: drift check
-    os.environ["CPFFT_IZ_PIPE"] = mode
+for mode, lpc in (("00", 8), ("10", 8), ("01", 8), ("11", 8), ("00", 8)):   # (iz_pipe, cg_fuse_x); baseline first and last: drift check
+    os.environ["CPFFT_IZ_PIPE"] = mode[0]
+    os.environ["CPFFT_CG_FUSE_X"] = mode[1]
     os.environ["CPFFT_IZ_LPC"] = str(lpc)
     s = Solver(p)
     s.drive_eps_sig(1, 0)
@@ -39,7 +41,8 @@ for mode, lpc in (("0", 8), ("1", 8), ("2", 8), ("1", 4), ("2", 4), ("1", 16), (
     ent["cg_ms"] = {k: round(v[0] / max(v[1], 1), 4) for k, v in t.items() if v[1]}
     ent["cg_iters"] = it
     ent["checksum"] = chk
-    key = f"iz_pipe={mode} lpc={lpc}" + ("" if f"iz_pipe={mode} lpc={lpc}" not in out["modes"] else " (again)")
+    key = f"iz_pipe={mode[0]} cg_fuse_x={mode[1]}" + ("" if f"iz_pipe={mode[0]} cg_fuse_x={mode[1]}" not in out["modes"] else " (again)")
+    ent["cg_ms_per_iteration"] = round(sum(v[0] for v in t.values()) / max(it, 1), 4)
     out["modes"][key] = ent
     print(key, json.dumps(ent), flush=True)
     del s
