@@ -150,16 +150,19 @@ def ncu_profile_data():
         return None
 
 
-def algorithmic_bytes_per_voxel(cls, N):
-    """SURVEY.md 8d per-unit figures (FP64, half spectrum, Ghat and phases recomputed)."""
+def algorithmic_bytes_per_voxel(cls, N, cg_frac=0.0, cg_fused_frac=0.0):
+    """SURVEY.md 8d per-unit figures (FP64, half spectrum, Ghat and phases recomputed), plus the
+    minimum traffic of the CG vector work that is fused into the z passes:
+      forward z pass of CG iterations 2.. of a solve (share cg_fused_frac of its launches):
+          p <- r + beta p : r read 72, p write 72;   x += alpha p : x read + write 144   (p is read anyway)
+      inverse z pass inside CG (share cg_frac): p.Ap partial sums: p read 72 (Ap is in registers)."""
     half = 16.0 * (N // 2 + 1) / N          # complex half-spectrum bytes per voxel-component
     return {
-        # K4 + p in, 9 spectrum lines out; inside CG the kernel also reads r and writes p (+144)
-        "k_fwd_z_K4": (81 + 9) * 8 + 9 * half,
+        "k_fwd_z_K4": (81 + 9) * 8 + 9 * half + 288.0 * cg_fused_frac,
         "k_fwd_z": 9 * 8 + 9 * half,
         "k_fft_y": 2 * 9 * half,
         "k_x_green": 2 * 9 * half,
-        "k_inv_z": 9 * half + 9 * 8,
+        "k_inv_z": 9 * half + 9 * 8 + 72.0 * cg_frac,
         "k_pk1_tangent": (18 + 6 + 36) * 8 + (9 + 81) * 8,
         "k_update_mm10": 8.0 * (18 + 9 + 6 + 30) + 8.0 * (9 + 6 + 9 + 36 + 36 + 80),
         "k_update_mm01": 8.0 * (18 + 11 + 9 + 6) + 8.0 * (9 + 6 + 9 + 11 + 36),
@@ -229,7 +232,7 @@ def main():
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    applies = sweeps = cgits = nfail = nfail_final = 0
+    applies = sweeps = cgits = nfail = nfail_final = nsolves = 0
     t_pcg = t_sig = 0.0
     nr_hist = []
     for _ in range(K):
@@ -238,6 +241,7 @@ def main():
         nfail += int(r["counters"][3]); nfail_final += int(r["counters"][4])
         t_pcg += float(r["buckets"][0]); t_sig += float(r["buckets"][1])
         nr_hist.append(int(r["nr_iters"][0]))
+        nsolves += sum(len(row) for row in r["cg_iters"])
     ev1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -292,7 +296,10 @@ def main():
     for name, (kms, cnt) in table.items():
         if cnt == 0:
             continue
-        b = algorithmic_bytes_per_voxel(name, N)
+        # share of the launches of the z passes that carry fused CG work (counted, not assumed)
+        cg_frac = min(1.0, cgits / cnt) if name == "k_inv_z" else 0.0
+        cg_fused = min(1.0, max(0, cgits - nsolves) / cnt) if name == "k_fwd_z_K4" else 0.0
+        b = algorithmic_bytes_per_voxel(name, N, cg_frac, cg_fused)
         ent = {"ms_total": kms, "launches": cnt, "share": kms / tot_ms, "ms_per_launch": kms / cnt}
         if b is not None:
             gbs = b * (s.n3) / (kms / cnt * 1e-3) / 1e9
@@ -335,7 +342,7 @@ def main():
                    "grid": N, "voxels": int(nvox), "voxels_per_gpu": int(s.n3), "parallelism": f"x-slabs x{world}",
                    "l2": "working set (>= 1.2 GB per field) far exceeds the 126 MB L2; no flush needed",
                    "step": "one FFT_nr3 load step", "newton_iters_per_step": nr_hist,
-                   "G_K_dF_applies": applies, "drive_eps_sig_sweeps": sweeps, "cg_iterations": cgits,
+                   "G_K_dF_applies": applies, "drive_eps_sig_sweeps": sweeps, "cg_iterations": cgits, "cg_solves": nsolves,
                    "newton_normalised_voxel_updates_per_s": nvox * sweeps / secs,
                    # VG/s = voxels x G_K_dF applications / bucket 1 (pcg), VU/s = voxels x
                    # drive_eps_sig sweeps / bucket 2 (sig-eps), the reference's own thyme() buckets

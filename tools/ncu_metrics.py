@@ -36,18 +36,22 @@ WANT = [
 
 
 def load(path):
+    """one (name, grid, block, metrics) tuple per kernel of the report"""
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-    name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
-    grid = d.get("Grid Size", ("", ""))[0]; block = d.get("Block Size", ("", ""))[0]
-    return name, grid, block, d
+    hdr, units = rows[0], rows[1]
+    res = []
+    for vals in rows[2:]:
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
+        grid = d.get("Grid Size", ("", ""))[0]; block = d.get("Block Size", ("", ""))[0]
+        res.append((name, grid, block, d))
+    return res
 
 
 def main(paths):
-    reps = [load(p) for p in paths]
-    print("ncu --set full --clock-control none, one launch per kernel inside `bench.py --grid 256 --steps 1 --warmup 1`")
+    reps = [r for p in paths for r in load(p)]
+    print("ncu --set full --clock-control none, one launch per kernel (command: profiles/README.md)")
     print()
     print("| metric | " + " | ".join(r[0] for r in reps) + " |")
     print("|---|" + "---:|" * len(reps))
