@@ -139,3 +139,91 @@ def test_mm10_local_failure_points(libs):
     assert np.array_equal(k.local_iters, o.local_iters)
     assert np.array_equal(k.local_iters[:nb], d["liters"])
     _compare_state(k, o)
+
+
+def _variant_problem(kind):
+    """Edge-case variants of the fcc / bcc48 Voce crystal and of the grid make-up."""
+    import copy
+    from cpfft_b200.polycrystal import polycrystal
+    from cpfft_b200.problem import Material
+    p = polycrystal(4, ngrains=9)
+    c = p.crystals[0]
+    if kind == "cubic_elasticity":           # elastic_type 2: mu independent of e, nu (mod_crystals.f:1840-1860)
+        c.elastic_type = 2; c.mu = 60000.0
+    elif kind == "voce_m_2":                 # |h|^m with m != 1: the pow path of mm10_h_voche
+        c.voche_m = 2.0
+    elif kind == "rate_exponent_7p5":        # non-integer harden_n: pow instead of repeated squaring
+        c.harden_n = 7.5
+    elif kind == "diffusion":                # iD_v != 0: rs*dt*iD_v slip term (mm10_b.f:1805-1835)
+        c.iD_v = 2.0e-7
+    elif kind == "alter_mode":               # dg = gamma_bar * dt (mm10_a.f:2073)
+        c.alter_mode = 1; c.eps_dot_0_y = 4.0e-5; c.harden_n = 5.0; p.tstep = 10.0
+    elif kind == "bcc48":
+        c.slip_type = 8
+    elif kind == "mixed_materials":          # mm01 and mm10 voxels in one grid (blocks break at material changes)
+        p.materials.append(Material(name="iso", type=1, e=70000.0, nu=0.33, beta=0.5, tan_e=2000.0, yld_pt=150.0))
+        p.matlist = p.matlist.copy(); p.matlist[::3] = 2
+    elif kind == "two_crystal_types":        # two library crystals, two cp materials
+        c2 = copy.copy(c); c2.tau_y = 60.0; c2.theta_0 = 300.0; c2.e = 120000.0; c2.mu = 120000.0 / 2.6
+        p.crystals.append(c2)
+        p.materials.append(Material(name="soft", type=10, crystal=2))
+        p.matlist = p.matlist.copy(); p.matlist[1::2] = 2
+    else:
+        raise KeyError(kind)
+    return p
+
+
+@pytest.mark.parametrize("kind", ["cubic_elasticity", "voce_m_2", "rate_exponent_7p5", "diffusion", "alter_mode",
+                                  "bcc48", "mixed_materials", "two_crystal_types"])
+def test_crystal_and_grid_variants(libs, kind):
+    """three load steps (0.3 % strain each, well into plastic flow) with two sweeps per step"""
+    HostKernels, Oracle = libs
+    p = _variant_problem(kind)
+    k, o = HostKernels(p), Oracle(p)
+    assert k.H == o.H
+    rng = np.random.default_rng(11)
+    G = rng.standard_normal((9, p.N3))
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.45; bar[1] = 0.3
+    I = np.zeros((9, p.N3)); I[[0, 4, 8]] = 1.0
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    total = 0
+    for step in range(1, 4):
+        for it, frac in ((0, 0.8), (1, 1.0)):
+            F = I + 0.003 * (step - 1 + frac) * (bar + 0.25 * G)
+            k.Fn1[:] = F; o.Fn1[:] = F
+            assert k.drive_eps_sig(step, it) == o.drive_eps_sig(step, it)
+            assert np.array_equal(k.local_iters, o.local_iters)
+            assert np.array_equal(k.fail_flags, np.ctypeslib.as_array(o.L.orc_fail_flags(o.h), shape=(o.N3,)))
+            errs = {"Pn1": relerr(k.Pn1, o.Pn1), "K4": relerr(k.K4, o.K4), "urcs": relerr(k.urcs_n1.T, o.urcs_n1)}
+            assert max(errs.values()) <= TOL_SMALL_STRAIN, (kind, step, it, errs)
+            total += int(o.local_iters.sum())
+        k.Fn[:] = k.Fn1; o.Fn[:] = o.Fn1
+        k.update(); o.update()
+    assert relerr(k.hist_n.T[:, :o.H], o.hist_n) <= 50 * TOL_SMALL_STRAIN     # u(12..14) diagnostics amplify by n
+    assert total > 0
+
+
+def test_large_increment_triggers_substepping(libs):
+    """a 3 % strain increment in one sweep: mm10_solve_strup halves the step (mm10_a.f:2759-2843);
+    iteration counts (which include the failed attempts) and results must agree"""
+    from cpfft_b200.polycrystal import polycrystal
+    HostKernels, Oracle = libs
+    p = polycrystal(4, ngrains=9)
+    k, o = HostKernels(p), Oracle(p)
+    rng = np.random.default_rng(2)
+    I = np.zeros((9, p.N3)); I[[0, 4, 8]] = 1.0
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.5; bar[5] = 0.4
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    F1 = I + 0.004 * (bar + 0.2 * rng.standard_normal((9, p.N3)))
+    for F, step in ((F1, 1), (I + 0.034 * (bar + 0.2 * rng.standard_normal((9, p.N3))), 2)):
+        for it in (0, 1):
+            k.Fn1[:] = F; o.Fn1[:] = F
+            nf_k, nf_o = k.drive_eps_sig(step, it), o.drive_eps_sig(step, it)
+            assert nf_k == nf_o
+            assert np.array_equal(k.local_iters, o.local_iters)
+        k.Fn[:] = F; o.Fn[:] = F
+        k.update(); o.update()
+    # more update iterations than a plain solve needs: sub-steps were taken somewhere
+    assert o.local_iters[:, 1].max() > 12
+    ok = np.ctypeslib.as_array(o.L.orc_fail_flags(o.h), shape=(o.N3,)) == 0
+    assert relerr(k.urcs_n.T[ok], o.urcs_n[ok]) <= TOL_SMALL_STRAIN
