@@ -16,7 +16,7 @@ from typing import List
 
 import numpy as np
 
-from .problem import Crystal, Material, Problem, SLIP_TYPES, ELASTIC_TYPES, COMPONENTS
+from .problem import Crystal, Material, Problem, SLIP_TYPES, ELASTIC_TYPES, COMPONENTS, HARDENING
 
 
 class DeckError(ValueError):
@@ -92,6 +92,10 @@ _CRYSTAL_NUM = {
     "tau_y": "tau_y", "tau_v": "tau_v", "voche_m": "voche_m", "voce_m": "voche_m",
     "iD_v": "iD_v", "eps_dot_0_y": "eps_dot_0_y", "gamma_bar": "eps_dot_0_y", "k_0": "k_0",
     "b": "burgers", "atol": "atol", "atol1": "atol1", "rtol": "rtol", "rtol1": "rtol1",
+    # MTS (incrystal.f:165-236)
+    "tau_a": "tau_a", "tau_hat_y": "tau_hat_y", "g_0_y": "g_0_y", "tau_hat_v": "tau_hat_v", "g_0_v": "g_0_v",
+    "p_y": "p_y", "q_y": "q_y", "p_v": "p_v", "q_v": "q_v", "boltz": "boltzman", "eps_dot_0_v": "eps_dot_0_v",
+    "mu_0": "mu_0", "D_0": "D_0", "T_0": "T_0",
 }
 
 
@@ -113,9 +117,9 @@ def _read_crystal(lines: _Lines, toks: List[str], crystals: dict):
         elif k == "elastic_type":
             c.elastic_type = ELASTIC_TYPES[pt[i + 1]]; i += 2
         elif k == "hardening":
-            if pt[i + 1] not in ("voce", "voche"):
-                raise DeckError(f"hardening {pt[i + 1]} not supported (voce only)")
-            c.h_type = 1; i += 2
+            if pt[i + 1] not in HARDENING:
+                raise DeckError(f"hardening {pt[i + 1]} not supported (voce, mts)")
+            c.h_type = HARDENING[pt[i + 1]]; i += 2
         elif k == "alter_mode":
             c.alter_mode = 1 if pt[i + 1].lower() in ("on", "true") else 0; i += 2
         elif k == "miter":

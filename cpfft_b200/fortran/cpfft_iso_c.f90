@@ -34,6 +34,9 @@ module cpfft_iso_c
      integer(c_int32_t) :: slip_type, elastic_type, h_type, alter_mode, miter, pad_
      real(c_double) :: e, nu, mu, harden_n, theta_0, tau_y, tau_v, voche_m, iD_v,   &
                        eps_dot_0_y, k_0, burgers, atol, atol1, rtol, rtol1
+     ! MTS hardening (h_type 2)
+     real(c_double) :: tau_a, tau_hat_y, g_0_y, tau_hat_v, g_0_v, p_y, q_y, p_v, q_v,   &
+                       boltzman, eps_dot_0_v, mu_0, D_0, T_0
   end type cpfft_crystal
 
   interface

@@ -11,6 +11,7 @@ from typing import List
 
 import numpy as np
 
+HARDENING = {"voce": 1, "voche": 1, "mts": 2}     # incrystal.f:305-331 (supported subset)
 SLIP_TYPES = {"fcc": 1, "bcc48": 8}           # mod_crystals.f:164-172 (supported subset)
 ELASTIC_TYPES = {"isotropic": 1, "cubic": 2}  # mod_crystals.f:173-176
 COMPONENTS = ["xx", "xy", "xz", "yx", "yy", "yz", "zx", "zy", "zz"]  # inlodcase.f:29-139
@@ -26,6 +27,11 @@ class CrystalPOD(C.Structure):
         ("voche_m", C.c_double), ("iD_v", C.c_double), ("eps_dot_0_y", C.c_double),
         ("k_0", C.c_double), ("burgers", C.c_double),
         ("atol", C.c_double), ("atol1", C.c_double), ("rtol", C.c_double), ("rtol1", C.c_double),
+        # MTS hardening (h_type 2)
+        ("tau_a", C.c_double), ("tau_hat_y", C.c_double), ("g_0_y", C.c_double), ("tau_hat_v", C.c_double),
+        ("g_0_v", C.c_double), ("p_y", C.c_double), ("q_y", C.c_double), ("p_v", C.c_double), ("q_v", C.c_double),
+        ("boltzman", C.c_double), ("eps_dot_0_v", C.c_double), ("mu_0", C.c_double), ("D_0", C.c_double),
+        ("T_0", C.c_double),
     ]
 
 
@@ -62,6 +68,21 @@ class Crystal:
     atol1: float = 1.0e-5
     rtol: float = 5.0e-5
     rtol1: float = 1.0e-5
+    # MTS hardening, h_type 2 (defaults mod_crystals.f:256-275)
+    tau_a: float = 0.0
+    tau_hat_y: float = -1.0
+    g_0_y: float = -1.0
+    tau_hat_v: float = -1.0
+    g_0_v: float = -1.0
+    p_y: float = 0.5
+    q_y: float = 2.0
+    p_v: float = 0.5
+    q_v: float = 2.0
+    boltzman: float = 1.3806e-20
+    eps_dot_0_v: float = 1.0e10
+    mu_0: float = 69000.0 / 2.0 / 1.33
+    D_0: float = 0.0
+    T_0: float = 294.0
 
     def pod(self) -> CrystalPOD:
         p = CrystalPOD()

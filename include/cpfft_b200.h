@@ -46,12 +46,16 @@ enum {
 typedef struct {
   int32_t slip_type;    /* 1 fcc, 8 bcc48 (mod_crystals.f:164-172)   */
   int32_t elastic_type; /* 1 isotropic, 2 cubic (mod_crystals.f:173) */
-  int32_t h_type;       /* 1 voce                                    */
+  int32_t h_type;       /* 1 voce, 2 mts (incrystal.f:305-331)       */
   int32_t alter_mode;   /* mm10_a.f:2073                             */
   int32_t miter;        /* mod_crystals.f:398                        */
   int32_t pad_;
   double e, nu, mu, harden_n, theta_0, tau_y, tau_v, voche_m, iD_v, eps_dot_0_y, k_0, burgers;
   double atol, atol1, rtol, rtol1;
+  /* MTS hardening, h_type 2 (mm10_a.f:2109-2175, mm10_b.f:2080-2345; defaults
+     mod_crystals.f:256-275, deck keywords incrystal.f:165-236) */
+  double tau_a, tau_hat_y, g_0_y, tau_hat_v, g_0_v, p_y, q_y, p_v, q_v;
+  double boltzman, eps_dot_0_v, mu_0, D_0, T_0;
 } cpfft_crystal;
 
 /* material table entry: matprp slots of inmat.f:97-133 (REAL*4 on purpose) / :176-298 */

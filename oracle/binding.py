@@ -65,6 +65,7 @@ def _lib():
         L.orc_formG_entry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_crystal_stiffness.argtypes = [C.c_void_p, dp]
         L.orc_slip_table.argtypes = [C.c_int, ip, dp, dp]
+        L.orc_mm10_residual_jacobian.argtypes = [C.c_void_p, dp, dp, C.c_double, dp, dp, C.c_double, dp, dp]
         _LIB = L
     return _LIB
 
@@ -219,6 +220,16 @@ class Oracle:
         Cm = np.zeros(36)
         _lib().orc_crystal_stiffness(C.addressof(pod), _dp(Cm))
         return Cm.reshape(6, 6, order="F")
+
+    @staticmethod
+    def mm10_residual_jacobian(crystal, angles, D6, dt, x7, n_stress, n_tt):
+        """R(x) (7,) and J(x) (7,7) of the local Newton system of one crystal (mm10_formR / mm10_formJ)"""
+        pod = crystal.pod()
+        a = [np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (angles, D6, x7, n_stress)]
+        R, J = np.zeros(7), np.zeros(49)
+        _lib().orc_mm10_residual_jacobian(C.addressof(pod), _dp(a[0]), _dp(a[1]), float(dt), _dp(a[2]), _dp(a[3]),
+                                          float(n_tt), _dp(R), _dp(J))
+        return R, J.reshape(7, 7)
 
     @staticmethod
     def slip_table(slip_type):

@@ -10,7 +10,8 @@
  *   rtcmp1 .. getrm1                     (src/polar.f)
  *   cep2A                                (src/cep2A.f)
  *   mm01 + cnst1                         (src/mm01.f)
- *   mm10 (Voce hardening, NR solver)     (src/mm10_a.f, src/mm10_b.f)
+ *   mm10 (Voce and MTS hardening, NR solver, one or several crystals per point)
+ *                                        (src/mm10_a.f, src/mm10_b.f)
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product
@@ -38,7 +39,7 @@ extern "C" {
 typedef struct {
   int32_t slip_type;    /* 1 = fcc (12), 8 = bcc48 (48)  (mod_crystals.f:164-172) */
   int32_t elastic_type; /* 1 = isotropic, 2 = cubic        (mod_crystals.f:173-176) */
-  int32_t h_type;       /* 1 = voce (only one supported)                          */
+  int32_t h_type;       /* 1 = voce, 2 = mts                                      */
   int32_t alter_mode;   /* mm10_a.f:2073                                          */
   int32_t miter;        /* mod_crystals.f:398                                     */
   int32_t pad_;
@@ -48,6 +49,9 @@ typedef struct {
   double eps_dot_0_y;   /* gamma_bar synonym (incrystal.f:217) */
   double k_0, burgers;
   double atol, atol1, rtol, rtol1;
+  /* MTS hardening (h_type 2; mod_crystals.f:256-275 defaults, incrystal.f:165-236 keywords) */
+  double tau_a, tau_hat_y, g_0_y, tau_hat_v, g_0_v, p_y, q_y, p_v, q_v;
+  double boltzman, eps_dot_0_v, mu_0, D_0, T_0;
 } orc_crystal;
 
 /* one material (inmat.f:97-133 for bilinear, :176-298 for cp) */
@@ -119,6 +123,8 @@ void orc_point_update(orc_model*, int voxel, int step, int iter, const double* F
 void orc_formG_entry(int N, int ii, int jj, int kk, double* G81);
 void orc_crystal_stiffness(const orc_crystal*, double* C36_colmajor);
 void orc_slip_table(int slip_type, int* nslip, double* b, double* n);
+void orc_mm10_residual_jacobian(const orc_crystal* c, const double* angles_deg, const double* D6, double dt,
+                                const double* x7, const double* n_stress6, double n_tau_tilde, double* R7, double* J49);
 
 #ifdef __cplusplus
 }

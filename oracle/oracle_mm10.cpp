@@ -146,9 +146,11 @@ HistLayout mm10_history_layout(int nslip, int num_hard) {  // mm10_d.f:137-331
 }
 
 // ----------------------------------------------------------------------------
-struct Props {   // crystal_props subset actually reached by the Voce / NR path
-  int nslip, alter_mode, miter;
+struct Props {   // crystal_props subset actually reached by the Voce / MTS NR path
+  int nslip, alter_mode, miter, h_type;
   double rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, eps_dot_0_y, k_0, burgers;
+  // MTS (mm10_a.f:2109-2175, mm10_b.f:2080-2345)
+  double tau_a, tau_hat_y, G_0_y, tau_hat_v, G_0_v, p_y, q_y, p_v, q_v, boltzman, eps_dot_0_v, mu_0, D_0, T_0;
   double atol, atol1, rtol, rtol1;
   M33 g;
   double ms[ORC_MAX_SLIP][6], qs[ORC_MAX_SLIP][3], ns[ORC_MAX_SLIP][3];
@@ -161,6 +163,7 @@ struct State {   // crystal_state subset
   M66 tangent;
   double ms[ORC_MAX_SLIP][6], qs[ORC_MAX_SLIP][3], qc[ORC_MAX_SLIP][3], tau_l[ORC_MAX_SLIP];
   double dg, tinc, temp, mu_harden, work_inc, p_work_inc, p_strain_inc;
+  double tau_y, tau_v;   // MTS threshold contributions of the (sub)step
 };
 
 // setup_mm10_rknstr (drive_eps_sig.f:537-1002): per point, per call
@@ -170,6 +173,13 @@ static void setup_props(const CrystalLib& cry, const double* angles, Props& p) {
   p.rate_n = in.harden_n; p.theta_0 = in.theta_0; p.tau_y = in.tau_y; p.tau_v = in.tau_v;
   p.voche_m = in.voche_m; p.iD_v = in.iD_v; p.eps_dot_0_y = in.eps_dot_0_y; p.k_0 = in.k_0;
   p.burgers = in.burgers; p.atol = in.atol; p.atol1 = in.atol1; p.rtol = in.rtol; p.rtol1 = in.rtol1;
+  p.h_type = in.h_type;
+  p.tau_a = in.tau_a; p.tau_hat_y = in.tau_hat_y; p.G_0_y = in.g_0_y; p.tau_hat_v = in.tau_hat_v; p.G_0_v = in.g_0_v;
+  p.p_y = in.p_y; p.q_y = in.q_y; p.p_v = in.p_v; p.q_v = in.q_v; p.boltzman = in.boltzman;
+  p.eps_dot_0_v = in.eps_dot_0_v; p.mu_0 = in.mu_0; p.D_0 = in.D_0; p.T_0 = in.T_0;
+  // the diffusion slip rs dt iD_v exists in the Voce branches only (mm10_b.f:1180-1200, 1253-1270,
+  // 1325-1345, 2005-2030): with iD_v = 0 the shared code below adds exact zeros for MTS
+  if (p.h_type == 2) p.iD_v = 0.0;
   rotation_matrix_kocks_deg(angles, p.g);
   M33 trot;
   for (int i = 0; i < 3; ++i)
@@ -213,8 +223,31 @@ static void setup_np1(const M33 R, const double* D, double dt, State& s) {
     for (int j = 0; j < 3; ++j) s.R[i][j] = R[i][j];
 }
 
+// mm10_setup_mts (mm10_a.f:2109-2175).  Also fills the n-state values that are kept as flags
+// (< 0) in the history until the first plastic update: n.tau_y, n.mu_harden, n.tau_tilde.
+static void mm10_setup_mts(const Props& p, State& np1, State& n) {
+  const double init_hard = 0.1;
+  const double dgc = np1.dg / np1.tinc;
+  if (np1.temp == 0.0) np1.mu_harden = p.mu_0;
+  else np1.mu_harden = p.mu_0 - p.D_0 / (std::exp(p.T_0 / np1.temp) - 1.0);
+  if (dgc == 0.0) {
+    np1.tau_v = p.tau_hat_v;
+    np1.tau_y = p.tau_hat_y;
+  } else {
+    np1.tau_v = p.tau_hat_v * std::pow(1.0 - std::pow(p.boltzman * np1.temp / (np1.mu_harden * std::pow(p.burgers, 3.0) * p.G_0_v) *
+                                                         std::log(p.eps_dot_0_v / dgc), 1.0 / p.q_v), 1.0 / p.p_v);
+    np1.tau_y = p.tau_hat_y * std::pow(1.0 - std::pow(p.boltzman * np1.temp / (np1.mu_harden * std::pow(p.burgers, 3.0) * p.G_0_y) *
+                                                         std::log(p.eps_dot_0_y / dgc), 1.0 / p.q_y), 1.0 / p.p_y);
+  }
+  np1.u[0] = np1.tau_y;
+  if (n.u[0] < 0.0) n.tau_y = np1.tau_y; else n.tau_y = n.u[0];
+  np1.u[1] = np1.mu_harden;
+  if (n.u[1] < 0.0) n.mu_harden = np1.mu_harden; else n.mu_harden = n.u[1];
+  if (n.tau_tilde < 0.0) n.tau_tilde = p.tau_a + (np1.mu_harden / p.mu_0) * np1.tau_y + init_hard;
+}
+
 // mm10_setup + mm10_setup_voche (mm10_a.f:830-962, 2057-2075)
-static void mm10_setup(const Props& p, State& np1, const State& n) {
+static void mm10_setup(const Props& p, State& np1, State& n) {
   double t1 = np1.D[0] * np1.D[0] + np1.D[1] * np1.D[1] + np1.D[2] * np1.D[2];
   double t2 = np1.D[3] * np1.D[3] + np1.D[4] * np1.D[4] + np1.D[5] * np1.D[5];
   const double twothirds = 2.0 / 3.0;
@@ -231,8 +264,11 @@ static void mm10_setup(const Props& p, State& np1, const State& n) {
     matvec3(RW, p.qs[i], np1.qs[i]);
     matvec3(RWC, p.qs[i], np1.qc[i]);
   }
-  np1.mu_harden = p.stiffness[5][5];
-  if (p.alter_mode) np1.dg = p.eps_dot_0_y * np1.tinc;
+  if (p.h_type == 2) mm10_setup_mts(p, np1, n);
+  else {
+    np1.mu_harden = p.stiffness[5][5];
+    if (p.alter_mode) np1.dg = p.eps_dot_0_y * np1.tinc;
+  }
   // geometric hardening: curvature is identically zero (gradFeinv never filled)
   const double alpha = 1.0 / 3.0;
   double cst = p.k_0 * p.burgers * alpha * alpha * np1.mu_harden * np1.mu_harden / 2.0 / p.theta_0;
@@ -301,8 +337,19 @@ static double h_voche(const Props& p, const State& np1, const State& n, const do
   }
   return n.tau_tilde + p.theta_0 * h;
 }
+static double h_mts(const Props& p, const State& np1, const State& n, const double* stress, double tt) {
+  const double cta = (p.mu_0 / np1.mu_harden) * tt - (p.mu_0 / np1.mu_harden) * p.tau_a - np1.tau_y;   // mm10_b.f:2080-2111
+  const double ct = 1.0 - cta / np1.tau_v;
+  double h = 0.0;
+  for (int i = 0; i < p.nslip; ++i) {
+    double slipinc = mm10_slipinc(p, np1, stress, tt, i);
+    h = h + std::pow(ct + np1.tau_l[i] / cta, p.voche_m) * std::fabs(slipinc);
+  }
+  return p.tau_a * (1.0 - np1.mu_harden / n.mu_harden) + (np1.mu_harden / p.mu_0) * (np1.tau_y - n.tau_y) +
+         (np1.mu_harden / n.mu_harden) * n.tau_tilde + p.theta_0 * (np1.mu_harden / p.mu_0) * h;
+}
 static void formR2(const Props& p, State& np1, const State& n, const double* stress, double tt, double* R2) {
-  double h = h_voche(p, np1, n, stress, tt);                               // mm10_b.f:63-113
+  double h = (p.h_type == 2) ? h_mts(p, np1, n, stress, tt) : h_voche(p, np1, n, stress, tt);   // mm10_b.f:63-113
   *R2 = tt - h;
   np1.tt_rate = (h - n.tau_tilde) / np1.tinc;
 }
@@ -362,6 +409,26 @@ static void formJ(const Props& p, const State& np1, const double* x, double J[7]
     double dgam = mm10_slipinc(p, np1, stress, tt, i);
     double dgdtt = -p.rate_n / tt * dgam;
     for (int k = 0; k < 6; ++k) J[k][6] += tm[k] * dgdtt;
+  }
+  if (p.h_type == 2) {
+    // J21 = -estress_mts (mm10_b.f:2114-2147), J22 = ehard_mts (mm10_b.f:2150-2186)
+    const double cta = (p.mu_0 / np1.mu_harden) * tt - (p.mu_0 / np1.mu_harden) * p.tau_a - np1.tau_y;
+    const double ct = 1.0 - cta / np1.tau_v;
+    const double ur = np1.mu_harden / p.mu_0;
+    double et[6] = {0, 0, 0, 0, 0, 0}, etau = 0.0;
+    for (int i = 0; i < p.nslip; ++i) {
+      double rs = mm10_rs(np1, stress, i);
+      double f = std::pow(ct + np1.tau_l[i] / cta, p.voche_m) * std::pow(std::fabs(rs), p.rate_n - 2.0) * rs;
+      for (int k = 0; k < 6; ++k) et[k] = et[k] + f * np1.ms[i][k];
+      double slipinc = mm10_slipinc(p, np1, stress, tt, i);
+      etau = etau + (p.voche_m * (1.0 / np1.tau_v + np1.tau_l[i] / (cta * cta)) * std::pow(ct + np1.tau_l[i] / cta, -1.0) +
+                     ur * p.rate_n / tt) * std::pow(ct + np1.tau_l[i] / cta, p.voche_m) * std::fabs(slipinc);
+    }
+    const double fac = p.theta_0 * (np1.mu_harden / p.mu_0);
+    for (int k = 0; k < 6; ++k) J[6][k] = -(fac * et[k] * p.rate_n * np1.dg / std::pow(tt, p.rate_n));
+    etau = -p.theta_0 * etau;
+    J[6][6] = 1.0 - etau;
+    return;
   }
   // J21 = -estress (mm10_b.f:369-417, 1918-1948)
   double et[6] = {0, 0, 0, 0, 0, 0};
@@ -504,15 +571,66 @@ static bool mm10_solve(const Props& p, State& np1, const State& n, double* stres
   return fail;
 }
 
-// mm10_tangent, Voce: ed = 0, dgammadd = 0 => JA = JB = 0 (mm10_a.f:658-815)
+// mm10_ed_mts (mm10_b.f:2189-2264): derivative of the hardening function wrt the strain increment
+static void ed_mts(const Props& p, const State& np1, const double* stress, double tt, double* ed) {
+  double d_mod[6], dydd[6], dvdd[6];
+  for (int k = 0; k < 6; ++k) d_mod[k] = (k < 3) ? np1.D[k] : 0.5 * np1.D[k];
+  const double dgc = np1.dg / np1.tinc;
+  const double b3 = std::pow(p.burgers, 3.0);
+  const double lny = std::log(p.eps_dot_0_y / dgc);
+  const double ty = p.boltzman * np1.temp / (np1.mu_harden * b3 * p.G_0_y) * lny;
+  const double cy = 2.0 * p.tau_hat_y / (3.0 * np1.dg * np1.dg * p.q_y * p.p_y * lny) *
+                    std::pow(1.0 - std::pow(ty, 1.0 / p.q_y), 1.0 / p.p_y - 1.0) * std::pow(ty, 1.0 / p.q_y);
+  const double lnv = std::log(p.eps_dot_0_v / dgc);
+  const double tv = p.boltzman * np1.temp / (np1.mu_harden * b3 * p.G_0_v) * lnv;
+  const double cv = 2.0 * p.tau_hat_v / (3.0 * np1.dg * np1.dg * p.q_v * p.p_v * lnv) *
+                    std::pow(1.0 - std::pow(tv, 1.0 / p.q_v), 1.0 / p.p_v - 1.0) * std::pow(tv, 1.0 / p.q_v);
+  for (int k = 0; k < 6; ++k) { dydd[k] = cy * d_mod[k]; dvdd[k] = cv * d_mod[k]; }
+  const double mnp0 = np1.mu_harden / p.mu_0;
+  const double sc = tt / mnp0 - p.tau_a / mnp0 - np1.tau_y;
+  for (int k = 0; k < 6; ++k) ed[k] = 0.0;
+  for (int s = 0; s < p.nslip; ++s) {
+    const double slipinc = mm10_slipinc(p, np1, stress, tt, s);
+    const double base = 1.0 - sc / np1.tau_v + np1.tau_l[s] / sc;
+    const double a = p.voche_m * (1.0 / np1.tau_v + np1.tau_l[s] / (sc * sc)) * std::pow(base, p.voche_m - 1.0);
+    const double b = p.voche_m / (np1.tau_v * np1.tau_v) * sc * std::pow(base, p.voche_m - 1.0);
+    const double c = 2.0 / (3.0 * np1.dg * np1.dg) * std::pow(base, p.voche_m);
+    for (int k = 0; k < 6; ++k) ed[k] = ed[k] + (a * dydd[k] + b * dvdd[k] + c * d_mod[k]) * std::fabs(slipinc);
+  }
+  for (int k = 0; k < 6; ++k) ed[k] = p.theta_0 * mnp0 * ed[k] + mnp0 * dydd[k];
+}
+
+// mm10_tangent (mm10_a.f:658-815).  Voce: ed = 0, dgammadd = 0 => JA = JB = 0.  MTS: JA from
+// dgammadd (mm10_b.f:2316-2345), JB = J12 J22^-1 ed.
 static void mm10_tangent(const Props& p, State& np1, const double J[7][7]) {
   double JJ[36], JR[36];
+  double JA[6][6], JB[6][6];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { JA[i][j] = 0.0; JB[i][j] = 0.0; }
+  if (p.h_type == 2) {
+    double ed[6], d_mod[6];
+    ed_mts(p, np1, np1.stress, np1.tau_tilde, ed);
+    for (int k = 0; k < 6; ++k) d_mod[k] = (k < 3) ? np1.D[k] : 0.5 * np1.D[k];
+    const double alpha = 2.0 / (3.0 * np1.dg * np1.dg);
+    for (int i = 0; i < p.nslip; ++i) {
+      double symtq[6], wv[6], dgdd[6];
+      symswmat_col(np1.stress, np1.qc[i], symtq);
+      for (int k = 0; k < 6; ++k) wv[k] = 2.0 * symtq[k];                   // mm10_a_mult_type_4
+      for (int j = 0; j < 6; ++j)
+        for (int k = 0; k < 6; ++k) wv[k] = wv[k] + p.stiffness[k][j] * np1.ms[i][j];
+      const double dgam = mm10_slipinc(p, np1, np1.stress, np1.tau_tilde, i);
+      for (int k = 0; k < 6; ++k) dgdd[k] = alpha * dgam * d_mod[k];
+      for (int a = 0; a < 6; ++a)                                           // mm10_a_mult_type_5
+        for (int b = 0; b < 6; ++b) JA[a][b] += wv[a] * dgdd[b];
+    }
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) JB[a][b] = J[a][6] * (ed[b] / J[6][6]);   // J12 * (J22^-1 ed), len = 1
+  }
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 6; ++j) {
       // beta = J22^-1 J21 (DGESV len=1), JJ = J11 - J12 * beta
       double beta = J[6][j] / J[6][6];
       JJ[i * 6 + j] = J[i][j] + (-1.0) * J[i][6] * beta;
-      JR[i * 6 + j] = p.stiffness[i][j] - 0.0 - 0.0;
+      JR[i * 6 + j] = p.stiffness[i][j] - JA[i][j] - JB[i][j];
     }
   lu_solve(6, JJ, JR, 6);
   for (int i = 0; i < 6; ++i)
@@ -653,6 +771,7 @@ static int mm10_crystal(int step, int iter, const CrystalLib& cry, const double*
     for (int k = 0; k < 6; ++k) { hn[L.c_D + k] = 0.0; hn[L.c_eps + k] = 0.0; }
     for (int k = 0; k < L.len_slip; ++k) hn[L.c_slipinc + k] = 0.0;
     hn[L.c_tt] = p.tau_y + 1.0e-5;  // mm10_init_voche (mm10_a.f:2042-2055); other slots undefined there
+    if (p.h_type == 2) { hn[L.c_tt] = -1.0; hn[L.c_u] = -1.0; hn[L.c_u + 1] = -1.0; }   // mm10_init_mts: flags (mm10_a.f:2090-2106)
   }
   // mm10_copy_cc_hist (mm10_a.f:2464-2561)
   std::memset(&n, 0, sizeof(State));
@@ -662,6 +781,7 @@ static int mm10_crystal(int step, int iter, const CrystalLib& cry, const double*
   for (int k = 0; k < 3; ++k) n.euler[k] = hn[L.c_euler + k];
   n.tau_tilde = hn[L.c_tt];
   n.tt_rate = hn[L.c_ttrate];
+  for (int k = 0; k < 14; ++k) n.u[k] = hn[L.c_u + k];      // n%u(1:len2-1) (mm10_a.f:2544)
   // mm10_setup_np1
   M33 R;
   for (int j = 0; j < 3; ++j)
@@ -726,6 +846,7 @@ static int mm10_crystal(int step, int iter, const CrystalLib& cry, const double*
       for (int k = 0; k < L.len_slip; ++k) h1[L.c_slipinc + k] = 0.0;
       h1[L.c_tt] = n.tau_tilde; h1[L.c_ttrate] = 0.0;
       for (int k = 0; k < 15; ++k) h1[L.c_u + k] = 0.0;
+      if (p.h_type == 2) { h1[L.c_u] = n.u[0]; h1[L.c_u + 1] = n.u[1]; }    // MTS: tau_y / mu_harden of the n state (or their flags)
       for (int j = 0; j < 6; ++j) for (int i = 0; i < 6; ++i) out.tangent[i][j] = p.stiffness[i][j];
       return 1;
     }
@@ -833,6 +954,29 @@ int mm10_point(int step, int iter, int ncrystals, const CrystalLib* const* cryst
 }
 
 } // namespace orc
+
+// unit probe for the pinning tests: residual R(x) (7) and Jacobian J(x) (7x7 row-major) of the
+// local Newton system of one crystal (mm10_formR / mm10_formJ, mm10_b.f:1029-1051, 901-954) for a
+// strain increment D6 over dt with R = I, Rp_n = I, n state (stress, tau_tilde); the MTS n-state
+// values tau_y, mu_harden are taken from the step itself (history flags < 0)
+extern "C" void orc_mm10_residual_jacobian(const orc_crystal* c, const double* angles, const double* D6, double dt,
+                                           const double* x7, const double* n_stress6, double n_tt, double* R7, double* J49) {
+  using namespace orc;
+  CrystalLib L; L.in = *c; finalize_crystal(L);
+  static thread_local Props p; static thread_local State n, np1;
+  setup_props(L, angles, p);
+  std::memset(&n, 0, sizeof(State));
+  M33 I = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { n.R[i][j] = I[i][j]; n.Rp[i][j] = I[i][j]; }
+  for (int k = 0; k < 6; ++k) n.stress[k] = n_stress6[k];
+  n.tau_tilde = n_tt; n.u[0] = -1.0; n.u[1] = -1.0;
+  setup_np1(I, D6, dt, np1);
+  mm10_setup(p, np1, n);
+  formR(p, np1, n, x7, R7);
+  double J[7][7];
+  formJ(p, np1, x7, J);
+  for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) J49[7 * i + j] = J[i][j];
+}
 
 extern "C" void orc_crystal_stiffness(const orc_crystal* c, double* C36) {
   orc::CrystalLib L; L.in = *c; orc::finalize_crystal(L);
