@@ -70,7 +70,7 @@ def test_pod_layouts_match_header():
     import ctypes as C
     from cpfft_b200.problem import CrystalPOD, MaterialPOD
     from cpfft_b200.api import Config
-    assert C.sizeof(CrystalPOD) == 6 * 4 + 16 * 8
+    assert C.sizeof(CrystalPOD) == 6 * 4 + (16 + 14) * 8      # Voce block + 14 MTS parameters
     assert C.sizeof(MaterialPOD) == 2 * 4 + 6 * 4
     assert C.sizeof(Config) == 6 * 4 + 3 * 8
 
