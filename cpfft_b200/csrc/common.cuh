@@ -57,7 +57,8 @@ struct cpfft_handle {
   double* d_grains;          // grain table
   int ngrains;
   bool has_mm01, has_mm10;
-  bool has_mm10_single, has_taylor;   // cp materials with one crystal / with n_crystals > 1 per point
+  bool has_taylor;                    // some cp material has n_crystals > 1 per point
+  bool mm10_kern[2][3];               // [Taylor point][hardening law 1 Voce, 2 MTS]: update kernels to launch
   CpfHistLayout L;
   int32_t* d_fail; int32_t* d_liters;
   int* d_failcnt;            // {mm10 local failures since reset, failures of the last sweep}

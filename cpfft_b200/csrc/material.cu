@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
   extern __shared__ double mm10_sm[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n3) return;
-  upd_mm10_voxel<false>(a, e, mm10_sm + threadIdx.x);
+  upd_mm10_voxel<false, MM10_VOCE>(a, e, mm10_sm + threadIdx.x);
 }
 
 // polycrystalline material points (n_crystals > 1): same per-crystal integration, Taylor average
@@ -36,7 +36,21 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_tayl
   extern __shared__ double mm10_sm[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n3) return;
-  upd_mm10_voxel<true>(a, e, mm10_sm + threadIdx.x);
+  upd_mm10_voxel<true, MM10_VOCE>(a, e, mm10_sm + threadIdx.x);
+}
+
+// MTS hardening (`hardening mts`), single crystal and Taylor points: same source, other law
+__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_mts(UpdArgs a) {
+  extern __shared__ double mm10_sm[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n3) return;
+  upd_mm10_voxel<false, MM10_MTS>(a, e, mm10_sm + threadIdx.x);
+}
+__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_taylor_mts(UpdArgs a) {
+  extern __shared__ double mm10_sm[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n3) return;
+  upd_mm10_voxel<true, MM10_MTS>(a, e, mm10_sm + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, const double* Fn1, const double* urcs_n1,
@@ -56,8 +70,7 @@ int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const
   if (rc) { cpf_set_error(h, err); return rc; }
   h->has_mm01 = T.has_mm01; h->has_mm10 = T.has_mm10; h->ngrains = T.ngrains; h->L = T.L;
   h->has_taylor = T.has_taylor;
-  h->has_mm10_single = false;
-  for (const CpfMatDev& m : T.md) if (m.type == 10 && m.ncry == 1) h->has_mm10_single = true;
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) h->mm10_kern[i][j] = T.kern[i][j];
   const int H = T.H;
   // (re)allocate history fields
   for (int f : {CPFFT_HIST_N, CPFFT_HIST_N1}) {
@@ -104,19 +117,19 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
     k_update_mm01<<<grid, UPD_THREADS, 0, h->stream>>>(a); h->launches++;
     cpf_prof_end(h, tk);
   }
-  if (h->has_mm10_single) {
-    CPF_CUDA(cudaFuncSetAttribute(k_update_mm10, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS)));
-    const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
-    k_update_mm10<<<grid, UPD_THREADS, sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS, h->stream>>>(a); h->launches++;
-    cpf_prof_end(h, tk);
-  }
-  if (h->has_taylor) {
-    CPF_CUDA(cudaFuncSetAttribute(k_update_mm10_taylor, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS)));
-    const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
-    k_update_mm10_taylor<<<grid, UPD_THREADS, sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS, h->stream>>>(a); h->launches++;
-    cpf_prof_end(h, tk);
+  {
+    // one kernel per (one crystal | Taylor point) x (Voce | MTS) combination present in the model
+    typedef void (*Kern)(UpdArgs);
+    const Kern kerns[2][3] = {{nullptr, k_update_mm10, k_update_mm10_mts}, {nullptr, k_update_mm10_taylor, k_update_mm10_taylor_mts}};
+    const size_t smem = sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS;
+    for (int multi = 0; multi < 2; ++multi)
+      for (int hard = 1; hard <= 2; ++hard) {
+        if (!h->mm10_kern[multi][hard]) continue;
+        CPF_CUDA(cudaFuncSetAttribute(kerns[multi][hard], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
+        kerns[multi][hard]<<<grid, UPD_THREADS, smem, h->stream>>>(a); h->launches++;
+        cpf_prof_end(h, tk);
+      }
   }
   const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);
   k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);

@@ -24,6 +24,7 @@ struct CpfMatTables {
   std::vector<int32_t> gcry;         // per grain-table entry: 0-based crystal library index
   int ncmax = 1;                     // crystals per material point the tables are sized for
   bool has_taylor = false;           // some cp material has n_crystals > 1
+  bool kern[2][3] = {{false, false, false}, {false, false, false}};   // [n_crystals > 1][hardening law]: kernels to launch
   std::vector<double> gtab;          // ngrains x CPF_GRAIN_STRIDE
   int ngrains = 0, nslip_max = 0;
   bool has_mm01 = false, has_mm10 = false;
@@ -73,7 +74,7 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
   for (int i = 0; i < nmat; ++i) {
     const cpfft_material& m = mats[i];
     md[i].type = m.type; md[i].crystal = m.crystal - 1;
-    md[i].ncry = (m.type == 10 && m.n_crystals > 1) ? m.n_crystals : 1; md[i].pad_ = 0;
+    md[i].ncry = (m.type == 10 && m.n_crystals > 1) ? m.n_crystals : 1; md[i].hard = 0;   // hard: from the crystals in use, below
     if (md[i].ncry > ncmax) { err = "n_crystals of a material exceeds the crystals per voxel of cpfft_set_voxels_taylor"; return CPFFT_ERR_USAGE; }
     if (md[i].ncry > 1) T.has_taylor = true;
     md[i].ym = (double)m.e; md[i].nu = (double)m.nu; md[i].beta = (double)m.beta;
@@ -91,7 +92,7 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
   for (int i = 0; i < ncry; ++i) {
     const cpfft_crystal& c = crys[i];
     CpfCryDev& d = cd[i];
-    if (c.h_type != 1) { err = "only Voce hardening (h_type 1) is supported"; return CPFFT_ERR_USAGE; }
+    if (c.h_type != 1 && c.h_type != 2) { err = "unsupported hardening law (h_type 1 = voce, 2 = mts)"; return CPFFT_ERR_USAGE; }
     const signed char (*tb)[3]; const signed char (*tn)[3];
     if (c.slip_type == 1) { d.nslip = 12; tb = CPF_FCC_B; tn = CPF_FCC_N; }
     else if (c.slip_type == 8) { d.nslip = 48; tb = CPF_BCC48_B; tn = CPF_BCC48_N; }
@@ -106,6 +107,17 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
     d.rate_n = c.harden_n; d.theta_0 = c.theta_0; d.tau_y = c.tau_y; d.tau_v = c.tau_v; d.voche_m = c.voche_m;
     d.iD_v = c.iD_v; d.eps_dot_0_y = c.eps_dot_0_y; d.k_0 = c.k_0; d.burgers = c.burgers;
     d.atol = c.atol; d.atol1 = c.atol1; d.rtol = c.rtol; d.rtol1 = c.rtol1;
+    d.hard = c.h_type; d.pad_ = 0;
+    {  // MTS constants (mm10_setup_mts, mm10_a.f:2109-2175)
+      d.tau_a = c.tau_a; d.tau_hat_y = c.tau_hat_y; d.tau_hat_v = c.tau_hat_v; d.eps_dot_0_v = c.eps_dot_0_v;
+      d.mu_0 = c.mu_0; d.D_0 = c.D_0; d.T_0 = c.T_0;
+      const double b3 = std::pow(c.burgers, 3.0);
+      d.kby = c.boltzman / (b3 * c.g_0_y);
+      d.kbv = c.boltzman / (b3 * c.g_0_v);
+      d.p_y = c.p_y; d.q_y = c.q_y; d.p_v = c.p_v; d.q_v = c.q_v;
+      d.iq_y = 1.0 / c.q_y; d.ip_y = 1.0 / c.p_y; d.iq_v = 1.0 / c.q_v; d.ip_v = 1.0 / c.p_v;
+      if (c.h_type == 2) d.iD_v = 0.0;      // the diffusion slip exists in the Voce branches only
+    }
     const double em1 = c.harden_n - 1.0;
     d.rate_int = (em1 >= 0.0 && em1 <= 64.0 && em1 == std::floor(em1)) ? (int)em1 : -1;
     double flex[6][6] = {{0}}, st[6][6];
@@ -131,6 +143,8 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
     const int ci = (crystal_ids ? crystal_ids[(size_t)e * ncmax + cc] : mats[m].crystal) - 1;
     if (ci < 0 || ci >= ncry) { err = "voxel refers to an undefined crystal"; return CPFFT_ERR_USAGE; }
     nslip_max = std::max(nslip_max, cd[ci].nslip);       // over the crystals in use (mm10_d.f:85-110)
+    if (md[m].hard == 0) md[m].hard = cd[ci].hard;
+    else if (md[m].hard != cd[ci].hard) { err = "the crystals of one cp material must share one hardening law"; return CPFFT_ERR_USAGE; }
     const double* av = angles + ((size_t)e * ncmax + cc) * 3;
     std::array<double, 4> key = {(double)ci, av[0], av[1], av[2]};
     auto it = gmap.find(key);
@@ -175,6 +189,8 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
   }
   T.ngrains = (int)gmap.size();
   if (gtab.empty()) { gtab.assign(CPF_GRAIN_STRIDE, 0.0); T.gcry.assign(1, 0); }
+  for (int i = 0; i < nmat; ++i)
+    if (md[i].type == 10 && md[i].hard >= 1 && md[i].hard <= 2) T.kern[md[i].ncry > 1 ? 1 : 0][md[i].hard] = true;
   T.nslip_max = nslip_max;
   T.H = 11;
   if (T.has_mm10) {

@@ -16,7 +16,7 @@ struct CpfHistLayout {
 // per-material constants in device memory
 struct CpfMatDev {
   int type, crystal;        // crystal: 0-based index into crystal table
-  int ncry, pad_;           // crystals per material point (imatprp(101)); > 1 = Taylor average
+  int ncry, hard;           // crystals per material point (imatprp(101)), > 1 = Taylor average; hardening law of its crystals (1 Voce, 2 MTS)
   double ym, nu, beta, tan_e, yld, hprime;  // mm01 (REAL*4 promoted, drive_eps_sig.f:486-521)
 };
 
@@ -25,6 +25,10 @@ struct CpfCryDev {
   int nslip, alter_mode, miter, rate_int;   // rate_int: harden_n-1 if small integer else -1
   double rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, eps_dot_0_y, k_0, burgers;
   double atol, atol1, rtol, rtol1;
+  // MTS (hard == 2): mu(T) = mu_0 - D_0 / (exp(T_0 / T) - 1); kby / kbv = boltz / (b^3 G_0_y / G_0_v),
+  // so that boltz T / (mu b^3 G_0) = kb T / mu; inverse exponents of the thermal activation law
+  int hard, pad_;
+  double tau_a, mu_0, D_0, T_0, tau_hat_y, tau_hat_v, kby, kbv, iq_y, ip_y, iq_v, ip_v, p_y, q_y, p_v, q_v, eps_dot_0_v;
 };
 
 // per-grain (unique crystal+orientation) table entry, device, doubles:

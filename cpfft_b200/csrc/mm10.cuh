@@ -182,7 +182,14 @@ struct Mm10Ctx {
   double ttn;      // tau_tilde at n
   double D[6];     // strain increment of the (sub)step
   double dg, tinc, taul;
+  // MTS hardening (HARD == 2) only, set by mts_substep(): ur = mu/mu_0, tau_a, and the part of
+  // the hardening target that does not depend on the unknowns,
+  //   h0 = tau_a (1 - mu/mu_n) + ur (tau_y - tau_y_n) + (mu/mu_n) tau_tilde_n   (mm10_b.f:2103-2108);
+  // tau_y / tau_v above then hold the thresholds of the (sub)step (mm10_setup_mts)
+  double ur, tau_a, h0;
 };
+#define MM10_VOCE 1
+#define MM10_MTS 2
 
 // Current Schmid vectors of system s.  The reference forms ms = RT2RVE(Rp_n^T) ms0 and
 // qs = RT2RVW(Rp_n^T) qs0 (mm10_a.f:867-876).  RT2RVE is the stress-type 6x6 operator, so in
@@ -211,7 +218,16 @@ CPF_DI void mm10_slip_geom(const Mm10Ctx& c, int s, double* ms, double* qs) {
   qs[2] = c.RWQ[6] * w0 + c.RWQ[7] * w1 + c.RWQ[8] * w2;
 }
 
+template <int HARD>
 CPF_DI double mm10_hfac(const Mm10Ctx& c, double tt, double* hterm_out) {
+  if (HARD == MM10_MTS) {
+    // ct = 1 - cta / tau_v, cta = (mu_0/mu) (tt - tau_a) - tau_y; the reference raises the signed
+    // value to the power voche_m (mm10_b.f:2093-2101); tau_l = 0
+    const double cta = (tt - c.tau_a) / c.ur - c.tau_y;
+    const double ct = 1.0 - cta / c.tau_v;
+    *hterm_out = ct;
+    return (c.voche_m == 1.0) ? ct : cpf_pow(ct, c.voche_m);
+  }
   const double hterm = 1.0 - (tt - c.tau_y) / c.tau_v + c.taul / (tt - c.tau_y);
   *hterm_out = hterm;
   const double ah = fabs(hterm);
@@ -221,6 +237,7 @@ CPF_DI double mm10_hfac(const Mm10Ctx& c, double tt, double* hterm_out) {
 
 // Residual (mm10_formR / formR1 / formR2).  R[0..5] = R1, R[6] = R2 (0 unless want2); returns
 // the hardening target h (np1%tt_rate = (h - tt_n)/tinc).
+template <int HARD>
 CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double* R, bool want2) {
   double dbarp[6] = {0, 0, 0, 0, 0, 0}, wq[3] = {0, 0, 0}, sabs = 0.0;
   const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v;
@@ -254,8 +271,9 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
   R[6] = 0.0;
   if (want2) {
     double ht;
-    const double hf = mm10_hfac(c, tt, &ht);
-    h = c.ttn + c.theta_0 * (hf * sabs);
+    const double hf = mm10_hfac<HARD>(c, tt, &ht);
+    if (HARD == MM10_MTS) h = c.h0 + c.theta_0 * c.ur * (hf * sabs);    // mm10_h_mts
+    else h = c.ttn + c.theta_0 * (hf * sabs);
     R[6] = tt - h;
   }
   return h;
@@ -263,6 +281,7 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
 
 // Jacobian (mm10_formJ) into c.J (7x7 row-major, shared memory).  full = false: J11 only
 // (stress predictor), padded with an identity row / column.
+template <int HARD>
 CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool full) {
   double dps[6], wqs[3], wqf[3], es[6], sabs = 0.0, ssum = 0.0;
   {
@@ -363,8 +382,15 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
     }
     // J21 = -theta0 dg n / tt * hfac * sum sgn(rs) |rs/tt|^(n-1) ms
     double ht;
-    const double hf = mm10_hfac(c, tt, &ht);
+    const double hf = mm10_hfac<HARD>(c, tt, &ht);
     const double dgn = c.dg * c.rate_n / tt;
+    if (HARD == MM10_MTS) {
+      // mm10_estress_mts / mm10_ehard_mts (mm10_b.f:2114-2186), tau_l = 0
+      const double fac = c.theta_0 * c.ur * dgn * hf;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c.J[42 + k] = -(fac * es[k]);
+      c.J[48] = 1.0 + c.theta_0 * ((c.voche_m / (c.tau_v * ht) + c.ur * c.rate_n / tt) * hf * sabs);
+    } else {
     const double fac = c.theta_0 * dgn * hf;
 #pragma unroll
     for (int k = 0; k < 6; ++k) c.J[42 + k] = -(fac * es[k]);
@@ -374,6 +400,7 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
     const double A = -1.0 / c.tau_v - c.taul / ((tt - c.tau_y) * (tt - c.tau_y));
     const double etau = (c.voche_m * A * sabs / ah - ssum * c.rate_n / tt * cpf_sgn(ht)) * pw;
     c.J[48] = 1.0 - c.theta_0 * etau;
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < 6; ++k) { c.J[7 * k + 6] = 0.0; c.J[42 + k] = 0.0; }
@@ -381,9 +408,26 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
   }
 }
 
+// MTS (mm10_setup_mts, mm10_a.f:2109-2175).  Shear modulus and activation constants at
+// temperature T, then the thresholds of a (sub)step from its strain rate dgc = dg / tinc.
+struct Mm10Mts {
+  double tau_hat_y, tau_hat_v, ky, kv, iq_y, ip_y, iq_v, ip_v, eps_dot_0_y, eps_dot_0_v;
+};
+CPF_DI void mts_at_temperature(const CpfCryDev& cr, double T, double* mu, Mm10Mts* m) {
+  *mu = (T == 0.0) ? cr.mu_0 : cr.mu_0 - cr.D_0 / (exp(cr.T_0 / T) - 1.0);
+  m->ky = cr.kby * T / *mu;         // boltz T / (mu b^3 G_0_y)
+  m->kv = cr.kbv * T / *mu;
+}
+CPF_DI void mts_thresholds(const Mm10Mts& m, double dgc, double* tau_y, double* tau_v) {
+  if (dgc == 0.0) { *tau_v = m.tau_hat_v; *tau_y = m.tau_hat_y; return; }
+  *tau_v = m.tau_hat_v * cpf_pow(1.0 - cpf_pow(m.kv * log(m.eps_dot_0_v / dgc), m.iq_v), m.ip_v);
+  *tau_y = m.tau_hat_y * cpf_pow(1.0 - cpf_pow(m.ky * log(m.eps_dot_0_y / dgc), m.iq_y), m.ip_y);
+}
+
 // mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening
 // (phase 0, 6 unknowns), then the coupled update (phase 1, 7 unknowns), as one state machine.
 // x[7] in/out.  c.J keeps the last Jacobian formed (lagged tangent).  Returns true on failure.
+template <int HARD>
 CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, int* it_pred, int* it_upd,
                        double* h_last) {
   const double cc = 1.0e-4, red = 0.5;
@@ -405,7 +449,7 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, in
       double yt[7], Rt[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) yt[k] = init ? y[k] : y[k] + alpha * dx[k];
-      h = mm10_resid(c, yt, yt[6], Rt, phase == 1);
+      h = mm10_resid<HARD>(c, yt, yt[6], Rt, phase == 1);
       double dot = 0.0;
 #pragma unroll
       for (int k = 0; k < 7; ++k) dot += Rt[k] * Rt[k];
@@ -437,7 +481,7 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, in
           else { *it_upd += iter; done = true; }
         } else {
           // Newton step: dx = -J^-1 R with the Armijo data of the line search
-          mm10_jacobian(c, y, y[6], phase == 1);
+          mm10_jacobian<HARD>(c, y, y[6], phase == 1);
           double wv[7];
           dot = 0.0;
 #pragma unroll

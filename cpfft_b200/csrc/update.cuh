@@ -68,11 +68,17 @@ CPF_DI void upd_mm01_voxel(const UpdArgs& a, const int64_t e) {
 //   and stress, tangent, slip and work increments are Taylor-averaged
 //   (mm10_a_crystal_avgs, mm10_a.f:139-164).  The sums of the 36 tangent entries and of the
 //   slip increments are kept in the voxel's own n+1 slots (a.cep, hist_n1 slip sums).
-template <bool MULTI>
+// HARD: hardening law of the material's crystals, MM10_VOCE or MM10_MTS (`hardening mts`:
+//   thresholds tau_y, tau_v of every (sub)step from the strain rate, mm10_setup_mts
+//   mm10_a.f:2109-2175; h / estress / ehard mm10_b.f:2080-2186; tangent terms JA, JB from
+//   dgamma/dD and ed, mm10_a.f:740-810, mm10_b.f:2189-2345 -- both proportional to the strain
+//   increment, so C - JA - JB is a rank-one correction of C).
+template <bool MULTI, int HARD>
 CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   const CpfMatDev mp = a.mats[a.matidx[e]];
   if (mp.type != 10) return;
   if ((mp.ncry > 1) != MULTI) return;
+  if (mp.hard != HARD) return;
   const int64_t n3 = a.n3;
   const CpfHistLayout& L = a.L;
   double R[9], de[6];
@@ -118,7 +124,17 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       Rpn[3 * i + j] = first ? ((i == j) ? 1.0 : 0.0) : a.hist_n[((L.c_Rp + co) + 3 * j + i) * n3 + e];
-  c.ttn = first ? (cr.tau_y + 1.0e-5) : a.hist_n[(L.c_tt + co) * n3 + e];
+  c.ttn = first ? ((HARD == MM10_MTS) ? -1.0 : (cr.tau_y + 1.0e-5)) : a.hist_n[(L.c_tt + co) * n3 + e];
+  // MTS: tau_y and mu_harden of the n state live in u(1:2); < 0 = not set yet (mm10_init_mts)
+  double u1n = -1.0, u2n = -1.0, tau_y_full = 0.0, tau_v_full = 0.0;
+  Mm10Mts mts;
+  if (HARD == MM10_MTS) {
+    if (!first) { u1n = a.hist_n[((L.c_u + co) + 0) * n3 + e]; u2n = a.hist_n[((L.c_u + co) + 1) * n3 + e]; }
+    mts.tau_hat_y = cr.tau_hat_y; mts.tau_hat_v = cr.tau_hat_v; mts.ky = 0.0; mts.kv = 0.0;
+    mts.iq_y = cr.iq_y; mts.ip_y = cr.ip_y; mts.iq_v = cr.iq_v; mts.ip_v = cr.ip_v;
+    mts.eps_dot_0_y = cr.eps_dot_0_y; mts.eps_dot_0_v = cr.eps_dot_0_v;
+    c.ur = 1.0; c.tau_a = cr.tau_a; c.iD_v = 0.0; c.h0 = 0.0;
+  }
   ttrate_n = first ? 0.0 : a.hist_n[(L.c_ttrate + co) * n3 + e];
 #pragma unroll
   for (int k = 0; k < 3; ++k) work_n[k] = first ? 0.0 : a.hist_n[(L.work + k) * n3 + e];
@@ -142,17 +158,29 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   }
   const double t1 = de[0] * de[0] + de[1] * de[1] + de[2] * de[2];
   const double t2 = de[3] * de[3] + de[4] * de[4] + de[5] * de[5];
-  const double dg_full = cr.alter_mode ? cr.eps_dot_0_y * dt : sqrt((2.0 / 3.0) * (t1 + 0.5 * t2));
+  const bool alter = (HARD == MM10_VOCE) && cr.alter_mode;       // mm10_setup_voche only (mm10_a.f:2073)
+  const double dg_full = alter ? cr.eps_dot_0_y * dt : sqrt((2.0 / 3.0) * (t1 + 0.5 * t2));
   double sn2 = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) sn2 += c.sn[k] * c.sn[k];
   const bool no_load = (sn2 == 0.0) && ((t1 + t2) == 0.0);
   const bool elastic = (a.iter == 0) || no_load;  // iter_0_extrapolate_off (rstgp1.f:870-877)
 
+  // MTS, full step (np1) at 297 K: mu, thresholds, and the n-state hardening value when the
+  // history still holds the flag (mm10_a.f:2170-2173).  The elastic path stores the RAW n value
+  // (mm10_solve_strup copies tt before mm10_setup runs, mm10_a.f:2674-2677).
+  const double ttn_raw = c.ttn;
+  double mu_full = 0.0;
+  if (HARD == MM10_MTS) {
+    mts_at_temperature(cr, 297.0, &mu_full, &mts);
+    mts_thresholds(mts, dg_full / dt, &tau_y_full, &tau_v_full);
+    c.ur = mu_full / cr.mu_0; c.tau_y = tau_y_full; c.tau_v = tau_v_full;
+    if (c.ttn < 0.0) c.ttn = cr.tau_a + c.ur * tau_y_full + 0.1;
+  }
   double x[7];
 #pragma unroll
   for (int k = 0; k < 6; ++k) x[k] = c.sn[k];
-  x[6] = c.ttn;
+  x[6] = (HARD == MM10_MTS && elastic) ? ttn_raw : c.ttn;
   double tang[36];   // row-major
   double tt_rate = 0.0;
   int itp = 0, itu = 0;
@@ -165,7 +193,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
     for (int k = 0; k < 36; ++k) tang[k] = CPF_LDG(c.C + k);
     if (!no_load) {
       double R1[7];
-      mm10_resid(c, x, x[6], R1, false);
+      mm10_resid<HARD>(c, x, x[6], R1, false);
 #pragma unroll
       for (int k = 0; k < 6; ++k) x[k] = x[k] - R1[k];
     }
@@ -202,10 +230,20 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) c.D[k] = de[k] * sc;
       c.tinc = dt * sc;
-      c.dg = cr.alter_mode ? cr.eps_dot_0_y * c.tinc : sqrt((2.0 / 3.0) * ((t1 * sc * sc) + 0.5 * (t2 * sc * sc)));
-      if (!cr.alter_mode && sc == 1.0) c.dg = dg_full;
+      c.dg = alter ? cr.eps_dot_0_y * c.tinc : sqrt((2.0 / 3.0) * ((t1 * sc * sc) + 0.5 * (t2 * sc * sc)));
+      if (!alter && sc == 1.0) c.dg = dg_full;
+      if (HARD == MM10_MTS) {
+        // mm10_setup_mts for the sub-step state `curr`; its temperature is 297 (step + frac) because
+        // n%temp = 0 in this code base (mm10_a.f:2486, 2769)
+        double mu_s, ty, tv;
+        mts_at_temperature(cr, 297.0 * sc, &mu_s, &mts);
+        mts_thresholds(mts, c.dg / c.tinc, &ty, &tv);
+        const double ty_n = (u1n < 0.0) ? ty : u1n, mu_n = (u2n < 0.0) ? mu_s : u2n;
+        c.ur = mu_s / cr.mu_0; c.tau_y = ty; c.tau_v = tv;
+        c.h0 = cr.tau_a * (1.0 - mu_s / mu_n) + c.ur * (ty - ty_n) + (mu_s / mu_n) * c.ttn;
+      }
       x[6] = c.ttn;
-      fail = mm10_solve(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
+      fail = mm10_solve<HARD>(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
       if (fail) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) x[k] = ox[k];
@@ -228,6 +266,53 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) c.D[k] = de[k];
       c.dg = dg_full; c.tinc = dt;
+      // MTS: C - JA - JB = C - w (x) d_mod, w = alpha va + (ce / J22) J12 with the lagged J12, J22,
+      //   va = sum_s slip_s (C ms_s + 2 symSW(sigma, qc_s)) and ed = ce d_mod at the converged state
+      //   (mm10_dgdd_mts, mm10_ed_mts with tau_l = 0; mm10_a.f:760-805)
+      double wv[7] = {0, 0, 0, 0, 0, 0, 0}, dmod[6] = {0, 0, 0, 0, 0, 0};
+      if (HARD == MM10_MTS) {
+        mts_at_temperature(cr, 297.0, &mu_full, &mts);
+        c.ur = mu_full / cr.mu_0; c.tau_y = tau_y_full; c.tau_v = tau_v_full;
+        double dps[6] = {0, 0, 0, 0, 0, 0}, wqs[3] = {0, 0, 0}, sabs = 0.0;
+        const double tt = x[6], itt = 1.0 / tt, dgtt = c.dg / tt;
+#pragma unroll 1
+        for (int s = 0; s < nslip; ++s) {
+          double ms[6], qs[3];
+          mm10_slip_geom(c, s, ms, qs);
+          const double rs = x[0] * ms[0] + x[1] * ms[1] + x[2] * ms[2] + x[3] * ms[3] + x[4] * ms[4] + x[5] * ms[5];
+          const double slip = dgtt * cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0) * rs;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) dps[k] += slip * ms[k];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) wqs[k] += slip * qs[k];
+          sabs += fabs(slip);
+        }
+        double wc[3], sw[6];
+        cpf_mv3(c.RWR, wqs, wc);
+        cpf_symsw(x, wc, sw);
+        const double alpha = 2.0 / (3.0 * c.dg * c.dg);
+        const double dgc = c.dg / c.tinc;
+        const double lny = log(mts.eps_dot_0_y / dgc), lnv = log(mts.eps_dot_0_v / dgc);
+        const double ty = mts.ky * lny, tv = mts.kv * lnv;
+        const double cy = 2.0 * cr.tau_hat_y / (3.0 * c.dg * c.dg * cr.q_y * cr.p_y * lny) *
+                          cpf_pow(1.0 - cpf_pow(ty, mts.iq_y), mts.ip_y - 1.0) * cpf_pow(ty, mts.iq_y);
+        const double cv = 2.0 * cr.tau_hat_v / (3.0 * c.dg * c.dg * cr.q_v * cr.p_v * lnv) *
+                          cpf_pow(1.0 - cpf_pow(tv, mts.iq_v), mts.ip_v - 1.0) * cpf_pow(tv, mts.iq_v);
+        const double scc = tt / c.ur - c.tau_a / c.ur - c.tau_y;
+        const double base = 1.0 - scc / c.tau_v;
+        const double bm1 = cpf_pow(base, c.voche_m - 1.0);
+        const double ce = c.theta_0 * c.ur * ((c.voche_m / c.tau_v * bm1) * cy + (c.voche_m / (c.tau_v * c.tau_v) * scc * bm1) * cv +
+                                             alpha * (bm1 * base)) * sabs + c.ur * cy;
+        const double j22 = c.J[48];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          double va = 2.0 * sw[i];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) va += CPF_LDG(c.C + 6 * i + k) * dps[k];
+          wv[i] = alpha * va + (ce / j22) * c.J[7 * i + 6];
+          dmod[i] = (i < 3) ? de[i] : 0.5 * de[i];
+        }
+      }
       // mm10_tangent (Voce: ed = 0, dgammadd = 0): T = (J11 - J12 J21 / J22)^-1 C.  The Schur
       // complement replaces the lagged Jacobian in shared memory (padded to 7x7) and the six
       // columns of C go through the kernel's single LU site one at a time.
@@ -252,6 +337,13 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
       }
 #pragma unroll
       for (int k = 0; k < 36; ++k) tang[k] = c.acc[k];
+      if (HARD == MM10_MTS) {       // T = JJ^-1 C - (JJ^-1 w) (x) d_mod
+        mm10_lu7(c.J.p, 1.0, wv);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) tang[6 * i + j] -= wv[i] * dmod[j];
+      }
 #pragma unroll
       for (int i = 0; i < 6; ++i)   // mm10_a_make_symm_1
 #pragma unroll
@@ -425,6 +517,10 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
     for (int i = 0; i < 3; ++i) a.hist_n1[((L.c_Rp + co) + 3 * j + i) * n3 + e] = Rp1[3 * i + j];
   a.hist_n1[(L.c_tt + co) * n3 + e] = x[6];
   a.hist_n1[(L.c_ttrate + co) * n3 + e] = tt_rate;
+  if (HARD == MM10_MTS) {   // np1%u(1:2) = tau_y, mu_harden of the full step; a failed point keeps the n values
+    a.hist_n1[((L.c_u + co) + 0) * n3 + e] = fail ? u1n : tau_y_full;
+    a.hist_n1[((L.c_u + co) + 1) * n3 + e] = fail ? u2n : mu_full;
+  }
   a.hist_n1[((L.c_u + co) + 5) * n3 + e] = u6;
   a.hist_n1[((L.c_u + co) + 6) * n3 + e] = u7;
   a.hist_n1[((L.c_u + co) + 7) * n3 + e] = u8;

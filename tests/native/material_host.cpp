@@ -94,8 +94,11 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
     if (mp.type == 1) upd_mm01_voxel(a, e);
     else if (mp.type == 10) {
       double sm[MM10_SMEM_DOUBLES];
-      if (mp.ncry > 1) upd_mm10_voxel<true>(a, e, sm);
-      else upd_mm10_voxel<false>(a, e, sm);
+      if (mp.hard == MM10_MTS) {
+        if (mp.ncry > 1) upd_mm10_voxel<true, MM10_MTS>(a, e, sm);
+        else upd_mm10_voxel<false, MM10_MTS>(a, e, sm);
+      } else if (mp.ncry > 1) upd_mm10_voxel<true, MM10_VOCE>(a, e, sm);
+      else upd_mm10_voxel<false, MM10_VOCE>(a, e, sm);
     }
     upd_pk1_voxel(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
   }

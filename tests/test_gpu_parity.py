@@ -231,8 +231,12 @@ def test_taylor_points(libs, mixed):
     assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
 
 
-@pytest.mark.parametrize("kind", ["cubic_elasticity", "voce_m_2", "rate_exponent_7p5", "diffusion", "alter_mode",
-                                  "bcc48", "mixed_materials", "two_crystal_types"])
+def _variant_kinds():
+    from test_host_kernels import VARIANTS
+    return VARIANTS
+
+
+@pytest.mark.parametrize("kind", _variant_kinds())
 def test_crystal_and_grid_variants(libs, kind):
     """edge-case variants of the Voce crystal and of the grid make-up (tests/test_host_kernels.py runs
     the same cases on the host build of the kernel source): three load steps, two sweeps each.
