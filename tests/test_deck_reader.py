@@ -128,3 +128,14 @@ def test_polycrystalline_points_from_a_crystal_file(tmp_path):
     f.write_text("1 10 20 30\n2 1 2 3\n2 4 5 6\n")            # element 1 has one line, two are needed
     with pytest.raises(DeckError):
         read_crystal_file(str(f), 2, 2, True, False)
+
+
+def test_mts_crystal_keywords():
+    """`hardening mts` and its property keywords (incrystal.f:165-236, 305-331)"""
+    p = deck("mts_mm10.in")
+    c = p.crystals[0]
+    assert c.h_type == 2 and c.slip_type == 1
+    assert (c.tau_a, c.tau_hat_y, c.g_0_y, c.tau_hat_v, c.g_0_v) == (20.0, 180.0, 0.4, 300.0, 1.2)
+    assert (c.burgers, c.boltzman, c.eps_dot_0_y, c.eps_dot_0_v) == (2.5e-7, 1.3806e-20, 1.0e10, 1.0e10)
+    assert (c.p_y, c.q_y, c.p_v, c.q_v, c.mu_0, c.D_0, c.T_0) == (0.5, 2.0, 0.5, 2.0, 80000.0, 3000.0, 200.0)
+    assert c.theta_0 == 1500.0 and c.harden_n == 20.0

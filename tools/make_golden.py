@@ -36,7 +36,9 @@ def main():
            "test_mm10.in+angle2.in": run(mm10_variant("angle2.in"), nstep=4),
            "test_mm01.in+P_yy=P_zz=0": run(stress_bc_variant(deck("test_mm01.in")), nstep=3),
            # derived deck: polycrystalline material points (n_crystals 2, fcc + bcc48 from a crystal file)
-           "taylor_mm10.in": run(deck("taylor_mm10.in"))}
+           "taylor_mm10.in": run(deck("taylor_mm10.in")),
+           # derived deck: MTS hardening law
+           "mts_mm10.in": run(deck("mts_mm10.in"))}
     path = os.path.join(ROOT, "tests", "golden", "deck_results.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
