@@ -169,6 +169,46 @@ def algorithmic_bytes_per_voxel(cls, N, cg_frac=0.0, cg_fused_frac=0.0):
     }.get(cls)
 
 
+def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
+    """per-kernel-class table {ms, launches, share, algorithmic bytes, achieved GB/s, fraction of the
+    measured HBM peak, ncu DRAM traffic / FP64 counts when profiles/ncu_traffic.json matches} and the
+    `roofline` object of the kernel class that takes the most time.  table: {class: (ms, launches)}."""
+    peak, which = measured_peaks()
+    stages = {}
+    tot_ms = sum(v[0] for v in table.values()) or 1.0
+    for name, (kms, cnt) in table.items():
+        if cnt == 0:
+            continue
+        # share of the launches of the z passes that carry fused CG work (counted, not assumed)
+        cg_frac = min(1.0, cgits / cnt) if name == "k_inv_z" else 0.0
+        cg_fused = min(1.0, max(0, cgits - nsolves) / cnt) if name == "k_fwd_z_K4" else 0.0
+        b = algorithmic_bytes_per_voxel(name, N, cg_frac, cg_fused)
+        ent = {"ms_total": kms, "launches": cnt, "share": kms / tot_ms, "ms_per_launch": kms / cnt}
+        if b is not None:
+            gbs = b * n3 / (kms / cnt * 1e-3) / 1e9
+            ent.update({"alg_bytes_per_voxel": b, "achieved_gbs": gbs, "frac_of_hbm": gbs / peak})
+        stages[name] = ent
+    prof = ncu_profile_data()
+    if prof and prof.get("grid") == N and world == 1:
+        for name, ent in prof["kernels"].items():
+            if name in stages:
+                stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
+                if "fp64_flop" in ent and fp64_peak:
+                    tf = ent["fp64_flop"] / (stages[name]["ms_per_launch"] * 1e-3) / 1e12
+                    stages[name].update({"fp64_flop_per_launch_ncu": ent["fp64_flop"], "fp64_tflops": tf,
+                                         "fp64_peak_tflops_measured": fp64_peak, "frac_of_fp64": tf / fp64_peak})
+    cand = [k for k in stages if "achieved_gbs" in stages[k]]
+    dom = max(cand, key=lambda k: stages[k]["ms_total"]) if cand else None
+    roof = None
+    if dom:
+        d = stages[dom]
+        roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["achieved_gbs"] / peak, "traffic": d.get("ncu_dram_bytes_per_launch"),
+                "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
+                "alg_bytes_per_launch": d["alg_bytes_per_voxel"] * n3, "ms_per_launch": d["ms_per_launch"]}
+    return stages, roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,38 +330,7 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (CUDA events on the launching stream) ----
-    peak, which = measured_peaks()
-    stages = {}
-    tot_ms = sum(v[0] for v in table.values()) or 1.0
-    for name, (kms, cnt) in table.items():
-        if cnt == 0:
-            continue
-        # share of the launches of the z passes that carry fused CG work (counted, not assumed)
-        cg_frac = min(1.0, cgits / cnt) if name == "k_inv_z" else 0.0
-        cg_fused = min(1.0, max(0, cgits - nsolves) / cnt) if name == "k_fwd_z_K4" else 0.0
-        b = algorithmic_bytes_per_voxel(name, N, cg_frac, cg_fused)
-        ent = {"ms_total": kms, "launches": cnt, "share": kms / tot_ms, "ms_per_launch": kms / cnt}
-        if b is not None:
-            gbs = b * (s.n3) / (kms / cnt * 1e-3) / 1e9
-            ent.update({"alg_bytes_per_voxel": b, "achieved_gbs": gbs, "frac_of_hbm": gbs / peak})
-        stages[name] = ent
-    prof = ncu_profile_data()
-    if prof and prof.get("grid") == N and world == 1:
-        for name, ent in prof["kernels"].items():
-            if name in stages:
-                stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
-                if "fp64_flop" in ent:
-                    tf = ent["fp64_flop"] / (stages[name]["ms_per_launch"] * 1e-3) / 1e12
-                    stages[name].update({"fp64_flop_per_launch_ncu": ent["fp64_flop"], "fp64_tflops": tf,
-                                         "fp64_peak_tflops_measured": fp64_peak, "frac_of_fp64": tf / fp64_peak})
-    cand = [k for k in stages if "achieved_gbs" in stages[k]]
-    dom = max(cand, key=lambda k: stages[k]["ms_total"]) if cand else None
-    roof = None
-    if dom:
-        d = stages[dom]
-        roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["achieved_gbs"] / peak, "traffic": d.get("ncu_dram_bytes_per_launch"), "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
-                "alg_bytes_per_launch": d["alg_bytes_per_voxel"] * s.n3, "ms_per_launch": d["ms_per_launch"]}
+    stages, roof = stage_rooflines(table, N, s.n3, cgits, nsolves, world, fp64_peak)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
