@@ -102,7 +102,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   for (int ci = 0; ci < ncry; ++ci) {
   const int co = MULTI ? ci * (L.total - L.c_stress) : 0;            // offset of this crystal's history block
   const int gi = a.grain[(MULTI ? (int64_t)ci * n3 : (int64_t)0) + e];
-  const CpfCryDev cr = a.crys[MULTI ? a.grain_cry[gi] : mp.crystal];
+  const CpfCryDev cr = a.crys[a.grain_cry[gi]];       // the grain-table entry knows its crystal (crystal_input single or file)
   const double* gt = a.grains + (int64_t)gi * CPF_GRAIN_STRIDE;
   const int nslip = cr.nslip;
   Mm10Ctx c;

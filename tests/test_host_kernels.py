@@ -177,6 +177,12 @@ def _variant_problem(kind):
         from cpfft_b200.polycrystal import taylor_polycrystal
         p = taylor_polycrystal(4, ncrystals=2, ngrains=9)
         p.crystals = [mts_crystal()]
+    elif kind == "crystal_file_single":      # n_crystals 1 with `crystal_input file`: crystal number per voxel
+        c2 = copy.copy(c); c2.tau_y = 60.0; c2.theta_0 = 300.0; c2.slip_type = 8
+        p.crystals.append(c2)
+        p.materials[0].crystal_input = 2; p.materials[0].crystal = 0
+        ids = np.ones((p.N3, 1), dtype=np.int32); ids[::2] = 2
+        p.crystal_ids = ids
     elif kind == "two_crystal_types":        # two library crystals, two cp materials
         c2 = copy.copy(c); c2.tau_y = 60.0; c2.theta_0 = 300.0; c2.e = 120000.0; c2.mu = 120000.0 / 2.6
         p.crystals.append(c2)
@@ -188,7 +194,7 @@ def _variant_problem(kind):
 
 
 VARIANTS = ["cubic_elasticity", "voce_m_2", "rate_exponent_7p5", "diffusion", "alter_mode", "bcc48", "mixed_materials",
-            "two_crystal_types", "mts", "mts_athermal", "mts_voce_m_2", "mts_and_voce", "mts_taylor"]
+            "two_crystal_types", "crystal_file_single", "mts", "mts_athermal", "mts_voce_m_2", "mts_and_voce", "mts_taylor"]
 
 
 @pytest.mark.parametrize("kind", VARIANTS)
