@@ -1,0 +1,40 @@
+#!/bin/bash
+# Standard GPU-box sequences, sized from the timings measured in round 1 (one B200, this image):
+#   getting a box + pushing the repo ~20 s; no-torch python start ~3 s; first `import torch` ~30 s;
+#   pytest -m gpu (whole suite) ~125 s; bench.py --steps 2 --warmup 3 --no-cpu-baseline ~60 s.
+# Everything writes under gpurun_out/ (merged back by gpurun).  Usage, from the repo root:
+#   gpurun --timeout 240 -- 'tools/gpu_session.sh tests'         whole GPU suite
+#   gpurun --timeout 120 -- 'tools/gpu_session.sh quick'         parity + golden + bit-identity tests (~15 s)
+#   gpurun --timeout 200 -- 'tools/gpu_session.sh bench TAG'     bench line -> gpurun_out/TAG_bench256.json
+#   gpurun --timeout 200 -- 'tools/gpu_session.sh launches TAG'  ncu launch list of one bench step
+#   gpurun --timeout 120 -- 'tools/gpu_session.sh ncu-cg TAG'    ncu --set full of the kernels of one CG iteration
+#   gpurun --timeout 300 -- 'tools/gpu_session.sh ncu-update TAG' ncu --set full of k_update_mm10 / k_pk1_tangent
+#   gpurun --timeout 120 -- 'tools/gpu_session.sh ab'            A/B of the kernel-variant switches (tools/ab_iz.py)
+set -u
+MODE=${1:-quick}; TAG=${2:-rXX}
+mkdir -p gpurun_out
+case "$MODE" in
+  tests)
+    timeout 220 python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -25 | tee gpurun_out/${TAG}_gpu_tests.log ;;
+  quick)
+    timeout 100 python -m pytest tests/test_gpu_parity.py tests/test_golden_decks.py \
+        "tests/test_gpu_spectral.py::test_kernel_variants_are_bit_identical" -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_quick.log ;;
+  bench)
+    timeout 180 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench256.json 2> gpurun_out/${TAG}_bench256.err
+    tail -c 400 gpurun_out/${TAG}_bench256.json ;;
+  launches)
+    timeout 180 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_${TAG}.csv \
+        python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+    python tools/ncu_summary.py gpurun_out/launches_${TAG}.csv | head -24 ;;
+  ncu-cg)
+    timeout 100 ncu --set full --clock-control none --import-source on -k 'regex:^(k_fz|k_fyf|k_fx|k_fyi|k_iz_pipe|k_cg_update_r)$' \
+        -s 16 -c 6 -f -o gpurun_out/prof_${TAG}_cg python tools/ncu_cg.py 256 > gpurun_out/${TAG}_ncu_cg.log 2>&1
+    tail -3 gpurun_out/${TAG}_ncu_cg.log; ls -la gpurun_out/prof_${TAG}_cg.ncu-rep ;;
+  ncu-update)
+    timeout 280 ncu --set full --clock-control none --import-source on -k 'regex:^(k_update_mm10|k_pk1_tangent)$' -s 4 -c 2 -f \
+        -o gpurun_out/prof_${TAG}_update python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_update.log 2>&1
+    tail -3 gpurun_out/${TAG}_ncu_update.log; ls -la gpurun_out/prof_${TAG}_update.ncu-rep ;;
+  ab)
+    timeout 100 python tools/ab_iz.py 256 10 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab256.log ;;
+  *) echo "unknown mode $MODE"; exit 2 ;;
+esac
