@@ -31,19 +31,29 @@ def Oracle(oracle_built):
     return Oracle
 
 
-@pytest.mark.parametrize("law", ["voce", "mts"])
+@pytest.mark.parametrize("law", ["voce", "voce_bcc48", "voce_m2_n7p5", "voce_alter_mode", "mts", "mts_m2", "mts_bcc48"])
 def test_local_jacobian_matches_central_differences(Oracle, law):
     from cpfft_b200.problem import Crystal
     rng = np.random.default_rng(5)
-    if law == "mts":
+    if law.startswith("mts"):
         c = mts_crystal()
+        if law == "mts_m2":
+            c.voche_m = 2.0
+        if law == "mts_bcc48":
+            c.slip_type = 8
     else:
         c = Crystal(slip_type=1, e=200000.0, nu=0.3, mu=200000.0 / 2.6, harden_n=20.0, theta_0=100.0,
                     tau_v=100.0, tau_y=100.0, iD_v=1.0e-7)
+        if law == "voce_bcc48":
+            c.slip_type = 8
+        if law == "voce_m2_n7p5":
+            c.voche_m = 2.0; c.harden_n = 7.5
+        if law == "voce_alter_mode":
+            c.alter_mode = 1; c.eps_dot_0_y = 2.0e-3
     ang = (25.0, 40.0, 70.0)
     D = 2.0e-3 * np.array([1.0, -0.4, -0.5, 0.3, -0.2, 0.1])
     sn = 60.0 * rng.standard_normal(6)
-    ttn = 230.0 if law == "mts" else 115.0
+    ttn = 230.0 if law.startswith("mts") else 115.0
     x = np.concatenate([sn + 25.0 * rng.standard_normal(6), [ttn + 4.0]])
     R, J = Oracle.mm10_residual_jacobian(c, ang, D, 1.0, x, sn, ttn)
     assert np.all(np.isfinite(R)) and np.all(np.isfinite(J))
@@ -56,14 +66,14 @@ def test_local_jacobian_matches_central_differences(Oracle, law):
                     Oracle.mm10_residual_jacobian(c, ang, D, 1.0, xm, sn, ttn)[0]) / (2 * h)
     scale = np.abs(fd).max(axis=1, keepdims=True)
     diff = np.abs(J - fd)
-    if law == "voce":
+    if law.startswith("voce"):
         # reference quirk, reproduced on purpose: mm10_ehard_voche (mm10_b.f:1962-1975) multiplies the
         # d|slip|/d(tau_tilde) term by sign(slipinc), so J22 is only exact while no system slips
         # backwards; every other entry is the exact derivative
-        assert 0 < diff[6, 6] <= 1e-3
+        assert 0 < diff[6, 6] <= 1e-2
         diff[6, 6] = 0.0
     assert diff.max() <= 2e-6 * np.abs(fd).max(), diff.max() / np.abs(fd).max()
-    assert (diff / scale).max() <= 1e-5          # row by row (the hardening row is much smaller)
+    assert (diff / scale).max() <= 2e-5          # row by row (the hardening row is much smaller)
 
 
 def _drive(o, F_path, after_first_commit=None):
