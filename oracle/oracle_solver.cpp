@@ -18,36 +18,106 @@ static double now_s() {
 }
 
 // ----------------------------------------------------------------------------
-// 1-D complex DFT of arbitrary length: recursive mixed radix (generic butterflies),
-// stand-in for MKL DFTI (G_K_dF.f:130-154).  exponent sign = dir (-1 forward).
+// 1-D complex DFT of arbitrary length, stand-in for MKL DFTI (G_K_dF.f:130-154): Stockham
+// autosort, one pass per prime factor (4 taken as one radix), explicit butterflies for radix
+// 2, 3, 4, 5 and an O(R^2) butterfly for any other prime; twiddles precomputed per stage.
+// exponent sign = dir (-1 forward, +1 backward), unscaled.
 struct Fft1d {
-  int n; std::vector<int> factors; std::vector<cplx> wf, wb;
+  int n;
+  std::vector<int> radices;
+  std::vector<std::vector<cplx>> tw;     // stage s: tw[s][k * R + r] = exp(-2 pi i k r / (Ns R)), k < Ns
+  std::vector<std::vector<cplx>> twc;    // conjugates (backward transform)
+  std::vector<std::vector<cplx>> roots;  // generic radix R: exp(-2 pi i q / R), q < R
   void init(int n_) {
-    n = n_; factors.clear();
+    n = n_; radices.clear(); tw.clear(); twc.clear(); roots.clear();
     int m = n;
-    for (int p = 2; p * p <= m;) { if (m % p == 0) { factors.push_back(p); m /= p; } else ++p; }
-    if (m > 1) factors.push_back(m);
-    wf.resize(n); wb.resize(n);
-    for (int k = 0; k < n; ++k) {
-      double a = -2.0 * M_PI * (double)k / (double)n;
-      wf[k] = cplx(std::cos(a), std::sin(a)); wb[k] = std::conj(wf[k]);
+    while (m % 4 == 0) { radices.push_back(4); m /= 4; }
+    for (int p = 2; p * p <= m;) { if (m % p == 0) { radices.push_back(p); m /= p; } else ++p; }
+    if (m > 1) radices.push_back(m);
+    int Ns = 1;
+    for (int R : radices) {
+      std::vector<cplx> t((size_t)Ns * R), rt(R);
+      for (int k = 0; k < Ns; ++k)
+        for (int r = 0; r < R; ++r) {
+          double a = -2.0 * M_PI * (double)k * (double)r / ((double)Ns * (double)R);
+          t[(size_t)k * R + r] = cplx(std::cos(a), std::sin(a));
+        }
+      for (int q = 0; q < R; ++q) { double a = -2.0 * M_PI * (double)q / (double)R; rt[q] = cplx(std::cos(a), std::sin(a)); }
+      std::vector<cplx> tc(t.size());
+      for (size_t i = 0; i < t.size(); ++i) tc[i] = std::conj(t[i]);
+      tw.push_back(t); twc.push_back(tc); roots.push_back(rt);
+      Ns *= R;
     }
   }
-  // Decimation in time: X[k + q m] = sum_r W_len^{r (k + q m)} Y_r[k], Y_r = DFT_m(x[r + p j]).
-  // out[k], k<len, of in[0], in[stride], ...; W_len^e = w[(e mod len) * (n/len)].
-  void rec(const cplx* in, int stride, cplx* out, int len, int fi, const std::vector<cplx>& w, cplx* scratch) const {
-    if (len == 1) { out[0] = in[0]; return; }
-    int p = factors[fi], m = len / p, tw = n / len;
-    for (int r = 0; r < p; ++r) rec(in + (size_t)r * stride, stride * p, out + (size_t)r * m, m, fi + 1, w, scratch);
-    for (int k = 0; k < m; ++k) {
-      for (int q = 0; q < p; ++q) {
-        cplx s(0, 0);
-        long long kk = k + (long long)q * m;
-        for (int r = 0; r < p; ++r) s += out[r * m + k] * w[(size_t)((r * kk) % len) * tw];
-        scratch[q] = s;
+  static inline cplx mul_i(cplx a, int dir) { return dir < 0 ? cplx(a.imag(), -a.real()) : cplx(-a.imag(), a.real()); }  // a * (dir * i)
+  // one Stockham pass with a compile-time radix: values in registers, loops unrolled
+  template <int R>
+  void pass(const cplx* in, cplx* out, const cplx* t, int Ns, int dir) const {
+    const int M = n / R;
+    for (int j0 = 0; j0 < M; j0 += Ns)
+      for (int k = 0; k < Ns; ++k) {
+        const int j = j0 + k;
+        cplx v[R];
+        v[0] = in[j];
+        for (int r = 1; r < R; ++r) v[r] = in[j + (size_t)r * M] * t[(size_t)k * R + r];
+        cplx* o = out + (size_t)j0 * R + k;
+        if (R == 2) {
+          o[0] = v[0] + v[1]; o[Ns] = v[0] - v[1];
+        } else if (R == 4) {
+          const cplx a0 = v[0] + v[2], a1 = v[0] - v[2], a2 = v[1] + v[3], a3 = mul_i(v[1] - v[3], dir);
+          o[0] = a0 + a2; o[Ns] = a1 + a3; o[2 * Ns] = a0 - a2; o[3 * Ns] = a1 - a3;
+        } else if (R == 3) {
+          const double c = -0.5, sn = dir * 0.86602540378443864676;
+          const cplx t1 = v[1] + v[2], t2 = v[0] + c * t1, t3 = mul_i(v[1] - v[2], 1) * sn;
+          o[0] = v[0] + t1; o[Ns] = t2 + t3; o[2 * Ns] = t2 - t3;
+        } else {   // R == 5
+          const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+          const double s1 = dir * 0.95105651629515357212, s2 = dir * 0.58778525229247312917;
+          const cplx a1 = v[1] + v[4 % R], a2 = v[2] + v[3], b1 = v[1] - v[4 % R], b2 = v[2] - v[3];
+          const cplx m1 = v[0] + c1 * a1 + c2 * a2, m2 = v[0] + c2 * a1 + c1 * a2;
+          const cplx n1 = mul_i(s1 * b1 + s2 * b2, 1), n2 = mul_i(s2 * b1 - s1 * b2, 1);
+          o[0] = v[0] + a1 + a2; o[Ns] = m1 + n1; o[4 * Ns] = m1 - n1; o[2 * Ns] = m2 + n2; o[3 * Ns] = m2 - n2;
+        }
       }
-      for (int q = 0; q < p; ++q) out[k + q * m] = scratch[q];
+  }
+  // any other prime radix: O(R^2) butterfly, scratch behind the ping-pong buffer
+  void pass_generic(const cplx* in, cplx* out, const cplx* t, const cplx* rt, cplx* vv, int R, int Ns, int dir) const {
+    const int M = n / R;
+    for (int j0 = 0; j0 < M; j0 += Ns)
+      for (int k = 0; k < Ns; ++k) {
+        const int j = j0 + k;
+        vv[0] = in[j];
+        for (int r = 1; r < R; ++r) vv[r] = in[j + (size_t)r * M] * t[(size_t)k * R + r];
+        cplx* o = out + (size_t)j0 * R + k;
+        for (int q = 0; q < R; ++q) {
+          cplx acc(0, 0);
+          for (int r = 0; r < R; ++r) {
+            cplx w = rt[(int)(((long long)q * r) % R)];
+            if (dir > 0) w = std::conj(w);
+            acc += vv[r] * w;
+          }
+          o[(size_t)q * Ns] = acc;
+        }
+      }
+  }
+  // data (n) is transformed; tmp (2 n) is scratch; the result ends in `data`
+  void run(cplx* data, cplx* tmp, int dir) const {
+    cplx* in = data; cplx* out = tmp;
+    int Ns = 1;
+    for (size_t s = 0; s < radices.size(); ++s) {
+      const int R = radices[s];
+      const cplx* t = (dir < 0 ? tw[s] : twc[s]).data();
+      switch (R) {
+        case 2: pass<2>(in, out, t, Ns, dir); break;
+        case 3: pass<3>(in, out, t, Ns, dir); break;
+        case 4: pass<4>(in, out, t, Ns, dir); break;
+        case 5: pass<5>(in, out, t, Ns, dir); break;
+        default: pass_generic(in, out, t, roots[s].data(), tmp + n, R, Ns, dir);
+      }
+      std::swap(in, out);
+      Ns *= R;
     }
+    if (in != data) for (int i = 0; i < n; ++i) data[i] = in[i];
   }
 };
 
@@ -315,19 +385,37 @@ extern "C" void orc_formG_entry(int N, int ii, int jj, int kk, double* G81) {
 }
 
 // 3-D complex transform of one component, strides (N^2, N, 1), by three sweeps of 1-D DFTs
-static void fft3d(const orc_model* m, cplx* a, int dir) {
-  const int N = m->N;
-  const std::vector<cplx>& w = dir < 0 ? m->fft.wf : m->fft.wb;
-  std::vector<cplx> line(N), out(N), scratch(4 * N + 64);
+// one axis pass of the 3-D transform of all 9 components (the reference runs the 9 components
+// in parallel with OpenMP and lets MKL thread inside, G_K_dF.f:50-57; here (component, plane)
+// pairs are the parallel tasks)
+static void fft3d_all(const orc_model* m, cplx* W, int dir) {
+  const int N = m->N; const size_t n3 = m->N3;
   for (int axis = 0; axis < 3; ++axis) {
-    size_t stride = axis == 0 ? 1 : (axis == 1 ? (size_t)N : (size_t)N * N);
-    for (int u = 0; u < N; ++u)
-      for (int v = 0; v < N; ++v) {
-        size_t base = axis == 0 ? ((size_t)u * N + v) * N : (axis == 1 ? (size_t)u * N * N + v : (size_t)u * N + v);
-        for (int k = 0; k < N; ++k) line[k] = a[base + k * stride];
-        m->fft.rec(line.data(), 1, out.data(), N, 0, w, scratch.data());
-        for (int k = 0; k < N; ++k) a[base + k * stride] = out[k];
-      }
+    const size_t stride = axis == 0 ? 1 : (axis == 1 ? (size_t)N : (size_t)N * N);
+#pragma omp parallel
+    {
+      constexpr int NB = 8;                                  // lines gathered together on the strided axes
+      std::vector<cplx> lines((size_t)NB * N), tmp(2 * (size_t)N);
+#pragma omp for collapse(2) schedule(static)
+      for (int c = 0; c < 9; ++c)
+        for (int u = 0; u < N; ++u) {
+          cplx* a = W + (size_t)c * n3;
+          if (axis == 0) {
+            for (int v = 0; v < N; ++v) m->fft.run(a + ((size_t)u * N + v) * N, tmp.data(), dir);
+          } else {
+            // axis 1: lines (x = u, z = v), stride N; axis 2: lines (y = u, z = v), stride N^2; consecutive v are adjacent
+            const size_t base0 = axis == 1 ? (size_t)u * N * N : (size_t)u * N;
+            for (int v0 = 0; v0 < N; v0 += NB) {
+              const int nb = std::min(NB, N - v0);
+              for (int k = 0; k < N; ++k)
+                for (int b = 0; b < nb; ++b) lines[(size_t)b * N + k] = a[base0 + v0 + b + k * stride];
+              for (int b = 0; b < nb; ++b) m->fft.run(lines.data() + (size_t)b * N, tmp.data(), dir);
+              for (int k = 0; k < N; ++k)
+                for (int b = 0; b < nb; ++b) a[base0 + v0 + b + k * stride] = lines[(size_t)b * N + k];
+            }
+          }
+        }
+    }
   }
 }
 
@@ -357,8 +445,8 @@ extern "C" void orc_G_K_dF(orc_model* m, const double* F, double* GKF, int flgK)
       double x = real1[c * n3 + e];
       a[e] = cplx(x * m->c1[i + j + k], x * m->c2[i + j + k]);
     }
-    fft3d(m, a, -1);
   }
+  fft3d_all(m, W, -1);
   // Ghat4 contraction of real and imaginary parts separately (G_K_dF.f:64-65)
 #pragma omp parallel for schedule(static)
   for (long long e = 0; e < (long long)n3; ++e) {
@@ -372,10 +460,10 @@ extern "C" void orc_G_K_dF(orc_model* m, const double* F, double* GKF, int flgK)
   }
   // ifftfem3d (G_K_dF.f:171-227): backward scaled 1/N3, out = re*c1 + im*c2
   const double scale = 1.0 / (double)n3;
+  fft3d_all(m, W, +1);
 #pragma omp parallel for schedule(static)
   for (int c = 0; c < 9; ++c) {
     cplx* a = W + (size_t)c * n3;
-    fft3d(m, a, +1);
     for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) for (int k = 0; k < N; ++k) {
       size_t e = ((size_t)i * N + j) * N + k;
       double re = a[e].real() * scale, im = a[e].imag() * scale;

@@ -95,7 +95,7 @@ def test_formG_entries_match_reference_table(Oracle, N):
         assert np.array_equal(Oracle.formG_entry(N, int(ii), int(jj), int(kk)), G[e])
 
 
-@pytest.mark.parametrize("N", [5, 7])
+@pytest.mark.parametrize("N", [5, 7, 9, 11, 13, 15, 21, 25])      # radix 3 / 5 passes, generic prime passes and their products
 def test_G_K_dF_matches_numpy_restatement(Oracle, N):
     p = _toy_problem(N)
     o = Oracle(p)
@@ -143,7 +143,7 @@ def _grad_field(N, rng, kmax):
     return grad.reshape(9, -1)
 
 
-@pytest.mark.parametrize("N", [5, 7, 6, 8])
+@pytest.mark.parametrize("N", [5, 7, 6, 8, 12, 16, 20, 24])       # even: radix 2 / 4 passes
 def test_green_projection_identities(Oracle, N):
     """Ghat:grad(u) = grad(u), Ghat:const = 0, idempotence, self-adjointness.  For even N the
     identities hold on fields without Nyquist content (documented convention)."""
