@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 METRIC = "voxel-iterations/sec (mm10 update + FFT/Green step)"
 UNIT = "voxel-iterations/s"
 GRID_FOR_GPUS = {1: 256, 2: 320, 4: 400, 8: 512}   # ~16.8 M voxels per GPU (weak scaling)
-CPU_SAMPLE_N = 24                                   # bounded CPU sample of the same workload
+CPU_SAMPLE_N = 32                                   # bounded CPU sample of the same workload
 
 
 def measured_peaks():
