@@ -261,3 +261,56 @@ def test_large_increment_triggers_substepping(libs, law):
     assert (o.local_iters[:, 1].max() > 12) if law == "voce" else (o.local_iters[:, 0].max() > 8)
     ok = np.ctypeslib.as_array(o.L.orc_fail_flags(o.h), shape=(o.N3,)) == 0
     assert relerr(k.urcs_n.T[ok], o.urcs_n[ok]) <= TOL_SMALL_STRAIN
+
+
+def _hybrid_FFT_nr3(k, o, prob, nstep):
+    """FFT_nr3's strain-controlled step / Newton loop (FFT_nr3.f:51-185) in Python: material sweeps by
+    the host build of the KERNEL source, spectral operator and CG by the oracle."""
+    bc = prob.BC_all()
+    barF = np.array([1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0])
+    nr, pbar = [], []
+    k.drive_eps_sig(1, 0)
+    for step in range(1, nstep + 1):
+        dF = np.repeat((bc[step - 1] - barF)[:, None], prob.N3, axis=1)
+        Fnorm = np.linalg.norm(k.Fn1)
+        k.Fn1[:] += dF
+        o.K4[:] = k.K4
+        rc, x, it, rr = o.fftPcg(-o.G_K_dF(dF, 1), prob.tolPCG)
+        assert rc == 0
+        k.Fn1[:] += x
+        res, it_nr = 1.0, 0
+        while res > prob.tolNR:
+            k.drive_eps_sig(step, it_nr)
+            o.K4[:] = k.K4
+            rc, x, it, rr = o.fftPcg(-o.G_K_dF(np.ascontiguousarray(k.Pn1), 0), prob.tolPCG)
+            assert rc == 0
+            k.Fn1[:] += x
+            res = np.linalg.norm(x) / Fnorm
+            it_nr += 1
+            assert it_nr < prob.maxIter
+        k.drive_eps_sig(step, it_nr)
+        pbar.append(k.Pn1.mean(axis=1))
+        k.Fn[:] = k.Fn1
+        k.update()
+        barF = bc[step - 1].copy()
+        nr.append(it_nr)
+    return nr, np.array(pbar)
+
+
+@pytest.mark.parametrize("name,nstep", [("test_mm10.in", 6), ("test_mm01.in", 4), ("taylor_mm10.in", 5), ("mts_mm10.in", 4)])
+def test_full_solve_with_kernel_source(libs, name, nstep):
+    """whole load steps with the kernels' own source doing the material sweeps: Newton iteration
+    counts and the homogenised stress must be those of the pure oracle run (1e-10)"""
+    HostKernels, Oracle = libs
+    p = deck(name)
+    o_ref = Oracle(p)
+    o_ref.drive_eps_sig(1, 0)
+    r = o_ref.FFT_nr3(nstep=nstep)
+    assert r["rc"] == 0
+    k, o = HostKernels(p), Oracle(p)
+    nr, pbar = _hybrid_FFT_nr3(k, o, p, nstep)
+    assert nr == [int(v) for v in r["nr_iters"]]
+    # mts_mm10.in: slowly converging Newton loop (DESIGN.md 4), round-off differences of the two
+    # implementations are amplified to 2e-10 on the curve; the other decks meet 1e-10
+    assert np.abs(pbar - r["Pbar"]).max() / np.abs(r["Pbar"]).max() <= (1e-9 if name == "mts_mm10.in" else 1e-10)
+    assert relerr(k.Fn1, o_ref.Fn1) <= (1e-8 if name == "mts_mm10.in" else 1e-9)
