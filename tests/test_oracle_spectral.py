@@ -167,3 +167,39 @@ def test_reference_table_is_broken_for_even_N():
         g = _grad_field(N, rng, kmax=1)
         err = np.abs(ref_G_K_dF(N, g) - g).max() / np.abs(g).max()
         assert (err <= 1e-12) == ok
+
+
+def conv_G_K_dF(N, F, K4=None):
+    """The documented even-N convention stated WITHOUT the phase ramp: plain 3-D FFT, signed integer
+    frequencies xi = -N/2+1 .. N/2-1, Ghat_ijkl = delta_ik xi_j xi_l / |xi|^2, zero at xi = 0 and on the
+    three Nyquist planes.  (For odd N this is algebraically the reference's operator.)"""
+    x = F.T if K4 is None else ref_ddot42n(K4.T, F.T)
+    xi1 = np.fft.fftfreq(N, d=1.0 / N)
+    xi = np.stack(np.meshgrid(xi1, xi1, xi1, indexing="ij"), axis=-1).reshape(-1, 3)
+    qq = (xi * xi).sum(axis=1)
+    nyq = (np.abs(xi) == N / 2).any(axis=1) if N % 2 == 0 else np.zeros(len(xi), bool)
+    zero = nyq | (qq == 0)
+    X = np.stack([np.fft.fftn(x[:, c].reshape(N, N, N)).ravel() for c in range(9)], axis=1).reshape(-1, 3, 3)
+    # out_ij = xi_j (sum_l xi_l X_il) / |xi|^2
+    s = np.einsum("eil,el->ei", X, xi)
+    s[~zero] /= qq[~zero, None]
+    s[zero] = 0.0
+    Y = (s[:, :, None] * xi[:, None, :]).reshape(-1, 9)
+    out = np.stack([np.fft.ifftn(Y[:, c].reshape(N, N, N)).real.ravel() for c in range(9)], axis=1)
+    return out.T
+
+
+@pytest.mark.parametrize("N", [5, 6, 8, 9, 12, 16])
+def test_G_K_dF_matches_plain_fft_statement_of_the_convention(Oracle, N):
+    p = _toy_problem(N)
+    o = Oracle(p)
+    rng = np.random.default_rng(N)
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += 0.02 * rng.standard_normal((9, p.N3))
+    o.Fn1[:] = F
+    o.drive_eps_sig(1, 1)
+    x = rng.standard_normal((9, p.N3))
+    for flgK in (0, 1):
+        got = o.G_K_dF(x, flgK)
+        want = conv_G_K_dF(N, x, o.K4.copy() if flgK else None)
+        assert np.abs(got - want).max() <= 5e-13 * np.abs(want).max(), (N, flgK)
