@@ -19,9 +19,11 @@
  *
  * PARITY UNPINNED: the reference ships no golden vectors, no tests and cannot
  * be built here (ifort + MKL).  The oracle is pinned only by derived
- * identities (tests/test_oracle_*.py): Green-operator projection identities,
- * finite-difference checks of cep2A / cnst1 / mm10_tangent, homogeneous-deck
- * behaviour and an independent numpy restatement of the kinematics.
+ * identities (tests/test_oracle_*.py, tests/test_py_mm10.py): Green-operator
+ * projection identities, independent numpy restatements of G_K_dF and of the
+ * mm10 / Voce crystal update (same Newton iteration counts), finite-difference
+ * checks of cep2A / cnst1 / the local Jacobian / mm10_tangent, the degenerate
+ * case MTS == Voce, homogeneous-deck behaviour.
  */
 #ifndef CPFFT_ORACLE_H
 #define CPFFT_ORACLE_H

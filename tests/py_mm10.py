@@ -1,0 +1,245 @@
+"""A second, independent restatement of the reference's crystal-plasticity update for ONE crystal with
+Voce hardening, in plain numpy, written routine by routine from the Fortran (SURVEY.md 8c item 6,
+"oracle vs oracle").  TEST INFRASTRUCTURE ONLY.  It shares no code with oracle/ (C++) or with the CUDA
+sources: the stiffness and Schmid tensors are built with numpy linear algebra, the Jacobian is
+assembled with outer products, the linear solves are numpy.linalg.solve.
+
+  setup_mm10_rknstr      drive_eps_sig.f:537-1002   -> crystal_setup
+  mm10_setup(+_voche)    mm10_a.f:830-962, 2057-2075 -> step_setup
+  mm10_formR1 / R2       mm10_b.f:1065-1101, 63-113  -> residual
+  mm10_formJ11/12/21/22  mm10_b.f:177-481            -> jacobian
+  mm10_solve             mm10_a.f:2860-3295          -> solve
+  mm10_solve_strup       mm10_a.f:2628-2845          -> update
+  mm10_tangent           mm10_a.f:658-815            -> tangent (lagged Jacobian, symmetrised)
+  mm10_update_rotation   mm10_a.f:3310-3414          -> Rp
+"""
+import numpy as np
+
+VOIGT = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]      # xx yy zz xy yz xz
+
+
+def kocks(ang_deg):                                            # mm10_a.f:1287-1345
+    psi, th, phi = np.deg2rad(ang_deg)
+    return np.array([
+        [-np.sin(psi) * np.sin(phi) - np.cos(psi) * np.cos(phi) * np.cos(th),
+         np.cos(psi) * np.sin(phi) - np.sin(psi) * np.cos(phi) * np.cos(th), np.cos(phi) * np.sin(th)],
+        [np.sin(psi) * np.cos(phi) - np.cos(psi) * np.sin(phi) * np.cos(th),
+         -np.cos(psi) * np.cos(phi) - np.sin(psi) * np.sin(phi) * np.cos(th), np.sin(phi) * np.sin(th)],
+        [np.cos(psi) * np.sin(th), np.sin(psi) * np.sin(th), np.cos(th)]])
+
+
+def sym6(T, eng):
+    """symmetric tensor -> Voigt 6-vector (engineering shear when `eng`)"""
+    f = 2.0 if eng else 1.0
+    return np.array([T[0, 0], T[1, 1], T[2, 2], f * T[0, 1], f * T[1, 2], f * T[0, 2]])
+
+
+def ten(v, eng):
+    f = 0.5 if eng else 1.0
+    return np.array([[v[0], f * v[3], f * v[5]], [f * v[3], v[1], f * v[4]], [f * v[5], f * v[4], v[2]]])
+
+
+def skew3(W):
+    """wv = (w23, w13, w12) (mm10_a.f:1529-1531)"""
+    return np.array([W[1, 2], W[0, 2], W[0, 1]])
+
+
+def skewt(w):
+    return np.array([[0, w[2], w[1]], [-w[2], 0, w[0]], [-w[1], -w[0], 0.0]])
+
+
+def stiffness_isotropic(e, nu):
+    """engineering-shear 6x6 stiffness = inverse of the compliance (mod_crystals.f:1793-1931)"""
+    S = np.zeros((6, 6))
+    S[:3, :3] = -nu / e
+    S[np.arange(3), np.arange(3)] = 1.0 / e
+    S[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e
+    return np.linalg.inv(S)
+
+
+def rot6_stress(Q):
+    """6x6 operator of T -> Q T Q^T on stress-type Voigt vectors (mm10_RT2RVE, mm10_a.f:1400-1447)"""
+    M = np.zeros((6, 6))
+    for J, (k, l) in enumerate(VOIGT):
+        E = np.zeros((3, 3)); E[k, l] = E[l, k] = 1.0
+        M[:, J] = sym6(Q @ E @ Q.T, False)
+    return M
+
+
+class Crystal:
+    def __init__(self, b, n, C6, angles, rate_n, theta_0, tau_y, tau_v, voche_m=1.0, iD_v=0.0, miter=30,
+                 atol=1e-5, atol1=1e-5, rtol=5e-5, rtol1=1e-5):
+        g = kocks(angles)
+        self.g = g
+        bs, ns = b @ g, n @ g                                   # g^T applied to the crystal-frame vectors
+        self.M0 = [0.5 * (np.outer(x, y) + np.outer(y, x)) for x, y in zip(bs, ns)]     # sym Schmid tensors
+        self.W0 = [0.5 * (np.outer(x, y) - np.outer(y, x)) for x, y in zip(bs, ns)]     # skew parts
+        R6 = rot6_stress(g.T)
+        self.C = R6 @ C6 @ R6.T                                 # stiffness in the RVE frame
+        self.n, self.theta_0, self.tau_y, self.tau_v, self.m, self.iD_v = rate_n, theta_0, tau_y, tau_v, voche_m, iD_v
+        self.miter, self.atol, self.atol1, self.rtol, self.rtol1 = miter, atol, atol1, rtol, rtol1
+
+
+def rvw(rt):
+    """mm10_rt2rvw (mm10_a.f:1461-1479): rotates the (w23, w13, w12) skew vectors"""
+    return np.array([
+        [rt[1, 1] * rt[2, 2] - rt[1, 2] * rt[2, 1], rt[1, 0] * rt[2, 2] - rt[1, 2] * rt[2, 0], rt[1, 0] * rt[2, 1] - rt[1, 1] * rt[2, 0]],
+        [rt[0, 1] * rt[2, 2] - rt[0, 2] * rt[2, 1], rt[0, 0] * rt[2, 2] - rt[0, 2] * rt[2, 0], rt[0, 0] * rt[2, 1] - rt[0, 1] * rt[2, 0]],
+        [rt[0, 1] * rt[1, 2] - rt[0, 2] * rt[1, 1], rt[0, 0] * rt[1, 2] - rt[0, 2] * rt[1, 0], rt[0, 0] * rt[1, 1] - rt[0, 1] * rt[1, 0]]])
+
+
+class Step:
+    """mm10_setup (mm10_a.f:830-962): current Schmid vectors, dg, tinc.  The reference rotates the
+    engineering-shear vectors ms0 with mm10_RT2RVE, which is the tensor-component (stress-type)
+    operator (mm10_a.f:1400-1447): reproduced as such."""
+    def __init__(self, cr, R, D, dt, Rpn):
+        Q = Rpn.T
+        RE, RW, RWC = rot6_stress(Q), rvw(Q), rvw(R @ Q)
+        self.ms = [RE @ sym6(M, True) for M in cr.M0]
+        self.qs = [RW @ skew3(W) for W in cr.W0]
+        self.qc = [RWC @ skew3(W) for W in cr.W0]
+        self.D, self.tinc = np.asarray(D, float), dt
+        self.dg = np.sqrt(2.0 / 3.0 * (D[:3] @ D[:3] + 0.5 * (D[3:] @ D[3:])))
+
+
+def symsw(s, w):
+    """mm10_symSW (mm10_b.f:1505-1524)"""
+    return np.array([s[3] * w[2] - s[5] * w[1],
+                     s[3] * w[2] - s[4] * w[0],
+                     s[5] * w[1] + s[4] * w[0],
+                     0.5 * (w[2] * (s[0] - s[1]) + w[0] * s[5] - w[1] * s[4]),
+                     0.5 * (w[0] * (s[1] - s[2]) + w[1] * s[3] + w[2] * s[5]),
+                     0.5 * (w[1] * (s[0] - s[2]) + w[0] * s[3] - w[2] * s[4])])
+
+
+def slips(cr, st, sig, tt):
+    rs = np.array([sig @ m for m in st.ms])
+    return rs, st.dg / tt * np.abs(rs / tt) ** (cr.n - 1.0) * rs
+
+
+def residual(cr, st, sn, ttn, x, both=True):
+    sig, tt = x[:6], x[6]
+    rs, gam = slips(cr, st, sig, tt)
+    f = gam + rs * st.tinc * cr.iD_v
+    dbarp = sum(fi * m for fi, m in zip(f, st.ms))
+    wp = sum(fi * q for fi, q in zip(f, st.qc))
+    R1 = sig - sn - cr.C @ (st.D - dbarp) + 2.0 * symsw(sig, wp)
+    hterm = 1.0 - (tt - cr.tau_y) / cr.tau_v
+    h = ttn + cr.theta_0 * np.sum(np.abs(hterm) ** cr.m * np.sign(hterm) * np.abs(gam))
+    return np.concatenate([R1, [tt - h if both else 0.0]]), h
+
+
+def jacobian(cr, st, x):
+    sig, tt = x[:6], x[6]
+    rs, gam = slips(cr, st, sig, tt)
+    dgdt = st.dg * cr.n / tt ** cr.n * np.abs(rs) ** (cr.n - 1.0) + st.tinc * cr.iD_v
+    J = np.zeros((7, 7))
+    wvec = [cr.C @ m + 2.0 * symsw(sig, q) for m, q in zip(st.ms, st.qc)]
+    for w, m, d, g in zip(wvec, st.ms, dgdt, gam):
+        J[:6, :6] += d * np.outer(w, m)
+        J[:6, 6] += w * (-cr.n / tt * g)
+    f = gam + rs * st.tinc * cr.iD_v
+    wp = sum(fi * q for fi, q in zip(f, st.qc))
+    IW = np.zeros((6, 6))                                       # d(2 symSW(sig, wp))/d sig  (mm10_iw, mm10_b.f:1605-1634)
+    for j in range(6):
+        e = np.zeros(6); e[j] = 1.0
+        IW[:, j] = 2.0 * symsw(e, wp)
+    J[:6, :6] += IW + np.eye(6)
+    hterm = 1.0 - (tt - cr.tau_y) / cr.tau_v
+    hp = np.abs(hterm) ** cr.m
+    et = sum(hp * np.sign(hterm) * np.abs(r) ** (cr.n - 2.0) * r * m for r, m in zip(rs, st.ms))
+    J[6, :6] = -(cr.theta_0 * st.dg * cr.n / tt ** cr.n * et)
+    # reference quirk kept: sign(slipinc) in mm10_ehard_voche (mm10_b.f:1962-1975)
+    etau = np.sum((cr.m * (-1.0 / cr.tau_v) * np.abs(gam) / np.abs(hterm)
+                   - np.abs(gam) * cr.n / tt * np.sign(hterm) * np.where(gam >= 0, 1.0, -1.0)) * hp)
+    J[6, 6] = 1.0 - cr.theta_0 * etau
+    return J
+
+
+def newton(cr, st, sn, ttn, x, nun, atol, rtol, mmin, inR_fallback=None):
+    """one phase of mm10_solve: nun unknowns (6: stress predictor at fixed x[6]; 7: coupled update).
+    Armijo halving line search c = 1e-4, <= 10 halvings.  Returns x, iterations, fail, J_last, h, inR."""
+    both = (nun == 7)
+    R, h = residual(cr, st, sn, ttn, x, both)
+    nR = np.linalg.norm(R[:nun]); inR = nR
+    if both and inR == 0.0:
+        inR = inR_fallback
+    it, J = 0, None
+    while ((nR > atol) and (nR / inR > rtol)) or (it < mmin):
+        J = jacobian(cr, st, x)
+        if not both:
+            J[:6, 6] = 0.0; J[6, :6] = 0.0; J[6, 6] = 1.0
+        dx = np.zeros(7)
+        dx[:nun] = np.linalg.solve(-J[:nun, :nun], R[:nun])
+        ls1 = 0.5 * (R[:nun] @ R[:nun])
+        ls2 = 1.0e-4 * (dx[:nun] @ (J[:nun, :nun].T @ R[:nun]))
+        alpha, ls = 1.0, 0
+        while True:
+            xn = x + alpha * dx
+            R, h = residual(cr, st, sn, ttn, xn, both)
+            if 0.5 * (R[:nun] @ R[:nun]) <= ls1 + ls2 * alpha or ls > 10:
+                x = xn
+                break
+            alpha *= 0.5; ls += 1
+        nR = np.linalg.norm(R[:nun])
+        it += 1
+        if it > cr.miter or np.any(np.isnan(x)):
+            return x, it, True, J, h, inR
+    return x, it, False, J, h, inR
+
+
+def update(cr, R, D, dt, sn, ttn, ttrate_n, Dn, Rpn, iter0):
+    """mm10_solve_strup + mm10_tangent + mm10_update_rotation for one crystal.
+    Returns dict(stress, tt, tangent, Rp, slip, iters=(predictor, update), fail)."""
+    D = np.asarray(D, float)
+    full = Step(cr, R, D, dt, Rpn)
+    no_load = (sn @ sn == 0.0) and (D @ D == 0.0)
+    if iter0 or no_load:                                        # elastic predictor (mm10_a.f:2735-2751)
+        x = np.concatenate([sn, [ttn]])
+        sig = sn.copy()
+        if not no_load:
+            sig = sn - residual(cr, full, sn, ttn, x, False)[0][:6]
+        return dict(stress=sig, tt=ttn, tangent=cr.C.copy(), Rp=None, slip=None, iters=(0, 0), fail=False)
+
+    def dev_dir(d):
+        d = d.copy(); d[:3] -= d[:3].sum() / 3.0
+        nrm = np.sqrt(d @ d)
+        return d / nrm if nrm > 0 else 0.0 * d
+    cos_ang = max(dev_dir(D) @ dev_dir(np.asarray(Dn, float)), 0.0)
+    frac, stp, cuts = 0.0, 1.0, 0
+    x = np.concatenate([sn, [ttn]]); ox = x.copy()
+    itp = itu = 0
+    fail, J, h, st = False, None, ttn, full
+    while frac < 1.0:
+        sc = stp + frac
+        st = Step(cr, R, D * sc, dt * sc, Rpn)
+        x[6] = ttn
+        x0 = x.copy(); x0[6] = ttn + cos_ang * ttrate_n * (dt * stp)
+        x1, i1, f1, _, _, inR1 = newton(cr, st, sn, ttn, x0, 6, cr.atol1, cr.rtol1, 0)
+        itp += i1
+        xs = x.copy() if f1 else x1                              # a failed predictor leaves x untouched; update still runs
+        x2, i2, f2, J2, h, _ = newton(cr, st, sn, ttn, xs, 7, cr.atol, cr.rtol, 1, inR1)
+        itu += i2
+        J = J2
+        if f1 or f2:
+            x = ox.copy(); stp *= 0.5; cuts += 1
+            if cuts > 4:
+                fail = True
+                break
+        else:
+            x = x2; ox = x.copy(); frac += stp
+    if fail or np.any(np.isnan(x)):
+        return dict(stress=sn.copy(), tt=ttn, tangent=cr.C.copy(), Rp=Rpn.copy(), slip=None, iters=(itp, itu), fail=True)
+    # tangent from the LAGGED Jacobian of the last sub-step (mm10_a.f:1137), Voce: JA = JB = 0
+    JJ = J[:6, :6] - np.outer(J[:6, 6], J[6, :6]) / J[6, 6]
+    T = np.linalg.solve(JJ, cr.C)
+    T = 0.5 * (T + T.T)
+    sig, tt = x[:6], x[6]
+    rs, gam = slips(cr, full, sig, tt)
+    f = gam + rs * dt * cr.iD_v
+    wbar = sum(fi * q for fi, q in zip(f, full.qs))
+    W = skewt(wbar)
+    al = np.sqrt(W[1, 2] ** 2 + W[0, 2] ** 2 + W[0, 1] ** 2)
+    ex = np.eye(3) if al < 1e-16 else np.eye(3) + (1.0 - np.cos(al)) / al ** 2 * (W @ W) + np.sin(al) / al * W
+    return dict(stress=sig, tt=tt, tangent=T, Rp=ex @ Rpn, slip=f, iters=(itp, itu), fail=False,
+                tt_rate=(h - ttn) / st.tinc)
