@@ -12,6 +12,8 @@ assembled with outer products, the linear solves are numpy.linalg.solve.
   mm10_solve_strup       mm10_a.f:2628-2845          -> update
   mm10_tangent           mm10_a.f:658-815            -> tangent (lagged Jacobian, symmetrised)
   mm10_update_rotation   mm10_a.f:3310-3414          -> Rp
+  MTS hardening          mm10_a.f:2090-2175 (init / setup), mm10_b.f:2080-2345 (h, estress, ehard, ed,
+                         dgdt, dgdh, dgdd), tangent terms JA / JB mm10_a.f:740-810 -> `mts=` branches
 """
 import numpy as np
 
@@ -78,6 +80,7 @@ class Crystal:
         self.C = R6 @ C6 @ R6.T                                 # stiffness in the RVE frame
         self.n, self.theta_0, self.tau_y, self.tau_v, self.m, self.iD_v = rate_n, theta_0, tau_y, tau_v, voche_m, iD_v
         self.miter, self.atol, self.atol1, self.rtol, self.rtol1 = miter, atol, atol1, rtol, rtol1
+        self.mts = None        # dict of the MTS parameters when `hardening mts`
 
 
 def rvw(rt):
@@ -100,6 +103,24 @@ class Step:
         self.qc = [RWC @ skew3(W) for W in cr.W0]
         self.D, self.tinc = np.asarray(D, float), dt
         self.dg = np.sqrt(2.0 / 3.0 * (D[:3] @ D[:3] + 0.5 * (D[3:] @ D[3:])))
+
+    def setup_mts(self, cr, temp, n):
+        """mm10_setup_mts (mm10_a.f:2109-2175); n = dict(tt, u1, u2) of the n state (modified: flags < 0
+        are replaced by the values of this step)"""
+        m = cr.mts
+        dgc = self.dg / self.tinc
+        self.temp = temp
+        self.mu = m["mu_0"] if temp == 0.0 else m["mu_0"] - m["D_0"] / (np.exp(m["T_0"] / temp) - 1.0)
+        if dgc == 0.0:
+            self.tau_v, self.tau_y = m["tau_hat_v"], m["tau_hat_y"]
+        else:
+            kT = m["boltz"] * temp / (self.mu * m["b"] ** 3)
+            self.tau_v = m["tau_hat_v"] * (1.0 - (kT / m["G_0_v"] * np.log(m["eps_dot_0_v"] / dgc)) ** (1.0 / m["q_v"])) ** (1.0 / m["p_v"])
+            self.tau_y = m["tau_hat_y"] * (1.0 - (kT / m["G_0_y"] * np.log(m["eps_dot_0_y"] / dgc)) ** (1.0 / m["q_y"])) ** (1.0 / m["p_y"])
+        self.tau_y_n = self.tau_y if n["u1"] < 0.0 else n["u1"]
+        self.mu_n = self.mu if n["u2"] < 0.0 else n["u2"]
+        if n["tt"] < 0.0:
+            n["tt"] = m["tau_a"] + (self.mu / m["mu_0"]) * self.tau_y + 0.1
 
 
 def symsw(s, w):
@@ -124,9 +145,18 @@ def residual(cr, st, sn, ttn, x, both=True):
     dbarp = sum(fi * m for fi, m in zip(f, st.ms))
     wp = sum(fi * q for fi, q in zip(f, st.qc))
     R1 = sig - sn - cr.C @ (st.D - dbarp) + 2.0 * symsw(sig, wp)
+    if not both:
+        return np.concatenate([R1, [0.0]]), ttn
+    if cr.mts:                                                  # mm10_h_mts (mm10_b.f:2080-2111), tau_l = 0
+        m = cr.mts
+        cta = (m["mu_0"] / st.mu) * tt - (m["mu_0"] / st.mu) * m["tau_a"] - st.tau_y
+        ct = 1.0 - cta / st.tau_v
+        h = (m["tau_a"] * (1.0 - st.mu / st.mu_n) + (st.mu / m["mu_0"]) * (st.tau_y - st.tau_y_n) + (st.mu / st.mu_n) * ttn
+             + cr.theta_0 * (st.mu / m["mu_0"]) * np.sum(ct ** cr.m * np.abs(gam)))
+        return np.concatenate([R1, [tt - h]]), h
     hterm = 1.0 - (tt - cr.tau_y) / cr.tau_v
     h = ttn + cr.theta_0 * np.sum(np.abs(hterm) ** cr.m * np.sign(hterm) * np.abs(gam))
-    return np.concatenate([R1, [tt - h if both else 0.0]]), h
+    return np.concatenate([R1, [tt - h]]), h
 
 
 def jacobian(cr, st, x):
@@ -145,6 +175,18 @@ def jacobian(cr, st, x):
         e = np.zeros(6); e[j] = 1.0
         IW[:, j] = 2.0 * symsw(e, wp)
     J[:6, :6] += IW + np.eye(6)
+    if cr.mts:                                                  # mm10_estress_mts / mm10_ehard_mts (mm10_b.f:2114-2186)
+        m = cr.mts
+        if not hasattr(st, "mu"):
+            return J
+        cta = (m["mu_0"] / st.mu) * tt - (m["mu_0"] / st.mu) * m["tau_a"] - st.tau_y
+        ct = 1.0 - cta / st.tau_v
+        ur = st.mu / m["mu_0"]
+        et = sum(ct ** cr.m * np.abs(r) ** (cr.n - 2.0) * r * mm for r, mm in zip(rs, st.ms))
+        J[6, :6] = -(cr.theta_0 * ur * et * cr.n * st.dg / tt ** cr.n)
+        etau = np.sum((cr.m * (1.0 / st.tau_v) / ct + ur * cr.n / tt) * ct ** cr.m * np.abs(gam))
+        J[6, 6] = 1.0 + cr.theta_0 * etau
+        return J
     hterm = 1.0 - (tt - cr.tau_y) / cr.tau_v
     hp = np.abs(hterm) ** cr.m
     et = sum(hp * np.sign(hterm) * np.abs(r) ** (cr.n - 2.0) * r * m for r, m in zip(rs, st.ms))
@@ -188,18 +230,28 @@ def newton(cr, st, sn, ttn, x, nun, atol, rtol, mmin, inR_fallback=None):
     return x, it, False, J, h, inR
 
 
-def update(cr, R, D, dt, sn, ttn, ttrate_n, Dn, Rpn, iter0):
+def update(cr, R, D, dt, sn, ttn, ttrate_n, Dn, Rpn, iter0, u1n=-1.0, u2n=-1.0):
     """mm10_solve_strup + mm10_tangent + mm10_update_rotation for one crystal.
-    Returns dict(stress, tt, tangent, Rp, slip, iters=(predictor, update), fail)."""
+    Returns dict(stress, tt, tangent, Rp, slip, iters=(predictor, update), fail[, u1, u2]).
+    MTS: ttn, u1n, u2n are the raw history values (< 0 = flags of mm10_init_mts)."""
     D = np.asarray(D, float)
     full = Step(cr, R, D, dt, Rpn)
+    nst = dict(tt=ttn, u1=u1n, u2=u2n)
+    tt_raw = ttn
+    if cr.mts:
+        full.setup_mts(cr, 297.0, nst)                           # may replace the tau_tilde flag
+        ttn = nst["tt"]
     no_load = (sn @ sn == 0.0) and (D @ D == 0.0)
     if iter0 or no_load:                                        # elastic predictor (mm10_a.f:2735-2751)
-        x = np.concatenate([sn, [ttn]])
+        # tt was copied before mm10_setup ran (mm10_a.f:2674-2677): the raw n value, flag included
+        x = np.concatenate([sn, [tt_raw]])
         sig = sn.copy()
         if not no_load:
-            sig = sn - residual(cr, full, sn, ttn, x, False)[0][:6]
-        return dict(stress=sig, tt=ttn, tangent=cr.C.copy(), Rp=None, slip=None, iters=(0, 0), fail=False)
+            sig = sn - residual(cr, full, sn, tt_raw, x, False)[0][:6]
+        out = dict(stress=sig, tt=tt_raw, tangent=cr.C.copy(), Rp=None, slip=None, iters=(0, 0), fail=False)
+        if cr.mts:
+            out.update(u1=full.tau_y, u2=full.mu)
+        return out
 
     def dev_dir(d):
         d = d.copy(); d[:3] -= d[:3].sum() / 3.0
@@ -213,6 +265,8 @@ def update(cr, R, D, dt, sn, ttn, ttrate_n, Dn, Rpn, iter0):
     while frac < 1.0:
         sc = stp + frac
         st = Step(cr, R, D * sc, dt * sc, Rpn)
+        if cr.mts:
+            st.setup_mts(cr, 297.0 * sc, nst)                    # curr%temp = 297 (step + frac): n%temp = 0 (mm10_a.f:2769)
         x[6] = ttn
         x0 = x.copy(); x0[6] = ttn + cos_ang * ttrate_n * (dt * stp)
         x1, i1, f1, _, _, inR1 = newton(cr, st, sn, ttn, x0, 6, cr.atol1, cr.rtol1, 0)
@@ -229,17 +283,43 @@ def update(cr, R, D, dt, sn, ttn, ttrate_n, Dn, Rpn, iter0):
         else:
             x = x2; ox = x.copy(); frac += stp
     if fail or np.any(np.isnan(x)):
-        return dict(stress=sn.copy(), tt=ttn, tangent=cr.C.copy(), Rp=Rpn.copy(), slip=None, iters=(itp, itu), fail=True)
+        return dict(stress=sn.copy(), tt=ttn, tangent=cr.C.copy(), Rp=Rpn.copy(), slip=None, iters=(itp, itu), fail=True,
+                    u1=u1n, u2=u2n)
     # tangent from the LAGGED Jacobian of the last sub-step (mm10_a.f:1137), Voce: JA = JB = 0
-    JJ = J[:6, :6] - np.outer(J[:6, 6], J[6, :6]) / J[6, 6]
-    T = np.linalg.solve(JJ, cr.C)
-    T = 0.5 * (T + T.T)
     sig, tt = x[:6], x[6]
     rs, gam = slips(cr, full, sig, tt)
+    JR = cr.C.copy()
+    if cr.mts:                                                  # mm10_dgdd_mts, mm10_ed_mts at the converged state, full step
+        m = cr.mts
+        d_mod = D.copy(); d_mod[3:] *= 0.5
+        alpha = 2.0 / (3.0 * full.dg ** 2)
+        JA = sum(np.outer(cr.C @ ms + 2.0 * symsw(sig, qc), alpha * g * d_mod) for ms, qc, g in zip(full.ms, full.qc, gam))
+        dgc = full.dg / full.tinc
+        kT = m["boltz"] * full.temp / (full.mu * m["b"] ** 3)
+        lny, lnv = np.log(m["eps_dot_0_y"] / dgc), np.log(m["eps_dot_0_v"] / dgc)
+        ty, tv = kT / m["G_0_y"] * lny, kT / m["G_0_v"] * lnv
+        dydd = (2.0 * m["tau_hat_y"] / (3.0 * full.dg ** 2 * m["q_y"] * m["p_y"] * lny)
+                * (1.0 - ty ** (1.0 / m["q_y"])) ** (1.0 / m["p_y"] - 1.0) * ty ** (1.0 / m["q_y"]) * d_mod)
+        dvdd = (2.0 * m["tau_hat_v"] / (3.0 * full.dg ** 2 * m["q_v"] * m["p_v"] * lnv)
+                * (1.0 - tv ** (1.0 / m["q_v"])) ** (1.0 / m["p_v"] - 1.0) * tv ** (1.0 / m["q_v"]) * d_mod)
+        mnp0 = full.mu / m["mu_0"]
+        sc_ = tt / mnp0 - m["tau_a"] / mnp0 - full.tau_y
+        base = 1.0 - sc_ / full.tau_v
+        ed = sum((cr.m / full.tau_v * base ** (cr.m - 1.0) * dydd + cr.m / full.tau_v ** 2 * sc_ * base ** (cr.m - 1.0) * dvdd
+                  + 2.0 / (3.0 * full.dg ** 2) * base ** cr.m * d_mod) * abs(g) for g in gam)
+        ed = cr.theta_0 * mnp0 * ed + mnp0 * dydd
+        JB = np.outer(J[:6, 6], ed) / J[6, 6]
+        JR = cr.C - JA - JB
+    JJ = J[:6, :6] - np.outer(J[:6, 6], J[6, :6]) / J[6, 6]
+    T = np.linalg.solve(JJ, JR)
+    T = 0.5 * (T + T.T)
     f = gam + rs * dt * cr.iD_v
     wbar = sum(fi * q for fi, q in zip(f, full.qs))
     W = skewt(wbar)
     al = np.sqrt(W[1, 2] ** 2 + W[0, 2] ** 2 + W[0, 1] ** 2)
     ex = np.eye(3) if al < 1e-16 else np.eye(3) + (1.0 - np.cos(al)) / al ** 2 * (W @ W) + np.sin(al) / al * W
-    return dict(stress=sig, tt=tt, tangent=T, Rp=ex @ Rpn, slip=f, iters=(itp, itu), fail=False,
-                tt_rate=(h - ttn) / st.tinc)
+    out = dict(stress=sig, tt=tt, tangent=T, Rp=ex @ Rpn, slip=f, iters=(itp, itu), fail=False,
+               tt_rate=(h - ttn) / st.tinc)
+    if cr.mts:
+        out.update(u1=full.tau_y, u2=full.mu)
+    return out

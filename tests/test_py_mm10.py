@@ -89,3 +89,65 @@ def test_oracle_matches_numpy_restatement(Oracle, slip_type, iD_v):
         o.Fn[:] = F1
         o.update()
     assert plastic_iters > 0
+
+
+def test_oracle_mts_matches_numpy_restatement(Oracle):
+    """the MTS law (thermally activated thresholds, mu(T), n-state flags, tangent terms JA / JB)"""
+    from cpfft_b200.polycrystal import polycrystal
+    from test_oracle_mts import mts_crystal
+    p = polycrystal(2, ngrains=4)
+    c = mts_crystal()
+    p.crystals = [c]
+    o = Oracle(p)
+    b, n = Oracle.slip_table(1)
+    C6 = py_mm10.stiffness_isotropic(c.e, c.nu)
+    L = mm10_layout(12)
+    N3 = p.N3
+    rng = np.random.default_rng(21)
+    I = np.zeros((9, N3)); I[[0, 4, 8]] = 1.0
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = -0.35; bar[8] = -0.6; bar[1] = 0.25
+    G = rng.standard_normal((9, N3))
+    crys = []
+    for v in range(N3):
+        cr = py_mm10.Crystal(b, n, C6, p.angles[v], c.harden_n, c.theta_0, 0.0, 0.0, c.voche_m, 0.0)
+        cr.mts = dict(tau_a=c.tau_a, tau_hat_y=c.tau_hat_y, G_0_y=c.g_0_y, tau_hat_v=c.tau_hat_v, G_0_v=c.g_0_v,
+                      p_y=c.p_y, q_y=c.q_y, p_v=c.p_v, q_v=c.q_v, boltz=c.boltzman, b=c.burgers,
+                      eps_dot_0_y=c.eps_dot_0_y, eps_dot_0_v=c.eps_dot_0_v, mu_0=c.mu_0, D_0=c.D_0, T_0=c.T_0)
+        crys.append(cr)
+    state = [dict(sn=np.zeros(6), tt=-1.0, u1=-1.0, u2=-1.0, ttrate=0.0, Dn=np.zeros(6), Rp=np.eye(3)) for _ in range(N3)]
+    o.drive_eps_sig(1, 0)
+    u0 = L["u"][0]
+    plastic = 0
+    for step in (1, 2, 3):
+        for it, frac in ((0, 0.9), (1, 1.0)):
+            F1 = I + 0.003 * (step - 1 + frac) * (bar + 0.15 * G)
+            o.Fn1[:] = F1
+            nfail = o.drive_eps_sig(step, it)
+            flags = np.ctypeslib.as_array(o.L.orc_fail_flags(o.h), shape=(o.N3,)).copy()
+            for v in range(N3):
+                h = o.hist_n1[v]
+                R = h[L["R"][0]:L["R"][1]].reshape(3, 3).T
+                d = h[L["D"][0]:L["D"][1]].copy()
+                st = state[v]
+                r = py_mm10.update(crys[v], R, d, p.tstep, st["sn"], st["tt"], st["ttrate"], st["Dn"], st["Rp"], it == 0,
+                                   st["u1"], st["u2"])
+                scale = max(np.abs(h[L["stress"][0]:L["stress"][1]]).max(), 1.0)
+                assert np.abs(r["stress"] - h[L["stress"][0]:L["stress"][1]]).max() <= 2e-9 * scale, (step, it, v)
+                assert abs(r["tt"] - h[L["tau_tilde"][0]]) <= 1e-9 * abs(h[L["tau_tilde"][0]]), (step, it, v)
+                assert abs(r["u1"] - h[u0]) <= 1e-11 * abs(h[u0]) and abs(r["u2"] - h[u0 + 1]) <= 1e-11 * abs(h[u0 + 1])
+                T = h[0:36].reshape(6, 6).T
+                assert np.abs(r["tangent"] - T).max() <= 1e-8 * np.abs(T).max(), (step, it, v)
+                assert tuple(r["iters"]) == tuple(o.local_iters[v]), (step, it, v, r["iters"], o.local_iters[v])
+                assert bool(r["fail"]) == bool(flags[v])
+                if it > 0 and not r["fail"]:
+                    Rp = h[L["Rp"][0]:L["Rp"][1]].reshape(3, 3).T
+                    assert np.abs(r["Rp"] - Rp).max() <= 1e-10
+                    plastic += r["iters"][1]
+                st["last"] = (r, d)
+        for v in range(N3):
+            r, d = state[v]["last"]
+            state[v].update(sn=r["stress"].copy(), tt=r["tt"], u1=r["u1"], u2=r["u2"], ttrate=r.get("tt_rate", 0.0), Dn=d.copy(),
+                            Rp=r["Rp"])
+        o.Fn[:] = F1
+        o.update()
+    assert plastic > 0
