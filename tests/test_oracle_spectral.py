@@ -203,3 +203,49 @@ def test_G_K_dF_matches_plain_fft_statement_of_the_convention(Oracle, N):
         got = o.G_K_dF(x, flgK)
         want = conv_G_K_dF(N, x, o.K4.copy() if flgK else None)
         assert np.abs(got - want).max() <= 5e-13 * np.abs(want).max(), (N, flgK)
+
+
+def test_tangent_homo_is_the_derivative_of_the_mean_stress(Oracle):
+    """tangent_homo (tangent_homo.f:11-73): C_homo = d P_bar / d F_bar.  Checked by finite differences
+    of whole FFT_nr3 solves of a two-phase elastic block under F_bar = I + delta e_kl."""
+    from cpfft_b200.problem import Problem
+    base = _toy_problem(5)
+    o = Oracle(base)
+    o.drive_eps_sig(1, 0)
+    rc, C = o.tangent_homo()
+    assert rc == 0
+    C = C.reshape(9, 9)                        # row ij, column kl (FFT_init.f:283-304 ordering)
+    delta = 1.0e-6
+    fd = np.zeros((9, 9))
+    for kl in range(9):
+        cols = []
+        for sgn in (+1.0, -1.0):
+            p = Problem(**{k: getattr(base, k) for k in base.__dataclass_fields__})
+            p.FP_max = np.zeros(9); p.FP_max[kl] = sgn * delta
+            p.mults = np.ones(1); p.tolNR = 1.0e-9; p.tolPCG = 1.0e-12; p.maxIter = 20
+            q = Oracle(p)
+            q.drive_eps_sig(1, 0)
+            r = q.FFT_nr3()
+            assert r["rc"] == 0
+            cols.append(r["Pbar"][0])
+        fd[:, kl] = (cols[0] - cols[1]) / (2.0 * delta)
+    assert np.abs(C - fd).max() <= 2e-5 * np.abs(fd).max(), np.abs(C - fd).max() / np.abs(fd).max()
+    # a heterogeneous block is softer than the volume average of the phase tangents (Voigt bound)
+    voigt = o.K4.mean(axis=1).reshape(9, 9)
+    assert C[0, 0] < voigt[0, 0] and C[0, 0] > 0.5 * voigt[0, 0]
+
+
+def test_stress_boundary_conditions_are_met(Oracle):
+    """NBC_update + the stress-BC loop (FFT_nr3.f:127-165, 375-433): the prescribed mean stresses are
+    reached to the loop's own stop test, and the free strains contract (uniaxial tension)."""
+    from helpers import stress_bc_variant
+    p = stress_bc_variant(deck("test_mm01.in"))
+    o = Oracle(p)
+    o.drive_eps_sig(1, 0)
+    r = o.FFT_nr3(nstep=3)
+    assert r["rc"] == 0
+    for P in r["Pbar"]:
+        assert np.sqrt(P[4] ** 2 + P[8] ** 2) <= p.tolNR * np.linalg.norm(P)
+        assert P[0] > 0
+    Fbar = o.Fn1.mean(axis=1)
+    assert Fbar[0] > 1.0 and Fbar[4] < 1.0 and Fbar[8] < 1.0
