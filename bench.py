@@ -169,6 +169,25 @@ def algorithmic_bytes_per_voxel(cls, N, cg_frac=0.0, cg_fused_frac=0.0):
     }.get(cls)
 
 
+def workload_variant(prob, variant, ngrains):
+    """the benchmark polycrystal with another material law (kernel measurements, not the headline)"""
+    import dataclasses
+    from cpfft_b200.polycrystal import grain_angles
+    if variant == "mts":       # `hardening mts` with the thresholds of tests/golden/decks/mts_mm10.in
+        c = dataclasses.replace(prob.crystals[0], h_type=2, theta_0=1500.0, tau_a=20.0, tau_hat_y=180.0, g_0_y=0.4,
+                                tau_hat_v=300.0, g_0_v=1.2, burgers=2.5e-7, mu_0=80000.0, D_0=3000.0, T_0=200.0)
+        prob.crystals = [c]
+        return prob
+    nc = int(variant[-1])      # taylorN: N crystals per material point, further draws from the orientation table
+    table = grain_angles(ngrains + nc)
+    base = np.asarray(prob.angles)
+    key = np.abs(base[:, 0] * 1000.0).astype(np.int64) % ngrains           # one key per grain (its first Kocks angle)
+    ang = np.stack([base] + [table[(key + 7 * k) % len(table)] for k in range(1, nc)], axis=1)
+    prob.angles = np.ascontiguousarray(ang)
+    prob.materials[0].n_crystals = nc
+    return prob
+
+
 def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
     """per-kernel-class table {ms, launches, share, algorithmic bytes, achieved GB/s, fraction of the
     measured HBM peak, ncu DRAM traffic / FP64 counts when profiles/ncu_traffic.json matches} and the
@@ -220,6 +239,9 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", default="voce", choices=["voce", "mts", "taylor2", "taylor4"],
+                    help="workload variant for kernel measurements (NOT the BASELINE.json metric unless 'voce'): "
+                         "MTS hardening law, or 2 / 4 crystals per material point (Taylor average)")
     ap.add_argument("--stress-bc", action="store_true",
                     help="uniaxial tension with P_yy = P_zz = 0 (stress-BC loop, tangent_homo) instead of pure strain control")
     args = ap.parse_args()
@@ -251,6 +273,8 @@ def main():
     nx = N // world
     prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + 2 * K + 2), x_range=(rank * nx, (rank + 1) * nx),
                        stress_bc=args.stress_bc)
+    if args.variant != "voce":
+        prob = workload_variant(prob, args.variant, args.grains)
     s = Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=nccl_id, local_slab=True)
     stream = torch.cuda.ExternalStream(s.stream())
 
@@ -346,7 +370,8 @@ def main():
         "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal ({args.grains} random-orientation fcc grains, "
-                               "mm10/Voce), finite-strain uniaxial tension, " +
+                               f"mm10/{ {'voce': 'Voce', 'mts': 'MTS (variant, not the BASELINE metric)'}.get(args.variant, 'Voce, ' + args.variant[-1] + ' crystals per point (variant, not the BASELINE metric)') }), "
+                               "finite-strain uniaxial tension, " +
                                ("F_xx driven with P_yy = P_zz = 0" if args.stress_bc else "strain-controlled") + ", 0.1 % per load step",
                    "grid": N, "voxels": int(nvox), "voxels_per_gpu": int(s.n3), "parallelism": f"x-slabs x{world}",
                    "l2": "working set (>= 1.2 GB per field) far exceeds the 126 MB L2; no flush needed",
