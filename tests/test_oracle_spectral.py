@@ -249,3 +249,36 @@ def test_stress_boundary_conditions_are_met(Oracle):
         assert P[0] > 0
     Fbar = o.Fn1.mean(axis=1)
     assert Fbar[0] > 1.0 and Fbar[4] < 1.0 and Fbar[8] < 1.0
+
+
+def test_fftPcg_matches_a_textbook_cg(Oracle):
+    """fftPcg (FFT_nr3.f:214-360, MKL RCI dcg with the user stop test ||r|| <= tol ||b|| or ||r|| <= tol
+    checked before every iteration): same iteration count and solution as a plain numpy CG on the
+    same operator."""
+    p = _toy_problem(7)
+    o = Oracle(p)
+    rng = np.random.default_rng(2)
+    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+    F += 0.002 * rng.standard_normal((9, p.N3))
+    o.Fn1[:] = F
+    o.drive_eps_sig(1, 1)
+    b = -o.G_K_dF(rng.standard_normal((9, p.N3)), 1)
+    tol = 1e-9
+    rc, x, it, rr = o.fftPcg(b, tol)
+    assert rc == 0
+    xs = np.zeros_like(b); r = b.copy(); pvec = None; rr_old = None; k = 0
+    nb = np.linalg.norm(b)
+    while True:
+        rn = np.linalg.norm(r)
+        if rn <= tol * nb or rn <= tol:
+            break
+        rho = float((r * r).sum())
+        pvec = r.copy() if pvec is None else r + (rho / rr_old) * pvec
+        q = o.G_K_dF(pvec, 1)
+        alpha = rho / float((pvec * q).sum())
+        xs += alpha * pvec; r -= alpha * q
+        rr_old = rho; k += 1
+        assert k < 1000
+    assert k == it and 5 < it < 200
+    assert np.abs(xs - x).max() <= 1e-10 * np.abs(x).max()
+    assert abs(rr - rn / nb) <= 1e-6 * rr
