@@ -169,25 +169,6 @@ def algorithmic_bytes_per_voxel(cls, N, cg_frac=0.0, cg_fused_frac=0.0):
     }.get(cls)
 
 
-def workload_variant(prob, variant, ngrains):
-    """the benchmark polycrystal with another material law (kernel measurements, not the headline)"""
-    import dataclasses
-    from cpfft_b200.polycrystal import grain_angles
-    if variant == "mts":       # `hardening mts` with the thresholds of tests/golden/decks/mts_mm10.in
-        c = dataclasses.replace(prob.crystals[0], h_type=2, theta_0=1500.0, tau_a=20.0, tau_hat_y=180.0, g_0_y=0.4,
-                                tau_hat_v=300.0, g_0_v=1.2, burgers=2.5e-7, mu_0=80000.0, D_0=3000.0, T_0=200.0)
-        prob.crystals = [c]
-        return prob
-    nc = int(variant[-1])      # taylorN: N crystals per material point, further draws from the orientation table
-    table = grain_angles(ngrains + nc)
-    base = np.asarray(prob.angles)
-    key = np.abs(base[:, 0] * 1000.0).astype(np.int64) % ngrains           # one key per grain (its first Kocks angle)
-    ang = np.stack([base] + [table[(key + 7 * k) % len(table)] for k in range(1, nc)], axis=1)
-    prob.angles = np.ascontiguousarray(ang)
-    prob.materials[0].n_crystals = nc
-    return prob
-
-
 def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
     """per-kernel-class table {ms, launches, share, algorithmic bytes, achieved GB/s, fraction of the
     measured HBM peak, ncu DRAM traffic / FP64 counts when profiles/ncu_traffic.json matches} and the
@@ -274,6 +255,7 @@ def main():
     prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + 2 * K + 2), x_range=(rank * nx, (rank + 1) * nx),
                        stress_bc=args.stress_bc)
     if args.variant != "voce":
+        from cpfft_b200.polycrystal import workload_variant
         prob = workload_variant(prob, args.variant, args.grains)
     s = Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=nccl_id, local_slab=True)
     stream = torch.cuda.ExternalStream(s.stream())

@@ -84,3 +84,23 @@ def taylor_polycrystal(N: int, ncrystals: int = 4, ngrains: int = 1000, seed: in
         ids[:, 1::2] = 2
         p.crystal_ids = ids
     return p
+
+
+def workload_variant(prob, variant, ngrains):
+    """the benchmark polycrystal (possibly one rank's slab of it) with another material law: ``mts`` or
+    ``taylorN`` = N crystals per material point.  For kernel measurements and the multi-GPU self-check,
+    not the headline workload."""
+    import dataclasses
+    if variant == "mts":       # `hardening mts` with the thresholds of tests/golden/decks/mts_mm10.in
+        c = dataclasses.replace(prob.crystals[0], h_type=2, theta_0=1500.0, tau_a=20.0, tau_hat_y=180.0, g_0_y=0.4,
+                                tau_hat_v=300.0, g_0_v=1.2, burgers=2.5e-7, mu_0=80000.0, D_0=3000.0, T_0=200.0)
+        prob.crystals = [c]
+        return prob
+    nc = int(variant[-1])      # taylorN: N crystals per material point, further draws from the orientation table
+    table = grain_angles(ngrains + nc)
+    base = np.asarray(prob.angles)
+    key = np.abs(base[:, 0] * 1000.0).astype(np.int64) % ngrains           # one key per grain (its first Kocks angle)
+    ang = np.stack([base] + [table[(key + 7 * k) % len(table)] for k in range(1, nc)], axis=1)
+    prob.angles = np.ascontiguousarray(ang)
+    prob.materials[0].n_crystals = nc
+    return prob

@@ -24,11 +24,12 @@ def main():
     ap.add_argument("--grid", type=int, default=32)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--grains", type=int, default=40)
+    ap.add_argument("--variant", default="voce", choices=["voce", "mts", "taylor2", "taylor4"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
     from cpfft_b200 import Solver
-    from cpfft_b200.polycrystal import polycrystal
+    from cpfft_b200.polycrystal import polycrystal, workload_variant
     from cpfft_b200.dist import broadcast_nccl_id, slab_range
 
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"])
@@ -38,6 +39,8 @@ def main():
     N = args.grid
     x0, x1 = slab_range(N, rank, world)
     p_loc = polycrystal(N, ngrains=args.grains, x_range=(x0, x1))
+    if args.variant != "voce":
+        p_loc = workload_variant(p_loc, args.variant, args.grains)
     s = Solver(p_loc, device=lr, rank=rank, world=world, nccl_id=nccl_id, local_slab=True)
     s.drive_eps_sig(1, 0)
     r = s.FFT_nr3(nstep=args.steps)
@@ -49,6 +52,8 @@ def main():
     if rank == 0:
         Pm = torch.cat(Pl, dim=1).cpu().numpy(); Fm = torch.cat(Fl, dim=1).cpu().numpy()
         p = polycrystal(N, ngrains=args.grains)
+        if args.variant != "voce":
+            p = workload_variant(p, args.variant, args.grains)
         s1 = Solver(p, device=lr)
         s1.drive_eps_sig(1, 0)
         r1 = s1.FFT_nr3(nstep=args.steps)
