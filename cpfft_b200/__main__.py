@@ -30,15 +30,33 @@ def main(argv=None):
     s = Solver(prob, device=args.device)
     t0 = time.time()
     s.drive_eps_sig(1, 0)
+    # the reference's three wall-time buckets (thyme.f:15-47): 1 pcg, 2 sig-eps, 3 patran output
+    times = [[0.0, 0], [0.0, 0], [0.0, 0]]
     for step in range(1, nstep + 1):
         r = s.FFT_nr3(nstep=1, first=step - 1)
         sys.stdout.write(r["log"])
+        times[0][0] += float(r["buckets"][0]); times[0][1] += len(r["cg_iters"][0])
+        times[1][0] += float(r["buckets"][1]); times[1][1] += int(r["counters"][1])
         if step in prob.out_steps:
+            t_out = time.time()
             write_step(args.outdir, step, s.download("URCS_N1", 1), s.download("EPS_N1", 1), prob.name, prob.N)
+            times[2][0] += time.time() - t_out; times[2][1] += 1
             print(f"       results of step {step} written to {args.outdir}")
     fails = s.material_failures()[0]
     print(f"\n >> analysis done: {nstep} steps, {time.time() - t0:.2f} s, mm10 local failures {fails}")
+    print_timings(times, time.time() - t0)
     return 0
+
+
+def print_timings(times, total):
+    """the exit summary of outime (outime.f:29-49, formats 9000-9020)"""
+    print("\n\n\n\n >>>>>  solution timings   <<<<<")
+    labels = ("pcg solution vector update:   ", "sig-eps & internal force:     ", "patran output:                ")
+    for label, (secs, calls) in zip(labels, times):
+        if calls < 0.01:
+            continue
+        print(f"\n\n  calculations for {label}")
+        print(f"\n   wall time (secs): {secs:10.4f}{100.0 * secs / max(total, 1e-30):5.1f} (%) no. calls: {calls:8d}")
 
 
 if __name__ == "__main__":

@@ -139,3 +139,14 @@ def test_mts_crystal_keywords():
     assert (c.burgers, c.boltzman, c.eps_dot_0_y, c.eps_dot_0_v) == (2.5e-7, 1.3806e-20, 1.0e10, 1.0e10)
     assert (c.p_y, c.q_y, c.p_v, c.q_v, c.mu_0, c.D_0, c.T_0) == (0.5, 2.0, 0.5, 2.0, 80000.0, 3000.0, 200.0)
     assert c.theta_0 == 1500.0 and c.harden_n == 20.0
+
+
+def test_cli_timing_summary_format(capsys):
+    """the three thyme() buckets printed like outime (outime.f:29-49)"""
+    from cpfft_b200.__main__ import print_timings
+    print_timings([[1.2345, 12], [0.5, 30], [0.0, 0]], 2.0)
+    out = capsys.readouterr().out
+    assert ">>>>>  solution timings   <<<<<" in out
+    assert "calculations for pcg solution vector update:" in out and "sig-eps & internal force:" in out
+    assert "patran output" not in out                       # buckets without calls are skipped
+    assert "wall time (secs):     1.2345 61.7 (%) no. calls:       12" in out
