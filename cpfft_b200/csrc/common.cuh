@@ -36,7 +36,7 @@ struct cpfft_handle {
   bool fast_pow2;            // spectral_pow2.cu handles this grid
   bool cg_fuse_x;            // CG: solution update x += alpha p fused into the next forward z pass (k_fz MODE 3)
   int iz_lpc;                // grid lines per CTA of k_iz_pipe
-  int iz_pipe;               // inverse z pass: 1 software-pipelined k_iz_pipe (default), 0 k_iz (CPFFT_IZ_PIPE=0)
+  int iz_pipe;               // inverse z pass: 1 k_iz_pipe with cp.async (default), 0 k_iz, 2 k_iz_pipe with TMA bulk copies (CPFFT_IZ_PIPE)
   int nxloc, x0;             // local slab
   int64_t n3;                // local voxels
   int H;                     // history comps

@@ -305,7 +305,12 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g
 // requested before the current one is touched, one CTA per SM fewer) measured 0.578 / 0.652 ms
 // and was dropped; 4, 8 or 16 lines per CTA make no difference.
 #include <cuda_pipeline.h>
-template <int N, bool DOT>
+#include <cuda/barrier>
+#include <cuda/ptx>
+// TMA = true (CPFFT_IZ_PIPE=2, NOT the default, not yet measured): the nine 2 KB rows of the next
+// line are fetched by nine 1-D bulk copies (cp.async.bulk, SASS UBLKCP) issued by one thread and
+// tracked by an mbarrier transaction count, instead of 9 LDGSTS per thread.
+template <int N, bool DOT, bool TMA = false>
 __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                                                               const double* __restrict__ pvec, double* __restrict__ partials, int64_t nlines, int lpc) {
   typedef ZSmem<N> Z;
@@ -318,19 +323,43 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz_pipe(Pow2A
   const int64_t nxN = (int64_t)g.nx * N;
   const int64_t L0 = (int64_t)blockIdx.x * lpc;          // lpc consecutive grid lines per CTA
   const int nl = (int)((nlines - L0) < lpc ? (nlines - L0) : lpc);
+  typedef cuda::barrier<cuda::thread_scope_block> barrier_t;
+#pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ barrier_t bar;
+  barrier_t::arrival_token tok;
+  if (TMA) {
+    if (threadIdx.x == 0) init(&bar, blockDim.x);
+    __syncthreads();
+  }
   auto prefetch = [&](int64_t L) {
-    for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
-      const int c = idx / H, k = idx - c * H;
-      __pipeline_memcpy_async(B + c * HB + k, spec + ((int64_t)c * nxN + L) * H + k, sizeof(cplx));
+    if constexpr (TMA) {
+      // every thread arrives; thread 0 also posts the nine bulk copies and their byte count.  All
+      // generic-proxy accesses of B by this CTA are ordered before by the barrier the caller just
+      // passed; the proxy fence orders them against the asynchronous-proxy writes that follow.
+      if (threadIdx.x == 0) {
+        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+#pragma unroll
+        for (int c = 0; c < 9; ++c)
+          cuda::device::memcpy_async_tx(B + c * HB, spec + ((int64_t)c * nxN + L) * H, cuda::aligned_size_t<16>(sizeof(cplx) * H), bar);
+        tok = cuda::device::barrier_arrive_tx(bar, 1, 9 * sizeof(cplx) * H);
+      } else {
+        tok = bar.arrive();
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
+        const int c = idx / H, k = idx - c * H;
+        __pipeline_memcpy_async(B + c * HB + k, spec + ((int64_t)c * nxN + L) * H + k, sizeof(cplx));
+      }
+      __pipeline_commit();
     }
-    __pipeline_commit();
   };
   prefetch(L0);
   const int t = threadIdx.x;
   constexpr int NP = H / 2 + 1;
   for (int il = 0; il < nl; ++il) {
     const int64_t L = L0 + il;
-    __pipeline_wait_prior(0);
+    if (TMA) bar.wait(std::move(tok));                  // all bytes of line L have landed (and every thread has arrived)
+    else __pipeline_wait_prior(0);
     __syncthreads();                                    // line L has landed for every thread (and tw on the first trip)
     const int64_t e0 = L * N + 2 * t;
     double2 pv[9];
@@ -717,7 +746,11 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   if (h->iz_pipe) {
     const int lpc = h->iz_lpc;
     const unsigned pgrid = (zgrid + lpc - 1) / lpc;
-    if (cg) { k_iz_pipe<N, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
+    if (cg) const_cast<CgFuse*>(cg)->nparts = (int)zgrid;
+    if (h->iz_pipe == 2) {      // development variant: TMA bulk copies
+      if (cg) k_iz_pipe<N, true, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
+      else k_iz_pipe<N, false, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
+    } else if (cg) k_iz_pipe<N, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
     else k_iz_pipe<N, false><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
   } else if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
   else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
@@ -743,6 +776,8 @@ static int init_pow2(cpfft_handle* h) {
   CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
   CPF_SMEM_ATTR((k_iz_pipe<N, true>), sm_z);
   CPF_SMEM_ATTR((k_iz_pipe<N, false>), sm_z);
+  CPF_SMEM_ATTR((k_iz_pipe<N, true, true>), sm_z);
+  CPF_SMEM_ATTR((k_iz_pipe<N, false, true>), sm_z);
   CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
   CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
   CPF_SMEM_ATTR((k_fyi<N>), sm_y);

@@ -36,5 +36,7 @@ case "$MODE" in
     tail -3 gpurun_out/${TAG}_ncu_update.log; ls -la gpurun_out/prof_${TAG}_update.ncu-rep ;;
   ab)
     timeout 100 python tools/ab_iz.py 256 10 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab256.log ;;
+  ab-tma)   # includes the untested TMA variant of k_iz_pipe (CPFFT_IZ_PIPE=2); own short timeout: an mbarrier bug would hang
+    AB_TMA=1 timeout 60 python tools/ab_iz.py 64 5 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab_tma64.log ;;
   *) echo "unknown mode $MODE"; exit 2 ;;
 esac
