@@ -141,7 +141,15 @@ CPF_DI void voxel_kinematics(const double* fn, const double* fn1, double* Rh, do
 // t6: unrotated Cauchy stress (Voigt), C: 6x6 [D] row-major.  Algebraically identical to
 // cep2A_a (cep2A.f:86-284) but every rank-one structure of dR/dF, dRh/dF and dL/dF is
 // contracted analytically, so the cost is O(81 * const) instead of four 81x9 loop nests.
-CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t6, const double* C,
+// C: anything indexable as C[k], k = 6 * row + col -- a register array, or StridedCep, which re-reads
+// the voxel's [D] from global memory (L1-resident: 36 x 256 B per warp) and takes its 36 values out
+// of the register budget of the 9 x 9 output loop.
+struct StridedCep {
+  const double* p; int64_t stride;
+  CPF_DI double operator[](int k) const { return CPF_LDG(p + (int64_t)k * stride); }
+};
+template <class Cep>
+CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t6, const Cep& C,
                             double* P, double* A /*81, may alias nothing*/,
                             double* __restrict__ outA, int64_t strideA) {
   double Rh[9], R[9], fh[9], df[9], fhinv[9], finv[9], t[9];

@@ -57,7 +57,14 @@ __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, c
                                                               const double* cep, double* Pn1, double* K4, int64_t n3) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n3) return;
-  upd_pk1_voxel(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
+  upd_pk1_voxel<true>(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
+}
+// development variant (CPFFT_PK1_CEP=mem): [D] re-read from memory in the output loop, see upd_pk1_voxel
+__global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent_cepmem(const double* Fn, const double* Fn1, const double* urcs_n1,
+                                                                    const double* cep, double* Pn1, double* K4, int64_t n3) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n3) return;
+  upd_pk1_voxel<false>(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -132,7 +139,9 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
       }
   }
   const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);
-  k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
+  static const bool cep_mem = [] { const char* v = getenv("CPFFT_PK1_CEP"); return v && v[0] == 'm'; }();
+  if (cep_mem) k_pk1_tangent_cepmem<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
+  else k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
   cpf_prof_end(h, tk);
   h->launches++;
   CPF_CUDA(cudaGetLastError());
