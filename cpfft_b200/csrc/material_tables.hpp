@@ -95,8 +95,12 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
     if (c.h_type != 1 && c.h_type != 2) { err = "unsupported hardening law (h_type 1 = voce, 2 = mts)"; return CPFFT_ERR_USAGE; }
     const signed char (*tb)[3]; const signed char (*tn)[3];
     if (c.slip_type == 1) { d.nslip = 12; tb = CPF_FCC_B; tn = CPF_FCC_N; }
+    else if (c.slip_type == 2) { d.nslip = 12; tb = CPF_BCC_B; tn = CPF_BCC_N; }
+    else if (c.slip_type == 3) { d.nslip = 1; tb = CPF_SINGLE_B; tn = CPF_SINGLE_N; }
+    else if (c.slip_type == 6) { d.nslip = 12; tb = CPF_ROTERS_B; tn = CPF_ROTERS_N; }
+    else if (c.slip_type == 7) { d.nslip = 12; tb = CPF_BCC12_B; tn = CPF_BCC12_N; }
     else if (c.slip_type == 8) { d.nslip = 48; tb = CPF_BCC48_B; tn = CPF_BCC48_N; }
-    else { err = "unsupported slip_type (1 = fcc, 8 = bcc48)"; return CPFFT_ERR_USAGE; }
+    else { err = "unsupported slip_type (1 fcc, 2 bcc, 3 single, 6 roters, 7 bcc12, 8 bcc48; hcp needs the ti6242 elasticity)"; return CPFFT_ERR_USAGE; }
     bi[i].resize(3 * d.nslip); ni[i].resize(3 * d.nslip);
     for (int s = 0; s < d.nslip; ++s) {
       double sb = 0, sn = 0;

@@ -112,7 +112,7 @@ def _read_crystal(lines: _Lines, toks: List[str], crystals: dict):
         if k == "slip_type":
             v = pt[i + 1]
             if v not in SLIP_TYPES:
-                raise DeckError(f"slip_type {v} not supported (fcc, bcc48)")
+                raise DeckError(f"slip_type {v} not supported (fcc, bcc, single, roters, bcc12, bcc48)")
             c.slip_type = SLIP_TYPES[v]; i += 2
         elif k == "elastic_type":
             c.elastic_type = ELASTIC_TYPES[pt[i + 1]]; i += 2

@@ -12,7 +12,7 @@ from typing import List
 import numpy as np
 
 HARDENING = {"voce": 1, "voche": 1, "mts": 2}     # incrystal.f:305-331 (supported subset)
-SLIP_TYPES = {"fcc": 1, "bcc48": 8}           # mod_crystals.f:164-172 (supported subset)
+SLIP_TYPES = {"fcc": 1, "bcc": 2, "single": 3, "roters": 6, "bcc12": 7, "bcc48": 8}   # mod_crystals.f:164-172 (cubic families; hcp6 / hcp18 not supported)
 ELASTIC_TYPES = {"isotropic": 1, "cubic": 2}  # mod_crystals.f:173-176
 COMPONENTS = ["xx", "xy", "xz", "yx", "yy", "yz", "zx", "zy", "zz"]  # inlodcase.f:29-139
 

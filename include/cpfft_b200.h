@@ -44,7 +44,7 @@ enum {
 
 /* crystal library entry, c_array(n) of mod_crystals.f:142-214 (Voce subset) */
 typedef struct {
-  int32_t slip_type;    /* 1 fcc, 8 bcc48 (mod_crystals.f:164-172)   */
+  int32_t slip_type;    /* 1 fcc, 2 bcc, 3 single, 6 roters, 7 bcc12, 8 bcc48 (mod_crystals.f:164-172) */
   int32_t elastic_type; /* 1 isotropic, 2 cubic (mod_crystals.f:173) */
   int32_t h_type;       /* 1 voce, 2 mts (incrystal.f:305-331)       */
   int32_t alter_mode;   /* mm10_a.f:2073                             */

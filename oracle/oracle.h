@@ -39,7 +39,7 @@ extern "C" {
 
 /* one entry of the crystal library c_array (mod_crystals.f:142-214), Voce subset */
 typedef struct {
-  int32_t slip_type;    /* 1 = fcc (12), 8 = bcc48 (48)  (mod_crystals.f:164-172) */
+  int32_t slip_type;    /* 1 fcc, 2 bcc, 3 single, 6 roters, 7 bcc12 (12 or 1 systems), 8 bcc48 (mod_crystals.f:164-172) */
   int32_t elastic_type; /* 1 = isotropic, 2 = cubic        (mod_crystals.f:173-176) */
   int32_t h_type;       /* 1 = voce, 2 = mts                                      */
   int32_t alter_mode;   /* mm10_a.f:2073                                          */

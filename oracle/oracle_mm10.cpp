@@ -104,6 +104,10 @@ static inline void matvec3(const M33 b, const double* c, double* a) {  // mm10_a
 void finalize_crystal(CrystalLib& c) {  // mod_crystals.f:414-1931 (fcc, bcc48; isotropic/cubic)
   const int (*tab)[6]; int n;
   if (c.in.slip_type == 1) { tab = ORC_SLIP_FCC; n = 12; }
+  else if (c.in.slip_type == 2) { tab = ORC_SLIP_BCC; n = 12; }
+  else if (c.in.slip_type == 3) { tab = ORC_SLIP_SINGLE; n = 1; }
+  else if (c.in.slip_type == 6) { tab = ORC_SLIP_ROTERS; n = 12; }
+  else if (c.in.slip_type == 7) { tab = ORC_SLIP_BCC12; n = 12; }
   else if (c.in.slip_type == 8) { tab = ORC_SLIP_BCC48; n = 48; }
   else { std::fprintf(stderr, "oracle: unsupported slip_type %d\n", c.in.slip_type); n = 0; tab = ORC_SLIP_FCC; }
   c.nslip = n;

@@ -46,6 +46,9 @@ def stress_bc_variant(prob):
     return p
 
 
+NSLIP = {1: 12, 2: 12, 3: 1, 6: 12, 7: 12, 8: 48}     # systems per slip_type (mod_crystals.f:438-1205)
+
+
 def mm10_layout(nslip, num_hard=1):
     """0-based slot ranges of the mm10 history vector (mm10_d.f:137-331)."""
     use_max = (num_hard == 48 or nslip == 48)

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from helpers import (deck, relerr, TOL_VOXEL, TOL_MACRO, mm10_variant, stress_bc_variant,
-                     compare_mm10_history, assert_same_cg_counts)
+                     compare_mm10_history, assert_same_cg_counts, NSLIP)
 
 pytestmark = pytest.mark.gpu
 
@@ -25,7 +25,7 @@ def _compare_state(s, o, hist=True, tol=TOL_VOXEL):
     if hist:
         hg = s.download("HIST_N1", 1)[:, :o.H]
         if any(m.type == 10 for m in o.prob.materials):
-            nslip = {1: 12, 8: 48}[o.prob.crystals[0].slip_type]
+            nslip = NSLIP[o.prob.crystals[0].slip_type]
             errs.update({"hist." + k: v for k, v in compare_mm10_history(hg, o.hist_n1, nslip, tol).items()})
         else:
             errs["hist_n1"] = relerr(hg, o.hist_n1)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import deck, relerr, TOL_VOXEL, compare_mm10_history
+from helpers import deck, relerr, TOL_VOXEL, compare_mm10_history, NSLIP
 
 # Small-strain tolerance: the reference's closed-form polar decomposition (polar.f:224-307) loses
 # digits when the principal stretches differ by < 3e-3; two builds of the SAME source then differ
@@ -35,7 +35,7 @@ def _compare_state(k, o, tol=TOL_VOXEL):
     }
     hk = k.hist_n1.T[:, :o.H]
     if any(m.type == 10 for m in o.prob.materials):
-        nslip = max({1: 12, 8: 48}[c.slip_type] for c in o.prob.crystals)
+        nslip = max(NSLIP[c.slip_type] for c in o.prob.crystals)
         ncry = max(m.n_crystals for m in o.prob.materials if m.type == 10)
         errs.update({"hist." + n: v for n, v in compare_mm10_history(hk, o.hist_n1, nslip, tol, ncry).items()})
     else:
@@ -160,6 +160,8 @@ def _variant_problem(kind):
         c.alter_mode = 1; c.eps_dot_0_y = 4.0e-5; c.harden_n = 5.0; p.tstep = 10.0
     elif kind == "bcc48":
         c.slip_type = 8
+    elif kind in ("bcc", "single", "roters", "bcc12"):       # the other cubic slip families (mod_crystals.f:516-811)
+        c.slip_type = {"bcc": 2, "single": 3, "roters": 6, "bcc12": 7}[kind]
     elif kind == "mixed_materials":          # mm01 and mm10 voxels in one grid (blocks break at material changes)
         p.materials.append(Material(name="iso", type=1, e=70000.0, nu=0.33, beta=0.5, tan_e=2000.0, yld_pt=150.0))
         p.matlist = p.matlist.copy(); p.matlist[::3] = 2
@@ -193,7 +195,8 @@ def _variant_problem(kind):
     return p
 
 
-VARIANTS = ["cubic_elasticity", "voce_m_2", "rate_exponent_7p5", "diffusion", "alter_mode", "bcc48", "mixed_materials",
+VARIANTS = ["cubic_elasticity", "voce_m_2", "rate_exponent_7p5", "diffusion", "alter_mode", "bcc48", "bcc", "single", "roters",
+            "bcc12", "mixed_materials",
             "two_crystal_types", "crystal_file_single", "mts", "mts_athermal", "mts_voce_m_2", "mts_and_voce", "mts_taylor"]
 
 

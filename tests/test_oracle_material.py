@@ -113,9 +113,10 @@ def test_crystal_stiffness_isotropic(Oracle):
     assert np.abs(C - want).max() <= 1e-9 * lam
 
 
-@pytest.mark.parametrize("slip_type,nslip", [(1, 12), (8, 48)])
+@pytest.mark.parametrize("slip_type,nslip", [(1, 12), (2, 12), (3, 1), (6, 12), (7, 12), (8, 48)])
 def test_slip_tables(Oracle, slip_type, nslip):
-    """unit vectors, slip direction in the slip plane; fcc = {111}<110>."""
+    """unit vectors, slip direction in the slip plane; fcc = {111}<110>, bcc / bcc12 = {110}<111>,
+    roters = the fcc family in another order (mod_crystals.f:438-1205)."""
     b, n = Oracle.slip_table(slip_type)
     assert b.shape == (nslip, 3) and n.shape == (nslip, 3)
     assert np.abs(np.linalg.norm(b, axis=1) - 1).max() <= 1e-14
@@ -125,6 +126,13 @@ def test_slip_tables(Oracle, slip_type, nslip):
         assert np.allclose(np.abs(n), 1 / np.sqrt(3))
         assert np.allclose(np.sort(np.abs(b), axis=1), [0, 1 / np.sqrt(2), 1 / np.sqrt(2)])
         assert len({tuple(np.round(np.r_[x, y], 6)) for x, y in zip(b, n)}) == 12
+    if slip_type in (2, 7):
+        assert np.allclose(np.abs(b), 1 / np.sqrt(3))
+        assert np.allclose(np.sort(np.abs(n), axis=1), [0, 1 / np.sqrt(2), 1 / np.sqrt(2)])
+    if slip_type == 6:                               # same 12 systems as fcc up to order and sign
+        bf, nf = Oracle.slip_table(1)
+        key = lambda x, y: tuple(np.round(np.abs(np.outer(x, y) + np.outer(y, x)).ravel(), 6))
+        assert {key(x, y) for x, y in zip(b, n)} == {key(x, y) for x, y in zip(bf, nf)}
 
 
 def test_history_layout_sizes(Oracle):

@@ -27,7 +27,7 @@ def _kinematics(Fn, Fn1):
     return R, py_mm10.sym6(d, True)
 
 
-@pytest.mark.parametrize("slip_type,iD_v", [(1, 0.0), (8, 0.0), (1, 2.0e-7)])
+@pytest.mark.parametrize("slip_type,iD_v", [(1, 0.0), (8, 0.0), (1, 2.0e-7), (2, 0.0), (6, 0.0), (7, 0.0)])
 def test_oracle_matches_numpy_restatement(Oracle, slip_type, iD_v):
     from cpfft_b200.polycrystal import polycrystal
     p = polycrystal(2, ngrains=4, slip_type=slip_type)

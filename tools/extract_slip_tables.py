@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Development-time helper: read the slip-system geometry the reference defines in
-src/mod_crystals.f (fcc :438-515, bcc48 :812-1205) and print it as integer Miller
+src/mod_crystals.f (fcc :438-515, bcc :516-593, single :594-603, roters :604-704, bcc12 :705-811,
+bcc48 :812-1205) and print it as integer Miller
 indices (direction b, plane normal n) in the reference's system ORDER, which the
 per-system slip history depends on.  Output was pasted (as data, integer form)
 into oracle/slip_tables.inc and cpfft_b200/csrc/slip_tables.cuh.
@@ -11,18 +12,20 @@ import re, sys, math
 
 def main(path):
     src = open(path).read().split('\n')
-    blocks = {1: (438, 515), 8: (812, 1205)}
+    blocks = {1: (438, 515), 2: (516, 593), 3: (594, 603), 6: (604, 704), 7: (705, 811), 8: (812, 1205)}
     consts = {'z0': 0, 'f': None, 'f2': 1, 'f3': 1, 'f112': 1, 'f211': 2, 'f123': 1, 'f213': 2, 'f312': 3}
     for st, (a, b) in blocks.items():
         bi, ni = {}, {}
         for line in src[a - 1:b]:
-            m = re.search(r'%(bi|ni)\(\s*(\d+),(\d)\)\s*=\s*([-+]?)\s*(\w+)', line)
+            m = re.search(r'%(bi|ni)\(\s*(\d+)\s*,\s*(\d)\s*\)\s*=\s*([-+]?)\s*([\w.]+)', line)
             if not m:
                 continue
             which, s, k, sign, val = m.groups()
             s, k = int(s), int(k)
-            if val in ('0',):
+            if val in ('0', '0.0', '0.d0'):
                 v = 0
+            elif val == '1.0':
+                v = 1
             elif val == 'f':
                 v = 1
             else:
