@@ -86,3 +86,22 @@ def test_fortran_module_binds_every_symbol():
     names = [n for n in names if n != "CPFFT_NUM_FIELDS"]
     for i, n in enumerate(names):
         assert re.search(rf"\b{n} = {i}\b", f90), (n, i)
+
+
+def test_fortran_hooks_use_only_bound_symbols():
+    """cpfft_b200/fortran/cpfft_hooks.f (the reference-side replacement bodies of INTEGRATION.md 4,
+    fixed form): every cpfft_* routine it calls is bound by the interface module, and no line runs
+    past column 72."""
+    base = os.path.join(ROOT, "cpfft_b200", "fortran")
+    hooks = open(os.path.join(base, "cpfft_hooks.f")).read()
+    f90 = open(os.path.join(base, "cpfft_iso_c.f90")).read()
+    bound = set(re.findall(r"name='(cpfft_[A-Za-z0-9_]+)'", f90))
+    helpers = {"cpfft_check", "cpfft_h", "cpfft_model_to_gpu", "cpfft_download_results", "cpfft_iso_c",
+               "cpfft_config", "cpfft_material", "cpfft_crystal", "cpfft_hooks"}
+    code = "\n".join(l for l in hooks.splitlines() if l[:1] not in ("c", "C"))
+    used = set(re.findall(r"\b(cpfft_[A-Za-z0-9_]+)", code))
+    assert used - helpers <= bound, sorted(used - helpers - bound)
+    assert {"cpfft_create", "cpfft_set_materials", "cpfft_set_voxels", "cpfft_drive_eps_sig", "cpfft_G_K_dF",
+            "cpfft_FFT_nr3", "cpfft_step_log"} <= used
+    assert all(len(l) <= 72 for l in hooks.splitlines())
+    assert all(h in f90 or h in ("cpfft_model_to_gpu", "cpfft_download_results", "cpfft_hooks") for h in helpers)
