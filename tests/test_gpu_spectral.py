@@ -185,25 +185,3 @@ def test_kernel_variants_are_bit_identical(libs, N, monkeypatch):
         assert np.array_equal(g, res[0][0])
         assert it == res[0][2] and rr == res[0][3]
         assert np.array_equal(sol, res[0][1])
-
-
-@pytest.mark.parametrize("N", [16, 32, 64])
-def test_fast_path_matches_plain_fft_statement(libs, N):
-    """the GPU operator against numpy's FFT directly (plain statement of the even-N convention,
-    tests/test_oracle_spectral.py::conv_G_K_dF), not through the oracle"""
-    from test_oracle_spectral import _toy_problem, conv_G_K_dF
-    Solver, _ = libs
-    p = _toy_problem(N)
-    s = Solver(p)
-    rng = np.random.default_rng(N)
-    F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
-    F += 0.002 * rng.standard_normal((9, p.N3))
-    s.upload("FN1", F)
-    s.drive_eps_sig(1, 1)
-    K4 = s.download("K4")
-    x = rng.standard_normal((9, p.N3))
-    s.upload("DFM", x)
-    for flgK in (0, 1):
-        s.G_K_dF("DFM", "B", flgK)
-        want = conv_G_K_dF(N, x, K4 if flgK else None)
-        assert relerr(s.download("B"), want) <= 1e-12, (N, flgK)
