@@ -317,3 +317,47 @@ def test_full_solve_with_kernel_source(libs, name, nstep):
     # implementations are amplified to 2e-10 on the curve; the other decks meet 1e-10
     assert np.abs(pbar - r["Pbar"]).max() / np.abs(r["Pbar"]).max() <= (1e-9 if name == "mts_mm10.in" else 1e-10)
     assert relerr(k.Fn1, o_ref.Fn1) <= (1e-8 if name == "mts_mm10.in" else 1e-9)
+
+
+def test_taylor_point_with_failing_crystals(libs):
+    """a Taylor point whose crystals are the captured failing states (tests/golden/mm10_fail_points.npz):
+    crystal 0 fails, crystal 1 (the same state with a benign increment history) may or may not; the
+    point is flagged, the failed crystal keeps its n state and elastic tangent, the averages and the
+    summed iteration counts agree between the kernel source and the oracle."""
+    from cpfft_b200.polycrystal import taylor_polycrystal
+    from helpers import mm10_layout
+    HostKernels, Oracle = libs
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "mm10_fail_points.npz"))
+    nb = d["Fn"].shape[1]
+    p = taylor_polycrystal(2, ncrystals=2, ngrains=8)
+    ang = np.asarray(p.angles).copy()
+    for v in range(p.N3):
+        ang[v, 0] = d["angles"][v % nb]
+        ang[v, 1] = d["angles"][(v + 1) % nb]
+    p.angles = ang
+    k, o = HostKernels(p), Oracle(p)
+    L = mm10_layout(12)
+    common, per = L["stress"][0], L["total"] - L["stress"][0]
+    assert k.H == o.H == common + 2 * per
+    H1 = d["hist_n"].shape[0]
+    for v in range(p.N3):
+        src0, src1 = v % nb, (v + 1) % nb
+        k.hist_n[:common, v] = d["hist_n"][:common, src0]
+        k.hist_n[common:common + per, v] = d["hist_n"][common:common + per, src0]
+        k.hist_n[common + per:common + 2 * per, v] = d["hist_n"][common:common + per, src1]
+        k.urcs_n[:, v] = d["urcs_n"][:, src0]; k.eps_n[:, v] = d["eps_n"][:, src0]
+        k.Fn[:, v] = d["Fn"][:, src0]
+        k.Fn1[:, v] = d["Fn1"][:, src0]
+    o.hist_n[:] = k.hist_n.T[:, :o.H]; o.urcs_n[:] = k.urcs_n.T; o._view("eps_n", (o.N3, 6))[:] = k.eps_n.T
+    o.Fn[:] = k.Fn; o.Fn1[:] = k.Fn1
+    step, it = int(d["step"]), int(d["iter"])
+    nf_k, nf_o = k.drive_eps_sig(step, it), o.drive_eps_sig(step, it)
+    assert nf_k == nf_o == p.N3                       # crystal 0 of every point fails
+    assert np.array_equal(k.local_iters, o.local_iters)
+    assert k.fail_flags.all()
+    assert relerr(k.urcs_n1.T, o.urcs_n1) <= TOL_SMALL_STRAIN
+    assert relerr(k.K4, o.K4) <= TOL_SMALL_STRAIN
+    compare_mm10_history(k.hist_n1.T[:, :o.H], o.hist_n1, 12, TOL_SMALL_STRAIN, ncrystals=2)
+    # the failed crystal's block holds its n state
+    a, b = L["stress"]
+    assert np.array_equal(k.hist_n1[a:b], k.hist_n[a:b])
