@@ -39,6 +39,14 @@ def _worker(rank, world, port, N, out_dir):
     ang = gather_slabs(np.ascontiguousarray(p.angles.T))          # (3, n3loc) -> (3, N^3)
     if rank == 0:
         np.save(os.path.join(out_dir, "angles.npy"), ang)
+    # polycrystalline material points: the per-rank Taylor tables are slabs of the global ones
+    from cpfft_b200.polycrystal import workload_variant
+    pt = workload_variant(polycrystal(N, ngrains=30, x_range=(x0, x1)), "taylor2", 30)
+    nc, ang_t, ids = pt.taylor_tables()
+    assert nc == 2 and ang_t.shape == ((x1 - x0) * N * N, 2, 3) and ids is None and pt.taylor
+    tay = gather_slabs(np.ascontiguousarray(ang_t.reshape(len(ang_t), 6).T))      # (6, n3loc) -> (6, N^3)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "taylor.npy"), tay)
     # the reductions of the solver are sums over slabs: emulate P_bar
     local = torch.tensor([float(p.angles[:, 0].sum())], dtype=torch.float64)
     dist.all_reduce(local)
@@ -56,6 +64,9 @@ def test_two_rank_slab_decomposition(tmp_path):
     ang = np.load(tmp_path / "angles.npy")
     assert np.array_equal(ang, full.angles.T)
     assert np.isclose(np.load(tmp_path / "sum.npy")[0], full.angles[:, 0].sum(), rtol=1e-14)
+    from cpfft_b200.polycrystal import workload_variant
+    full_t = workload_variant(polycrystal(N, ngrains=30), "taylor2", 30)
+    assert np.array_equal(np.load(tmp_path / "taylor.npy"), np.asarray(full_t.angles).reshape(N ** 3, 6).T)
 
 
 def test_slab_range_rules():
