@@ -153,9 +153,10 @@ class Problem:
     def taylor_tables(self):
         """(ncmax, angles (N3,ncmax,3) float64, crystal_ids (N3,ncmax) int32 or None), C-contiguous"""
         nc = self.ncmax
-        ang = np.ascontiguousarray(np.asarray(self.angles, dtype=np.float64).reshape(self.N3, nc, 3))
+        nv = len(self.matlist)              # N3, or the voxels of one rank's slab
+        ang = np.ascontiguousarray(np.asarray(self.angles, dtype=np.float64).reshape(nv, nc, 3))
         ids = None if self.crystal_ids is None else \
-            np.ascontiguousarray(np.asarray(self.crystal_ids, dtype=np.int32).reshape(self.N3, nc))
+            np.ascontiguousarray(np.asarray(self.crystal_ids, dtype=np.int32).reshape(nv, nc))
         return nc, ang, ids
 
     @property
