@@ -150,3 +150,26 @@ def test_cli_timing_summary_format(capsys):
     assert "calculations for pcg solution vector update:" in out and "sig-eps & internal force:" in out
     assert "patran output" not in out                       # buckets without calls are skipped
     assert "wall time (secs):     1.2345 61.7 (%) no. calls:       12" in out
+
+
+def test_single_crystal_points_with_a_crystal_file(tmp_path, oracle_built):
+    """n_crystals 1 with `crystal_input file` and `orientation_input single`: the flat file carries
+    `elem crystal` only (read_defs with angles = .false., mod_crystals.f:2262-2264); the oracle and the
+    host build of the kernel source run it."""
+    import shutil
+    from cpfft_b200.deck import read_deck
+    src = open(os.path.join(DECKS, "taylor_mm10.in")).read()
+    src = src.replace("n_crystals 2", "n_crystals 1").replace("orientation_input file filename 'taylor_crystals.in'",
+                                                                "orientation_input single angles 10.0 20.0 30.0 filename 'cry.in'")
+    (tmp_path / "deck.in").write_text(src)
+    (tmp_path / "cry.in").write_text("".join(f"{e} {1 + (e % 2)}\n" for e in range(1, 126)))
+    p = read_deck(str(tmp_path / "deck.in"))
+    assert p.ncmax == 1 and p.taylor and p.angles.shape == (125, 3) and p.crystal_ids.shape == (125, 1)
+    assert np.all(p.angles == [10.0, 20.0, 30.0])
+    assert p.crystal_ids[:4, 0].tolist() == [2, 1, 2, 1]
+    from oracle import Oracle
+    from host_kernels import HostKernels
+    o, k = Oracle(p), HostKernels(p)
+    assert o.H == k.H == 357                      # the bcc48 crystal forces the 48-system layout on every point
+    o.drive_eps_sig(1, 0); k.drive_eps_sig(1, 0)
+    assert np.abs(k.K4 - o.K4).max() <= 1e-9 * np.abs(o.K4).max()
