@@ -361,3 +361,30 @@ def test_taylor_point_with_failing_crystals(libs):
     # the failed crystal's block holds its n state
     a, b = L["stress"]
     assert np.array_equal(k.hist_n1[a:b], k.hist_n[a:b])
+
+
+def test_material_table_errors(libs, capfd):
+    """usage errors of cpfft_set_voxels[_taylor] are caught when the tables are built (material_tables.hpp)"""
+    import copy
+    from cpfft_b200.polycrystal import polycrystal, taylor_polycrystal
+    from test_oracle_mts import mts_crystal
+    HostKernels, _ = libs
+    # crystals of one cp material with different hardening laws
+    p = taylor_polycrystal(2, ncrystals=2, ngrains=4, mixed=True)
+    p.crystals[1] = mts_crystal()
+    with pytest.raises(RuntimeError):
+        HostKernels(p)
+    assert "share one hardening law" in capfd.readouterr().err
+    # a voxel that names a crystal outside the library
+    p = taylor_polycrystal(2, ncrystals=2, ngrains=4, mixed=True)
+    p.crystal_ids = p.crystal_ids.copy(); p.crystal_ids[3, 1] = 7
+    with pytest.raises(RuntimeError):
+        HostKernels(p)
+    assert "undefined crystal" in capfd.readouterr().err
+    # unsupported hardening law / slip family
+    for field, val, msg in (("h_type", 4, "hardening law"), ("slip_type", 9, "slip_type")):
+        p = polycrystal(2, ngrains=4)
+        c = copy.copy(p.crystals[0]); setattr(c, field, val); p.crystals = [c]
+        with pytest.raises(RuntimeError):
+            HostKernels(p)
+        assert msg in capfd.readouterr().err
