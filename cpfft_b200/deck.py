@@ -176,8 +176,9 @@ def _read_material(lines: _Lines, toks: List[str], materials: List[Material], ba
                     raise DeckError("only kocks angles are supported")
                 i += 2
             elif k == "angle_type":
-                if pt[i + 1] != "degrees":
-                    raise DeckError("only degrees are supported")
+                if pt[i + 1] not in ("degrees", "radians"):
+                    raise DeckError("angle_type must be degrees or radians (inmat.f:206-216)")
+                m.angle_scale = 1.0 if pt[i + 1] == "degrees" else 180.0 / np.pi   # the C ABI takes degrees
                 i += 2
             elif k == "n_crystals":
                 ncry = int(pt[i + 1]); i += 2
@@ -336,9 +337,9 @@ def read_deck(path: str) -> Problem:
         if m.orientation_input == 2 or m.crystal_input == 2:
             fa, fi = read_crystal_file(m.orientation_file, n3, nc, m.orientation_input == 2, m.crystal_input == 2)
         if m.orientation_input == 2:
-            angles[sel, :nc] = fa[sel]
+            angles[sel, :nc] = fa[sel] * m.angle_scale
         else:
-            angles[sel, :nc] = m.angles
+            angles[sel, :nc] = np.asarray(m.angles) * m.angle_scale
         if crystal_ids is not None:
             crystal_ids[sel, :nc] = fi[sel] if m.crystal_input == 2 else m.crystal
     if ncmax == 1:

@@ -109,6 +109,7 @@ class Material:
     orientation_file: str = ""
     angles: tuple = (0.0, 0.0, 0.0)
     orientation_input: int = 1  # 1 single, 2 file
+    angle_scale: float = 1.0    # deck reader: factor to degrees (`angle_type radians`)
 
     def pod(self) -> MaterialPOD:
         p = MaterialPOD()

@@ -173,3 +173,14 @@ def test_single_crystal_points_with_a_crystal_file(tmp_path, oracle_built):
     assert o.H == k.H == 357                      # the bcc48 crystal forces the 48-system layout on every point
     o.drive_eps_sig(1, 0); k.drive_eps_sig(1, 0)
     assert np.abs(k.K4 - o.K4).max() <= 1e-9 * np.abs(o.K4).max()
+
+
+def test_angle_type_radians(tmp_path):
+    """`angle_type radians` (inmat.f:206-216): converted to the degrees the C ABI takes"""
+    from cpfft_b200.deck import read_deck
+    src = open(os.path.join(DECKS, "test_mm10.in")).read().replace("angle_type degrees", "angle_type radians")
+    src = src.replace("filename 'angle_bc.in'", "filename 'ang.in'")
+    (tmp_path / "deck.in").write_text(src)
+    (tmp_path / "ang.in").write_text("".join(f"{e}, {0.25 * np.pi}, 0.0, 0.1\n" for e in range(1, 344)))
+    p = read_deck(str(tmp_path / "deck.in"))
+    assert np.allclose(p.angles, [45.0, 0.0, np.degrees(0.1)], rtol=0, atol=1e-12)
