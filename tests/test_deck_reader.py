@@ -184,3 +184,50 @@ def test_angle_type_radians(tmp_path):
     (tmp_path / "ang.in").write_text("".join(f"{e}, {0.25 * np.pi}, 0.0, 0.1\n" for e in range(1, 344)))
     p = read_deck(str(tmp_path / "deck.in"))
     assert np.allclose(p.angles, [45.0, 0.0, np.degrees(0.1)], rtol=0, atol=1e-12)
+
+
+def test_cli_host_glue_with_the_oracle_standing_in(tmp_path, monkeypatch, capsys, oracle_built):
+    """`python -m cpfft_b200 deck` end to end on the CPU: the CLI's host glue (deck reader, step loop,
+    result files of the selected steps, timing summary) with the oracle standing in for the CUDA
+    library behind the Solver interface (test infrastructure; the product Solver needs a GPU)."""
+    import ctypes as C
+    import cpfft_b200.__main__ as cli
+    from oracle import Oracle
+
+    class OracleSolver:
+        def __init__(self, prob, device=0):
+            self.o, self.prob = Oracle(prob, threads=2), prob
+
+        def drive_eps_sig(self, step, it):
+            self.o.drive_eps_sig(step, it)
+
+        def FFT_nr3(self, nstep=1, first=0):
+            o, n = self.o, nstep
+            bc = np.ascontiguousarray(self.prob.BC_all()[first:first + n])
+            nbc = np.ascontiguousarray(self.prob.isNBC, dtype=np.int32)
+            nr = np.zeros(n, dtype=np.int32); cg = np.full((n, 64), -1, dtype=np.int32)
+            pb = np.zeros((n, 9)); bk = np.zeros(3); cnt = np.zeros(5, dtype=np.int64)
+            dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+            rc = o.L.orc_FFT_nr3_from(o.h, first + 1, n, bc.ctypes.data_as(dp), nbc.ctypes.data_as(ip), nr.ctypes.data_as(ip),
+                                      cg.ctypes.data_as(ip), 64, pb.ctypes.data_as(dp), bk.ctypes.data_as(dp),
+                                      cnt.ctypes.data_as(C.POINTER(C.c_int64)))
+            assert rc == 0
+            cgl = [list(r[:list(r).index(-1)]) if -1 in r else list(r) for r in cg]
+            return dict(nr_iters=nr, cg_iters=cgl, Pbar=pb, buckets=bk, counters=cnt,
+                        log=f"     Now starting step: {first + 1:7d}\\n")
+
+        def download(self, name, layout=0):
+            return {"URCS_N1": self.o.urcs_n1, "EPS_N1": self.o.eps_n1}[name]
+
+        def material_failures(self):
+            return (0, 0)
+
+    monkeypatch.setattr(cli, "Solver", OracleSolver)
+    rc = cli.main([os.path.join(DECKS, "test_mm10.in"), "--outdir", str(tmp_path), "--steps", "4"])
+    assert rc == 0
+    out = capsys.readouterr().out
+    assert out.count("Now starting step") == 4
+    assert sorted(os.listdir(tmp_path)) == ["wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text"]
+    rows = open(tmp_path / "wes00004_text").read().splitlines()[7:]
+    assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
+    assert "solution timings" in out and "pcg solution vector update" in out and "patran output" in out
