@@ -31,6 +31,14 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdA
   upd_mm10_voxel<false, MM10_VOCE>(a, e, mm10_sm + threadIdx.x);
 }
 
+// development variant (CPFFT_MM10_LF=1): residual slip loop in the lattice frame, see mm10_resid
+__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_lf(UpdArgs a) {
+  extern __shared__ double mm10_sm[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n3) return;
+  upd_mm10_voxel<false, MM10_VOCE, true>(a, e, mm10_sm + threadIdx.x);
+}
+
 // polycrystalline material points (n_crystals > 1): same per-crystal integration, Taylor average
 __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_taylor(UpdArgs a) {
   extern __shared__ double mm10_sm[];
@@ -127,7 +135,9 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
   {
     // one kernel per (one crystal | Taylor point) x (Voce | MTS) combination present in the model
     typedef void (*Kern)(UpdArgs);
-    const Kern kerns[2][3] = {{nullptr, k_update_mm10, k_update_mm10_mts}, {nullptr, k_update_mm10_taylor, k_update_mm10_taylor_mts}};
+    static const bool lf = [] { const char* v = getenv("CPFFT_MM10_LF"); return v && v[0] == '1'; }();
+    const Kern kerns[2][3] = {{nullptr, lf ? k_update_mm10_lf : k_update_mm10, k_update_mm10_mts},
+                              {nullptr, k_update_mm10_taylor, k_update_mm10_taylor_mts}};
     const size_t smem = sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS;
     for (int multi = 0; multi < 2; ++multi)
       for (int hard = 1; hard <= 2; ++hard) {

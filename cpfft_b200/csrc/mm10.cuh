@@ -237,10 +237,75 @@ CPF_DI double mm10_hfac(const Mm10Ctx& c, double tt, double* hterm_out) {
 
 // Residual (mm10_formR / formR1 / formR2).  R[0..5] = R1, R[6] = R2 (0 unless want2); returns
 // the hardening target h (np1%tt_rate = (h - tt_n)/tinc).
-template <int HARD>
+//
+// LF = true (development variant, CPFFT_MM10_LF=1, Voce single crystal only): the slip loop runs
+// in the lattice frame.  With Sh the stress tensor with halved shears, rs_s = Sh : (Q M~_s Q^T) =
+// (Q^T Sh Q) : M~_s, so the stress is rotated once and each system costs a 6-term dot product;
+// the plastic strain / spin sums are accumulated on ms0 / qs0 and rotated back once (both maps
+// are linear).  Same algebra, different summation order: results agree to round-off, not bit
+// for bit, which is why this is not the default before it has been through the GPU suite.
+template <int HARD, bool LF = false>
 CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double* R, bool want2) {
   double dbarp[6] = {0, 0, 0, 0, 0, 0}, wq[3] = {0, 0, 0}, sabs = 0.0;
   const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v;
+  if (LF) {
+    double y[6];
+    {
+      const double h3 = 0.5 * sig[3], h4 = 0.5 * sig[4], h5 = 0.5 * sig[5];
+      double U[9];   // U = Sh Q
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const double q0 = c.Q[b], q1 = c.Q[3 + b], q2 = c.Q[6 + b];
+        U[b] = sig[0] * q0 + h3 * q1 + h5 * q2;
+        U[3 + b] = h3 * q0 + sig[1] * q1 + h4 * q2;
+        U[6 + b] = h5 * q0 + h4 * q1 + sig[2] * q2;
+      }
+      // Y = Q^T U, Voigt with doubled shears
+      y[0] = c.Q[0] * U[0] + c.Q[3] * U[3] + c.Q[6] * U[6];
+      y[1] = c.Q[1] * U[1] + c.Q[4] * U[4] + c.Q[7] * U[7];
+      y[2] = c.Q[2] * U[2] + c.Q[5] * U[5] + c.Q[8] * U[8];
+      y[3] = 2.0 * (c.Q[0] * U[1] + c.Q[3] * U[4] + c.Q[6] * U[7]);
+      y[4] = 2.0 * (c.Q[1] * U[2] + c.Q[4] * U[5] + c.Q[7] * U[8]);
+      y[5] = 2.0 * (c.Q[0] * U[2] + c.Q[3] * U[5] + c.Q[6] * U[8]);
+    }
+    double am[6] = {0, 0, 0, 0, 0, 0}, aw[3] = {0, 0, 0};
+#pragma unroll 1
+    for (int s = 0; s < c.nslip; ++s) {
+      const double* t = c.ms0 + 9 * s;
+      double m[6], w[3];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m[k] = CPF_LDG(t + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[k] = CPF_LDG(t + 6 + k);
+      const double rs = y[0] * m[0] + y[1] * m[1] + y[2] * m[2] + y[3] * m[3] + y[4] * m[4] + y[5] * m[5];
+      const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
+      const double slip = dgtt * p * rs;
+      const double f = rs * dif + slip;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) am[k] += f * m[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) aw[k] += f * w[k];
+      sabs += fabs(slip);
+    }
+    // dbarp = V6(Q A~ Q^T), wq = RWQ aw  (the maps of mm10_slip_geom applied to the sums)
+    double T[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double a = c.Q[3 * i], b = c.Q[3 * i + 1], d = c.Q[3 * i + 2];
+      T[3 * i + 0] = a * am[0] + b * am[3] + d * am[5];
+      T[3 * i + 1] = a * am[3] + b * am[1] + d * am[4];
+      T[3 * i + 2] = a * am[5] + b * am[4] + d * am[2];
+    }
+    dbarp[0] = T[0] * c.Q[0] + T[1] * c.Q[1] + T[2] * c.Q[2];
+    dbarp[1] = T[3] * c.Q[3] + T[4] * c.Q[4] + T[5] * c.Q[5];
+    dbarp[2] = T[6] * c.Q[6] + T[7] * c.Q[7] + T[8] * c.Q[8];
+    dbarp[3] = T[0] * c.Q[3] + T[1] * c.Q[4] + T[2] * c.Q[5];
+    dbarp[4] = T[3] * c.Q[6] + T[4] * c.Q[7] + T[5] * c.Q[8];
+    dbarp[5] = T[0] * c.Q[6] + T[1] * c.Q[7] + T[2] * c.Q[8];
+    wq[0] = c.RWQ[0] * aw[0] + c.RWQ[1] * aw[1] + c.RWQ[2] * aw[2];
+    wq[1] = c.RWQ[3] * aw[0] + c.RWQ[4] * aw[1] + c.RWQ[5] * aw[2];
+    wq[2] = c.RWQ[6] * aw[0] + c.RWQ[7] * aw[1] + c.RWQ[8] * aw[2];
+  } else
 #pragma unroll 1
   for (int s = 0; s < c.nslip; ++s) {
     double ms[6], qs[3];
@@ -427,7 +492,7 @@ CPF_DI void mts_thresholds(const Mm10Mts& m, double dgc, double* tau_y, double* 
 // mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening
 // (phase 0, 6 unknowns), then the coupled update (phase 1, 7 unknowns), as one state machine.
 // x[7] in/out.  c.J keeps the last Jacobian formed (lagged tangent).  Returns true on failure.
-template <int HARD>
+template <int HARD, bool LF = false>
 CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, int* it_pred, int* it_upd,
                        double* h_last) {
   const double cc = 1.0e-4, red = 0.5;
@@ -449,7 +514,7 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, in
       double yt[7], Rt[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) yt[k] = init ? y[k] : y[k] + alpha * dx[k];
-      h = mm10_resid<HARD>(c, yt, yt[6], Rt, phase == 1);
+      h = mm10_resid<HARD, LF>(c, yt, yt[6], Rt, phase == 1);
       double dot = 0.0;
 #pragma unroll
       for (int k = 0; k < 7; ++k) dot += Rt[k] * Rt[k];

@@ -73,7 +73,7 @@ CPF_DI void upd_mm01_voxel(const UpdArgs& a, const int64_t e) {
 //   mm10_a.f:2109-2175; h / estress / ehard mm10_b.f:2080-2186; tangent terms JA, JB from
 //   dgamma/dD and ed, mm10_a.f:740-810, mm10_b.f:2189-2345 -- both proportional to the strain
 //   increment, so C - JA - JB is a rank-one correction of C).
-template <bool MULTI, int HARD>
+template <bool MULTI, int HARD, bool LF = false>
 CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   const CpfMatDev mp = a.mats[a.matidx[e]];
   if (mp.type != 10) return;
@@ -243,7 +243,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
           c.h0 = cr.tau_a * (1.0 - mu_s / mu_n) + c.ur * (ty - ty_n) + (mu_s / mu_n) * c.ttn;
         }
         x[6] = c.ttn;
-        fail = mm10_solve<HARD>(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
+        fail = mm10_solve<HARD, LF>(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
         if (fail) {
   #pragma unroll
           for (int k = 0; k < 7; ++k) x[k] = ox[k];

@@ -47,6 +47,7 @@ def _lib():
         L.mh_local_iters.argtypes = [C.c_void_p]
         L.mh_drive_eps_sig.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.mh_update.argtypes = [C.c_void_p]
+        L.mh_set_lattice_frame.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -58,7 +59,7 @@ class HostKernels:
     NCOMP = {"Fn": 9, "Fn1": 9, "Pn1": 9, "K4": 81, "urcs_n": 9, "urcs_n1": 9, "eps_n": 6, "eps_n1": 6,
              "rot_n1": 9, "cep": 36}
 
-    def __init__(self, prob):
+    def __init__(self, prob, lattice_frame=False):
         L = _lib()
         self.L, self.prob, self.N3 = L, prob, prob.N3
         mats, crys = prob.material_pods(), prob.crystal_pods()
@@ -71,6 +72,7 @@ class HostKernels:
         if not self.h:
             raise RuntimeError("mh_create failed")
         self.H = L.mh_hist_size(self.h)
+        L.mh_set_lattice_frame(self.h, int(lattice_frame))
 
     def __del__(self):
         try:

@@ -20,6 +20,7 @@ struct mh_model {
   std::vector<double> Fn, Fn1, Pn1, K4, urcs_n, urcs_n1, eps_n, eps_n1, rot_n1, hist_n, hist_n1, cep;
   std::vector<int32_t> fail, liters;
   int failcnt[2];
+  bool lattice_frame = false;   // CPFFT_MM10_LF variant of the Voce single-crystal kernel
 };
 
 extern "C" {
@@ -51,6 +52,7 @@ mh_model* mh_create(int64_t n3, int nmat, const cpfft_material* mats, int ncry, 
   return m;
 }
 void mh_destroy(mh_model* m) { delete m; }
+void mh_set_lattice_frame(mh_model* m, int on) { m->lattice_frame = on != 0; }
 int mh_hist_size(mh_model* m) { return m->T.H; }
 int mh_ngrains(mh_model* m) { return m->T.ngrains; }
 
@@ -98,6 +100,7 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
         if (mp.ncry > 1) upd_mm10_voxel<true, MM10_MTS>(a, e, sm);
         else upd_mm10_voxel<false, MM10_MTS>(a, e, sm);
       } else if (mp.ncry > 1) upd_mm10_voxel<true, MM10_VOCE>(a, e, sm);
+      else if (m->lattice_frame) upd_mm10_voxel<false, MM10_VOCE, true>(a, e, sm);
       else upd_mm10_voxel<false, MM10_VOCE>(a, e, sm);
     }
     // even voxels: [D] in registers (the kernel's default), odd voxels: the memory-resident variant

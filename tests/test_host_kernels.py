@@ -319,6 +319,43 @@ def test_full_solve_with_kernel_source(libs, name, nstep):
     assert relerr(k.Fn1, o_ref.Fn1) <= (1e-8 if name == "mts_mm10.in" else 1e-9)
 
 
+def test_lattice_frame_residual_variant(libs):
+    """the CPFFT_MM10_LF development variant (residual slip loop in the lattice frame, mm10.cuh
+    mm10_resid<.., LF = true>) is the same algebra in another summation order: same results to
+    round-off and the SAME local iteration counts along a plastic load path with a large,
+    sub-stepped increment, and the same Newton counts / curve on the test deck."""
+    from cpfft_b200.polycrystal import polycrystal
+    HostKernels, Oracle = libs
+    p = polycrystal(6, ngrains=20)
+    k, o = HostKernels(p, lattice_frame=True), Oracle(p)
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((9, p.N3)); G[[0, 4, 8]] -= G[[0, 4, 8]].mean(axis=0)
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.45
+    I = np.zeros((9, p.N3)); I[[0, 4, 8]] = 1.0
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    plastic = 0
+    for step, amp in enumerate((0.002, 0.004, 0.006, 0.03), start=1):     # last step: 2.4 % increment
+        for it, frac in ((0, 0.9), (1, 1.0)):
+            F = I + amp * frac * (bar + 0.3 * G)
+            k.Fn1[:] = F; o.Fn1[:] = F
+            assert k.drive_eps_sig(step, it) == o.drive_eps_sig(step, it)
+            ok = np.ctypeslib.as_array(o.L.orc_fail_flags(o.h), shape=(o.N3,)) == 0
+            assert relerr(k.urcs_n1.T[ok], o.urcs_n1[ok]) <= TOL_SMALL_STRAIN
+            assert relerr(k.K4[:, ok], o.K4[:, ok]) <= TOL_SMALL_STRAIN
+            assert np.array_equal(k.local_iters, o.local_iters)
+            plastic += int(o.local_iters[:, 1].sum())
+        k.Fn[:] = k.Fn1; o.Fn[:] = o.Fn1
+        k.update(); o.update()
+    assert plastic > 0 and o.local_iters[:, 1].max() > 12          # plastic, and sub-steps were taken
+    # whole solve on the reference's deck
+    p = deck("test_mm10.in")
+    o_ref = Oracle(p); o_ref.drive_eps_sig(1, 0)
+    r = o_ref.FFT_nr3(nstep=6)
+    nr, pbar = _hybrid_FFT_nr3(HostKernels(p, lattice_frame=True), Oracle(p), p, 6)
+    assert nr == [int(v) for v in r["nr_iters"]]
+    assert np.abs(pbar - r["Pbar"]).max() / np.abs(r["Pbar"]).max() <= 1e-10
+
+
 def test_taylor_point_with_failing_crystals(libs):
     """a Taylor point whose crystals are the captured failing states (tests/golden/mm10_fail_points.npz):
     crystal 0 fails, crystal 1 (the same state with a benign increment history) may or may not; the

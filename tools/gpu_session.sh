@@ -11,6 +11,7 @@
 #   gpurun --timeout 300 -- 'tools/gpu_session.sh ncu-update TAG' ncu --set full of k_update_mm10 / k_pk1_tangent
 #   gpurun --timeout 120 -- 'tools/gpu_session.sh ab'            A/B of the kernel-variant switches (tools/ab_iz.py)
 #   gpurun --timeout 150 -- 'tools/gpu_session.sh ab-pk1'        A/B of the two k_pk1_tangent variants (tools/time_update.py)
+#   gpurun --timeout 150 -- 'tools/gpu_session.sh ab-lf'         A/B of the lattice-frame residual variant of k_update_mm10 (CPFFT_MM10_LF=1)
 #   gpurun --timeout 100 -- 'tools/gpu_session.sh ab-tma'        adds the untested TMA variant of k_iz_pipe at 64^3
 set -u
 MODE=${1:-quick}; TAG=${2:-rXX}
@@ -40,6 +41,8 @@ case "$MODE" in
     timeout 100 python tools/ab_iz.py 256 10 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab256.log ;;
   ab-pk1)   # k_pk1_tangent with [D] in registers (default, 1200 B stack) vs re-read from memory (824 B stack)
     (timeout 60 python tools/time_update.py 128; CPFFT_PK1_CEP=mem timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_pk1.log ;;
+  ab-lf)    # k_update_mm10 vs k_update_mm10_lf (residual slip loop in the lattice frame): time, checksum, local iterations
+    (timeout 60 python tools/time_update.py 128; CPFFT_MM10_LF=1 timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_lf.log ;;
   ab-tma)   # includes the untested TMA variant of k_iz_pipe (CPFFT_IZ_PIPE=2); own short timeout: an mbarrier bug would hang
     AB_TMA=1 timeout 60 python tools/ab_iz.py 64 5 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab_tma64.log ;;
   *) echo "unknown mode $MODE"; exit 2 ;;
