@@ -92,3 +92,29 @@ def test_mts_deck_matches_golden():
     ref = np.array(gold["Pbar"])
     assert np.abs(r["Pbar"] - ref).max() / np.abs(ref).max() <= 1e-9
     assert abs(np.abs(s.download("PN1")).max() / gold["P_absmax"] - 1.0) <= 1e-7
+
+
+def test_lattice_frame_variant_in_subprocess():
+    """CPFFT_MM10_LF=1 (k_update_mm10_lf, residual slip loop in the lattice frame; the switch is read once
+    per process, hence the subprocess): same Newton / CG counts and the same curve as the default kernel
+    on the reference's crystal-plasticity deck -- the golden fixture."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import json, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from helpers import deck\nfrom cpfft_b200 import Solver\n"
+            "s = Solver(deck('test_mm10.in')); s.drive_eps_sig(1, 0); r = s.FFT_nr3()\n"
+            "print('RESULT ' + json.dumps({'nr': [int(v) for v in r['nr_iters']], 'cg': [[int(v) for v in row] for row in r['cg_iters']],"
+            " 'Pbar': r['Pbar'].tolist(), 'launches': s.kernel_launches()}))\n") % (here, os.path.dirname(here))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CPFFT_MM10_LF="1"), capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    gold = json.load(open(os.path.join(here, "golden", "deck_results.json")))["test_mm10.in"]
+    assert got["launches"] > 0
+    assert got["nr"] == gold["nr_iters"]
+    assert_same_cg_counts(got["cg"], gold["cg_iters"], 1)
+    ref = np.array(gold["Pbar"])
+    assert np.abs(np.array(got["Pbar"]) - ref).max() / np.abs(ref).max() <= 1e-10
