@@ -241,6 +241,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from cpfft_b200.api import library_path
+    if not os.path.exists(library_path()):       # tree without built artefacts: compile first (rank 0), nvcc is in the image
+        if local_rank == 0:
+            from cpfft_b200.build import build as build_cuda
+            build_cuda()
+        for _ in range(3000):                    # the other ranks wait for the file
+            if os.path.exists(library_path()):
+                break
+            time.sleep(0.1)
     nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -42,7 +42,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # the four translation units are independent: compile them side by side, then link
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-ldl"])
+    tmp = LIB + f".tmp{os.getpid()}"      # link aside, then rename: a concurrent reader never sees a partial file
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs + ["-ldl"])
+    os.replace(tmp, LIB)
     return LIB
 
 
