@@ -105,3 +105,28 @@ def test_fortran_hooks_use_only_bound_symbols():
             "cpfft_FFT_nr3", "cpfft_step_log"} <= used
     assert all(len(l) <= 72 for l in hooks.splitlines())
     assert all(h in f90 or h in ("cpfft_model_to_gpu", "cpfft_download_results", "cpfft_hooks") for h in helpers)
+
+
+def test_plain_c_host(lib, tmp_path):
+    """a C99 program compiled against include/cpfft_b200.h and linked with the library (the view of a cgo /
+    ISO_C_BINDING caller): the header is valid C, the struct sizes are those of the Python mirror, and without a
+    GPU cpfft_create fails with a CUDA error instead of falling back to anything"""
+    import ctypes
+    import subprocess
+    import torch
+    from cpfft_b200.api import library_path, Config
+    from cpfft_b200.problem import MaterialPOD, CrystalPOD
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.dirname(library_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "native", "c_host.c"), "-o", exe, "-L", libdir, "-lcpfft_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and out.stdout.startswith("created N=8 voxels=512"), out.stdout
+    else:
+        assert out.returncode == 10, (out.returncode, out.stdout)
+        sizes = dict(kv.split("=") for kv in out.stdout.split()[3:])
+        assert int(sizes["sizeof(config)"]) == ctypes.sizeof(Config)
+        assert int(sizes["sizeof(material)"]) == ctypes.sizeof(MaterialPOD)
+        assert int(sizes["sizeof(crystal)"]) == ctypes.sizeof(CrystalPOD)
