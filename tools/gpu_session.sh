@@ -13,6 +13,7 @@
 #   gpurun --timeout 150 -- 'tools/gpu_session.sh ab-pk1'        A/B of the two k_pk1_tangent variants (tools/time_update.py)
 #   gpurun --timeout 150 -- 'tools/gpu_session.sh ab-lf'         A/B of the lattice-frame residual variant of k_update_mm10 (CPFFT_MM10_LF=1)
 #   gpurun --timeout 100 -- 'tools/gpu_session.sh ab-tma'        adds the untested TMA variant of k_iz_pipe at 64^3
+#   gpurun --timeout 600 -- 'tools/gpu_session.sh first TAG'    first call of a round: new GPU tests, the three unmeasured variants, bench
 set -u
 MODE=${1:-quick}; TAG=${2:-rXX}
 mkdir -p gpurun_out
@@ -45,5 +46,9 @@ case "$MODE" in
     (timeout 60 python tools/time_update.py 128; CPFFT_MM10_LF=1 timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_lf.log ;;
   ab-tma)   # includes the untested TMA variant of k_iz_pipe (CPFFT_IZ_PIPE=2); own short timeout: an mbarrier bug would hang
     AB_TMA=1 timeout 60 python tools/ab_iz.py 64 5 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab_tma64.log ;;
+  first)    # everything written without a GPU, cheapest first; every leg has its own timeout and log
+    timeout 200 python -m pytest tests/test_zz_gpu_new_features.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_zz_tests.log
+    "$0" ab-lf "$TAG"; "$0" ab-pk1 "$TAG"; "$0" ab-tma "$TAG"
+    "$0" bench "$TAG" ;;
   *) echo "unknown mode $MODE"; exit 2 ;;
 esac
