@@ -39,7 +39,8 @@ def main(argv=None):
         times[1][0] += float(r["buckets"][1]); times[1][1] += int(r["counters"][1])
         if step in prob.out_steps:
             t_out = time.time()
-            write_step(args.outdir, step, s.download("URCS_N1", 1), s.download("EPS_N1", 1), prob.name, prob.N)
+            write_step(args.outdir, step, s.download("URCS_N1", 1), s.download("EPS_N1", 1), prob.name, prob.N,
+                       Fn1=s.download("FN1"), lengths=prob.lengths)
             times[2][0] += time.time() - t_out; times[2][1] += 1
             print(f"       results of step {step} written to {args.outdir}")
     fails = s.material_failures()[0]

@@ -253,6 +253,7 @@ def read_deck(path: str) -> Problem:
     mults: dict = {}
     tolNR, tolPCG, maxIter, tstep = 1e-5, 1e-10, 10, 1.0
     name, out_steps = "", ()
+    lengths = [1.0, 1.0, 1.0]                # l_x, l_y, l_z (mod_fft.f:8); only the output mesh uses them
     while True:
         line = lines.next()
         if line is None:
@@ -316,7 +317,15 @@ def read_deck(path: str) -> Problem:
             low = [t.lower() for t in toks]
             if len(low) > 2 and low[1].startswith("result") and low[2].startswith("step"):
                 out_steps = tuple(_int_list(toks[3:]))
-        elif key in ("sizes", "blocking", "compute"):
+        elif key == "sizes":
+            # `sizes of x_direction <l_x> y_direction <l_y> z_direction <l_z>` (FFT_finite_3d.f:97-114): the
+            # cell lengths.  formG ignores them (FFT_init.f:272-340); they size the output mesh of oumodel / f2disp
+            low = [t.lower() for t in toks]
+            for j, t in enumerate(low[:-1]):
+                for ax, word in enumerate(("x_direction", "y_direction", "z_direction")):
+                    if len(t) >= 4 and word.startswith(t):
+                        lengths[ax] = float(toks[j + 1])
+        elif key in ("blocking", "compute"):
             pass
         elif key == "stop":
             break
@@ -351,4 +360,5 @@ def read_deck(path: str) -> Problem:
     mult_arr = np.array([mults.get(s + 1, 0.0) for s in range(nstep)])
     return Problem(N=N, materials=materials, crystals=cry_list, matlist=elem_mat, angles=angles,
                    FP_max=FP_max, isNBC=isNBC, mults=mult_arr, tolNR=tolNR, tolPCG=tolPCG,
-                   maxIter=maxIter, tstep=tstep, name=name, out_steps=out_steps, crystal_ids=crystal_ids)
+                   maxIter=maxIter, tstep=tstep, name=name, out_steps=out_steps, crystal_ids=crystal_ids,
+                   lengths=tuple(lengths))

@@ -1,4 +1,5 @@
-"""Result files in the reference's flat-text format (src/ouresult.f): per output step one
+"""Result files in the reference's flat-text format (src/ouresult.f): per output step one ``wnd#####_text``
+(nodal displacements recovered from F, ``oudisp`` ouresult.f:56-124, three ``e15.6`` values per node), one
 ``wes#####_text`` (unrotated Cauchy stresses) and one ``wee#####_text`` (strains) file with the
 ``ouddpa_flat_header`` header (ouresult.f:335-398) and one ``30e15.6`` record per element
 (ouresult.f:296-298; 11 + 15 values per stress record, 7 + 15 per strain record, of which the
@@ -30,8 +31,8 @@ def fortran_e(x: float, width: int = 15, digits: int = 6) -> str:
 
 
 def flat_name(kind: str, step: int) -> str:
-    """``wes`` / ``wee`` + step (i5.5) + ``_text`` (ouresult.f:704-711)."""
-    return {"stresses": "wes", "strains": "wee"}[kind] + f"{step:05d}_text"
+    """``wes`` / ``wee`` / ``wnd`` + step (i5.5) + ``_text`` (ouresult.f:440, 704-711)."""
+    return {"stresses": "wes", "strains": "wee", "displacements": "wnd"}[kind] + f"{step:05d}_text"
 
 
 def write_flat(path: str, kind: str, step: int, values: np.ndarray, structure: str = "", nnode: int = 0):
@@ -52,9 +53,28 @@ def write_flat(path: str, kind: str, step: int, values: np.ndarray, structure: s
             f.write("".join(fortran_e(float(v)) for v in row[:6]) + pad + "\n")
 
 
-def write_step(outdir: str, step: int, urcs_n1: np.ndarray, eps_n1: np.ndarray, structure: str = "", N: int = 0):
-    """urcs_n1 (nelem, >= 6), eps_n1 (nelem, 6): the AoS block order of the reference."""
+def write_nodal(path: str, step: int, u: np.ndarray, structure: str = "", nelem: int = 0):
+    """u: (nnode, 3) nodal displacements in node order (ouresult.f:104-113, format 930 = 3e15.6)."""
+    with open(path, "w") as f:
+        f.write("#\n")
+        f.write(f"#  WARP3D nodal results: {'displacements':<15s}\n")
+        f.write(f"#  Structure name: {structure[:8]:<8s}\n")
+        f.write(f"#  Model nodes, elements: {u.shape[0]:8d}{nelem:8d}\n")
+        f.write(f"#  {time.strftime('%a %b %d %H:%M:%S %Y'):<24s}\n")
+        f.write(f"#  Load(time) step: {step:8d}\n")
+        f.write("#\n")
+        for row in u:
+            f.write("".join(fortran_e(float(v)) for v in row[:3]) + "\n")
+
+
+def write_step(outdir: str, step: int, urcs_n1: np.ndarray, eps_n1: np.ndarray, structure: str = "", N: int = 0,
+               Fn1: np.ndarray | None = None, lengths=(1.0, 1.0, 1.0)):
+    """urcs_n1 (nelem, >= 6), eps_n1 (nelem, 6): the AoS block order of the reference.  Fn1 (9, nelem): also the
+    nodal displacement file, recovered from the deformation gradients as the reference's f2disp does."""
     os.makedirs(outdir, exist_ok=True)
     nnode = (N + 1) ** 3 if N else 0
+    if Fn1 is not None and N:
+        from .f2disp import f2disp
+        write_nodal(os.path.join(outdir, flat_name("displacements", step)), step, f2disp(Fn1, N, lengths), structure, N ** 3)
     write_flat(os.path.join(outdir, flat_name("stresses", step)), "stresses", step, urcs_n1[:, :6], structure, nnode)
     write_flat(os.path.join(outdir, flat_name("strains", step)), "strains", step, eps_n1[:, :6], structure, nnode)

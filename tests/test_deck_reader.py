@@ -217,7 +217,7 @@ def test_cli_host_glue_with_the_oracle_standing_in(tmp_path, monkeypatch, capsys
                         log=f"     Now starting step: {first + 1:7d}\\n")
 
         def download(self, name, layout=0):
-            return {"URCS_N1": self.o.urcs_n1, "EPS_N1": self.o.eps_n1}[name]
+            return {"URCS_N1": self.o.urcs_n1, "EPS_N1": self.o.eps_n1, "FN1": self.o.Fn1}[name]
 
         def material_failures(self):
             return (0, 0)
@@ -227,7 +227,14 @@ def test_cli_host_glue_with_the_oracle_standing_in(tmp_path, monkeypatch, capsys
     assert rc == 0
     out = capsys.readouterr().out
     assert out.count("Now starting step") == 4
-    assert sorted(os.listdir(tmp_path)) == ["wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text"]
+    assert sorted(os.listdir(tmp_path)) == ["wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text",
+                                            "wnd00002_text", "wnd00004_text"]
+    # nodal displacements recovered from F: 8^3 nodes, the far corner carries the applied mean stretch
+    nod = open(tmp_path / "wnd00004_text").read().splitlines()[7:]
+    assert len(nod) == 512
+    bc = deck("test_mm10.in").BC_all()[3]
+    far = np.array([float(nod[-1][15 * k:15 * k + 15]) for k in range(3)])
+    assert np.abs(far - 100.0 * (bc.reshape(3, 3) - np.eye(3)).sum(axis=1)).max() <= 2e-2 * np.abs(far).max()
     rows = open(tmp_path / "wes00004_text").read().splitlines()[7:]
     assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
     assert "solution timings" in out and "pcg solution vector update" in out and "patran output" in out

@@ -1,0 +1,61 @@
+"""cpfft_b200/f2disp.py (DCT-I solution of the reference's least-squares displacement recovery) against a literal
+assembly + dense solve of the same normal equations (tests/py_f2disp.py), and against closed forms."""
+import numpy as np
+import pytest
+
+from cpfft_b200.f2disp import f2disp, rhs, node_coordinates
+from py_f2disp import f2disp_literal
+
+
+@pytest.mark.parametrize("N,lengths", [(2, (1.0, 1.0, 1.0)), (3, (1.0, 1.0, 1.0)), (4, (2.0, 1.0, 0.5)), (5, (1.0, 3.0, 1.0))])
+def test_matches_literal_normal_equations(N, lengths):
+    rng = np.random.default_rng(N)
+    F = np.zeros((9, N ** 3)); F[[0, 4, 8]] = 1.0
+    F += 0.05 * rng.standard_normal(F.shape)
+    u_ref, A, b_ref = f2disp_literal(F, N, lengths)
+    b = rhs(F, N, lengths).reshape(3, -1).T
+    assert np.abs(b - b_ref).max() <= 1e-13 * np.abs(b_ref).max()
+    assert np.abs(b.sum(axis=0)).max() <= 1e-12 * np.abs(b).max()              # compatible right-hand side
+    u = f2disp(F, N, lengths)
+    assert np.abs(u - u_ref).max() <= 1e-10 * np.abs(u_ref).max()
+    assert np.abs(u[0]).max() == 0.0                                           # node 1 is pinned (f2disp.f:171)
+
+
+def test_homogeneous_gradient_is_reproduced_exactly():
+    """F constant: the trilinear mesh carries x = F X, u = (F - I) X"""
+    N, lengths = 6, (1.0, 2.0, 1.5)
+    Fc = np.array([[1.02, 0.01, 0.0], [0.03, 0.97, -0.02], [0.0, 0.015, 1.01]])
+    F = np.repeat(Fc.reshape(9, 1), N ** 3, axis=1)
+    X = node_coordinates(N, lengths)
+    u = f2disp(F, N, lengths)
+    assert np.abs(u - X @ (Fc - np.eye(3)).T).max() <= 1e-13
+
+
+def test_node_order_is_x_fastest():
+    X = node_coordinates(2, (1.0, 1.0, 1.0))
+    assert X.shape == (27, 3)
+    assert np.allclose(X[1], (0.5, 0.0, 0.0)) and np.allclose(X[3], (0.0, 0.5, 0.0)) and np.allclose(X[9], (0.0, 0.0, 0.5))
+
+
+def test_nodal_displacement_file(tmp_path):
+    """wnd#####_text of oudisp (ouresult.f:56-124): nodal-results header, 3e15.6 per node, node order x fastest;
+    the deck's `sizes of x_direction ...` card gives the mesh lengths (FFT_finite_3d.f:97-114)"""
+    from helpers import deck
+    from cpfft_b200.results import write_step, flat_name
+    p = deck("test_mm10.in")
+    assert p.lengths == (100.0, 100.0, 100.0)
+    assert flat_name("displacements", 3) == "wnd00003_text"
+    N = p.N
+    Fc = np.array([[1.01, 0.0, 0.0], [0.0, 0.997, 0.0], [0.0, 0.0, 0.997]])
+    F = np.repeat(Fc.reshape(9, 1), N ** 3, axis=1)
+    write_step(str(tmp_path), 3, np.zeros((N ** 3, 9)), np.zeros((N ** 3, 6)), p.name, N, Fn1=F, lengths=p.lengths)
+    lines = open(tmp_path / "wnd00003_text").read().splitlines()
+    assert lines[1].startswith("#  WARP3D nodal results: displacements")
+    assert lines[3] == f"#  Model nodes, elements: {(N + 1) ** 3:8d}{N ** 3:8d}" and lines[5] == "#  Load(time) step:        3"
+    rows = lines[7:]
+    assert len(rows) == (N + 1) ** 3 and all(len(r) == 45 for r in rows)
+    u = np.array([[float(r[15 * k:15 * k + 15]) for k in range(3)] for r in rows])
+    assert np.abs(u[0]).max() == 0.0
+    assert abs(u[N, 0] - 1.0) <= 1e-6 and abs(u[-1, 0] - 1.0) <= 1e-6            # 1 % of l_x = 100 at the x = l_x face
+    assert abs(u[-1, 1] + 0.3) <= 1e-6 and abs(u[-1, 2] + 0.3) <= 1e-6
+    assert (tmp_path / "wes00003_text").exists() and (tmp_path / "wee00003_text").exists()
