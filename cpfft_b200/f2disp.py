@@ -3,15 +3,23 @@ the post-processing step behind the ``wnd#####_text`` result file (``oudisp``, s
 output code, not part of the GPU hot path.
 
 What the reference computes: on the (N+1)^3-node mesh of trilinear 8-node bricks that ``blkgen`` lays over the box
-[0,l_x] x [0,l_y] x [0,l_z] (nodes and elements numbered x fastest, src/oumodel.f:923-955), the current nodal positions
+[0,l_x] x [0,l_y] x [0,l_z] (src/oumodel.f:44-62, 178-330), the current nodal positions
 x (one scalar problem per component c) that fit the element gradients in the least-squares sense,
 
     A x_c = b_c,   A = sum_e int_e B^T B        (8-point Gauss, ``form_BTB`` f2disp.f:202-445)
                    b_c = sum_e V_e B_e(0)^T F_e^T(:, c)   (1-point Gauss, f2disp.f:104-131)
 
-with node 1 removed (x = 0 there), solved by PARDISO; the displacement is u = x - X (f2disp.f:171-176).  Element
-``ii`` takes the deformation gradient of voxel ``ii`` (f2disp.f:64-66, 119-127) -- literally, although the voxel index
-runs z fastest (FFT_init.f:311-318) and the element index x fastest; that pairing is the reference's and is kept.
+with node 1 removed (x = 0 there), solved by PARDISO; the displacement is u = x - X (f2disp.f:171-176).  Nodes are
+numbered x fastest (``vblkn``, oumodel.f:932-955), elements z fastest (``vblke`` loops i, j, k with k innermost,
+oumodel.f:735-745), i.e. element ``ii`` is voxel ``ii`` of the solver (FFT_init.f:311-318) and takes its deformation
+gradient (f2disp.f:64-66, 119-127).
+
+Not reproduced: ``form_BTB`` stores the upper triangle and adds A_local(kk, ll), kk <= ll, at (row of node kk, column of
+node ll) (f2disp.f:428-439); for the local pairs (3,4) and (7,8) the global numbers are in the other order, the column
+search falls through and the value lands on the first entry of the next row.  Those two entries couple nodes that
+share an x-edge; on cubic cells (l_x = l_y = l_z, every shipped deck) the edge-neighbour entry of the trilinear
+stiffness is exactly zero, so the slip is harmless there and the reference solves the equations written above.  For
+unequal cell lengths it does not, and what it solves instead is an accident of its storage scheme.
 
 How it is solved here: on the uniform mesh A = Kx (x) My (x) Mz + Mx (x) Ky (x) Mz + Mx (x) My (x) Kz with the 1-D
 linear-element stiffness K = tridiag(-1, 2, -1)/h (corner entries 1/h) and mass M = h tridiag(1, 4, 1)/6 (corners
@@ -37,10 +45,11 @@ def node_coordinates(N: int, lengths=(1.0, 1.0, 1.0)) -> np.ndarray:
 
 def rhs(Fn1: np.ndarray, N: int, lengths=(1.0, 1.0, 1.0)) -> np.ndarray:
     """b (3, N+1, N+1, N+1) indexed [component, kz, jy, ix]: sum over the 8 elements of a node of
-    V_e dN/dX_J(centre) F_cJ (f2disp.f:104-142).  Fn1: (9, N^3), row-major F per voxel (column ii = element ii)."""
+    V_e dN/dX_J(centre) F_cJ (f2disp.f:104-142).  Fn1: (9, N^3), row-major F per voxel, voxels in solver order."""
     h = [float(l) / N for l in lengths]
     V = h[0] * h[1] * h[2]
-    F = np.asarray(Fn1, dtype=np.float64).reshape(3, 3, N, N, N)          # [c, J, ek, ej, ei]
+    # voxel / element index ii = x N^2 + y N + z  ->  [c, J, ek, ej, ei] like the node arrays
+    F = np.asarray(Fn1, dtype=np.float64).reshape(3, 3, N, N, N).transpose(0, 1, 4, 3, 2)
     b = np.zeros((3, N + 1, N + 1, N + 1))
     for sz in (0, 1):
         for sy in (0, 1):

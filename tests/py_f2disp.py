@@ -27,9 +27,9 @@ def f2disp_literal(Fn1, N, lengths=(1.0, 1.0, 1.0)):
     b = np.zeros((nn, 3))
     gp = 1.0 / np.sqrt(3.0)
     e = 0
-    for ek in range(N):
+    for ei in range(N):                                                 # elements: z fastest (vblke, oumodel.f:735-745)
         for ej in range(N):
-            for ei in range(N):
+            for ek in range(N):
                 ids = [node(ei + (int(s[0]) + 1) // 2, ej + (int(s[1]) + 1) // 2, ek + (int(s[2]) + 1) // 2) for s in _SIGNS]
                 xe = X[ids]                                             # (8, 3)
                 for q in _SIGNS * gp:                                   # 8-point rule, weights 1

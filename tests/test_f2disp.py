@@ -59,3 +59,24 @@ def test_nodal_displacement_file(tmp_path):
     assert abs(u[N, 0] - 1.0) <= 1e-6 and abs(u[-1, 0] - 1.0) <= 1e-6            # 1 % of l_x = 100 at the x = l_x face
     assert abs(u[-1, 1] + 0.3) <= 1e-6 and abs(u[-1, 2] + 0.3) <= 1e-6
     assert (tmp_path / "wes00003_text").exists() and (tmp_path / "wee00003_text").exists()
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_layered_stretch_is_integrated_along_the_right_axis(axis):
+    """F_aa varying with the voxel coordinate a only (a compatible field the trilinear mesh represents exactly):
+    u_a(node) = sum of h (F_aa - 1) over the layers below it, constant across the other two directions.  Pins
+    the pairing of the solver's voxel order (x slowest, FFT_init.f:311-318) with the mesh (elements z fastest,
+    nodes x fastest, oumodel.f:735-745, 932-955)."""
+    N, lengths = 5, (1.0, 1.0, 1.0)
+    stretch = 1.0 + 0.01 * np.arange(1, N + 1)
+    idx = np.indices((N, N, N))[axis].ravel()                     # voxel order: x slowest, z fastest
+    F = np.zeros((9, N ** 3)); F[[0, 4, 8]] = 1.0
+    F[4 * axis] = stretch[idx]
+    u = f2disp(F, N, lengths).T.reshape(3, N + 1, N + 1, N + 1)   # [c, kz, jy, ix]
+    want = np.concatenate([[0.0], np.cumsum((stretch - 1.0) / N)])
+    shape = [1, 1, 1]; shape[2 - axis] = N + 1                    # node arrays are [kz, jy, ix]
+    assert np.abs(u[axis] - want.reshape(shape)).max() <= 1e-13
+    others = [c for c in range(3) if c != axis]
+    assert np.abs(u[others]).max() <= 1e-13
+    u_ref, _, _ = f2disp_literal(F, N, lengths)
+    assert np.abs(u.reshape(3, -1).T - u_ref).max() <= 1e-12
