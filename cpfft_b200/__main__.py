@@ -10,11 +10,12 @@ module is host glue (deck reader, printing, file writing)."""
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 import time
 
 from . import Solver, read_deck
-from .results import write_step
+from .results import write_step, write_model
 
 
 def main(argv=None):
@@ -27,6 +28,9 @@ def main(argv=None):
     prob = read_deck(args.deck)
     nstep = args.steps or prob.nstep
     print(f" >> deck {args.deck}: grid {prob.N}^3, {len(prob.materials)} material(s), {nstep} load step(s)")
+    if prob.model_file:                      # `output model "<file>"`: the mesh the nodal results refer to
+        mf = write_model(os.path.join(args.outdir, os.path.basename(prob.model_file)), prob.N, prob.lengths, prob.name)
+        print(f" >>>>>> Model description file: {mf}")
     s = Solver(prob, device=args.device)
     t0 = time.time()
     s.drive_eps_sig(1, 0)

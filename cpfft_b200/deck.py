@@ -252,7 +252,7 @@ def read_deck(path: str) -> Problem:
     isNBC = np.zeros(9, dtype=np.int32)
     mults: dict = {}
     tolNR, tolPCG, maxIter, tstep = 1e-5, 1e-10, 10, 1.0
-    name, out_steps = "", ()
+    name, out_steps, model_file = "", (), ""
     lengths = [1.0, 1.0, 1.0]                # l_x, l_y, l_z (mod_fft.f:8); only the output mesh uses them
     while True:
         line = lines.next()
@@ -312,11 +312,12 @@ def read_deck(path: str) -> Problem:
         elif key == "project":
             name = toks[1] if len(toks) > 1 else ""
         elif key == "output":
-            # `output results steps <integer list>` selects the steps written by ouresult;
-            # `output model ...` (mesh files) is not part of the hot path
+            # `output results steps <integer list>` selects the steps written by ouresult
             low = [t.lower() for t in toks]
             if len(low) > 2 and low[1].startswith("result") and low[2].startswith("step"):
                 out_steps = tuple(_int_list(toks[3:]))
+            elif len(low) > 2 and low[1] == "model":          # `output model "<file>"` (oudriv.f:22, oumodel.f:63-73)
+                model_file = toks[2].strip('"\'')
         elif key == "sizes":
             # `sizes of x_direction <l_x> y_direction <l_y> z_direction <l_z>` (FFT_finite_3d.f:97-114): the
             # cell lengths.  formG ignores them (FFT_init.f:272-340); they size the output mesh of oumodel / f2disp
@@ -361,4 +362,4 @@ def read_deck(path: str) -> Problem:
     return Problem(N=N, materials=materials, crystals=cry_list, matlist=elem_mat, angles=angles,
                    FP_max=FP_max, isNBC=isNBC, mults=mult_arr, tolNR=tolNR, tolPCG=tolPCG,
                    maxIter=maxIter, tstep=tstep, name=name, out_steps=out_steps, crystal_ids=crystal_ids,
-                   lengths=tuple(lengths))
+                   lengths=tuple(lengths), model_file=model_file)

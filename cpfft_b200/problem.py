@@ -137,6 +137,7 @@ class Problem:
     name: str = ""                           # `project` card (stname)
     out_steps: tuple = ()                    # `output results steps <list>` (oudriv.f:82-166)
     lengths: tuple = (1.0, 1.0, 1.0)         # `sizes of x_direction .. ` l_x, l_y, l_z (output mesh only)
+    model_file: str = ""                     # `output model "<file>"`: mesh description file (oumodel.f)
     crystal_ids: np.ndarray = None           # (N3,ncmax) 1-based crystal numbers (crystal_input file) or None
 
     @property

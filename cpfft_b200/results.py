@@ -78,3 +78,37 @@ def write_step(outdir: str, step: int, urcs_n1: np.ndarray, eps_n1: np.ndarray, 
         write_nodal(os.path.join(outdir, flat_name("displacements", step)), step, f2disp(Fn1, N, lengths), structure, N ** 3)
     write_flat(os.path.join(outdir, flat_name("stresses", step)), "stresses", step, urcs_n1[:, :6], structure, nnode)
     write_flat(os.path.join(outdir, flat_name("strains", step)), "strains", step, eps_n1[:, :6], structure, nnode)
+
+
+def element_incidences(N: int) -> np.ndarray:
+    """(N^3, 8) 1-based node numbers of the 8-node bricks ``blkgen`` generates (oumodel.f:693-745): elements in the
+    solver's voxel order (x slowest, z fastest), nodes numbered x fastest, local order counter-clockwise bottom
+    face then top face."""
+    n1 = N + 1
+    i, j, k = np.meshgrid(np.arange(N), np.arange(N), np.arange(N), indexing="ij")
+    base = (1 + i + n1 * j + n1 * n1 * k).ravel()                       # node (i, j, k)
+    off = np.array([0, 1, 1 + n1, n1, n1 * n1, 1 + n1 * n1, 1 + n1 + n1 * n1, n1 + n1 * n1])
+    return base[:, None] + off[None, :]
+
+
+def write_model(path: str, N: int, lengths=(1.0, 1.0, 1.0), structure: str = "") -> str:
+    """The model description file of ``output model "<name>"`` (``ModelOut`` oumodel.f:11-120 -> ``oumodel_flat``
+    ouneut.f:19-200, text form, Patran convention): header, ``2i9`` node / element counts, ``3e25.13`` coordinates
+    per node, ``i4,i4,27i8`` per element (Patran type 8 = hex, block 1, 8 incidences, zero fill).  Returns the
+    file name (``.text`` appended when the name has no extension, ouneut.f:67-74)."""
+    from .f2disp import node_coordinates
+    if not (path.endswith(".text") or path.endswith(".str")):
+        path += ".text"
+    X = node_coordinates(N, lengths)
+    inc = element_incidences(N)
+    with open(path, "w") as f:
+        f.write("#\n#  " + ("Structure: " + structure.strip()).rstrip() + "\n")
+        f.write("#\n#  Created: " + f"{time.strftime('%b %d %Y'):<12s}" + "  " + time.strftime("%H:%M:%S") + "\n#\n")
+        f.write("#  Convention: " + f"{'Patran element type and node ordering':<40s}" + "\n#\n")
+        f.write(f"{X.shape[0]:9d}{inc.shape[0]:9d}\n")
+        for row in X:
+            f.write("".join(fortran_e(float(v), 25, 13) for v in row) + "\n")
+        tail = "".join(f"{0:8d}" for _ in range(19))
+        for row in inc:
+            f.write(f"{8:4d}{1:4d}" + "".join(f"{int(v):8d}" for v in row) + tail + "\n")
+    return path

@@ -80,3 +80,34 @@ def test_layered_stretch_is_integrated_along_the_right_axis(axis):
     assert np.abs(u[others]).max() <= 1e-13
     u_ref, _, _ = f2disp_literal(F, N, lengths)
     assert np.abs(u.reshape(3, -1).T - u_ref).max() <= 1e-12
+
+
+def test_model_description_file(tmp_path):
+    """`output model "<file>"`: oumodel_flat text form (ouneut.f:19-200): header, 2i9 counts, 3e25.13 per node,
+    i4,i4,27i8 per element (Patran hex = type 8, block 1, 8 incidences, zero fill); node / element numbering of
+    blkgen (oumodel.f:693-745, 932-955)"""
+    from helpers import deck
+    from cpfft_b200.results import write_model, element_incidences
+    p = deck("test_mm10.in")
+    assert p.model_file == "RM_model_flat"
+    N = 3
+    path = write_model(str(tmp_path / p.model_file), N, (3.0, 6.0, 9.0), p.name)
+    assert path.endswith("RM_model_flat.text")
+    lines = open(path).read().splitlines()
+    assert lines[0] == "#" and lines[1] == "#  Structure: test" and lines[3].startswith("#  Created: ")
+    assert lines[5].startswith("#  Convention: Patran element type and node ordering") and lines[6] == "#"
+    assert lines[7] == f"{64:9d}{27:9d}"
+    nodes, elems = lines[8:8 + 64], lines[8 + 64:]
+    assert len(elems) == 27 and all(len(r) == 75 for r in nodes) and all(len(r) == 8 + 27 * 8 for r in elems)
+    xyz = np.array([[float(r[25 * k:25 * k + 25]) for k in range(3)] for r in nodes])
+    assert np.allclose(xyz[1], (1.0, 0.0, 0.0)) and np.allclose(xyz[4], (0.0, 2.0, 0.0)) and np.allclose(xyz[16], (0.0, 0.0, 3.0))
+    assert np.allclose(xyz[-1], (3.0, 6.0, 9.0))
+    first = [int(elems[0][4 * k:4 * k + 4]) for k in range(2)] + [int(elems[0][8 + 8 * k:16 + 8 * k]) for k in range(27)]
+    assert first == [8, 1, 1, 2, 6, 5, 17, 18, 22, 21] + [0] * 19
+    inc = element_incidences(N)
+    assert inc[1].tolist() == [17, 18, 22, 21, 33, 34, 38, 37]           # element 2 is the next one in z (z fastest)
+    assert inc[-1].max() == 64
+    # every brick is right-handed with positive volume on this numbering
+    X = xyz[inc - 1]                                                       # (nel, 8, 3)
+    vol = np.einsum("ei,ei->e", np.cross(X[:, 1] - X[:, 0], X[:, 3] - X[:, 0]), X[:, 4] - X[:, 0])
+    assert np.allclose(vol, 1.0 * 2.0 * 3.0)
