@@ -44,7 +44,7 @@ def write_flat(path: str, kind: str, step: int, values: np.ndarray, structure: s
         f.write(f"#  WARP3D element results: {kind:<15s}\n")
         f.write(f"#  Structure name: {structure[:8]:<8s}\n")
         f.write(f"#  Model nodes, elements: {nnode:8d}{nelem:8d}\n")
-        f.write(f"#  {time.strftime('%a %b %d %H:%M:%S %Y'):<24s}\n")
+        f.write(f"#  {time.strftime('%a %b %e %H:%M:%S %Y'):<24s}\n")
         f.write(f"#  Load(time) step: {step:8d}\n")
         f.write("#\n")
         zero = fortran_e(0.0)
@@ -60,7 +60,7 @@ def write_nodal(path: str, step: int, u: np.ndarray, structure: str = "", nelem:
         f.write(f"#  WARP3D nodal results: {'displacements':<15s}\n")
         f.write(f"#  Structure name: {structure[:8]:<8s}\n")
         f.write(f"#  Model nodes, elements: {u.shape[0]:8d}{nelem:8d}\n")
-        f.write(f"#  {time.strftime('%a %b %d %H:%M:%S %Y'):<24s}\n")
+        f.write(f"#  {time.strftime('%a %b %e %H:%M:%S %Y'):<24s}\n")
         f.write(f"#  Load(time) step: {step:8d}\n")
         f.write("#\n")
         for row in u:
@@ -103,7 +103,7 @@ def write_model(path: str, N: int, lengths=(1.0, 1.0, 1.0), structure: str = "")
     inc = element_incidences(N)
     with open(path, "w") as f:
         f.write("#\n#  " + ("Structure: " + structure.strip()).rstrip() + "\n")
-        f.write("#\n#  Created: " + f"{time.strftime('%b %d %Y'):<12s}" + "  " + time.strftime("%H:%M:%S") + "\n#\n")
+        f.write("#\n#  Created: " + f"{time.strftime('%b %e %Y'):<12s}" + "  " + time.strftime("%H:%M:%S") + "\n#\n")
         f.write("#  Convention: " + f"{'Patran element type and node ordering':<40s}" + "\n#\n")
         f.write(f"{X.shape[0]:9d}{inc.shape[0]:9d}\n")
         for row in X:
