@@ -128,6 +128,15 @@ def _read_crystal(lines: _Lines, toks: List[str], crystals: dict):
             if pt[i + 1] != "nr":
                 raise DeckError("only solver nr is supported")
             i += 2
+        elif k == "tang_calc":
+            # 0 = the analytical tangent (default, mod_crystals.f:1750-1759); 1-4 select finite-difference /
+            # complex-step checks of the reference's debugging paths
+            if int(float(pt[i + 1])) != 0:
+                raise DeckError("only tang_calc 0 is supported")
+            i += 2
+        elif k in ("gpall", "gpp", "delem", "dstep", "diter"):
+            # debug print selectors of mm10, one argument each (incrystal.f:953-986): no effect on the solution
+            i += 2
         elif k in _CRYSTAL_NUM:
             setattr(c, _CRYSTAL_NUM[k], float(pt[i + 1])); i += 2
         else:

@@ -239,3 +239,24 @@ def test_cli_host_glue_with_the_oracle_standing_in(tmp_path, monkeypatch, capsys
     rows = open(tmp_path / "wes00004_text").read().splitlines()[7:]
     assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
     assert "solution timings" in out and "pcg solution vector update" in out and "patran output" in out
+
+
+def test_crystal_debug_and_tangent_keywords(tmp_path):
+    """`tang_calc 0` and the debug print selectors (gpall on|off, gpp / delem / dstep / diter <int>, incrystal.f:
+    953-986) are accepted and change nothing; another tang_calc or an unknown property is an error"""
+    from cpfft_b200.deck import read_deck, DeckError
+    src = open(os.path.join(DECKS, "test_mm10.in")).read()
+    assert "harden_n" in src
+    ref = deck("test_mm10.in")
+    for extra, ok in (("tang_calc 0 gpall off gpp 1 delem 3 dstep 2 diter 1", True), ("tang_calc 2", False), ("rho_0 1.0", False)):
+        path = tmp_path / "d.in"
+        path.write_text(src.replace("harden_n", extra + " harden_n", 1))
+        for f in ("angle_bc.in", "angle2.in"):                      # the deck names its angle file relative to itself
+            if os.path.exists(os.path.join(DECKS, f)):
+                (tmp_path / f).write_text(open(os.path.join(DECKS, f)).read())
+        if ok:
+            p = read_deck(str(path))
+            assert p.crystals[0] == ref.crystals[0]
+        else:
+            with pytest.raises(DeckError):
+                read_deck(str(path))
