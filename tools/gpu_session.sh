@@ -49,6 +49,8 @@ case "$MODE" in
   first)    # everything written without a GPU, cheapest first; every leg has its own timeout and log
     timeout 200 python -m pytest tests/test_zz_gpu_new_features.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_zz_tests.log
     "$0" ab-lf "$TAG"; "$0" ab-pk1 "$TAG"; "$0" ab-tma "$TAG"
+    timeout 150 python bench.py --variant mts --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench256_mts.json 2> gpurun_out/${TAG}_bench256_mts.err
+    tail -c 300 gpurun_out/${TAG}_bench256_mts.json
     "$0" bench "$TAG" ;;
   *) echo "unknown mode $MODE"; exit 2 ;;
 esac
