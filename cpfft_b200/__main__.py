@@ -25,6 +25,7 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--steps", type=int, default=0, help="run only the first STEPS load steps")
     args = ap.parse_args(argv)
+    os.makedirs(args.outdir, exist_ok=True)
     prob = read_deck(args.deck)
     nstep = args.steps or prob.nstep
     print(f" >> deck {args.deck}: grid {prob.N}^3, {len(prob.materials)} material(s), {nstep} load step(s)")

@@ -13,6 +13,12 @@ TOL_VOXEL = 1.0e-9
 TOL_MACRO = 1.0e-10
 
 
+# files `python -m cpfft_b200 test_mm10.in --steps 4` leaves in --outdir (ouresult.f:56-124, oumodel.f); one list for
+# the CPU stand-in test and the GPU test so they cannot drift apart
+CLI_MM10_FILES = ["RM_model_flat.text", "wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text",
+                  "wnd00002_text", "wnd00004_text"]
+
+
 def deck(name):
     return read_deck(os.path.join(DECKS, name))
 

@@ -227,8 +227,8 @@ def test_cli_host_glue_with_the_oracle_standing_in(tmp_path, monkeypatch, capsys
     assert rc == 0
     out = capsys.readouterr().out
     assert out.count("Now starting step") == 4
-    assert sorted(os.listdir(tmp_path)) == ["RM_model_flat.text", "wee00002_text", "wee00004_text", "wes00002_text",
-                                            "wes00004_text", "wnd00002_text", "wnd00004_text"]
+    from helpers import CLI_MM10_FILES
+    assert sorted(os.listdir(tmp_path)) == CLI_MM10_FILES
     assert open(tmp_path / "RM_model_flat.text").read().splitlines()[7] == f"{512:9d}{343:9d}"
     # nodal displacements recovered from F: 8^3 nodes, the far corner carries the applied mean stretch
     nod = open(tmp_path / "wnd00004_text").read().splitlines()[7:]

@@ -177,7 +177,7 @@ def test_cli_runs_a_deck_end_to_end(tmp_path):
     import re
     import subprocess
     import sys
-    from helpers import DECKS
+    from helpers import DECKS, CLI_MM10_FILES
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "cpfft_b200", os.path.join(DECKS, "test_mm10.in"), "--outdir", str(tmp_path),
                           "--steps", "4"], capture_output=True, text=True, cwd=root)
@@ -187,7 +187,7 @@ def test_cli_runs_a_deck_end_to_end(tmp_path):
     assert len(re.findall(r"^       Initial residual\s+[-0-9.]+D[+-]\d\d$", txt, flags=re.M)) == 4
     its = re.findall(r"^       Iteration\s+(\d+)\s+residual\s+([-0-9.]+D[+-]\d\d)$", txt, flags=re.M)
     assert len(its) == 1 + 1 + 3 + 3          # Newton iterations of steps 1-4 of test_mm10.in
-    assert sorted(os.listdir(tmp_path)) == ["wee00002_text", "wee00004_text", "wes00002_text", "wes00004_text"]
+    assert sorted(os.listdir(tmp_path)) == CLI_MM10_FILES
     rows = open(tmp_path / "wes00004_text").read().splitlines()[7:]
     assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
 
