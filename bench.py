@@ -2,10 +2,17 @@
 """bench.py -- voxel-iterations/s of the CPFFT hot path on B200.
 
 A "step" is one load step of FFT_nr3 (FFT_nr3.f:51-185) on the synthetic Voronoi polycrystal of
-BASELINE.json (1000 random-orientation fcc grains, mm10 / Voce): Newton loop, one
-drive_eps_sig sweep per Newton iteration, one CG solve (tens of G_K_dF applications) per
-Newton iteration.  metric = voxels x G_K_dF applications / second (SURVEY.md 8d "VI/s": one
-iteration = one Green-operator application with the material update amortised).
+BASELINE.json (1000 random-orientation fcc grains, mm10 / Voce) under the SURVEY.md 8d loading:
+finite-strain uniaxial tension, F_xx driven at 0.1 % per step with P_yy = P_zz = 0 -- the
+stress-BC loop (FFT_nr3.f:127-165) around the Newton loop, one drive_eps_sig sweep and one CG
+solve per Newton iteration, tangent_homo (9 CG solves) per stress iteration.  `--strain-bc` is the
+pure-strain variant for stage timing.  metric = voxels x G_K_dF applications / second (SURVEY.md
+8d "VI/s": one iteration = one Green-operator application with the material update amortised).
+
+Every timed step goes through the C ABI with HOST buffers: pinned F is uploaded, cpfft_FFT_nr3 runs
+the load step, F and P are downloaded.  `value` sums the device time of the K steps with the inputs
+already resident (event after the upload -> event before the download); `e2e` is the time of the
+same K steps including the copies.  Both are the max over ranks.
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -29,7 +36,10 @@ sys.path.insert(0, ROOT)
 METRIC = "voxel-iterations/sec (mm10 update + FFT/Green step)"
 UNIT = "voxel-iterations/s"
 GRID_FOR_GPUS = {1: 256, 2: 320, 4: 400, 8: 512}   # ~16.8 M voxels per GPU (weak scaling)
-CPU_SAMPLE_N = 32                                   # bounded CPU sample of the same workload
+CPU_SAMPLE_N = 64                                   # bounded CPU sample of the same workload: 64^3 is out of the host LLC
+CPU_SAMPLE_APPLIES = 40                             # G_K_dF applications (CG iterations) per reference "step"
+CPU_SWEEP_EVERY = 5                                 # one drive_eps_sig sweep per 5 x 40 = 200 applications: the GPU workload's mix
+PARITY_FIXTURE = os.path.join(ROOT, "tests", "golden", "poly32_strain.npz")
 
 
 def measured_peaks():
@@ -90,54 +100,77 @@ class ClockSampler:
 
 def run_reference(args):
     """The reference's CPU path: no Fortran compiler / MKL exists in this image, so this is the
-    C++/OpenMP oracle port (oracle/), all host threads, on a bounded sample of the workload."""
+    C++/OpenMP oracle port (oracle/), all host threads, on a BOUNDED sample of the workload.
+
+    The GPU workload at 256^3 costs the oracle hours per load step, so a reference "step" is a slice
+    of one: CPU_SAMPLE_APPLIES iterations of a real CG solve (G_K_dF with the K4 contraction + the CG
+    vector work, FFT_nr3.f:214-360) on the 64^3 polycrystal (same generator, grains scaled with the
+    volume, out of the LLC) in the plastic regime, and one drive_eps_sig sweep every CPU_SWEEP_EVERY
+    steps -- 1 sweep per 200 applications, the mix the stress-BC load steps of the GPU arm have."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import ctypes as C
     from oracle import Oracle
     from cpfft_b200.polycrystal import polycrystal
     N = args.cpu_n
-    prob = polycrystal(N, ngrains=max(8, int(1000 * (N / 256.0) ** 3)))
+    ngr = max(8, int(round(args.grains * (N / 256.0) ** 3)))
+    prob = polycrystal(N, ngrains=ngr, stress_bc=not args.strain_bc)
     cores = os.cpu_count() or 1
     o = Oracle(prob, threads=cores)
+    dp = C.POINTER(C.c_double)
+    n3 = N ** 3
+    # bring the sample into the plastic regime without paying for converged load steps: two 0.2 % increments
+    # of the macroscopic stretch, each followed by the plastic sweep and a committed state (drive_eps_sig +
+    # update, FFT_nr3.f:107-123, 173-179), then the 0.1 % increment of a benchmark load step
     o.drive_eps_sig(1, 0)
+    Fbar = np.zeros((9, 1))
+    step = 0
+    for inc in (0.002, 0.002, 0.001):
+        step += 1
+        Fbar[0] += inc; Fbar[4] -= 0.3 * inc; Fbar[8] -= 0.3 * inc
+        o.Fn1[:] = np.eye(3).reshape(9, 1) + Fbar
+        if o.drive_eps_sig(step, 1):
+            raise SystemExit("oracle sweep failed while preparing the CPU sample")
+        if inc != 0.001:
+            o.Fn[:] = o.Fn1
+            o.update()
+    b = -o.G_K_dF(o.Pn1, 0)                      # right-hand side of the Newton correction (FFT_nr3.f:110-111)
+    x = np.zeros_like(b)
     W, K = args.warmup, args.steps
-    o.FFT_nr3(nstep=W)        # warm-up load steps (also brings the sample into the plastic regime)
-    applies, secs = 0, 0.0
-    bc = prob.BC_all()
-    for k in range(K):        # K further steps, state persists inside the oracle model
-        step_bc = np.ascontiguousarray(bc[W + k:W + k + 1])
-        res = _oracle_steps(o, step_bc, W + k + 1)
-        applies += int(res["counters"][0]); secs += float(res["buckets"][2])
-    value = N ** 3 * applies / secs
+    cnt, sec = np.zeros(3, dtype=np.int64), np.zeros(2)
+
+    def sample(k):
+        t0 = time.perf_counter()
+        if k % CPU_SWEEP_EVERY == 0:
+            o.drive_eps_sig(step, 1)
+        it, rr = C.c_int32(0), C.c_double(0)
+        rc = o.L.orc_fftPcg_capped(o.h, b.ctypes.data_as(dp), x.ctypes.data_as(dp), 1e-14, CPU_SAMPLE_APPLIES, C.byref(it), C.byref(rr))
+        assert rc == 0 and it.value == CPU_SAMPLE_APPLIES, (rc, it.value)
+        return time.perf_counter() - t0, it.value
+
+    for k in range(W):
+        sample(k)
+    secs, applies = 0.0, 0
+    for k in range(K):
+        dt, it = sample(W + k)
+        secs += dt; applies += it
+    value = n3 * applies / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal, fcc mm10/Voce, pure-strain uniaxial "
-                               f"(bounded CPU sample of the {GRID_FOR_GPUS.get(args.gpus, 256)}^3 GPU workload)",
-                   "grid": N, "applies": applies},
+        "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal ({ngr} random-orientation fcc grains, mm10/Voce), plastic regime: "
+                               f"bounded CPU sample of the {GRID_FOR_GPUS.get(args.gpus, 256)}^3 GPU workload",
+                   "grid": N, "applies": applies, "step": f"{CPU_SAMPLE_APPLIES} CG iterations (G_K_dF + CG vector work) "
+                   f"+ one drive_eps_sig sweep every {CPU_SWEEP_EVERY} steps"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{K} plastic load steps of a {N}^3 polycrystal after {W} warm-up steps; "
+                         "sample": f"{K} x {CPU_SAMPLE_APPLIES} CG iterations + {len([k for k in range(W, W + K) if k % CPU_SWEEP_EVERY == 0])} "
+                                   f"drive_eps_sig sweeps on a {N}^3 polycrystal at 0.5 % strain after {W} warm-up samples; "
                                    f"C++/OpenMP restatement (oracle/), not the ifort/MKL binary"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def _oracle_steps(o, bc_rows, first_step):
-    """run load steps with explicit BC rows, continuing the oracle's committed state."""
-    import ctypes as C
-    n = len(bc_rows)
-    nbc = np.ascontiguousarray(o.prob.isNBC, dtype=np.int32)
-    nr = np.zeros(n, dtype=np.int32); cg = np.full((n, 64), -1, dtype=np.int32)
-    pb = np.zeros((n, 9)); bk = np.zeros(3); cnt = np.zeros(5, dtype=np.int64)
-    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
-    rc = o.L.orc_FFT_nr3_from(o.h, first_step, n, bc_rows.ctypes.data_as(dp), nbc.ctypes.data_as(ip),
-                              nr.ctypes.data_as(ip), cg.ctypes.data_as(ip), 64, pb.ctypes.data_as(dp),
-                              bk.ctypes.data_as(dp), cnt.ctypes.data_as(C.POINTER(C.c_int64)))
-    assert rc == 0, rc
-    return {"nr_iters": nr, "buckets": bk, "counters": cnt, "Pbar": pb}
 
 
 def ncu_profile_data():
@@ -189,14 +222,23 @@ def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
             ent.update({"alg_bytes_per_voxel": b, "achieved_gbs": gbs, "frac_of_hbm": gbs / peak})
         stages[name] = ent
     prof = ncu_profile_data()
-    if prof and prof.get("grid") == N and world == 1:
+    if prof and prof.get("grid") == N:
         for name, ent in prof["kernels"].items():
             if name in stages:
-                stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
-                if "fp64_flop" in ent and fp64_peak:
-                    tf = ent["fp64_flop"] / (stages[name]["ms_per_launch"] * 1e-3) / 1e12
-                    stages[name].update({"fp64_flop_per_launch_ncu": ent["fp64_flop"], "fp64_tflops": tf,
-                                         "fp64_peak_tflops_measured": fp64_peak, "frac_of_fp64": tf / fp64_peak})
+                # per-launch DRAM traffic of the same kernel on the same local problem (16.8 M voxels per GPU)
+                if world == 1 or ent.get("rank_local", False):
+                    stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
+                if "fp64_flop" in ent and fp64_peak and world == 1:
+                    # FP64 rate of the PROFILED launch: its own flop count over its own duration (the
+                    # profiled k_update_mm10 launch is a plastic sweep; elastic iter-0 sweeps are a class of their own)
+                    dur = ent.get("duration_us")
+                    tf_ncu = ent["fp64_flop"] / (dur * 1e-6) / 1e12 if dur else None
+                    tf_live = ent["fp64_flop"] / (stages[name]["ms_per_launch"] * 1e-3) / 1e12
+                    stages[name].update({"fp64_flop_per_launch_ncu": ent["fp64_flop"], "ncu_duration_us": dur,
+                                         "fp64_tflops_ncu_launch": tf_ncu, "fp64_tflops": tf_live,
+                                         "fp64_peak_tflops_measured": fp64_peak,
+                                         "frac_of_fp64_ncu_launch": tf_ncu / fp64_peak if tf_ncu else None,
+                                         "frac_of_fp64": tf_live / fp64_peak})
     cand = [k for k in stages if "achieved_gbs" in stages[k]]
     dom = max(cand, key=lambda k: stages[k]["ms_total"]) if cand else None
     roof = None
@@ -206,7 +248,59 @@ def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
                 "frac": d["achieved_gbs"] / peak, "traffic": d.get("ncu_dram_bytes_per_launch"),
                 "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
                 "alg_bytes_per_launch": d["alg_bytes_per_voxel"] * n3, "ms_per_launch": d["ms_per_launch"]}
+        if dom == "k_fwd_z_K4":
+            # the same launch against SURVEY.md 8d's operator-only figure (K4 contraction + forward z pass, no fused CG work)
+            op = algorithmic_bytes_per_voxel(dom, N)
+            roof["frac_operator_only"] = op * n3 / (d["ms_per_launch"] * 1e-3) / 1e9 / peak
+            roof["alg_bytes_per_voxel"] = d["alg_bytes_per_voxel"]; roof["alg_bytes_per_voxel_operator_only"] = op
+        # one whole CG iteration (G_K_dF with K4 + the CG vector work): its kernels' mean times against the bytes it has to move
+        names = ("k_fwd_z_K4", "k_fft_y", "k_x_green", "k_inv_z", "vector_ops", "exchange")
+        if cgits > 0 and all(k in stages for k in names[:4]):
+            it_ms = (stages["k_fwd_z_K4"]["ms_per_launch"] + 2 * stages["k_fft_y"]["ms_per_launch"] + stages["k_x_green"]["ms_per_launch"] +
+                     stages["k_inv_z"]["ms_per_launch"] + stages.get("vector_ops", {}).get("ms_total", 0.0) / cgits +
+                     stages.get("exchange", {}).get("ms_total", 0.0) / cgits)
+            roof["cg_iteration"] = {"ms": it_ms, "alg_bytes_per_voxel_fused": 1872.0, "frac_fused": 1872.0 * n3 / (it_ms * 1e-3) / 1e9 / peak,
+                                    "alg_bytes_per_voxel_survey_8d": 1224.0, "frac_survey_8d": 1224.0 * n3 / (it_ms * 1e-3) / 1e9 / peak}
     return stages, roof
+
+
+def parity_run(Solver, polycrystal, world, rank, local_rank, nccl_id, dist, torch):
+    """The 32^3, 64-grain benchmark polycrystal over 8 load steps (>= 6 plastic) on all ranks of this run against the
+    oracle's frozen output (tests/golden/poly32_strain.npz, tools/make_golden_poly.py): Newton iterations per step
+    identical, macroscopic stress <= 1e-10, F and P at 1024 sampled voxels <= 1e-9 (north_star tolerances)."""
+    if not os.path.exists(PARITY_FIXTURE):
+        return {"ok": None, "skipped": "fixture missing"}
+    g = np.load(PARITY_FIXTURE)
+    N, nstep = int(g["N"]), int(g["nstep"])
+    if N % world:
+        return {"ok": None, "skipped": f"{N} not divisible by {world} ranks"}
+    nx = N // world
+    p = polycrystal(N, ngrains=int(g["grains"]), stress_bc=bool(g["stress_bc"]), x_range=(rank * nx, (rank + 1) * nx))
+    s = Solver(p, device=local_rank, rank=rank, world=world, nccl_id=nccl_id, local_slab=True)
+    s.drive_eps_sig(1, 0)
+    r = s.FFT_nr3(nstep=nstep)
+    F, P = s.download("FN1"), s.download("PN1")
+    lo, hi = rank * s.n3, (rank + 1) * s.n3
+    idx = g["idx"]
+    mine = (idx >= lo) & (idx < hi)
+    eF = np.abs(F[:, idx[mine] - lo] - g["F"][:, mine]).max() if mine.any() else 0.0
+    eP = np.abs(P[:, idx[mine] - lo] - g["P"][:, mine]).max() if mine.any() else 0.0
+    errs = torch.tensor([eF, eP], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    s.close()
+    scale_P, scale_F = float(np.abs(g["P"]).max()), float(np.abs(g["F"]).max())
+    pbar_err = float(np.abs(r["Pbar"] - g["Pbar"]).max() / np.abs(g["Pbar"]).max())
+    cg_ref = [[int(v) for v in row if v >= 0] for row in g["cg_iters"]]
+    cg_dev = max((abs(a - b) for ra, rb in zip(r["cg_iters"], cg_ref) for a, b in zip(ra, rb)), default=0)
+    out = {"case": "poly32_strain: 32^3, 64 grains, 8 load steps, oracle fixture", "ranks": world,
+           "newton_iters": [int(v) for v in r["nr_iters"]], "newton_iters_equal": [int(v) for v in r["nr_iters"]] == [int(v) for v in g["nr_iters"]],
+           "cg_solves_equal": [len(a) for a in r["cg_iters"]] == [len(b) for b in cg_ref], "cg_iters_max_abs_diff": int(cg_dev),
+           "Pbar_rel_err": pbar_err, "F_rel_err_sampled": float(errs[0].item()) / scale_F, "P_rel_err_sampled": float(errs[1].item()) / scale_P,
+           "tolerances": {"Pbar": 1e-10, "F": 1e-9, "P": 1e-9}}
+    out["ok"] = bool(out["newton_iters_equal"] and out["cg_solves_equal"] and pbar_err <= 1e-10 and
+                     out["F_rel_err_sampled"] <= 1e-9 and out["P_rel_err_sampled"] <= 1e-9)
+    return out
 
 
 def main():
@@ -220,11 +314,15 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel CUDA events inside the timed region")
     ap.add_argument("--variant", default="voce", choices=["voce", "mts", "taylor2", "taylor4"],
                     help="workload variant for kernel measurements (NOT the BASELINE.json metric unless 'voce'): "
                          "MTS hardening law, or 2 / 4 crystals per material point (Taylor average)")
-    ap.add_argument("--stress-bc", action="store_true",
-                    help="uniaxial tension with P_yy = P_zz = 0 (stress-BC loop, tangent_homo) instead of pure strain control")
+    ap.add_argument("--strain-bc", action="store_true",
+                    help="pure strain control (F_yy = F_zz driven at -0.3 F_xx) instead of the default uniaxial tension with "
+                         "P_yy = P_zz = 0 (stress-BC loop + tangent_homo): the stage-timing variant of SURVEY.md 8d")
+    ap.add_argument("--stress-bc", action="store_true", help="(default; kept for older command lines)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 32^3 parity run against tests/golden/poly32_strain.npz")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -250,23 +348,36 @@ def main():
             if os.path.exists(library_path()):
                 break
             time.sleep(0.1)
-    nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def new_nccl_id():
+        """a fresh NCCL unique id for one Solver (one communicator), created on rank 0 and broadcast"""
+        if world == 1:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.tensor(list(Solver.nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
+        return bytes(idt.cpu().tolist())
+
     N = args.grid or GRID_FOR_GPUS.get(world, 256)
     W, K = max(args.warmup, 0), max(args.steps, 1)
+    stress_bc = not args.strain_bc
     nx = N // world
-    prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + 2 * K + 2), x_range=(rank * nx, (rank + 1) * nx),
-                       stress_bc=args.stress_bc)
+
+    # ---- N-GPU correctness before anything is timed: the 32^3 polycrystal of tests/golden (8 load steps, oracle
+    # output frozen by tools/make_golden_poly.py) on ALL ranks of this run, against the committed fixture ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_run(Solver, polycrystal, world, rank, local_rank, new_nccl_id(), dist if world > 1 else None, torch)
+
+    prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + K + 2), x_range=(rank * nx, (rank + 1) * nx),
+                       stress_bc=stress_bc)
     if args.variant != "voce":
         from cpfft_b200.polycrystal import workload_variant
         prob = workload_variant(prob, args.variant, args.grains)
-    s = Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=nccl_id, local_slab=True)
+    s = Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=new_nccl_id(), local_slab=True)
     stream = torch.cuda.ExternalStream(s.stream())
 
     def barrier():
@@ -275,23 +386,36 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    n3 = s.n3
+    hF = torch.empty(9 * n3, dtype=torch.float64).pin_memory()     # host buffers of the caller (pinned)
+    hP = torch.empty(9 * n3, dtype=torch.float64).pin_memory()
     s.drive_eps_sig(1, 0)                       # FFT_finite_3d.f:145
     step0 = 0
     for _ in range(W):                          # untimed warm-up load steps
         s.FFT_nr3(nstep=1, first=step0); step0 += 1
-    s.profile(True); s.profile_reset()
+    s.download_ptr("FN1", hF.data_ptr())
+    s.profile(not args.no_profile); s.profile_reset()
     launches0 = s.kernel_launches()
     clocks = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Event = torch.cuda.Event
+    ev0, ev1 = Event(enable_timing=True), Event(enable_timing=True)
+    marks = []
     ev0.record(stream)
     applies = sweeps = cgits = nfail = nfail_final = nsolves = 0
     t_pcg = t_sig = 0.0
     nr_hist = []
     for _ in range(K):
-        r = s.FFT_nr3(nstep=1, first=step0); step0 += 1
+        a, b = Event(enable_timing=True), Event(enable_timing=True)
+        s.upload_ptr("FN1", hF.data_ptr())                 # host -> device: the step's deformation field
+        a.record(stream)                                   # inputs resident in HBM: `value` starts here
+        r = s.FFT_nr3(nstep=1, first=step0); step0 += 1    # one load step through the ABI
+        b.record(stream)                                   # ... and stops here
+        s.download_ptr("FN1", hF.data_ptr())               # device -> host: F and P of the step
+        s.download_ptr("PN1", hP.data_ptr())
+        marks.append((a, b))
         applies += int(r["counters"][0]); sweeps += int(r["counters"][1]); cgits += int(r["counters"][2])
         nfail += int(r["counters"][3]); nfail_final += int(r["counters"][4])
         t_pcg += float(r["buckets"][0]); t_sig += float(r["buckets"][1])
@@ -300,43 +424,24 @@ def main():
     ev1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    dev_ms = sum(a.elapsed_time(b) for a, b in marks)
+    ms = torch.tensor([dev_ms, ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    secs = float(ms.item()) * 1e-3
+    secs, secs_e2e = float(ms[0].item()) * 1e-3, float(ms[1].item()) * 1e-3
     launches = s.kernel_launches() - launches0
     table = s.profile_table()
     s.profile(False)
     nvox = float(N) ** 3
     value = nvox * applies / secs
     fp64_peak = s.fp64_peak()
-
-    # ---- end-to-end through the public C ABI with HOST buffers (pinned) ----
     e2e = None
     if not args.no_e2e:
-        n3 = s.n3
-        hF = torch.empty(9 * n3, dtype=torch.float64).pin_memory()
-        hP = torch.empty(9 * n3, dtype=torch.float64).pin_memory()
-        s.download_ptr("FN1", hF.data_ptr())
-        Ke = max(1, min(K, 2))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        app_e = 0
-        for _ in range(Ke):
-            s.upload_ptr("FN1", hF.data_ptr())                 # host -> device: current deformation field
-            r = s.FFT_nr3(nstep=1, first=step0); step0 += 1    # one load step through the ABI
-            s.download_ptr("FN1", hF.data_ptr())               # device -> host: F and P of the step
-            s.download_ptr("PN1", hP.data_ptr())
-            app_e += int(r["counters"][0])
-        e1.record(stream)
-        barrier()
-        mse = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(mse, op=dist.ReduceOp.MAX)
-        e2e = {"value": nvox * app_e / (float(mse.item()) * 1e-3), "unit": UNIT,
+        e2e = {"value": nvox * applies / secs_e2e, "unit": UNIT,
                "h2d_bytes_per_step": int(9 * n3 * 8) * world, "d2h_bytes_per_step": int(18 * n3 * 8) * world,   # all ranks
-               "steps": Ke,
+               "steps": K, "ms_per_step": 1e3 * secs_e2e / K,
+               "what": "the same K load steps as `value`, each: cpfft_upload(FN1) from pinned host memory -> cpfft_FFT_nr3 -> "
+                       "cpfft_download(FN1, PN1) to pinned host memory; `value` leaves the copies out",
                "check": float(hP.abs().max())}
 
     if rank != 0:
@@ -350,8 +455,9 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
-                                  "--warmup", "3", "--cpu-n", str(args.cpu_n)], capture_output=True, text=True, timeout=900)
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
+                                  "--warmup", "1", "--cpu-n", str(args.cpu_n), "--grains", str(args.grains)] +
+                                 (["--strain-bc"] if args.strain_bc else []), capture_output=True, text=True, timeout=900)
             cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as ex:  # reported, never hidden
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
@@ -363,7 +469,8 @@ def main():
         "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal ({args.grains} random-orientation fcc grains, "
                                f"mm10/{ {'voce': 'Voce', 'mts': 'MTS (variant, not the BASELINE metric)'}.get(args.variant, 'Voce, ' + args.variant[-1] + ' crystals per point (variant, not the BASELINE metric)') }), "
                                "finite-strain uniaxial tension, " +
-                               ("F_xx driven with P_yy = P_zz = 0" if args.stress_bc else "strain-controlled") + ", 0.1 % per load step",
+                               ("F_xx driven with P_yy = P_zz = 0 (stress-BC loop + tangent_homo)" if stress_bc else "strain-controlled (stage-timing variant)") +
+                               ", 0.1 % per load step",
                    "grid": N, "voxels": int(nvox), "voxels_per_gpu": int(s.n3), "parallelism": f"x-slabs x{world}",
                    "l2": "working set (>= 1.2 GB per field) far exceeds the 126 MB L2; no flush needed",
                    "step": "one FFT_nr3 load step", "newton_iters_per_step": nr_hist,
@@ -375,9 +482,11 @@ def main():
                    "VU_per_s": nvox * sweeps / t_sig if t_sig > 0 else None,
                    "mm10_local_failures": {"all_sweeps": nfail, "final_sweeps": nfail_final},
                    "exchange_mode": s.exchange_mode(), "fp64_peak_tflops_measured": fp64_peak,
+                   "weak_scaling_note": "256^3 / 320^3 / 400^3 / 512^3 on 1 / 2 / 4 / 8 GPUs (~16.8 M voxels and ~80 GB per GPU): "
+                                        "512^3 needs >= 4 GPUs (4.8 KB of state per voxel), so strong scaling of it over 2 GPUs is not possible",
                    "even_N_convention": "Nyquist planes of Ghat zeroed (reference is only valid for odd N)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "stages": stages,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -46,7 +46,7 @@ EXPORTS = [
     "cpfft_create", "cpfft_destroy", "cpfft_last_error", "cpfft_set_materials", "cpfft_set_voxels",
     "cpfft_set_voxels_taylor",
     "cpfft_set_params", "cpfft_hist_size", "cpfft_local_voxels", "cpfft_drive_eps_sig", "cpfft_G_K_dF",
-    "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3", "cpfft_step_log",
+    "cpfft_fftPcg", "cpfft_tangent_homo", "cpfft_mean_P", "cpfft_update", "cpfft_FFT_nr3", "cpfft_step_log", "cpfft_step_counter",
     "cpfft_field_ncomp", "cpfft_upload", "cpfft_download", "cpfft_download_fail_flags",
     "cpfft_download_local_iters", "cpfft_material_failures", "cpfft_nccl_unique_id", "cpfft_nccl_init", "cpfft_exchange_mode", "cpfft_synchronize",
     "cpfft_stream", "cpfft_kernel_launches", "cpfft_profile_enable", "cpfft_profile_reset",
@@ -90,6 +90,7 @@ def load_library():
     L.cpfft_FFT_nr3.argtypes = [vp, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp, C.POINTER(C.c_int64)]
     L.cpfft_step_log.argtypes = [vp]
     L.cpfft_step_log.restype = C.c_char_p
+    L.cpfft_step_counter.argtypes = [vp, ip, ip]
     L.cpfft_field_ncomp.argtypes = [vp, C.c_int]
     L.cpfft_upload.argtypes = [vp, C.c_int, dp, C.c_int]
     L.cpfft_download.argtypes = [vp, C.c_int, dp, C.c_int]
@@ -125,7 +126,7 @@ def _ip(a):
 class Solver:
     """One GPU's share of a CPFFT analysis (the whole grid when ``world == 1``)."""
 
-    CG_CAP = 64
+    CG_CAP = 256     # CG solves returned per load step (stress-BC loops run (maxIter + 2) Newton loops at most)
 
     def __init__(self, prob: Problem, device: int = 0, rank: int = 0, world: int = 1, nccl_id: bytes | None = None,
                  local_slab: bool = False):
@@ -246,6 +247,8 @@ class Solver:
         """Run ``nstep`` load steps starting after the ones already taken by this solver."""
         prob = self.prob
         nstep = prob.nstep - first if nstep is None else nstep
+        if first != self.next_step() - 1:
+            raise CpfftError(-2, f"FFT_nr3(first={first}): the handle's next load step is {self.next_step()}")
         bc = np.ascontiguousarray(prob.BC_all()[first:first + nstep])
         nbc = np.ascontiguousarray(prob.isNBC, dtype=np.int32)
         nr = np.zeros(nstep, dtype=np.int32)
@@ -256,9 +259,19 @@ class Solver:
         rc = self.L.cpfft_FFT_nr3(self.h, nstep, _dp(bc), _ip(nbc), _ip(nr), _ip(cg), self.CG_CAP, _dp(pbar),
                                   _dp(sec), cnt.ctypes.data_as(C.POINTER(C.c_int64)))
         self._check(rc)
+        trunc = C.c_int32(0)
+        self._check(self.L.cpfft_step_counter(self.h, None, C.byref(trunc)))
+        if trunc.value:
+            raise CpfftError(-2, f"{trunc.value} CG iteration counts did not fit cg_cap = {self.CG_CAP}")
         cg_lists = [list(r[:list(r).index(-1)]) if -1 in r else list(r) for r in cg]
         return dict(rc=rc, nr_iters=nr, cg_iters=cg_lists, Pbar=pbar, buckets=sec, counters=cnt,
                     log=self.L.cpfft_step_log(self.h).decode())
+
+    def next_step(self):
+        """number of the load step the next FFT_nr3 call starts with (1-based, FFT_nr3.f:51)"""
+        n = C.c_int32(0)
+        self._check(self.L.cpfft_step_counter(self.h, C.byref(n), None))
+        return n.value
 
     def profile(self, on=True):
         self._check(self.L.cpfft_profile_enable(self.h, int(on)))

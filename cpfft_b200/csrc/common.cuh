@@ -8,6 +8,7 @@
 #include "material_types.h"
 
 #define CPF_MAX_WORLD 8   // one NVSwitch domain
+#define CPF_MAX_CHUNKS 16
 
 #define CPF_CUDA(call)                                                                    \
   do {                                                                                    \
@@ -21,9 +22,11 @@
 // kernel classes for the built-in CUDA-event profiler (cpfft_profile_*)
 enum CpfKernelClass {
   CPF_K_UPDATE_MM01 = 0, CPF_K_UPDATE_MM10, CPF_K_PK1_TANGENT, CPF_K_FWD_Z, CPF_K_FWD_Z_K4, CPF_K_FFT_Y,
-  CPF_K_X_GREEN, CPF_K_INV_Z, CPF_K_VECTOR, CPF_K_EXCHANGE, CPF_K_NUM
+  CPF_K_X_GREEN, CPF_K_INV_Z, CPF_K_VECTOR, CPF_K_EXCHANGE,
+  CPF_K_UPDATE_MM10_EL,      // mm10 sweeps with iter == 0 (elastic predictor, rstgp1.f:870-877): no local Newton solve
+  CPF_K_NUM
 };
-struct CpfProfEvt { cudaEvent_t a, b; int cls; };
+struct CpfProfEvt { cudaEvent_t a, b; int cls; cudaStream_t st; };
 
 struct cpfft_handle {
   cpfft_config cfg;
@@ -36,11 +39,16 @@ struct cpfft_handle {
   bool fast_pow2;            // spectral_pow2.cu handles this grid
   bool cg_fuse_x;            // CG: solution update x += alpha p fused into the next forward z pass (k_fz MODE 3)
   int iz_lpc;                // grid lines per CTA of k_iz_pipe
-  int iz_pipe;               // inverse z pass: 1 k_iz_pipe with cp.async (default), 0 k_iz, 2 k_iz_pipe with TMA bulk copies (CPFFT_IZ_PIPE)
+  int iz_pipe;               // inverse z pass: 1 k_iz_pipe with cp.async (default), 0 k_iz (CPFFT_IZ_PIPE)
   int nxloc, x0;             // local slab
   int64_t n3;                // local voxels
   int H;                     // history comps
   cudaStream_t stream;
+  // multi-GPU pipelining of the forward slab transpose: the NVLink-bound forward y pass of x-plane chunk c runs on
+  // `stream2` (higher priority) under the HBM-bound forward z pass of chunk c + 1 on `stream`
+  cudaStream_t stream2;
+  cudaEvent_t ev_chunk[CPF_MAX_CHUNKS]; cudaEvent_t ev_join;
+  int fwd_chunks;            // x-plane chunks of that pipeline (CPFFT_FWD_CHUNKS, default 4; 1 = no pipelining)
   std::string err;
   std::string log;           // the reference's step / iteration lines of the last cpfft_FFT_nr3 call
   int64_t launches;
@@ -76,6 +84,8 @@ struct cpfft_handle {
   double barF[9], barF_t[9], P_bar[9], C_homo[81];
   bool have_chomo;
   int next_step;
+  bool committed;            // cpfft_update ran and no sweep since: the n+1 names alias the n buffers
+  int cg_truncated;          // CG counts dropped by the last cpfft_FFT_nr3 because cg_cap was too small
   // stats
   double t_pcg, t_sig; int64_t n_apply, n_sweep, n_cg;
   // nccl
@@ -90,6 +100,7 @@ void cpf_set_error(cpfft_handle* h, const std::string& s);
 // CUDA-event bracket around one kernel launch (no-ops unless profiling is enabled)
 int cpf_prof_begin(cpfft_handle* h, int cls);
 void cpf_prof_end(cpfft_handle* h, int token);
+int cpf_prof_begin_on(cpfft_handle* h, int cls, cudaStream_t st);   // the same on another stream of the handle
 
 // material.cu
 int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const double* angles,
@@ -107,5 +118,6 @@ int cpf_apply_G_pow2(cpfft_handle* h, const double* src, double* dst, bool flgK,
 int cpf_cg_apply_pow2(cpfft_handle* h, double* p, double* q, const double* r, double beta, bool update_p, int* nparts,
                       double* x, double rr_alpha, const double* pq);
 
-// reduce.cu helpers (solver.cu)
+// solver.cu
+double* cpf_field_ptr(cpfft_handle* h, int f);
 int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double* out);

@@ -50,12 +50,21 @@ CPF_DI double m3_inv(const double* a, double* g) {
 // R = F U^-1 with U^-1 = a (b I + c C + d C^2), C = F^T F; eigenvalues of C by the closed
 // form trigonometric solution (polar.f:224-307), invariants of U (polar.f:196-208).
 CPF_DI void polar_R(const double* f, double* r) {
-  double c0 = f[0] * f[0] + f[3] * f[3] + f[6] * f[6];   // C11
-  double c1 = f[0] * f[1] + f[3] * f[4] + f[6] * f[7];   // C12
-  double c2 = f[1] * f[1] + f[4] * f[4] + f[7] * f[7];   // C22
-  double c3 = f[0] * f[2] + f[3] * f[5] + f[6] * f[8];   // C13
-  double c4 = f[1] * f[2] + f[4] * f[5] + f[7] * f[8];   // C23
-  double c5 = f[2] * f[2] + f[5] * f[5] + f[8] * f[8];   // C33
+  // From F to the discriminant every product and sum is rounded on its own, in source order
+  // (CPF_MUL / CPF_ADD / CPF_SUB, never contracted into an FMA).  The discriminant of the cubic
+  // cancels to round-off when the principal stretches differ by < 3e-3: the angle phi is then
+  // noise that reaches the stress at the order strain^3 ~ 1e-8.  With one fixed rounding
+  // sequence -- the same one in oracle/oracle_kin.cpp -- that noise is the same number everywhere,
+  // so per-voxel results are comparable to 1e-9 at small strain increments as well.
+#define M_(a, b) CPF_MUL(a, b)
+#define A_(a, b) CPF_ADD(a, b)
+#define S_(a, b) CPF_SUB(a, b)
+  const double c0 = A_(A_(M_(f[0], f[0]), M_(f[3], f[3])), M_(f[6], f[6]));   // C11
+  const double c1 = A_(A_(M_(f[0], f[1]), M_(f[3], f[4])), M_(f[6], f[7]));   // C12
+  const double c2 = A_(A_(M_(f[1], f[1]), M_(f[4], f[4])), M_(f[7], f[7]));   // C22
+  const double c3 = A_(A_(M_(f[0], f[2]), M_(f[3], f[5])), M_(f[6], f[8]));   // C13
+  const double c4 = A_(A_(M_(f[1], f[2]), M_(f[4], f[5])), M_(f[7], f[8]));   // C23
+  const double c5 = A_(A_(M_(f[2], f[2]), M_(f[5], f[5])), M_(f[8], f[8]));   // C33
   double cc0 = c0 * c0 + c1 * c1 + c3 * c3;
   double cc1 = c0 * c1 + c1 * c2 + c3 * c4;
   double cc2 = c1 * c1 + c2 * c2 + c4 * c4;
@@ -63,14 +72,17 @@ CPF_DI void polar_R(const double* f, double* r) {
   double cc4 = c1 * c3 + c2 * c4 + c4 * c5;
   double cc5 = c3 * c3 + c4 * c4 + c5 * c5;
   const double third = 0.3333333333333333333, oneroot3 = 0.5773502691896258;
-  double de = c1 * c4, dd = c1 * c1, ee = c4 * c4, ff = c3 * c3;
-  double m = c0 + c2 + c5;
-  double k1 = (c0 * c2 + c0 * c5 + c2 * c5) - (dd + ee + ff);
-  double k0 = c5 * dd + c0 * ee + c2 * ff - c0 * c2 * c5 - 2.0 * c3 * de;
-  double p = m * m - 3.0 * k1;
-  double q = m * (p - 1.5 * k1) - 13.5 * k0;
+  const double de = M_(c1, c4), dd = M_(c1, c1), ee = M_(c4, c4), ff = M_(c3, c3);
+  const double m = A_(A_(c0, c2), c5);
+  const double k1 = S_(A_(A_(M_(c0, c2), M_(c0, c5)), M_(c2, c5)), A_(A_(dd, ee), ff));
+  const double k0 = S_(S_(A_(A_(M_(c5, dd), M_(c0, ee)), M_(c2, ff)), M_(M_(c0, c2), c5)), M_(M_(2.0, c3), de));
+  const double p = S_(M_(m, m), M_(3.0, k1));
+  const double q = S_(M_(m, S_(p, M_(1.5, k1))), M_(13.5, k0));
+  double phi = M_(27.0, A_(M_(M_(M_(0.25, k1), k1), S_(p, k1)), M_(k0, A_(q, M_(6.75, k0)))));
+#undef M_
+#undef A_
+#undef S_
   double sqrtp = sqrt(fabs(p));
-  double phi = 27.0 * (0.25 * k1 * k1 * (p - k1) + k0 * (q + 6.75 * k0));
   phi = third * atan2(sqrt(fabs(phi)), q);
   double sphi_, cphi_;
   sincos(phi, &sphi_, &cphi_);
@@ -141,13 +153,6 @@ CPF_DI void voxel_kinematics(const double* fn, const double* fn1, double* Rh, do
 // t6: unrotated Cauchy stress (Voigt), C: 6x6 [D] row-major.  Algebraically identical to
 // cep2A_a (cep2A.f:86-284) but every rank-one structure of dR/dF, dRh/dF and dL/dF is
 // contracted analytically, so the cost is O(81 * const) instead of four 81x9 loop nests.
-// C: anything indexable as C[k], k = 6 * row + col -- a register array, or StridedCep, which re-reads
-// the voxel's [D] from global memory (L1-resident: 36 x 256 B per warp) and takes its 36 values out
-// of the register budget of the 9 x 9 output loop.
-struct StridedCep {
-  const double* p; int64_t stride;
-  CPF_DI double operator[](int k) const { return CPF_LDG(p + (int64_t)k * stride); }
-};
 template <class Cep>
 CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t6, const Cep& C,
                             double* P, double* A /*81, may alias nothing*/,

@@ -65,14 +65,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, c
                                                               const double* cep, double* Pn1, double* K4, int64_t n3) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n3) return;
-  upd_pk1_voxel<true>(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
-}
-// development variant (CPFFT_PK1_CEP=mem): [D] re-read from memory in the output loop, see upd_pk1_voxel
-__global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent_cepmem(const double* Fn, const double* Fn1, const double* urcs_n1,
-                                                                    const double* cep, double* Pn1, double* K4, int64_t n3) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n3) return;
-  upd_pk1_voxel<false>(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
+  upd_pk1_voxel(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -115,6 +108,7 @@ int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const
 }
 
 int cpf_launch_update(cpfft_handle* h, int step, int iter) {
+  h->committed = false;      // this sweep writes the n+1 buffers: the names stop aliasing the n state (cpfft_update)
   UpdArgs a;
   a.Fn = h->field[CPFFT_FN]; a.Fn1 = h->field[CPFFT_FN1];
   a.urcs_n = h->field[CPFFT_URCS_N]; a.urcs_n1 = h->field[CPFFT_URCS_N1];
@@ -143,15 +137,13 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
       for (int hard = 1; hard <= 2; ++hard) {
         if (!h->mm10_kern[multi][hard]) continue;
         CPF_CUDA(cudaFuncSetAttribute(kerns[multi][hard], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int tk = cpf_prof_begin(h, CPF_K_UPDATE_MM10);
+        const int tk = cpf_prof_begin(h, iter == 0 ? CPF_K_UPDATE_MM10_EL : CPF_K_UPDATE_MM10);
         kerns[multi][hard]<<<grid, UPD_THREADS, smem, h->stream>>>(a); h->launches++;
         cpf_prof_end(h, tk);
       }
   }
   const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);
-  static const bool cep_mem = [] { const char* v = getenv("CPFFT_PK1_CEP"); return v && v[0] == 'm'; }();
-  if (cep_mem) k_pk1_tangent_cepmem<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
-  else k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
+  k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
   cpf_prof_end(h, tk);
   h->launches++;
   CPF_CUDA(cudaGetLastError());

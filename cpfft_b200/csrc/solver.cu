@@ -14,23 +14,25 @@ static double wall_s() {
 }
 void cpf_set_error(cpfft_handle* h, const std::string& s) { if (h) h->err = s; }
 
-int cpf_prof_begin(cpfft_handle* h, int cls) {
+int cpf_prof_begin_on(cpfft_handle* h, int cls, cudaStream_t st) {
   if (!h->prof_on) return -1;
   CpfProfEvt e;
   if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); }
   else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
-  e.cls = cls;
-  cudaEventRecord(e.a, h->stream);
+  e.cls = cls; e.st = st;
+  cudaEventRecord(e.a, st);
   h->prof_live.push_back(e);
   return (int)h->prof_live.size() - 1;
 }
+int cpf_prof_begin(cpfft_handle* h, int cls) { return cpf_prof_begin_on(h, cls, h->stream); }
 void cpf_prof_end(cpfft_handle* h, int token) {
   if (token < 0) return;
-  cudaEventRecord(h->prof_live[token].b, h->stream);
+  cudaEventRecord(h->prof_live[token].b, h->prof_live[token].st);
 }
 static void prof_collect(cpfft_handle* h) {
   if (h->prof_live.empty()) return;
   cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   for (auto& e : h->prof_live) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { h->prof_ms[e.cls] += ms; h->prof_cnt[e.cls]++; }
@@ -301,6 +303,16 @@ int cpf_dot(cpfft_handle* h, const double* x, const double* y, int64_t n, double
   return fetch_scalars(h, 1, out);
 }
 
+// device pointer behind a field id: right after a commit the n+1 names alias the n buffers
+double* cpf_field_ptr(cpfft_handle* h, int f) {
+  if (h->committed) {
+    if (f == CPFFT_HIST_N1) return h->field[CPFFT_HIST_N];
+    if (f == CPFFT_EPS_N1) return h->field[CPFFT_EPS_N];
+    if (f == CPFFT_URCS_N1) return h->field[CPFFT_URCS_N];
+  }
+  return h->field[f];
+}
+
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -323,7 +335,9 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   h->nccl_comm = nullptr; h->nccl_lib = nullptr; h->xchg_send = h->xchg_recv = nullptr;
   h->p2p = false;
   for (int r = 0; r < CPF_MAX_WORLD; ++r) h->peer_spec_a[r] = h->peer_spec_b[r] = nullptr;
-  h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr;
+  h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr; h->stream2 = nullptr;
+  for (int c = 0; c < CPF_MAX_CHUNKS; ++c) h->ev_chunk[c] = nullptr;
+  h->ev_join = nullptr; h->fwd_chunks = 1;
   *out = h;  // returned even on failure so that cpfft_last_error works; caller destroys it
   if (cfg->N < 2) { cpf_set_error(h, "N must be >= 2"); return CPFFT_ERR_USAGE; }
   if (h->cfg.world > 1 && (cfg->N % h->cfg.world) != 0) {
@@ -333,7 +347,18 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   cudaDeviceProp prop;
   CPF_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   g_num_sms = prop.multiProcessorCount;
-  CPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;     // numerically lower = higher priority
+    CPF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CPF_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, lo));
+    CPF_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi));
+    for (int c = 0; c < CPF_MAX_CHUNKS; ++c) CPF_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
+    CPF_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    const char* fc = getenv("CPFFT_FWD_CHUNKS");
+    h->fwd_chunks = fc ? atoi(fc) : 4;
+    if (h->fwd_chunks < 1) h->fwd_chunks = 1;
+    if (h->fwd_chunks > CPF_MAX_CHUNKS) h->fwd_chunks = CPF_MAX_CHUNKS;
+  }
   h->nxloc = cfg->N / h->cfg.world; h->x0 = h->cfg.rank * h->nxloc;
   h->n3 = (int64_t)h->nxloc * cfg->N * cfg->N;
   const int nc[CPFFT_NUM_FIELDS] = {9, 9, 9, 9, 9, 9, 9, 9, 9, 81, 9, 9, 6, 6, 9, 0, 0, 36};
@@ -363,7 +388,7 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   int rc = cpf_spectral_init(h);
   if (rc) return rc;
   for (int i = 0; i < 9; ++i) { h->barF[i] = h->barF_t[i] = (i % 4 == 0) ? 1.0 : 0.0; h->P_bar[i] = 0.0; }
-  h->have_chomo = false; h->next_step = 1;
+  h->have_chomo = false; h->next_step = 1; h->committed = false; h->cg_truncated = 0;
   h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0;
   CPF_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
@@ -387,6 +412,9 @@ void cpfft_destroy(cpfft_handle* h) {
       }
   cpf_spectral_free(h);
   if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
+  for (int c = 0; c < CPF_MAX_CHUNKS; ++c) if (h->ev_chunk[c]) cudaEventDestroy(h->ev_chunk[c]);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -424,14 +452,24 @@ int cpfft_field_ncomp(const cpfft_handle* h, cpfft_field f) { return (h && f >= 
 
 int cpfft_upload(cpfft_handle* h, cpfft_field f, const double* host, cpfft_layout layout) {
   if (!h || f < 0 || f >= CPFFT_NUM_FIELDS || !h->field[f]) return CPFFT_ERR_USAGE;
+  if (h->committed && (f == CPFFT_HIST_N1 || f == CPFFT_EPS_N1 || f == CPFFT_URCS_N1 || f == CPFFT_HIST_N ||
+                       f == CPFFT_EPS_N || f == CPFFT_URCS_N)) {
+    // writing one name of an aliased pair: give n+1 its own copy again first
+    const int pairs[3][2] = {{CPFFT_HIST_N, CPFFT_HIST_N1}, {CPFFT_EPS_N, CPFFT_EPS_N1}, {CPFFT_URCS_N, CPFFT_URCS_N1}};
+    for (auto& pr : pairs)
+      if (h->field[pr[0]] && h->field[pr[1]])
+        CPF_CUDA(cudaMemcpyAsync(h->field[pr[1]], h->field[pr[0]], sizeof(double) * h->ncomp[pr[0]] * h->n3,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    h->committed = false;
+  }
   const int nc = h->ncomp[f]; const int64_t n3 = h->n3;
   if (layout == CPFFT_LAYOUT_SOA) {
-    CPF_CUDA(cudaMemcpyAsync(h->field[f], host, sizeof(double) * nc * n3, cudaMemcpyHostToDevice, h->stream));
+    CPF_CUDA(cudaMemcpyAsync(cpf_field_ptr(h, f), host, sizeof(double) * nc * n3, cudaMemcpyHostToDevice, h->stream));
     CPF_CUDA(cudaStreamSynchronize(h->stream));
   } else {
     std::vector<double> t((size_t)nc * n3);
     for (int64_t e = 0; e < n3; ++e) for (int c = 0; c < nc; ++c) t[(size_t)c * n3 + e] = host[(size_t)e * nc + c];
-    CPF_CUDA(cudaMemcpy(h->field[f], t.data(), sizeof(double) * nc * n3, cudaMemcpyHostToDevice));
+    CPF_CUDA(cudaMemcpy(cpf_field_ptr(h, f), t.data(), sizeof(double) * nc * n3, cudaMemcpyHostToDevice));
   }
   return 0;
 }
@@ -440,10 +478,10 @@ int cpfft_download(cpfft_handle* h, cpfft_field f, double* host, cpfft_layout la
   const int nc = h->ncomp[f]; const int64_t n3 = h->n3;
   CPF_CUDA(cudaStreamSynchronize(h->stream));
   if (layout == CPFFT_LAYOUT_SOA) {
-    CPF_CUDA(cudaMemcpy(host, h->field[f], sizeof(double) * nc * n3, cudaMemcpyDeviceToHost));
+    CPF_CUDA(cudaMemcpy(host, cpf_field_ptr(h, f), sizeof(double) * nc * n3, cudaMemcpyDeviceToHost));
   } else {
     std::vector<double> t((size_t)nc * n3);
-    CPF_CUDA(cudaMemcpy(t.data(), h->field[f], sizeof(double) * nc * n3, cudaMemcpyDeviceToHost));
+    CPF_CUDA(cudaMemcpy(t.data(), cpf_field_ptr(h, f), sizeof(double) * nc * n3, cudaMemcpyDeviceToHost));
     for (int64_t e = 0; e < n3; ++e) for (int c = 0; c < nc; ++c) host[(size_t)e * nc + c] = t[(size_t)c * n3 + e];
   }
   return 0;
@@ -503,7 +541,7 @@ int cpfft_material_failures(cpfft_handle* h, int64_t* total, int64_t* last_sweep
 int cpfft_G_K_dF(cpfft_handle* h, cpfft_field src, cpfft_field dst, int flgK) {
   if (!h || src < 0 || dst < 0 || src >= CPFFT_NUM_FIELDS || dst >= CPFFT_NUM_FIELDS || h->ncomp[src] != 9 ||
       h->ncomp[dst] != 9) { cpf_set_error(h, "G_K_dF needs 9-component fields"); return CPFFT_ERR_USAGE; }
-  return cpf_apply_G(h, h->field[src], h->field[dst], flgK != 0, 1.0);
+  return cpf_apply_G(h, cpf_field_ptr(h, src), cpf_field_ptr(h, dst), flgK != 0, 1.0);
 }
 
 // ---- fftPcg (FFT_nr3.f:214-360) on device vectors; x and b are 9*n3 device pointers ----
@@ -584,7 +622,7 @@ int cpfft_fftPcg(cpfft_handle* h, cpfft_field b, cpfft_field x, double tol, int*
   if (b == CPFFT_CG_P || b == CPFFT_CG_AP || b == CPFFT_CG_R || x == CPFFT_CG_P || x == CPFFT_CG_AP || x == CPFFT_CG_R) {
     cpf_set_error(h, "CG work fields cannot be operands"); return CPFFT_ERR_USAGE;
   }
-  return pcg_dev(h, h->field[b], h->field[x], tol, iters, relres);
+  return pcg_dev(h, cpf_field_ptr(h, b), cpf_field_ptr(h, x), tol, iters, relres);
 }
 
 int cpfft_mean_P(cpfft_handle* h, double Pbar[9]) {
@@ -624,18 +662,30 @@ int cpfft_tangent_homo(cpfft_handle* h, double C_homo[81]) {
   return 0;
 }
 
-int cpfft_update(cpfft_handle* h) {  // update.f:75-106 + FFT_nr3.f:174-175
+// update.f:75-106 + FFT_nr3.f:174-175: n <- n+1.  Fn <- Fn1 and Pn <- Pn1 are copies (Fn1 is
+// the start value of the next step).  History, strains and stresses -- 2 x (H + 15) doubles per
+// voxel -- are committed by exchanging the n and n+1 buffers: from here until the next
+// drive_eps_sig sweep both names refer to the committed buffer (cpf_field_ptr), exactly what
+// the reference's copies leave behind; the sweep then writes every n+1 entry it or a reader
+// ever looks at into the spare buffer (the mm01 kernel, which does not scatter its history at
+// iter 0, rplstr.f:78, carries the n values over instead).
+int cpfft_update(cpfft_handle* h) {
   if (!h) return CPFFT_ERR_USAGE;
   const int64_t n3 = h->n3;
-  const int pairs[5][2] = {{CPFFT_FN, CPFFT_FN1}, {CPFFT_PN, CPFFT_PN1}, {CPFFT_HIST_N, CPFFT_HIST_N1},
-                           {CPFFT_EPS_N, CPFFT_EPS_N1}, {CPFFT_URCS_N, CPFFT_URCS_N1}};
-  for (auto& pr : pairs)
-    if (h->field[pr[0]])
-      CPF_CUDA(cudaMemcpyAsync(h->field[pr[0]], h->field[pr[1]], sizeof(double) * h->ncomp[pr[0]] * n3,
-                               cudaMemcpyDeviceToDevice, h->stream));
+  const int copies[2][2] = {{CPFFT_FN, CPFFT_FN1}, {CPFFT_PN, CPFFT_PN1}};
+  for (auto& pr : copies)
+    CPF_CUDA(cudaMemcpyAsync(h->field[pr[0]], h->field[pr[1]], sizeof(double) * h->ncomp[pr[0]] * n3,
+                             cudaMemcpyDeviceToDevice, h->stream));
+  const int swaps[3][2] = {{CPFFT_HIST_N, CPFFT_HIST_N1}, {CPFFT_EPS_N, CPFFT_EPS_N1}, {CPFFT_URCS_N, CPFFT_URCS_N1}};
+  if (h->committed) {
+    // two commits without a sweep in between: n+1 == n already, nothing to exchange
+  } else {
+    for (auto& pr : swaps)
+      if (h->field[pr[0]] && h->field[pr[1]]) std::swap(h->field[pr[0]], h->field[pr[1]]);
+    h->committed = true;
+  }
   return 0;
 }
-
 // NBC_update (FFT_nr3.f:375-433), host, 9x9
 static int nbc_update(const double* C_homo, double* DbarF, const double* P_bar, const double* PBC, const int32_t* isNBC) {
   double A[81], bb[9];
@@ -682,7 +732,7 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
   bool existNBC = false;
   for (int i = 0; i < 9; ++i) if (isNBC[i]) existNBC = true;
   h->t_pcg = h->t_sig = 0; h->n_apply = h->n_sweep = h->n_cg = 0; h->n_fail = 0;
-  h->log.clear();
+  h->log.clear(); h->cg_truncated = 0;
   int64_t fail_final_steps = 0;
   const double t_start = wall_s();
   int rc;
@@ -695,7 +745,11 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
   for (int s = 0; s < nstep; ++s) {
     const int step = h->next_step;
     int ncg = 0;
-    auto push_cg = [&](int it) { if (cg_iters && ncg < cg_cap - 1) cg_iters[(size_t)s * cg_cap + ncg++] = it; };
+    auto push_cg = [&](int it) {
+      if (!cg_iters || cg_cap <= 0) return;
+      if (ncg < cg_cap - 1) cg_iters[(size_t)s * cg_cap + ncg++] = it;
+      else h->cg_truncated++;              // reported by cpfft_step_counter, never silent
+    };
     {  // format 1000
       char hd[160];
       snprintf(hd, sizeof(hd), "\n    -------------------------------------------------------------------------\n     Now starting step: %7d\n", step);
@@ -772,7 +826,7 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
     for (int i = 0; i < 9; ++i) h->barF_t[i] = h->barF[i];
     rc = cpfft_update(h); if (rc) return rc;
     if (nr_iters) nr_iters[s] = total_nr;
-    if (cg_iters) cg_iters[(size_t)s * cg_cap + ncg] = -1;
+    if (cg_iters && cg_cap > 0) cg_iters[(size_t)s * cg_cap + ncg] = -1;
     if (Pbar_out) for (int i = 0; i < 9; ++i) Pbar_out[(size_t)s * 9 + i] = h->P_bar[i];
     h->next_step++;
   }
@@ -806,7 +860,8 @@ int cpfft_profile_reset(cpfft_handle* h) {
 int cpfft_profile_classes(void) { return CPF_K_NUM; }
 const char* cpfft_profile_name(int cls) {
   static const char* names[CPF_K_NUM] = {"k_update_mm01", "k_update_mm10", "k_pk1_tangent", "k_fwd_z", "k_fwd_z_K4",
-                                          "k_fft_y", "k_x_green", "k_inv_z", "vector_ops", "exchange"};
+                                          "k_fft_y", "k_x_green", "k_inv_z", "vector_ops", "exchange",
+                                          "k_update_mm10_elastic"};
   return (cls >= 0 && cls < CPF_K_NUM) ? names[cls] : "?";
 }
 int cpfft_profile_get(cpfft_handle* h, int cls, double* ms, int64_t* count) {
@@ -879,6 +934,13 @@ int cpfft_nccl_init(cpfft_handle* h, const void* id128) {
 }
 
 const char* cpfft_step_log(const cpfft_handle* h) { return h ? h->log.c_str() : ""; }
+
+int cpfft_step_counter(const cpfft_handle* h, int* next_step, int* cg_truncated) {
+  if (!h) return CPFFT_ERR_USAGE;
+  if (next_step) *next_step = h->next_step;
+  if (cg_truncated) *cg_truncated = h->cg_truncated;
+  return 0;
+}
 
 int cpfft_fp64_peak(cpfft_handle* h, double* tflops) {
   if (!h || !tflops) return CPFFT_ERR_USAGE;

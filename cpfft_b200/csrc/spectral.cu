@@ -249,7 +249,7 @@ int cpf_spectral_init(cpfft_handle* h) {
   h->fast_pow2 = cpf_pow2_supported(N) && (getenv("CPFFT_GENERIC_FFT") == nullptr);
   {  // development switches for A/B measurements; every setting gives bit-identical results
     const char* e = getenv("CPFFT_IZ_PIPE");
-    h->iz_pipe = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
+    h->iz_pipe = e ? (e[0] == '0' ? 0 : 1) : 1;
     const char* fx = getenv("CPFFT_CG_FUSE_X");
     h->cg_fuse_x = fx ? (fx[0] != '0') : true;
     const char* l = getenv("CPFFT_IZ_LPC");

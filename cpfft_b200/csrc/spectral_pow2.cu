@@ -18,6 +18,7 @@
 
 struct Pow2Args {
   int nx, x0;    // local x planes (z / y passes) and their global offset
+  int xoff, nxc; // z / forward y pass: this launch covers local x planes [xoff, xoff + nxc) (multi-GPU pipelining)
   int NY, y0;    // x pass: local y extent and its global offset (slab-transposed layout)
   int64_t n3;    // local voxels
   const cplx* tw;  // exp(-2 pi i k / N), k < N
@@ -43,6 +44,10 @@ template <int N> struct Pow2Cfg {
   static constexpr int ZT = (N / 2 + 31) / 32 * 32;   // threads of k_fz / k_iz (N/2 of them work)
 };
 template <> struct Pow2Cfg<256> { static constexpr int H = 128, TZY = 16, TZX = 8, ZT = 128; };
+// 512^3 only runs slab-decomposed: the last stage of the x pass stores over NVLink, where 64-byte runs (TZX = 4,
+// what the 64 KB shared-memory rule gives) reach half the link rate of 128-byte runs (round 1, 8 GPUs: k_fx 1.66 ms
+// for the 617 MB that k_fyf, with 128-byte runs, moves in 0.84 ms).  TZX = 8: 136 KB of shared memory, one CTA per SM.
+template <> struct Pow2Cfg<512> { static constexpr int H = 256, TZY = 8, TZX = 8, ZT = 256; };
 template <> struct Pow2Cfg<40> { static constexpr int H = 20, TZY = 10, TZX = 5, ZT = 32; };
 template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, ZT = 64; };
 template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 128; };
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_fz(Pow2Args g
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   const int64_t n3 = g.n3;
   const int t = threadIdx.x;
-  const int64_t L = blockIdx.x;                         // grid line x * N + y
+  const int64_t L = (int64_t)g.xoff * N + blockIdx.x;   // grid line x * N + y
   const int64_t e0 = L * N + 2 * t;
   if (t < H) {
     double2 f[9];
@@ -304,13 +309,10 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g
 // and 0.831 -> 0.661 ms with the fused dot product; a variant with two B buffers (next line
 // requested before the current one is touched, one CTA per SM fewer) measured 0.578 / 0.652 ms
 // and was dropped; 4, 8 or 16 lines per CTA make no difference.
+// A variant that fetched the nine 2 KB rows with 1-D bulk copies (cp.async.bulk + mbarrier) instead of
+// 16-byte LDGSTS measured the same or slower (profiles/r02a_ab_tma64.log) and was removed.
 #include <cuda_pipeline.h>
-#include <cuda/barrier>
-#include <cuda/ptx>
-// TMA = true (CPFFT_IZ_PIPE=2, NOT the default, not yet measured): the nine 2 KB rows of the next
-// line are fetched by nine 1-D bulk copies (cp.async.bulk, SASS UBLKCP) issued by one thread and
-// tracked by an mbarrier transaction count, instead of 9 LDGSTS per thread.
-template <int N, bool DOT, bool TMA = false>
+template <int N, bool DOT>
 __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                                                               const double* __restrict__ pvec, double* __restrict__ partials, int64_t nlines, int lpc) {
   typedef ZSmem<N> Z;
@@ -323,43 +325,19 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz_pipe(Pow2A
   const int64_t nxN = (int64_t)g.nx * N;
   const int64_t L0 = (int64_t)blockIdx.x * lpc;          // lpc consecutive grid lines per CTA
   const int nl = (int)((nlines - L0) < lpc ? (nlines - L0) : lpc);
-  typedef cuda::barrier<cuda::thread_scope_block> barrier_t;
-#pragma nv_diag_suppress static_var_with_dynamic_init
-  __shared__ barrier_t bar;
-  barrier_t::arrival_token tok;
-  if (TMA) {
-    if (threadIdx.x == 0) init(&bar, blockDim.x);
-    __syncthreads();
-  }
   auto prefetch = [&](int64_t L) {
-    if constexpr (TMA) {
-      // every thread arrives; thread 0 also posts the nine bulk copies and their byte count.  All
-      // generic-proxy accesses of B by this CTA are ordered before by the barrier the caller just
-      // passed; the proxy fence orders them against the asynchronous-proxy writes that follow.
-      if (threadIdx.x == 0) {
-        cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
-#pragma unroll
-        for (int c = 0; c < 9; ++c)
-          cuda::device::memcpy_async_tx(B + c * HB, spec + ((int64_t)c * nxN + L) * H, cuda::aligned_size_t<16>(sizeof(cplx) * H), bar);
-        tok = cuda::device::barrier_arrive_tx(bar, 1, 9 * sizeof(cplx) * H);
-      } else {
-        tok = bar.arrive();
-      }
-    } else {
-      for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
-        const int c = idx / H, k = idx - c * H;
-        __pipeline_memcpy_async(B + c * HB + k, spec + ((int64_t)c * nxN + L) * H + k, sizeof(cplx));
-      }
-      __pipeline_commit();
+    for (int idx = threadIdx.x; idx < 9 * H; idx += blockDim.x) {
+      const int c = idx / H, k = idx - c * H;
+      __pipeline_memcpy_async(B + c * HB + k, spec + ((int64_t)c * nxN + L) * H + k, sizeof(cplx));
     }
+    __pipeline_commit();
   };
   prefetch(L0);
   const int t = threadIdx.x;
   constexpr int NP = H / 2 + 1;
   for (int il = 0; il < nl; ++il) {
     const int64_t L = L0 + il;
-    if (TMA) bar.wait(std::move(tok));                  // all bytes of line L have landed (and every thread has arrived)
-    else __pipeline_wait_prior(0);
+    __pipeline_wait_prior(0);
     __syncthreads();                                    // line L has landed for every thread (and tw on the first trip)
     const int64_t e0 = L * N + 2 * t;
     double2 pv[9];
@@ -492,7 +470,7 @@ __global__ void __launch_bounds__(512) k_fyf(Pow2Args g, cplx* __restrict__ spec
   cplx* tw = sm + N * TZ;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   __syncthreads();
-  const int ls = blockIdx.x / g.nx, xl = blockIdx.x - ls * g.nx;
+  const int ls = blockIdx.x / g.nxc, xl = g.xoff + (blockIdx.x - ls * g.nxc);
   const int row = ls >> 1, kz0 = blockIdx.y * TZ;
   const int slot = 3 * row + (ls & 1);
   const int ny = g.NY;                                   // SCATTER: y planes per rank
@@ -682,17 +660,29 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   typedef FftPlan<N> P;
   const int nx = h->nxloc, world = h->cfg.world;
   Pow2Args g;
-  g.nx = nx; g.x0 = h->x0; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
+  g.nx = nx; g.x0 = h->x0; g.xoff = 0; g.nxc = nx; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
   PeerPtrs none = {};
   const size_t sm_z = ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
   const unsigned zgrid = (unsigned)(nx * N);
-  int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
-  if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
-  else if (cg && cg->update_p) k_fz<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
-  else if (flgK) k_fz<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-  else k_fz<N, 0><<<zgrid, ZT, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-  cpf_prof_end(h, tk);
+  // forward z pass of the local x planes [xoff, xoff + nxc)
+  auto launch_fz = [&](int xoff, int nxc) {
+    Pow2Args gz = g;
+    gz.xoff = xoff; gz.nxc = nxc;
+    const unsigned zg = (unsigned)(nxc * N);
+    const int tkz = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
+    if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
+    else if (cg && cg->update_p) k_fz<N, 2><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
+    else if (flgK) k_fz<N, 1><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    else k_fz<N, 0><<<zg, ZT, sm_z, h->stream>>>(gz, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    cpf_prof_end(h, tkz);
+  };
+  // multi-GPU with peer stores: the forward y pass of a chunk of x planes (NVLink-bound: its last stage stores
+  // into the peers' y slabs) runs on the second stream under the HBM-bound forward z pass of the next chunk
+  int nchunk = (world > 1 && h->p2p) ? h->fwd_chunks : 1;
+  while (nchunk > 1 && nx % nchunk) --nchunk;
+  int tk;
+  if (nchunk == 1) launch_fz(0, nx);
   constexpr int Rm12 = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
   constexpr int RminY = P::R3 > 1 ? (Rm12 < P::R3 ? Rm12 : P::R3) : Rm12;
   constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
@@ -717,9 +707,26 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
       for (int r = 0; r < CPF_MAX_WORLD; ++r) { pa.p[r] = h->peer_spec_a[r]; pb.p[r] = h->peer_spec_b[r]; }
       Pow2Args gs = g;
       gs.NY = ny;                                  // y planes per rank, for the scatter
-      tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-      k_fyf<N, true><<<gyf, thr_y, sm_y, h->stream>>>(gs, h->spec_a, pb);     // -> every rank's spec_b
-      cpf_prof_end(h, tk);
+      if (nchunk == 1) {
+        tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+        k_fyf<N, true><<<gyf, thr_y, sm_y, h->stream>>>(gs, h->spec_a, pb);     // -> every rank's spec_b
+        cpf_prof_end(h, tk);
+      } else {
+        const int nxc = nx / nchunk;
+        const dim3 gyc(6 * nxc, H / TZY);
+        for (int c = 0; c < nchunk; ++c) {
+          launch_fz(c * nxc, nxc);
+          CPF_CUDA(cudaEventRecord(h->ev_chunk[c], h->stream));
+          CPF_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_chunk[c], 0));
+          gs.xoff = c * nxc; gs.nxc = nxc;
+          tk = cpf_prof_begin_on(h, CPF_K_FFT_Y, h->stream2);
+          k_fyf<N, true><<<gyc, thr_y, sm_y, h->stream2>>>(gs, h->spec_a, pb);
+          cpf_prof_end(h, tk);
+        }
+        CPF_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+        CPF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        h->launches += 2 * (nchunk - 1);
+      }
       int rc = cpf_rank_barrier(h); if (rc) return rc;
       tk = cpf_prof_begin(h, CPF_K_X_GREEN);
       k_fx<N, true><<<gx, thr_x, sm_x, h->stream>>>(gt, h->spec_b, pa);        // -> every rank's spec_a
@@ -747,10 +754,7 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
     const int lpc = h->iz_lpc;
     const unsigned pgrid = (zgrid + lpc - 1) / lpc;
     if (cg) const_cast<CgFuse*>(cg)->nparts = (int)zgrid;
-    if (h->iz_pipe == 2) {      // development variant: TMA bulk copies
-      if (cg) k_iz_pipe<N, true, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
-      else k_iz_pipe<N, false, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
-    } else if (cg) k_iz_pipe<N, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
+    if (cg) k_iz_pipe<N, true><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials, (int64_t)zgrid, lpc);
     else k_iz_pipe<N, false><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
   } else if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
   else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
@@ -776,8 +780,6 @@ static int init_pow2(cpfft_handle* h) {
   CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
   CPF_SMEM_ATTR((k_iz_pipe<N, true>), sm_z);
   CPF_SMEM_ATTR((k_iz_pipe<N, false>), sm_z);
-  CPF_SMEM_ATTR((k_iz_pipe<N, true, true>), sm_z);
-  CPF_SMEM_ATTR((k_iz_pipe<N, false, true>), sm_z);
   CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
   CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
   CPF_SMEM_ATTR((k_fyi<N>), sm_y);

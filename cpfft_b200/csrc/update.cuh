@@ -55,6 +55,11 @@ CPF_DI void upd_mm01_voxel(const UpdArgs& a, const int64_t e) {
       for (int i = 0; i < 3; ++i) a.rot_n1[(3 * j + i) * n3 + e] = R[3 * i + j];
 #pragma unroll
     for (int k = 0; k < 11; ++k) a.hist_n1[k * n3 + e] = h1[k];
+  } else {
+    // iter 0 leaves history n+1 untouched in the reference, i.e. equal to history n since the last
+    // commit; cpfft_update exchanges the two buffers instead of copying, so carry the n values over
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a.hist_n1[k * n3 + e] = a.hist_n[k * n3 + e];
   }
 #pragma unroll
   for (int k = 0; k < 36; ++k) a.cep[k * n3 + e] = cep[k];
@@ -605,10 +610,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   }
 }
 
-// P and K4 of one voxel from (Fn, Fn1, unrotated stress, [D]).  CEP_REGS = false: [D] is re-read from
-// memory inside the output loop instead of being held in 72 registers (development variant,
-// CPFFT_PK1_CEP=mem; the kernel spills 1200 B per thread with [D] in registers).
-template <bool CEP_REGS = true>
+// P and K4 of one voxel from (Fn, Fn1, unrotated stress, [D]).
 CPF_DI void upd_pk1_voxel(const double* Fn, const double* Fn1, const double* urcs_n1, const double* cep,
                           double* Pn1, double* K4, const int64_t n3, const int64_t e) {
   double fn[9], fn1[9], t6[6], P[9];
@@ -616,15 +618,10 @@ CPF_DI void upd_pk1_voxel(const double* Fn, const double* Fn1, const double* urc
   for (int k = 0; k < 9; ++k) { fn[k] = Fn[k * n3 + e]; fn1[k] = Fn1[k * n3 + e]; }
 #pragma unroll
   for (int k = 0; k < 6; ++k) t6[k] = urcs_n1[k * n3 + e];
-  if constexpr (CEP_REGS) {
-    double C[36];
+  double C[36];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) C[k] = cep[k * n3 + e];
-    pk1_and_tangent(fn, fn1, t6, C, P, nullptr, K4 + e, n3);
-  } else {
-    StridedCep C{cep + e, n3};
-    pk1_and_tangent(fn, fn1, t6, C, P, nullptr, K4 + e, n3);
-  }
+  for (int k = 0; k < 36; ++k) C[k] = cep[k * n3 + e];
+  pk1_and_tangent(fn, fn1, t6, C, P, nullptr, K4 + e, n3);
 #pragma unroll
   for (int k = 0; k < 9; ++k) Pn1[k * n3 + e] = P[k];
 }

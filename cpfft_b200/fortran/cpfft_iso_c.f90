@@ -142,6 +142,11 @@ module cpfft_iso_c
        import :: c_ptr
        type(c_ptr), value :: handle
      end function
+     integer(c_int) function cpfft_step_counter(handle, next_step, cg_truncated) bind(c, name='cpfft_step_counter')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: handle
+       integer(c_int), intent(out) :: next_step, cg_truncated
+     end function
      integer(c_int) function cpfft_field_ncomp(handle, f) bind(c, name='cpfft_field_ncomp')
        import :: c_int, c_ptr
        type(c_ptr), value :: handle

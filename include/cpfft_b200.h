@@ -124,7 +124,8 @@ int cpfft_fftPcg(cpfft_handle* h, cpfft_field b, cpfft_field x, double tol,
                  int* iters, double* relres);                          /* FFT_nr3.f:214         */
 int cpfft_tangent_homo(cpfft_handle* h, double C_homo[81]);            /* tangent_homo.f:11     */
 int cpfft_mean_P(cpfft_handle* h, double Pbar[9]);                     /* FFT_nr3.f:127-134     */
-int cpfft_update(cpfft_handle* h);                  /* update.f:75-106 + dcopy FFT_nr3.f:174-175 */
+int cpfft_update(cpfft_handle* h);                  /* update.f:75-106 + dcopy FFT_nr3.f:174-175:
+                                                       n/n+1 history buffers exchanged, Fn/Pn copied */
 
 /* The whole step loop of FFT_nr3 (FFT_nr3.f:14-200) with zero host traffic inside:
  * BC_all (nstep,9) row-major cumulative table (inlod.f:57-63), isNBC[9].
@@ -142,6 +143,10 @@ int cpfft_FFT_nr3(cpfft_handle* h, int nstep, const double* BC_all, const int32_
  * FFT_nr3.f:195-199: step banner, "Initial residual", "Iteration i residual", "Stress
  * iteration"), for the steps of the last cpfft_FFT_nr3 call; the host prints them verbatim. */
 const char* cpfft_step_log(const cpfft_handle* h);
+/* next_step: number of the load step the next cpfft_FFT_nr3 call starts with (the `step` loop
+ * variable of FFT_nr3.f:51); cg_truncated: CG counts the last call could not return because
+ * cg_cap was too small (0 = the cg_iters rows are complete). */
+int cpfft_step_counter(const cpfft_handle* h, int* next_step, int* cg_truncated);
 
 /* ---- host <-> device movement of whole fields ---- */
 int cpfft_field_ncomp(const cpfft_handle* h, cpfft_field f);

@@ -52,6 +52,8 @@ def _lib():
         L.orc_drive_eps_sig.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_G_K_dF.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_fftPcg.argtypes = [C.c_void_p, dp, dp, C.c_double, ip, dp]
+        L.orc_fftPcg_capped.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_int, ip, dp]
+        L.orc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), dp]
         L.orc_tangent_homo.argtypes = [C.c_void_p, dp]
         L.orc_update.argtypes = [C.c_void_p]
         L.orc_mean_P.argtypes = [C.c_void_p, dp]

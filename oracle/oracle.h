@@ -98,6 +98,11 @@ int32_t* orc_local_iters(orc_model*); /* (N3,2): mm10 predictor / update NR iter
 int  orc_drive_eps_sig(orc_model*, int step, int iter);
 void orc_G_K_dF(orc_model*, const double* F, double* GKF, int flgK);
 int  orc_fftPcg(orc_model*, const double* b, double* x, double tol, int* iters, double* relres);
+/* the same loop left after `cap` iterations without an error, and the model's work counters
+ * {G_K_dF applications, sweeps, CG iterations} / seconds {pcg, sig-eps}: for the bounded CPU
+ * sample of bench.py --impl reference */
+int  orc_fftPcg_capped(orc_model*, const double* b, double* x, double tol, int cap, int* iters, double* relres);
+void orc_counters(const orc_model*, int64_t* c3, double* t2);
 int  orc_tangent_homo(orc_model*, double* C_homo);
 void orc_update(orc_model*);
 void orc_mean_P(orc_model*, double* Pbar);

@@ -8,17 +8,24 @@ namespace orc {
 // ---------------------------------------------------------------------------
 // evcmp1_new (polar.f:224-307): closed-form (Cardano) eigenvalues of the metric
 // tensor, c in upper-triangular order (11,12,22,13,23,33).
+// Every product and sum up to the discriminant is rounded on its own, in source order, never
+// contracted into an FMA (nc_*): the discriminant cancels to round-off for nearly equal
+// stretches, and a fixed rounding sequence makes that noise reproducible across builds.
+static inline double nc_mul(double a, double b) { double r = a * b; __asm__ volatile("" : "+x"(r)); return r; }
+static inline double nc_add(double a, double b) { double r = a + b; __asm__ volatile("" : "+x"(r)); return r; }
+static inline double nc_sub(double a, double b) { double r = a - b; __asm__ volatile("" : "+x"(r)); return r; }
 static void evcmp1_new(const double c[6], double lam[3]) {
   const double third = 0.3333333333333333333, oneroot3 = 0.5773502691896258;
   double m11 = c[0], m12 = c[1], m13 = c[3], m22 = c[2], m23 = c[4], m33 = c[5];
-  double de = m12 * m23, dd = m12 * m12, ee = m23 * m23, ff = m13 * m13;
-  double m = m11 + m22 + m33;
-  double c1 = (m11 * m22 + m11 * m33 + m22 * m33) - (dd + ee + ff);
-  double c0 = m33 * dd + m11 * ee + m22 * ff - m11 * m22 * m33 - 2.0 * m13 * de;
-  double p = m * m - 3.0 * c1;
-  double q = m * (p - 1.5 * c1) - 13.5 * c0;
+  double de = nc_mul(m12, m23), dd = nc_mul(m12, m12), ee = nc_mul(m23, m23), ff = nc_mul(m13, m13);
+  double m = nc_add(nc_add(m11, m22), m33);
+  double c1 = nc_sub(nc_add(nc_add(nc_mul(m11, m22), nc_mul(m11, m33)), nc_mul(m22, m33)), nc_add(nc_add(dd, ee), ff));
+  double c0 = nc_sub(nc_sub(nc_add(nc_add(nc_mul(m33, dd), nc_mul(m11, ee)), nc_mul(m22, ff)), nc_mul(nc_mul(m11, m22), m33)),
+                     nc_mul(nc_mul(2.0, m13), de));
+  double p = nc_sub(nc_mul(m, m), nc_mul(3.0, c1));
+  double q = nc_sub(nc_mul(m, nc_sub(p, nc_mul(1.5, c1))), nc_mul(13.5, c0));
+  double phi = nc_mul(27.0, nc_add(nc_mul(nc_mul(nc_mul(0.25, c1), c1), nc_sub(p, c1)), nc_mul(c0, nc_add(q, nc_mul(6.75, c0)))));
   double sqrtp = std::sqrt(std::fabs(p));
-  double phi = 27.0 * (0.25 * c1 * c1 * (p - c1) + c0 * (q + 6.75 * c0));
   phi = third * std::atan2(std::sqrt(std::fabs(phi)), q);
   double cphi = sqrtp * std::cos(phi);
   double sphi = oneroot3 * sqrtp * std::sin(phi);
@@ -35,12 +42,11 @@ static void evcmp1_new(const double c[6], double lam[3]) {
 // rtcmp1 / irscp1 / ivcmp1 (polar.f:18-211): R = F U^-1
 void rtcmp1(const M33 f, M33 r) {
   double c[6], cc[6], ev[3];
-  c[0] = f[0][0] * f[0][0] + f[1][0] * f[1][0] + f[2][0] * f[2][0];
-  c[1] = f[0][0] * f[0][1] + f[1][0] * f[1][1] + f[2][0] * f[2][1];
-  c[2] = f[0][1] * f[0][1] + f[1][1] * f[1][1] + f[2][1] * f[2][1];
-  c[3] = f[0][0] * f[0][2] + f[1][0] * f[1][2] + f[2][0] * f[2][2];
-  c[4] = f[0][1] * f[0][2] + f[1][1] * f[1][2] + f[2][1] * f[2][2];
-  c[5] = f[0][2] * f[0][2] + f[1][2] * f[1][2] + f[2][2] * f[2][2];
+  auto dot3 = [&](int a, int b) {
+    return nc_add(nc_add(nc_mul(f[0][a], f[0][b]), nc_mul(f[1][a], f[1][b])), nc_mul(f[2][a], f[2][b]));
+  };
+  c[0] = dot3(0, 0); c[1] = dot3(0, 1); c[2] = dot3(1, 1);
+  c[3] = dot3(0, 2); c[4] = dot3(1, 2); c[5] = dot3(2, 2);
   cc[0] = c[0] * c[0] + c[1] * c[1] + c[3] * c[3];
   cc[1] = c[0] * c[1] + c[1] * c[2] + c[3] * c[4];
   cc[2] = c[1] * c[1] + c[2] * c[2] + c[4] * c[4];

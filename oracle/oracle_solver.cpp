@@ -490,7 +490,8 @@ static double dot(const double* x, const double* y, size_t n) {
 
 // fftPcg (FFT_nr3.f:214-360): unpreconditioned CG (stand-in for MKL RCI dcg) with the user
 // stopping test ||r|| <= tol*||b|| or ||r|| <= tol, evaluated before every iteration.
-extern "C" int orc_fftPcg(orc_model* m, const double* b, double* x, double tol, int* iters, double* relres) {
+// cap > 0: leave the loop after `cap` iterations without an error (bench.py's bounded CPU sample)
+static int fftPcg_impl(orc_model* m, const double* b, double* x, double tol, int* iters, double* relres, int cap) {
   double t0 = now_s();
   const size_t n = 9 * (size_t)m->N3;
   const int maxIter = 1000;
@@ -507,6 +508,7 @@ extern "C" int orc_fftPcg(orc_model* m, const double* b, double* x, double tol, 
     resnorm = nrm2(r.data(), n);
     if (resnorm <= tolb || resnorm <= tol) break;
     if (it >= maxIter) { rc = 2; break; }  // FFT_nr3.f:335
+    if (cap > 0 && it >= cap) break;
     if (it == 0) p = r;
     else {
       double beta = rr / rr_old;
@@ -524,6 +526,17 @@ extern "C" int orc_fftPcg(orc_model* m, const double* b, double* x, double tol, 
   if (relres) *relres = resnorm / n2b;
   m->t_pcg += now_s() - t0;
   return rc;
+}
+
+extern "C" int orc_fftPcg(orc_model* m, const double* b, double* x, double tol, int* iters, double* relres) {
+  return fftPcg_impl(m, b, x, tol, iters, relres, 0);
+}
+extern "C" int orc_fftPcg_capped(orc_model* m, const double* b, double* x, double tol, int cap, int* iters, double* relres) {
+  return fftPcg_impl(m, b, x, tol, iters, relres, cap);
+}
+extern "C" void orc_counters(const orc_model* m, int64_t* c3, double* t2) {
+  c3[0] = m->n_apply; c3[1] = m->n_sweep; c3[2] = m->n_cg;
+  t2[0] = m->t_pcg; t2[1] = m->t_sig;
 }
 
 extern "C" void orc_mean_P(orc_model* m, double* Pbar) {

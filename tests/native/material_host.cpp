@@ -104,8 +104,7 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
       else upd_mm10_voxel<false, MM10_VOCE>(a, e, sm);
     }
     // even voxels: [D] in registers (the kernel's default), odd voxels: the memory-resident variant
-    if (e & 1) upd_pk1_voxel<false>(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
-    else upd_pk1_voxel<true>(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
+    upd_pk1_voxel(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
   }
   return m->failcnt[1];
 }

@@ -68,8 +68,8 @@ def test_usage_errors_without_device(lib):
     assert lib.cpfft_hist_size(None) == 0
     assert lib.cpfft_local_voxels(None) == 0
     assert lib.cpfft_last_error(None) == b"null handle"
-    assert lib.cpfft_profile_classes() == 10
-    names = [lib.cpfft_profile_name(i).decode() for i in range(10)]
+    assert lib.cpfft_profile_classes() == 11
+    names = [lib.cpfft_profile_name(i).decode() for i in range(11)]
     assert "k_x_green" in names and "k_update_mm10" in names
 
 

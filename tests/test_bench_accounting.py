@@ -103,9 +103,9 @@ def test_bench_main_dry_run(monkeypatch, capsys):
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
-    for extra in ([], ["--variant", "taylor2"], ["--stress-bc"]):
+    for extra in ([], ["--variant", "taylor2"], ["--strain-bc"]):
         monkeypatch.setattr(sys, "argv", ["bench.py", "--grid", "8", "--grains", "5", "--steps", "2", "--warmup", "3",
-                                          "--no-cpu-baseline"] + extra)
+                                          "--no-cpu-baseline", "--no-parity"] + extra)
         b.main()
         line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -113,7 +113,9 @@ def test_bench_main_dry_run(monkeypatch, capsys):
                     "cpu_baseline"):
             assert key in line, key
         assert line["metric"] == b.METRIC and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3
-        assert line["value"] == 8 ** 3 * 100 / 0.25 and line["ms_per_step"] == 125.0
+        assert line["value"] == 8 ** 3 * 100 / 0.5 and line["ms_per_step"] == 250.0     # 2 steps x 250 ms of device time
+        assert line["e2e"]["value"] == 8 ** 3 * 100 / 0.25 and line["e2e"]["steps"] == 2     # stub events: 250 ms whatever the bracket
+        assert ("stress-BC loop" in line["config"]["workload"]) == (extra != ["--strain-bc"])
         assert line["gpu_launches"] == 3000 and line["config"]["cg_solves"] == 8
         assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
         assert line["e2e"]["h2d_bytes_per_step"] == 9 * 512 * 8 and line["e2e"]["d2h_bytes_per_step"] == 18 * 512 * 8

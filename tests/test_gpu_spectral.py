@@ -109,49 +109,68 @@ def test_projection_identities_at_benchmark_size(libs, N):
     assert abs((Gx * y).sum() - (x * Gy).sum()) <= 1e-10 * np.sqrt((x * x).sum() * (y * y).sum())
 
 
-@pytest.mark.parametrize("N,grains", [(16, 20), (15, 20)])
-def test_polycrystal_steps_match_oracle(libs, N, grains):
+@pytest.mark.parametrize("N,grains,stress_bc", [(16, 20, False), (15, 20, False), (16, 20, True), (15, 20, True)])
+def test_polycrystal_steps_match_oracle(libs, N, grains, stress_bc):
     """the synthetic fcc/Voce Voronoi polycrystal of the benchmark at a size the oracle runs in
-    seconds: identical Newton and CG iteration counts, stress-strain curve, fields, history."""
+    seconds, 8 load steps of 0.1 % (>= 6 of them plastic), strain-controlled and with the
+    stress-BC loop of the benchmark's loading (P_yy = P_zz = 0: tangent_homo, 9 CG solves through
+    the fused fast path, NBC_update): identical Newton and CG iteration counts, stress-strain
+    curve, fields, history -- at the north-star tolerances (the polar decomposition's small-strain
+    noise is the same number on both sides, kin.cuh polar_R)."""
     from cpfft_b200.polycrystal import polycrystal
     Solver, Oracle = libs
-    p = polycrystal(N, ngrains=grains)
+    p = polycrystal(N, ngrains=grains, stress_bc=stress_bc)
     s, o = Solver(p), Oracle(p, threads=8)
     s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
-    rs, ro = s.FFT_nr3(nstep=4), o.FFT_nr3(nstep=4)
+    rs, ro = s.FFT_nr3(nstep=8), o.FFT_nr3(nstep=8)
     assert ro["rc"] == 0
     assert list(rs["nr_iters"]) == list(ro["nr_iters"])
-    assert_same_cg_counts(rs["cg_iters"], ro["cg_iters"])
-    assert int(rs["counters"][3]) == int(ro["counters"][3]) == 0
+    assert_same_cg_counts(rs["cg_iters"], ro["cg_iters"], slack=1 if stress_bc else 0)
+    assert int(rs["counters"][3]) == int(ro["counters"][3])
     scale = np.abs(ro["Pbar"]).max()
     errs = {"Pbar": np.abs(rs["Pbar"] - ro["Pbar"]).max() / scale, "P": relerr(s.download("PN1"), o.Pn1),
             "F": relerr(s.download("FN1"), o.Fn1)}
-    print("polycrystal parity", N, errs)
-    # F and the macroscopic curve meet the north-star tolerances; the per-voxel stress at 0.1 %
-    # strain increments is limited by the round-off noise floor of the reference's own polar
-    # decomposition (tests/test_oracle_material.py::test_stress_noise_floor_...): 5e-8
+    print("polycrystal parity", N, stress_bc, errs)
     assert errs["Pbar"] <= TOL_MACRO, errs
     assert errs["F"] <= TOL_VOXEL, errs
-    assert errs["P"] <= 5e-8, errs
-    compare_mm10_history(s.download("HIST_N", 1)[:, :o.H], o.hist_n, 12, tol=5e-8)
+    assert errs["P"] <= TOL_VOXEL, errs
+    if stress_bc:
+        assert np.abs(rs["Pbar"][:, [4, 8]]).max() <= 1e-5 * scale      # the prescribed stresses are met
+    compare_mm10_history(s.download("HIST_N", 1)[:, :o.H], o.hist_n, 12, tol=TOL_VOXEL)
+    # after the commit the n+1 names still read the committed state (cpfft_update exchanges buffers)
+    assert np.array_equal(s.download("HIST_N1", 1), s.download("HIST_N", 1))
+    assert relerr(s.download("URCS_N1", 1), o.urcs_n1) <= TOL_VOXEL
 
 
-def test_polycrystal_stress_bc_matches_oracle(libs):
-    """uniaxial tension with P_yy = P_zz = 0 on the benchmark polycrystal (N = 16): the
-    stress-BC loop, tangent_homo (9 CG solves through the fused fast path) and NBC_update."""
+@pytest.mark.parametrize("name", ["poly32_strain", "poly32_stress", "poly64_strain"])
+def test_polycrystal_matches_frozen_oracle(libs, name):
+    """the benchmark polycrystal at 32^3 (both loadings) and 64^3, 8 load steps: sizes the oracle needs
+    minutes for, so its output is a committed fixture (tools/make_golden_poly.py -> tests/golden/<name>.npz:
+    iteration counts, macroscopic curve, F / P / unrotated stress / mm10 history at 1024 sampled voxels)."""
     from cpfft_b200.polycrystal import polycrystal
-    Solver, Oracle = libs
-    p = polycrystal(16, ngrains=20, stress_bc=True)
-    s, o = Solver(p), Oracle(p, threads=8)
-    s.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
-    rs, ro = s.FFT_nr3(nstep=3), o.FFT_nr3(nstep=3)
-    assert ro["rc"] == 0
-    assert list(rs["nr_iters"]) == list(ro["nr_iters"])
-    assert_same_cg_counts(rs["cg_iters"], ro["cg_iters"], slack=1)
-    scale = np.abs(ro["Pbar"]).max()
-    assert np.abs(rs["Pbar"] - ro["Pbar"]).max() / scale <= 1e-9
-    assert np.abs(rs["Pbar"][:, [4, 8]]).max() <= 1e-5 * scale      # the prescribed stresses are met
-    assert relerr(s.download("FN1"), o.Fn1) <= TOL_VOXEL
+    Solver, _ = libs
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    g = np.load(path)
+    N, nstep, sbc = int(g["N"]), int(g["nstep"]), bool(g["stress_bc"])
+    s = Solver(polycrystal(N, ngrains=int(g["grains"]), stress_bc=sbc))
+    s.drive_eps_sig(1, 0)
+    r = s.FFT_nr3(nstep=nstep)
+    assert list(r["nr_iters"]) == list(g["nr_iters"])
+    assert_same_cg_counts(r["cg_iters"], [[v for v in row if v >= 0] for row in g["cg_iters"]], slack=1 if sbc else 0)
+    assert [int(v) for v in r["counters"][3:5]] == [int(v) for v in g["failures"]]
+    idx = g["idx"]
+    F, P = s.download("FN1"), s.download("PN1")
+    errs = {"Pbar": np.abs(r["Pbar"] - g["Pbar"]).max() / np.abs(g["Pbar"]).max(),
+            "F": np.abs(F[:, idx] - g["F"]).max() / np.abs(g["F"]).max(), "P": np.abs(P[:, idx] - g["P"]).max() / np.abs(g["P"]).max(),
+            "P_absmax": abs(np.abs(P).max() - float(g["P_absmax"])) / float(g["P_absmax"]),
+            "F_abssum": abs(np.abs(F).sum() - float(g["F_abssum"])) / float(g["F_abssum"]),
+            "urcs": relerr(s.download("URCS_N1", 1)[idx], g["urcs"])}
+    print("frozen-oracle parity", name, errs)
+    assert errs["Pbar"] <= TOL_MACRO, errs
+    assert max(errs["F"], errs["P"], errs["urcs"], errs["P_absmax"]) <= TOL_VOXEL and errs["F_abssum"] <= 1e-12, errs
+    compare_mm10_history(s.download("HIST_N", 1)[idx], g["hist"], 12, tol=TOL_VOXEL)
 
 
 @pytest.mark.parametrize("N", [16, 32, 40, 64, 80, 128])

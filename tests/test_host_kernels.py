@@ -15,7 +15,7 @@ from helpers import deck, relerr, TOL_VOXEL, compare_mm10_history, NSLIP
 # by a few 1e-9 in R and in everything rotated by it (measured for the oracle itself in
 # tests/test_oracle_material.py::test_stress_noise_floor_..., bound 5e-8; the GPU polycrystal
 # test uses the same bound).  Local Newton iteration counts are compared exactly.
-TOL_SMALL_STRAIN = 5.0e-8
+TOL_SMALL_STRAIN = 1.0e-9
 
 
 @pytest.fixture(scope="module")

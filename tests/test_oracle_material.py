@@ -159,18 +159,23 @@ def test_homogeneous_single_crystal_is_uniform(Oracle):
 
 
 def test_stress_noise_floor_of_the_reference_polar_decomposition(oracle_built, tmp_path):
-    """Why the small-strain parity tolerance on P is 5e-8 and not 1e-9.
+    """The small-strain noise of the reference's polar decomposition, and how it is pinned.
 
     The reference gets R = F U^-1 from closed-form trigonometric eigenvalues of C = F^T F
     (polar.f:224-307).  Its discriminant cancels catastrophically when the principal stretches
-    differ by less than ~3e-3, the angle phi becomes round-off noise, and the stress inherits a
-    noise of order strain^3 ~ 1e-9..1e-8 (relative).  Two builds of the SAME oracle source that
-    differ only in compiler flags (FMA contraction on/off) therefore disagree by ~1e-8 at
-    strain increments of 1e-3 and agree to <1e-9 only at increments >= 2e-2 -- an
-    implementation-independent 1e-9 per-voxel stress match is not defined below that."""
+    differ by less than ~3e-3: the angle phi becomes round-off noise and R (hence the stress)
+    carries an error of order strain^3 ~ 1e-9..1e-8 against the exact polar factor -- a property
+    of the formula, shared by every implementation of it, the ifort binary included.  Which
+    noise one gets depends on the rounding sequence, so the oracle (oracle_kin.cpp nc_*) and the
+    kernels (kin.cuh CPF_MUL/ADD/SUB) evaluate F -> discriminant with every product and sum
+    rounded on its own in source order.  Then (a) two builds of the oracle that differ in
+    compiler flags (FMA contraction on/off) agree to round-off even at 0.1 % strain, which is
+    what lets the parity tests hold 1e-9 per voxel on the small-increment polycrystal, while
+    (b) the distance to the exact polar factor stays at the formula's noise floor."""
     import ctypes as C
     import os
     import subprocess
+    from scipy.linalg import polar
     src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
     alt = str(tmp_path / "liboracle_alt.so")
     subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=c++17", "-shared", "-o", alt] +
@@ -184,17 +189,18 @@ def test_stress_noise_floor_of_the_reference_polar_decomposition(oracle_built, t
 
     def maxdiff(amp, n=400):
         rng = np.random.default_rng(1)
-        worst = 0.0
+        builds, exact = 0.0, 0.0
         for _ in range(n):
             F = np.eye(3).ravel() + amp * rng.standard_normal(9)
             R = [np.zeros(9), np.zeros(9)]
             for L, r in zip(libs, R):
                 L.orc_rtcmp1(F.ctypes.data_as(dp), r.ctypes.data_as(dp))
             # sigma = R t R^T and d = Rh^T D Rh: a rotation error dR is a relative stress error ~ 2 dR
-            worst = max(worst, np.abs(R[0] - R[1]).max())
-        return worst
+            builds = max(builds, np.abs(R[0] - R[1]).max())
+            exact = max(exact, np.abs(R[0] - polar(F.reshape(3, 3))[0].ravel()).max())
+        return builds, exact
 
-    small, large = maxdiff(1e-3), maxdiff(5e-2)
-    assert small > 5e-10, small         # noise floor is real at 0.1 % strain increments ...
-    assert small < 5e-8, small          # ... and bounded
-    assert large < 1e-11, large         # well separated stretches: reproducible
+    (b_small, x_small), (b_large, x_large) = maxdiff(1e-3), maxdiff(5e-2)
+    assert b_small < 1e-13 and b_large < 1e-13, (b_small, b_large)   # (a) reproducible across builds
+    assert 5e-10 < x_small < 5e-8, x_small    # (b) the formula's noise floor at 0.1 % strain increments ...
+    assert x_large < 1e-11, x_large           # ... gone once the stretches are well separated

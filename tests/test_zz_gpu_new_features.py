@@ -50,7 +50,7 @@ def test_crystal_and_grid_variants(libs, kind):
             same = (d.sum(axis=1) == 0)
             for name, ref in (("PN1", o.Pn1), ("K4", o.K4)):
                 got = s.download(name)
-                assert relerr(got[:, same], ref[:, same]) <= 5e-8, (kind, step, it, name)
+                assert relerr(got[:, same], ref[:, same]) <= 1e-9, (kind, step, it, name)
         s.upload("FN", F); o.Fn[:] = F
         s.update(); o.update()
     assert o.local_iters.sum() > 0

@@ -1,5 +1,5 @@
 """Development helper: A/B timing of the kernel variants behind the development switches
-(CPFFT_IZ_PIPE = 0 k_iz / 1 k_iz_pipe / 2 k_iz_pipe with TMA bulk copies, only with AB_TMA=1; CPFFT_CG_FUSE_X = 0 separate CG update pass / 1 solution
+(CPFFT_IZ_PIPE = 0 k_iz / 1 k_iz_pipe; CPFFT_CG_FUSE_X = 0 separate CG update pass / 1 solution
 update fused into the next forward z pass) inside G_K_dF and inside a CG solve, one process, one
 grid.  CUDA events on the launching stream (the library's kernel-class profiler).
     python tools/ab_iz.py [N=256] [repeats=20]"""
@@ -21,8 +21,6 @@ rng = np.random.default_rng(0)
 x = rng.standard_normal((9, p.N3))
 out = {"grid": N, "repeats": REP, "modes": {}}
 MODES = [("00", 8), ("10", 8), ("01", 8), ("11", 8), ("00", 8)]   # (iz_pipe, cg_fuse_x); baseline first and last: drift check
-if os.environ.get("AB_TMA"):          # the TMA bulk-copy variant of k_iz_pipe (unmeasured so far): last, so a hang costs nothing else
-    MODES.append(("21", 8))
 for mode, lpc in MODES:
     os.environ["CPFFT_IZ_PIPE"] = mode[0]
     os.environ["CPFFT_CG_FUSE_X"] = mode[1]

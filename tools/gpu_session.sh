@@ -10,9 +10,7 @@
 #   gpurun --timeout 120 -- 'tools/gpu_session.sh ncu-cg TAG'    ncu --set full of the kernels of one CG iteration
 #   gpurun --timeout 300 -- 'tools/gpu_session.sh ncu-update TAG' ncu --set full of k_update_mm10 / k_pk1_tangent
 #   gpurun --timeout 120 -- 'tools/gpu_session.sh ab'            A/B of the kernel-variant switches (tools/ab_iz.py)
-#   gpurun --timeout 150 -- 'tools/gpu_session.sh ab-pk1'        A/B of the two k_pk1_tangent variants (tools/time_update.py)
 #   gpurun --timeout 150 -- 'tools/gpu_session.sh ab-lf'         A/B of the lattice-frame residual variant of k_update_mm10 (CPFFT_MM10_LF=1)
-#   gpurun --timeout 100 -- 'tools/gpu_session.sh ab-tma'        adds the untested TMA variant of k_iz_pipe at 64^3
 #   gpurun --timeout 600 -- 'tools/gpu_session.sh first TAG'    first call of a round: new GPU tests, the three unmeasured variants, bench
 set -u
 MODE=${1:-quick}; TAG=${2:-rXX}
@@ -40,15 +38,11 @@ case "$MODE" in
     tail -3 gpurun_out/${TAG}_ncu_update.log; ls -la gpurun_out/prof_${TAG}_update.ncu-rep ;;
   ab)
     timeout 100 python tools/ab_iz.py 256 10 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab256.log ;;
-  ab-pk1)   # k_pk1_tangent with [D] in registers (default, 1200 B stack) vs re-read from memory (824 B stack)
-    (timeout 60 python tools/time_update.py 128; CPFFT_PK1_CEP=mem timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_pk1.log ;;
   ab-lf)    # k_update_mm10 vs k_update_mm10_lf (residual slip loop in the lattice frame): time, checksum, local iterations
     (timeout 60 python tools/time_update.py 128; CPFFT_MM10_LF=1 timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_lf.log ;;
-  ab-tma)   # includes the untested TMA variant of k_iz_pipe (CPFFT_IZ_PIPE=2); own short timeout: an mbarrier bug would hang
-    AB_TMA=1 timeout 60 python tools/ab_iz.py 64 5 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab_tma64.log ;;
   first)    # everything written without a GPU, cheapest first; every leg has its own timeout and log
     timeout 200 python -m pytest tests/test_zz_gpu_new_features.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_zz_tests.log
-    "$0" ab-lf "$TAG"; "$0" ab-pk1 "$TAG"; "$0" ab-tma "$TAG"
+    "$0" ab-lf "$TAG"
     timeout 150 python bench.py --variant mts --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench256_mts.json 2> gpurun_out/${TAG}_bench256_mts.err
     tail -c 300 gpurun_out/${TAG}_bench256_mts.json
     "$0" bench "$TAG" ;;
