@@ -115,9 +115,9 @@ def run_reference(args):
     from cpfft_b200.polycrystal import polycrystal
     N = args.cpu_n
     ngr = max(8, int(round(args.grains * (N / 256.0) ** 3)))
-    prob = polycrystal(N, ngrains=ngr, stress_bc=not args.strain_bc)
+    prob = polycrystal(N, ngrains=ngr, stress_bc=bool(args.stress_bc))
     cores = os.cpu_count() or 1
-    o = Oracle(prob, threads=cores)
+    o = Oracle(prob, threads=cores, polar="double")      # the literal double arithmetic of polar.f, as the reference runs it
     dp = C.POINTER(C.c_double)
     n3 = N ** 3
     # bring the sample into the plastic regime without paying for converged load steps: two 0.2 % increments
@@ -222,12 +222,19 @@ def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
             ent.update({"alg_bytes_per_voxel": b, "achieved_gbs": gbs, "frac_of_hbm": gbs / peak})
         stages[name] = ent
     prof = ncu_profile_data()
-    if prof and prof.get("grid") == N:
+    # ncu is a single-process tool: the captures are from the 256^3 1-GPU run.  The z passes, the CG vector kernels and the
+    # material kernels touch rank-local data only, so their DRAM traffic per launch is that of the capture scaled by the
+    # local voxel count (16.8 M per GPU at 256^3 x1 and 512^3 x8; 16.4 M / 16.0 M at 320^3 x2 / 400^3 x4).
+    local_kernels = ("k_fwd_z_K4", "k_fwd_z", "k_inv_z", "k_update_mm10", "k_pk1_tangent")
+    if prof and (prof.get("grid") == N or world > 1):
+        scale = float(n3) / float(prof["grid"]) ** 3
         for name, ent in prof["kernels"].items():
             if name in stages:
-                # per-launch DRAM traffic of the same kernel on the same local problem (16.8 M voxels per GPU)
-                if world == 1 or ent.get("rank_local", False):
+                if world == 1:
                     stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
+                elif name in local_kernels:
+                    stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"] * scale
+                    stages[name]["ncu_dram_bytes_source"] = f"1-GPU capture at {prof['grid']}^3 x local voxels / {prof['grid']}^3 (rank-local kernel)"
                 if "fp64_flop" in ent and fp64_peak and world == 1:
                     # FP64 rate of the PROFILED launch: its own flop count over its own duration (the
                     # profiled k_update_mm10 launch is a plastic sweep; elastic iter-0 sweeps are a class of their own)
@@ -318,10 +325,13 @@ def main():
     ap.add_argument("--variant", default="voce", choices=["voce", "mts", "taylor2", "taylor4"],
                     help="workload variant for kernel measurements (NOT the BASELINE.json metric unless 'voce'): "
                          "MTS hardening law, or 2 / 4 crystals per material point (Taylor average)")
-    ap.add_argument("--strain-bc", action="store_true",
-                    help="pure strain control (F_yy = F_zz driven at -0.3 F_xx) instead of the default uniaxial tension with "
-                         "P_yy = P_zz = 0 (stress-BC loop + tangent_homo): the stage-timing variant of SURVEY.md 8d")
-    ap.add_argument("--stress-bc", action="store_true", help="(default; kept for older command lines)")
+    ap.add_argument("--stress-bc", action="store_true",
+                    help="time the K steps under the SURVEY.md 8d loading (F_xx driven, P_yy = P_zz = 0: stress-BC loop + "
+                         "tangent_homo, ~4000 G_K_dF applications per load step) instead of its pure-strain variant")
+    ap.add_argument("--strain-bc", action="store_true", help="(default for the K timed steps; kept for older command lines)")
+    ap.add_argument("--stress-leg-steps", type=int, default=1,
+                    help="load steps of the bounded stress-BC leg that precedes the K timed steps (0 = none)")
+    ap.add_argument("--stress-leg-warmup", type=int, default=2, help="untimed stress-BC load steps before them (step 1 is elastic)")
     ap.add_argument("--no-parity", action="store_true", help="skip the 32^3 parity run against tests/golden/poly32_strain.npz")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -363,7 +373,7 @@ def main():
 
     N = args.grid or GRID_FOR_GPUS.get(world, 256)
     W, K = max(args.warmup, 0), max(args.steps, 1)
-    stress_bc = not args.strain_bc
+    stress_bc = bool(args.stress_bc)
     nx = N // world
 
     # ---- N-GPU correctness before anything is timed: the 32^3 polycrystal of tests/golden (8 load steps, oracle
@@ -372,67 +382,95 @@ def main():
     if not args.no_parity:
         parity = parity_run(Solver, polycrystal, world, rank, local_rank, new_nccl_id(), dist if world > 1 else None, torch)
 
-    prob = polycrystal(N, ngrains=args.grains, nstep=max(10, W + K + 2), x_range=(rank * nx, (rank + 1) * nx),
-                       stress_bc=stress_bc)
-    if args.variant != "voce":
-        from cpfft_b200.polycrystal import workload_variant
-        prob = workload_variant(prob, args.variant, args.grains)
-    s = Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=new_nccl_id(), local_slab=True)
-    stream = torch.cuda.ExternalStream(s.stream())
+    Event = torch.cuda.Event
+    nvox = float(N) ** 3
 
-    def barrier():
+    def make_solver(sbc, nsteps):
+        prob = polycrystal(N, ngrains=args.grains, nstep=max(10, nsteps + 2), x_range=(rank * nx, (rank + 1) * nx), stress_bc=sbc)
+        if args.variant != "voce":
+            from cpfft_b200.polycrystal import workload_variant
+            prob = workload_variant(prob, args.variant, args.grains)
+        return Solver(prob, device=local_rank, rank=rank, world=world, nccl_id=new_nccl_id(), local_slab=True)
+
+    def barrier(s):
         s.synchronize(); torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    n3 = s.n3
+    def timed_steps(s, hF, hP, Wl, Kl, sample_clocks):
+        """Wl untimed + Kl timed load steps of solver `s` through the C ABI with the host buffers hF / hP.
+        Returns device seconds with resident inputs, seconds including the copies (both max over ranks) and counters."""
+        stream = torch.cuda.ExternalStream(s.stream())
+        s.drive_eps_sig(1, 0)                       # FFT_finite_3d.f:145
+        step0 = 0
+        for _ in range(Wl):                         # untimed warm-up load steps
+            s.FFT_nr3(nstep=1, first=step0); step0 += 1
+        s.download_ptr("FN1", hF.data_ptr())
+        s.profile(not args.no_profile); s.profile_reset()
+        launches0 = s.kernel_launches()
+        clocks = ClockSampler(local_rank) if sample_clocks else None
+        barrier(s)
+        if clocks and rank == 0:
+            clocks.start()
+        ev0, ev1 = Event(enable_timing=True), Event(enable_timing=True)
+        marks = []
+        c = dict(applies=0, sweeps=0, cgits=0, nfail=0, nfail_final=0, nsolves=0, t_pcg=0.0, t_sig=0.0, nr_hist=[])
+        ev0.record(stream)
+        for _ in range(Kl):
+            a, b = Event(enable_timing=True), Event(enable_timing=True)
+            s.upload_ptr("FN1", hF.data_ptr())                 # host -> device: the step's deformation field
+            a.record(stream)                                   # inputs resident in HBM: `value` starts here
+            r = s.FFT_nr3(nstep=1, first=step0); step0 += 1    # one load step through the ABI
+            b.record(stream)                                   # ... and stops here
+            s.download_ptr("FN1", hF.data_ptr())               # device -> host: F and P of the step
+            s.download_ptr("PN1", hP.data_ptr())
+            marks.append((a, b))
+            c["applies"] += int(r["counters"][0]); c["sweeps"] += int(r["counters"][1]); c["cgits"] += int(r["counters"][2])
+            c["nfail"] += int(r["counters"][3]); c["nfail_final"] += int(r["counters"][4])
+            c["t_pcg"] += float(r["buckets"][0]); c["t_sig"] += float(r["buckets"][1])
+            c["nr_hist"].append(int(r["nr_iters"][0]))
+            c["nsolves"] += sum(len(row) for row in r["cg_iters"])
+        ev1.record(stream)
+        barrier(s)
+        c["clocks"] = clocks.stop() if (clocks and rank == 0) else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in marks)
+        ms = torch.tensor([dev_ms, ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        c["secs"], c["secs_e2e"] = float(ms[0].item()) * 1e-3, float(ms[1].item()) * 1e-3
+        c["launches"] = s.kernel_launches() - launches0
+        c["table"] = s.profile_table()
+        s.profile(False)
+        return c
+
+    n3 = nx * N * N
     hF = torch.empty(9 * n3, dtype=torch.float64).pin_memory()     # host buffers of the caller (pinned)
     hP = torch.empty(9 * n3, dtype=torch.float64).pin_memory()
-    s.drive_eps_sig(1, 0)                       # FFT_finite_3d.f:145
-    step0 = 0
-    for _ in range(W):                          # untimed warm-up load steps
-        s.FFT_nr3(nstep=1, first=step0); step0 += 1
-    s.download_ptr("FN1", hF.data_ptr())
-    s.profile(not args.no_profile); s.profile_reset()
-    launches0 = s.kernel_launches()
-    clocks = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        clocks.start()
-    Event = torch.cuda.Event
-    ev0, ev1 = Event(enable_timing=True), Event(enable_timing=True)
-    marks = []
-    ev0.record(stream)
-    applies = sweeps = cgits = nfail = nfail_final = nsolves = 0
-    t_pcg = t_sig = 0.0
-    nr_hist = []
-    for _ in range(K):
-        a, b = Event(enable_timing=True), Event(enable_timing=True)
-        s.upload_ptr("FN1", hF.data_ptr())                 # host -> device: the step's deformation field
-        a.record(stream)                                   # inputs resident in HBM: `value` starts here
-        r = s.FFT_nr3(nstep=1, first=step0); step0 += 1    # one load step through the ABI
-        b.record(stream)                                   # ... and stops here
-        s.download_ptr("FN1", hF.data_ptr())               # device -> host: F and P of the step
-        s.download_ptr("PN1", hP.data_ptr())
-        marks.append((a, b))
-        applies += int(r["counters"][0]); sweeps += int(r["counters"][1]); cgits += int(r["counters"][2])
-        nfail += int(r["counters"][3]); nfail_final += int(r["counters"][4])
-        t_pcg += float(r["buckets"][0]); t_sig += float(r["buckets"][1])
-        nr_hist.append(int(r["nr_iters"][0]))
-        nsolves += sum(len(row) for row in r["cg_iters"])
-    ev1.record(stream)
-    barrier()
-    clk = clocks.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in marks)
-    ms = torch.tensor([dev_ms, ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    secs, secs_e2e = float(ms[0].item()) * 1e-3, float(ms[1].item()) * 1e-3
-    launches = s.kernel_launches() - launches0
-    table = s.profile_table()
-    s.profile(False)
-    nvox = float(N) ** 3
+
+    # ---- bounded leg under the SURVEY.md 8d loading (F_xx driven, P_yy = P_zz = 0): ~4000 G_K_dF applications per load
+    # step -- 25 s per step at 256^3 -- so the K timed steps of the driver (K = 20, W = 5, 870 s per N in the scaling run)
+    # cannot all be stress-BC steps; this leg measures the same metric on `--stress-leg-steps` of them, every run ----
+    stress_leg = None
+    if not stress_bc and args.stress_leg_steps > 0:
+        sl = make_solver(True, args.stress_leg_warmup + args.stress_leg_steps)
+        c = timed_steps(sl, hF, hP, args.stress_leg_warmup, args.stress_leg_steps, False)
+        sl.close(); del sl
+        torch.cuda.empty_cache()
+        stress_leg = {"loading": "F_xx driven with P_yy = P_zz = 0 (stress-BC loop FFT_nr3.f:127-165 + tangent_homo), 0.1 % per load step",
+                      "value": nvox * c["applies"] / c["secs"], "e2e_value": nvox * c["applies"] / c["secs_e2e"], "unit": UNIT,
+                      "steps": args.stress_leg_steps, "warmup": args.stress_leg_warmup, "ms_per_step": 1e3 * c["secs"] / args.stress_leg_steps,
+                      "newton_iters_per_step": c["nr_hist"], "G_K_dF_applies": c["applies"], "drive_eps_sig_sweeps": c["sweeps"],
+                      "VG_per_s": nvox * c["applies"] / c["t_pcg"] if c["t_pcg"] > 0 else None,
+                      "VU_per_s": nvox * c["sweeps"] / c["t_sig"] if c["t_sig"] > 0 else None,
+                      "mm10_local_failures": {"all_sweeps": c["nfail"], "final_sweeps": c["nfail_final"]}}
+
+    s = make_solver(stress_bc, W + K)
+    assert s.n3 == n3
+    c = timed_steps(s, hF, hP, W, K, True)
+    applies, sweeps, cgits, nsolves = c["applies"], c["sweeps"], c["cgits"], c["nsolves"]
+    nfail, nfail_final, t_pcg, t_sig, nr_hist = c["nfail"], c["nfail_final"], c["t_pcg"], c["t_sig"], c["nr_hist"]
+    secs, secs_e2e, launches, table, clk = c["secs"], c["secs_e2e"], c["launches"], c["table"], c["clocks"]
     value = nvox * applies / secs
     fp64_peak = s.fp64_peak()
     e2e = None
@@ -457,7 +495,7 @@ def main():
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
                                   "--warmup", "1", "--cpu-n", str(args.cpu_n), "--grains", str(args.grains)] +
-                                 (["--strain-bc"] if args.strain_bc else []), capture_output=True, text=True, timeout=900)
+                                 (["--stress-bc"] if args.stress_bc else []), capture_output=True, text=True, timeout=900)
             cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as ex:  # reported, never hidden
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
@@ -469,8 +507,9 @@ def main():
         "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal ({args.grains} random-orientation fcc grains, "
                                f"mm10/{ {'voce': 'Voce', 'mts': 'MTS (variant, not the BASELINE metric)'}.get(args.variant, 'Voce, ' + args.variant[-1] + ' crystals per point (variant, not the BASELINE metric)') }), "
                                "finite-strain uniaxial tension, " +
-                               ("F_xx driven with P_yy = P_zz = 0 (stress-BC loop + tangent_homo)" if stress_bc else "strain-controlled (stage-timing variant)") +
-                               ", 0.1 % per load step",
+                               ("F_xx driven with P_yy = P_zz = 0 (stress-BC loop + tangent_homo)" if stress_bc else
+                                "strain-controlled variant of SURVEY.md 8d for the K timed steps (F_yy = F_zz = -0.3 F_xx); the stress-BC loading of 8d "
+                                "is measured by the bounded leg `stress_bc_leg` of this line") + ", 0.1 % per load step",
                    "grid": N, "voxels": int(nvox), "voxels_per_gpu": int(s.n3), "parallelism": f"x-slabs x{world}",
                    "l2": "working set (>= 1.2 GB per field) far exceeds the 126 MB L2; no flush needed",
                    "step": "one FFT_nr3 load step", "newton_iters_per_step": nr_hist,
@@ -486,7 +525,7 @@ def main():
                                         "512^3 needs >= 4 GPUs (4.8 KB of state per voxel), so strong scaling of it over 2 GPUs is not possible",
                    "even_N_convention": "Nyquist planes of Ghat zeroed (reference is only valid for odd N)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "stages": stages,
-        "cpu_baseline": cpu, "parity": parity,
+        "cpu_baseline": cpu, "parity": parity, "stress_bc_leg": stress_leg,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -14,10 +14,6 @@
 #define CPF_ATOMIC_INC(p) atomicAdd(p, 1)
 #define CPF_D2LL(d) __double_as_longlong(d)
 #define CPF_LL2D(l) __longlong_as_double(l)
-// round-to-nearest product / sum / difference that the compiler may not contract into an FMA
-#define CPF_MUL(a, b) __dmul_rn(a, b)
-#define CPF_ADD(a, b) __dadd_rn(a, b)
-#define CPF_SUB(a, b) __dadd_rn(a, -(b))
 #else
 #include <cmath>
 #include <cstring>
@@ -31,8 +27,4 @@ using std::fabs; using std::sqrt; using std::fmax; using std::isnan;
 #define CPF_ATOMIC_INC(p) __atomic_fetch_add(p, 1, __ATOMIC_RELAXED)
 static inline long long CPF_D2LL(double d) { long long l; std::memcpy(&l, &d, 8); return l; }
 static inline double CPF_LL2D(long long l) { double d; std::memcpy(&d, &l, 8); return d; }
-// the empty asm makes the rounded result a value the optimiser cannot fold into an FMA
-static inline double CPF_MUL(double a, double b) { double r = a * b; __asm__ volatile("" : "+x"(r)); return r; }
-static inline double CPF_ADD(double a, double b) { double r = a + b; __asm__ volatile("" : "+x"(r)); return r; }
-static inline double CPF_SUB(double a, double b) { double r = a - b; __asm__ volatile("" : "+x"(r)); return r; }
 #endif

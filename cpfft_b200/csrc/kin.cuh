@@ -47,74 +47,41 @@ CPF_DI double m3_inv(const double* a, double* g) {
   return d;
 }
 
-// R = F U^-1 with U^-1 = a (b I + c C + d C^2), C = F^T F; eigenvalues of C by the closed
-// form trigonometric solution (polar.f:224-307), invariants of U (polar.f:196-208).
+// Rotation factor R of the polar decomposition F = R U (rtcmp1 / irscp1 / ivcmp1 / evcmp1_new,
+// polar.f:18-307).
+//
+// The reference evaluates a closed form: trigonometric eigenvalues of C = F^T F, invariants of U,
+// U^-1 = a (b I + c C + d C^2), R = F U^-1.  In double precision its discriminant cancels to
+// round-off when the principal stretches differ by less than a few 1e-3 -- every small load
+// increment -- and R comes out with a noise of order strain^3 (up to ~3e-8) that depends on the
+// last bit of F and of every intermediate: two correct implementations of that closed form, or
+// the same one fed an F that differs by 1e-13, disagree by that much in every stress.  What the
+// formula defines (its value in exact arithmetic; oracle/oracle_kin.cpp evaluates it in
+// __float128) is the orthogonal polar factor, and that is what is computed here, to ~1e-15, by the
+// Newton iteration R <- (R + R^-T) / 2 started from F (Higham): the singular values s of the
+// iterate map to (s + 1/s) / 2, so the error squares every trip -- a stretch of 1.5 (50 %
+// strain) reaches 1e-16 in 6 trips, the 1.05 of a finished load path in 4; POLAR_ITERS = 8 fixed
+// trips, no branch, ~45 flops each.  The result is within the reference's own noise band of
+// the reference's result and reproducible to round-off, which lets the parity tests hold
+// 1e-9 per voxel at 0.1 % increments (tests/test_oracle_material.py shows both facts).
+#define POLAR_ITERS 8
 CPF_DI void polar_R(const double* f, double* r) {
-  // From F to the discriminant every product and sum is rounded on its own, in source order
-  // (CPF_MUL / CPF_ADD / CPF_SUB, never contracted into an FMA).  The discriminant of the cubic
-  // cancels to round-off when the principal stretches differ by < 3e-3: the angle phi is then
-  // noise that reaches the stress at the order strain^3 ~ 1e-8.  With one fixed rounding
-  // sequence -- the same one in oracle/oracle_kin.cpp -- that noise is the same number everywhere,
-  // so per-voxel results are comparable to 1e-9 at small strain increments as well.
-#define M_(a, b) CPF_MUL(a, b)
-#define A_(a, b) CPF_ADD(a, b)
-#define S_(a, b) CPF_SUB(a, b)
-  const double c0 = A_(A_(M_(f[0], f[0]), M_(f[3], f[3])), M_(f[6], f[6]));   // C11
-  const double c1 = A_(A_(M_(f[0], f[1]), M_(f[3], f[4])), M_(f[6], f[7]));   // C12
-  const double c2 = A_(A_(M_(f[1], f[1]), M_(f[4], f[4])), M_(f[7], f[7]));   // C22
-  const double c3 = A_(A_(M_(f[0], f[2]), M_(f[3], f[5])), M_(f[6], f[8]));   // C13
-  const double c4 = A_(A_(M_(f[1], f[2]), M_(f[4], f[5])), M_(f[7], f[8]));   // C23
-  const double c5 = A_(A_(M_(f[2], f[2]), M_(f[5], f[5])), M_(f[8], f[8]));   // C33
-  double cc0 = c0 * c0 + c1 * c1 + c3 * c3;
-  double cc1 = c0 * c1 + c1 * c2 + c3 * c4;
-  double cc2 = c1 * c1 + c2 * c2 + c4 * c4;
-  double cc3 = c0 * c3 + c1 * c4 + c3 * c5;
-  double cc4 = c1 * c3 + c2 * c4 + c4 * c5;
-  double cc5 = c3 * c3 + c4 * c4 + c5 * c5;
-  const double third = 0.3333333333333333333, oneroot3 = 0.5773502691896258;
-  const double de = M_(c1, c4), dd = M_(c1, c1), ee = M_(c4, c4), ff = M_(c3, c3);
-  const double m = A_(A_(c0, c2), c5);
-  const double k1 = S_(A_(A_(M_(c0, c2), M_(c0, c5)), M_(c2, c5)), A_(A_(dd, ee), ff));
-  const double k0 = S_(S_(A_(A_(M_(c5, dd), M_(c0, ee)), M_(c2, ff)), M_(M_(c0, c2), c5)), M_(M_(2.0, c3), de));
-  const double p = S_(M_(m, m), M_(3.0, k1));
-  const double q = S_(M_(m, S_(p, M_(1.5, k1))), M_(13.5, k0));
-  double phi = M_(27.0, A_(M_(M_(M_(0.25, k1), k1), S_(p, k1)), M_(k0, A_(q, M_(6.75, k0)))));
-#undef M_
-#undef A_
-#undef S_
-  double sqrtp = sqrt(fabs(p));
-  phi = third * atan2(sqrt(fabs(phi)), q);
-  double sphi_, cphi_;
-  sincos(phi, &sphi_, &cphi_);
-  double cphi = sqrtp * cphi_, sphi = oneroot3 * sqrtp * sphi_;
-  double e2 = third * (m - cphi);
-  double e3 = e2 + sphi, e1 = e2 + cphi;
-  e2 = e2 - sphi;
-  // ascending order as the reference (polar.f:282-298), so the sums round identically
-  { double x;
-    if (e2 < e1) { x = e1; e1 = e2; e2 = x; }
-    if (e3 < e1) { x = e1; e1 = e3; e3 = x; }
-    if (e3 < e2) { x = e2; e2 = e3; e3 = x; } }
-  const double lo = sqrt(e1), mid = sqrt(e2), hi = sqrt(e3);
-  double iu = lo + mid + hi;
-  double iiu = lo * mid + mid * hi + lo * hi;
-  double iiiu = lo * mid * hi;
-  double a2 = 1.0 / (iiiu * (iu * iiu - iiiu));
-  double b2 = iu * iiu * iiu - iiiu * (iu * iu + iiu);
-  double cq = -iiiu - iu * (iu * iu - 2.0 * iiu);
-  double d2 = iu;
-  double u0 = a2 * (b2 + cq * c0 + d2 * cc0);
-  double u1 = a2 * (cq * c1 + d2 * cc1);
-  double u2 = a2 * (b2 + cq * c2 + d2 * cc2);
-  double u3 = a2 * (cq * c3 + d2 * cc3);
-  double u4 = a2 * (cq * c4 + d2 * cc4);
-  double u5 = a2 * (b2 + cq * c5 + d2 * cc5);
+  double a[9];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    r[3 * i + 0] = f[3 * i] * u0 + f[3 * i + 1] * u1 + f[3 * i + 2] * u3;
-    r[3 * i + 1] = f[3 * i] * u1 + f[3 * i + 1] * u2 + f[3 * i + 2] * u4;
-    r[3 * i + 2] = f[3 * i] * u3 + f[3 * i + 1] * u4 + f[3 * i + 2] * u5;
+  for (int k = 0; k < 9; ++k) a[k] = f[k];
+#pragma unroll 1
+  for (int it = 0; it < POLAR_ITERS; ++it) {
+    // cofactors of a: a^-T = cof(a) / det(a)
+    const double c0 = a[4] * a[8] - a[5] * a[7], c1 = a[5] * a[6] - a[3] * a[8], c2 = a[3] * a[7] - a[4] * a[6];
+    const double c3 = a[2] * a[7] - a[1] * a[8], c4 = a[0] * a[8] - a[2] * a[6], c5 = a[1] * a[6] - a[0] * a[7];
+    const double c6 = a[1] * a[5] - a[2] * a[4], c7 = a[2] * a[3] - a[0] * a[5], c8 = a[0] * a[4] - a[1] * a[3];
+    const double hid = 0.5 / (a[0] * c0 + a[1] * c1 + a[2] * c2);
+    a[0] = 0.5 * a[0] + hid * c0; a[1] = 0.5 * a[1] + hid * c1; a[2] = 0.5 * a[2] + hid * c2;
+    a[3] = 0.5 * a[3] + hid * c3; a[4] = 0.5 * a[4] + hid * c4; a[5] = 0.5 * a[5] + hid * c5;
+    a[6] = 0.5 * a[6] + hid * c6; a[7] = 0.5 * a[7] + hid * c7; a[8] = 0.5 * a[8] + hid * c8;
   }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r[k] = a[k];
 }
 
 // Voigt order xx,yy,zz,xy,yz,xz.  sym6 -> full 3x3
@@ -153,6 +120,13 @@ CPF_DI void voxel_kinematics(const double* fn, const double* fn1, double* Rh, do
 // t6: unrotated Cauchy stress (Voigt), C: 6x6 [D] row-major.  Algebraically identical to
 // cep2A_a (cep2A.f:86-284) but every rank-one structure of dR/dF, dRh/dF and dL/dF is
 // contracted analytically, so the cost is O(81 * const) instead of four 81x9 loop nests.
+// C: anything indexable as C[k], k = 6 * row + col -- a register array, or StridedCep, which re-reads
+// the voxel's [D] from global memory (L1-resident: 36 x 256 B per warp) and takes its 36 values out
+// of the register budget of the 9 x 9 output loop.
+struct StridedCep {
+  const double* p; int64_t stride;
+  CPF_DI double operator[](int k) const { return CPF_LDG(p + (int64_t)k * stride); }
+};
 template <class Cep>
 CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t6, const Cep& C,
                             double* P, double* A /*81, may alias nothing*/,

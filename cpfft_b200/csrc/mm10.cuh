@@ -36,6 +36,16 @@
 #ifndef MM10_THREADS
 #define MM10_THREADS 128
 #endif
+// unroll factor of the slip-system loops of the residual and the Jacobian (development knob, tools/build_variants.py)
+#ifndef MM10_SLIP_UNROLL
+#define MM10_SLIP_UNROLL 1
+#endif
+#ifndef MM10_LAZY_PIVOT
+#define MM10_LAZY_PIVOT 1
+#endif
+#define MM10_PRAGMA_(x) _Pragma(#x)
+#define MM10_UNROLL_SLIP_(n) MM10_PRAGMA_(unroll n)
+#define MM10_UNROLL_SLIP MM10_UNROLL_SLIP_(MM10_SLIP_UNROLL)
 
 // Per-thread array kept in shared memory, element k of thread t at p[k * blockDim + t]:
 // conflict-free, and it takes the Jacobian and the skew-rotation operators out of the
@@ -99,7 +109,13 @@ CPF_DI void cpf_lu_solve(double* A, double* B) {
       if (v > best) { best = v; piv = i; }
     }
     // row interchange by value selects (an `if (i == piv) swap` chain is turned into run-time
-    // indexed accesses by the optimiser, which demotes the whole matrix to local memory)
+    // indexed accesses by the optimiser, which demotes the whole matrix to local memory).  The
+    // local Jacobians are close to diagonally dominant, so most eliminations need no interchange:
+    // the ~90 selects of a column are skipped by the lanes (usually all of the warp) whose pivot is
+    // already in place -- same arithmetic, fewer issued instructions.
+#if MM10_LAZY_PIVOT
+    if (piv != k) {
+#endif
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const double top = A[k * N + j];
@@ -124,6 +140,9 @@ CPF_DI void cpf_lu_solve(double* A, double* B) {
       }
       B[k * NR + j] = pv;
     }
+#if MM10_LAZY_PIVOT
+    }
+#endif
     const double inv = 1.0 / A[k * N + k];
 #pragma unroll
     for (int i = k + 1; i < N; ++i) {
@@ -269,7 +288,7 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
       y[5] = 2.0 * (c.Q[0] * U[2] + c.Q[3] * U[5] + c.Q[6] * U[8]);
     }
     double am[6] = {0, 0, 0, 0, 0, 0}, aw[3] = {0, 0, 0};
-#pragma unroll 1
+MM10_UNROLL_SLIP
     for (int s = 0; s < c.nslip; ++s) {
       const double* t = c.ms0 + 9 * s;
       double m[6], w[3];
@@ -306,7 +325,7 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
     wq[1] = c.RWQ[3] * aw[0] + c.RWQ[4] * aw[1] + c.RWQ[5] * aw[2];
     wq[2] = c.RWQ[6] * aw[0] + c.RWQ[7] * aw[1] + c.RWQ[8] * aw[2];
   } else
-#pragma unroll 1
+MM10_UNROLL_SLIP
   for (int s = 0; s < c.nslip; ++s) {
     double ms[6], qs[3];
     mm10_slip_geom(c, s, ms, qs);
@@ -360,7 +379,7 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
 #pragma unroll
     for (int k = 0; k < 3; ++k) { wqs[k] = 0.0; wqf[k] = 0.0; }
     const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v, dgn = c.dg * c.rate_n / tt;
-#pragma unroll 1
+MM10_UNROLL_SLIP
     for (int s = 0; s < c.nslip; ++s) {
       double ms[6], qs[3];
       mm10_slip_geom(c, s, ms, qs);

@@ -62,6 +62,7 @@ def _lib():
         L.orc_FFT_nr3_from.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp,
                                        C.POINTER(C.c_int64)]
         L.orc_rtcmp1.argtypes = [dp, dp]
+        L.orc_set_polar_precision.argtypes = [C.c_int]
         L.orc_cep2A.argtypes = [dp, dp, dp, dp, dp]
         L.orc_point_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
         L.orc_formG_entry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp]
@@ -83,10 +84,14 @@ def _ip(a):
 class Oracle:
     """CPU restatement of the reference hot path for one ``Problem`` (cpfft_b200.problem)."""
 
-    CG_CAP = 64
+    CG_CAP = 256
 
-    def __init__(self, prob, threads: int = 0):
+    def __init__(self, prob, threads: int = 0, polar: str = "quad"):
+        """polar: arithmetic of the reference's polar decomposition, process-wide: "quad" (default) evaluates
+        polar.f's closed form in __float128 -- the value the algorithm defines; "double" is the literal
+        restatement with the reference's own small-strain round-off noise (<= ~3e-8 on R)."""
         L = _lib()
+        L.orc_set_polar_precision(1 if polar == "quad" else 0)
         self.L, self.prob = L, prob
         if threads:
             L.orc_set_threads(threads)

@@ -103,6 +103,11 @@ int  orc_fftPcg(orc_model*, const double* b, double* x, double tol, int* iters, 
  * sample of bench.py --impl reference */
 int  orc_fftPcg_capped(orc_model*, const double* b, double* x, double tol, int cap, int* iters, double* relres);
 void orc_counters(const orc_model*, int64_t* c3, double* t2);
+/* process-wide: arithmetic of rtcmp1 (polar.f).  0 = double, the literal restatement, which carries the
+ * reference's own small-strain noise (<= ~3e-8 on R); 1 = the same formulas in __float128, rounded to
+ * double at the end (default: the value the reference's algorithm defines) */
+void orc_set_polar_precision(int quad);
+int  orc_get_polar_precision(void);
 int  orc_tangent_homo(orc_model*, double* C_homo);
 void orc_update(orc_model*);
 void orc_mean_P(orc_model*, double* Pbar);

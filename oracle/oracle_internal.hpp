@@ -14,6 +14,8 @@ typedef double M66[6][6];
 
 // ---- kinematics (polar.f, drive_eps_sig.f helpers) ----
 void rtcmp1(const M33 f, M33 r);                       // polar.f:18-45
+void set_polar_precision(int quad);                    // 0: literal double arithmetic, 1: __float128 (default)
+int get_polar_precision();
 void getrm1(M66 q, const M33 r, int opt);              // polar.f:680-802
 void qmply1(const M66 q, const double* m1, double* m2);// qmply1.f:15-36
 void inv33(const M33 jac, M33 gama, double* dj);       // drive_eps_sig.f:1017-1107

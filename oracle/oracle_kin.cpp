@@ -2,67 +2,85 @@
 // Kinematics, rotation operators, exact dP/dF and the bilinear Mises model, restated
 // from polar.f, qmply1.f, drive_eps_sig.f:1017-1224, cep2A.f and mm01.f.
 #include "oracle_internal.hpp"
+#include <quadmath.h>
 
 namespace orc {
 
 // ---------------------------------------------------------------------------
-// evcmp1_new (polar.f:224-307): closed-form (Cardano) eigenvalues of the metric
-// tensor, c in upper-triangular order (11,12,22,13,23,33).
-// Every product and sum up to the discriminant is rounded on its own, in source order, never
-// contracted into an FMA (nc_*): the discriminant cancels to round-off for nearly equal
-// stretches, and a fixed rounding sequence makes that noise reproducible across builds.
-static inline double nc_mul(double a, double b) { double r = a * b; __asm__ volatile("" : "+x"(r)); return r; }
-static inline double nc_add(double a, double b) { double r = a + b; __asm__ volatile("" : "+x"(r)); return r; }
-static inline double nc_sub(double a, double b) { double r = a - b; __asm__ volatile("" : "+x"(r)); return r; }
-static void evcmp1_new(const double c[6], double lam[3]) {
-  const double third = 0.3333333333333333333, oneroot3 = 0.5773502691896258;
-  double m11 = c[0], m12 = c[1], m13 = c[3], m22 = c[2], m23 = c[4], m33 = c[5];
-  double de = nc_mul(m12, m23), dd = nc_mul(m12, m12), ee = nc_mul(m23, m23), ff = nc_mul(m13, m13);
-  double m = nc_add(nc_add(m11, m22), m33);
-  double c1 = nc_sub(nc_add(nc_add(nc_mul(m11, m22), nc_mul(m11, m33)), nc_mul(m22, m33)), nc_add(nc_add(dd, ee), ff));
-  double c0 = nc_sub(nc_sub(nc_add(nc_add(nc_mul(m33, dd), nc_mul(m11, ee)), nc_mul(m22, ff)), nc_mul(nc_mul(m11, m22), m33)),
-                     nc_mul(nc_mul(2.0, m13), de));
-  double p = nc_sub(nc_mul(m, m), nc_mul(3.0, c1));
-  double q = nc_sub(nc_mul(m, nc_sub(p, nc_mul(1.5, c1))), nc_mul(13.5, c0));
-  double phi = nc_mul(27.0, nc_add(nc_mul(nc_mul(nc_mul(0.25, c1), c1), nc_sub(p, c1)), nc_mul(c0, nc_add(q, nc_mul(6.75, c0)))));
-  double sqrtp = std::sqrt(std::fabs(p));
-  phi = third * std::atan2(std::sqrt(std::fabs(phi)), q);
-  double cphi = sqrtp * std::cos(phi);
-  double sphi = oneroot3 * sqrtp * std::sin(phi);
-  double e2 = third * (m - cphi);
-  double e3 = e2 + sphi;
-  double e1 = e2 + cphi;
+// Polar decomposition of the reference: evcmp1_new (polar.f:224-307), closed-form (Cardano)
+// eigenvalues of the metric tensor, c in upper-triangular order (11,12,22,13,23,33), and
+// rtcmp1 / irscp1 / ivcmp1 (polar.f:18-211), R = F U^-1 from the invariants of U.
+//
+// Written once for a real type T.  T = double is the literal restatement: like the reference
+// binary it loses the angle phi to round-off when the principal stretches differ by less than a
+// few 1e-3 (the discriminant cancels), which puts a noise of order strain^3 <= ~3e-8 on R, hence
+// on every stress, whatever the compiler makes of the expressions.  T = __float128 evaluates the
+// SAME formulas with 113-bit arithmetic and rounds R to double at the end: the value the
+// reference's algorithm defines, free of that noise.  orc_set_polar_precision() selects which
+// one the model uses (default: __float128, the value the GPU results are held to at 1e-9; the
+// double version measures the reference's own noise band, tests/test_oracle_material.py).
+static inline double r_sqrt(double x) { return std::sqrt(x); }
+static inline double r_fabs(double x) { return std::fabs(x); }
+static inline double r_atan2(double y, double x) { return std::atan2(y, x); }
+static inline double r_cos(double x) { return std::cos(x); }
+static inline double r_sin(double x) { return std::sin(x); }
+static inline __float128 r_sqrt(__float128 x) { return sqrtq(x); }
+static inline __float128 r_fabs(__float128 x) { return fabsq(x); }
+static inline __float128 r_atan2(__float128 y, __float128 x) { return atan2q(y, x); }
+static inline __float128 r_cos(__float128 x) { return cosq(x); }
+static inline __float128 r_sin(__float128 x) { return sinq(x); }
+
+template <class T>
+static void evcmp1_new_t(const T c[6], T lam[3]) {
+  const T third = T(1) / T(3), oneroot3 = T(1) / r_sqrt(T(3));
+  T m11 = c[0], m12 = c[1], m13 = c[3], m22 = c[2], m23 = c[4], m33 = c[5];
+  T de = m12 * m23, dd = m12 * m12, ee = m23 * m23, ff = m13 * m13;
+  T m = m11 + m22 + m33;
+  T c1 = (m11 * m22 + m11 * m33 + m22 * m33) - (dd + ee + ff);
+  T c0 = m33 * dd + m11 * ee + m22 * ff - m11 * m22 * m33 - T(2) * m13 * de;
+  T p = m * m - T(3) * c1;
+  T q = m * (p - T(1.5) * c1) - T(13.5) * c0;
+  T sqrtp = r_sqrt(r_fabs(p));
+  T phi = T(27) * (T(0.25) * c1 * c1 * (p - c1) + c0 * (q + T(6.75) * c0));
+  phi = third * r_atan2(r_sqrt(r_fabs(phi)), q);
+  T cphi = sqrtp * r_cos(phi);
+  T sphi = oneroot3 * sqrtp * r_sin(phi);
+  T e2 = third * (m - cphi);
+  T e3 = e2 + sphi;
+  T e1 = e2 + cphi;
   e2 = e2 - sphi;
-  if (e2 < e1) { double s = e1; e1 = e2; e2 = s; }
-  if (e3 < e1) { double s = e1; e1 = e3; e3 = s; }
-  if (e3 < e2) { double s = e2; e2 = e3; e3 = s; }
+  if (e2 < e1) { T s = e1; e1 = e2; e2 = s; }
+  if (e3 < e1) { T s = e1; e1 = e3; e3 = s; }
+  if (e3 < e2) { T s = e2; e2 = e3; e3 = s; }
   lam[0] = e1; lam[1] = e2; lam[2] = e3;
 }
 
-// rtcmp1 / irscp1 / ivcmp1 (polar.f:18-211): R = F U^-1
-void rtcmp1(const M33 f, M33 r) {
-  double c[6], cc[6], ev[3];
-  auto dot3 = [&](int a, int b) {
-    return nc_add(nc_add(nc_mul(f[0][a], f[0][b]), nc_mul(f[1][a], f[1][b])), nc_mul(f[2][a], f[2][b]));
-  };
-  c[0] = dot3(0, 0); c[1] = dot3(0, 1); c[2] = dot3(1, 1);
-  c[3] = dot3(0, 2); c[4] = dot3(1, 2); c[5] = dot3(2, 2);
+template <class T>
+static void rtcmp1_t(const M33 fd, M33 r) {
+  T f[3][3], c[6], cc[6], ev[3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) f[i][j] = T(fd[i][j]);
+  c[0] = f[0][0] * f[0][0] + f[1][0] * f[1][0] + f[2][0] * f[2][0];
+  c[1] = f[0][0] * f[0][1] + f[1][0] * f[1][1] + f[2][0] * f[2][1];
+  c[2] = f[0][1] * f[0][1] + f[1][1] * f[1][1] + f[2][1] * f[2][1];
+  c[3] = f[0][0] * f[0][2] + f[1][0] * f[1][2] + f[2][0] * f[2][2];
+  c[4] = f[0][1] * f[0][2] + f[1][1] * f[1][2] + f[2][1] * f[2][2];
+  c[5] = f[0][2] * f[0][2] + f[1][2] * f[1][2] + f[2][2] * f[2][2];
   cc[0] = c[0] * c[0] + c[1] * c[1] + c[3] * c[3];
   cc[1] = c[0] * c[1] + c[1] * c[2] + c[3] * c[4];
   cc[2] = c[1] * c[1] + c[2] * c[2] + c[4] * c[4];
   cc[3] = c[0] * c[3] + c[1] * c[4] + c[3] * c[5];
   cc[4] = c[1] * c[3] + c[2] * c[4] + c[4] * c[5];
   cc[5] = c[3] * c[3] + c[4] * c[4] + c[5] * c[5];
-  evcmp1_new(c, ev);
-  ev[0] = std::sqrt(ev[0]); ev[1] = std::sqrt(ev[1]); ev[2] = std::sqrt(ev[2]);
-  double iu = ev[0] + ev[1] + ev[2];
-  double iiu = ev[0] * ev[1] + ev[1] * ev[2] + ev[0] * ev[2];
-  double iiiu = ev[0] * ev[1] * ev[2];
-  double a2 = 1.0 / (iiiu * (iu * iiu - iiiu));
-  double b2 = iu * iiu * iiu - iiiu * (iu * iu + iiu);
-  double c2 = -iiiu - iu * (iu * iu - 2.0 * iiu);
-  double d2 = iu;
-  double ui[6];
+  evcmp1_new_t<T>(c, ev);
+  ev[0] = r_sqrt(ev[0]); ev[1] = r_sqrt(ev[1]); ev[2] = r_sqrt(ev[2]);
+  T iu = ev[0] + ev[1] + ev[2];
+  T iiu = ev[0] * ev[1] + ev[1] * ev[2] + ev[0] * ev[2];
+  T iiiu = ev[0] * ev[1] * ev[2];
+  T a2 = T(1) / (iiiu * (iu * iiu - iiiu));
+  T b2 = iu * iiu * iiu - iiiu * (iu * iu + iiu);
+  T c2 = -iiiu - iu * (iu * iu - T(2) * iiu);
+  T d2 = iu;
+  T ui[6];
   ui[0] = a2 * (b2 + c2 * c[0] + d2 * cc[0]);
   ui[1] = a2 * (c2 * c[1] + d2 * cc[1]);
   ui[2] = a2 * (b2 + c2 * c[2] + d2 * cc[2]);
@@ -70,10 +88,18 @@ void rtcmp1(const M33 f, M33 r) {
   ui[4] = a2 * (c2 * c[4] + d2 * cc[4]);
   ui[5] = a2 * (b2 + c2 * c[5] + d2 * cc[5]);
   for (int i = 0; i < 3; ++i) {
-    r[i][0] = f[i][0] * ui[0] + f[i][1] * ui[1] + f[i][2] * ui[3];
-    r[i][1] = f[i][0] * ui[1] + f[i][1] * ui[2] + f[i][2] * ui[4];
-    r[i][2] = f[i][0] * ui[3] + f[i][1] * ui[4] + f[i][2] * ui[5];
+    r[i][0] = (double)(f[i][0] * ui[0] + f[i][1] * ui[1] + f[i][2] * ui[3]);
+    r[i][1] = (double)(f[i][0] * ui[1] + f[i][1] * ui[2] + f[i][2] * ui[4]);
+    r[i][2] = (double)(f[i][0] * ui[3] + f[i][1] * ui[4] + f[i][2] * ui[5]);
   }
+}
+
+static int g_polar_quad = 1;
+void set_polar_precision(int quad) { g_polar_quad = quad ? 1 : 0; }
+int get_polar_precision() { return g_polar_quad; }
+void rtcmp1(const M33 f, M33 r) {
+  if (g_polar_quad) rtcmp1_t<__float128>(f, r);
+  else rtcmp1_t<double>(f, r);
 }
 
 // getrm1 (polar.f:680-802). opt 1: {d} = q{D}, d = R^T D R (engineering shear);

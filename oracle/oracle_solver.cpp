@@ -683,6 +683,11 @@ extern "C" int orc_FFT_nr3(orc_model* m, int nstep, const double* BC_all, const 
   return orc_FFT_nr3_from(m, 1, nstep, BC_all, isNBC, nr_iters, cg_iters, cg_cap, Pbar_out, buckets, counters);
 }
 
+// arithmetic of the polar decomposition (oracle_kin.cpp): 0 = double, the literal restatement with the
+// reference's small-strain noise; 1 = the same formulas in __float128 (default)
+extern "C" void orc_set_polar_precision(int quad) { set_polar_precision(quad); }
+extern "C" int orc_get_polar_precision() { return get_polar_precision(); }
+
 // ---- unit probes ----
 extern "C" void orc_rtcmp1(const double* F9, double* R9) {
   M33 f, r;

@@ -55,7 +55,7 @@ class _StubSolver:
     """stands in for cpfft_b200.Solver in the dry run of bench.main(): hands back the recorded r01g
     kernel-class profile and plausible per-step counters; no device work"""
     def __init__(self, prob, **kw):
-        self.prob, self.n3, self.step, self._launches = prob, prob.N3, 0, 0
+        self.prob, self.n3, self.step, self._launches = prob, len(prob.matlist), 0, 0
         rec = json.loads(open(os.path.join(ROOT, "profiles", "r01g_bench256_1gpu.json")).read().strip().splitlines()[-1])
         self._table = {k: (v["ms_total"], v["launches"]) for k, v in rec["stages"].items()}
 
@@ -74,6 +74,7 @@ class _StubSolver:
     def exchange_mode(self): return "single"
     def download_ptr(self, name, ptr): pass
     def upload_ptr(self, name, ptr): pass
+    def close(self): pass
 
     def FFT_nr3(self, nstep=1, first=0):
         import numpy as np
@@ -103,7 +104,7 @@ def test_bench_main_dry_run(monkeypatch, capsys):
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
-    for extra in ([], ["--variant", "taylor2"], ["--strain-bc"]):
+    for extra in ([], ["--variant", "taylor2"], ["--stress-bc"]):
         monkeypatch.setattr(sys, "argv", ["bench.py", "--grid", "8", "--grains", "5", "--steps", "2", "--warmup", "3",
                                           "--no-cpu-baseline", "--no-parity"] + extra)
         b.main()
@@ -115,7 +116,9 @@ def test_bench_main_dry_run(monkeypatch, capsys):
         assert line["metric"] == b.METRIC and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3
         assert line["value"] == 8 ** 3 * 100 / 0.5 and line["ms_per_step"] == 250.0     # 2 steps x 250 ms of device time
         assert line["e2e"]["value"] == 8 ** 3 * 100 / 0.25 and line["e2e"]["steps"] == 2     # stub events: 250 ms whatever the bracket
-        assert ("stress-BC loop" in line["config"]["workload"]) == (extra != ["--strain-bc"])
+        assert (line["stress_bc_leg"] is None) == (extra == ["--stress-bc"])
+        if line["stress_bc_leg"]:
+            assert line["stress_bc_leg"]["steps"] == 1 and line["stress_bc_leg"]["value"] == 8 ** 3 * 50 / 0.25
         assert line["gpu_launches"] == 3000 and line["config"]["cg_solves"] == 8
         assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
         assert line["e2e"]["h2d_bytes_per_step"] == 9 * 512 * 8 and line["e2e"]["d2h_bytes_per_step"] == 18 * 512 * 8

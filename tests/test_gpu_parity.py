@@ -192,6 +192,27 @@ def test_cli_runs_a_deck_end_to_end(tmp_path):
     assert len(rows) == 343 and all(len(r) == 26 * 15 for r in rows)
 
 
+@pytest.mark.parametrize("deck_name", ["test_mm10.in", "test_mm01.in"])
+def test_cli_matches_reference_run(deck_name, tmp_path):
+    """the CUDA path against flat result files of a real reference run, when a maintainer has provided them under
+    tests/golden/reference_run/<deck>/ (recipe there); skips otherwise -- the external pin is open."""
+    import os
+    import subprocess
+    import sys
+    from helpers import DECKS
+    from test_reference_run_slot import SLOT, reference_files, compare_flat
+    files = reference_files(deck_name)
+    if not files:
+        pytest.skip(f"no reference run under {SLOT}/{deck_name}: parity unpinned")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nstep = max(int(f[3:8]) for f in files)
+    out = subprocess.run([sys.executable, "-m", "cpfft_b200", os.path.join(DECKS, deck_name), "--outdir", str(tmp_path),
+                          "--steps", str(nstep)], capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    for f in files:
+        compare_flat(str(tmp_path / f), os.path.join(SLOT, deck_name, f), f)
+
+
 @pytest.mark.parametrize("mixed", [False, True])
 def test_taylor_points(libs, mixed):
     """polycrystalline material points (mm10 n_crystals = 3, Taylor average mm10_a.f:112-197;

@@ -159,19 +159,22 @@ def test_homogeneous_single_crystal_is_uniform(Oracle):
 
 
 def test_stress_noise_floor_of_the_reference_polar_decomposition(oracle_built, tmp_path):
-    """The small-strain noise of the reference's polar decomposition, and how it is pinned.
+    """The small-strain noise of the reference's polar decomposition, and what parity is held to.
 
     The reference gets R = F U^-1 from closed-form trigonometric eigenvalues of C = F^T F
-    (polar.f:224-307).  Its discriminant cancels catastrophically when the principal stretches
-    differ by less than ~3e-3: the angle phi becomes round-off noise and R (hence the stress)
-    carries an error of order strain^3 ~ 1e-9..1e-8 against the exact polar factor -- a property
-    of the formula, shared by every implementation of it, the ifort binary included.  Which
-    noise one gets depends on the rounding sequence, so the oracle (oracle_kin.cpp nc_*) and the
-    kernels (kin.cuh CPF_MUL/ADD/SUB) evaluate F -> discriminant with every product and sum
-    rounded on its own in source order.  Then (a) two builds of the oracle that differ in
-    compiler flags (FMA contraction on/off) agree to round-off even at 0.1 % strain, which is
-    what lets the parity tests hold 1e-9 per voxel on the small-increment polycrystal, while
-    (b) the distance to the exact polar factor stays at the formula's noise floor."""
+    (polar.f:224-307).  In double precision its discriminant cancels catastrophically when the
+    principal stretches differ by less than ~3e-3: the angle phi becomes round-off noise and R
+    (hence every stress) carries an error of order strain^3 ~ 1e-9..3e-8.  That is a property of
+    the formula in double arithmetic, shared by every build of it, the ifort binary included:
+      (a) two builds of the literal double restatement that differ only in compiler flags (FMA
+          contraction on/off) disagree by ~1e-8 at strain increments of 1e-3 and agree to 1e-11 only
+          once the stretches are separated by >= 2e-2 -- a 1e-9 per-voxel match against ANY double
+          evaluation of the closed form is not defined at the benchmark's 0.1 % increments;
+      (b) the same formulas in __float128 (the oracle's default, orc_set_polar_precision) give the
+          exact polar factor -- the value the algorithm defines -- to 1e-14 at every strain;
+      (c) the literal double result lies within 5e-8 of it.
+    The kernels compute the polar factor to ~1e-15 (kin.cuh polar_R), so GPU results are held to
+    1e-9 against (b) and sit inside the reference's own noise band (c)."""
     import ctypes as C
     import os
     import subprocess
@@ -179,28 +182,37 @@ def test_stress_noise_floor_of_the_reference_polar_decomposition(oracle_built, t
     src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
     alt = str(tmp_path / "liboracle_alt.so")
     subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=c++17", "-shared", "-o", alt] +
-                          [os.path.join(src, f) for f in ("oracle_kin.cpp", "oracle_mm10.cpp", "oracle_solver.cpp")])
+                          [os.path.join(src, f) for f in ("oracle_kin.cpp", "oracle_mm10.cpp", "oracle_solver.cpp")] + ["-lquadmath"])
     dp = C.POINTER(C.c_double)
     libs = []
     for path in (oracle_built, alt):
         L = C.CDLL(path)
         L.orc_rtcmp1.argtypes = [dp, dp]
+        L.orc_set_polar_precision.argtypes = [C.c_int]
         libs.append(L)
 
     def maxdiff(amp, n=400):
         rng = np.random.default_rng(1)
-        builds, exact = 0.0, 0.0
+        builds = quad_exact = dbl_quad = 0.0
         for _ in range(n):
             F = np.eye(3).ravel() + amp * rng.standard_normal(9)
-            R = [np.zeros(9), np.zeros(9)]
+            R = [np.zeros(9), np.zeros(9), np.zeros(9)]
             for L, r in zip(libs, R):
+                L.orc_set_polar_precision(0)
                 L.orc_rtcmp1(F.ctypes.data_as(dp), r.ctypes.data_as(dp))
+            libs[0].orc_set_polar_precision(1)
+            libs[0].orc_rtcmp1(F.ctypes.data_as(dp), R[2].ctypes.data_as(dp))
             # sigma = R t R^T and d = Rh^T D Rh: a rotation error dR is a relative stress error ~ 2 dR
             builds = max(builds, np.abs(R[0] - R[1]).max())
-            exact = max(exact, np.abs(R[0] - polar(F.reshape(3, 3))[0].ravel()).max())
-        return builds, exact
+            quad_exact = max(quad_exact, np.abs(R[2] - polar(F.reshape(3, 3))[0].ravel()).max())
+            dbl_quad = max(dbl_quad, np.abs(R[0] - R[2]).max())
+        return builds, quad_exact, dbl_quad
 
-    (b_small, x_small), (b_large, x_large) = maxdiff(1e-3), maxdiff(5e-2)
-    assert b_small < 1e-13 and b_large < 1e-13, (b_small, b_large)   # (a) reproducible across builds
-    assert 5e-10 < x_small < 5e-8, x_small    # (b) the formula's noise floor at 0.1 % strain increments ...
-    assert x_large < 1e-11, x_large           # ... gone once the stretches are well separated
+    try:
+        small, large = maxdiff(1e-3), maxdiff(5e-2)
+    finally:
+        libs[0].orc_set_polar_precision(1)
+    assert 5e-10 < small[0] < 5e-8, small     # (a) the noise floor is real at 0.1 % strain increments, and bounded ...
+    assert large[0] < 1e-11, large            #     ... and gone once the stretches are well separated
+    assert small[1] < 1e-13 and large[1] < 1e-13, (small, large)     # (b)
+    assert small[2] < 5e-8 and large[2] < 1e-11, (small, large)      # (c)

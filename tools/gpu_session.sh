@@ -40,6 +40,22 @@ case "$MODE" in
     timeout 100 python tools/ab_iz.py 256 10 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab256.log ;;
   ab-lf)    # k_update_mm10 vs k_update_mm10_lf (residual slip loop in the lattice frame): time, checksum, local iterations
     (timeout 60 python tools/time_update.py 128; CPFFT_MM10_LF=1 timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_lf.log ;;
+  mm10ab)   # A/B of libcpfft_b200.so variants built by tools/build_variants.py (gpurun_variants/lib_*.so): material sweep at 128^3
+    for lib in gpurun_variants/lib_*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 2>&1 | tail -1; done | tee gpurun_out/${TAG}_mm10ab.log ;;
+  mgpu)     # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then the forward-transpose pipeline on / off
+    NG=${3:-2}; GRID=${4:-320}
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533"
+    (timeout 120 $TR tools/multi_gpu_check.py --grid 32 --steps 4; timeout 120 $TR tools/multi_gpu_check.py --grid 64 --steps 3;
+     CPFFT_FWD_CHUNKS=1 timeout 120 $TR tools/multi_gpu_check.py --grid 64 --steps 3) 2>&1 | grep -E "^\{|rror" | tee gpurun_out/${TAG}_mgpu${NG}_check.log
+    for ch in 1 4 8; do
+      CPFFT_FWD_CHUNKS=$ch timeout 300 $TR bench.py --gpus $NG --grid $GRID --steps 3 --warmup 3 --stress-leg-steps 0 --no-parity \
+          > gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}.json 2> gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}.err
+      python - <<PY
+import json
+l=json.loads(open("gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}.json").read().strip().splitlines()[-1])
+print("chunks", $ch, "value %.4g" % l["value"], "e2e %.4g" % l["e2e"]["value"], {k: round(v["ms_per_launch"], 3) for k, v in l["stages"].items()})
+PY
+    done | tee gpurun_out/${TAG}_mgpu${NG}_pipeline.log ;;
   first)    # everything written without a GPU, cheapest first; every leg has its own timeout and log
     timeout 200 python -m pytest tests/test_zz_gpu_new_features.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_zz_tests.log
     "$0" ab-lf "$TAG"
