@@ -140,12 +140,21 @@ __global__ void k_sum_comp_partial(const double* x, int64_t n3, double* partials
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = s;
 }
+// Second stage: one CTA per slot sums nb partials in a fixed order.  Four independent accumulators per thread keep
+// four loads in flight: the p.Ap sums of the fast spectral path arrive as one partial per grid line (65536 at 256^3),
+// and a single dependent chain per thread made this 8-byte result cost 0.15 ms per CG iteration (round 1: 256 threads).
 __global__ void k_final_sum(const double* partials, int nb, double* out) {  // blockIdx.x = slot
-  double s = 0.0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partials[blockIdx.x * nb + i];
+  const double* p = partials + (int64_t)blockIdx.x * nb;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int T = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * T < nb; i += 4 * T) { s0 += p[i]; s1 += p[i + T]; s2 += p[i + 2 * T]; s3 += p[i + 3 * T]; }
+  for (; i < nb; i += T) s0 += p[i];
+  double s = (s0 + s1) + (s2 + s3);
   s = block_sum(s);
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
+static inline int final_threads(int nb) { return nb > 4096 ? 1024 : VEC_THREADS; }
 
 // FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread, enough CTAs to fill
 // the chip.  MEASURED_PEAKS.json carries no FP64 figure, so the roofline denominator of the
@@ -577,7 +586,7 @@ static int pcg_dev(cpfft_handle* h, const double* b, double* x, double tol, int*
       rc = cpf_cg_apply_pow2(h, p, q, r, (it == 0) ? 0.0 : rr / rr_old, it > 0, &nparts,
                              (fuse_x && it > 0) ? x : nullptr, rr_old, pq_dev); if (rc) return rc;
       const int tk = cpf_prof_begin(h, CPF_K_VECTOR);
-      k_final_sum<<<1, VEC_THREADS, 0, h->stream>>>(h->d_partials, nparts, pq_dev);
+      k_final_sum<<<1, final_threads(nparts), 0, h->stream>>>(h->d_partials, nparts, pq_dev);
       cpf_prof_end(h, tk);
       h->launches++;
     } else {

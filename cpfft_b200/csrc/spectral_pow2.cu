@@ -57,6 +57,12 @@ template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8
 // floor the compiler spends 254 registers per thread on k_fz and a single CTA fits (measured
 // at 320^3: occupancy 7.6 %, 56 % of the HBM peak).
 template <int N> struct ZOcc { static constexpr int MINB = (512 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT; };
+// resident CTAs the inverse z pass is compiled for (development knob IZ_MINB, tools/build_variants.py)
+#ifdef IZ_MINB
+template <int N> struct ZOccI { static constexpr int MINB = (N == 256) ? IZ_MINB : ZOcc<N>::MINB; };
+#else
+template <int N> struct ZOccI { static constexpr int MINB = ZOcc<N>::MINB; };
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // z passes: one grid line (x, y) and its 9 components per CTA, H = N/2 threads, two voxels
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz(Pow2Args g
 // 16-byte LDGSTS measured the same or slower (profiles/r02a_ab_tma64.log) and was removed.
 #include <cuda_pipeline.h>
 template <int N, bool DOT>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOccI<N>::MINB) k_iz_pipe(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
                                                                               const double* __restrict__ pvec, double* __restrict__ partials, int64_t nlines, int lpc) {
   typedef ZSmem<N> Z;
   constexpr int H = Z::H, HB = Z::HB;

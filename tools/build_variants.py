@@ -3,6 +3,7 @@
 gpurun_variants/ (travels to the GPU box; git-ignored) for A/B timing with CPFFT_B200_LIB=...:
 
     python tools/build_variants.py t64c4:-DUPD_THREADS=64,-DMM10_MIN_CTAS=4 unroll2:-DMM10_SLIP_UNROLL=2
+    python tools/build_variants.py iz5:tu=spectral_pow2.cu,-DIZ_MINB=5      # another translation unit
 """
 import os
 import subprocess
@@ -19,21 +20,23 @@ OUT = os.path.join(ROOT, "gpurun_variants")
 def build(name, defines):
     objdir = os.path.join(OUT, "obj_" + name)
     os.makedirs(objdir, exist_ok=True)
+    tus = [d[3:] for d in defines if d.startswith("tu=")] or ["material.cu"]
+    defines = [d for d in defines if not d.startswith("tu=")]
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + defines + ["-Xptxas", "-v"]
     objs = []
-    for src in ("material.cu",):
+    for src in tus:
         obj = os.path.join(objdir, src[:-3] + ".o")
         log = subprocess.run(["nvcc"] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
         if log.returncode:
             raise SystemExit(log.stderr[-3000:])
         lines = log.stderr.splitlines()
         for i, l in enumerate(lines):
-            if "Compiling entry function '_Z13k_update_mm107UpdArgs'" in l:
+            if "Compiling entry function '_Z13k_update_mm107UpdArgs'" in l or ("k_iz_pipeILi256ELb1E" in l and "Compiling" in l):
                 print(name, "|", lines[i + 2].strip(), "|", lines[i + 3].strip())
         objs.append(obj)
     # the other translation units are the default build's objects
     base = os.path.join(ROOT, "cpfft_b200", "build")
-    objs += [os.path.join(base, f) for f in ("spectral.o", "spectral_pow2.o", "solver.o")]
+    objs += [os.path.join(base, f[:-3] + ".o") for f in ("material.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu") if f not in tus]
     lib = os.path.join(OUT, f"lib_{name}.so")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-ldl"])
     return lib

@@ -42,6 +42,8 @@ case "$MODE" in
     (timeout 60 python tools/time_update.py 128; CPFFT_MM10_LF=1 timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_lf.log ;;
   mm10ab)   # A/B of libcpfft_b200.so variants built by tools/build_variants.py (gpurun_variants/lib_*.so): material sweep at 128^3
     for lib in gpurun_variants/lib_*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 2>&1 | tail -1; done | tee gpurun_out/${TAG}_mm10ab.log ;;
+  izab)     # A/B of the inverse z pass occupancy variants (gpurun_variants/lib_iz*.so) at 256^3
+    for lib in gpurun_variants/lib_iz*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_apply.py 256 2>&1 | tail -2; done | tee gpurun_out/${TAG}_izab.log ;;
   mgpu)     # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then the forward-transpose pipeline on / off
     NG=${3:-2}; GRID=${4:-320}
     TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533"

@@ -20,3 +20,13 @@ for _ in range(20):
 t = s.profile_table()
 print(os.environ.get("CPFFT_B200_LIB", "default"), "N", N, {k: round(v[0] / max(v[1], 1), 4) for k, v in t.items() if v[1]},
       "checksum", float(np.abs(s.download("B")).sum()))
+# the same kernels inside a CG solve (fused direction / solution updates in k_fz, p.Ap sums in k_iz_pipe)
+F = np.zeros((9, p.N3)); F[[0, 4, 8]] = 1.0
+F += 0.002 * rng.standard_normal((9, p.N3))
+s.upload("FN1", F); s.drive_eps_sig(1, 1)
+s.upload("DFM", x); s.G_K_dF("DFM", "B", 1)
+s.profile_reset()
+it, rr = s.fftPcg("B", "DFM", 1e-6)
+t = s.profile_table()
+print("   CG", it, "iterations", {k: round(v[0] / max(v[1], 1), 4) for k, v in t.items() if v[1]},
+      "ms/iteration", round(sum(v[0] for v in t.values()) / max(it, 1), 4))
