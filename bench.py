@@ -322,9 +322,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel CUDA events inside the timed region")
-    ap.add_argument("--variant", default="voce", choices=["voce", "mts", "taylor2", "taylor4"],
+    ap.add_argument("--variant", default="voce", choices=["voce", "mts", "taylor2", "taylor4", "bcc48"],
                     help="workload variant for kernel measurements (NOT the BASELINE.json metric unless 'voce'): "
-                         "MTS hardening law, or 2 / 4 crystals per material point (Taylor average)")
+                         "MTS hardening law, 2 / 4 crystals per material point (Taylor average), or 48-system bcc grains")
     ap.add_argument("--stress-bc", action="store_true",
                     help="time the K steps under the SURVEY.md 8d loading (F_xx driven, P_yy = P_zz = 0: stress-BC loop + "
                          "tangent_homo, ~4000 G_K_dF applications per load step) instead of its pure-strain variant")
@@ -505,7 +505,7 @@ def main():
         "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic {N}^3 Voronoi polycrystal ({args.grains} random-orientation fcc grains, "
-                               f"mm10/{ {'voce': 'Voce', 'mts': 'MTS (variant, not the BASELINE metric)'}.get(args.variant, 'Voce, ' + args.variant[-1] + ' crystals per point (variant, not the BASELINE metric)') }), "
+                               f"mm10/{ {'voce': 'Voce', 'mts': 'MTS (variant, not the BASELINE metric)', 'bcc48': 'Voce, bcc48 slip family (variant, not the BASELINE metric)'}.get(args.variant, 'Voce, ' + args.variant[-1] + ' crystals per point (variant, not the BASELINE metric)') }), "
                                "finite-strain uniaxial tension, " +
                                ("F_xx driven with P_yy = P_zz = 0 (stress-BC loop + tangent_homo)" if stress_bc else
                                 "strain-controlled variant of SURVEY.md 8d for the K timed steps (F_yy = F_zz = -0.3 F_xx); the stress-BC loading of 8d "

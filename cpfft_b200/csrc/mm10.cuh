@@ -40,9 +40,6 @@
 #ifndef MM10_SLIP_UNROLL
 #define MM10_SLIP_UNROLL 1
 #endif
-#ifndef MM10_LAZY_PIVOT
-#define MM10_LAZY_PIVOT 1
-#endif
 #define MM10_PRAGMA_(x) _Pragma(#x)
 #define MM10_UNROLL_SLIP_(n) MM10_PRAGMA_(unroll n)
 #define MM10_UNROLL_SLIP MM10_UNROLL_SLIP_(MM10_SLIP_UNROLL)
@@ -109,13 +106,10 @@ CPF_DI void cpf_lu_solve(double* A, double* B) {
       if (v > best) { best = v; piv = i; }
     }
     // row interchange by value selects (an `if (i == piv) swap` chain is turned into run-time
-    // indexed accesses by the optimiser, which demotes the whole matrix to local memory).  The
-    // local Jacobians are close to diagonally dominant, so most eliminations need no interchange:
-    // the ~90 selects of a column are skipped by the lanes (usually all of the warp) whose pivot is
-    // already in place -- same arithmetic, fewer issued instructions.
-#if MM10_LAZY_PIVOT
-    if (piv != k) {
-#endif
+    // indexed accesses by the optimiser, which demotes the whole matrix to local memory).
+    // Skipping the selects when the pivot is already in place (`if (piv != k)`, the common case)
+    // measured 4 % SLOWER (profiles/r02c_mm10ab.log: 21.4 vs 20.5 ms at 128^3): the branch costs
+    // more than the ~90 predicated selects it saves.
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const double top = A[k * N + j];
@@ -140,9 +134,6 @@ CPF_DI void cpf_lu_solve(double* A, double* B) {
       }
       B[k * NR + j] = pv;
     }
-#if MM10_LAZY_PIVOT
-    }
-#endif
     const double inv = 1.0 / A[k * N + k];
 #pragma unroll
     for (int i = k + 1; i < N; ++i) {

@@ -91,6 +91,9 @@ def workload_variant(prob, variant, ngrains):
     ``taylorN`` = N crystals per material point.  For kernel measurements and the multi-GPU self-check,
     not the headline workload."""
     import dataclasses
+    if variant == "bcc48":     # the 48-system bcc family of test_mm10.in (mod_crystals.f:812-1205) on every grain
+        prob.crystals = [dataclasses.replace(prob.crystals[0], slip_type=8)]
+        return prob
     if variant == "mts":       # `hardening mts` with the thresholds of tests/golden/decks/mts_mm10.in
         c = dataclasses.replace(prob.crystals[0], h_type=2, theta_0=1500.0, tau_a=20.0, tau_hat_y=180.0, g_0_y=0.4,
                                 tau_hat_v=300.0, g_0_v=1.2, burgers=2.5e-7, mu_0=80000.0, D_0=3000.0, T_0=200.0)
