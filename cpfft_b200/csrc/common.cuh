@@ -49,6 +49,7 @@ struct cpfft_handle {
   cudaStream_t stream2;
   cudaEvent_t ev_chunk[CPF_MAX_CHUNKS]; cudaEvent_t ev_join;
   int fwd_chunks;            // x-plane chunks of that pipeline (CPFFT_FWD_CHUNKS, default 4; 1 = no pipelining)
+  int fyf_ctas;              // CTAs of the persistent forward y pass of a chunk (CPFFT_FYF_CTAS)
   std::string err;
   std::string log;           // the reference's step / iteration lines of the last cpfft_FFT_nr3 call
   int64_t launches;

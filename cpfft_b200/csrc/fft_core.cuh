@@ -1,6 +1,6 @@
-// cpfft_b200: register-resident radix-2/4/8/16 butterflies and in-place shared-memory FFT stages
-// for power-of-two and a few 5-smooth line lengths (the benchmark grids; everything else goes
-// through the generic Stockham path in spectral.cu).
+// cpfft_b200: register-resident radix-2/3/4/5/8/15/16/17 butterflies and in-place shared-memory FFT
+// stages for power-of-two, a few 5-smooth and the odd 15 / 51 / 85 / 255 line lengths (the benchmark
+// grids; everything else goes through the generic Stockham path in spectral.cu).
 //
 // Decomposition of an N-point line, N = R1 R2 [R3]: decimation in frequency, every stage in
 // place.  Stage with current sub-transform length Ns and radix R, M = Ns / R: task (q, t)
@@ -62,6 +62,78 @@ template <int DIR> struct Dft<5, DIR> {
     v[0] = make_double2(x0.x + a.x + b.x, x0.y + a.y + b.y);
     v[1] = c_add(p1, q1); v[4] = c_sub(p1, q1);
     v[2] = c_add(p2, q2); v[3] = c_sub(p2, q2);
+  }
+};
+template <int DIR> struct Dft<3, DIR> {
+  static FHD void run(cplx* v) {
+    const double s = 0.86602540378443864676;                                  // sin(2 pi/3)
+    const cplx a = c_add(v[1], v[2]), d = c_sub(v[1], v[2]), x0 = v[0];
+    const cplx p = make_double2(x0.x - 0.5 * a.x, x0.y - 0.5 * a.y);
+    const cplx q = c_rot<DIR>(make_double2(s * d.x, s * d.y));                // forward: X1 = p - i s d
+    v[0] = c_add(x0, a); v[1] = c_add(p, q); v[2] = c_sub(p, q);
+  }
+};
+// Odd prime radix held in registers (17 for the 255 = 3 x 5 x 17 grid, the reference-faithful size next to
+// 256): with a_n = x_n + x_{P-n}, b_n = x_n - x_{P-n} the outputs come in pairs
+//   X_k, X_{P-k} = (x_0 + sum_n a_n cos(2 pi n k / P))  -/+  i sum_n b_n sin(2 pi n k / P)   (forward),
+// (P-1)^2 / 2 real multiply-adds per complex component instead of (P-1)^2 complex ones.
+template <int DIR> struct Dft<17, DIR> {
+  static FHD void run(cplx* v) {
+    constexpr int P = 17, Hh = 8;
+    const double cs[P] = {1.0, 0.932472229404355804573, 0.739008917220659115925, 0.445738355776538267396, 0.0922683594633019952397, -0.273662990072082863539, -0.602634636379256389179, -0.850217135729614152134, -0.982973099683901778282, -0.982973099683901778282, -0.850217135729614152134, -0.602634636379256389179, -0.273662990072082863539, 0.0922683594633019952397, 0.445738355776538267396, 0.739008917220659115925, 0.932472229404355804573};
+    const double sn[P] = {0.0, 0.361241666187152948745, 0.673695643646557211713, 0.895163291355062322067, 0.995734176295034521871, 0.961825643172819070409, 0.798017227280239503333, 0.526432162877355800245, 0.183749517816570331574, -0.183749517816570331574, -0.526432162877355800245, -0.798017227280239503333, -0.961825643172819070409, -0.995734176295034521871, -0.895163291355062322067, -0.673695643646557211713, -0.361241666187152948745};
+    cplx a[Hh], b[Hh];
+#pragma unroll
+    for (int n = 1; n <= Hh; ++n) { a[n - 1] = c_add(v[n], v[P - n]); b[n - 1] = c_sub(v[n], v[P - n]); }
+    const cplx x0 = v[0];
+    cplx sum = x0;
+#pragma unroll
+    for (int n = 0; n < Hh; ++n) sum = c_add(sum, a[n]);
+    v[0] = sum;
+#pragma unroll
+    for (int k = 1; k <= Hh; ++k) {
+      double pr = x0.x, pi = x0.y, qr = 0.0, qi = 0.0;
+#pragma unroll
+      for (int n = 1; n <= Hh; ++n) {
+        const int m = (n * k) % P;
+        pr += cs[m] * a[n - 1].x; pi += cs[m] * a[n - 1].y;
+        qr += sn[m] * b[n - 1].x; qi += sn[m] * b[n - 1].y;
+      }
+      const cplx q = c_rot<DIR>(make_double2(qr, qi));
+      v[k] = make_double2(pr + q.x, pi + q.y);
+      v[P - k] = make_double2(pr - q.x, pi - q.y);
+    }
+  }
+};
+// 15 = 3 x 5 (Cooley-Tukey inside the registers, as DftCT below with the 15th roots)
+template <int DIR> struct Dft<15, DIR> {
+  static FHD void run(cplx* v) {
+    constexpr int R1 = 3, R2 = 5, R = 15;
+    const double cs[R] = {1.0, 0.913545457642600895502, 0.669130606358858213826, 0.309016994374947424102, -0.1045284632676534714, -0.5, -0.809016994374947424102, -0.978147600733805637929, -0.978147600733805637929, -0.809016994374947424102, -0.5, -0.1045284632676534714, 0.309016994374947424102, 0.669130606358858213826, 0.913545457642600895502};
+    const double sn[R] = {0.0, 0.406736643075800207754, 0.743144825477394235015, 0.951056516295153572116, 0.994521895368273336923, 0.866025403784438646764, 0.587785252292473129169, 0.207911690817759337102, -0.207911690817759337102, -0.587785252292473129169, -0.866025403784438646764, -0.994521895368273336923, -0.951056516295153572116, -0.743144825477394235015, -0.406736643075800207754};
+    cplx y[R2][R1];
+#pragma unroll
+    for (int b = 0; b < R2; ++b) {
+      cplx t[R1];
+#pragma unroll
+      for (int a = 0; a < R1; ++a) t[a] = v[R2 * a + b];
+      Dft<R1, DIR>::run(t);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) {
+        const int m = (b * k1) % R;
+        const cplx w = make_double2(cs[m], DIR < 0 ? -sn[m] : sn[m]);
+        y[b][k1] = (b == 0 || k1 == 0) ? t[k1] : c_mul(t[k1], w);
+      }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      cplx t[R2];
+#pragma unroll
+      for (int b = 0; b < R2; ++b) t[b] = y[b][k1];
+      Dft<R2, DIR>::run(t);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = t[k2];
+    }
   }
 };
 template <int DIR> struct Dft<8, DIR> {
@@ -174,6 +246,14 @@ template <> struct FftPlan<160> { static constexpr int R1 = 10, R2 = 16, R3 = 1;
 template <> struct FftPlan<200> { static constexpr int R1 = 5,  R2 = 5,  R3 = 8; };
 template <> struct FftPlan<320> { static constexpr int R1 = 5,  R2 = 8,  R3 = 8; };   // measured: radix 20 spills in the x / y passes
 template <> struct FftPlan<400> { static constexpr int R1 = 5,  R2 = 5,  R3 = 16; };
+
+// odd sizes: 255 = 15 x 17 is the reference-faithful neighbour of 256 (the reference's Ghat is a projection for
+// odd N only, FFT_init.f:146-147, 370-375); 15, 51, 85 are its small relatives for the parity tests
+template <> struct FftPlan<15>  { static constexpr int R1 = 15, R2 = 1,  R3 = 1; };
+// (radix 17 first: the last forward stage of the y pass keeps its outputs in registers, the fewer the better)
+template <> struct FftPlan<51>  { static constexpr int R1 = 17, R2 = 3,  R3 = 1; };
+template <> struct FftPlan<85>  { static constexpr int R1 = 17, R2 = 5,  R3 = 1; };
+template <> struct FftPlan<255> { static constexpr int R1 = 17, R2 = 15, R3 = 1; };
 
 // position (after the forward stages) <-> natural frequency index
 template <int N> FHD int fft_natural(int p) {

@@ -367,6 +367,9 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
     h->fwd_chunks = fc ? atoi(fc) : 4;
     if (h->fwd_chunks < 1) h->fwd_chunks = 1;
     if (h->fwd_chunks > CPF_MAX_CHUNKS) h->fwd_chunks = CPF_MAX_CHUNKS;
+    const char* fy = getenv("CPFFT_FYF_CTAS");
+    h->fyf_ctas = fy ? atoi(fy) : g_num_sms / 2;
+    if (h->fyf_ctas < 1) h->fyf_ctas = 1;
   }
   h->nxloc = cfg->N / h->cfg.world; h->x0 = h->cfg.rank * h->nxloc;
   h->n3 = (int64_t)h->nxloc * cfg->N * cfg->N;

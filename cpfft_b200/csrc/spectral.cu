@@ -256,7 +256,7 @@ int cpf_spectral_init(cpfft_handle* h) {
     h->iz_lpc = l ? atoi(l) : 8;
     if (h->iz_lpc < 1) h->iz_lpc = 1;
   }
-  if (h->fast_pow2) h->Nh = N / 2;   // the Nyquist bin is never stored (Ghat = 0 there)
+  if (h->fast_pow2) h->Nh = (N & 1) ? (N + 1) / 2 : N / 2;   // even N: the Nyquist bin is never stored (Ghat = 0 there)
   choose_radices(N, h->radices, &h->nrad);
   std::vector<cplx> tw(N);
   for (int k = 0; k < N; ++k) {
@@ -270,7 +270,7 @@ int cpf_spectral_init(cpfft_handle* h) {
   CPF_CUDA(cudaMemcpy(h->d_radices, h->radices, sizeof(int) * 32, cudaMemcpyHostToDevice));
   CPF_CUDA(cudaMalloc(&h->spec_a, sizeof(cplx) * spec_elems));
   h->spec_b = nullptr; h->spec_c = nullptr;
-  if (h->fast_pow2) CPF_CUDA(cudaMalloc(&h->spec_c, sizeof(cplx) * (size_t)9 * h->nxloc * N * (N / 2)));
+  if (h->fast_pow2) CPF_CUDA(cudaMalloc(&h->spec_c, sizeof(cplx) * spec_elems));
   if ((size_t)2 * 9 * N * sizeof(cplx) > 227 * 1024) {
     cpf_set_error(h, "grid edge too large for the shared-memory z pass (N <= 806)");
     return CPFFT_ERR_USAGE;

@@ -15,6 +15,7 @@
 // Spectrum layout: spec[((c * NX + x) * NY + y) * NZ + kz], NZ = N/2, complex double.
 #include "common.cuh"
 #include "fft_core.cuh"
+#include <algorithm>
 
 struct Pow2Args {
   int nx, x0;    // local x planes (z / y passes) and their global offset
@@ -37,6 +38,12 @@ struct PeerPtrs { cplx* p[CPF_MAX_WORLD]; };
 //   * z passes: one grid line per CTA beats two (k_iz 0.78 -> 0.70 ms);
 //   * giving the whole L1 to shared memory (cudaSharedmemCarveoutMaxShared) slows every pass
 //     down (k_fz 1.9 -> 3.0 ms): the streaming loads want the L1.
+// KB = stored kz bins per line: N/2 for even N (the Nyquist bin is never stored), (N+1)/2 for odd N (all of
+// kz = 0 .. (N-1)/2; an odd grid has no Nyquist frequency and reproduces the reference's Ghat exactly).
+template <int N> struct KzBins { static constexpr int value = (N & 1) ? (N + 1) / 2 : N / 2; };
+// signed integer frequency of bin k of an N-point transform: 0 .. ceil(N/2)-1, then -floor(N/2) .. -1
+template <int N> __device__ __forceinline__ double sfreq(int k) { return (double)((2 * k < N) ? k : k - N); }
+
 template <int N> struct Pow2Cfg {
   static constexpr int H = N / 2;
   static constexpr int TZY = (H < 16 ? H : 16) < (4096 / N) ? (H < 16 ? H : 16) : (4096 / N);
@@ -53,6 +60,13 @@ template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, 
 template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 128; };
 template <> struct Pow2Cfg<320> { static constexpr int H = 160, TZY = 16, TZX = 8, ZT = 160; };
 template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8, ZT = 224; };
+// CTA size the y / x pass kernels are compiled for: 255 runs 272 -> 288 threads, which leaves its radix-17 butterflies
+// 224 registers instead of 128
+template <int N> struct YXBound { static constexpr int value = (N == 255) ? 288 : 512; };
+// odd grids (z passes: k_fz_odd / k_iz_odd, one voxel per thread): TZY / TZX divide KB = (N+1)/2
+template <> struct Pow2Cfg<15>  { static constexpr int H = 7,   TZY = 8,  TZX = 8,  ZT = 32; };
+template <> struct Pow2Cfg<51>  { static constexpr int H = 25,  TZY = 13, TZX = 13, ZT = 64; };
+template <> struct Pow2Cfg<255> { static constexpr int H = 127, TZY = 16, TZX = 8,  ZT = 256; };
 // Resident CTAs per SM the z passes are compiled for: keep >= 512 threads per SM.  Without a
 // floor the compiler spends 254 registers per thread on k_fz and a single CTA fits (measured
 // at 320^3: occupancy 7.6 %, 56 % of the HBM peak).
@@ -404,6 +418,174 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOccI<N>::MINB) k_iz_pipe(Pow2
 }
 
 // ---------------------------------------------------------------------------------------------
+// z passes for ODD N (15, 51, 255): the reference-faithful grids -- its Ghat is a projection for odd N only
+// (FFT_init.f:146-147, 370-375).  A real line of odd length cannot be packed as an N/2-point complex line, so
+// the nine real lines of a grid line (x, y) travel as five complex lines z_j = c_{2j} + i c_{2j+1} (j = 0..3) and
+// z_4 = c_8, one N-point transform each, and are separated with
+//   C_{2j}[k] = (Z[k] + conj Z[N-k]) / 2,   C_{2j+1}[k] = (Z[k] - conj Z[N-k]) / (2 i),   k = 0 .. (N-1)/2.
+// One voxel per thread (lines of odd length are not 16-byte aligned); everything else -- the K4 contraction with
+// the reference's summation tree, the fused CG direction / solution updates (MODE), the fused p.Ap sums (DOT) --
+// is what k_fz / k_iz do.  Shared memory: A[i * 5 + j] (in-place stages), B[j * NB + k] (natural order), tw[N].
+template <int N> struct OddZ {
+  static constexpr int KB = (N + 1) / 2, NB = N + 1;
+  static constexpr int ZT = (N + 31) / 32 * 32;
+  static constexpr int MINB = (512 + ZT - 1) / ZT > 8 ? 8 : (512 + ZT - 1) / ZT;
+  static constexpr size_t bytes = sizeof(cplx) * (5 * N + 5 * NB + N);
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(OddZ<N>::ZT, OddZ<N>::MINB) k_fz_odd(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
+                                              cplx* __restrict__ spec, const double* __restrict__ rvec, double beta,
+                                              double* __restrict__ xvec, double rr_alpha, const double* __restrict__ pq) {
+  typedef FftPlan<N> P;
+  constexpr int KB = OddZ<N>::KB, NB = OddZ<N>::NB, N1 = N / P::R1;
+  static_assert(P::R3 == 1, "odd plans have at most two stages");
+  extern __shared__ cplx sm[];
+  cplx* A = sm;
+  cplx* B = sm + 5 * N;
+  cplx* tw = B + 5 * NB;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  const int64_t n3 = g.n3;
+  const int t = threadIdx.x;
+  const int64_t L = (int64_t)g.xoff * N + blockIdx.x;   // grid line x * N + y
+  const int64_t e = L * N + t;
+  if (t < N) {
+    double f[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) f[c] = src[c * n3 + e];
+    if (MODE >= 2) {
+      double alpha = 0.0;
+      if (MODE == 3) alpha = rr_alpha / *pq;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const double r = rvec[c * n3 + e];
+        if (MODE == 3) xvec[c * n3 + e] += alpha * f[c];
+        f[c] = r + beta * f[c];
+        src[c * n3 + e] = f[c];
+      }
+    }
+    double v[10];
+    if (MODE >= 1) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        double ta[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) ta[j] = __dmul_rn(K4[(int64_t)(9 * i + j) * n3 + e], f[j]);
+        // ddot42n's summation tree (G_K_dF.f:258-264)
+        v[i] = ta[0] + (((ta[1] + ta[5]) + (ta[3] + ta[7])) + ((ta[2] + ta[6]) + (ta[4] + ta[8])));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) v[c] = f[c];
+    }
+    v[9] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) A[t * 5 + j] = make_double2(v[2 * j], v[2 * j + 1]);
+  }
+  __syncthreads();
+  auto to_B = [&](int c, int p, cplx val) { B[c * NB + fft_natural<N>(p)] = val; };
+  for (int task = threadIdx.x; task < 5 * (N / P::R1); task += blockDim.x) {
+    const int j = task / 5, c = task - j * 5;
+    if (P::R2 == 1) fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return A[i * 5 + c]; }, [&](int i, cplx val) { to_B(c, i, val); });
+    else fft_stage_dif<N, P::R1, -1, 1>(j, tw, [&](int i) { return A[i * 5 + c]; }, [&](int i, cplx val) { A[i * 5 + c] = val; });
+  }
+  __syncthreads();
+  if constexpr (P::R2 > 1) {
+    for (int task = threadIdx.x; task < 5 * (N / P::R2); task += blockDim.x) {
+      const int j = task / 5, c = task - j * 5;
+      fft_stage_dif<N1, P::R2, -1, N / N1>(j, tw, [&](int i) { return A[i * 5 + c]; }, [&](int i, cplx val) { to_B(c, i, val); });
+    }
+    __syncthreads();
+  }
+  const int64_t nxN = (int64_t)g.nx * N;
+  for (int idx = threadIdx.x; idx < 9 * KB; idx += blockDim.x) {
+    const int c = idx / KB, k = idx - c * KB;
+    const cplx* row = B + (c >> 1) * NB;
+    const cplx Zk = row[k];
+    const cplx Zm = c_conj(row[(k == 0) ? 0 : N - k]);
+    cplx X;
+    if ((c & 1) == 0) { const cplx E = c_add(Zk, Zm); X = make_double2(0.5 * E.x, 0.5 * E.y); }
+    else { const cplx D = c_sub(Zk, Zm); X = make_double2(0.5 * D.y, -0.5 * D.x); }       // D / (2 i)
+    spec[((int64_t)c * nxN + L) * KB + k] = X;
+  }
+}
+
+template <int N, bool DOT>
+__global__ void __launch_bounds__(OddZ<N>::ZT, OddZ<N>::MINB) k_iz_odd(Pow2Args g, const cplx* __restrict__ spec, double* __restrict__ dst, double scale,
+                                              const double* __restrict__ pvec, double* __restrict__ partials) {
+  typedef FftPlan<N> P;
+  constexpr int KB = OddZ<N>::KB, NB = OddZ<N>::NB, N1 = N / P::R1;
+  extern __shared__ cplx sm[];
+  cplx* A = sm;                 // also the staging area S[c * KB + k] of the nine half-spectrum rows (9 KB <= 5 N)
+  cplx* B = sm + 5 * N;
+  cplx* tw = B + 5 * NB;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  const int64_t nxN = (int64_t)g.nx * N;
+  const int64_t L = blockIdx.x;
+  for (int idx = threadIdx.x; idx < 9 * KB; idx += blockDim.x) {
+    const int c = idx / KB, k = idx - c * KB;
+    A[idx] = spec[((int64_t)c * nxN + L) * KB + k];
+  }
+  __syncthreads();
+  // Z_j[k] = C_{2j}[k] + i C_{2j+1}[k],  Z_j[N-k] = conj C_{2j}[k] + i conj C_{2j+1}[k];  C[0] is real
+  for (int idx = threadIdx.x; idx < 5 * KB; idx += blockDim.x) {
+    const int j = idx / KB, k = idx - j * KB;
+    const cplx Xa = A[(2 * j) * KB + k];
+    const cplx Xb = (j < 4) ? A[(2 * j + 1) * KB + k] : make_double2(0.0, 0.0);
+    if (k == 0) B[j * NB] = make_double2(Xa.x, Xb.x);
+    else {
+      B[j * NB + k] = make_double2(Xa.x - Xb.y, Xa.y + Xb.x);
+      B[j * NB + N - k] = make_double2(Xa.x + Xb.y, Xb.x - Xa.y);
+    }
+  }
+  __syncthreads();
+  auto from_B = [&](int c, int p) { return B[c * NB + fft_natural<N>(p)]; };
+  if constexpr (P::R2 > 1) {
+    for (int task = threadIdx.x; task < 5 * (N / P::R2); task += blockDim.x) {
+      const int j = task / 5, c = task - j * 5;
+      fft_stage_dit_inv<N1, P::R2, N / N1>(j, tw, [&](int i) { return from_B(c, i); }, [&](int i, cplx val) { A[i * 5 + c] = val; });
+    }
+    __syncthreads();
+  }
+  for (int task = threadIdx.x; task < 5 * (N / P::R1); task += blockDim.x) {
+    const int j = task / 5, c = task - j * 5;
+    if (P::R2 == 1) fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return from_B(c, i); }, [&](int i, cplx val) { A[i * 5 + c] = val; });
+    else fft_stage_dit_inv<N, P::R1, 1>(j, tw, [&](int i) { return A[i * 5 + c]; }, [&](int i, cplx val) { A[i * 5 + c] = val; });
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int64_t e = L * N + t;
+  double acc = 0.0;
+  if (t < N) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const cplx z = A[t * 5 + j];
+      const double o0 = z.x * scale;
+      dst[(2 * j) * g.n3 + e] = o0;
+      if (DOT) acc += o0 * pvec[(2 * j) * g.n3 + e];
+      if (j < 4) {
+        const double o1 = z.y * scale;
+        dst[(2 * j + 1) * g.n3 + e] = o1;
+        if (DOT) acc += o1 * pvec[(2 * j + 1) * g.n3 + e];
+      }
+    }
+  }
+  if (DOT) {
+    __shared__ double red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int i = 0; i < OddZ<N>::ZT / 32; ++i) sum += red[i];
+      partials[blockIdx.x] = sum;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // y passes.  Shared memory s[i * TZ + l] (+ twiddles), tile of TZ consecutive kz per CTA.
 //
 // The Green operator of a tensor row r is rank one (see k_fx): the x pass needs only
@@ -466,18 +648,15 @@ __device__ __forceinline__ void y_line_fft(cplx* s, const cplx* tw, Ld ld, Fin f
 //   ls odd : components 3r+1 and 3r+2 -> slot 3r+1 = xi_y(ky) F(t_r1) + xi_z(kz) F(t_r2)
 // in place in spec (x-slab layout), or SCATTER: to the y-slab layout [slot][x global][y local][kz]
 // of the rank that owns y (forward slab transpose fused into the store).
+// One tile (bx, by) of the forward y pass: bx = line slot * nxc + x plane of the launch's chunk, by = kz tile.
 template <int N, bool SCATTER>
-__global__ void __launch_bounds__(512) k_fyf(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
+__device__ __forceinline__ void fyf_tile(const Pow2Args& g, cplx* __restrict__ spec, const PeerPtrs& peers, cplx* s, const cplx* tw,
+                                         int bx, int by) {
   typedef FftPlan<N> P;
-  constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZY;
+  constexpr int H = KzBins<N>::value, TZ = Pow2Cfg<N>::TZY;
   constexpr int RL = (P::R2 == 1) ? P::R1 : ((P::R3 == 1) ? P::R2 : P::R3);
-  extern __shared__ cplx sm[];
-  cplx* s = sm;
-  cplx* tw = sm + N * TZ;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
-  __syncthreads();
-  const int ls = blockIdx.x / g.nxc, xl = g.xoff + (blockIdx.x - ls * g.nxc);
-  const int row = ls >> 1, kz0 = blockIdx.y * TZ;
+  const int ls = bx / g.nxc, xl = g.xoff + (bx - ls * g.nxc);
+  const int row = ls >> 1, kz0 = by * TZ;
   const int slot = 3 * row + (ls & 1);
   const int ny = g.NY;                                   // SCATTER: y planes per rank
   const int64_t plane = (int64_t)N * H;                  // one (component, x) plane of the x-slab layout
@@ -499,7 +678,7 @@ __global__ void __launch_bounds__(512) k_fyf(Pow2Args g, cplx* __restrict__ spec
     cplx keep[2][RL];
     y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
                       [&](int it, int cnt, int y, int, cplx v) {
-                        const double fy = (double)(y < H ? y : y - N);
+                        const double fy = sfreq<N>(y);
                         keep[it][cnt] = make_double2(fy * v.x, fy * v.y);
                       });
     __syncthreads();                                     // the tile buffer is reused for component 3r+2
@@ -512,12 +691,41 @@ __global__ void __launch_bounds__(512) k_fyf(Pow2Args g, cplx* __restrict__ spec
   }
 }
 
+template <int N, bool SCATTER>
+__global__ void __launch_bounds__(YXBound<N>::value) k_fyf(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
+  constexpr int TZ = Pow2Cfg<N>::TZY;
+  extern __shared__ cplx sm[];
+  cplx* s = sm;
+  cplx* tw = sm + N * TZ;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  __syncthreads();
+  fyf_tile<N, SCATTER>(g, spec, peers, s, tw, blockIdx.x, blockIdx.y);
+}
+// Persistent form for the multi-GPU pipeline: gridDim.x CTAs walk the ntx x nty tiles of a chunk.  This pass is
+// NVLink-bound; run with a grid that covers only part of the SMs (CPFFT_FYF_CTAS) it leaves the rest of the
+// machine to the HBM-bound forward z pass of the next chunk instead of evicting it (launched as an ordinary grid
+// on the high-priority stream it took every CTA slot and the z pass stalled for as long as it ran).
+template <int N, bool SCATTER>
+__global__ void __launch_bounds__(YXBound<N>::value) k_fyf_persist(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers, int ntx, int nty) {
+  constexpr int TZ = Pow2Cfg<N>::TZY;
+  extern __shared__ cplx sm[];
+  cplx* s = sm;
+  cplx* tw = sm + N * TZ;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
+  __syncthreads();
+  const int total = ntx * nty;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    fyf_tile<N, SCATTER>(g, spec, peers, s, tw, tile % ntx, tile / ntx);
+    __syncthreads();                                     // the tile buffer is reused
+  }
+}
+
 // inverse y pass, grid = (9 * nx, NZ / TZ), out of place: component c = 3r + m reads line slot
 // 3r (m = 0) or 3r+1 scaled by xi_y(ky) (m = 1) / xi_z(kz) (m = 2) and writes component c of
 // `dst` (x-slab layout, all 9 components again).
 template <int N>
-__global__ void __launch_bounds__(512) k_fyi(Pow2Args g, const cplx* __restrict__ src, cplx* __restrict__ dst) {
-  constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZY;
+__global__ void __launch_bounds__(YXBound<N>::value) k_fyi(Pow2Args g, const cplx* __restrict__ src, cplx* __restrict__ dst) {
+  constexpr int H = KzBins<N>::value, TZ = Pow2Cfg<N>::TZY;
   extern __shared__ cplx sm[];
   cplx* s = sm;
   cplx* tw = sm + N * TZ;
@@ -532,7 +740,7 @@ __global__ void __launch_bounds__(512) k_fyi(Pow2Args g, const cplx* __restrict_
   y_line_fft<N, +1>(s, tw, [&](int i, int l) {
                       const cplx v = Gin[(int64_t)i * H + l];
                       if (m == 0) return v;
-                      const double f = (m == 1) ? (double)(i < H ? i : i - N) : (double)(kz0 + l);
+                      const double f = (m == 1) ? sfreq<N>(i) : (double)(kz0 + l);
                       return make_double2(f * v.x, f * v.y);
                     },
                     [&](int, int, int y, int l, cplx v) { Gout[(int64_t)y * H + l] = v; });
@@ -551,9 +759,9 @@ __global__ void __launch_bounds__(512) k_fyi(Pow2Args g, const cplx* __restrict_
 // transforms.  SCATTER: the inverse-transformed lines (natural x order) go back to the x-slab
 // layout [c][x local][y global][kz] of the rank that owns x (backward transpose fused in).
 template <int N, bool SCATTER>
-__global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
+__global__ void __launch_bounds__(YXBound<N>::value) k_fx(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
   typedef FftPlan<N> P;
-  constexpr int H = N / 2, TZ = Pow2Cfg<N>::TZX;
+  constexpr int H = KzBins<N>::value, TZ = Pow2Cfg<N>::TZX;
   constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
   extern __shared__ cplx sm[];
   cplx* s = sm;
@@ -565,7 +773,7 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec,
   const int64_t cs = (int64_t)N * xs;                         // stride between components
   cplx* G = spec + ((int64_t)(3 * row) * N * g.NY + y) * H + kz0;   // + cl * cs + x * xs + l
   const int ky = y + g.y0;
-  const double fy = (double)(ky < H ? ky : ky - N);
+  const double fy = sfreq<N>(ky);
   // ---- forward: stage 1 from global memory ----
   for (int task = threadIdx.x; task < 2 * TZ * (N / P::R1); task += blockDim.x) {
     const int l = task % TZ, r = task / TZ;
@@ -598,9 +806,10 @@ __global__ void __launch_bounds__(512) k_fx(Pow2Args g, cplx* __restrict__ spec,
   for (int idx = threadIdx.x; idx < N * TZ; idx += blockDim.x) {
     const int l = idx % TZ, p = idx / TZ;
     const int kx = fft_natural<N>(p);
-    const double fx = (double)(kx < H ? kx : kx - N), fz = (double)(kz0 + l);
+    const double fx = sfreq<N>(kx), fz = (double)(kz0 + l);
     const double qq = fx * fx + fy * fy + fz * fz;
-    const bool zero = (kx == H) || (ky == H) || (fabs(qq) <= 1e-10);
+    // even N: Ghat = 0 on the kx / ky Nyquist planes (the kz one is not stored); odd N has none
+    const bool zero = ((N & 1) == 0 && (2 * kx == N || 2 * ky == N)) || (fabs(qq) <= 1e-10);
     cplx* a = s + p * TZ + l;
     const cplx A = a[0], B = a[N * TZ];
     double sr = 0.0, si = 0.0;
@@ -662,13 +871,15 @@ struct CgFuse { const double* r; double beta; bool update_p; int nparts; double*
 
 template <int N>
 static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, double scale_out, const CgFuse* cg) {
-  constexpr int H = N / 2, TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX, ZT = Pow2Cfg<N>::ZT;
+  constexpr bool ODD = (N & 1) != 0;
+  constexpr int H = KzBins<N>::value, TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX, ZT = ODD ? OddZ<N>::ZT : Pow2Cfg<N>::ZT;
+  static_assert(H % TZY == 0 && H % TZX == 0, "kz tiles must divide the stored bins");
   typedef FftPlan<N> P;
   const int nx = h->nxloc, world = h->cfg.world;
   Pow2Args g;
   g.nx = nx; g.x0 = h->x0; g.xoff = 0; g.nxc = nx; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
   PeerPtrs none = {};
-  const size_t sm_z = ZSmem<N>::bytes;
+  const size_t sm_z = ODD ? OddZ<N>::bytes : ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
   const unsigned zgrid = (unsigned)(nx * N);
   // forward z pass of the local x planes [xoff, xoff + nxc)
@@ -677,10 +888,17 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
     gz.xoff = xoff; gz.nxc = nxc;
     const unsigned zg = (unsigned)(nxc * N);
     const int tkz = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
-    if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
-    else if (cg && cg->update_p) k_fz<N, 2><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
-    else if (flgK) k_fz<N, 1><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-    else k_fz<N, 0><<<zg, ZT, sm_z, h->stream>>>(gz, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    if constexpr (ODD) {
+      if (cg && cg->update_p && cg->x) k_fz_odd<N, 3><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
+      else if (cg && cg->update_p) k_fz_odd<N, 2><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
+      else if (flgK) k_fz_odd<N, 1><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+      else k_fz_odd<N, 0><<<zg, ZT, sm_z, h->stream>>>(gz, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    } else {
+      if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
+      else if (cg && cg->update_p) k_fz<N, 2><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
+      else if (flgK) k_fz<N, 1><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+      else k_fz<N, 0><<<zg, ZT, sm_z, h->stream>>>(gz, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    }
     cpf_prof_end(h, tkz);
   };
   // multi-GPU with peer stores: the forward y pass of a chunk of x planes (NVLink-bound: its last stage stores
@@ -691,8 +909,9 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   if (nchunk == 1) launch_fz(0, nx);
   constexpr int Rm12 = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
   constexpr int RminY = P::R3 > 1 ? (Rm12 < P::R3 ? Rm12 : P::R3) : Rm12;
-  constexpr int thr_y = (TZY * (N / RminY)) > 512 ? 512 : (TZY * (N / RminY) < 32 ? 32 : TZY * (N / RminY));
-  constexpr int thr_x = (2 * TZX * (N / RminY)) > 512 ? 512 : (2 * TZX * (N / RminY) < 32 ? 32 : 2 * TZX * (N / RminY));
+  constexpr int ty0 = (TZY * (N / RminY) + 31) / 32 * 32, tx0 = (2 * TZX * (N / RminY) + 31) / 32 * 32;
+  constexpr int thr_y = ty0 > YXBound<N>::value ? YXBound<N>::value : ty0;
+  constexpr int thr_x = tx0 > YXBound<N>::value ? YXBound<N>::value : tx0;
   const dim3 gy(9 * nx, H / TZY);
   const dim3 gyf(6 * nx, H / TZY);
   if (world == 1) {
@@ -726,7 +945,8 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
           CPF_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_chunk[c], 0));
           gs.xoff = c * nxc; gs.nxc = nxc;
           tk = cpf_prof_begin_on(h, CPF_K_FFT_Y, h->stream2);
-          k_fyf<N, true><<<gyc, thr_y, sm_y, h->stream2>>>(gs, h->spec_a, pb);
+          const int tiles = (int)(gyc.x * gyc.y);
+          k_fyf_persist<N, true><<<std::min(tiles, h->fyf_ctas), thr_y, sm_y, h->stream2>>>(gs, h->spec_a, pb, (int)gyc.x, (int)gyc.y);
           cpf_prof_end(h, tk);
         }
         CPF_CUDA(cudaEventRecord(h->ev_join, h->stream2));
@@ -756,6 +976,10 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   cpf_prof_end(h, tk);
   const double scale = scale_out / ((double)N * (double)N * (double)N);
   tk = cpf_prof_begin(h, CPF_K_INV_Z);
+  if constexpr (ODD) {
+    if (cg) { k_iz_odd<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
+    else k_iz_odd<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
+  } else {
   if (h->iz_pipe) {
     const int lpc = h->iz_lpc;
     const unsigned pgrid = (zgrid + lpc - 1) / lpc;
@@ -764,6 +988,7 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
     else k_iz_pipe<N, false><<<pgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr, (int64_t)zgrid, lpc);
   } else if (cg) { k_iz<N, true><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, src, h->d_partials); const_cast<CgFuse*>(cg)->nparts = (int)zgrid; }
   else k_iz<N, false><<<zgrid, ZT, sm_z, h->stream>>>(g, h->spec_c, dst, scale, nullptr, nullptr);
+  }
   cpf_prof_end(h, tk);
   h->launches += 5;
   CPF_CUDA(cudaGetLastError());
@@ -774,20 +999,31 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
 template <int N>
 static int init_pow2(cpfft_handle* h) {
   constexpr int TZY = Pow2Cfg<N>::TZY, TZX = Pow2Cfg<N>::TZX;
-  const size_t sm_z = ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
 #define CPF_SMEM_ATTR(kern, bytes) \
   CPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));
-  CPF_SMEM_ATTR((k_fz<N, 0>), sm_z);
-  CPF_SMEM_ATTR((k_fz<N, 1>), sm_z);
-  CPF_SMEM_ATTR((k_fz<N, 2>), sm_z);
-  CPF_SMEM_ATTR((k_fz<N, 3>), sm_z);
-  CPF_SMEM_ATTR((k_iz<N, true>), sm_z);
-  CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
-  CPF_SMEM_ATTR((k_iz_pipe<N, true>), sm_z);
-  CPF_SMEM_ATTR((k_iz_pipe<N, false>), sm_z);
+  if constexpr ((N & 1) != 0) {
+    const size_t sm_z = OddZ<N>::bytes;
+    CPF_SMEM_ATTR((k_fz_odd<N, 0>), sm_z);
+    CPF_SMEM_ATTR((k_fz_odd<N, 1>), sm_z);
+    CPF_SMEM_ATTR((k_fz_odd<N, 2>), sm_z);
+    CPF_SMEM_ATTR((k_fz_odd<N, 3>), sm_z);
+    CPF_SMEM_ATTR((k_iz_odd<N, true>), sm_z);
+    CPF_SMEM_ATTR((k_iz_odd<N, false>), sm_z);
+  } else {
+    const size_t sm_z = ZSmem<N>::bytes;
+    CPF_SMEM_ATTR((k_fz<N, 0>), sm_z);
+    CPF_SMEM_ATTR((k_fz<N, 1>), sm_z);
+    CPF_SMEM_ATTR((k_fz<N, 2>), sm_z);
+    CPF_SMEM_ATTR((k_fz<N, 3>), sm_z);
+    CPF_SMEM_ATTR((k_iz<N, true>), sm_z);
+    CPF_SMEM_ATTR((k_iz<N, false>), sm_z);
+    CPF_SMEM_ATTR((k_iz_pipe<N, true>), sm_z);
+    CPF_SMEM_ATTR((k_iz_pipe<N, false>), sm_z);
+  }
   CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
   CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
+  CPF_SMEM_ATTR((k_fyf_persist<N, true>), sm_y);
   CPF_SMEM_ATTR((k_fyi<N>), sm_y);
   CPF_SMEM_ATTR((k_fx<N, false>), sm_x);
   CPF_SMEM_ATTR((k_fx<N, true>), sm_x);
@@ -806,12 +1042,16 @@ int cpf_pow2_init(cpfft_handle* h) {
     case 200: return init_pow2<200>(h);
     case 320: return init_pow2<320>(h);
     case 400: return init_pow2<400>(h);
+    case 15: return init_pow2<15>(h);
+    case 51: return init_pow2<51>(h);
+    case 255: return init_pow2<255>(h);
   }
   return CPFFT_ERR_USAGE;
 }
 
 bool cpf_pow2_supported(int N) {
-  return N == 16 || N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 320 || N == 400 || N == 40 || N == 80 || N == 200;
+  return N == 16 || N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 320 || N == 400 || N == 40 || N == 80 || N == 200 ||
+         N == 15 || N == 51 || N == 255;       // odd: the reference-faithful grids
 }
 
 template <int N> struct Tag {};
@@ -828,6 +1068,9 @@ template <class F> static int dispatch_pow2(cpfft_handle* h, F f) {
     case 200: return f(Tag<200>());
     case 320: return f(Tag<320>());
     case 400: return f(Tag<400>());
+    case 15: return f(Tag<15>());
+    case 51: return f(Tag<51>());
+    case 255: return f(Tag<255>());
   }
   cpf_set_error(h, "power-of-two spectral path called with an unsupported N");
   return CPFFT_ERR_USAGE;

@@ -127,14 +127,48 @@ template <int N> static void test_real_pack() {
   }
 }
 
+// two real lines of ODD length N through one N-point complex transform (k_fz_odd / k_iz_odd): z = a + i b,
+//   A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / (2 i),  bins k = 0 .. (N-1)/2; and back
+template <int N> static void test_two_real_lines() {
+  constexpr int KB = (N + 1) / 2;
+  auto tw = twiddles(N);
+  std::vector<cplx> xa(N), xb(N), z(N);
+  for (int n = 0; n < N; ++n) {
+    xa[n] = make_double2(drand48() - 0.5, 0.0); xb[n] = make_double2(drand48() - 0.5, 0.0);
+    z[n] = make_double2(xa[n].x, xb[n].x);
+  }
+  auto XA = naive(xa, -1), XB = naive(xb, -1);
+  run_dif<N, -1>(z, tw, 1);
+  std::vector<cplx> A(KB), B(KB);
+  for (int k = 0; k < KB; ++k) {
+    const cplx Zk = z[fft_position<N>(k)], Zm = c_conj(z[fft_position<N>((N - k) % N)]);
+    const cplx E = c_add(Zk, Zm), D = c_sub(Zk, Zm);
+    A[k] = make_double2(0.5 * E.x, 0.5 * E.y);
+    B[k] = make_double2(0.5 * D.y, -0.5 * D.x);              // D / (2 i)
+    chk(A[k], XA[k], N); chk(B[k], XB[k], N);
+  }
+  std::vector<cplx> zz(N);
+  for (int k = 0; k < KB; ++k) {                              // Z[k] = A[k] + i B[k], Z[N-k] = conj A[k] + i conj B[k]
+    zz[fft_position<N>(k)] = make_double2(A[k].x - B[k].y, A[k].y + B[k].x);
+    if (k > 0) zz[fft_position<N>(N - k)] = make_double2(A[k].x + B[k].y, B[k].x - A[k].y);
+  }
+  run_dit_inv<N>(zz, tw);
+  for (int n = 0; n < N; ++n) {
+    chk(make_double2(zz[n].x / N, 0), make_double2(xa[n].x, 0), 1.0);
+    chk(make_double2(zz[n].y / N, 0), make_double2(xb[n].x, 0), 1.0);
+  }
+}
+
 int main() {
   srand48(12345);
-  test_dft<2>(); test_dft<4>(); test_dft<5>(); test_dft<8>(); test_dft<10>(); test_dft<16>(); test_dft<20>();
+  test_dft<2>(); test_dft<4>(); test_dft<5>(); test_dft<8>(); test_dft<10>(); test_dft<16>(); test_dft<20>(); test_dft<3>(); test_dft<15>(); test_dft<17>();
   printf("butterflies maxerr %.3e\n", maxerr);
-  test_line<8>(); test_line<16>(); test_line<32>(); test_line<64>(); test_line<128>(); test_line<256>(); test_line<512>(); test_line<20>(); test_line<40>(); test_line<80>(); test_line<100>(); test_line<160>(); test_line<200>(); test_line<320>(); test_line<400>();
+  test_line<8>(); test_line<16>(); test_line<32>(); test_line<64>(); test_line<128>(); test_line<256>(); test_line<512>(); test_line<20>(); test_line<40>(); test_line<80>(); test_line<100>(); test_line<160>(); test_line<200>(); test_line<320>(); test_line<400>(); test_line<15>(); test_line<51>(); test_line<85>(); test_line<255>();
   printf("lines maxerr %.3e\n", maxerr);
   test_real_pack<16>(); test_real_pack<32>(); test_real_pack<64>(); test_real_pack<128>(); test_real_pack<256>(); test_real_pack<512>(); test_real_pack<40>(); test_real_pack<80>(); test_real_pack<200>(); test_real_pack<320>(); test_real_pack<400>();
   printf("real pack maxerr %.3e\n", maxerr);
+  test_two_real_lines<15>(); test_two_real_lines<51>(); test_two_real_lines<85>(); test_two_real_lines<255>();
+  printf("two real lines maxerr %.3e\n", maxerr);
   if (!(maxerr < 1e-13)) { printf("FAIL\n"); return 1; }
   printf("OK\n");
   return 0;

@@ -32,11 +32,12 @@ def _hetero_state(p, s, o, amp=0.02, seed=3):
     return rng
 
 
-@pytest.mark.parametrize("N", [9, 12, 15, 16, 32, 40, 64, 80])
+@pytest.mark.parametrize("N", [9, 12, 15, 16, 32, 40, 51, 64, 80])
 @pytest.mark.parametrize("flgK", [0, 1])
 def test_G_K_dF_matches_oracle(libs, N, flgK):
     """odd N = reference-faithful; even N = documented Nyquist-zero convention; 16/32/64 (radix
-    2/4/8/16) and 40/80 (radix 5) run through the fast path, 9/12/15 through the generic one."""
+    2/4/8/16), 40/80 (radix 5) and the odd 15/51 (radix 3/5/17, two real lines per complex transform
+    in the z passes: the plan family of 255^3) run through the fast path, 9/12 through the generic one."""
     Solver, Oracle = libs
     p = _toy_problem(N)
     s, o = Solver(p), Oracle(p, threads=8)
@@ -60,10 +61,11 @@ def test_G_K_dF_128_matches_oracle(libs):
     assert relerr(s.download("B"), o.G_K_dF(x, 1)) <= 1e-13
 
 
-@pytest.mark.parametrize("N", [32, 200])
+@pytest.mark.parametrize("N", [32, 200, 15, 51, 255])
 def test_generic_and_fast_path_agree(libs, N):
-    """the same even grid through both implementations (CPFFT_GENERIC_FFT forces the generic one);
-    200 = 5 x 5 x 8 is the three-stage radix-5 plan family of the 400^3 weak-scaling grid"""
+    """the same grid through both implementations (CPFFT_GENERIC_FFT forces the generic one);
+    200 = 5 x 5 x 8 is the three-stage radix-5 plan family of the 400^3 weak-scaling grid; 15, 51 and
+    255 = 17 x 15 are the odd grids, on which the operator is the reference's own"""
     Solver, _ = libs
     p = _toy_problem(N)
     rng = np.random.default_rng(1)
@@ -84,7 +86,7 @@ def test_generic_and_fast_path_agree(libs, N):
     assert relerr(out[0], out[1]) <= 1e-13
 
 
-@pytest.mark.parametrize("N", [200, 256, 320])
+@pytest.mark.parametrize("N", [200, 255, 256, 320])
 def test_projection_identities_at_benchmark_size(libs, N):
     """Ghat:grad(u) = grad(u), Ghat:const = 0, idempotence and self-adjointness at 256^3, where
     the oracle is too slow: the operator is an orthogonal projection at any size."""
