@@ -8,7 +8,6 @@
 #include "material_types.h"
 
 #define CPF_MAX_WORLD 8   // one NVSwitch domain
-#define CPF_MAX_CHUNKS 16
 
 #define CPF_CUDA(call)                                                                    \
   do {                                                                                    \
@@ -26,7 +25,7 @@ enum CpfKernelClass {
   CPF_K_UPDATE_MM10_EL,      // mm10 sweeps with iter == 0 (elastic predictor, rstgp1.f:870-877): no local Newton solve
   CPF_K_NUM
 };
-struct CpfProfEvt { cudaEvent_t a, b; int cls; cudaStream_t st; };
+struct CpfProfEvt { cudaEvent_t a, b; int cls; };
 
 struct cpfft_handle {
   cpfft_config cfg;
@@ -44,12 +43,6 @@ struct cpfft_handle {
   int64_t n3;                // local voxels
   int H;                     // history comps
   cudaStream_t stream;
-  // multi-GPU pipelining of the forward slab transpose: the NVLink-bound forward y pass of x-plane chunk c runs on
-  // `stream2` (higher priority) under the HBM-bound forward z pass of chunk c + 1 on `stream`
-  cudaStream_t stream2;
-  cudaEvent_t ev_chunk[CPF_MAX_CHUNKS]; cudaEvent_t ev_join;
-  int fwd_chunks;            // x-plane chunks of that pipeline (CPFFT_FWD_CHUNKS, default 4; 1 = no pipelining)
-  int fyf_ctas;              // CTAs of the persistent forward y pass of a chunk (CPFFT_FYF_CTAS)
   std::string err;
   std::string log;           // the reference's step / iteration lines of the last cpfft_FFT_nr3 call
   int64_t launches;
@@ -101,7 +94,6 @@ void cpf_set_error(cpfft_handle* h, const std::string& s);
 // CUDA-event bracket around one kernel launch (no-ops unless profiling is enabled)
 int cpf_prof_begin(cpfft_handle* h, int cls);
 void cpf_prof_end(cpfft_handle* h, int token);
-int cpf_prof_begin_on(cpfft_handle* h, int cls, cudaStream_t st);   // the same on another stream of the handle
 
 // material.cu
 int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const double* angles,

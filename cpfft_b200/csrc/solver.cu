@@ -14,25 +14,23 @@ static double wall_s() {
 }
 void cpf_set_error(cpfft_handle* h, const std::string& s) { if (h) h->err = s; }
 
-int cpf_prof_begin_on(cpfft_handle* h, int cls, cudaStream_t st) {
+int cpf_prof_begin(cpfft_handle* h, int cls) {
   if (!h->prof_on) return -1;
   CpfProfEvt e;
   if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); }
   else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
-  e.cls = cls; e.st = st;
-  cudaEventRecord(e.a, st);
+  e.cls = cls;
+  cudaEventRecord(e.a, h->stream);
   h->prof_live.push_back(e);
   return (int)h->prof_live.size() - 1;
 }
-int cpf_prof_begin(cpfft_handle* h, int cls) { return cpf_prof_begin_on(h, cls, h->stream); }
 void cpf_prof_end(cpfft_handle* h, int token) {
   if (token < 0) return;
-  cudaEventRecord(h->prof_live[token].b, h->prof_live[token].st);
+  cudaEventRecord(h->prof_live[token].b, h->stream);
 }
 static void prof_collect(cpfft_handle* h) {
   if (h->prof_live.empty()) return;
   cudaStreamSynchronize(h->stream);
-  if (h->stream2) cudaStreamSynchronize(h->stream2);
   for (auto& e : h->prof_live) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { h->prof_ms[e.cls] += ms; h->prof_cnt[e.cls]++; }
@@ -344,9 +342,7 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   h->nccl_comm = nullptr; h->nccl_lib = nullptr; h->xchg_send = h->xchg_recv = nullptr;
   h->p2p = false;
   for (int r = 0; r < CPF_MAX_WORLD; ++r) h->peer_spec_a[r] = h->peer_spec_b[r] = nullptr;
-  h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr; h->stream2 = nullptr;
-  for (int c = 0; c < CPF_MAX_CHUNKS; ++c) h->ev_chunk[c] = nullptr;
-  h->ev_join = nullptr; h->fwd_chunks = 1;
+  h->H = 0; h->ngrains = 0; h->has_mm01 = h->has_mm10 = false; h->stream = nullptr;
   *out = h;  // returned even on failure so that cpfft_last_error works; caller destroys it
   if (cfg->N < 2) { cpf_set_error(h, "N must be >= 2"); return CPFFT_ERR_USAGE; }
   if (h->cfg.world > 1 && (cfg->N % h->cfg.world) != 0) {
@@ -356,21 +352,7 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   cudaDeviceProp prop;
   CPF_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   g_num_sms = prop.multiProcessorCount;
-  {
-    int lo = 0, hi = 0;     // numerically lower = higher priority
-    CPF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CPF_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, lo));
-    CPF_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi));
-    for (int c = 0; c < CPF_MAX_CHUNKS; ++c) CPF_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
-    CPF_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    const char* fc = getenv("CPFFT_FWD_CHUNKS");
-    h->fwd_chunks = fc ? atoi(fc) : 4;
-    if (h->fwd_chunks < 1) h->fwd_chunks = 1;
-    if (h->fwd_chunks > CPF_MAX_CHUNKS) h->fwd_chunks = CPF_MAX_CHUNKS;
-    const char* fy = getenv("CPFFT_FYF_CTAS");
-    h->fyf_ctas = fy ? atoi(fy) : g_num_sms / 2;
-    if (h->fyf_ctas < 1) h->fyf_ctas = 1;
-  }
+  CPF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->nxloc = cfg->N / h->cfg.world; h->x0 = h->cfg.rank * h->nxloc;
   h->n3 = (int64_t)h->nxloc * cfg->N * cfg->N;
   const int nc[CPFFT_NUM_FIELDS] = {9, 9, 9, 9, 9, 9, 9, 9, 9, 81, 9, 9, 6, 6, 9, 0, 0, 36};
@@ -424,9 +406,6 @@ void cpfft_destroy(cpfft_handle* h) {
       }
   cpf_spectral_free(h);
   if (h->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(h->nccl_comm);
-  for (int c = 0; c < CPF_MAX_CHUNKS; ++c) if (h->ev_chunk[c]) cudaEventDestroy(h->ev_chunk[c]);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

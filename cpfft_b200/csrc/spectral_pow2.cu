@@ -19,7 +19,6 @@
 
 struct Pow2Args {
   int nx, x0;    // local x planes (z / y passes) and their global offset
-  int xoff, nxc; // z / forward y pass: this launch covers local x planes [xoff, xoff + nxc) (multi-GPU pipelining)
   int NY, y0;    // x pass: local y extent and its global offset (slab-transposed layout)
   int64_t n3;    // local voxels
   const cplx* tw;  // exp(-2 pi i k / N), k < N
@@ -60,6 +59,11 @@ template <> struct Pow2Cfg<80> { static constexpr int H = 40, TZY = 8, TZX = 8, 
 template <> struct Pow2Cfg<200> { static constexpr int H = 100, TZY = 10, TZX = 5, ZT = 128; };
 template <> struct Pow2Cfg<320> { static constexpr int H = 160, TZY = 16, TZX = 8, ZT = 160; };
 template <> struct Pow2Cfg<400> { static constexpr int H = 200, TZY = 8, TZX = 8, ZT = 224; };
+// kz tile of the forward y pass when its last stage stores over NVLink (world > 1): runs of TZY x 16 B.  At 4 and 8
+// GPUs the 128-byte runs of the HBM-tuned tile reached 55-65 % of the link rate (round 1: 0.75-0.8 ms of link time
+// took 1.3-1.4 ms); 256-byte runs, one CTA of 100-130 KB per SM -- this pass waits on the link, not on occupancy.
+template <int N> struct ScatterTile { static constexpr int TZY = Pow2Cfg<N>::TZY; };
+template <> struct ScatterTile<512> { static constexpr int TZY = 16; };
 // CTA size the y / x pass kernels are compiled for: 255 runs 272 -> 288 threads, which leaves its radix-17 butterflies
 // 224 registers instead of 128
 template <int N> struct YXBound { static constexpr int value = (N == 255) ? 288 : 512; };
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_fz(Pow2Args g
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   const int64_t n3 = g.n3;
   const int t = threadIdx.x;
-  const int64_t L = (int64_t)g.xoff * N + blockIdx.x;   // grid line x * N + y
+  const int64_t L = blockIdx.x;                         // grid line x * N + y
   const int64_t e0 = L * N + 2 * t;
   if (t < H) {
     double2 f[9];
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(OddZ<N>::ZT, OddZ<N>::MINB) k_fz_odd(Pow2Args 
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
   const int64_t n3 = g.n3;
   const int t = threadIdx.x;
-  const int64_t L = (int64_t)g.xoff * N + blockIdx.x;   // grid line x * N + y
+  const int64_t L = blockIdx.x;                         // grid line x * N + y
   const int64_t e = L * N + t;
   if (t < N) {
     double f[9];
@@ -597,10 +601,9 @@ __global__ void __launch_bounds__(OddZ<N>::ZT, OddZ<N>::MINB) k_iz_odd(Pow2Args 
 
 // all stages of one y line tile; `ld(i, l)` supplies the input, `fin(it, cnt, i, l, v)` receives
 // the natural-order result of task iteration `it` (cnt-th output of that butterfly)
-template <int N, int DIR, class Ld, class Fin>
+template <int N, int DIR, int TZ, class Ld, class Fin>
 __device__ __forceinline__ void y_line_fft(cplx* s, const cplx* tw, Ld ld, Fin fin) {
   typedef FftPlan<N> P;
-  constexpr int TZ = Pow2Cfg<N>::TZY;
   constexpr int N1 = N / P::R1, N2 = N1 / P::R2;
   constexpr bool single = (P::R2 == 1), two = (P::R3 == 1);
   constexpr int RL = single ? P::R1 : (two ? P::R2 : P::R3);
@@ -648,14 +651,14 @@ __device__ __forceinline__ void y_line_fft(cplx* s, const cplx* tw, Ld ld, Fin f
 //   ls odd : components 3r+1 and 3r+2 -> slot 3r+1 = xi_y(ky) F(t_r1) + xi_z(kz) F(t_r2)
 // in place in spec (x-slab layout), or SCATTER: to the y-slab layout [slot][x global][y local][kz]
 // of the rank that owns y (forward slab transpose fused into the store).
-// One tile (bx, by) of the forward y pass: bx = line slot * nxc + x plane of the launch's chunk, by = kz tile.
+// One tile (bx, by) of the forward y pass: bx = line slot * nx + local x plane, by = kz tile.
 template <int N, bool SCATTER>
 __device__ __forceinline__ void fyf_tile(const Pow2Args& g, cplx* __restrict__ spec, const PeerPtrs& peers, cplx* s, const cplx* tw,
                                          int bx, int by) {
   typedef FftPlan<N> P;
-  constexpr int H = KzBins<N>::value, TZ = Pow2Cfg<N>::TZY;
+  constexpr int H = KzBins<N>::value, TZ = SCATTER ? ScatterTile<N>::TZY : Pow2Cfg<N>::TZY;
   constexpr int RL = (P::R2 == 1) ? P::R1 : ((P::R3 == 1) ? P::R2 : P::R3);
-  const int ls = bx / g.nxc, xl = g.xoff + (bx - ls * g.nxc);
+  const int ls = bx / g.nx, xl = bx - ls * g.nx;
   const int row = ls >> 1, kz0 = by * TZ;
   const int slot = 3 * row + (ls & 1);
   const int ny = g.NY;                                   // SCATTER: y planes per rank
@@ -672,18 +675,18 @@ __device__ __forceinline__ void fyf_tile(const Pow2Args& g, cplx* __restrict__ s
     }
   };
   if ((ls & 1) == 0) {
-    y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
+    y_line_fft<N, -1, TZ>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
                       [&](int, int, int y, int l, cplx v) { out(y, l, v); });
   } else {
     cplx keep[2][RL];
-    y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
+    y_line_fft<N, -1, TZ>(s, tw, [&](int i, int l) { return G1[(int64_t)i * H + l]; },
                       [&](int it, int cnt, int y, int, cplx v) {
                         const double fy = sfreq<N>(y);
                         keep[it][cnt] = make_double2(fy * v.x, fy * v.y);
                       });
     __syncthreads();                                     // the tile buffer is reused for component 3r+2
     const cplx* G2 = G1 + (int64_t)g.nx * plane;
-    y_line_fft<N, -1>(s, tw, [&](int i, int l) { return G2[(int64_t)i * H + l]; },
+    y_line_fft<N, -1, TZ>(s, tw, [&](int i, int l) { return G2[(int64_t)i * H + l]; },
                       [&](int it, int cnt, int y, int l, cplx v) {
                         const double fz = (double)(kz0 + l);
                         out(y, l, make_double2(keep[it][cnt].x + fz * v.x, keep[it][cnt].y + fz * v.y));
@@ -693,7 +696,7 @@ __device__ __forceinline__ void fyf_tile(const Pow2Args& g, cplx* __restrict__ s
 
 template <int N, bool SCATTER>
 __global__ void __launch_bounds__(YXBound<N>::value) k_fyf(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers) {
-  constexpr int TZ = Pow2Cfg<N>::TZY;
+  constexpr int TZ = SCATTER ? ScatterTile<N>::TZY : Pow2Cfg<N>::TZY;
   extern __shared__ cplx sm[];
   cplx* s = sm;
   cplx* tw = sm + N * TZ;
@@ -701,25 +704,6 @@ __global__ void __launch_bounds__(YXBound<N>::value) k_fyf(Pow2Args g, cplx* __r
   __syncthreads();
   fyf_tile<N, SCATTER>(g, spec, peers, s, tw, blockIdx.x, blockIdx.y);
 }
-// Persistent form for the multi-GPU pipeline: gridDim.x CTAs walk the ntx x nty tiles of a chunk.  This pass is
-// NVLink-bound; run with a grid that covers only part of the SMs (CPFFT_FYF_CTAS) it leaves the rest of the
-// machine to the HBM-bound forward z pass of the next chunk instead of evicting it (launched as an ordinary grid
-// on the high-priority stream it took every CTA slot and the z pass stalled for as long as it ran).
-template <int N, bool SCATTER>
-__global__ void __launch_bounds__(YXBound<N>::value) k_fyf_persist(Pow2Args g, cplx* __restrict__ spec, PeerPtrs peers, int ntx, int nty) {
-  constexpr int TZ = Pow2Cfg<N>::TZY;
-  extern __shared__ cplx sm[];
-  cplx* s = sm;
-  cplx* tw = sm + N * TZ;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = g.tw[i];
-  __syncthreads();
-  const int total = ntx * nty;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    fyf_tile<N, SCATTER>(g, spec, peers, s, tw, tile % ntx, tile / ntx);
-    __syncthreads();                                     // the tile buffer is reused
-  }
-}
-
 // inverse y pass, grid = (9 * nx, NZ / TZ), out of place: component c = 3r + m reads line slot
 // 3r (m = 0) or 3r+1 scaled by xi_y(ky) (m = 1) / xi_z(kz) (m = 2) and writes component c of
 // `dst` (x-slab layout, all 9 components again).
@@ -737,7 +721,7 @@ __global__ void __launch_bounds__(YXBound<N>::value) k_fyi(Pow2Args g, const cpl
   const int64_t plane = (int64_t)N * H;
   const cplx* Gin = src + ((int64_t)slot * g.nx + xl) * plane + kz0;
   cplx* Gout = dst + ((int64_t)c * g.nx + xl) * plane + kz0;
-  y_line_fft<N, +1>(s, tw, [&](int i, int l) {
+  y_line_fft<N, +1, TZ>(s, tw, [&](int i, int l) {
                       const cplx v = Gin[(int64_t)i * H + l];
                       if (m == 0) return v;
                       const double f = (m == 1) ? sfreq<N>(i) : (double)(kz0 + l);
@@ -877,36 +861,24 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   typedef FftPlan<N> P;
   const int nx = h->nxloc, world = h->cfg.world;
   Pow2Args g;
-  g.nx = nx; g.x0 = h->x0; g.xoff = 0; g.nxc = nx; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
+  g.nx = nx; g.x0 = h->x0; g.NY = N; g.y0 = 0; g.n3 = h->n3; g.tw = h->tw;
   PeerPtrs none = {};
   const size_t sm_z = ODD ? OddZ<N>::bytes : ZSmem<N>::bytes;
   const size_t sm_y = sizeof(cplx) * (N * TZY + N), sm_x = sizeof(cplx) * (2 * N * TZX + N);
   const unsigned zgrid = (unsigned)(nx * N);
-  // forward z pass of the local x planes [xoff, xoff + nxc)
-  auto launch_fz = [&](int xoff, int nxc) {
-    Pow2Args gz = g;
-    gz.xoff = xoff; gz.nxc = nxc;
-    const unsigned zg = (unsigned)(nxc * N);
-    const int tkz = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
-    if constexpr (ODD) {
-      if (cg && cg->update_p && cg->x) k_fz_odd<N, 3><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
-      else if (cg && cg->update_p) k_fz_odd<N, 2><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
-      else if (flgK) k_fz_odd<N, 1><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-      else k_fz_odd<N, 0><<<zg, ZT, sm_z, h->stream>>>(gz, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-    } else {
-      if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
-      else if (cg && cg->update_p) k_fz<N, 2><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
-      else if (flgK) k_fz<N, 1><<<zg, ZT, sm_z, h->stream>>>(gz, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-      else k_fz<N, 0><<<zg, ZT, sm_z, h->stream>>>(gz, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
-    }
-    cpf_prof_end(h, tkz);
-  };
-  // multi-GPU with peer stores: the forward y pass of a chunk of x planes (NVLink-bound: its last stage stores
-  // into the peers' y slabs) runs on the second stream under the HBM-bound forward z pass of the next chunk
-  int nchunk = (world > 1 && h->p2p) ? h->fwd_chunks : 1;
-  while (nchunk > 1 && nx % nchunk) --nchunk;
-  int tk;
-  if (nchunk == 1) launch_fz(0, nx);
+  int tk = cpf_prof_begin(h, flgK ? CPF_K_FWD_Z_K4 : CPF_K_FWD_Z);
+  if constexpr (ODD) {
+    if (cg && cg->update_p && cg->x) k_fz_odd<N, 3><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
+    else if (cg && cg->update_p) k_fz_odd<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
+    else if (flgK) k_fz_odd<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    else k_fz_odd<N, 0><<<zgrid, ZT, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+  } else {
+    if (cg && cg->update_p && cg->x) k_fz<N, 3><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, cg->x, cg->rr_alpha, cg->pq);
+    else if (cg && cg->update_p) k_fz<N, 2><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, cg->r, cg->beta, nullptr, 0.0, nullptr);
+    else if (flgK) k_fz<N, 1><<<zgrid, ZT, sm_z, h->stream>>>(g, src, h->field[CPFFT_K4], h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+    else k_fz<N, 0><<<zgrid, ZT, sm_z, h->stream>>>(g, src, nullptr, h->spec_a, nullptr, 0.0, nullptr, 0.0, nullptr);
+  }
+  cpf_prof_end(h, tk);
   constexpr int Rm12 = P::R2 > 1 ? (P::R1 < P::R2 ? P::R1 : P::R2) : P::R1;
   constexpr int RminY = P::R3 > 1 ? (Rm12 < P::R3 ? Rm12 : P::R3) : Rm12;
   constexpr int ty0 = (TZY * (N / RminY) + 31) / 32 * 32, tx0 = (2 * TZX * (N / RminY) + 31) / 32 * 32;
@@ -914,6 +886,13 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
   constexpr int thr_x = tx0 > YXBound<N>::value ? YXBound<N>::value : tx0;
   const dim3 gy(9 * nx, H / TZY);
   const dim3 gyf(6 * nx, H / TZY);
+  // forward y pass with the slab transpose fused in: its own kz tile (ScatterTile)
+  constexpr int TZYS = ScatterTile<N>::TZY;
+  static_assert(H % TZYS == 0, "kz tiles must divide the stored bins");
+  constexpr int tys0 = (TZYS * (N / RminY) + 31) / 32 * 32;
+  constexpr int thr_ys = tys0 > YXBound<N>::value ? YXBound<N>::value : tys0;
+  const size_t sm_ys = sizeof(cplx) * (N * TZYS + N);
+  const dim3 gyfs(6 * nx, H / TZYS);
   if (world == 1) {
     tk = cpf_prof_begin(h, CPF_K_FFT_Y);
     k_fyf<N, false><<<gyf, thr_y, sm_y, h->stream>>>(g, h->spec_a, none);
@@ -932,27 +911,13 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
       for (int r = 0; r < CPF_MAX_WORLD; ++r) { pa.p[r] = h->peer_spec_a[r]; pb.p[r] = h->peer_spec_b[r]; }
       Pow2Args gs = g;
       gs.NY = ny;                                  // y planes per rank, for the scatter
-      if (nchunk == 1) {
-        tk = cpf_prof_begin(h, CPF_K_FFT_Y);
-        k_fyf<N, true><<<gyf, thr_y, sm_y, h->stream>>>(gs, h->spec_a, pb);     // -> every rank's spec_b
-        cpf_prof_end(h, tk);
-      } else {
-        const int nxc = nx / nchunk;
-        const dim3 gyc(6 * nxc, H / TZY);
-        for (int c = 0; c < nchunk; ++c) {
-          launch_fz(c * nxc, nxc);
-          CPF_CUDA(cudaEventRecord(h->ev_chunk[c], h->stream));
-          CPF_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_chunk[c], 0));
-          gs.xoff = c * nxc; gs.nxc = nxc;
-          tk = cpf_prof_begin_on(h, CPF_K_FFT_Y, h->stream2);
-          const int tiles = (int)(gyc.x * gyc.y);
-          k_fyf_persist<N, true><<<std::min(tiles, h->fyf_ctas), thr_y, sm_y, h->stream2>>>(gs, h->spec_a, pb, (int)gyc.x, (int)gyc.y);
-          cpf_prof_end(h, tk);
-        }
-        CPF_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-        CPF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        h->launches += 2 * (nchunk - 1);
-      }
+      // A variant that ran this NVLink-bound pass chunk by chunk on a second stream under the forward z pass of the next
+      // chunk of x planes (ordinary or persistent grid, 37..296 CTAs, 4 or 8 chunks) measured 1-4 % SLOWER on 2 GPUs
+      // (profiles/r02d_mgpu2_pipeline.log, r02f_mgpu2_pipeline.log): k_fz is latency-bound, it loses throughput in
+      // proportion to the CTA slots the y pass holds while it waits on the link, so nothing is hidden.  Removed.
+      tk = cpf_prof_begin(h, CPF_K_FFT_Y);
+      k_fyf<N, true><<<gyfs, thr_ys, sm_ys, h->stream>>>(gs, h->spec_a, pb);     // -> every rank's spec_b
+      cpf_prof_end(h, tk);
       int rc = cpf_rank_barrier(h); if (rc) return rc;
       tk = cpf_prof_begin(h, CPF_K_X_GREEN);
       k_fx<N, true><<<gx, thr_x, sm_x, h->stream>>>(gt, h->spec_b, pa);        // -> every rank's spec_a
@@ -1022,8 +987,7 @@ static int init_pow2(cpfft_handle* h) {
     CPF_SMEM_ATTR((k_iz_pipe<N, false>), sm_z);
   }
   CPF_SMEM_ATTR((k_fyf<N, false>), sm_y);
-  CPF_SMEM_ATTR((k_fyf<N, true>), sm_y);
-  CPF_SMEM_ATTR((k_fyf_persist<N, true>), sm_y);
+  CPF_SMEM_ATTR((k_fyf<N, true>), sizeof(cplx) * (N * ScatterTile<N>::TZY + N));
   CPF_SMEM_ATTR((k_fyi<N>), sm_y);
   CPF_SMEM_ATTR((k_fx<N, false>), sm_x);
   CPF_SMEM_ATTR((k_fx<N, true>), sm_x);

@@ -44,18 +44,17 @@ case "$MODE" in
     for lib in gpurun_variants/lib_*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 2>&1 | tail -1; done | tee gpurun_out/${TAG}_mm10ab.log ;;
   izab)     # A/B of the inverse z pass occupancy variants (gpurun_variants/lib_iz*.so) at 256^3
     for lib in gpurun_variants/lib_iz*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_apply.py 256 2>&1 | tail -2; done | tee gpurun_out/${TAG}_izab.log ;;
-  mgpu)     # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then the forward-transpose pipeline on / off
+  mgpu)     # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then a short strain-BC bench
     NG=${3:-2}; GRID=${4:-320}
     TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533"
-    (timeout 120 $TR tools/multi_gpu_check.py --grid 32 --steps 4; timeout 120 $TR tools/multi_gpu_check.py --grid 64 --steps 3;
-     CPFFT_FWD_CHUNKS=1 timeout 120 $TR tools/multi_gpu_check.py --grid 64 --steps 3) 2>&1 | grep -E "^\{|rror" | tee gpurun_out/${TAG}_mgpu${NG}_check.log
-    for ch in 1 4 8; do
-      CPFFT_FWD_CHUNKS=$ch timeout 300 $TR bench.py --gpus $NG --grid $GRID --steps 3 --warmup 3 --stress-leg-steps 0 --no-parity \
-          > gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}.json 2> gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}.err
+    (timeout 120 $TR tools/multi_gpu_check.py --grid 64 --steps 3) 2>&1 | grep -E "^\{|rror" | tee gpurun_out/${TAG}_mgpu${NG}_check.log
+    for ch in 1; do ct=0
+      timeout 300 $TR bench.py --gpus $NG --grid $GRID --steps 3 --warmup 3 --stress-leg-steps 0 --no-parity \
+          > gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}_${ct}.json 2> gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}_${ct}.err
       python - <<PY
 import json
-l=json.loads(open("gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}.json").read().strip().splitlines()[-1])
-print("chunks", $ch, "value %.4g" % l["value"], "e2e %.4g" % l["e2e"]["value"], {k: round(v["ms_per_launch"], 3) for k, v in l["stages"].items()})
+l=json.loads(open("gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}_${ct}.json").read().strip().splitlines()[-1])
+print("chunks", $ch, "fyf ctas", $ct, "value %.4g" % l["value"], "e2e %.4g" % l["e2e"]["value"], {k: round(v["ms_per_launch"], 3) for k, v in l["stages"].items()})
 PY
     done | tee gpurun_out/${TAG}_mgpu${NG}_pipeline.log ;;
   first)    # everything written without a GPU, cheapest first; every leg has its own timeout and log
