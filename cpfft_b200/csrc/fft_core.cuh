@@ -245,7 +245,10 @@ template <> struct FftPlan<100> { static constexpr int R1 = 10, R2 = 10, R3 = 1;
 template <> struct FftPlan<160> { static constexpr int R1 = 10, R2 = 16, R3 = 1; };
 template <> struct FftPlan<200> { static constexpr int R1 = 5,  R2 = 5,  R3 = 8; };
 template <> struct FftPlan<320> { static constexpr int R1 = 5,  R2 = 8,  R3 = 8; };   // measured: radix 20 spills in the x / y passes
-template <> struct FftPlan<400> { static constexpr int R1 = 5,  R2 = 5,  R3 = 16; };
+// 400: two radix-20 stages.  Measured at 400^3 on one B200 (profiles/r02i_plan400ab.log, ms per launch, y pass / x pass):
+// 5.5.16 3.19 / 2.98 (round 1; its last radix-16 stage spilled 320 B in the forward y pass), 10.10.4 2.50 / 2.96,
+// 16.5.5 2.76 / 2.67, 4.10.10 3.11 / 3.15, 20.20 1.70 / 2.45 -- one shared-memory exchange less.
+template <> struct FftPlan<400> { static constexpr int R1 = 20, R2 = 20, R3 = 1; };
 
 // odd sizes: 255 = 15 x 17 is the reference-faithful neighbour of 256 (the reference's Ghat is a projection for
 // odd N only, FFT_init.f:146-147, 370-375); 15, 51, 85 are its small relatives for the parity tests

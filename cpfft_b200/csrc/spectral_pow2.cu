@@ -75,6 +75,16 @@ template <> struct Pow2Cfg<255> { static constexpr int H = 127, TZY = 16, TZX = 
 // floor the compiler spends 254 registers per thread on k_fz and a single CTA fits (measured
 // at 320^3: occupancy 7.6 %, 56 % of the HBM peak).
 template <int N> struct ZOcc { static constexpr int MINB = (512 + Pow2Cfg<N>::ZT - 1) / Pow2Cfg<N>::ZT; };
+// resident CTAs the forward z pass is compiled for (development knob -DFZ_N=320 -DFZ_MINB=3, tools/build_variants.py)
+#ifdef FZ_MINB
+template <int N> struct ZOccF { static constexpr int MINB = (N == FZ_N) ? FZ_MINB : ZOcc<N>::MINB; };
+#else
+template <int N> struct ZOccF { static constexpr int MINB = ZOcc<N>::MINB; };
+// 320: 160 threads x 4 CTAs leave the forward pass 96 registers, too few to keep a K4 row of loads in flight (ncu: 67 % of
+// the DRAM peak, long-scoreboard stalls 37 vs 27 at 256^3); 3 CTAs x 128 registers measured 5.51 vs 6.42 ms at 320^3
+// (profiles/r02h_fz320ab.log; 2 CTAs x 168 registers: 5.84)
+template <> struct ZOccF<320> { static constexpr int MINB = 3; };
+#endif
 // resident CTAs the inverse z pass is compiled for (development knob IZ_MINB, tools/build_variants.py)
 #ifdef IZ_MINB
 template <int N> struct ZOccI { static constexpr int MINB = (N == 256) ? IZ_MINB : ZOcc<N>::MINB; };
@@ -176,7 +186,7 @@ __device__ __forceinline__ void z_fft_inv(cplx* A, const cplx* tw, LoadFirst loa
 // pass then only updates the residual (one read of p and one read + write of x less per
 // iteration on balance: 72 B / voxel).
 template <int N, int MODE>
-__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOcc<N>::MINB) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
+__global__ void __launch_bounds__(Pow2Cfg<N>::ZT, ZOccF<N>::MINB) k_fz(Pow2Args g, double* __restrict__ src, const double* __restrict__ K4,
                                           cplx* __restrict__ spec, const double* __restrict__ rvec, double beta,
                                           double* __restrict__ xvec, double rr_alpha, const double* __restrict__ pq) {
   typedef ZSmem<N> Z;
