@@ -924,7 +924,11 @@ static int apply_pow2(cpfft_handle* h, double* src, double* dst, bool flgK, doub
       // A variant that ran this NVLink-bound pass chunk by chunk on a second stream under the forward z pass of the next
       // chunk of x planes (ordinary or persistent grid, 37..296 CTAs, 4 or 8 chunks) measured 1-4 % SLOWER on 2 GPUs
       // (profiles/r02d_mgpu2_pipeline.log, r02f_mgpu2_pipeline.log): k_fz is latency-bound, it loses throughput in
-      // proportion to the CTA slots the y pass holds while it waits on the link, so nothing is hidden.  Removed.
+      // proportion to the CTA slots the y pass holds while it waits on the link, so nothing is hidden.  Moving the
+      // transfer to the copy engines instead (y pass in place or into a staging layout, 3-D or contiguous peer copies
+      // on a second stream under the z / y passes of the next chunk; the copies alone run at 0.9-1.2 TB/s,
+      // profiles/r02l_xfer_probe.log) also lost: -4 % on 2 GPUs, -3 % on 8 (profiles/r02m_*, r02n_*): the chunked z pass
+      // runs 5-8 % slower and the last chunk's copies stay exposed.  Both removed; the fused peer stores stay.
       tk = cpf_prof_begin(h, CPF_K_FFT_Y);
       k_fyf<N, true><<<gyfs, thr_ys, sm_ys, h->stream>>>(gs, h->spec_a, pb);     // -> every rank's spec_b
       cpf_prof_end(h, tk);

@@ -44,17 +44,30 @@ case "$MODE" in
     for lib in gpurun_variants/lib_*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 2>&1 | tail -1; done | tee gpurun_out/${TAG}_mm10ab.log ;;
   izab)     # A/B of the inverse z pass occupancy variants (gpurun_variants/lib_iz*.so) at 256^3
     for lib in gpurun_variants/lib_iz*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_apply.py 256 2>&1 | tail -2; done | tee gpurun_out/${TAG}_izab.log ;;
+  scale)    # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then bench.py as the driver launches it
+    NG=${3:-8}; K=${4:-3}; W=${5:-3}
+    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533"
+    timeout 150 $TR tools/multi_gpu_check.py --grid 64 --steps 3 2>&1 | grep -E "^\{|rror" | tee gpurun_out/${TAG}_check_${NG}gpu.log
+    timeout 900 $TR bench.py --gpus $NG --steps $K --warmup $W > gpurun_out/${TAG}_bench_${NG}gpu.json 2> gpurun_out/${TAG}_bench_${NG}gpu.err
+    tail -3 gpurun_out/${TAG}_bench_${NG}gpu.err
+    python - <<PY
+import json
+l=json.loads(open("gpurun_out/${TAG}_bench_${NG}gpu.json").read().strip().splitlines()[-1])
+print("N", l["n_gpus"], "grid", l["config"]["grid"], "value %.4g" % l["value"], "e2e %.4g" % l["e2e"]["value"], "stress leg %.4g" % (l["stress_bc_leg"] or {}).get("value", 0),
+      "parity", (l["parity"] or {}).get("ok"), {k: round(v["ms_per_launch"], 3) for k, v in l["stages"].items()})
+PY
+    ;;
   mgpu)     # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then a short strain-BC bench
     NG=${3:-2}; GRID=${4:-320}
     TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533"
     (timeout 120 $TR tools/multi_gpu_check.py --grid 64 --steps 3) 2>&1 | grep -E "^\{|rror" | tee gpurun_out/${TAG}_mgpu${NG}_check.log
-    for ch in 1; do ct=0
+    for ch in 1; do ct=store
       timeout 300 $TR bench.py --gpus $NG --grid $GRID --steps 3 --warmup 3 --stress-leg-steps 0 --no-parity \
           > gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}_${ct}.json 2> gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}_${ct}.err
       python - <<PY
 import json
 l=json.loads(open("gpurun_out/${TAG}_bench${GRID}_${NG}gpu_chunks${ch}_${ct}.json").read().strip().splitlines()[-1])
-print("chunks", $ch, "fyf ctas", $ct, "value %.4g" % l["value"], "e2e %.4g" % l["e2e"]["value"], {k: round(v["ms_per_launch"], 3) for k, v in l["stages"].items()})
+print("xfer", "$ct", "chunks", $ch, "value %.4g" % l["value"], "e2e %.4g" % l["e2e"]["value"], {k: round(v["ms_per_launch"], 3) for k, v in l["stages"].items()})
 PY
     done | tee gpurun_out/${TAG}_mgpu${NG}_pipeline.log ;;
   first)    # everything written without a GPU, cheapest first; every leg has its own timeout and log
