@@ -120,23 +120,30 @@ CPF_DI void voxel_kinematics(const double* fn, const double* fn1, double* Rh, do
 // t6: unrotated Cauchy stress (Voigt), C: 6x6 [D] row-major.  Algebraically identical to
 // cep2A_a (cep2A.f:86-284) but every rank-one structure of dR/dF, dRh/dF and dL/dF is
 // contracted analytically, so the cost is O(81 * const) instead of four 81x9 loop nests.
-// C: anything indexable as C[k], k = 6 * row + col -- a register array, or StridedCep, which re-reads
-// the voxel's [D] from global memory (L1-resident: 36 x 256 B per warp) and takes its 36 values out
-// of the register budget of the 9 x 9 output loop.
-struct StridedCep {
-  const double* p; int64_t stride;
-  CPF_DI double operator[](int k) const { return CPF_LDG(p + (int64_t)k * stride); }
+//
+// Register budget.  Written as one pass the 81 outputs keep ~200 doubles live (twice what a thread has): the first
+// version spilled 1200 B per thread and moved 32.5 GB of DRAM traffic per 256^3 launch for 20.1 GB of algorithmic
+// bytes.  Now two phases with disjoint operand sets: phase 1 forms the geometric part of all 81 entries (dJ/dF,
+// dF^-T/dF, dR/dF terms: RtRF, SF, F^-1, RYR, RY, A1..A6) into the scratch tile `S`; phase 2 forms the material part
+// J (R dt Uinv), dt = [D] : dd/dF (Yh, B1, RYh, B2, UU, VV, [D], R, Uinv), adds and stores.  `S` is 81 doubles per
+// thread in shared memory in the kernel (element m of thread t at S.p[m * PK1_THREADS + t]), a plain array on the host.
+#ifndef PK1_THREADS
+#define PK1_THREADS 128
+#endif
+struct Pk1Scratch {
+  double* p;
+#ifdef __CUDACC__
+  CPF_DI double& operator[](int k) const { return p[k * PK1_THREADS]; }
+#else
+  CPF_DI double& operator[](int k) const { return p[k]; }
+#endif
 };
-template <class Cep>
-CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t6, const Cep& C,
+// C: [D] as stored, entry 6 * row + col at C[(6 * row + col) * strideC]
+CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t6, const double* __restrict__ C, int64_t strideC,
                             double* P, double* A /*81, may alias nothing*/,
-                            double* __restrict__ outA, int64_t strideA) {
-  double Rh[9], R[9], fh[9], df[9], fhinv[9], finv[9], t[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) { fh[k] = 0.5 * (fn[k] + fn1[k]); df[k] = fn1[k] - fn[k]; }
-  polar_R(fh, Rh);
+                            double* __restrict__ outA, int64_t strideA, const Pk1Scratch S) {
+  double R[9], finv[9], t[9];
   polar_R(fn1, R);
-  m3_inv(fh, fhinv);
   const double J = m3_inv(fn1, finv);
   v6_to_m3(t6, t);
   double U[9], Y[9], RY[9], RYR[9], sigma[9], Uinv[9], tUinv[9], Rt[9], RtRF[9], tmp[9];
@@ -157,7 +164,37 @@ CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t
   m3_mul_nt(sigma, finv, SF);
 #pragma unroll
   for (int k = 0; k < 9; ++k) P[k] = J * SF[k];
-  // half-step quantities
+  // ---- phase 1: geometric part of the 81 entries -> S ----
+  {
+    double A1[9], A2[9], A3[9], A4[9], A5[9], A6[9];
+    m3_mul(Y, tUinv, A1);
+    m3_mul(RY, tUinv, A2);
+    m3_mul_nt(Rt, Y, A3);
+    m3_mul(finv, RYR, A4);
+    m3_mul_nt(Rt, RY, A5);
+    m3_mul(finv, RY, A6);
+    const double Jy = J * y;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double dJ = J * finv[3 * l + k];  // dJdF(k,l) = J finv(l,k)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            S[27 * i + 9 * j + 3 * k + l] = RtRF[3 * i + j] * dJ - J * SF[3 * i + l] * finv[3 * j + k] +
+                                            Jy * (RYR[3 * i + k] * A1[3 * l + j] - RY[3 * i + l] * A2[3 * k + j]) +
+                                            Jy * (A3[3 * i + l] * A4[3 * j + k] - A5[3 * i + k] * A6[3 * j + l]);
+      }
+  }
+  // ---- phase 2: material part J (R dt Uinv), dt = [D] : d(d)/dF ----
+  // half-step quantities (formed only now: their 108 doubles must not be live during phase 1)
+  double Rh[9], fh[9], df[9], fhinv[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { fh[k] = 0.5 * (fn[k] + fn1[k]); df[k] = fn1[k] - fn[k]; }
+  polar_R(fh, Rh);
+  m3_inv(fh, fhinv);
   double Uh[9], Yh[9], RYh[9], RYRh[9], G[9], Lm[9], D2[9], E[9], B1[9], B2[9], UU[9], VV[9];
   m3_mul_tn(Rh, fh, Uh);
   double trUh = Uh[0] + Uh[4] + Uh[8];
@@ -180,15 +217,9 @@ CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t
 #pragma unroll
   for (int k = 0; k < 9; ++k) UU[k] = Rh[k] - tmp[k];
   m3_mul(G, Rh, VV);
-  // products for the dR/dF terms
-  double A1[9], A2[9], A3[9], A4[9], A5[9], A6[9];
-  m3_mul(Y, tUinv, A1);
-  m3_mul(RY, tUinv, A2);
-  m3_mul_nt(Rt, Y, A3);
-  m3_mul(finv, RYR, A4);
-  m3_mul_nt(Rt, RY, A5);
-  m3_mul(finv, RY, A6);
-  const double Jy = J * y;
+  double Cr[36];
+#pragma unroll
+  for (int q = 0; q < 36; ++q) Cr[q] = CPF_LDG(C + (int64_t)q * strideC);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -210,23 +241,19 @@ CPF_DI void pk1_and_tangent(const double* fn, const double* fn1, const double* t
       for (int v = 0; v < 6; ++v) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < 6; ++w) s += C[6 * w + v] * dv[w];
+        for (int w = 0; w < 6; ++w) s += Cr[6 * w + v] * dv[w];
         dt6[v] = s;
       }
       double dtm[9], T1[9], T2[9];
       v6_to_m3(dt6, dtm);
       m3_mul(R, dtm, T1);
       m3_mul(T1, Uinv, T2);
-      const double dJ = J * finv[3 * l + k];  // dJdF(k,l) = J finv(l,k)
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          double v = RtRF[3 * i + j] * dJ - J * SF[3 * i + l] * finv[3 * j + k] +
-                     Jy * (RYR[3 * i + k] * A1[3 * l + j] - RY[3 * i + l] * A2[3 * k + j]) +
-                     J * T2[3 * i + j] +
-                     Jy * (A3[3 * i + l] * A4[3 * j + k] - A5[3 * i + k] * A6[3 * j + l]);
           const int m = 27 * i + 9 * j + 3 * k + l;
+          const double v = S[m] + J * T2[3 * i + j];
           if (outA) outA[(int64_t)m * strideA] = v;
           if (A) A[m] = v;
         }

@@ -14,6 +14,7 @@
 #define MM10_MIN_CTAS 2     // 255 registers; 3 CTAs (168 registers) spill and run 1.5x slower
 #endif
 #define MM10_THREADS UPD_THREADS
+#define PK1_THREADS UPD_THREADS
 #include "update.cuh"
 #include "material_tables.hpp"
 
@@ -63,9 +64,11 @@ __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_tayl
 
 __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, const double* Fn1, const double* urcs_n1,
                                                               const double* cep, double* Pn1, double* K4, int64_t n3) {
+  extern __shared__ double pk1_sm[];        // 81 doubles per thread: the geometric part of dP/dF between the two phases
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n3) return;
-  upd_pk1_voxel(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e);
+  Pk1Scratch S; S.p = pk1_sm + threadIdx.x;
+  upd_pk1_voxel(Fn, Fn1, urcs_n1, cep, Pn1, K4, n3, e, S);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -143,7 +146,9 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
       }
   }
   const int tk = cpf_prof_begin(h, CPF_K_PK1_TANGENT);
-  k_pk1_tangent<<<grid, UPD_THREADS, 0, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
+  const size_t sm_pk1 = sizeof(double) * 81 * UPD_THREADS;
+  CPF_CUDA(cudaFuncSetAttribute(k_pk1_tangent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pk1));
+  k_pk1_tangent<<<grid, UPD_THREADS, sm_pk1, h->stream>>>(a.Fn, a.Fn1, a.urcs_n1, a.cep, h->field[CPFFT_PN1], h->field[CPFFT_K4], n3);
   cpf_prof_end(h, tk);
   h->launches++;
   CPF_CUDA(cudaGetLastError());

@@ -612,16 +612,13 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
 
 // P and K4 of one voxel from (Fn, Fn1, unrotated stress, [D]).
 CPF_DI void upd_pk1_voxel(const double* Fn, const double* Fn1, const double* urcs_n1, const double* cep,
-                          double* Pn1, double* K4, const int64_t n3, const int64_t e) {
+                          double* Pn1, double* K4, const int64_t n3, const int64_t e, const Pk1Scratch S) {
   double fn[9], fn1[9], t6[6], P[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) { fn[k] = Fn[k * n3 + e]; fn1[k] = Fn1[k * n3 + e]; }
 #pragma unroll
   for (int k = 0; k < 6; ++k) t6[k] = urcs_n1[k * n3 + e];
-  double C[36];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) C[k] = cep[k * n3 + e];
-  pk1_and_tangent(fn, fn1, t6, C, P, nullptr, K4 + e, n3);
+  pk1_and_tangent(fn, fn1, t6, cep + e, n3, P, nullptr, K4 + e, n3, S);
 #pragma unroll
   for (int k = 0; k < 9; ++k) Pn1[k * n3 + e] = P[k];
 }

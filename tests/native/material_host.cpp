@@ -104,7 +104,9 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
       else upd_mm10_voxel<false, MM10_VOCE>(a, e, sm);
     }
     // even voxels: [D] in registers (the kernel's default), odd voxels: the memory-resident variant
-    upd_pk1_voxel(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e);
+    double pk1_scratch[81];
+    Pk1Scratch S; S.p = pk1_scratch;
+    upd_pk1_voxel(a.Fn, a.Fn1, a.urcs_n1, a.cep, m->Pn1.data(), m->K4.data(), n3, e, S);
   }
   return m->failcnt[1];
 }
