@@ -230,7 +230,9 @@ def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
         scale = float(n3) / float(prof["grid"]) ** 3
         for name, ent in prof["kernels"].items():
             if name in stages:
-                if world == 1:
+                if "dram_bytes" not in ent:
+                    pass
+                elif world == 1:
                     stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"]
                 elif name in local_kernels:
                     stages[name]["ncu_dram_bytes_per_launch"] = ent["dram_bytes"] * scale

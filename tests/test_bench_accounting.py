@@ -27,7 +27,9 @@ def test_stage_rooflines_on_recorded_profile():
     assert 214.0 < stages["k_inv_z"]["alg_bytes_per_voxel"] <= 216.6
     assert 0.9 < roof["frac"] < 1.05 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
     assert roof["traffic"] and 0.95 < roof["traffic"] / roof["alg_bytes_per_launch"] < 1.1     # ncu DRAM bytes ~ algorithmic
-    assert 0.2 < stages["k_update_mm10"]["frac_of_fp64"] < 0.4
+    assert 0.15 < stages["k_update_mm10"]["frac_of_fp64"] < 0.4
+    # the FP64 rate of the profiled launch itself: its own flop count over its own duration (about 0.2 of the measured peak)
+    assert 0.15 < stages["k_update_mm10"]["frac_of_fp64_ncu_launch"] < 0.25
     assert abs(sum(v["share"] for v in stages.values()) - 1.0) < 1e-9
     json.dumps({"stages": stages, "roofline": roof})          # serialisable
 
