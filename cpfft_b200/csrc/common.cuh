@@ -61,6 +61,7 @@ struct cpfft_handle {
   bool has_mm01, has_mm10;
   bool has_taylor;                    // some cp material has n_crystals > 1 per point
   bool mm10_kern[2][3];               // [Taylor point][hardening law 1 Voce, 2 MTS]: update kernels to launch
+  int uni_cry; CpfCryDev cr0;         // >= 0: every grain uses this crystal-library entry (constants passed as kernel parameters)
   CpfHistLayout L;
   int32_t* d_fail; int32_t* d_liters;
   int* d_failcnt;            // {mm10 local failures since reset, failures of the last sweep}

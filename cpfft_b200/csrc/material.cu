@@ -25,42 +25,27 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm01(UpdArgs a) {
   upd_mm01_voxel(a, e);
 }
 
-__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10(UpdArgs a) {
-  extern __shared__ double mm10_sm[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n3) return;
-  upd_mm10_voxel<false, MM10_VOCE>(a, e, mm10_sm + threadIdx.x);
-}
-
-// development variant (CPFFT_MM10_LF=1): residual slip loop in the lattice frame, see mm10_resid
-__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_lf(UpdArgs a) {
-  extern __shared__ double mm10_sm[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n3) return;
-  upd_mm10_voxel<false, MM10_VOCE, true>(a, e, mm10_sm + threadIdx.x);
-}
-
-// polycrystalline material points (n_crystals > 1): same per-crystal integration, Taylor average
-__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_taylor(UpdArgs a) {
-  extern __shared__ double mm10_sm[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n3) return;
-  upd_mm10_voxel<true, MM10_VOCE>(a, e, mm10_sm + threadIdx.x);
-}
-
-// MTS hardening (`hardening mts`), single crystal and Taylor points: same source, other law
-__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_mts(UpdArgs a) {
-  extern __shared__ double mm10_sm[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n3) return;
-  upd_mm10_voxel<false, MM10_MTS>(a, e, mm10_sm + threadIdx.x);
-}
-__global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) k_update_mm10_taylor_mts(UpdArgs a) {
-  extern __shared__ double mm10_sm[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.n3) return;
-  upd_mm10_voxel<true, MM10_MTS>(a, e, mm10_sm + threadIdx.x);
-}
+// The mm10 sweep kernels: (one crystal per point | Taylor point) x (Voce | MTS), each compiled twice --
+// crystal constants per voxel from the crystal table, or (suffix _u) from the kernel parameters when the
+// whole model uses one crystal-library entry (UpdArgs::uni_cry).  k_update_mm10_lf*: residual slip loop
+// in the lattice frame (mm10_resid<.., LF = true>), the default; CPFFT_MM10_LF=0 selects the sample-frame loop.
+#define MM10_KERNEL(name, MULTI, HARD, LF, UNI)                                                       \
+  __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) name(const __grid_constant__ UpdArgs a) { \
+    extern __shared__ double mm10_sm[];                                                               \
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                                 \
+    if (e >= a.n3) return;                                                                            \
+    upd_mm10_voxel<MULTI, HARD, LF, UNI>(a, e, mm10_sm + threadIdx.x);                                \
+  }
+MM10_KERNEL(k_update_mm10, false, MM10_VOCE, false, false)
+MM10_KERNEL(k_update_mm10_u, false, MM10_VOCE, false, true)
+MM10_KERNEL(k_update_mm10_lf, false, MM10_VOCE, true, false)
+MM10_KERNEL(k_update_mm10_lf_u, false, MM10_VOCE, true, true)
+MM10_KERNEL(k_update_mm10_taylor, true, MM10_VOCE, false, false)        // n_crystals > 1: Taylor average
+MM10_KERNEL(k_update_mm10_taylor_u, true, MM10_VOCE, false, true)
+MM10_KERNEL(k_update_mm10_mts, false, MM10_MTS, false, false)           // `hardening mts`: same source, other law
+MM10_KERNEL(k_update_mm10_mts_u, false, MM10_MTS, false, true)
+MM10_KERNEL(k_update_mm10_taylor_mts, true, MM10_MTS, false, false)
+MM10_KERNEL(k_update_mm10_taylor_mts_u, true, MM10_MTS, false, true)
 
 __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, const double* Fn1, const double* urcs_n1,
                                                               const double* cep, double* Pn1, double* K4, int64_t n3) {
@@ -81,6 +66,13 @@ int cpf_material_setup(cpfft_handle* h, const int32_t* matlist, int ncmax, const
   if (rc) { cpf_set_error(h, err); return rc; }
   h->has_mm01 = T.has_mm01; h->has_mm10 = T.has_mm10; h->ngrains = T.ngrains; h->L = T.L;
   h->has_taylor = T.has_taylor;
+  // one crystal-library entry behind every grain: its constants travel as kernel parameters
+  h->uni_cry = -1;
+  if (T.has_mm10 && !T.gcry.empty()) {
+    h->uni_cry = T.gcry[0];
+    for (int32_t ci : T.gcry) if (ci != h->uni_cry) { h->uni_cry = -1; break; }
+    if (h->uni_cry >= 0) h->cr0 = T.cd[h->uni_cry];
+  }
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) h->mm10_kern[i][j] = T.kern[i][j];
   const int H = T.H;
   // (re)allocate history fields
@@ -131,10 +123,18 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
   }
   {
     // one kernel per (one crystal | Taylor point) x (Voce | MTS) combination present in the model
-    typedef void (*Kern)(UpdArgs);
-    static const bool lf = [] { const char* v = getenv("CPFFT_MM10_LF"); return v && v[0] == '1'; }();
-    const Kern kerns[2][3] = {{nullptr, lf ? k_update_mm10_lf : k_update_mm10, k_update_mm10_mts},
-                              {nullptr, k_update_mm10_taylor, k_update_mm10_taylor_mts}};
+    typedef void (*Kern)(const UpdArgs);
+    // residual slip loop of the Voce single-crystal kernel in the lattice frame (default; CPFFT_MM10_LF=0: sample frame)
+    static const bool lf = [] { const char* v = getenv("CPFFT_MM10_LF"); return !(v && v[0] == '0'); }();
+    static const bool nouni = [] { const char* v = getenv("CPFFT_MM10_UNI"); return v && v[0] == '0'; }();
+    const bool uni = h->uni_cry >= 0 && !nouni;
+    a.uni_cry = uni ? 1 : 0;
+    a.cr0 = h->cr0;
+    const Kern kerns_t[2][2][3] = {{{nullptr, lf ? k_update_mm10_lf : k_update_mm10, k_update_mm10_mts},
+                                    {nullptr, k_update_mm10_taylor, k_update_mm10_taylor_mts}},
+                                   {{nullptr, lf ? k_update_mm10_lf_u : k_update_mm10_u, k_update_mm10_mts_u},
+                                    {nullptr, k_update_mm10_taylor_u, k_update_mm10_taylor_mts_u}}};
+    const auto& kerns = kerns_t[uni ? 1 : 0];
     const size_t smem = sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS;
     for (int multi = 0; multi < 2; ++multi)
       for (int hard = 1; hard <= 2; ++hard) {

@@ -40,9 +40,28 @@
 #ifndef MM10_SLIP_UNROLL
 #define MM10_SLIP_UNROLL 1
 #endif
+#ifndef MM10_RESID_UNROLL
+#define MM10_RESID_UNROLL MM10_SLIP_UNROLL
+#endif
+#ifndef MM10_JAC_UNROLL
+#define MM10_JAC_UNROLL MM10_SLIP_UNROLL
+#endif
 #define MM10_PRAGMA_(x) _Pragma(#x)
 #define MM10_UNROLL_SLIP_(n) MM10_PRAGMA_(unroll n)
-#define MM10_UNROLL_SLIP MM10_UNROLL_SLIP_(MM10_SLIP_UNROLL)
+#define MM10_UNROLL_RESID MM10_UNROLL_SLIP_(MM10_RESID_UNROLL)
+#define MM10_UNROLL_JAC MM10_UNROLL_SLIP_(MM10_JAC_UNROLL)
+// MM10_PREFETCH: the nine grain-table entries of slip system s + 1 are loaded while system s is
+// being processed (the loops are not unrolled, so the compiler cannot overlap the load latency
+// of one trip with the arithmetic of the previous one by itself).
+#ifndef MM10_PREFETCH
+#define MM10_PREFETCH 1
+#endif
+// the lattice-frame residual loop is short (per system 9 loads, a 6-term dot product, the power, 9 FMA):
+// unrolled, the loads of several systems are in flight together
+#ifndef MM10_LF_UNROLL
+#define MM10_LF_UNROLL 1
+#endif
+#define MM10_UNROLL_LF MM10_UNROLL_SLIP_(MM10_LF_UNROLL)
 
 // Per-thread array kept in shared memory, element k of thread t at p[k * blockDim + t]:
 // conflict-free, and it takes the Jacobian and the skew-rotation operators out of the
@@ -56,17 +75,41 @@ struct SArr {
 #define MM10_SM_RWR 58   // 9 : RW(R)
 #define MM10_SM_ACC 67   // 39: S (21) and T (18) slip sums of the Jacobian
 #define MM10_SMEM_DOUBLES 106
+// |rs/tt|^(n-1) of the first MM10_PCACHE systems, left in the `acc` slots by the residual for the
+// Jacobian that follows it: mm10_solve always forms the Jacobian at the point of its last
+// residual evaluation (the start point or the accepted line-search point), and `acc` is dead
+// between the two.  Saves half of the power evaluations; the values are the ones the Jacobian
+// would recompute, bit for bit.
+#define MM10_PCACHE 39
 
 CPF_DNOINLINE double cpf_pow(double x, double y) { return pow(x, y); }
 CPF_DNOINLINE double cpf_atan2(double y, double x) { return atan2(y, x); }
 
 CPF_DI double cpf_sgn(double x) { return x >= 0.0 ? 1.0 : -1.0; }  // Fortran sign(one,x)
 
-CPF_DI double cpf_pow_abs(double x, int ie, double fe) {  // x >= 0
+// x^ie for 0 <= ie <= 64 (x >= 0), else pow(x, fe).  Square-and-multiply from the low bit, written
+// without a loop: the chain of squares x^2 .. x^16 is straight-line code and every bit of the
+// exponent costs one predicated multiply.  The products are formed in the order of the
+// `while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }` loop this replaces (bit-identical results);
+// that loop was 13 instructions per bit behind a divergence-safe branch, 15 % of all
+// instructions the kernel executed (ncu source page, profiles/r02r_update_hotspots.md).
+CPF_DI double cpf_pow_abs(double x, int ie, double fe) {
   if (ie < 0) return cpf_pow(x, fe);
-  double r = 1.0, b = x;
-  int e = ie;
-  while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
+  double r = (ie & 1) ? x : 1.0;
+  double b = x * x;
+  r = (ie & 2) ? r * b : r;
+  b = b * b;
+  r = (ie & 4) ? r * b : r;
+  b = b * b;
+  r = (ie & 8) ? r * b : r;
+  b = b * b;
+  r = (ie & 16) ? r * b : r;
+  if (ie >= 32) {
+    b = b * b;
+    r = (ie & 32) ? r * b : r;
+    b = b * b;
+    r = (ie & 64) ? r * b : r;
+  }
   return r;
 }
 
@@ -177,6 +220,82 @@ CPF_DNOINLINE void mm10_lu7(const double* Jp, double sign, double* b) {
   for (int k = 0; k < 7; ++k) b[k] = x[k];
 }
 
+// ---- the 7x7 LU in shared memory (Voce kernels) ------------------------------------------------
+// mm10_lu7_factor: in-place factorisation of the matrix in J with partial pivoting in DGETRF's
+// order -- whole-row interchanges, unit-lower multipliers below the diagonal -- and the RECIPROCAL
+// of the pivot on the diagonal.  Shared memory can be indexed at run time, registers cannot: the
+// row interchange is two indexed rows behind a (rare, 1 % per column) branch instead of the
+// ~530 predicated selects cpf_lu_solve spends on every call, and the 49 entries no longer sit in
+// 98 registers.  Returns the pivot rows, 3 bits each.
+// mm10_lu7_solve: b <- A^-1 b from those factors (row interchanges, forward, back substitution).
+// The arithmetic on every entry is cpf_lu_solve's, operation for operation (l = a_ik * (1/a_kk),
+// a_ij -= l a_kj, b_i -= l b_k, x_k = (b_k - sum a_kc x_c) * (1/a_kk)): same results bit for bit,
+// and (-A)^-1 b == -(A^-1 b) exactly, so the Newton step solves with J and negates.
+#ifndef MM10_SMEM_LU
+#define MM10_SMEM_LU 1
+#endif
+CPF_DI int mm10_lu7_factor(SArr J) {
+  int pack = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    int piv = k;
+    double best = fabs(J[7 * k + k]);
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) {
+      const double v = fabs(J[7 * i + k]);
+      if (v > best) { best = v; piv = i; }
+    }
+    pack |= piv << (3 * k);
+    if (piv != k) {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const double t = J[7 * k + j];
+        J[7 * k + j] = J[7 * piv + j];
+        J[7 * piv + j] = t;
+      }
+    }
+    const double inv = 1.0 / J[7 * k + k];
+    J[7 * k + k] = inv;
+    double u[7];
+#pragma unroll
+    for (int j = k + 1; j < 7; ++j) u[j] = J[7 * k + j];
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) {
+      const double l = J[7 * i + k] * inv;
+      J[7 * i + k] = l;
+#pragma unroll
+      for (int j = k + 1; j < 7; ++j) J[7 * i + j] -= l * u[j];
+    }
+  }
+  return pack;
+}
+CPF_DI void mm10_lu7_solve(SArr J, int pack, double* b) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int piv = (pack >> (3 * k)) & 7;
+    const double top = b[k];
+    double pv = top;
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) {
+      const double cur = b[i];
+      pv = (piv == i) ? cur : pv;
+      b[i] = (piv == i) ? top : cur;
+    }
+    b[k] = pv;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) b[i] -= J[7 * i + k] * b[k];
+#pragma unroll
+  for (int k = 6; k >= 0; --k) {
+    double sum = b[k];
+#pragma unroll
+    for (int c2 = k + 1; c2 < 7; ++c2) sum -= J[7 * k + c2] * b[c2];
+    b[k] = sum * J[7 * k + k];
+  }
+}
+
 struct Mm10Ctx {
   const double* __restrict__ ms0;    // grain table: per system ms0[6], qs0[3] (drive_eps_sig.f:975-986)
   const double* __restrict__ C;      // rotated stiffness, 36 row-major
@@ -205,10 +324,20 @@ struct Mm10Ctx {
 // qs = RT2RVW(Rp_n^T) qs0 (mm10_a.f:867-876).  RT2RVE is the stress-type 6x6 operator, so in
 // tensor form ms = V6( Q M~ Q^T ) with M~ the symmetric tensor whose Voigt vector (no shear
 // doubling) is ms0, Q = Rp_n^T; that is what is evaluated here (45 FMA, no 6x6 operator).
-CPF_DI void mm10_slip_geom(const Mm10Ctx& c, int s, double* ms, double* qs) {
+CPF_DI void mm10_slip_load(const Mm10Ctx& c, int s, double* g) {
   const double* t = c.ms0 + 9 * s;
-  const double m0 = CPF_LDG(t), m1 = CPF_LDG(t + 1), m2 = CPF_LDG(t + 2), m3 = CPF_LDG(t + 3), m4 = CPF_LDG(t + 4), m5 = CPF_LDG(t + 5);
-  const double w0 = CPF_LDG(t + 6), w1 = CPF_LDG(t + 7), w2 = CPF_LDG(t + 8);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g[k] = CPF_LDG(t + k);
+}
+CPF_DI void mm10_slip_geom_v(const Mm10Ctx& c, const double* g, double* ms, double* qs);
+CPF_DI void mm10_slip_geom(const Mm10Ctx& c, int s, double* ms, double* qs) {
+  double g[9];
+  mm10_slip_load(c, s, g);
+  mm10_slip_geom_v(c, g, ms, qs);
+}
+CPF_DI void mm10_slip_geom_v(const Mm10Ctx& c, const double* g, double* ms, double* qs) {
+  const double m0 = g[0], m1 = g[1], m2 = g[2], m3 = g[3], m4 = g[4], m5 = g[5];
+  const double w0 = g[6], w1 = g[7], w2 = g[8];
   double T[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -279,16 +408,29 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
       y[5] = 2.0 * (c.Q[0] * U[2] + c.Q[3] * U[5] + c.Q[6] * U[8]);
     }
     double am[6] = {0, 0, 0, 0, 0, 0}, aw[3] = {0, 0, 0};
-MM10_UNROLL_SLIP
+#if MM10_PREFETCH
+    double gn[9];
+    mm10_slip_load(c, 0, gn);
+#endif
+MM10_UNROLL_LF
     for (int s = 0; s < c.nslip; ++s) {
-      const double* t = c.ms0 + 9 * s;
       double m[6], w[3];
+#if MM10_PREFETCH
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m[k] = gn[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[k] = gn[6 + k];
+      mm10_slip_load(c, (s + 1 < c.nslip) ? s + 1 : s, gn);
+#else
+      const double* t = c.ms0 + 9 * s;
 #pragma unroll
       for (int k = 0; k < 6; ++k) m[k] = CPF_LDG(t + k);
 #pragma unroll
       for (int k = 0; k < 3; ++k) w[k] = CPF_LDG(t + 6 + k);
+#endif
       const double rs = y[0] * m[0] + y[1] * m[1] + y[2] * m[2] + y[3] * m[3] + y[4] * m[4] + y[5] * m[5];
       const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
+      if (s < MM10_PCACHE) c.acc[s] = p;
       const double slip = dgtt * p * rs;
       const double f = rs * dif + slip;
 #pragma unroll
@@ -316,12 +458,26 @@ MM10_UNROLL_SLIP
     wq[1] = c.RWQ[3] * aw[0] + c.RWQ[4] * aw[1] + c.RWQ[5] * aw[2];
     wq[2] = c.RWQ[6] * aw[0] + c.RWQ[7] * aw[1] + c.RWQ[8] * aw[2];
   } else
-MM10_UNROLL_SLIP
+  {
+#if MM10_PREFETCH
+  double gn[9];
+  mm10_slip_load(c, 0, gn);
+#endif
+MM10_UNROLL_RESID
   for (int s = 0; s < c.nslip; ++s) {
     double ms[6], qs[3];
+#if MM10_PREFETCH
+    double g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = gn[k];
+    mm10_slip_load(c, (s + 1 < c.nslip) ? s + 1 : s, gn);
+    mm10_slip_geom_v(c, g, ms, qs);
+#else
     mm10_slip_geom(c, s, ms, qs);
+#endif
     const double rs = sig[0] * ms[0] + sig[1] * ms[1] + sig[2] * ms[2] + sig[3] * ms[3] + sig[4] * ms[4] + sig[5] * ms[5];
     const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
+    if (s < MM10_PCACHE) c.acc[s] = p;
     const double slip = dgtt * p * rs;
     const double f = rs * dif + slip;
 #pragma unroll
@@ -329,6 +485,7 @@ MM10_UNROLL_SLIP
 #pragma unroll
     for (int k = 0; k < 3; ++k) wq[k] += f * qs[k];
     sabs += fabs(slip);
+  }
   }
   double wp[3], sw[6], w1[6];
   cpf_mv3(c.RWR, wq, wp);
@@ -370,12 +527,24 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
 #pragma unroll
     for (int k = 0; k < 3; ++k) { wqs[k] = 0.0; wqf[k] = 0.0; }
     const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v, dgn = c.dg * c.rate_n / tt;
-MM10_UNROLL_SLIP
+#if MM10_PREFETCH
+    double gn[9];
+    mm10_slip_load(c, 0, gn);
+#endif
+MM10_UNROLL_JAC
     for (int s = 0; s < c.nslip; ++s) {
       double ms[6], qs[3];
+#if MM10_PREFETCH
+      double g[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g[k] = gn[k];
+      mm10_slip_load(c, (s + 1 < c.nslip) ? s + 1 : s, gn);
+      mm10_slip_geom_v(c, g, ms, qs);
+#else
       mm10_slip_geom(c, s, ms, qs);
+#endif
       const double rs = sig[0] * ms[0] + sig[1] * ms[1] + sig[2] * ms[2] + sig[3] * ms[3] + sig[4] * ms[4] + sig[5] * ms[5];
-      const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
+      const double p = (s < MM10_PCACHE) ? c.acc[s] : cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
       const double slip = dgtt * p * rs;
       const double dgdt = dgn * p + dif;
       const double f = rs * dif + slip;
@@ -502,9 +671,11 @@ CPF_DI void mts_thresholds(const Mm10Mts& m, double dgc, double* tau_y, double* 
 // mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening
 // (phase 0, 6 unknowns), then the coupled update (phase 1, 7 unknowns), as one state machine.
 // x[7] in/out.  c.J keeps the last Jacobian formed (lagged tangent).  Returns true on failure.
+// lu_piv (Voce kernels, MM10_SMEM_LU): c.J is left FACTORED (mm10_lu7_factor of the last Jacobian
+// formed), *lu_piv its pivot rows; the tangent solves with those factors.
 template <int HARD, bool LF = false>
 CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, int* it_pred, int* it_upd,
-                       double* h_last) {
+                       double* h_last, int* lu_piv) {
   const double cc = 1.0e-4, red = 0.5;
   const int mls = 10, mmin = 1;
   double y[7], dx[7], R[7];
@@ -569,7 +740,12 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, in
             for (int i = 0; i < 7; ++i) sj += c.J[7 * i + j] * R[i];
             wv[j] = sj;
           }
-          mm10_lu7_inl(c.J, -1.0, dx);
+          if (HARD == MM10_VOCE && MM10_SMEM_LU) {
+            *lu_piv = mm10_lu7_factor(c.J);
+            mm10_lu7_solve(c.J, *lu_piv, dx);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) dx[k] = -dx[k];
+          } else mm10_lu7_inl(c.J, -1.0, dx);
           double d = 0.0;
 #pragma unroll
           for (int k = 0; k < 7; ++k) d += dx[k] * wv[k];

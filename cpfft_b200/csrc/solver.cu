@@ -336,6 +336,7 @@ int cpfft_create(const cpfft_config* cfg, cpfft_handle** out) {
   for (int f = 0; f < CPFFT_NUM_FIELDS; ++f) { h->field[f] = nullptr; h->ncomp[f] = 0; }
   h->d_mats = nullptr; h->d_crys = nullptr; h->d_matidx = nullptr; h->d_grain = nullptr; h->d_grain_cry = nullptr; h->d_grains = nullptr;
   h->has_taylor = false;
+  h->uni_cry = -1; memset(&h->cr0, 0, sizeof(h->cr0));
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) h->mm10_kern[i][j] = false;
   h->d_fail = nullptr; h->d_liters = nullptr; h->d_failcnt = nullptr; h->n_fail = h->n_fail_final = 0; h->spec_a = h->spec_b = h->spec_c = nullptr; h->tw = nullptr; h->d_radices = nullptr;
   h->work9 = nullptr; h->d_partials = nullptr; h->d_scalars = nullptr; h->h_scalars = nullptr;

@@ -27,6 +27,12 @@ struct UpdArgs {
   int32_t* fail; int32_t* liters; int* failcnt;
   int64_t n3; int step, iter; double dt;
   CpfHistLayout L;
+  // The model's crystal constants when every grain refers to the same crystal-library entry
+  // (uni_cry = 1; the usual polycrystal: one crystal definition, many orientations).  The UNI
+  // kernels read them from the kernel-parameter constant bank -- instruction operands, no loads
+  // and no registers held across the Newton loop -- and the exponent test of the slip-rate power
+  // becomes warp-uniform.
+  CpfCryDev cr0; int uni_cry;
 };
 
 
@@ -78,7 +84,7 @@ CPF_DI void upd_mm01_voxel(const UpdArgs& a, const int64_t e) {
 //   mm10_a.f:2109-2175; h / estress / ehard mm10_b.f:2080-2186; tangent terms JA, JB from
 //   dgamma/dD and ed, mm10_a.f:740-810, mm10_b.f:2189-2345 -- both proportional to the strain
 //   increment, so C - JA - JB is a rank-one correction of C).
-template <bool MULTI, int HARD, bool LF = false>
+template <bool MULTI, int HARD, bool LF = false, bool UNI = false>
 CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   const CpfMatDev mp = a.mats[a.matidx[e]];
   if (mp.type != 10) return;
@@ -107,7 +113,9 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   for (int ci = 0; ci < ncry; ++ci) {
     const int co = MULTI ? ci * (L.total - L.c_stress) : 0;            // offset of this crystal's history block
     const int gi = a.grain[(MULTI ? (int64_t)ci * n3 : (int64_t)0) + e];
-    const CpfCryDev cr = a.crys[a.grain_cry[gi]];       // the grain-table entry knows its crystal (crystal_input single or file)
+    CpfCryDev cr_l;
+    if (!UNI) cr_l = a.crys[a.grain_cry[gi]];           // the grain-table entry knows its crystal (crystal_input single or file)
+    const CpfCryDev& cr = UNI ? a.cr0 : cr_l;
     const double* gt = a.grains + (int64_t)gi * CPF_GRAIN_STRIDE;
     const int nslip = cr.nslip;
     Mm10Ctx c;
@@ -227,7 +235,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
         cos_ang = fmax(p1 + p2, 0.0);
       }
       double frac = 0.0, stp = 1.0, ox[7], h_last = c.ttn;
-      int cuts = 0;
+      int cuts = 0, lu_piv = 0;
   #pragma unroll
       for (int k = 0; k < 7; ++k) ox[k] = x[k];
       while (frac < 1.0) {  // mm10_solve_strup_iterate (mm10_a.f:2759-2843)
@@ -248,7 +256,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
           c.h0 = cr.tau_a * (1.0 - mu_s / mu_n) + c.ur * (ty - ty_n) + (mu_s / mu_n) * c.ttn;
         }
         x[6] = c.ttn;
-        fail = mm10_solve<HARD, LF>(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last);
+        fail = mm10_solve<HARD, LF>(c, x, cos_ang * ttrate_n * (dt * stp), &itp, &itu, &h_last, &lu_piv);
         if (fail) {
   #pragma unroll
           for (int k = 0; k < 7; ++k) x[k] = ox[k];
@@ -321,6 +329,21 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
         // mm10_tangent (Voce: ed = 0, dgammadd = 0): T = (J11 - J12 J21 / J22)^-1 C.  The Schur
         // complement replaces the lagged Jacobian in shared memory (padded to 7x7) and the six
         // columns of C go through the kernel's single LU site one at a time.
+        if (HARD == MM10_VOCE && MM10_SMEM_LU) {
+          // The Schur complement is never formed: (J11 - J12 J21 / J22)^-1 C is the leading 6x6 block of
+          // J^-1 [C; 0], and c.J already holds the LU factors of the lagged Jacobian (the last Newton
+          // step's), so a column of the tangent is one pair of triangular solves.
+  #pragma unroll 1
+          for (int col = 0; col < 6; ++col) {
+            double b7[7];
+  #pragma unroll
+            for (int k = 0; k < 6; ++k) b7[k] = CPF_LDG(c.C + 6 * k + col);
+            b7[6] = 0.0;
+            mm10_lu7_solve(c.J, lu_piv, b7);
+  #pragma unroll
+            for (int k = 0; k < 6; ++k) c.acc[6 * k + col] = b7[k];
+          }
+        } else {
   #pragma unroll
         for (int j = 0; j < 6; ++j) {
           const double beta = c.J[42 + j] / c.J[48];
@@ -339,6 +362,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
           mm10_lu7(c.J.p, 1.0, b7);
   #pragma unroll
           for (int k = 0; k < 6; ++k) c.acc[6 * k + col] = b7[k];
+        }
         }
   #pragma unroll
         for (int k = 0; k < 36; ++k) tang[k] = c.acc[k];
@@ -462,7 +486,8 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   #pragma unroll
         for (int k = 0; k < 6; ++k) eu[k] = x[k];
         eu[6] = 0.0;
-        mm10_lu7(c.J.p, 1.0, eu);
+        if (HARD == MM10_VOCE && MM10_SMEM_LU) mm10_lu7_solve(c.J, mm10_lu7_factor(c.J), eu);
+        else mm10_lu7(c.J.p, 1.0, eu);
         // ee = RT2RVE(R) eeunrot: the stress-type operator (mm10_a.f:3538-3539), i.e. R E~ R^T
         double E[9], T[9], S2[9];
         v6_to_m3(eu, E);

@@ -59,7 +59,7 @@ class HostKernels:
     NCOMP = {"Fn": 9, "Fn1": 9, "Pn1": 9, "K4": 81, "urcs_n": 9, "urcs_n1": 9, "eps_n": 6, "eps_n1": 6,
              "rot_n1": 9, "cep": 36}
 
-    def __init__(self, prob, lattice_frame=False):
+    def __init__(self, prob, lattice_frame=True):   # the product's default (CPFFT_MM10_LF unset)
         L = _lib()
         self.L, self.prob, self.N3 = L, prob, prob.N3
         mats, crys = prob.material_pods(), prob.crystal_pods()

@@ -320,14 +320,15 @@ def test_full_solve_with_kernel_source(libs, name, nstep):
 
 
 def test_lattice_frame_residual_variant(libs):
-    """the CPFFT_MM10_LF development variant (residual slip loop in the lattice frame, mm10.cuh
-    mm10_resid<.., LF = true>) is the same algebra in another summation order: same results to
-    round-off and the SAME local iteration counts along a plastic load path with a large,
+    """the residual slip loop exists twice (mm10.cuh mm10_resid<.., LF>): in the lattice frame (the
+    product's default and the default of HostKernels, i.e. what every other test here runs) and in the
+    sample frame (CPFFT_MM10_LF=0, this test).  Same algebra in another summation order: same results
+    to round-off and the SAME local iteration counts along a plastic load path with a large,
     sub-stepped increment, and the same Newton counts / curve on the test deck."""
     from cpfft_b200.polycrystal import polycrystal
     HostKernels, Oracle = libs
     p = polycrystal(6, ngrains=20)
-    k, o = HostKernels(p, lattice_frame=True), Oracle(p)
+    k, o = HostKernels(p, lattice_frame=False), Oracle(p)
     rng = np.random.default_rng(3)
     G = rng.standard_normal((9, p.N3)); G[[0, 4, 8]] -= G[[0, 4, 8]].mean(axis=0)
     bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.45
@@ -351,7 +352,7 @@ def test_lattice_frame_residual_variant(libs):
     p = deck("test_mm10.in")
     o_ref = Oracle(p); o_ref.drive_eps_sig(1, 0)
     r = o_ref.FFT_nr3(nstep=6)
-    nr, pbar = _hybrid_FFT_nr3(HostKernels(p, lattice_frame=True), Oracle(p), p, 6)
+    nr, pbar = _hybrid_FFT_nr3(HostKernels(p, lattice_frame=False), Oracle(p), p, 6)
     assert nr == [int(v) for v in r["nr_iters"]]
     assert np.abs(pbar - r["Pbar"]).max() / np.abs(r["Pbar"]).max() <= 1e-10
 

@@ -95,9 +95,10 @@ def test_mts_deck_matches_golden():
 
 
 def test_lattice_frame_variant_in_subprocess():
-    """CPFFT_MM10_LF=1 (k_update_mm10_lf, residual slip loop in the lattice frame; the switch is read once
-    per process, hence the subprocess): same Newton / CG counts and the same curve as the default kernel
-    on the reference's crystal-plasticity deck -- the golden fixture."""
+    """CPFFT_MM10_LF=0 CPFFT_MM10_UNI=0 (k_update_mm10: residual slip loop in the sample frame, crystal
+    constants from the crystal table instead of the kernel parameters; the switches are read once per
+    process, hence the subprocess): same Newton / CG counts and the same curve as the default kernel
+    (k_update_mm10_lf_u) on the reference's crystal-plasticity deck -- the golden fixture."""
     import json
     import os
     import subprocess
@@ -108,7 +109,7 @@ def test_lattice_frame_variant_in_subprocess():
             "s = Solver(deck('test_mm10.in')); s.drive_eps_sig(1, 0); r = s.FFT_nr3()\n"
             "print('RESULT ' + json.dumps({'nr': [int(v) for v in r['nr_iters']], 'cg': [[int(v) for v in row] for row in r['cg_iters']],"
             " 'Pbar': r['Pbar'].tolist(), 'launches': s.kernel_launches()}))\n") % (here, os.path.dirname(here))
-    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CPFFT_MM10_LF="1"), capture_output=True,
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CPFFT_MM10_LF="0", CPFFT_MM10_UNI="0"), capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     got = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])

@@ -31,7 +31,7 @@ def build(name, defines):
             raise SystemExit(log.stderr[-3000:])
         lines = log.stderr.splitlines()
         for i, l in enumerate(lines):
-            if "Compiling entry function '_Z13k_update_mm107UpdArgs'" in l or ("Compiling" in l and any(k in l for k in ("k_iz_pipeILi256ELb1E", "k_fzILi320ELi3E", "k_fzILi400ELi3E", "k_fxILi400ELb0E", "k_fyfILi400ELb0E", "k_fyiILi400E"))):
+            if "Compiling entry function '_Z15k_update_mm10_u7UpdArgs'" in l or "Compiling entry function '_Z18k_update_mm10_lf_u7UpdArgs'" in l or ("Compiling" in l and any(k in l for k in ("k_iz_pipeILi256ELb1E", "k_fzILi320ELi3E", "k_fzILi400ELi3E", "k_fxILi400ELb0E", "k_fyfILi400ELb0E", "k_fyiILi400E"))):
                 print(name, "|", lines[i + 2].strip(), "|", lines[i + 3].strip())
         objs.append(obj)
     # the other translation units are the default build's objects

@@ -33,7 +33,7 @@ case "$MODE" in
         -s 16 -c 6 -f -o gpurun_out/prof_${TAG}_cg python tools/ncu_cg.py 256 > gpurun_out/${TAG}_ncu_cg.log 2>&1
     tail -3 gpurun_out/${TAG}_ncu_cg.log; ls -la gpurun_out/prof_${TAG}_cg.ncu-rep ;;
   ncu-update)
-    timeout 280 ncu --set full --clock-control none --import-source on -k 'regex:^(k_update_mm10|k_pk1_tangent)$' -s 4 -c 2 -f \
+    timeout 280 ncu --set full --clock-control none --import-source on -k 'regex:^(k_update_mm10[a-z_]*|k_pk1_tangent)$' -s 4 -c 2 -f \
         -o gpurun_out/prof_${TAG}_update python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_update.log 2>&1
     tail -3 gpurun_out/${TAG}_ncu_update.log; ls -la gpurun_out/prof_${TAG}_update.ncu-rep ;;
   ab)
@@ -42,6 +42,19 @@ case "$MODE" in
     (timeout 60 python tools/time_update.py 128; CPFFT_MM10_LF=1 timeout 60 python tools/time_update.py 128) 2>&1 | tail -4 | tee gpurun_out/${TAG}_ab_lf.log ;;
   mm10ab)   # A/B of libcpfft_b200.so variants built by tools/build_variants.py (gpurun_variants/lib_*.so): material sweep at 128^3
     for lib in gpurun_variants/lib_*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 2>&1 | tail -1; done | tee gpurun_out/${TAG}_mm10ab.log ;;
+  mm10ab2)  # round-2 k_update_mm10 changes: HEAD~ library vs the new one with its switches, then the LF-unroll variants
+    L=$PWD/gpurun_variants
+    ( CPFFT_B200_LIB=$L/lib_base.so timeout 90 python tools/time_update.py 128 2>&1 | tail -1
+      CPFFT_B200_LIB=$L/lib_new.so CPFFT_MM10_UNI=0 timeout 90 python tools/time_update.py 128 2>&1 | tail -1
+      CPFFT_B200_LIB=$L/lib_new.so timeout 90 python tools/time_update.py 128 2>&1 | tail -1
+      CPFFT_B200_LIB=$L/lib_new.so CPFFT_MM10_LF=1 timeout 90 python tools/time_update.py 128 2>&1 | tail -1
+      for v in ${3:-lfu2 lfu3 lfu4}; do CPFFT_B200_LIB=$L/lib_$v.so CPFFT_MM10_LF=1 timeout 90 python tools/time_update.py 128 2>&1 | tail -1; done
+    ) | tee gpurun_out/${TAG}_mm10ab.log ;;
+  mm10ab3)  # every library variant under gpurun_variants/, default and lattice-frame residual
+    for lib in gpurun_variants/lib_*.so; do
+      CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py ${3:-128} 2>&1 | tail -1
+      CPFFT_B200_LIB=$PWD/$lib CPFFT_MM10_LF=1 timeout 90 python tools/time_update.py ${3:-128} 2>&1 | tail -1
+    done | tee gpurun_out/${TAG}_mm10ab.log ;;
   izab)     # A/B of the inverse z pass occupancy variants (gpurun_variants/lib_iz*.so) at 256^3
     for lib in gpurun_variants/lib_iz*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_apply.py 256 2>&1 | tail -2; done | tee gpurun_out/${TAG}_izab.log ;;
   scale)    # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then bench.py as the driver launches it

@@ -36,6 +36,8 @@ def main(grid, paths, merge=None):
             name = d["Kernel Name"][0]
             base = name.replace("void ", "").split("<")[0].split("(")[0]
             cls = CLASS.get(base, base)
+            if base.startswith("k_update_mm10"):      # k_update_mm10[_lf][_u], _taylor, _mts: one profiler class
+                cls = "k_update_mm10"
             if base == "k_fz":
                 cls = "k_fwd_z_K4" if any(("<%d, %d>" % (grid, m)) in name for m in (1, 2, 3)) else "k_fwd_z"
             ent = {"kernel": name, "report": p.split("/")[-1],

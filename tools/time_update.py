@@ -20,5 +20,6 @@ for it in range(5):
     s.drive_eps_sig(4, 1)
 t = s.profile_table()
 P = s.download("PN1")
-print(os.environ.get("CPFFT_B200_LIB", "default"), "LF" if os.environ.get("CPFFT_MM10_LF") == "1" else "std", "N", N, {k: round(v[0] / max(v[1], 1), 3) for k, v in t.items() if v[1]},
+print(os.path.basename(os.environ.get("CPFFT_B200_LIB", "default")), "std" if os.environ.get("CPFFT_MM10_LF") == "0" else "LF",
+      "nouni" if os.environ.get("CPFFT_MM10_UNI") == "0" else "uni", "N", N, {k: round(v[0] / max(v[1], 1), 3) for k, v in t.items() if v[1]},
       "checksum", float(np.abs(P).sum()), "fail", s.material_failures(), "iters", s.local_iters().mean(axis=0))
