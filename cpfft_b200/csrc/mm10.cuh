@@ -234,6 +234,8 @@ CPF_DNOINLINE void mm10_lu7(const double* Jp, double sign, double* b) {
 #ifndef MM10_SMEM_LU
 #define MM10_SMEM_LU 1
 #endif
+// (Keeping the row loops rolled takes ~400 instructions out of the Newton loop's instruction-cache
+// footprint but measured 3 % slower, profiles/r02u_mm10ab_fp64lat.log.)
 CPF_DI int mm10_lu7_factor(SArr J) {
   int pack = 0;
 #pragma unroll
@@ -357,6 +359,45 @@ CPF_DI void mm10_slip_geom_v(const Mm10Ctx& c, const double* g, double* ms, doub
   qs[2] = c.RWQ[6] * w0 + c.RWQ[7] * w1 + c.RWQ[8] * w2;
 }
 
+// The map of mm10_slip_geom, ms = L ms0 with L = RT2RVE(Rp_n^T) (6x6, linear), applied to whole sums instead of
+// per system.  mm10_to_lattice: y = L^T sig, so that rs = sig . ms = y . ms0 (Sh = stress tensor with halved
+// shears, Y = Q^T Sh Q, shear entries of y doubled).  mm10_from_lattice: out = L a = V6(Q A~ Q^T), A~ the
+// symmetric tensor whose Voigt vector (no shear doubling) is a.
+CPF_DI void mm10_to_lattice(const Mm10Ctx& c, const double* sig, double* y) {
+  const double h3 = 0.5 * sig[3], h4 = 0.5 * sig[4], h5 = 0.5 * sig[5];
+  double U[9];   // U = Sh Q
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const double q0 = c.Q[b], q1 = c.Q[3 + b], q2 = c.Q[6 + b];
+    U[b] = sig[0] * q0 + h3 * q1 + h5 * q2;
+    U[3 + b] = h3 * q0 + sig[1] * q1 + h4 * q2;
+    U[6 + b] = h5 * q0 + h4 * q1 + sig[2] * q2;
+  }
+  // Y = Q^T U, Voigt with doubled shears
+  y[0] = c.Q[0] * U[0] + c.Q[3] * U[3] + c.Q[6] * U[6];
+  y[1] = c.Q[1] * U[1] + c.Q[4] * U[4] + c.Q[7] * U[7];
+  y[2] = c.Q[2] * U[2] + c.Q[5] * U[5] + c.Q[8] * U[8];
+  y[3] = 2.0 * (c.Q[0] * U[1] + c.Q[3] * U[4] + c.Q[6] * U[7]);
+  y[4] = 2.0 * (c.Q[1] * U[2] + c.Q[4] * U[5] + c.Q[7] * U[8]);
+  y[5] = 2.0 * (c.Q[0] * U[2] + c.Q[3] * U[5] + c.Q[6] * U[8]);
+}
+CPF_DI void mm10_from_lattice(const Mm10Ctx& c, const double* am, double* out) {
+  double T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double a = c.Q[3 * i], b = c.Q[3 * i + 1], d = c.Q[3 * i + 2];
+    T[3 * i + 0] = a * am[0] + b * am[3] + d * am[5];
+    T[3 * i + 1] = a * am[3] + b * am[1] + d * am[4];
+    T[3 * i + 2] = a * am[5] + b * am[4] + d * am[2];
+  }
+  out[0] = T[0] * c.Q[0] + T[1] * c.Q[1] + T[2] * c.Q[2];
+  out[1] = T[3] * c.Q[3] + T[4] * c.Q[4] + T[5] * c.Q[5];
+  out[2] = T[6] * c.Q[6] + T[7] * c.Q[7] + T[8] * c.Q[8];
+  out[3] = T[0] * c.Q[3] + T[1] * c.Q[4] + T[2] * c.Q[5];
+  out[4] = T[3] * c.Q[6] + T[4] * c.Q[7] + T[5] * c.Q[8];
+  out[5] = T[0] * c.Q[6] + T[1] * c.Q[7] + T[2] * c.Q[8];
+}
+
 template <int HARD>
 CPF_DI double mm10_hfac(const Mm10Ctx& c, double tt, double* hterm_out) {
   if (HARD == MM10_MTS) {
@@ -389,24 +430,7 @@ CPF_DI double mm10_resid(const Mm10Ctx& c, const double* sig, double tt, double*
   const double itt = 1.0 / tt, dgtt = c.dg / tt, dif = c.tinc * c.iD_v;
   if (LF) {
     double y[6];
-    {
-      const double h3 = 0.5 * sig[3], h4 = 0.5 * sig[4], h5 = 0.5 * sig[5];
-      double U[9];   // U = Sh Q
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const double q0 = c.Q[b], q1 = c.Q[3 + b], q2 = c.Q[6 + b];
-        U[b] = sig[0] * q0 + h3 * q1 + h5 * q2;
-        U[3 + b] = h3 * q0 + sig[1] * q1 + h4 * q2;
-        U[6 + b] = h5 * q0 + h4 * q1 + sig[2] * q2;
-      }
-      // Y = Q^T U, Voigt with doubled shears
-      y[0] = c.Q[0] * U[0] + c.Q[3] * U[3] + c.Q[6] * U[6];
-      y[1] = c.Q[1] * U[1] + c.Q[4] * U[4] + c.Q[7] * U[7];
-      y[2] = c.Q[2] * U[2] + c.Q[5] * U[5] + c.Q[8] * U[8];
-      y[3] = 2.0 * (c.Q[0] * U[1] + c.Q[3] * U[4] + c.Q[6] * U[7]);
-      y[4] = 2.0 * (c.Q[1] * U[2] + c.Q[4] * U[5] + c.Q[7] * U[8]);
-      y[5] = 2.0 * (c.Q[0] * U[2] + c.Q[3] * U[5] + c.Q[6] * U[8]);
-    }
+    mm10_to_lattice(c, sig, y);
     double am[6] = {0, 0, 0, 0, 0, 0}, aw[3] = {0, 0, 0};
 #if MM10_PREFETCH
     double gn[9];
@@ -440,23 +464,8 @@ MM10_UNROLL_LF
       sabs += fabs(slip);
     }
     // dbarp = V6(Q A~ Q^T), wq = RWQ aw  (the maps of mm10_slip_geom applied to the sums)
-    double T[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double a = c.Q[3 * i], b = c.Q[3 * i + 1], d = c.Q[3 * i + 2];
-      T[3 * i + 0] = a * am[0] + b * am[3] + d * am[5];
-      T[3 * i + 1] = a * am[3] + b * am[1] + d * am[4];
-      T[3 * i + 2] = a * am[5] + b * am[4] + d * am[2];
-    }
-    dbarp[0] = T[0] * c.Q[0] + T[1] * c.Q[1] + T[2] * c.Q[2];
-    dbarp[1] = T[3] * c.Q[3] + T[4] * c.Q[4] + T[5] * c.Q[5];
-    dbarp[2] = T[6] * c.Q[6] + T[7] * c.Q[7] + T[8] * c.Q[8];
-    dbarp[3] = T[0] * c.Q[3] + T[1] * c.Q[4] + T[2] * c.Q[5];
-    dbarp[4] = T[3] * c.Q[6] + T[4] * c.Q[7] + T[5] * c.Q[8];
-    dbarp[5] = T[0] * c.Q[6] + T[1] * c.Q[7] + T[2] * c.Q[8];
-    wq[0] = c.RWQ[0] * aw[0] + c.RWQ[1] * aw[1] + c.RWQ[2] * aw[2];
-    wq[1] = c.RWQ[3] * aw[0] + c.RWQ[4] * aw[1] + c.RWQ[5] * aw[2];
-    wq[2] = c.RWQ[6] * aw[0] + c.RWQ[7] * aw[1] + c.RWQ[8] * aw[2];
+    mm10_from_lattice(c, am, dbarp);
+    cpf_mv3(c.RWQ, aw, wq);
   } else
   {
 #if MM10_PREFETCH
@@ -513,6 +522,8 @@ MM10_UNROLL_RESID
 
 // Jacobian (mm10_formJ) into c.J (7x7 row-major, shared memory).  full = false: J11 only
 // (stress predictor), padded with an identity row / column.
+// (Forming the slip sums in the lattice frame, as the residual does, and mapping S, T and the four vectors back
+// costs what it saves for 12 systems and measured 7 % slower for 48, profiles/r02u_mm10ab_fp64lat.log: not kept.)
 template <int HARD>
 CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool full) {
   double dps[6], wqs[3], wqf[3], es[6], sabs = 0.0, ssum = 0.0;

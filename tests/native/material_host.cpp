@@ -88,6 +88,12 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
   a.mats = m->T.md.data(); a.crys = m->T.cd.data(); a.grains = m->T.gtab.data();
   a.fail = m->fail.data(); a.liters = m->liters.data(); a.failcnt = m->failcnt;
   a.n3 = m->n3; a.step = step; a.iter = iter; a.dt = m->dt; a.L = m->T.L;
+  // one crystal-library entry behind every grain: the product launches the _u kernels (constants from the kernel parameters)
+  bool uni = m->T.has_mm10 && !m->T.gcry.empty();
+  for (int32_t ci : m->T.gcry) uni = uni && ci == m->T.gcry[0];
+  a.uni_cry = uni ? 1 : 0;
+  std::memset(&a.cr0, 0, sizeof(a.cr0));
+  if (uni) a.cr0 = m->T.cd[m->T.gcry[0]];
   m->failcnt[1] = 0;
   const int64_t n3 = m->n3;
 #pragma omp parallel for schedule(dynamic, 64)
@@ -100,7 +106,8 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
         if (mp.ncry > 1) upd_mm10_voxel<true, MM10_MTS>(a, e, sm);
         else upd_mm10_voxel<false, MM10_MTS>(a, e, sm);
       } else if (mp.ncry > 1) upd_mm10_voxel<true, MM10_VOCE>(a, e, sm);
-      else if (m->lattice_frame) upd_mm10_voxel<false, MM10_VOCE, true>(a, e, sm);
+      else if (m->lattice_frame && uni) upd_mm10_voxel<false, MM10_VOCE, true, true>(a, e, sm);                             // k_update_mm10_lf_u
+      else if (m->lattice_frame) upd_mm10_voxel<false, MM10_VOCE, true>(a, e, sm);                                          // k_update_mm10_lf
       else upd_mm10_voxel<false, MM10_VOCE>(a, e, sm);
     }
     // even voxels: [D] in registers (the kernel's default), odd voxels: the memory-resident variant

@@ -26,15 +26,15 @@ case "$MODE" in
     tail -c 400 gpurun_out/${TAG}_bench256.json ;;
   launches)
     timeout 180 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_${TAG}.csv \
-        python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+        python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity --stress-leg-steps 0 > gpurun_out/${TAG}_ncu_bench.log 2>&1
     python tools/ncu_summary.py gpurun_out/launches_${TAG}.csv | head -24 ;;
   ncu-cg)
     timeout 100 ncu --set full --clock-control none --import-source on -k 'regex:^(k_fz|k_fyf|k_fx|k_fyi|k_iz_pipe|k_cg_update_r)$' \
         -s 16 -c 6 -f -o gpurun_out/prof_${TAG}_cg python tools/ncu_cg.py 256 > gpurun_out/${TAG}_ncu_cg.log 2>&1
     tail -3 gpurun_out/${TAG}_ncu_cg.log; ls -la gpurun_out/prof_${TAG}_cg.ncu-rep ;;
   ncu-update)
-    timeout 280 ncu --set full --clock-control none --import-source on -k 'regex:^(k_update_mm10[a-z_]*|k_pk1_tangent)$' -s 4 -c 2 -f \
-        -o gpurun_out/prof_${TAG}_update python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_update.log 2>&1
+    timeout 280 ncu --set full --clock-control none --import-source on -k 'regex:^(k_update_mm10[a-z_]*|k_pk1_tangent)$' -s 14 -c 2 -f \
+        -o gpurun_out/prof_${TAG}_update python bench.py --grid 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity --stress-leg-steps 0 > gpurun_out/${TAG}_ncu_update.log 2>&1
     tail -3 gpurun_out/${TAG}_ncu_update.log; ls -la gpurun_out/prof_${TAG}_update.ncu-rep ;;
   ab)
     timeout 100 python tools/ab_iz.py 256 10 2>&1 | tail -8 | tee gpurun_out/${TAG}_ab256.log ;;
@@ -55,6 +55,13 @@ case "$MODE" in
       CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py ${3:-128} 2>&1 | tail -1
       CPFFT_B200_LIB=$PWD/$lib CPFFT_MM10_LF=1 timeout 90 python tools/time_update.py ${3:-128} 2>&1 | tail -1
     done | tee gpurun_out/${TAG}_mm10ab.log ;;
+  mm10ab4)  # variants x (fcc, bcc48 with and without the lattice-frame Jacobian); FP64 latency microbenchmark
+    ( [ -x gpurun_variants/fp64_latency ] && timeout 60 gpurun_variants/fp64_latency
+      for lib in gpurun_variants/lib_*.so; do
+        CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 2>&1 | tail -1
+        CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_update.py 128 bcc48 2>&1 | tail -1
+      done
+    ) | tee gpurun_out/${TAG}_mm10ab.log ;;
   izab)     # A/B of the inverse z pass occupancy variants (gpurun_variants/lib_iz*.so) at 256^3
     for lib in gpurun_variants/lib_iz*.so; do CPFFT_B200_LIB=$PWD/$lib timeout 90 python tools/time_apply.py 256 2>&1 | tail -2; done | tee gpurun_out/${TAG}_izab.log ;;
   scale)    # N-GPU call (gpurun --gpus N): correctness against the 1-GPU run, then bench.py as the driver launches it

@@ -7,7 +7,8 @@ from cpfft_b200 import Solver
 from cpfft_b200.polycrystal import polycrystal
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-p = polycrystal(N, ngrains=200)
+SLIP = sys.argv[2] if len(sys.argv) > 2 else "fcc"           # fcc | bcc48
+p = polycrystal(N, ngrains=200, slip_type={"fcc": 1, "bcc48": 8}[SLIP])
 s = Solver(p)
 s.drive_eps_sig(1, 0)
 s.FFT_nr3(nstep=3)
@@ -21,5 +22,5 @@ for it in range(5):
 t = s.profile_table()
 P = s.download("PN1")
 print(os.path.basename(os.environ.get("CPFFT_B200_LIB", "default")), "std" if os.environ.get("CPFFT_MM10_LF") == "0" else "LF",
-      "nouni" if os.environ.get("CPFFT_MM10_UNI") == "0" else "uni", "N", N, {k: round(v[0] / max(v[1], 1), 3) for k, v in t.items() if v[1]},
+      "nouni" if os.environ.get("CPFFT_MM10_UNI") == "0" else "uni", SLIP, "N", N, {k: round(v[0] / max(v[1], 1), 3) for k, v in t.items() if v[1]},
       "checksum", float(np.abs(P).sum()), "fail", s.material_failures(), "iters", s.local_iters().mean(axis=0))
