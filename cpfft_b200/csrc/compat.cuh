@@ -9,6 +9,8 @@
 #define CPF_DI __device__ __forceinline__
 #define CPF_DNOINLINE static __device__ __noinline__
 #define CPF_LDG(p) __ldg(p)
+// two consecutive doubles with one 16-byte load (p 16-byte aligned)
+#define CPF_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
 #define CPF_ANY_SYNC(mask, pred) __any_sync(mask, pred)
 #define CPF_ACTIVEMASK() __activemask()
 #define CPF_ATOMIC_INC(p) atomicAdd(p, 1)
@@ -22,6 +24,7 @@ using std::fabs; using std::sqrt; using std::fmax; using std::isnan;
 #define CPF_DI inline
 #define CPF_DNOINLINE static
 #define CPF_LDG(p) (*(p))
+#define CPF_LDG2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
 #define CPF_ANY_SYNC(mask, pred) (pred)          // one "lane" per call on the host
 #define CPF_ACTIVEMASK() 1u
 #define CPF_ATOMIC_INC(p) __atomic_fetch_add(p, 1, __ATOMIC_RELAXED)

@@ -184,7 +184,7 @@ static int cpf_build_material_tables(const std::vector<cpfft_material>& mats, co
         vn[i] = tr[i][0] * ni[ci][3 * s] + tr[i][1] * ni[ci][3 * s + 1] + tr[i][2] * ni[ci][3 * s + 2];
       }
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = vb[i] * vn[j];
-      double* o = t + CPF_GRAIN_B + 9 * s;
+      double* o = t + CPF_GRAIN_B + CPF_SLIP_STRIDE * s;
       o[0] = 0.5 * (A[0][0] + A[0][0]); o[1] = 0.5 * (A[1][1] + A[1][1]); o[2] = 0.5 * (A[2][2] + A[2][2]);
       o[3] = 2.0 * (0.5 * (A[0][1] + A[1][0])); o[4] = 2.0 * (0.5 * (A[1][2] + A[2][1])); o[5] = 2.0 * (0.5 * (A[0][2] + A[2][0]));
       o[6] = 0.5 * (A[1][2] - A[2][1]); o[7] = 0.5 * (A[0][2] - A[2][0]); o[8] = 0.5 * (A[0][1] - A[1][0]);

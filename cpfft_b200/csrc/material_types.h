@@ -32,14 +32,27 @@ struct CpfCryDev {
 };
 
 // per-grain (unique crystal+orientation) table entry, device, doubles:
-//   [0..8] g (row-major), [9..44] rotated stiffness C (row-major 6x6),
-//   [45 + 9 s ..): ms0[6] (engineering-shear Schmid vector), qs0[3] (skew vector) of system s,
-//   [45 + 9*48 ..+3): the Kocks angles in degrees
+//   g (9, row-major), rotated stiffness C (36, row-major 6x6), per slip system ms0[6] (engineering-shear Schmid
+//   vector) + qs0[3] (skew vector), the Kocks angles in degrees (3).
+// CPF_TAB_VEC = 1: C and the slip entries start on 16-byte boundaries and a slip entry is padded to 10 doubles, so the
+// kernels fetch them with 16-byte loads (half the load instructions of the hot loops); 0: packed layout, 8-byte loads.
+#ifndef CPF_TAB_VEC
+#define CPF_TAB_VEC 1
+#endif
 #define CPF_GRAIN_G 0
+#if CPF_TAB_VEC
+#define CPF_SLIP_STRIDE 10
+#define CPF_GRAIN_C 10
+#define CPF_GRAIN_B 46
+#define CPF_GRAIN_ANG (CPF_GRAIN_B + CPF_SLIP_STRIDE * CPF_MAX_SLIP)
+#define CPF_GRAIN_STRIDE (CPF_GRAIN_ANG + 4)     // even: every entry of the table starts 16-byte aligned
+#else
+#define CPF_SLIP_STRIDE 9
 #define CPF_GRAIN_C 9
 #define CPF_GRAIN_B 45
-#define CPF_GRAIN_ANG (45 + 9 * CPF_MAX_SLIP)   // Kocks angles (degrees) of the grain
-#define CPF_GRAIN_STRIDE (48 + 9 * CPF_MAX_SLIP)
+#define CPF_GRAIN_ANG (CPF_GRAIN_B + CPF_SLIP_STRIDE * CPF_MAX_SLIP)   // Kocks angles (degrees) of the grain
+#define CPF_GRAIN_STRIDE (CPF_GRAIN_ANG + 3)
+#endif
 
 
 // mm10_d.f:137-331

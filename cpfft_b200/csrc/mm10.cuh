@@ -327,9 +327,26 @@ struct Mm10Ctx {
 // tensor form ms = V6( Q M~ Q^T ) with M~ the symmetric tensor whose Voigt vector (no shear
 // doubling) is ms0, Q = Rp_n^T; that is what is evaluated here (45 FMA, no 6x6 operator).
 CPF_DI void mm10_slip_load(const Mm10Ctx& c, int s, double* g) {
-  const double* t = c.ms0 + 9 * s;
+  const double* t = c.ms0 + CPF_SLIP_STRIDE * s;
+#if CPF_TAB_VEC
+  double pad;
+  CPF_LDG2(t, g[0], g[1]); CPF_LDG2(t + 2, g[2], g[3]); CPF_LDG2(t + 4, g[4], g[5]); CPF_LDG2(t + 6, g[6], g[7]);
+  CPF_LDG2(t + 8, g[8], pad);
+  (void)pad;
+#else
 #pragma unroll
   for (int k = 0; k < 9; ++k) g[k] = CPF_LDG(t + k);
+#endif
+}
+// row i of the grain's rotated stiffness
+CPF_DI void mm10_c_row(const Mm10Ctx& c, int i, double* r) {
+  const double* t = c.C + 6 * i;
+#if CPF_TAB_VEC
+  CPF_LDG2(t, r[0], r[1]); CPF_LDG2(t + 2, r[2], r[3]); CPF_LDG2(t + 4, r[4], r[5]);
+#else
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r[k] = CPF_LDG(t + k);
+#endif
 }
 CPF_DI void mm10_slip_geom_v(const Mm10Ctx& c, const double* g, double* ms, double* qs);
 CPF_DI void mm10_slip_geom(const Mm10Ctx& c, int s, double* ms, double* qs) {
@@ -446,11 +463,12 @@ MM10_UNROLL_LF
       for (int k = 0; k < 3; ++k) w[k] = gn[6 + k];
       mm10_slip_load(c, (s + 1 < c.nslip) ? s + 1 : s, gn);
 #else
-      const double* t = c.ms0 + 9 * s;
+      double g9[9];
+      mm10_slip_load(c, s, g9);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) m[k] = CPF_LDG(t + k);
+      for (int k = 0; k < 6; ++k) m[k] = g9[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) w[k] = CPF_LDG(t + 6 + k);
+      for (int k = 0; k < 3; ++k) w[k] = g9[6 + k];
 #endif
       const double rs = y[0] * m[0] + y[1] * m[1] + y[2] * m[2] + y[3] * m[3] + y[4] * m[4] + y[5] * m[5];
       const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
@@ -503,9 +521,10 @@ MM10_UNROLL_RESID
   for (int k = 0; k < 6; ++k) w1[k] = c.D[k] - dbarp[k];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    double s = 0.0;
+    double s = 0.0, cr[6];
+    mm10_c_row(c, i, cr);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) s += CPF_LDG(c.C + 6 * i + j) * w1[j];
+    for (int j = 0; j < 6; ++j) s += cr[j] * w1[j];
     R[i] = sig[i] - c.sn[i] - s + 2.0 * sw[i];
   }
   double h = 0.0;
@@ -604,9 +623,10 @@ MM10_UNROLL_JAC
     cpf_symsw(sig, tc, sw);
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      double s = 2.0 * sw[a];
+      double s = 2.0 * sw[a], cr[6];
+      mm10_c_row(c, a, cr);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += CPF_LDG(c.C + 6 * a + k) * scol[k];
+      for (int k = 0; k < 6; ++k) s += cr[k] * scol[k];
       c.J[7 * a + b] = s;
     }
   }
@@ -630,9 +650,10 @@ MM10_UNROLL_JAC
     const double nt = -c.rate_n / tt;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      double s = 2.0 * sw[a];
+      double s = 2.0 * sw[a], cr[6];
+      mm10_c_row(c, a, cr);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += CPF_LDG(c.C + 6 * a + k) * dps[k];
+      for (int k = 0; k < 6; ++k) s += cr[k] * dps[k];
       c.J[7 * a + 6] = nt * s;
     }
     // J21 = -theta0 dg n / tt * hfac * sum sgn(rs) |rs/tt|^(n-1) ms
