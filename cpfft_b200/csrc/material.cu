@@ -42,6 +42,8 @@ MM10_KERNEL(k_update_mm10_lf, false, MM10_VOCE, true, false)
 MM10_KERNEL(k_update_mm10_lf_u, false, MM10_VOCE, true, true)
 MM10_KERNEL(k_update_mm10_taylor, true, MM10_VOCE, false, false)        // n_crystals > 1: Taylor average
 MM10_KERNEL(k_update_mm10_taylor_u, true, MM10_VOCE, false, true)
+MM10_KERNEL(k_update_mm10_taylor_lf, true, MM10_VOCE, true, false)
+MM10_KERNEL(k_update_mm10_taylor_lf_u, true, MM10_VOCE, true, true)
 MM10_KERNEL(k_update_mm10_mts, false, MM10_MTS, false, false)           // `hardening mts`: same source, other law
 MM10_KERNEL(k_update_mm10_mts_u, false, MM10_MTS, false, true)
 MM10_KERNEL(k_update_mm10_taylor_mts, true, MM10_MTS, false, false)
@@ -131,9 +133,9 @@ int cpf_launch_update(cpfft_handle* h, int step, int iter) {
     a.uni_cry = uni ? 1 : 0;
     a.cr0 = h->cr0;
     const Kern kerns_t[2][2][3] = {{{nullptr, lf ? k_update_mm10_lf : k_update_mm10, k_update_mm10_mts},
-                                    {nullptr, k_update_mm10_taylor, k_update_mm10_taylor_mts}},
+                                    {nullptr, lf ? k_update_mm10_taylor_lf : k_update_mm10_taylor, k_update_mm10_taylor_mts}},
                                    {{nullptr, lf ? k_update_mm10_lf_u : k_update_mm10_u, k_update_mm10_mts_u},
-                                    {nullptr, k_update_mm10_taylor_u, k_update_mm10_taylor_mts_u}}};
+                                    {nullptr, lf ? k_update_mm10_taylor_lf_u : k_update_mm10_taylor_u, k_update_mm10_taylor_mts_u}}};
     const auto& kerns = kerns_t[uni ? 1 : 0];
     const size_t smem = sizeof(double) * MM10_SMEM_DOUBLES * UPD_THREADS;
     for (int multi = 0; multi < 2; ++multi)

@@ -52,9 +52,11 @@
 #define MM10_UNROLL_JAC MM10_UNROLL_SLIP_(MM10_JAC_UNROLL)
 // MM10_PREFETCH: the nine grain-table entries of slip system s + 1 are loaded while system s is
 // being processed (the loops are not unrolled, so the compiler cannot overlap the load latency
-// of one trip with the arithmetic of the previous one by itself).
+// of one trip with the arithmetic of the previous one by itself).  1: into a second buffer, copied
+// at the top of the trip; 2 (default): in the Jacobian, whose geometry step is the only consumer of
+// the entry, right after that step into the same registers (no copy).  0: plain loads.
 #ifndef MM10_PREFETCH
-#define MM10_PREFETCH 1
+#define MM10_PREFETCH 2
 #endif
 // the lattice-frame residual loop is short (per system 9 loads, a 6-term dot product, the power, 9 FMA):
 // unrolled, the loads of several systems are in flight together
@@ -564,7 +566,12 @@ CPF_DI void mm10_jacobian(const Mm10Ctx& c, const double* sig, double tt, bool f
 MM10_UNROLL_JAC
     for (int s = 0; s < c.nslip; ++s) {
       double ms[6], qs[3];
-#if MM10_PREFETCH
+#if MM10_PREFETCH == 2
+      // the geometry is the only consumer of the table entry: the next one is requested right after it, into the
+      // same registers, and lands under the ~110 instructions of the slip sums
+      mm10_slip_geom_v(c, gn, ms, qs);
+      mm10_slip_load(c, (s + 1 < c.nslip) ? s + 1 : s, gn);
+#elif MM10_PREFETCH
       double g[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) g[k] = gn[k];

@@ -105,7 +105,9 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
       if (mp.hard == MM10_MTS) {
         if (mp.ncry > 1) upd_mm10_voxel<true, MM10_MTS>(a, e, sm);
         else upd_mm10_voxel<false, MM10_MTS>(a, e, sm);
-      } else if (mp.ncry > 1) upd_mm10_voxel<true, MM10_VOCE>(a, e, sm);
+      } else if (mp.ncry > 1 && m->lattice_frame && uni) upd_mm10_voxel<true, MM10_VOCE, true, true>(a, e, sm);   // k_update_mm10_taylor_lf_u
+      else if (mp.ncry > 1 && m->lattice_frame) upd_mm10_voxel<true, MM10_VOCE, true>(a, e, sm);                  // k_update_mm10_taylor_lf
+      else if (mp.ncry > 1) upd_mm10_voxel<true, MM10_VOCE>(a, e, sm);
       else if (m->lattice_frame && uni) upd_mm10_voxel<false, MM10_VOCE, true, true>(a, e, sm);                             // k_update_mm10_lf_u
       else if (m->lattice_frame) upd_mm10_voxel<false, MM10_VOCE, true>(a, e, sm);                                          // k_update_mm10_lf
       else upd_mm10_voxel<false, MM10_VOCE>(a, e, sm);
