@@ -240,14 +240,15 @@ def stage_rooflines(table, N, n3, cgits, nsolves, world, fp64_peak):
                 if "fp64_flop" in ent and fp64_peak and world == 1:
                     # FP64 rate of the PROFILED launch: its own flop count over its own duration (the
                     # profiled k_update_mm10 launch is a plastic sweep; elastic iter-0 sweeps are a class of their own)
+                    # (this run's launches of the class do other amounts of work -- the material sweeps differ in their
+                    # Newton iteration counts -- so the capture's flop count is never divided by this run's times)
                     dur = ent.get("duration_us")
                     tf_ncu = ent["fp64_flop"] / (dur * 1e-6) / 1e12 if dur else None
-                    tf_live = ent["fp64_flop"] / (stages[name]["ms_per_launch"] * 1e-3) / 1e12
                     stages[name].update({"fp64_flop_per_launch_ncu": ent["fp64_flop"], "ncu_duration_us": dur,
-                                         "fp64_tflops_ncu_launch": tf_ncu, "fp64_tflops": tf_live,
+                                         "fp64_tflops_ncu_launch": tf_ncu, "fp64_tflops": tf_ncu,
                                          "fp64_peak_tflops_measured": fp64_peak,
                                          "frac_of_fp64_ncu_launch": tf_ncu / fp64_peak if tf_ncu else None,
-                                         "frac_of_fp64": tf_live / fp64_peak})
+                                         "frac_of_fp64": tf_ncu / fp64_peak if tf_ncu else None})
     cand = [k for k in stages if "achieved_gbs" in stages[k]]
     dom = max(cand, key=lambda k: stages[k]["ms_total"]) if cand else None
     roof = None
