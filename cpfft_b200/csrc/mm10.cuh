@@ -16,19 +16,29 @@
 //    (RW(R Rp^T) = RW(R) RW(Rp^T)), so qc is never formed per system;
 //  * the Jacobian blocks are assembled from slip-system sums (S = sum dgdt m (x) m etc.) and
 //    multiplied by the stiffness once, instead of a DGER per system;
-//  * |rs/tt|^(n-1) is evaluated ONCE per system per evaluation (the reference calls
-//    mm10_slipinc up to three times) and by repeated squaring when n-1 is a small integer.
+//  * |rs/tt|^(n-1) is evaluated ONCE per system per point (the reference calls mm10_slipinc up
+//    to three times per evaluation): by straight-line square-and-multiply when n-1 is a small
+//    integer, in the residual, which leaves the values in shared memory for the Jacobian;
+//  * the residual's slip loop runs in the lattice frame (LF, the default): the stress is mapped
+//    once (rs_s = (L^T sigma) . ms0_s), the plastic strain / spin sums are formed on (ms0, qs0)
+//    and mapped back once -- both maps are linear, so this is the same algebra in another
+//    summation order (equal to round-off);
+//  * the 7x7 systems are factorised in shared memory (mm10_lu7_factor / mm10_lu7_solve); the
+//    tangent reuses the factors of the last Newton step instead of forming and factorising the
+//    Schur complement six times (equal to round-off).
 // Control flow that decides iteration counts (tolerances, Armijo test, at least one update
 // iteration, lagged Jacobian for the tangent, sub-stepping) follows the reference exactly.
 //
 // Code layout.  The first version of this kernel was instruction-fetch bound (17 k SASS
 // instructions, instruction-cache hit rate 56 %, "no instruction" the top stall reason in ncu).
 // Now the stress predictor (6 unknowns) and the coupled update (7 unknowns) of mm10_solve run
-// through ONE Newton state machine with one residual site, one Jacobian site and one
-// non-inlined 7x7 LU; the predictor pads its system with an identity row / column, which
-// leaves the arithmetic of the first six unknowns bit-identical.  The tangent (6 right-hand
-// sides) and the lattice-strain solve reuse the same LU.  Libm functions with long inline
-// expansions sit behind non-inlined wrappers.
+// through ONE Newton state machine with one residual site, one Jacobian site and one LU site;
+// the predictor pads its system with an identity row / column, which leaves the arithmetic of
+// the first six unknowns bit-identical.  Libm functions with long inline expansions sit behind
+// non-inlined wrappers.  Round 2 (ncu source page, profiles/r02r_update_hotspots.md): the loop
+// is still ~2.6 k instructions (42 KB > the 32 KB L1.5 I-cache), the kernel is bound by issue
+// latency at 2 warps per scheduler (255 registers); the changes listed above removed a quarter
+// of the executed instructions, the grain-table loads are requested one slip system ahead.
 #pragma once
 #include "kin.cuh"
 #include "material_types.h"
