@@ -93,6 +93,10 @@ struct SArr {
 // between the two.  Saves half of the power evaluations; the values are the ones the Jacobian
 // would recompute, bit for bit.
 #define MM10_PCACHE 39
+// MTS kernels: acc[MM10_SM_STASH .. +7) keeps column 7 of the last Jacobian (J12, J22) next to its LU factors --
+// their tangent needs the raw entries (mm10_a.f:760-805) -- so the hand-over uses the slots below it
+#define MM10_SM_STASH 32
+#define MM10_PC(HARD) ((HARD) == MM10_MTS ? MM10_SM_STASH : MM10_PCACHE)
 
 CPF_DNOINLINE double cpf_pow(double x, double y) { return pow(x, y); }
 CPF_DNOINLINE double cpf_atan2(double y, double x) { return atan2(y, x); }
@@ -148,104 +152,20 @@ CPF_DI void cpf_mv3(const Mat& M, const double* v, double* o) {
   o[2] = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
 }
 
-// Dense solve with partial pivoting (stand-in for DGESV), A is N x N row-major, B is N x NR.
-template <int N, int NR>
-CPF_DI void cpf_lu_solve(double* A, double* B) {
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    int piv = k;
-    double best = fabs(A[k * N + k]);
-#pragma unroll
-    for (int i = k + 1; i < N; ++i) {
-      double v = fabs(A[i * N + k]);
-      if (v > best) { best = v; piv = i; }
-    }
-    // row interchange by value selects (an `if (i == piv) swap` chain is turned into run-time
-    // indexed accesses by the optimiser, which demotes the whole matrix to local memory).
-    // Skipping the selects when the pivot is already in place (`if (piv != k)`, the common case)
-    // measured 4 % SLOWER (profiles/r02c_mm10ab.log: 21.4 vs 20.5 ms at 128^3): the branch costs
-    // more than the ~90 predicated selects it saves.
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const double top = A[k * N + j];
-      double pv = top;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
-        const double cur = A[i * N + j];
-        pv = (piv == i) ? cur : pv;
-        A[i * N + j] = (piv == i) ? top : cur;
-      }
-      A[k * N + j] = pv;
-    }
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      const double top = B[k * NR + j];
-      double pv = top;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
-        const double cur = B[i * NR + j];
-        pv = (piv == i) ? cur : pv;
-        B[i * NR + j] = (piv == i) ? top : cur;
-      }
-      B[k * NR + j] = pv;
-    }
-    const double inv = 1.0 / A[k * N + k];
-#pragma unroll
-    for (int i = k + 1; i < N; ++i) {
-      const double l = A[i * N + k] * inv;
-#pragma unroll
-      for (int j = k + 1; j < N; ++j) A[i * N + j] -= l * A[k * N + j];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) B[i * NR + j] -= l * B[k * NR + j];
-    }
-  }
-#pragma unroll
-  for (int k = N - 1; k >= 0; --k) {
-    const double inv = 1.0 / A[k * N + k];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      double s = B[k * NR + j];
-#pragma unroll
-      for (int c = k + 1; c < N; ++c) s -= A[k * N + c] * B[c * NR + j];
-      B[k * NR + j] = s * inv;
-    }
-  }
-}
-
-// The one LU site of the kernel: b <- (sign * J)^-1 b for the 7x7 matrix held in shared
-// memory (left untouched).  Systems of 6 unknowns are padded with an identity row / column.
-CPF_DI void mm10_lu7_inl(SArr J, double sign, double* b) {
-  double M[49];
-#pragma unroll
-  for (int k = 0; k < 49; ++k) M[k] = sign * J[k];
-  cpf_lu_solve<7, 1>(M, b);
-}
-// out-of-line copy for the cold call sites (tangent columns, lattice strain): a call makes the
-// caller spill its live registers, which the Newton loop cannot afford but the epilogue can
-CPF_DNOINLINE void mm10_lu7(const double* Jp, double sign, double* b) {
-  SArr J; J.p = const_cast<double*>(Jp);
-  double x[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) x[k] = b[k];
-  mm10_lu7_inl(J, sign, x);
-#pragma unroll
-  for (int k = 0; k < 7; ++k) b[k] = x[k];
-}
-
-// ---- the 7x7 LU in shared memory (Voce kernels) ------------------------------------------------
-// mm10_lu7_factor: in-place factorisation of the matrix in J with partial pivoting in DGETRF's
-// order -- whole-row interchanges, unit-lower multipliers below the diagonal -- and the RECIPROCAL
-// of the pivot on the diagonal.  Shared memory can be indexed at run time, registers cannot: the
-// row interchange is two indexed rows behind a (rare, 1 % per column) branch instead of the
-// ~530 predicated selects cpf_lu_solve spends on every call, and the 49 entries no longer sit in
-// 98 registers.  Returns the pivot rows, 3 bits each.
+// ---- the 7x7 LU in shared memory ----------------------------------------------------------------
+// Dense solve with partial pivoting, the stand-in for DGESV (mm10_solve, mm10_tangent, the lattice strain).
+// mm10_lu7_factor: in-place factorisation of the matrix in J in DGETRF's order -- whole-row
+// interchanges, unit-lower multipliers below the diagonal -- and the RECIPROCAL of the pivot on the
+// diagonal.  Shared memory can be indexed at run time, registers cannot: the row interchange is two
+// indexed rows behind a (rare, 1 % per column) branch.  The first version of this kernel kept the
+// matrix in 98 registers and interchanged rows by ~530 predicated selects per solve (an `if (i ==
+// piv) swap` chain is turned into run-time indexed accesses by the optimiser, which demotes the
+// whole matrix to local memory): 17 % of all executed instructions, and the tangent repeated the
+// factorisation for each of its six right-hand sides.  Returns the pivot rows, 3 bits each.
 // mm10_lu7_solve: b <- A^-1 b from those factors (row interchanges, forward, back substitution).
-// The arithmetic on every entry is cpf_lu_solve's, operation for operation (l = a_ik * (1/a_kk),
-// a_ij -= l a_kj, b_i -= l b_k, x_k = (b_k - sum a_kc x_c) * (1/a_kk)): same results bit for bit,
-// and (-A)^-1 b == -(A^-1 b) exactly, so the Newton step solves with J and negates.
-#ifndef MM10_SMEM_LU
-#define MM10_SMEM_LU 1
-#endif
+// The arithmetic on every entry is Gaussian elimination's, operation for operation (l = a_ik *
+// (1/a_kk), a_ij -= l a_kj, b_i -= l b_k, x_k = (b_k - sum a_kc x_c) * (1/a_kk)), and (-A)^-1 b ==
+// -(A^-1 b) exactly, so the Newton step solves with J and negates.
 // (Keeping the row loops rolled takes ~400 instructions out of the Newton loop's instruction-cache
 // footprint but measured 3 % slower, profiles/r02u_mm10ab_fp64lat.log.)
 CPF_DI int mm10_lu7_factor(SArr J) {
@@ -484,7 +404,7 @@ MM10_UNROLL_LF
 #endif
       const double rs = y[0] * m[0] + y[1] * m[1] + y[2] * m[2] + y[3] * m[3] + y[4] * m[4] + y[5] * m[5];
       const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
-      if (s < MM10_PCACHE) c.acc[s] = p;
+      if (s < MM10_PC(HARD)) c.acc[s] = p;
       const double slip = dgtt * p * rs;
       const double f = rs * dif + slip;
 #pragma unroll
@@ -516,7 +436,7 @@ MM10_UNROLL_RESID
 #endif
     const double rs = sig[0] * ms[0] + sig[1] * ms[1] + sig[2] * ms[2] + sig[3] * ms[3] + sig[4] * ms[4] + sig[5] * ms[5];
     const double p = cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
-    if (s < MM10_PCACHE) c.acc[s] = p;
+    if (s < MM10_PC(HARD)) c.acc[s] = p;
     const double slip = dgtt * p * rs;
     const double f = rs * dif + slip;
 #pragma unroll
@@ -591,7 +511,7 @@ MM10_UNROLL_JAC
       mm10_slip_geom(c, s, ms, qs);
 #endif
       const double rs = sig[0] * ms[0] + sig[1] * ms[1] + sig[2] * ms[2] + sig[3] * ms[3] + sig[4] * ms[4] + sig[5] * ms[5];
-      const double p = (s < MM10_PCACHE) ? c.acc[s] : cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
+      const double p = (s < MM10_PC(HARD)) ? c.acc[s] : cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0);
       const double slip = dgtt * p * rs;
       const double dgdt = dgn * p + dif;
       const double f = rs * dif + slip;
@@ -720,8 +640,8 @@ CPF_DI void mts_thresholds(const Mm10Mts& m, double dgc, double* tau_y, double* 
 // mm10_solve (mm10_a.f:2860-3295): predictor on the stress with extrapolated hardening
 // (phase 0, 6 unknowns), then the coupled update (phase 1, 7 unknowns), as one state machine.
 // x[7] in/out.  c.J keeps the last Jacobian formed (lagged tangent).  Returns true on failure.
-// lu_piv (Voce kernels, MM10_SMEM_LU): c.J is left FACTORED (mm10_lu7_factor of the last Jacobian
-// formed), *lu_piv its pivot rows; the tangent solves with those factors.
+// c.J is left FACTORED (mm10_lu7_factor of the last Jacobian formed), *lu_piv its pivot rows; the
+// tangent solves with those factors.
 template <int HARD, bool LF = false>
 CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, int* it_pred, int* it_upd,
                        double* h_last, int* lu_piv) {
@@ -789,12 +709,14 @@ CPF_DI bool mm10_solve(const Mm10Ctx& c, double* x, double cos_ang_ttrate_dt, in
             for (int i = 0; i < 7; ++i) sj += c.J[7 * i + j] * R[i];
             wv[j] = sj;
           }
-          if (HARD == MM10_VOCE && MM10_SMEM_LU) {
-            *lu_piv = mm10_lu7_factor(c.J);
-            mm10_lu7_solve(c.J, *lu_piv, dx);
+          if (HARD == MM10_MTS) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) dx[k] = -dx[k];
-          } else mm10_lu7_inl(c.J, -1.0, dx);
+            for (int k = 0; k < 7; ++k) c.acc[MM10_SM_STASH + k] = c.J[7 * k + 6];
+          }
+          *lu_piv = mm10_lu7_factor(c.J);
+          mm10_lu7_solve(c.J, *lu_piv, dx);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) dx[k] = -dx[k];
           double d = 0.0;
 #pragma unroll
           for (int k = 0; k < 7; ++k) d += dx[k] * wv[k];

@@ -316,58 +316,34 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
           const double bm1 = cpf_pow(base, c.voche_m - 1.0);
           const double ce = c.theta_0 * c.ur * ((c.voche_m / c.tau_v * bm1) * cy + (c.voche_m / (c.tau_v * c.tau_v) * scc * bm1) * cv +
                                                alpha * (bm1 * base)) * sabs + c.ur * cy;
-          const double j22 = c.J[48];
+          const double j22 = c.acc[MM10_SM_STASH + 6];     // raw J12, J22 of the lagged Jacobian (c.J holds its LU factors)
   #pragma unroll
           for (int i = 0; i < 6; ++i) {
             double va = 2.0 * sw[i];
   #pragma unroll
             for (int k = 0; k < 6; ++k) va += CPF_LDG(c.C + 6 * i + k) * dps[k];
-            wv[i] = alpha * va + (ce / j22) * c.J[7 * i + 6];
+            wv[i] = alpha * va + (ce / j22) * c.acc[MM10_SM_STASH + i];
             dmod[i] = (i < 3) ? de[i] : 0.5 * de[i];
           }
         }
         // mm10_tangent (Voce: ed = 0, dgammadd = 0): T = (J11 - J12 J21 / J22)^-1 C.  The Schur
-        // complement replaces the lagged Jacobian in shared memory (padded to 7x7) and the six
-        // columns of C go through the kernel's single LU site one at a time.
-        if (HARD == MM10_VOCE && MM10_SMEM_LU) {
-          // The Schur complement is never formed: (J11 - J12 J21 / J22)^-1 C is the leading 6x6 block of
-          // J^-1 [C; 0], and c.J already holds the LU factors of the lagged Jacobian (the last Newton
-          // step's), so a column of the tangent is one pair of triangular solves.
-  #pragma unroll 1
-          for (int col = 0; col < 6; ++col) {
-            double b7[7];
-  #pragma unroll
-            for (int k = 0; k < 6; ++k) b7[k] = CPF_LDG(c.C + 6 * k + col);
-            b7[6] = 0.0;
-            mm10_lu7_solve(c.J, lu_piv, b7);
-  #pragma unroll
-            for (int k = 0; k < 6; ++k) c.acc[6 * k + col] = b7[k];
-          }
-        } else {
-  #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const double beta = c.J[42 + j] / c.J[48];
-  #pragma unroll
-          for (int i = 0; i < 6; ++i) c.J[7 * i + j] = c.J[7 * i + j] - c.J[7 * i + 6] * beta;
-        }
-  #pragma unroll
-        for (int k = 0; k < 6; ++k) { c.J[7 * k + 6] = 0.0; c.J[42 + k] = 0.0; }
-        c.J[48] = 1.0;
+        // complement is never formed: (J11 - J12 J21 / J22)^-1 B is the leading 6 rows of J^-1 [B; 0], and
+        // c.J already holds the LU factors of the lagged Jacobian (the last Newton step's), so a column
+        // of the tangent is one pair of triangular solves.
+        if (HARD == MM10_MTS) mm10_lu7_solve(c.J, lu_piv, wv);      // JJ^-1 w (w was formed from the stashed J12, J22 above)
   #pragma unroll 1
         for (int col = 0; col < 6; ++col) {
           double b7[7];
   #pragma unroll
           for (int k = 0; k < 6; ++k) b7[k] = CPF_LDG(c.C + 6 * k + col);
           b7[6] = 0.0;
-          mm10_lu7(c.J.p, 1.0, b7);
+          mm10_lu7_solve(c.J, lu_piv, b7);
   #pragma unroll
           for (int k = 0; k < 6; ++k) c.acc[6 * k + col] = b7[k];
-        }
         }
   #pragma unroll
         for (int k = 0; k < 36; ++k) tang[k] = c.acc[k];
         if (HARD == MM10_MTS) {       // T = JJ^-1 C - (JJ^-1 w) (x) d_mod
-          mm10_lu7(c.J.p, 1.0, wv);
   #pragma unroll
           for (int i = 0; i < 6; ++i)
   #pragma unroll
@@ -486,8 +462,7 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
   #pragma unroll
         for (int k = 0; k < 6; ++k) eu[k] = x[k];
         eu[6] = 0.0;
-        if (HARD == MM10_VOCE && MM10_SMEM_LU) mm10_lu7_solve(c.J, mm10_lu7_factor(c.J), eu);
-        else mm10_lu7(c.J.p, 1.0, eu);
+        mm10_lu7_solve(c.J, mm10_lu7_factor(c.J), eu);
         // ee = RT2RVE(R) eeunrot: the stress-type operator (mm10_a.f:3538-3539), i.e. R E~ R^T
         double E[9], T[9], S2[9];
         v6_to_m3(eu, E);
