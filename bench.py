@@ -388,8 +388,12 @@ def main():
     Event = torch.cuda.Event
     nvox = float(N) ** 3
 
+    # load increment: 1 % strain over 10 steps; the MTS variant's parameter set needs quarter-size steps -- with 0.1 % its
+    # global Newton loop does not converge on grids >= 64^3, in the oracle either (profiles/r02z_mtsdiag.log)
+    steps_per_percent = 40 if args.variant == "mts" else 10
+
     def make_solver(sbc, nsteps):
-        prob = polycrystal(N, ngrains=args.grains, nstep=max(10, nsteps + 2), x_range=(rank * nx, (rank + 1) * nx), stress_bc=sbc)
+        prob = polycrystal(N, ngrains=args.grains, nstep=max(steps_per_percent, nsteps + 2), x_range=(rank * nx, (rank + 1) * nx), stress_bc=sbc)
         if args.variant != "voce":
             from cpfft_b200.polycrystal import workload_variant
             prob = workload_variant(prob, args.variant, args.grains)
@@ -512,7 +516,7 @@ def main():
                                "finite-strain uniaxial tension, " +
                                ("F_xx driven with P_yy = P_zz = 0 (stress-BC loop + tangent_homo)" if stress_bc else
                                 "strain-controlled variant of SURVEY.md 8d for the K timed steps (F_yy = F_zz = -0.3 F_xx); the stress-BC loading of 8d "
-                                "is measured by the bounded leg `stress_bc_leg` of this line") + ", 0.1 % per load step",
+                                "is measured by the bounded leg `stress_bc_leg` of this line") + f", {1.0 / steps_per_percent:g} % per load step",
                    "grid": N, "voxels": int(nvox), "voxels_per_gpu": int(s.n3), "parallelism": f"x-slabs x{world}",
                    "l2": "working set (>= 1.2 GB per field) far exceeds the 126 MB L2; no flush needed",
                    "step": "one FFT_nr3 load step", "newton_iters_per_step": nr_hist,
