@@ -48,6 +48,9 @@ def _lib():
         L.mh_drive_eps_sig.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.mh_update.argtypes = [C.c_void_p]
         L.mh_set_lattice_frame.argtypes = [C.c_void_p, C.c_int]
+        L.mh_lu7.argtypes = [dp, dp]
+        L.mh_pow_abs.restype = C.c_double
+        L.mh_pow_abs.argtypes = [C.c_double, C.c_int, C.c_double]
         _LIB = L
     return _LIB
 

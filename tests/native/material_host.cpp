@@ -120,6 +120,18 @@ int mh_drive_eps_sig(mh_model* m, int step, int iter) {
   return m->failcnt[1];
 }
 
+// building blocks of the mm10 kernels, exported for direct tests
+// A (7x7 row-major) x = b by the kernels' shared-memory LU (mm10_lu7_factor / mm10_lu7_solve); returns the packed pivot rows
+int mh_lu7(const double* A, double* b) {
+  double J[49];
+  for (int k = 0; k < 49; ++k) J[k] = A[k];
+  SArr Ja; Ja.p = J;                       // MM10_THREADS = 1 on the host: element k at J[k]
+  const int piv = mm10_lu7_factor(Ja);
+  mm10_lu7_solve(Ja, piv, b);
+  return piv;
+}
+double mh_pow_abs(double x, int ie, double fe) { return cpf_pow_abs(x, ie, fe); }
+
 // update.f:75-106 (history, eps, urcs) -- on the device a pointer swap in cpfft_commit_step
 void mh_update(mh_model* m) {
   m->hist_n = m->hist_n1; m->eps_n = m->eps_n1; m->urcs_n = m->urcs_n1;

@@ -426,3 +426,55 @@ def test_material_table_errors(libs, capfd):
         with pytest.raises(RuntimeError):
             HostKernels(p)
         assert msg in capfd.readouterr().err
+
+
+def test_shared_memory_lu_against_numpy():
+    """mm10_lu7_factor / mm10_lu7_solve (the 7x7 solve of the Newton step, the tangent and the lattice strain): random
+    matrices that need row interchanges in every column pattern, against numpy's LAPACK solve, and the pivot rows
+    against a plain partial-pivoting elimination (first maximum wins, as in DGETRF)."""
+    import ctypes as C
+    from host_kernels import _lib
+    L = _lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(11)
+    swaps = 0
+    for trial in range(400):
+        A = rng.standard_normal((7, 7))
+        if trial % 4 == 0:
+            A += 8.0 * np.eye(7)                       # diagonally dominant: no interchange at all
+        if trial % 4 == 1:
+            A[:, rng.integers(0, 7)] *= 1e3            # one badly scaled column
+        b = rng.standard_normal(7)
+        x = b.copy()
+        piv = L.mh_lu7(np.ascontiguousarray(A).ctypes.data_as(dp), x.ctypes.data_as(dp))
+        ref = np.linalg.solve(A, b)
+        assert np.abs(x - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()) * np.linalg.cond(A)
+        # pivot rows of a textbook elimination
+        M = A.copy(); want = 0
+        for k in range(7):
+            p = k + int(np.argmax(np.abs(M[k:, k])))
+            want |= p << (3 * k)
+            M[[k, p]] = M[[p, k]]
+            for i in range(k + 1, 7):
+                M[i, k:] -= M[i, k] / M[k, k] * M[k, k:]
+        assert piv == want
+        swaps += sum(((piv >> (3 * k)) & 7) != k for k in range(7))
+    assert swaps > 400                                 # the interchange path was exercised
+
+
+def test_integer_power_matches_repeated_squaring():
+    """cpf_pow_abs: the straight-line square-and-multiply equals the loop it replaced bit for bit for every
+    exponent 0..64, and falls back to pow() for non-integer exponents"""
+    from host_kernels import _lib
+    L = _lib()
+    rng = np.random.default_rng(5)
+    for x in list(rng.uniform(0.0, 1.3, 40)) + [0.0, 1.0]:
+        for ie in range(65):
+            r, b, e = 1.0, float(x), ie
+            while e:
+                if e & 1:
+                    r *= b
+                b *= b
+                e >>= 1
+            assert L.mh_pow_abs(float(x), ie, float(ie)) == r
+    assert abs(L.mh_pow_abs(0.7, -1, 18.5) - 0.7 ** 18.5) <= 1e-15
