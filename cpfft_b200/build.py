@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libcpfft_b200.so")
-SOURCES = ["material.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu"]
+SOURCES = ["material.cu", "material_taylor.cu", "material_mts.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.check_call([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj])
         return obj
 
-    # the four translation units are independent: compile them side by side, then link
+    # the translation units are independent: compile them side by side, then link
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
     tmp = LIB + f".tmp{os.getpid()}"      # link aside, then rename: a concurrent reader never sees a partial file

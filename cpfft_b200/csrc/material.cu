@@ -6,16 +6,7 @@
 //
 // All state is structure-of-arrays field[comp * n3 + voxel]; consecutive threads touch
 // consecutive voxels so every load/store is coalesced.
-#include "common.cuh"
-#ifndef UPD_THREADS
-#define UPD_THREADS 128
-#endif
-#ifndef MM10_MIN_CTAS
-#define MM10_MIN_CTAS 2     // 255 registers; 3 CTAs (168 registers) spill and run 1.5x slower
-#endif
-#define MM10_THREADS UPD_THREADS
-#define PK1_THREADS UPD_THREADS
-#include "update.cuh"
+#include "material_kernels.cuh"
 #include "material_tables.hpp"
 
 
@@ -25,29 +16,12 @@ __global__ void __launch_bounds__(UPD_THREADS) k_update_mm01(UpdArgs a) {
   upd_mm01_voxel(a, e);
 }
 
-// The mm10 sweep kernels: (one crystal per point | Taylor point) x (Voce | MTS), each compiled twice --
-// crystal constants per voxel from the crystal table, or (suffix _u) from the kernel parameters when the
-// whole model uses one crystal-library entry (UpdArgs::uni_cry).  k_update_mm10_lf*: residual slip loop
-// in the lattice frame (mm10_resid<.., LF = true>), the default; CPFFT_MM10_LF=0 selects the sample-frame loop.
-#define MM10_KERNEL(name, MULTI, HARD, LF, UNI)                                                       \
-  __global__ void __launch_bounds__(UPD_THREADS, MM10_MIN_CTAS) name(const __grid_constant__ UpdArgs a) { \
-    extern __shared__ double mm10_sm[];                                                               \
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                                 \
-    if (e >= a.n3) return;                                                                            \
-    upd_mm10_voxel<MULTI, HARD, LF, UNI>(a, e, mm10_sm + threadIdx.x);                                \
-  }
+// one crystal per material point, Voce hardening: the benchmark's kernels (the Taylor-point and MTS kernels are
+// compiled in material_taylor.cu / material_mts.cu, side by side with this file)
 MM10_KERNEL(k_update_mm10, false, MM10_VOCE, false, false)
 MM10_KERNEL(k_update_mm10_u, false, MM10_VOCE, false, true)
 MM10_KERNEL(k_update_mm10_lf, false, MM10_VOCE, true, false)
 MM10_KERNEL(k_update_mm10_lf_u, false, MM10_VOCE, true, true)
-MM10_KERNEL(k_update_mm10_taylor, true, MM10_VOCE, false, false)        // n_crystals > 1: Taylor average
-MM10_KERNEL(k_update_mm10_taylor_u, true, MM10_VOCE, false, true)
-MM10_KERNEL(k_update_mm10_taylor_lf, true, MM10_VOCE, true, false)
-MM10_KERNEL(k_update_mm10_taylor_lf_u, true, MM10_VOCE, true, true)
-MM10_KERNEL(k_update_mm10_mts, false, MM10_MTS, false, false)           // `hardening mts`: same source, other law
-MM10_KERNEL(k_update_mm10_mts_u, false, MM10_MTS, false, true)
-MM10_KERNEL(k_update_mm10_taylor_mts, true, MM10_MTS, false, false)
-MM10_KERNEL(k_update_mm10_taylor_mts_u, true, MM10_MTS, false, true)
 
 __global__ void __launch_bounds__(UPD_THREADS) k_pk1_tangent(const double* Fn, const double* Fn1, const double* urcs_n1,
                                                               const double* cep, double* Pn1, double* K4, int64_t n3) {

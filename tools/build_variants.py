@@ -20,7 +20,7 @@ OUT = os.path.join(ROOT, "gpurun_variants")
 def build(name, defines):
     objdir = os.path.join(OUT, "obj_" + name)
     os.makedirs(objdir, exist_ok=True)
-    tus = [d[3:] for d in defines if d.startswith("tu=")] or ["material.cu"]
+    tus = [d[3:] for d in defines if d.startswith("tu=")] or ["material.cu", "material_taylor.cu", "material_mts.cu"]
     defines = [d for d in defines if not d.startswith("tu=")]
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + defines + ["-Xptxas", "-v"]
     objs = []
@@ -36,7 +36,7 @@ def build(name, defines):
         objs.append(obj)
     # the other translation units are the default build's objects
     base = os.path.join(ROOT, "cpfft_b200", "build")
-    objs += [os.path.join(base, f[:-3] + ".o") for f in ("material.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu") if f not in tus]
+    objs += [os.path.join(base, f[:-3] + ".o") for f in ("material.cu", "material_taylor.cu", "material_mts.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu") if f not in tus]
     lib = os.path.join(OUT, f"lib_{name}.so")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-ldl"])
     return lib
