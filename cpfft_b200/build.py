@@ -9,7 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libcpfft_b200.so")
-SOURCES = ["material.cu", "material_taylor.cu", "material_mts.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu"]
+SOURCES = ["material.cu", "material_taylor.cu", "material_mts.cu", "spectral.cu", "spectral_pow2.cu",
+           "spectral_pow2_g1.cu", "spectral_pow2_g2.cu", "spectral_pow2_g3.cu", "solver.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

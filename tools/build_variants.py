@@ -3,7 +3,7 @@
 gpurun_variants/ (travels to the GPU box; git-ignored) for A/B timing with CPFFT_B200_LIB=...:
 
     python tools/build_variants.py t64c4:-DUPD_THREADS=64,-DMM10_MIN_CTAS=4 unroll2:-DMM10_SLIP_UNROLL=2
-    python tools/build_variants.py iz5:tu=spectral_pow2.cu,-DIZ_MINB=5      # another translation unit
+    python tools/build_variants.py iz5:tu=spectral_pow2_g1.cu,-DIZ_MINB=5   # another translation unit (256^3 lives in group 1)
 """
 import os
 import subprocess
@@ -36,7 +36,8 @@ def build(name, defines):
         objs.append(obj)
     # the other translation units are the default build's objects
     base = os.path.join(ROOT, "cpfft_b200", "build")
-    objs += [os.path.join(base, f[:-3] + ".o") for f in ("material.cu", "material_taylor.cu", "material_mts.cu", "spectral.cu", "spectral_pow2.cu", "solver.cu") if f not in tus]
+    objs += [os.path.join(base, f[:-3] + ".o") for f in ("material.cu", "material_taylor.cu", "material_mts.cu", "spectral.cu", "spectral_pow2.cu",
+                                                                 "spectral_pow2_g1.cu", "spectral_pow2_g2.cu", "spectral_pow2_g3.cu", "solver.cu") if f not in tus]
     lib = os.path.join(OUT, f"lib_{name}.so")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-ldl"])
     return lib
