@@ -478,3 +478,34 @@ def test_integer_power_matches_repeated_squaring():
                 e >>= 1
             assert L.mh_pow_abs(float(x), ie, float(ie)) == r
     assert abs(L.mh_pow_abs(0.7, -1, 18.5) - 0.7 ** 18.5) <= 1e-15
+
+
+def test_mts_with_48_systems_partial_handover(libs):
+    """MTS hardening on the 48-system bcc family: the residual hands |rs/tt|^(n-1) to the Jacobian for the first
+    32 systems only (slots 32..38 of the shared `acc` tile hold the stashed J12 / J22 of the factored Jacobian,
+    mm10.cuh MM10_SM_STASH), the other 16 are recomputed -- same results and local iteration counts as the oracle."""
+    import dataclasses
+    from cpfft_b200.polycrystal import polycrystal, workload_variant
+    HostKernels, Oracle = libs
+    p = workload_variant(polycrystal(5, ngrains=12), "mts", 12)
+    p.crystals = [dataclasses.replace(p.crystals[0], slip_type=8)]
+    k, o = HostKernels(p), Oracle(p)
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((9, p.N3)); G[[0, 4, 8]] -= G[[0, 4, 8]].mean(axis=0)
+    bar = np.zeros((9, 1)); bar[0] = 1.0; bar[4] = bar[8] = -0.45
+    I = np.zeros((9, p.N3)); I[[0, 4, 8]] = 1.0
+    k.drive_eps_sig(1, 0); o.drive_eps_sig(1, 0)
+    plastic = 0
+    for step, amp in enumerate((0.001, 0.002, 0.003, 0.01), start=1):
+        for it, frac in ((0, 0.9), (1, 1.0)):
+            F = I + amp * frac * (bar + 0.3 * G)
+            k.Fn1[:] = F; o.Fn1[:] = F
+            assert k.drive_eps_sig(step, it) == o.drive_eps_sig(step, it)
+            ok = np.ctypeslib.as_array(o.L.orc_fail_flags(o.h), shape=(o.N3,)) == 0
+            assert relerr(k.urcs_n1.T[ok], o.urcs_n1[ok]) <= TOL_SMALL_STRAIN
+            assert relerr(k.K4[:, ok], o.K4[:, ok]) <= TOL_SMALL_STRAIN
+            assert np.array_equal(k.local_iters, o.local_iters)
+            plastic += int(o.local_iters[:, 1].sum())
+        k.Fn[:] = k.Fn1; o.Fn[:] = o.Fn1
+        k.update(); o.update()
+    assert plastic > 0
