@@ -62,6 +62,8 @@ def _lib():
         L.orc_FFT_nr3_from.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, ip, ip, ip, C.c_int, dp, dp,
                                        C.POINTER(C.c_int64)]
         L.orc_rtcmp1.argtypes = [dp, dp]
+        L.orc_getrm1.argtypes = [dp, C.c_int, dp]
+        L.orc_ddot42_point.argtypes = [dp, dp, dp]
         L.orc_set_polar_precision.argtypes = [C.c_int]
         L.orc_cep2A.argtypes = [dp, dp, dp, dp, dp]
         L.orc_point_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
@@ -200,6 +202,20 @@ class Oracle:
         R = np.zeros(9)
         _lib().orc_rtcmp1(_dp(F), _dp(R))
         return R.reshape(3, 3)
+
+    @staticmethod
+    def getrm1(R, opt):
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+        q = np.zeros(36)
+        _lib().orc_getrm1(_dp(R), int(opt), _dp(q))
+        return q.reshape(6, 6)
+
+    @staticmethod
+    def ddot42_point(A81, B9):
+        a, b = (np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (A81, B9))
+        c = np.zeros(9)
+        _lib().orc_ddot42_point(_dp(a), _dp(b), _dp(c))
+        return c
 
     @staticmethod
     def cep2A(Fn, Fn1, t6, cep):

@@ -695,6 +695,16 @@ extern "C" void orc_rtcmp1(const double* F9, double* R9) {
   rtcmp1(f, r);
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R9[3 * i + j] = r[i][j];
 }
+// unit probes for tests/test_reference_vectors.py: getrm1 (polar.f:680-802) and the summation tree of ddot42n (G_K_dF.f:241-268)
+extern "C" void orc_getrm1(const double* R9, int opt, double* q36) {
+  M33 r; M66 q;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i][j] = R9[3 * i + j];
+  getrm1(q, r, opt);
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) q36[6 * i + j] = q[i][j];
+}
+extern "C" void orc_ddot42_point(const double* A81, const double* B9, double* C9) {
+  ddot42_point([&](int col) { return A81[col]; }, B9, C9);
+}
 extern "C" void orc_cep2A(const double* Fn9, const double* Fn19, const double* t6, const double* cep36, double* A81) {
   M33 fn, fn1, fnh, rnh, R, fnhinv, fn1inv, t; M66 C;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { fn[i][j] = Fn9[3 * i + j]; fn1[i][j] = Fn19[3 * i + j]; fnh[i][j] = 0.5 * (fn[i][j] + fn1[i][j]); }
