@@ -17,13 +17,20 @@
  * --impl reference legs may load this library.  The product
  * (cpfft_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, no tests and cannot
- * be built here (ifort + MKL).  The oracle is pinned only by derived
- * identities (tests/test_oracle_*.py, tests/test_py_mm10.py): Green-operator
- * projection identities, independent numpy restatements of G_K_dF and of the
- * mm10 / Voce crystal update (same Newton iteration counts), finite-difference
- * checks of cep2A / cnst1 / the local Jacobian / mm10_tangent, the degenerate
- * case MTS == Voce, homogeneous-deck behaviour.
+ * PARITY: the reference ships no golden vectors, no tests and cannot be built
+ * here (ifort + MKL).  PINNED by outputs of the reference's own source, executed
+ * statement by statement by tools/fortran_subset.py (fixture
+ * tests/golden/reference_vectors.npz, tests/test_reference_vectors.py): rtcmp1
+ * (polar.f), getrm1, cep2A_a, mm10_rotation_matrix, mm10_RT2RVE / RT2RVW,
+ * mm10_symSW, formG (odd N) and the summation tree of ddot42n.  UNPINNED: the
+ * drivers on derived types and MKL solvers (mm10_solve, FFT_nr3, fftPcg, mm01);
+ * those are held only by derived identities (tests/test_oracle_*.py,
+ * tests/test_py_mm10.py): Green-operator projection identities, independent
+ * numpy restatements of G_K_dF and of the mm10 / Voce crystal update (same
+ * Newton iteration counts), finite-difference checks of cep2A / cnst1 / the
+ * local Jacobian / mm10_tangent, the degenerate case MTS == Voce,
+ * homogeneous-deck behaviour -- and by the slot for a maintainer's ifort run
+ * (tests/golden/reference_run/).
  */
 #ifndef CPFFT_ORACLE_H
 #define CPFFT_ORACLE_H
