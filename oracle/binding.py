@@ -75,6 +75,9 @@ def _lib():
     return _LIB
 
 
+_DP = C.POINTER(C.c_double)
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -253,6 +256,33 @@ class Oracle:
         _lib().orc_mm10_residual_jacobian(C.addressof(pod), _dp(a[0]), _dp(a[1]), float(dt), _dp(a[2]), _dp(a[3]),
                                           float(n_tt), _dp(R), _dp(J))
         return R, J.reshape(7, 7)
+
+    @staticmethod
+    def mm10_residual_jacobian_rot(crystal, angles, D6, dt, x7, n_stress, n_tt, Rp, R):
+        """as mm10_residual_jacobian, with the plastic rotation Rp_n and the polar rotation R of the step; also returns
+        the current Schmid vectors ms (nslip, 6), qs, qc (nslip, 3) of mm10_setup"""
+        pod = crystal.pod()
+        a = [np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (angles, D6, x7, n_stress, Rp, R)]
+        Rv, J = np.zeros(7), np.zeros(49)
+        ms, qs, qc = np.zeros(48 * 6), np.zeros(48 * 3), np.zeros(48 * 3)
+        L = _lib()
+        L.orc_mm10_residual_jacobian_rot.argtypes = [C.c_void_p, _DP, _DP, C.c_double, _DP, _DP, C.c_double, _DP, _DP, _DP, _DP, _DP, _DP, _DP]
+        L.orc_mm10_residual_jacobian_rot(C.addressof(pod), _dp(a[0]), _dp(a[1]), float(dt), _dp(a[2]), _dp(a[3]), float(n_tt),
+                                         _dp(a[4]), _dp(a[5]), _dp(Rv), _dp(J), _dp(ms), _dp(qs), _dp(qc))
+        return Rv, J.reshape(7, 7), ms.reshape(48, 6), qs.reshape(48, 3), qc.reshape(48, 3)
+
+    @staticmethod
+    def mm10_crystal_probe(crystal, angles, dt, R, D6, it, n_state):
+        """the whole update of one crystal from an explicit n state (orc_mm10_crystal_probe): dict of the n+1 state"""
+        pod = crystal.pod()
+        a = [np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (angles, R, D6, n_state)]
+        out, iters = np.zeros(137), np.zeros(2, dtype=np.int32)
+        L = _lib()
+        L.orc_mm10_crystal_probe.argtypes = [C.c_void_p, _DP, C.c_double, _DP, _DP, C.c_int, _DP, _DP, C.POINTER(C.c_int32)]
+        fail = L.orc_mm10_crystal_probe(C.addressof(pod), _dp(a[0]), float(dt), _dp(a[1]), _dp(a[2]), int(it), _dp(a[3]), _dp(out), _ip(iters))
+        return dict(fail=int(fail), iters=iters.copy(), stress=out[:6], tt=out[6], tt_rate=out[7], tangent=out[8:44].reshape(6, 6),
+                    Rp=out[44:53].reshape(3, 3), euler=out[53:56], eps=out[56:62], slip_incs=out[62:110], u=out[110:125],
+                    ep=out[125:131], ed=out[131:137])
 
     @staticmethod
     def slip_table(slip_type):

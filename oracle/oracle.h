@@ -22,15 +22,16 @@
  * statement by statement by tools/fortran_subset.py (fixture
  * tests/golden/reference_vectors.npz, tests/test_reference_vectors.py): rtcmp1
  * (polar.f), getrm1, cep2A_a, mm10_rotation_matrix, mm10_RT2RVE / RT2RVW,
- * mm10_symSW, formG (odd N) and the summation tree of ddot42n.  UNPINNED: the
- * drivers on derived types and MKL solvers (mm10_solve, FFT_nr3, fftPcg, mm01);
- * those are held only by derived identities (tests/test_oracle_*.py,
- * tests/test_py_mm10.py): Green-operator projection identities, independent
- * numpy restatements of G_K_dF and of the mm10 / Voce crystal update (same
- * Newton iteration counts), finite-difference checks of cep2A / cnst1 / the
- * local Jacobian / mm10_tangent, the degenerate case MTS == Voce,
- * homogeneous-deck behaviour -- and by the slot for a maintainer's ifort run
- * (tests/golden/reference_run/).
+ * mm10_symSW, formG (odd N), the summation tree of ddot42n, mm10_setup /
+ * mm10_formR / mm10_formJ, and mm10_solve_crystal end to end (converged state,
+ * tangent, Newton iteration counts, failure flags; fcc and bcc48).  UNPINNED:
+ * the block drivers (drive_eps_sig, rstgp1, mm10), mm01 and the MKL-based global
+ * loop (FFT_nr3, fftPcg, fftfem3d); those are held by derived identities
+ * (tests/test_oracle_*.py, tests/test_py_mm10.py): Green-operator projection
+ * identities, independent numpy restatements of G_K_dF and of the crystal
+ * update, finite-difference checks of cep2A / cnst1 / the local Jacobian /
+ * mm10_tangent, MTS == Voce in the degenerate case, homogeneous-deck behaviour
+ * -- and by the slot for a maintainer's ifort run (tests/golden/reference_run/).
  */
 #ifndef CPFFT_ORACLE_H
 #define CPFFT_ORACLE_H

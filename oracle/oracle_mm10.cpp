@@ -3,6 +3,7 @@
 // per material point, restated from mm10_a.f / mm10_b.f / mm10_d.f / mod_crystals.f and
 // setup_mm10_rknstr (drive_eps_sig.f:537-1002).
 #include "oracle_internal.hpp"
+#include <vector>
 #include "slip_tables.inc"
 
 namespace orc {
@@ -980,6 +981,67 @@ extern "C" void orc_mm10_residual_jacobian(const orc_crystal* c, const double* a
   double J[7][7];
   formJ(p, np1, x7, J);
   for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) J49[7 * i + j] = J[i][j];
+}
+
+// the same probe with a plastic rotation Rp_n and a polar rotation R of the step (row-major 3x3): exercises the
+// rotation operators of mm10_setup (mm10_a.f:830-962); also returns the current Schmid vectors (tests/test_reference_vectors.py)
+extern "C" void orc_mm10_residual_jacobian_rot(const orc_crystal* c, const double* angles, const double* D6, double dt,
+                                               const double* x7, const double* n_stress6, double n_tt, const double* Rp9,
+                                               const double* R9, double* R7, double* J49, double* ms_out, double* qs_out, double* qc_out) {
+  using namespace orc;
+  CrystalLib L; L.in = *c; finalize_crystal(L);
+  static thread_local Props p; static thread_local State n, np1;
+  setup_props(L, angles, p);
+  std::memset(&n, 0, sizeof(State));
+  M33 I = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, Rm;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { n.R[i][j] = I[i][j]; n.Rp[i][j] = Rp9[3 * i + j]; Rm[i][j] = R9[3 * i + j]; }
+  for (int k = 0; k < 6; ++k) n.stress[k] = n_stress6[k];
+  n.tau_tilde = n_tt; n.u[0] = -1.0; n.u[1] = -1.0;
+  setup_np1(Rm, D6, dt, np1);
+  mm10_setup(p, np1, n);
+  formR(p, np1, n, x7, R7);
+  double J[7][7];
+  formJ(p, np1, x7, J);
+  for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) J49[7 * i + j] = J[i][j];
+  for (int s = 0; s < p.nslip; ++s) {
+    for (int k = 0; k < 6; ++k) ms_out[6 * s + k] = np1.ms[s][k];
+    for (int k = 0; k < 3; ++k) { qs_out[3 * s + k] = np1.qs[s][k]; qc_out[3 * s + k] = np1.qc[s][k]; }
+  }
+}
+
+// the whole update of one crystal (mm10_solve_crystal + history store, mm10_a.f:1080-1157, 976-1055) from an explicit n
+// state, for tests/test_reference_vectors.py.  3x3 matrices row-major.  n_state: stress[6], tau_tilde, tt_rate, D[6],
+// eps[6], euler[3], Rp[9], R[9] (41 doubles).  out: stress[6], tau_tilde, tt_rate, tangent[36] (row-major), Rp[9],
+// euler[3], eps[6], slip_incs[48], u[15], ep[6], ed[6] (137 doubles); iters[2] = predictor / update Newton iterations;
+// returns the failure flag.
+extern "C" int orc_mm10_crystal_probe(const orc_crystal* c, const double* angles, double dt, const double* R9, const double* D6,
+                                      int iter, const double* n_state, double* out137, int* iters) {
+  using namespace orc;
+  CrystalLib L; L.in = *c; finalize_crystal(L);
+  const HistLayout H = mm10_history_layout(L.nslip, 1);
+  std::vector<double> hn(H.total + 64, 0.0), h1(H.total + 64, 0.0);
+  const double* ns = n_state;
+  for (int k = 0; k < 6; ++k) { hn[H.c_stress + k] = ns[k]; hn[H.c_D + k] = ns[8 + k]; hn[H.c_eps + k] = ns[14 + k]; }
+  hn[H.c_tt] = ns[6]; hn[H.c_ttrate] = ns[7];
+  for (int k = 0; k < 3; ++k) hn[H.c_euler + k] = ns[20 + k];
+  for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) { hn[H.c_Rp + 3 * j + i] = ns[23 + 3 * i + j]; hn[H.R + 3 * j + i] = ns[32 + 3 * i + j]; }
+  hn[H.c_u] = -1.0; hn[H.c_u + 1] = -1.0;
+  double rot9[9], urcs_n[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) rot9[3 * j + i] = R9[3 * i + j];
+  static thread_local CrystalOut co;
+  iters[0] = iters[1] = 0;
+  const int fail = mm10_crystal(2, iter, L, angles, H, dt, rot9, D6, hn.data(), h1.data(), urcs_n, iters, co);
+  double* o = out137;
+  for (int k = 0; k < 6; ++k) o[k] = h1[H.c_stress + k];
+  o[6] = h1[H.c_tt]; o[7] = h1[H.c_ttrate];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) o[8 + 6 * i + j] = co.tangent[i][j];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[44 + 3 * i + j] = h1[H.c_Rp + 3 * j + i];
+  for (int k = 0; k < 3; ++k) o[53 + k] = h1[H.c_euler + k];
+  for (int k = 0; k < 6; ++k) o[56 + k] = h1[H.c_eps + k];
+  for (int k = 0; k < 48; ++k) o[62 + k] = (k < H.len_slip) ? h1[H.c_slipinc + k] : 0.0;
+  for (int k = 0; k < 15; ++k) o[110 + k] = h1[H.c_u + k];
+  for (int k = 0; k < 6; ++k) { o[125 + k] = h1[H.c_ep + k]; o[131 + k] = h1[H.c_ed + k]; }
+  return fail;
 }
 
 extern "C" void orc_crystal_stiffness(const orc_crystal* c, double* C36) {

@@ -116,3 +116,63 @@ def test_ddot42n_summation_tree():
         assert np.array_equal(tree, C9)
         # the oracle evaluates the same tree; its compiler may contract a product into the first add (FMA): last-bit level
         assert np.abs(Oracle.ddot42_point(A81, B9) - C9).max() <= 4e-16 * np.abs(t).max()
+
+
+def _mm10_case(k):
+    from cpfft_b200.problem import Crystal
+    rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["mm10_params"][k]
+    cr = Crystal(slip_type=int(V["mm10_slip_type"][k]), elastic_type=1, h_type=1, e=e, nu=nu, mu=e / 2.0 / (1.0 + nu), harden_n=rate_n,
+                 theta_0=theta_0, tau_y=tau_y, tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+    return Oracle.mm10_residual_jacobian_rot(cr, V["mm10_angles"][k], V["mm10_D6"][k], 1.0, V["mm10_x7"][k], V["mm10_n_stress"][k],
+                                             float(V["mm10_n_tt"][k]), V["mm10_Rp"][k], V["mm10_R"][k])
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_mm10_setup_residual_jacobian(k):
+    """mm10_setup -> mm10_formR -> mm10_formJ of the reference (mm10_a.f:830-962, mm10_b.f:1029-1110, 901-968 and the
+    Voce routines they call), executed on fcc (cases 0-2) and bcc48 (3-5) crystals at random orientations with a
+    plastic rotation Rp_n != I and a polar rotation R != I, rate exponents 20 and 7.5, voche_m 1 and 1.7, with and
+    without the diffusion term: the oracle's current Schmid vectors, residual and Jacobian at the same trial point."""
+    Rv, J, ms, qs, qc = _mm10_case(k)
+    nslip = 12 if V["mm10_slip_type"][k] == 1 else 48
+    assert np.abs(ms[:nslip] - V["mm10_ms"][k][:nslip]).max() <= 5e-16
+    assert np.abs(qs[:nslip] - V["mm10_qs"][k][:nslip]).max() <= 5e-16
+    assert np.abs(qc[:nslip] - V["mm10_qc"][k][:nslip]).max() <= 5e-16
+    assert rel(Rv, V["mm10_R7"][k]) <= 1e-12
+    assert rel(J, V["mm10_J"][k]) <= 1e-12
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_mm10_whole_crystal_update(k):
+    """mm10_solve_crystal of the reference (mm10_a.f:1080-1157), executed: mm10_solve_strup with its sub-stepping,
+    mm10_setup_np1 / mm10_setup, mm10_solve (stress predictor and coupled update, Armijo line search, LAPACK DGESV),
+    mm10_tangent, mm10_a_make_symm_1, mm10_update_rotation, mm10_output (lattice strain by DPOSV, Euler angles, slip
+    increments, the u(:) outputs) -- from explicit n states: virgin and loaded / rotated, fcc (0-4) and bcc48 (5-9), an
+    elastic iteration-0 sweep (1), the diffusion term (2, 7), n = 7.5 with voche_m = 1.7 (3, 8), and a 2.5 % strain increment
+    (4, 9) that makes mm10_solve fail and sub-step (fcc: five cuts, material_cut_step).  The oracle reproduces the
+    converged state AND the Newton iteration counts (predictor, update) = the reference's numbers of Jacobian formations."""
+    from cpfft_b200.problem import Crystal
+    rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["crystal_params"][k]
+    cr = Crystal(slip_type=int(V["crystal_slip_type"][k]), elastic_type=1, h_type=1, e=e, nu=nu, mu=e / 2.0 / (1.0 + nu), harden_n=rate_n,
+                 theta_0=theta_0, tau_y=tau_y, tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+    r = Oracle.mm10_crystal_probe(cr, V["crystal_angles"][k], 1.0, V["crystal_R"][k], V["crystal_D6"][k], int(V["crystal_iter"][k]),
+                                  V["crystal_n_state"][k])
+    assert bool(r["fail"]) == bool(V["crystal_fail"][k])
+    assert list(r["iters"]) == list(V["crystal_iters"][k])
+    if V["crystal_fail"][k]:
+        # material_cut_step: the reference resets stress / tau_tilde to the n state and leaves the rest undefined
+        assert np.array_equal(r["stress"], V["crystal_n_state"][k][:6]) and r["tt"] == V["crystal_n_state"][k][6]
+        return
+    nslip = 12 if V["crystal_slip_type"][k] == 1 else 48
+    assert rel(r["stress"], V["crystal_stress"][k]) <= 1e-11
+    assert abs(r["tt"] - V["crystal_tt"][k]) <= 1e-11 * abs(V["crystal_tt"][k])
+    assert abs(r["tt_rate"] - V["crystal_tt_rate"][k]) <= 1e-9 * max(1.0, abs(V["crystal_tt_rate"][k]))
+    assert rel(r["tangent"], V["crystal_tangent"][k]) <= 1e-10
+    assert np.abs(r["Rp"] - V["crystal_Rp"][k]).max() <= 1e-13
+    assert np.abs(r["euler"] - V["crystal_euler"][k]).max() <= 1e-10
+    assert np.abs(r["eps"] - V["crystal_eps"][k]).max() <= 1e-13
+    assert np.abs(r["slip_incs"][:nslip] - V["crystal_slip_incs"][k][:nslip]).max() <= 1e-12 * max(1e-3, np.abs(V["crystal_slip_incs"][k]).max())
+    assert np.abs(r["ep"] - V["crystal_ep"][k]).max() <= 1e-12 and np.abs(r["ed"] - V["crystal_ed"][k]).max() <= 1e-12
+    for j in (5, 6, 7, 10, 11, 12, 13, 14):                    # u(6:8), u(11:15): max slip rate, its system, active systems, ...
+        a, b = r["u"][j], V["crystal_u"][k][j]
+        assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (j, a, b)

@@ -33,7 +33,7 @@ INTRINSICS = {
     "log": "math.log", "dlog": "math.log", "max": "max", "dmax1": "max", "min": "min", "dmin1": "min", "dble": "_ftn_dble",
     "real": "float", "int": "_ftn_int", "sign": "_ftn_sign", "dsign": "_ftn_sign", "mod": "_ftn_mod", "sum": "np.sum",
     "dot_product": "_ftn_dot", "matmul": "np.matmul", "transpose": "np.transpose", "maxval": "np.max", "minval": "np.min",
-    "log10": "math.log10", "dlog10": "math.log10", "idint": "_ftn_int", "ifix": "_ftn_int", "dfloat": "float",
+    "isnan": "_ftn_isnan", "any": "np.any", "all": "np.all", "size": "np.size", "log10": "math.log10", "dlog10": "math.log10", "idint": "_ftn_int", "ifix": "_ftn_int", "dfloat": "float",
     "sinh": "math.sinh", "cosh": "math.cosh", "tanh": "math.tanh", "nint": "_ftn_nint", "float": "float",
 }
 
@@ -61,6 +61,10 @@ def _ftn_dot(a, b):
     return s
 
 
+def _ftn_isnan(a):
+    return np.isnan(a) if isinstance(a, np.ndarray) else math.isnan(a)
+
+
 def _ftn_dble(a):
     return np.asarray(a, dtype=np.float64) if isinstance(a, np.ndarray) else float(a)
 
@@ -75,6 +79,20 @@ def _flat(a, *idx):
         off += (int(i) - 1) * stride
         stride *= a.shape[k]
     return v[off:]
+
+
+def _assign_whole(a, v):
+    """a = v for a whole array.  A longer rank-1 right-hand side is cut to the extent of the left-hand side: what the
+    reference's compiler does with its one non-conforming assignment, work_vec1(7) = matmul(trans_J(14,7), R)
+    (mm10_a.f:3220, the first 7 entries are the intended J^T R)."""
+    if isinstance(v, np.ndarray) and v.ndim == 1 and a.ndim == 1 and v.size > a.size:
+        a[...] = v[:a.size]
+    else:
+        a[...] = v
+
+
+def _first(a):
+    return a.T.reshape(-1)[0] if isinstance(a, np.ndarray) else a
 
 
 def _reshape_dummy(a, shape):
@@ -104,7 +122,82 @@ def _daxpy(n, alpha, x, incx, y, incy):     # BLAS, unit strides: y += alpha x
     n = int(n); y[:n] = y[:n] + alpha * x[:n]
 
 
-BUILTIN_SUBS = {"vdmul": _vdmul, "vdadd": _vdadd, "daxpy": _daxpy}
+def _flat_any(a):
+    return _flat(a) if isinstance(a, np.ndarray) else a
+
+
+def _dger(m, n, alpha, x, incx, y, incy, a, lda):      # BLAS: A += alpha x y^T, column-major with leading dimension lda
+    if incx != 1 or incy != 1:
+        raise FortranError("dger with non-unit stride")
+    m, n, lda = int(m), int(n), int(lda)
+    for j in range(n):
+        if y[j] != 0.0:
+            t = alpha * y[j]
+            for i in range(m):
+                a[i + j * lda] = a[i + j * lda] + x[i] * t
+
+
+def _dgemv(trans, m, n, alpha, a, lda, x, incx, beta, y, incy):     # reference-BLAS loop order
+    if incx != 1 or incy != 1:
+        raise FortranError("dgemv with non-unit stride")
+    m, n, lda = int(m), int(n), int(lda)
+    t = trans.strip().lower()[0]
+    leny = m if t == "n" else n
+    for i in range(leny):
+        y[i] = 0.0 if beta == 0.0 else beta * y[i]
+    if t == "n":
+        for j in range(n):
+            tmp = alpha * x[j]
+            for i in range(m):
+                y[i] = y[i] + tmp * a[i + j * lda]
+    else:
+        for j in range(n):
+            tmp = 0.0
+            for i in range(m):
+                tmp = tmp + a[i + j * lda] * x[i]
+            y[j] = y[j] + alpha * tmp
+
+
+def _dgesv(n, nrhs, a, lda, ipiv, b, ldb, info):       # LAPACK itself (scipy): LU with partial pivoting, A and B overwritten
+    from scipy.linalg import lapack
+    n, nrhs, lda, ldb = int(n), int(nrhs), int(lda), int(ldb)
+    A = a[:lda * n].reshape((n, lda)).T[:n, :n]
+    B = b[:ldb * nrhs].reshape((nrhs, ldb)).T[:n, :nrhs]
+    lu, piv, x, inf = lapack.dgesv(np.array(A, order="F"), np.array(B, order="F"))
+    A[...] = lu; B[...] = x
+    k = min(n, ipiv.size)            # mm10_tangent hands a 1-entry ipiv to a 6x6 solve (mm10_a.f:684, 810): the pivots are not read back
+    ipiv[:k] = piv[:k] + 1
+    return int(inf)
+
+
+def _dposv(uplo, n, nrhs, a, lda, b, ldb, info):      # LAPACK itself (scipy): Cholesky solve, A and B overwritten
+    from scipy.linalg import lapack
+    n, nrhs, lda, ldb = int(n), int(nrhs), int(lda), int(ldb)
+    A = a[:lda * n].reshape((n, lda)).T[:n, :n]
+    B = b[:ldb * nrhs].reshape((nrhs, ldb)).T[:n, :nrhs]
+    c, x, inf = lapack.dposv(np.array(A, order="F"), np.array(B, order="F"), lower=0 if uplo.strip().lower()[0] == "u" else 1)
+    A[...] = c; B[...] = x
+    return int(inf)
+
+
+def _dgemm(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):      # reference-BLAS loop order, no transposes
+    if ta.strip().lower()[0] != "n" or tb.strip().lower()[0] != "n":
+        raise FortranError("dgemm with a transposed operand")
+    m, n, k, lda, ldb, ldc = int(m), int(n), int(k), int(lda), int(ldb), int(ldc)
+    for j in range(n):
+        for i in range(m):
+            c[i + j * ldc] = 0.0 if beta == 0.0 else beta * c[i + j * ldc]
+        for l in range(k):
+            t = alpha * b[l + j * ldb]
+            for i in range(m):
+                c[i + j * ldc] = c[i + j * ldc] + t * a[i + l * lda]
+
+
+BUILTIN_SUBS = {"vdmul": _vdmul, "vdadd": _vdadd, "daxpy": _daxpy, "dger": _dger, "dgemv": _dgemv, "dgesv": _dgesv, "dposv": _dposv,
+                "dgemm": _dgemm}
+BUILTIN_ARRAY_ARGS = {"vdmul": (1, 2, 3), "vdadd": (1, 2, 3), "daxpy": (2, 4), "dger": (3, 5, 7), "dgemv": (4, 6, 9),
+                      "dgesv": (2, 4, 5), "dposv": (3, 5), "dgemm": (6, 8, 11)}   # address arguments
+BUILTIN_INFO_ARG = {"dgesv": 7, "dposv": 7}
 
 
 def _ftn_pow(a, b):
@@ -118,7 +211,11 @@ def _ftn_pow(a, b):
                 r = r * a
             return r if b else 1.0
         return a ** int(b)
-    return math.pow(a, b)
+    try:
+        return math.pow(a, b)
+    except (OverflowError, ValueError):       # IEEE results instead of Python exceptions
+        with np.errstate(all="ignore"):
+            return float(np.power(np.float64(a), np.float64(b)))
 
 
 def _ftn_div(a, b):
@@ -126,6 +223,11 @@ def _ftn_div(a, b):
     if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)) and not isinstance(a, bool):
         q = abs(int(a)) // abs(int(b))
         return q if (a >= 0) == (b >= 0) else -q
+    if isinstance(b, np.ndarray) or isinstance(a, np.ndarray):
+        return a / b
+    if b == 0.0:                              # IEEE, not a Python exception: x / 0 = +-inf, 0 / 0 = nan
+        with np.errstate(all="ignore"):
+            return float(np.float64(a) / np.float64(b))
     return a / b
 
 
@@ -157,6 +259,7 @@ def logical_lines(text):
             else:
                 res.append(ch.lower())
         line = "".join(res).rstrip()
+        line = re.sub(r"\.\s*(eq|ne|lt|le|gt|ge|and|or|not|eqv|neqv|true|false)\s*\.", r".\1.", line)
         if not line.strip():
             continue
         cont = len(line) > 5 and line[5] not in " 0" and line[:5].strip() == ""
@@ -169,21 +272,34 @@ def logical_lines(text):
             cur = [label, line[6:].strip() if len(line) > 6 else ""]
     if cur is not None:
         out.append(tuple(cur))
-    return [(lab, st) for lab, st in out if st]
+    res = []
+    for lab, st in out:                      # `a = 1; b = 2`
+        parts = split_top(st, ";") if ";" in st else [st]
+        for k, p_ in enumerate(parts):
+            if p_.strip():
+                res.append((lab if k == 0 else "", p_.strip()))
+    return res
 
 
 def split_units(lines):
     """{name: (args, body statements)} for every subroutine"""
-    units, name, args, body = {}, None, None, None
+    units, name, args, body, kind, depth = {}, None, None, None, None, 0
     for lab, st in lines:
-        m = re.match(r"(?:recursive\s+)?subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$", st)
+        m = re.match(r"(?:recursive\s+)?(subroutine)\s+(\w+)\s*(?:\((.*)\))?\s*$", st) or \
+            re.match(r"(?:double precision\s+|real\s*(?:\(\w+\))?\s+|integer\s+|logical\s+)?(function)\s+(\w+)\s*\((.*)\)\s*$", st)
         if m and name is None:
-            name = m.group(1)
-            args = [a.strip() for a in m.group(2).split(",")] if m.group(2) and m.group(2).strip() else []
-            body = []
+            kind, name = m.group(1), m.group(2)
+            args = [a.strip() for a in m.group(3).split(",")] if m.group(3) and m.group(3).strip() else []
+            body, depth = [], 0
             continue
-        if name is not None and re.match(r"end(\s+subroutine(\s+\w+)?)?\s*$", st):
-            units[name] = (args, body)
+        if m and name is not None:             # an internal procedure (after `contains`)
+            depth += 1
+        if name is not None and re.match(r"end(\s+(subroutine|function)(\s+\w+)?)?\s*$", st):
+            if depth > 0:
+                depth -= 1
+                body.append((lab, st))
+                continue
+            units[name] = (args, body, kind)
             name = None
             continue
         if name is not None:
@@ -236,7 +352,7 @@ def split_top(s, sep=","):
     return out
 
 
-TOKEN = re.compile(r"\s*(?:(\d+\.?\d*(?:[de][+-]?\d+)?|\.\d+(?:[de][+-]?\d+)?)|(\.[a-z]+\.)|('(?:[^']|'')*'|\"[^\"]*\")|(\w+)|(\*\*|==|/=|<=|>=|\(/|/\)|[-+*/(),:<>=\[\]]))")
+TOKEN = re.compile(r"\s*(?:(\d+\.?\d*(?:[de][+-]?\d+)?|\.\d+(?:[de][+-]?\d+)?)|(\.[a-z]+\.)|('(?:[^']|'')*'|\"[^\"]*\")|(\w+(?:\s*%\s*\w+)*)|(\*\*|==|/=|<=|>=|\(/|/\)|[-+*/(),:<>=\[\]]))")
 DOTOPS = {".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".and.": " and ", ".or.": " or ",
           ".not.": " not ", ".true.": "True", ".false.": "False", ".eqv.": "==", ".neqv.": "!="}
 
@@ -378,6 +494,9 @@ class Translator:
                 raise FortranError("missing )")
             return f"({inner})"
         if kind == "name":
+            derived = "%" in t
+            if derived:
+                t = re.sub(r"\s*%\s*", ".", t)
             if self._peek() == ("op", "("):
                 self._take()
                 args = []
@@ -394,7 +513,9 @@ class Translator:
                     args.append(parts)
                     if self._take() == ("op", ")"):
                         break
-                if t in self.arrays:
+                if t in self.units and self.units[t][2] == "function":
+                    return f"_fcall({t!r}, {', '.join(a[0] for a in args)})"
+                if derived or t in self.arrays:
                     if all(len(a) == 1 and a[0] in self.arrays for a in args):      # vector subscripts c(iv, jv)
                         return f"{t}[np.ix_({', '.join(a[0] + ' - 1' for a in args)})]"
                     return f"{t}[{', '.join(self._index(a) for a in args)}]"
@@ -416,7 +537,7 @@ class Translator:
 
 
 # ------------------------------------------------------------------------------------------- program units
-DECL = re.compile(r"(double precision|real\s*\*\s*8|real(?:\s*\([^)]*\))?|integer|logical|character(?:\s*\*\s*\d+)?)\s*(.*)$")
+DECL = re.compile(r"(double precision|real\s*\*\s*8|real(?:\s*\([^)]*\))?|complex(?:\s*\([^)]*\))?|integer|logical|character(?:\s*\*\s*\d+)?)\s*(.*)$")
 
 
 class Interpreter:
@@ -425,6 +546,9 @@ class Interpreter:
         self.consts = dict(consts or {})
         self.funcs = {}
         self.sources = {}
+        self.array_dummies = {}
+        self.derived_factories = {}    # derived type name -> callable making a fresh object (types.SimpleNamespace) for locals
+        self.calls = {}
         self.module_vars = {}          # variables of `use <module>` (arrays by reference, scalars read-only): set by the harness
 
     def load(self, text):
@@ -434,13 +558,7 @@ class Interpreter:
         self.consts = parse_parameters(logical_lines(text), self.consts)
 
     # -- translation of one subroutine
-    def compile(self, name):
-        if name in self.funcs:
-            return self.funcs[name]
-        if name not in self.units:
-            raise FortranError(f"subroutine {name} not loaded")
-        args, body = self.units[name]
-        tr = Translator(self.units, self.consts)
+    def _parse_decls(self, body):
         arrays, scalars, dims, data_init, local_consts, int_arrays, module_names = set(), set(), {}, [], {}, set(), set()
         scalar_types = {}
         stmts = []
@@ -454,7 +572,12 @@ class Interpreter:
                     (arrays if isinstance(self.module_vars[nm], np.ndarray) else scalars).add(nm)
                     module_names.add(nm)
                 continue
-            if re.match(r"(implicit|use|include|intent|save|external|format|!dir|deallocate)", st) or st.startswith("c!dir"):
+            m = re.match(r"type\s*\(\s*(\w+)\s*\)\s*(?:,[^:]*)?::\s*(.*)$", st)
+            if m:
+                for nm in split_top(m.group(2)):
+                    data_init.append((nm.strip(), ("__derived__", m.group(1))))
+                continue
+            if re.match(r"(implicit|use|include|intent|save|external|format|!dir|deallocate|type\s*\()", st) or st.startswith("c!dir"):
                 continue
             m = re.match(r"dimension\s+(.*)$", st)
             if m:
@@ -477,6 +600,8 @@ class Interpreter:
                 if "::" in rest:
                     attrs, rest = rest.split("::", 1)
                 dim_attr = re.search(r"dimension\s*\((.*?)\)\s*(?:,|$)", attrs.replace(" ", "") + ",")
+                if "external" in attrs:
+                    continue
                 if "parameter" in attrs:
                     for it in split_top(rest):
                         k, v = it.split("=", 1)
@@ -503,6 +628,29 @@ class Interpreter:
                             data_init.append((item, init))
                 continue
             stmts.append((lab, st))
+        return arrays, scalars, dims, data_init, local_consts, int_arrays, module_names, scalar_types, stmts
+
+    def compile(self, name):
+        if name in self.funcs:
+            return self.funcs[name]
+        if name not in self.units:
+            raise FortranError(f"subroutine {name} not loaded")
+        saved = (getattr(self, "_internal", set()), getattr(self, "_int_arrays", set()))     # compile() recurses into callees
+        try:
+            return self._compile(name)
+        finally:
+            self._internal, self._int_arrays = saved
+
+    def _compile(self, name):
+        args, body, kind = self.units[name]
+        tr = Translator(self.units, self.consts)
+        internal = {}
+        for k_, (lab_, st_) in enumerate(body):
+            if st_ == "contains":
+                internal = split_units(body[k_ + 1:])
+                body = body[:k_]
+                break
+        arrays, scalars, dims, data_init, local_consts, int_arrays, module_names, scalar_types, stmts = self._parse_decls(body)
         self._int_arrays = int_arrays
         known = set(self.consts) | set(local_consts)
         py = [f"def {name}({', '.join(a + '_' if a in ('lambda',) else a for a in args)}):"]
@@ -518,28 +666,67 @@ class Interpreter:
             if a in arrays and dims.get(a) and not any(":" in d or d.strip() == "*" for d in dims[a]):
                 shape = ", ".join(f"int({tr.expr(d, arrays, scalars | known)})" for d in dims[a])
                 py.append(f"{ind}{a} = _reshape_dummy({a}, ({shape},))")
+        for a in args:                                          # an array actual seen through a scalar dummy: its first element
+            if a in scalar_types:
+                py.append(f"{ind}{a} = _first({a})")
         for sname, typ in sorted(scalar_types.items()):       # locals exist (undefined) before their first assignment
             if sname not in args and sname not in module_names:
                 py.append(f"{ind}{sname} = {'0' if typ.startswith('integer') else 'False' if typ.startswith('logical') else repr('') if typ.startswith('character') else '0.0'}")
         for n_, v_ in data_init:
+            if isinstance(v_, tuple):            # a local variable of derived type: made by the harness's factory
+                if n_ not in args:
+                    py.append(f"{ind}{n_} = _new_derived({v_[1]!r})")
+                continue
             py.append(f"{ind}{n_} = {tr.expr(v_, arrays, scalars | known)}")
         assigned = set()
+        self._internal = set(internal)
+        for iname, (iargs, ibody, ikind) in internal.items():      # host association: nested functions sharing the host's variables
+            if iargs:
+                raise FortranError(f"internal procedure {iname} with arguments")
+            ia, isc, idims, idata, iconsts, iint, _, istypes, istmts = self._parse_decls(ibody)
+            iassigned = set()
+            self._int_arrays = int_arrays | iint
+            ipy = self._block(istmts, tr, arrays | ia, scalars | known | isc | set(iconsts), args, iassigned, 2)
+            self._int_arrays = int_arrays
+            py.append(f"{ind}def {iname}():")
+            host_derived = {n_ for n_, v_ in data_init if isinstance(v_, tuple)}
+            nl = sorted(v for v in iassigned if v not in ia and v not in isc and v not in arrays and (v in scalars or v in args or v in host_derived))
+            if nl:
+                py.append(f"{ind}{ind}nonlocal {', '.join(nl)}")
+            for k, v in iconsts.items():
+                py.append(f"{ind}{ind}{k} = {tr.expr(v, arrays | ia, scalars | known | isc)}")
+            for a in sorted(ia):
+                shape = ", ".join(f"int({tr.expr(d, arrays | ia, scalars | known | isc)})" for d in idims[a])
+                py.append(f"{ind}{ind}{a} = np.zeros(({shape},), order='F'{', dtype=np.int64' if a in iint else ''})")
+            for sname, typ in sorted(istypes.items()):
+                py.append(f"{ind}{ind}{sname} = {'0' if typ.startswith('integer') else 'False' if typ.startswith('logical') else '0.0'}")
+            py += [l.replace("return _RET_", "return") for l in ipy]
+            py.append(f"{ind}{ind}return")
+            assigned |= {v for v in iassigned if v in args}
         body_py = self._block(stmts, tr, arrays, scalars | known, args, assigned, 1)
         py += body_py
         outs = [a for a in args if a in assigned and a not in arrays]
-        py.append(f"{ind}return {{{', '.join(repr(o) + ': ' + o for o in outs)}}}")
+        ret = name if kind == "function" else f"{{{', '.join(repr(o) + ': ' + o for o in outs)}}}"
+        py.append(f"{ind}return {ret}")
         src = "\n".join(py)
-        src = src.replace("return _RET_", f"return {{{', '.join(repr(o) + ': ' + o for o in outs)}}}")
+        src = src.replace("return _RET_", f"return {ret}")
+        self.array_dummies[name] = [a in arrays for a in args]
         self.sources[name] = src
         glob = {"np": np, "math": math, "_ftn_sign": _ftn_sign, "_ftn_mod": _ftn_mod, "_ftn_int": _ftn_int, "_ftn_div": _ftn_div, "_ftn_pow": _ftn_pow,
-                "_ftn_dot": _ftn_dot, "_ftn_nint": _ftn_nint, "_ftn_dble": _ftn_dble, "_flat": _flat, "_reshape_dummy": _reshape_dummy, "_call": self.call,
-                "_builtin": BUILTIN_SUBS, **self.consts, **self.module_vars}
+                "_ftn_dot": _ftn_dot, "_ftn_nint": _ftn_nint, "_ftn_dble": _ftn_dble, "_ftn_isnan": _ftn_isnan, "_flat": _flat, "_reshape_dummy": _reshape_dummy, "_call": self.call, "_fcall": self.call, "_first": _first, "_assign_whole": _assign_whole,
+                "_builtin": BUILTIN_SUBS, "_flat_any": _flat_any, "_new_derived": self.new_derived, **self.consts, **self.module_vars}
         exec(compile(src, f"<fortran {name}>", "exec"), glob)
         self.funcs[name] = glob[name]
         self.funcs[name]._outs = outs
         return self.funcs[name]
 
+    def new_derived(self, type_name):
+        if type_name not in self.derived_factories:
+            raise FortranError(f"no factory for derived type {type_name}")
+        return self.derived_factories[type_name]()
+
     def call(self, name, *args):
+        self.calls[name] = self.calls.get(name, 0) + 1        # call counts (e.g. Jacobian formations = Newton iterations)
         return self.compile(name)(*args)
 
     def _block(self, stmts, tr, arrays, scalars, args, assigned, depth):
@@ -576,6 +763,8 @@ class Interpreter:
                 if label:
                     do_labels.append(label)
                 continue
+            if re.match(r"do\s*$", st):
+                emit("while True:"); stack.append(("do", None)); emit("pass"); continue
             m = re.match(r"do\s+while\s*\((.*)\)\s*$", st)
             if m:
                 emit(f"while {tr.expr(m.group(1), arrays, scalars)}:"); stack.append(("do", None)); emit("pass"); continue
@@ -640,34 +829,63 @@ class Interpreter:
                 lines.append(f"{mm.group(1)} = np.zeros(({shape},), order='F'{', dtype=np.int64' if mm.group(1) in self._int_arrays else ''})")
                 assigned.add(mm.group(1))
             return lines
+        m = re.match(r"call\s+(\w+)\s*$", st)
+        if m and m.group(1) in getattr(self, "_internal", ()):
+            return [f"{m.group(1)}()"]
         m = re.match(r"call\s+(\w+)\s*(?:\((.*)\))?\s*$", st)
         if m and m.group(1) in BUILTIN_SUBS and m.group(1) not in self.units:
             pyargs = []
-            for a in split_top(m.group(2) or ""):
-                mm = re.match(r"(\w+)\s*\((.*)\)$", a.strip())
-                if a.strip() in arrays:
+            for k_, a in enumerate(split_top(m.group(2) or "")):
+                mm = re.match(r"(\w+(?:\s*%\s*\w+)*)\s*\((.*)\)$", a.strip())
+                if k_ not in BUILTIN_ARRAY_ARGS[m.group(1)]:
+                    pyargs.append(tr.expr(a, arrays, scalars))
+                elif a.strip() in arrays:
                     pyargs.append(f"_flat({a.strip()})")
-                elif mm and mm.group(1) in arrays:
-                    pyargs.append(f"_flat({mm.group(1)}, {', '.join(tr.expr(x, arrays, scalars) for x in split_top(mm.group(2)))})")
+                elif re.fullmatch(r"\w+(?:\s*%\s*\w+)+", a.strip()):
+                    pyargs.append(f"_flat_any({re.sub(r'\s*%\s*', '.', a.strip())})")
+                elif mm and (mm.group(1) in arrays or "%" in mm.group(1)):
+                    base = re.sub(r"\s*%\s*", ".", mm.group(1))
+                    pyargs.append(f"_flat({base}, {', '.join(tr.expr(x, arrays, scalars) for x in split_top(mm.group(2)))})")
                 else:
                     pyargs.append(tr.expr(a, arrays, scalars))
+            if m.group(1) in BUILTIN_INFO_ARG:       # LAPACK: the last argument receives `info`
+                info_name = split_top(m.group(2))[BUILTIN_INFO_ARG[m.group(1)]].strip()
+                assigned.add(info_name)
+                return [f"{info_name} = _builtin[{m.group(1)!r}]({', '.join(pyargs)})"]
             return [f"_builtin[{m.group(1)!r}]({', '.join(pyargs)})"]
         if m:
             callee, argtxt = m.group(1), m.group(2) or ""
             actual = split_top(argtxt)
-            if callee not in self.units:
-                raise FortranError(f"call to unknown subroutine {callee}")
+            if callee not in self.units:         # not loaded (another file, a library): an error only if the call is reached
+                return [f"raise RuntimeError({('call to unknown subroutine ' + callee)!r})"]
             cargs = self.units[callee][0]
-            pyargs = [tr.expr(a, arrays, scalars) if not (a in arrays) else a for a in actual]
             try:
                 outs = self.compile(callee)._outs
             except FortranError as e:      # a callee this interpreter cannot run: an error only if the call is reached
                 return [f"raise RuntimeError({('call ' + callee + ': ' + str(e))!r})"]
+            pyargs = []
+            for k, a in enumerate(actual):
+                a = a.strip()
+                mm = re.match(r"(\w+(?:\s*%\s*\w+)*)\s*\(([^:]*)\)$", a)
+                is_arr_dummy = k < len(self.array_dummies.get(callee, [])) and self.array_dummies[callee][k]
+                if a in arrays:
+                    pyargs.append(a)
+                elif mm and is_arr_dummy and (mm.group(1) in arrays or "%" in mm.group(1)) and ":" not in mm.group(2):
+                    base = re.sub(r"\s*%\s*", ".", mm.group(1))
+                    pyargs.append(f"_flat({base}, {', '.join(tr.expr(x, arrays, scalars) for x in split_top(mm.group(2)))})")
+                else:
+                    pyargs.append(tr.expr(a, arrays, scalars))
             lines = [f"_r = _call({callee!r}, {', '.join(pyargs)})"]
             for formal, act in zip(cargs, actual):
+                act = act.strip()
                 if formal in outs and re.fullmatch(r"\w+", act):
                     lines.append(f"{act} = _r[{formal!r}]")
                     assigned.add(act)
+                elif formal in outs and re.fullmatch(r"\w+(?:\s*%\s*\w+)*(?:\s*\([^()]*\))?", act) and not isinstance(self.consts.get(act), (int, float)):
+                    # a scalar result delivered into an array element or a derived-type component
+                    if re.match(r"\w+(?:\s*%\s*\w+)*\s*\(", act) or "%" in act:
+                        lines.append(f"{tr.expr(act, arrays, scalars)} = _r[{formal!r}]")
+                        assigned.add(re.match(r"\w+", act).group(0))
             return lines
         # assignment: find top-level '=' (not ==, <=, >=, /=)
         depth, pos = 0, None
@@ -682,7 +900,7 @@ class Interpreter:
         assigned.add(base)
         rhs_py = tr.expr(rhs, arrays, scalars)
         if base in arrays and lhs == base:
-            return [f"{base}[...] = {rhs_py}"]
+            return [f"_assign_whole({base}, {rhs_py})"]
         return [f"{tr.expr(lhs, arrays, scalars)} = {rhs_py}"]
 
 

@@ -15,6 +15,11 @@ order and precision the source states.  Routines (reference file:line of the sub
   mm10_a.f:1287 mm10_rotation_matrix                                     Kocks angles -> g               -> M2
   mm10_a.f:1400 mm10_rt2rve, :1461 mm10_rt2rvw                           slip-vector rotation operators  -> M4
   mm10_b.f      mm10_symSW                                               sym(S W) in Voigt form          -> M5
+  mm10_a.f:830  mm10_setup (+ setup_voche, mult_type_*, ET2EV, WT2WV)   current ms, qs, qc, dg           -> M4
+  mm10_b.f:1029 mm10_formR (+ formR1/R2, form_dbarp/wbarp/wp, slipinc, rs, h_voche, symSW)  residual   -> M5
+  mm10_b.f:901  mm10_formJ (+ formJ11..J22, formarrs, dgdt/estress/ehard_voche, IW, symSWmat, DGER)   Jacobian -> M6
+  mm10_a.f:1080 mm10_solve_crystal: mm10_solve_strup (:2628), mm10_solve (:2860, predictor / update Newton loops,
+                line search, DGESV), mm10_tangent (:658), mm10_update_rotation (:3310), mm10_output (:3433)      -> M3, M7-M10
   FFT_init.f:272 formG                                                   Green operator table, odd N     -> G3
   G_K_dF.f:241  ddot42n                                                  K4 : x with its summation tree  -> G1
 """
@@ -137,6 +142,154 @@ def main():
     C2, tmp = np.zeros((nv, 9), order="F"), np.zeros((nv, 9), order="F")
     it.call("ddot42n", A4, B2, C2, tmp, nv)
     out["ddot42_A4"], out["ddot42_B2"], out["ddot42_C2"] = np.ascontiguousarray(A4), np.ascontiguousarray(B2), np.ascontiguousarray(C2)
+
+    # ---- mm10: mm10_setup -> mm10_formR, mm10_formJ (Voce) at trial points, with a plastic rotation Rp_n and a
+    #      polar rotation R.  props%ms / qs / ns / stiffness are built the way setup_mm10_rknstr does
+    #      (drive_eps_sig.f:571-606, 975-986) from the reference's own mm10_rotation_matrix, mm10_RT2RVE, mm10_ET2EV,
+    #      mm10_WT2WV; the crystal-frame slip vectors and elastic constants are inputs of the fixture.
+    from types import SimpleNamespace as NS
+    sys.path.insert(0, ROOT)
+    from oracle import Oracle                                 # noqa: E402  only for the (b, n) tables extracted from mod_crystals.f
+
+    def slip_vectors(slip_type):       # unit vectors k / sqrt(k.k) of mod_crystals.f:438-1205 (tools/extract_slip_tables.py)
+        return Oracle.slip_table(slip_type)
+    mu, ms_max = it.consts["max_uhard"], it.consts["max_slip_sys"]
+    rec = {k: [] for k in ("slip_type", "angles", "D6", "x7", "n_stress", "n_tt", "Rp", "R", "R7", "J", "ms", "qs", "qc", "params")}
+    for slip_type in (1, 8):                                  # fcc, bcc48
+        b, nrm = slip_vectors(slip_type)
+        nslip = len(b)
+        for case in range(3):
+            ang = rng.uniform(0.0, 360.0, 3)
+            e_mod, nu = 200000.0, 0.3
+            prm = dict(rate_n=20.0 if case < 2 else 7.5, theta_0=100.0, tau_y=100.0, tau_v=100.0, voche_m=1.0 if case != 1 else 1.7,
+                       iD_v=0.0 if case != 2 else 1e-7, e=e_mod, nu=nu)
+            Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
+            Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
+            Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+            g = np.zeros((3, 3), order="F")
+            it.call("mm10_rotation_matrix", ang.copy(), "kocks", "degrees", g, 6)
+            trot = np.asfortranarray(g.T)
+            RE = np.zeros((6, 6), order="F")
+            it.call("mm10_rt2rve", trot, RE)
+            props = NS(nslip=nslip, num_hard=1, h_type=1, out=6, alter_mode=False, eps_dot_0_y=0.0, k_0=0.0, burgers=3.5e-7,
+                       cp_031=0.0, rate_n=prm["rate_n"], theta_0=prm["theta_0"], tau_y=prm["tau_y"], tau_v=prm["tau_v"],
+                       voche_m=prm["voche_m"], id_v=prm["iD_v"], stiffness=np.asfortranarray(RE @ Cc @ RE.T),
+                       ms=np.zeros((6, ms_max), order="F"), qs=np.zeros((3, ms_max), order="F"), ns=np.zeros((3, ms_max), order="F"))
+            for s_ in range(nslip):
+                bs, ns_ = trot @ b[s_], trot @ nrm[s_]
+                A = np.outer(bs, ns_)
+                ev, wv = np.zeros(6), np.zeros(3)
+                it.call("mm10_et2ev", np.asfortranarray(0.5 * (A + A.T)), ev)
+                it.call("mm10_wt2wv", np.asfortranarray(0.5 * (A - A.T)), wv)
+                props.ms[:, s_], props.qs[:, s_], props.ns[:, s_] = ev, wv, ns_
+            w = rng.standard_normal(3) * 0.03
+            Wm = np.array([[0, w[2], w[1]], [-w[2], 0, w[0]], [-w[1], -w[0], 0.0]])
+            Rp = np.eye(3) + Wm + 0.5 * Wm @ Wm; Rp, _ = np.linalg.qr(Rp); Rp = Rp * np.sign(np.diag(Rp))[None, :]
+            fb[:] = 0; rb[:] = 0; fb[0] = np.eye(3) + 0.02 * rng.standard_normal((3, 3))
+            it.call("rtcmp1", 1, fb, rb)
+            Rpol = rb[0].copy()
+            D6 = rng.standard_normal(6) * 1e-3
+            n_stress = rng.standard_normal(6) * 60.0
+            n_tt = 100.0 + 20.0 * rng.random()
+            x7 = np.concatenate([n_stress + rng.standard_normal(6) * 40.0, [n_tt + 3.0 * rng.random()]])
+            nst = NS(rp=np.asfortranarray(Rp), r=np.asfortranarray(np.eye(3)), stress=n_stress.copy(), tau_tilde=np.full(mu, n_tt),
+                     gradfeinv=np.zeros((3, 3, 3), order="F"))
+            np1 = NS(d=D6.copy(), r=np.asfortranarray(Rpol), tinc=1.0, dg=0.0, mu_harden=0.0, ms=np.zeros((6, ms_max), order="F"),
+                     qs=np.zeros((3, ms_max), order="F"), qc=np.zeros((3, ms_max), order="F"), tau_l=np.zeros(ms_max),
+                     tt_rate=np.zeros(mu))
+            it.call("mm10_setup", props, np1, nst)
+            vec1, vec2 = np.zeros(mu), np.zeros(mu)
+            arr1, arr2 = np.zeros((mu, mu), order="F"), np.zeros((mu, mu), order="F")
+            Rv, Jm = np.zeros(7), np.zeros((7, 7), order="F")
+            stress, tt = x7[:6].copy(), x7[6:7].copy()
+            it.call("mm10_formr", props, np1, nst, vec1, vec2, stress, tt, Rv, 1)
+            it.call("mm10_formj", props, np1, nst, vec1, vec2, arr1, arr2, stress, tt, Jm)
+            pad = lambda a, k: np.concatenate([a[:, :nslip].T, np.zeros((48 - nslip, k))])
+            for k, v in (("slip_type", slip_type), ("angles", ang), ("D6", D6), ("x7", x7), ("n_stress", n_stress), ("n_tt", n_tt), ("Rp", Rp),
+                         ("R", Rpol), ("R7", Rv.copy()), ("J", np.ascontiguousarray(Jm)), ("ms", pad(np1.ms, 6)), ("qs", pad(np1.qs, 3)),
+                         ("qc", pad(np1.qc, 3)), ("params", [prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")])):
+                rec[k].append(v)
+    for k, v in rec.items():
+        out["mm10_" + k] = np.array(v)
+
+    # ---- mm10: the WHOLE update of one crystal, mm10_solve_crystal (mm10_a.f:1080-1157) = mm10_solve_strup (sub-stepping,
+    #      mm10_setup_np1, mm10_solve with its predictor / update Newton loops, line search, DGESV) -> mm10_tangent ->
+    #      mm10_a_make_symm_1 -> mm10_update_rotation -> mm10_output (DPOSV), from explicit n states.  Newton iteration counts
+    #      = numbers of Jacobian formations (calls of mm10_formJ11 / mm10_formJ).
+    it.module_vars["asymmetric_assembly"] = False
+
+    def new_state():
+        return NS(r=np.zeros((3, 3), order="F"), rp=np.zeros((3, 3), order="F"), stress=np.zeros(6), d=np.zeros(6), eps=np.zeros(6),
+                  euler_angles=np.zeros(3), slip_incs=np.zeros(ms_max), tau_tilde=np.zeros(mu), tt_rate=np.zeros(mu), u=np.zeros(mu),
+                  ep=np.zeros(6), ed=np.zeros(6), tangent=np.zeros((6, 6), order="F"), ms=np.zeros((6, ms_max), order="F"),
+                  qs=np.zeros((3, ms_max), order="F"), qc=np.zeros((3, ms_max), order="F"), tau_l=np.zeros(ms_max),
+                  gradfeinv=np.zeros((3, 3, 3), order="F"), dg=0.0, tinc=0.0, temp=0.0, mu_harden=0.0, work_inc=0.0, p_work_inc=0.0,
+                  p_strain_inc=0.0, step=0, elem=0, iter=0, gp=0, tau_v=0.0, tau_y=0.0)
+    it.derived_factories["crystal_state"] = new_state
+    crec = {k: [] for k in ("slip_type", "angles", "iter", "R", "D6", "n_state", "params", "stress", "tt", "tt_rate", "tangent", "Rp", "euler",
+                            "eps", "slip_incs", "u", "ep", "ed", "iters", "fail")}
+    for slip_type in (1, 8):
+        b, nrm = slip_vectors(slip_type)
+        nslip = len(b)
+        for case in range(5):
+            ang = rng.uniform(0.0, 360.0, 3)
+            e_mod, nu = 200000.0, 0.3
+            prm = dict(rate_n=20.0 if case != 3 else 7.5, theta_0=100.0, tau_y=100.0, tau_v=100.0, voche_m=1.0 if case != 3 else 1.7,
+                       iD_v=0.0 if case != 2 else 1e-7, e=e_mod, nu=nu)
+            Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
+            Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
+            Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+            g = np.zeros((3, 3), order="F")
+            it.call("mm10_rotation_matrix", ang.copy(), "kocks", "degrees", g, 6)
+            trot = np.asfortranarray(g.T)
+            RE = np.zeros((6, 6), order="F")
+            it.call("mm10_rt2rve", trot, RE)
+            props = NS(nslip=nslip, num_hard=1, h_type=1, out=6, alter_mode=False, eps_dot_0_y=1.0e10, k_0=0.0, burgers=2.87e-7, cp_031=0.0,
+                       rate_n=prm["rate_n"], theta_0=prm["theta_0"], tau_y=prm["tau_y"], tau_v=prm["tau_v"], voche_m=prm["voche_m"],
+                       id_v=prm["iD_v"], stiffness=np.asfortranarray(RE @ Cc @ RE.T), ms=np.zeros((6, ms_max), order="F"),
+                       qs=np.zeros((3, ms_max), order="F"), ns=np.zeros((3, ms_max), order="F"), debug=False, gpall=False, gpp=0, solver=True,
+                       strategy=True, atol=1e-5, atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, miter=30, tang_calc=0,
+                       g=np.asfortranarray(g), init_angles=ang.copy(), angle_type=1, angle_convention=1)
+            for s_ in range(nslip):
+                bs, ns_ = trot @ b[s_], trot @ nrm[s_]
+                A = np.outer(bs, ns_)
+                ev, wv = np.zeros(6), np.zeros(3)
+                it.call("mm10_et2ev", np.asfortranarray(0.5 * (A + A.T)), ev)
+                it.call("mm10_wt2wv", np.asfortranarray(0.5 * (A - A.T)), wv)
+                props.ms[:, s_], props.qs[:, s_], props.ns[:, s_] = ev, wv, ns_
+            # n state: case 0 virgin (step-1 values), others a loaded, rotated state
+            n = new_state()
+            n.r[...] = np.eye(3); n.rp[...] = np.eye(3); n.tau_tilde[0] = prm["tau_y"] + 1.0e-5; n.euler_angles[:] = ang
+            if case > 0:
+                w = rng.standard_normal(3) * 0.02
+                Wm = np.array([[0, w[2], w[1]], [-w[2], 0, w[0]], [-w[1], -w[0], 0.0]])
+                q_, r_ = np.linalg.qr(np.eye(3) + Wm + 0.5 * Wm @ Wm)
+                n.rp[...] = q_ * np.sign(np.diag(r_))[None, :]
+                n.stress[:] = rng.standard_normal(6) * 80.0
+                n.tau_tilde[0] = 100.0 + 15.0 * rng.random()
+                n.tt_rate[0] = 0.5 * rng.random()
+                n.d[:] = rng.standard_normal(6) * 1e-3
+                n.eps[:] = rng.standard_normal(6) * 1e-3
+            np1 = new_state()
+            fb[:] = 0; rb[:] = 0; fb[0] = np.eye(3) + 0.02 * rng.standard_normal((3, 3))
+            it.call("rtcmp1", 1, fb, rb)
+            np1.r[...] = rb[0] if case > 0 else np.eye(3)
+            scale = {0: 2e-3, 1: 1.5e-3, 2: 1e-3, 3: 2e-3, 4: 2.5e-2}[case]        # case 4: a 2.5 % increment, sub-stepped
+            np1.d[:] = rng.standard_normal(6) * scale
+            np1.tinc, np1.step, np1.iter, np1.elem, np1.gp = 1.0, 2, (0 if (case == 1 and slip_type == 1) else 1), 1, 1
+            n_state = np.concatenate([n.stress, [n.tau_tilde[0], n.tt_rate[0]], n.d, n.eps, n.euler_angles, np.asarray(n.rp).ravel(), np.asarray(n.r).ravel()])
+            it.calls.clear()
+            res = it.call("mm10_solve_crystal", props, np1, n, False, 6, False, 1, np.zeros(6), np1.iter == 0)
+            nj, nj11 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
+            for k, v in (("slip_type", slip_type), ("angles", ang), ("iter", np1.iter), ("R", np.asarray(np1.r).copy()), ("D6", np1.d.copy()),
+                         ("n_state", n_state), ("params", [prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
+                         ("stress", np1.stress.copy()), ("tt", np1.tau_tilde[0]), ("tt_rate", np1.tt_rate[0]), ("tangent", np.ascontiguousarray(np1.tangent)),
+                         ("Rp", np.ascontiguousarray(np1.rp)), ("euler", np1.euler_angles.copy()), ("eps", np1.eps.copy()),
+                         ("slip_incs", np1.slip_incs[:48].copy()), ("u", np1.u[:15].copy()), ("ep", np1.ep.copy()), ("ed", np1.ed.copy()),
+                         ("iters", [nj11 - nj, nj]), ("fail", bool(res.get("cut", False)))):
+                crec[k].append(v)
+    for k, v in crec.items():
+        out["crystal_" + k] = np.array(v)
 
     prov = "; ".join(f"{f} sha256 {hashlib.sha256(open(REF + f, 'rb').read()).hexdigest()[:16]}" for f in FILES)
     out["provenance"] = np.array("maranGit/CPFFT src: " + prov + "; executed by tools/fortran_subset.py (tools/make_reference_vectors.py)")
