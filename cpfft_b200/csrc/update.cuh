@@ -286,7 +286,10 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
         if (HARD == MM10_MTS) {
           mts_at_temperature(cr, 297.0, &mu_full, &mts);
           c.ur = mu_full / cr.mu_0; c.tau_y = tau_y_full; c.tau_v = tau_v_full;
-          double dps[6] = {0, 0, 0, 0, 0, 0}, wqs[3] = {0, 0, 0}, sabs = 0.0;
+          // va: the reference hands `symtqmat` (its column 1), not `symtqmat(1,i)`, to mm10_a_mult_type_4 (mm10_a.f:771-772),
+          // so sym(sigma W) of the FIRST slip system enters every term: 2 symSW(sigma, qc_1) sum_s slip_s.  Reproduced
+          // (established by executing the reference's mm10_tangent, tests/test_reference_vectors.py).
+          double dps[6] = {0, 0, 0, 0, 0, 0}, wqs[3] = {0, 0, 0}, sabs = 0.0, ssum = 0.0;
           const double tt = x[6], itt = 1.0 / tt, dgtt = c.dg / tt;
   #pragma unroll 1
           for (int s = 0; s < nslip; ++s) {
@@ -296,10 +299,14 @@ CPF_DI void upd_mm10_voxel(const UpdArgs& a, const int64_t e, double* sm) {
             const double slip = dgtt * cpf_pow_abs(fabs(rs * itt), c.rate_int, c.rate_n - 1.0) * rs;
   #pragma unroll
             for (int k = 0; k < 6; ++k) dps[k] += slip * ms[k];
+            if (s == 0) {
   #pragma unroll
-            for (int k = 0; k < 3; ++k) wqs[k] += slip * qs[k];
-            sabs += fabs(slip);
+              for (int k = 0; k < 3; ++k) wqs[k] = qs[k];
+            }
+            sabs += fabs(slip); ssum += slip;
           }
+  #pragma unroll
+          for (int k = 0; k < 3; ++k) wqs[k] *= ssum;
           double wc[3], sw[6];
           cpf_mv3(c.RWR, wqs, wc);
           cpf_symsw(x, wc, sw);

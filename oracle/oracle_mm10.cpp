@@ -618,7 +618,10 @@ static void mm10_tangent(const Props& p, State& np1, const double J[7][7]) {
     const double alpha = 2.0 / (3.0 * np1.dg * np1.dg);
     for (int i = 0; i < p.nslip; ++i) {
       double symtq[6], wv[6], dgdd[6];
-      symswmat_col(np1.stress, np1.qc[i], symtq);
+      // the reference passes `symtqmat`, not `symtqmat(1,i)`, to mm10_a_mult_type_4 (mm10_a.f:771-772): every slip system
+      // gets column 1, i.e. sym(sigma W) of the FIRST system.  Reproduced (found by executing the reference's
+      // mm10_tangent, tests/test_reference_vectors.py: with the per-system column the MTS tangent is 1e-4 off).
+      symswmat_col(np1.stress, np1.qc[0], symtq);
       for (int k = 0; k < 6; ++k) wv[k] = 2.0 * symtq[k];                   // mm10_a_mult_type_4
       for (int j = 0; j < 6; ++j)
         for (int k = 0; k < 6; ++k) wv[k] = wv[k] + p.stiffness[k][j] * np1.ms[i][j];

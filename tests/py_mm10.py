@@ -293,7 +293,9 @@ def update(cr, R, D, dt, sn, ttn, ttrate_n, Dn, Rpn, iter0, u1n=-1.0, u2n=-1.0):
         m = cr.mts
         d_mod = D.copy(); d_mod[3:] *= 0.5
         alpha = 2.0 / (3.0 * full.dg ** 2)
-        JA = sum(np.outer(cr.C @ ms + 2.0 * symsw(sig, qc), alpha * g * d_mod) for ms, qc, g in zip(full.ms, full.qc, gam))
+        # mm10_a.f:771-772 hands `symtqmat` (= its column 1), not `symtqmat(1,i)`, to mm10_a_mult_type_4: the sym(sigma W) of
+        # the FIRST slip system enters every term.  Reproduced (established by executing the reference, test_reference_vectors.py).
+        JA = sum(np.outer(cr.C @ ms + 2.0 * symsw(sig, full.qc[0]), alpha * g * d_mod) for ms, g in zip(full.ms, gam))
         dgc = full.dg / full.tinc
         kT = m["boltz"] * full.temp / (full.mu * m["b"] ** 3)
         lny, lnv = np.log(m["eps_dot_0_y"] / dgc), np.log(m["eps_dot_0_v"] / dgc)

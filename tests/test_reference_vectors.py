@@ -142,19 +142,24 @@ def test_mm10_setup_residual_jacobian(k):
     assert rel(J, V["mm10_J"][k]) <= 1e-12
 
 
-@pytest.mark.parametrize("k", range(10))
+@pytest.mark.parametrize("k", range(14))
 def test_mm10_whole_crystal_update(k):
     """mm10_solve_crystal of the reference (mm10_a.f:1080-1157), executed: mm10_solve_strup with its sub-stepping,
     mm10_setup_np1 / mm10_setup, mm10_solve (stress predictor and coupled update, Armijo line search, LAPACK DGESV),
     mm10_tangent, mm10_a_make_symm_1, mm10_update_rotation, mm10_output (lattice strain by DPOSV, Euler angles, slip
-    increments, the u(:) outputs) -- from explicit n states: virgin and loaded / rotated, fcc (0-4) and bcc48 (5-9), an
-    elastic iteration-0 sweep (1), the diffusion term (2, 7), n = 7.5 with voche_m = 1.7 (3, 8), and a 2.5 % strain increment
-    (4, 9) that makes mm10_solve fail and sub-step (fcc: five cuts, material_cut_step).  The oracle reproduces the
-    converged state AND the Newton iteration counts (predictor, update) = the reference's numbers of Jacobian formations."""
+    increments, the u(:) outputs) -- from explicit n states: virgin and loaded / rotated, fcc (0-6) and bcc48 (7-13), an
+    elastic iteration-0 sweep (1), the diffusion term (2, 9), n = 7.5 with voche_m = 1.7 (3, 10), a 2.5 % strain increment
+    (4, 11) that makes mm10_solve fail and sub-step (five cuts, material_cut_step), and the MTS hardening law (5, 6, 12, 13:
+    mm10_setup_mts, mm10_h / estress / ehard / ed / dgdd_mts and the JA, JB terms of the tangent).  The oracle reproduces
+    the converged state AND the Newton iteration counts (predictor, update) = the reference's numbers of Jacobian formations."""
     from cpfft_b200.problem import Crystal
     rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["crystal_params"][k]
-    cr = Crystal(slip_type=int(V["crystal_slip_type"][k]), elastic_type=1, h_type=1, e=e, nu=nu, mu=e / 2.0 / (1.0 + nu), harden_n=rate_n,
-                 theta_0=theta_0, tau_y=tau_y, tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+    cr = Crystal(slip_type=int(V["crystal_slip_type"][k]), elastic_type=1, h_type=int(V["crystal_h_type"][k]), e=e, nu=nu, mu=e / 2.0 / (1.0 + nu),
+                 harden_n=rate_n, theta_0=theta_0, tau_y=tau_y, tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+    if cr.h_type == 2:
+        for name, val in zip(V["crystal_mts_names"], V["crystal_mts_params"]):
+            if str(name) != "theta_0":
+                setattr(cr, str(name), float(val))
     r = Oracle.mm10_crystal_probe(cr, V["crystal_angles"][k], 1.0, V["crystal_R"][k], V["crystal_D6"][k], int(V["crystal_iter"][k]),
                                   V["crystal_n_state"][k])
     assert bool(r["fail"]) == bool(V["crystal_fail"][k])

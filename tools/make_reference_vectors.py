@@ -226,15 +226,18 @@ def main():
                   gradfeinv=np.zeros((3, 3, 3), order="F"), dg=0.0, tinc=0.0, temp=0.0, mu_harden=0.0, work_inc=0.0, p_work_inc=0.0,
                   p_strain_inc=0.0, step=0, elem=0, iter=0, gp=0, tau_v=0.0, tau_y=0.0)
     it.derived_factories["crystal_state"] = new_state
-    crec = {k: [] for k in ("slip_type", "angles", "iter", "R", "D6", "n_state", "params", "stress", "tt", "tt_rate", "tangent", "Rp", "euler",
+    MTS = dict(theta_0=1500.0, tau_a=20.0, tau_hat_y=180.0, g_0_y=0.4, tau_hat_v=300.0, g_0_v=1.2, burgers=2.5e-7, mu_0=80000.0, D_0=3000.0,
+               T_0=200.0, p_y=0.5, q_y=2.0, p_v=0.5, q_v=2.0, boltzman=1.3806e-20, eps_dot_0_y=1.0e10, eps_dot_0_v=1.0e10)   # tests/golden/decks/mts_mm10.in
+    crec = {k: [] for k in ("h_type", "slip_type", "angles", "iter", "R", "D6", "n_state", "params", "stress", "tt", "tt_rate", "tangent", "Rp", "euler",
                             "eps", "slip_incs", "u", "ep", "ed", "iters", "fail")}
     for slip_type in (1, 8):
         b, nrm = slip_vectors(slip_type)
         nslip = len(b)
-        for case in range(5):
+        for case in range(7):                                   # 5, 6: MTS hardening (h_type 2)
+            mts = case >= 5
             ang = rng.uniform(0.0, 360.0, 3)
             e_mod, nu = 200000.0, 0.3
-            prm = dict(rate_n=20.0 if case != 3 else 7.5, theta_0=100.0, tau_y=100.0, tau_v=100.0, voche_m=1.0 if case != 3 else 1.7,
+            prm = dict(rate_n=20.0 if case != 3 else 7.5, theta_0=100.0 if not mts else MTS["theta_0"], tau_y=100.0, tau_v=100.0, voche_m=1.0 if case != 3 else 1.7,
                        iD_v=0.0 if case != 2 else 1e-7, e=e_mod, nu=nu)
             Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
             Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
@@ -250,6 +253,12 @@ def main():
                        qs=np.zeros((3, ms_max), order="F"), ns=np.zeros((3, ms_max), order="F"), debug=False, gpall=False, gpp=0, solver=True,
                        strategy=True, atol=1e-5, atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, miter=30, tang_calc=0,
                        g=np.asfortranarray(g), init_angles=ang.copy(), angle_type=1, angle_convention=1)
+            if mts:
+                props.h_type = 2
+                props.burgers, props.id_v = MTS["burgers"], 0.0
+                for k_, v_ in MTS.items():
+                    if k_ not in ("theta_0", "burgers"):
+                        setattr(props, k_.lower(), v_)
             for s_ in range(nslip):
                 bs, ns_ = trot @ b[s_], trot @ nrm[s_]
                 A = np.outer(bs, ns_)
@@ -270,18 +279,22 @@ def main():
                 n.tt_rate[0] = 0.5 * rng.random()
                 n.d[:] = rng.standard_normal(6) * 1e-3
                 n.eps[:] = rng.standard_normal(6) * 1e-3
+            if mts:
+                n.u[0] = n.u[1] = -1.0                      # tau_y / mu_harden of the n state not set yet (mm10_init_mts)
+                n.tau_tilde[0] = 150.0 + 20.0 * rng.random()
             np1 = new_state()
+            np1.temp = 297.0                               # mm10.f: constant temperature of this code base; n%temp = 0
             fb[:] = 0; rb[:] = 0; fb[0] = np.eye(3) + 0.02 * rng.standard_normal((3, 3))
             it.call("rtcmp1", 1, fb, rb)
             np1.r[...] = rb[0] if case > 0 else np.eye(3)
-            scale = {0: 2e-3, 1: 1.5e-3, 2: 1e-3, 3: 2e-3, 4: 2.5e-2}[case]        # case 4: a 2.5 % increment, sub-stepped
+            scale = {0: 2e-3, 1: 1.5e-3, 2: 1e-3, 3: 2e-3, 4: 2.5e-2, 5: 1.5e-3, 6: 4e-3}[case]        # case 4: a 2.5 % increment, sub-stepped
             np1.d[:] = rng.standard_normal(6) * scale
             np1.tinc, np1.step, np1.iter, np1.elem, np1.gp = 1.0, 2, (0 if (case == 1 and slip_type == 1) else 1), 1, 1
             n_state = np.concatenate([n.stress, [n.tau_tilde[0], n.tt_rate[0]], n.d, n.eps, n.euler_angles, np.asarray(n.rp).ravel(), np.asarray(n.r).ravel()])
             it.calls.clear()
             res = it.call("mm10_solve_crystal", props, np1, n, False, 6, False, 1, np.zeros(6), np1.iter == 0)
             nj, nj11 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
-            for k, v in (("slip_type", slip_type), ("angles", ang), ("iter", np1.iter), ("R", np.asarray(np1.r).copy()), ("D6", np1.d.copy()),
+            for k, v in (("h_type", props.h_type), ("slip_type", slip_type), ("angles", ang), ("iter", np1.iter), ("R", np.asarray(np1.r).copy()), ("D6", np1.d.copy()),
                          ("n_state", n_state), ("params", [prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
                          ("stress", np1.stress.copy()), ("tt", np1.tau_tilde[0]), ("tt_rate", np1.tt_rate[0]), ("tangent", np.ascontiguousarray(np1.tangent)),
                          ("Rp", np.ascontiguousarray(np1.rp)), ("euler", np1.euler_angles.copy()), ("eps", np1.eps.copy()),
@@ -290,6 +303,8 @@ def main():
                 crec[k].append(v)
     for k, v in crec.items():
         out["crystal_" + k] = np.array(v)
+    out["crystal_mts_params"] = np.array([MTS[k] for k in sorted(MTS)])
+    out["crystal_mts_names"] = np.array(sorted(MTS))
 
     prov = "; ".join(f"{f} sha256 {hashlib.sha256(open(REF + f, 'rb').read()).hexdigest()[:16]}" for f in FILES)
     out["provenance"] = np.array("maranGit/CPFFT src: " + prov + "; executed by tools/fortran_subset.py (tools/make_reference_vectors.py)")
