@@ -181,3 +181,18 @@ def test_mm10_whole_crystal_update(k):
     for j in (5, 6, 7, 10, 11, 12, 13, 14):                    # u(6:8), u(11:15): max slip rate, its system, active systems, ...
         a, b = r["u"][j], V["crystal_u"][k][j]
         assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (j, a, b)
+
+
+@pytest.mark.parametrize("N", [3, 5])
+def test_G_K_dF_operator(N):
+    """the spectral operator G_K_dF of the reference (G_K_dF.f:11-87), executed for odd N: K4 : F by ddot42n, fftfem3d with
+    the phase ramp of formfftshift and a 3-D complex DFT on split real / imaginary arrays, the Green contraction of both
+    parts, ifftfem3d -- with and without the K4 contraction.  The oracle's operator (which the GPU kernels are held to at
+    1e-12 in tests/test_gpu_spectral.py) agrees to a few ulp; for odd N its Green operator is the reference's by construction."""
+    from cpfft_b200.polycrystal import polycrystal
+    o = Oracle(polycrystal(N, ngrains=2), threads=1)
+    o.K4[:] = V[f"GKdF_{N}_K4"].T
+    F = np.ascontiguousarray(V[f"GKdF_{N}_F"].T)
+    for flg, key in ((1, "with_K4"), (0, "without_K4")):
+        ref = V[f"GKdF_{N}_{key}"].T
+        assert rel(o.G_K_dF(F, flg), ref) <= 1e-14

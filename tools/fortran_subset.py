@@ -99,6 +99,13 @@ def _reshape_dummy(a, shape):
     """an actual argument seen through a dummy of another shape (sequence association), as a view"""
     if not isinstance(a, np.ndarray) or a.shape == tuple(shape):
         return a
+    if shape and shape[-1] == -1:                 # assumed size: as many trailing slices as the actual holds
+        lead = 1
+        for d in shape[:-1]:
+            lead *= d
+        if a.ndim == len(shape) and a.shape[:-1] == tuple(shape[:-1]):
+            return a
+        shape = tuple(shape[:-1]) + (a.size // max(lead, 1),)
     n = 1
     for d in shape:
         n *= d
@@ -200,6 +207,49 @@ BUILTIN_ARRAY_ARGS = {"vdmul": (1, 2, 3), "vdadd": (1, 2, 3), "daxpy": (2, 4), "
 BUILTIN_INFO_ARG = {"dgesv": 7, "dposv": 7}
 
 
+def _dcopy(n, x, incx, y, incy):
+    if incx != 1 or incy != 1:
+        raise FortranError("dcopy with non-unit stride")
+    n = int(n); y[:n] = x[:n]
+
+
+BUILTIN_SUBS.update({"dcopy": _dcopy, "omp_set_dynamic": lambda *a: None})
+BUILTIN_ARRAY_ARGS.update({"dcopy": (1, 3), "omp_set_dynamic": ()})
+
+
+# MKL DFTI as the reference uses it (G_K_dF.f:101-224): a 3-D complex transform on split real / imaginary arrays
+# (DFTI_REAL_REAL), in place, strides (0, 1, N, N*N), forward scale 1, backward scale as set.  Computed by numpy's FFT.
+def _dfti_create(h, prec, dom, ndim, dims):
+    h.dims = tuple(int(d) for d in np.ravel(dims)[:int(ndim)]); h.fs, h.bs = 1.0, 1.0
+    return 0
+
+
+def _dfti_set(h, key, val):
+    if key == "forward_scale":
+        h.fs = float(val)
+    elif key == "backward_scale":
+        h.bs = float(val)
+    return 0
+
+
+def _dfti_compute(h, re_, im_, sign):
+    n = int(np.prod(h.dims))
+    z = (re_[:n] + 1j * im_[:n]).reshape(tuple(reversed(h.dims)))      # column-major (N1, N2, N3) storage
+    z = np.fft.fftn(z) * h.fs if sign < 0 else np.fft.ifftn(z) * n * h.bs
+    re_[:n] = z.real.reshape(-1); im_[:n] = z.imag.reshape(-1)
+    return 0
+
+
+BUILTIN_FUNCS = {
+    "dfticreatedescriptor": _dfti_create, "dftisetvalue": _dfti_set, "dfticommitdescriptor": lambda h: 0, "dftifreedescriptor": lambda h: 0,
+    "dfticomputeforward": lambda h, a, b: _dfti_compute(h, a, b, -1), "dfticomputebackward": lambda h, a, b: _dfti_compute(h, a, b, +1),
+    "omp_get_thread_num": lambda: 0,
+}
+DFTI_CONSTS = {"dfti_double": "double", "dfti_complex": "complex", "dfti_complex_storage": "complex_storage", "dfti_real_real": "real_real",
+               "dfti_placement": "placement", "dfti_inplace": "inplace", "dfti_input_strides": "input_strides",
+               "dfti_output_strides": "output_strides", "dfti_forward_scale": "forward_scale", "dfti_backward_scale": "backward_scale"}
+
+
 def _ftn_pow(a, b):
     """x ** n for a small integer n as the multiplication chain a compiler emits (x*x, x*x*x ...), otherwise pow()"""
     if isinstance(b, (int, np.integer)) and not isinstance(b, bool):
@@ -260,6 +310,7 @@ def logical_lines(text):
                 res.append(ch.lower())
         line = "".join(res).rstrip()
         line = re.sub(r"\.\s*(eq|ne|lt|le|gt|ge|and|or|not|eqv|neqv|true|false)\s*\.", r".\1.", line)
+        line = re.sub(r"\(\s+/(?!=)", "(/", line); line = re.sub(r"/\s+\)", "/)", line)      # ( / 1, 2 / )
         if not line.strip():
             continue
         cont = len(line) > 5 and line[5] not in " 0" and line[:5].strip() == ""
@@ -515,6 +566,9 @@ class Translator:
                         break
                 if t in self.units and self.units[t][2] == "function":
                     return f"_fcall({t!r}, {', '.join(a[0] for a in args)})"
+                if t in BUILTIN_FUNCS:
+                    pa = [f"_flat_any({a[0]})" if a[0] in self.arrays else a[0] for a in args if a[0] != ""]
+                    return f"_bfunc[{t!r}]({', '.join(pa)})"
                 if derived or t in self.arrays:
                     if all(len(a) == 1 and a[0] in self.arrays for a in args):      # vector subscripts c(iv, jv)
                         return f"{t}[np.ix_({', '.join(a[0] + ' - 1' for a in args)})]"
@@ -663,8 +717,8 @@ class Interpreter:
             shape = ", ".join(f"int({tr.expr(d, arrays, scalars | known)})" for d in dims[a])
             py.append(f"{ind}{a} = np.zeros(({shape},), order='F'{', dtype=np.int64' if a in int_arrays else ''})")
         for a in args:
-            if a in arrays and dims.get(a) and not any(":" in d or d.strip() == "*" for d in dims[a]):
-                shape = ", ".join(f"int({tr.expr(d, arrays, scalars | known)})" for d in dims[a])
+            if a in arrays and dims.get(a) and not any(":" in d for d in dims[a]) and not any(d.strip() == "*" for d in dims[a][:-1]):
+                shape = ", ".join("-1" if d.strip() == "*" else f"int({tr.expr(d, arrays, scalars | known)})" for d in dims[a])
                 py.append(f"{ind}{a} = _reshape_dummy({a}, ({shape},))")
         for a in args:                                          # an array actual seen through a scalar dummy: its first element
             if a in scalar_types:
@@ -714,7 +768,7 @@ class Interpreter:
         self.sources[name] = src
         glob = {"np": np, "math": math, "_ftn_sign": _ftn_sign, "_ftn_mod": _ftn_mod, "_ftn_int": _ftn_int, "_ftn_div": _ftn_div, "_ftn_pow": _ftn_pow,
                 "_ftn_dot": _ftn_dot, "_ftn_nint": _ftn_nint, "_ftn_dble": _ftn_dble, "_ftn_isnan": _ftn_isnan, "_flat": _flat, "_reshape_dummy": _reshape_dummy, "_call": self.call, "_fcall": self.call, "_first": _first, "_assign_whole": _assign_whole,
-                "_builtin": BUILTIN_SUBS, "_flat_any": _flat_any, "_new_derived": self.new_derived, **self.consts, **self.module_vars}
+                "_builtin": BUILTIN_SUBS, "_bfunc": BUILTIN_FUNCS, **DFTI_CONSTS, "_flat_any": _flat_any, "_new_derived": self.new_derived, **self.consts, **self.module_vars}
         exec(compile(src, f"<fortran {name}>", "exec"), glob)
         self.funcs[name] = glob[name]
         self.funcs[name]._outs = outs

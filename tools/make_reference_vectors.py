@@ -22,6 +22,7 @@ order and precision the source states.  Routines (reference file:line of the sub
                 line search, DGESV), mm10_tangent (:658), mm10_update_rotation (:3310), mm10_output (:3433)      -> M3, M7-M10
   FFT_init.f:272 formG                                                   Green operator table, odd N     -> G3
   G_K_dF.f:241  ddot42n                                                  K4 : x with its summation tree  -> G1
+  G_K_dF.f:11   G_K_dF (+ fftfem3d :101, ifftfem3d :163, formfftshift FFT_init.f:355; DFTI by numpy)  the operator -> G2, G4, G5
 """
 import hashlib
 import os
@@ -305,6 +306,28 @@ def main():
         out["crystal_" + k] = np.array(v)
     out["crystal_mts_params"] = np.array([MTS[k] for k in sorted(MTS)])
     out["crystal_mts_names"] = np.array(sorted(MTS))
+
+    # ---- the spectral operator itself: G_K_dF (G_K_dF.f:11-87) = ddot42n with K4 -> fftfem3d (phase ramp of formfftshift,
+    #      MKL DFTI forward, split real / imaginary storage) -> two ddot42n with Ghat4 -> ifftfem3d, for odd N.  DFTI is
+    #      computed by numpy's FFT (tools/fortran_subset.py), everything else is the reference's own statements.
+    it.derived_factories["dfti_descriptor"] = NS
+    for N in (3, 5):
+        N3 = N ** 3
+        G = np.zeros((N3, 81), order="F"); c1 = np.zeros((N, N, N), order="F"); c2 = np.zeros((N, N, N), order="F")
+        K4 = np.asfortranarray(rng.standard_normal((N3, 81)) * 1e4 + 1e5 * np.eye(9).reshape(81)[None, :])
+        it3 = F.Interpreter(it.consts); it3.units = it.units; it3.derived_factories = it.derived_factories
+        it3.module_vars = dict(n=N, nhalf=(N + 1) // 2, n3=N3, ndim1=3, ndim2=9, ghat4=G, k4=K4, dims=np.array([N, N, N]), coeffs1=c1, coeffs2=c2,
+                               real1=np.zeros((N3, 9), order="F"), real2=np.zeros((N3, 9), order="F"), real3=np.zeros((N3, 9), order="F"))
+        it3.call("formg"); it3.call("formfftshift", c1, c2)
+        Fm = np.asfortranarray(rng.standard_normal((N3, 9)) * 1e-3)
+        res = []
+        for flg in (True, False):
+            GKF = np.zeros((N3, 9), order="F")
+            it3.call("g_k_df", Fm, GKF, flg)
+            res.append(np.ascontiguousarray(GKF))
+        out[f"GKdF_{N}_K4"], out[f"GKdF_{N}_F"] = np.ascontiguousarray(K4), np.ascontiguousarray(Fm)
+        out[f"GKdF_{N}_with_K4"], out[f"GKdF_{N}_without_K4"] = res
+        out[f"fftshift_{N}"] = np.array([np.ascontiguousarray(c1), np.ascontiguousarray(c2)])
 
     prov = "; ".join(f"{f} sha256 {hashlib.sha256(open(REF + f, 'rb').read()).hexdigest()[:16]}" for f in FILES)
     out["provenance"] = np.array("maranGit/CPFFT src: " + prov + "; executed by tools/fortran_subset.py (tools/make_reference_vectors.py)")
