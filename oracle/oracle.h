@@ -22,11 +22,12 @@
  * statement by statement by tools/fortran_subset.py (fixture
  * tests/golden/reference_vectors.npz, tests/test_reference_vectors.py): rtcmp1
  * (polar.f), getrm1, cep2A_a, mm10_rotation_matrix, mm10_RT2RVE / RT2RVW,
- * mm10_symSW, formG (odd N), the summation tree of ddot42n, mm10_setup /
- * mm10_formR / mm10_formJ, and mm10_solve_crystal end to end (converged state,
- * tangent, Newton iteration counts, failure flags; fcc and bcc48).  UNPINNED:
- * the block drivers (drive_eps_sig, rstgp1, mm10), mm01 and the MKL-based global
- * loop (FFT_nr3, fftPcg, fftfem3d); those are held by derived identities
+ * mm10_symSW, formG (odd N), ddot42n and the whole operator G_K_dF (DFTI by
+ * numpy), mm01 + cnst1, mm10_setup / mm10_formR / mm10_formJ, and
+ * mm10_solve_crystal end to end (converged state, tangent, Newton iteration
+ * counts, failure flags; Voce and MTS, fcc and bcc48).  UNPINNED: the block
+ * drivers (drive_eps_sig, rstgp1, mm10) and the MKL RCI-based global loop
+ * (FFT_nr3, fftPcg, tangent_homo); those are held by derived identities
  * (tests/test_oracle_*.py, tests/test_py_mm10.py): Green-operator projection
  * identities, independent numpy restatements of G_K_dF and of the crystal
  * update, finite-difference checks of cep2A / cnst1 / the local Jacobian /

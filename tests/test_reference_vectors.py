@@ -196,3 +196,29 @@ def test_G_K_dF_operator(N):
     for flg, key in ((1, "with_K4"), (0, "without_K4")):
         ref = V[f"GKdF_{N}_{key}"].T
         assert rel(o.G_K_dF(F, flg), ref) <= 1e-14
+
+
+def test_mm01_path_and_cnst1():
+    """mm01 (mm01.f:28-230 with mm01_set_history, mm01_init, mm01_simple1, mm01_sig_final, mm01_plastic_work) and the
+    consistent tangent cnst1 (:1222-1374) of the reference, executed along a four-increment path (elastic, plastic,
+    plastic in another direction, unloading) on six points with isotropic / mixed / kinematic hardening; the history
+    carries the integer state word packed in a double.  Held to: the numpy restatement tests/py_mm01.py (which the
+    oracle and the kernel source are checked against at 1e-12, tests/test_py_mm01.py)."""
+    import py_mm01
+    ym, nu, yld, hprime = V["mm01_props"]
+    beta = V["mm01_beta"]
+    nplastic = 0
+    for step in range(4):
+        hist0 = V["mm01_hist"][step] if step else py_mm01.initial_history(6, yld, hprime)
+        parts = [py_mm01.update(V["mm01_cgn"][step][i:i + 1], hist0[i:i + 1], V["mm01_deps"][step][i:i + 1], ym, nu, float(beta[i]), hprime, yld)
+                 for i in range(6)]                                # the restatement takes one beta per call
+        cgn1, hist1, cep = (np.concatenate([p_[k] for p_ in parts]) for k in range(3))
+        ref_c, ref_h = V["mm01_cgn1"][step], V["mm01_hist1"][step]
+        assert np.abs(cgn1[:, :6] - ref_c[:, :6]).max() <= 1e-12 * max(1.0, np.abs(ref_c[:, :6]).max())
+        assert np.abs(cgn1[:, 6:] - ref_c[:, 6:]).max() <= 1e-12 * max(1.0, np.abs(ref_c[:, 6:]).max())
+        assert np.array_equal(hist1[:, 3].view(np.int64), ref_h[:, 3].view(np.int64))          # the packed state word
+        mask = np.ones(11, dtype=bool); mask[3] = False
+        assert np.abs(hist1[:, mask] - ref_h[:, mask]).max() <= 1e-12 * max(1.0, np.abs(ref_h[:, mask]).max())
+        assert rel(cep, V["mm01_cep"][step]) <= 1e-12
+        nplastic += int(np.count_nonzero(ref_h[:, 3].view(np.int64) & 0xFFFFFFFF == 1))
+    assert nplastic > 0                                                                         # the path did yield

@@ -281,6 +281,9 @@ def _ftn_div(a, b):
     return a / b
 
 
+PYKW = re.compile(r"(?<![.\w%])(yield|lambda|pass|del|def|class|from|as|with|global|assert|async|await|except|finally|import|nonlocal|raise|try|is)(?![.\w])")
+
+
 class FortranError(Exception):
     pass
 
@@ -311,6 +314,8 @@ def logical_lines(text):
         line = "".join(res).rstrip()
         line = re.sub(r"\.\s*(eq|ne|lt|le|gt|ge|and|or|not|eqv|neqv|true|false)\s*\.", r".\1.", line)
         line = re.sub(r"\(\s+/(?!=)", "(/", line); line = re.sub(r"/\s+\)", "/)", line)      # ( / 1, 2 / )
+        if q is None and PYKW.search(line):          # Fortran names that are Python keywords (yield, lambda, in, ...)
+            line = line[:6] + PYKW.sub(lambda m_: m_.group(0) + "_", line[6:]) if "'" not in line and '"' not in line else line
         if not line.strip():
             continue
         cont = len(line) > 5 and line[5] not in " 0" and line[:5].strip() == ""
@@ -576,7 +581,9 @@ class Translator:
                 if t in INTRINSICS:
                     return f"{INTRINSICS[t]}({', '.join(a[0] for a in args)})"
                 raise FortranError(f"unknown function or undeclared array `{t}`")
-            return t + "_" if t in ("lambda", "in", "is", "def", "class", "from", "as", "with", "pass", "del", "global") else t
+            if t in getattr(self, "eq_scalars", ()):
+                return f"{t}[0]"
+            return t
         raise FortranError(f"unexpected token {t!r}")
 
     @staticmethod
@@ -632,6 +639,10 @@ class Interpreter:
                     data_init.append((nm.strip(), ("__derived__", m.group(1))))
                 continue
             if re.match(r"(implicit|use|include|intent|save|external|format|!dir|deallocate|type\s*\()", st) or st.startswith("c!dir"):
+                continue
+            m = re.match(r"equivalence\s*\(\s*(\w+)\s*,\s*(\w+)\s*\)\s*$", st)
+            if m:
+                data_init.append((m.group(1), ("__equiv__", m.group(2))))
                 continue
             m = re.match(r"dimension\s+(.*)$", st)
             if m:
@@ -706,6 +717,7 @@ class Interpreter:
                 break
         arrays, scalars, dims, data_init, local_consts, int_arrays, module_names, scalar_types, stmts = self._parse_decls(body)
         self._int_arrays = int_arrays
+        tr.eq_scalars = {(n_ if n_ in scalar_types else v_[1]) for n_, v_ in data_init if isinstance(v_, tuple) and v_[0] == "__equiv__"}
         known = set(self.consts) | set(local_consts)
         py = [f"def {name}({', '.join(a + '_' if a in ('lambda',) else a for a in args)}):"]
         ind = "    "
@@ -727,6 +739,13 @@ class Interpreter:
             if sname not in args and sname not in module_names:
                 py.append(f"{ind}{sname} = {'0' if typ.startswith('integer') else 'False' if typ.startswith('logical') else repr('') if typ.startswith('character') else '0.0'}")
         for n_, v_ in data_init:
+            if isinstance(v_, tuple) and v_[0] == "__equiv__":
+                dname, iname = (n_, v_[1]) if n_ in scalar_types else (v_[1], n_)
+                py.append(f"{ind}{dname} = np.zeros(1)")
+                py.append(f"{ind}{iname} = {dname}.view(np.int32)")
+        for n_, v_ in data_init:
+            if isinstance(v_, tuple) and v_[0] == "__equiv__":      # a double scalar and an integer(2) array sharing storage
+                continue
             if isinstance(v_, tuple):            # a local variable of derived type: made by the harness's factory
                 if n_ not in args:
                     py.append(f"{ind}{n_} = _new_derived({v_[1]!r})")

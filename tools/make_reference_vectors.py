@@ -22,6 +22,7 @@ order and precision the source states.  Routines (reference file:line of the sub
                 line search, DGESV), mm10_tangent (:658), mm10_update_rotation (:3310), mm10_output (:3433)      -> M3, M7-M10
   FFT_init.f:272 formG                                                   Green operator table, odd N     -> G3
   G_K_dF.f:241  ddot42n                                                  K4 : x with its summation tree  -> G1
+  mm01.f:28     mm01 (+ mm01_set_history, _init, _simple1, _sig_final, _plastic_work) and cnst1 (:1222)            -> M1
   G_K_dF.f:11   G_K_dF (+ fftfem3d :101, ifftfem3d :163, formfftshift FFT_init.f:355; DFTI by numpy)  the operator -> G2, G4, G5
 """
 import hashlib
@@ -35,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import fortran_subset as F  # noqa: E402
 
 REF = "/root/reference/src/"
-FILES = ["param_def", "mod_crystals.f", "polar.f", "cep2A.f", "mm10_a.f", "mm10_b.f", "FFT_init.f", "G_K_dF.f"]
+FILES = ["param_def", "mod_crystals.f", "polar.f", "cep2A.f", "mm10_a.f", "mm10_b.f", "FFT_init.f", "G_K_dF.f", "mm01.f"]
 
 
 def interpreter():
@@ -44,7 +45,7 @@ def interpreter():
     mc = open(REF + "mod_crystals.f").read()
     i0 = mc.index("      module mm10_constants")
     it.add_constants(mc[i0:mc.index("      end module", i0)])
-    for f in FILES[2:]:
+    for f in FILES[2:8]:
         it.load(open(REF + f).read())
     return it
 
@@ -328,6 +329,36 @@ def main():
         out[f"GKdF_{N}_K4"], out[f"GKdF_{N}_F"] = np.ascontiguousarray(K4), np.ascontiguousarray(Fm)
         out[f"GKdF_{N}_with_K4"], out[f"GKdF_{N}_without_K4"] = res
         out[f"fftshift_{N}"] = np.array([np.ascontiguousarray(c1), np.ascontiguousarray(c2)])
+
+    # ---- mm01 (bilinear Mises plasticity, mixed hardening) + cnst1: a four-increment path (elastic, plastic, plastic in
+    #      another direction, unloading) on 6 points with beta = 0, 0.5, 1; the history carries the packed state word
+    #      (equivalence of a double and two integers, mm01.f:253-255)
+    it.load(open(REF + "mm01.f").read())
+    npt = 6
+    ym = np.zeros(mx); nuv = np.zeros(mx); beta = np.zeros(mx); hp = np.zeros(mx); yld = np.zeros(mx)
+    ym[:npt], nuv[:npt], yld[:npt] = 69000.0, 0.33, 100.0
+    beta[:npt] = [0.0, 0.5, 1.0, 0.0, 0.5, 1.0]
+    tan_e = 1000.0
+    hp[:npt] = tan_e * 69000.0 / (69000.0 - tan_e)
+    lnelas = np.zeros(mx)
+    cgn = np.zeros((mx, 9), order="F"); hist = np.zeros((npt, 11), order="F")
+    dirs = rng.standard_normal((4, npt, 6))
+    amps = [4e-4, 3e-3, 2e-3, -1.5e-3]
+    m01 = {k: [] for k in ("deps", "cgn", "hist", "cgn1", "hist1", "cep")}
+    for step in range(1, 5):
+        deps = np.zeros((mx, 6), order="F"); deps[:npt] = amps[step - 1] * dirs[step - 1] * np.array([1, 1, 1, 2, 2, 2.0])
+        cgn1 = np.zeros((mx, 9), order="F"); hist1 = np.zeros((npt, 11), order="F"); rtse = np.zeros((mx, 6), order="F")
+        it.call("mm01", npt, 1, 1, step, 1, ym, nuv, beta, hp, lnelas, yld, cgn, cgn1, deps, hist, hist1, rtse, np.zeros(mx), ym, nuv, 6)
+        cep = np.zeros((mx, 6, 6), order="F")
+        it.call("cnst1", npt, cep, rtse, nuv, ym, np.asfortranarray(hist1[:, 1].copy()), np.asfortranarray(hist1[:, 4].copy()), beta,
+                np.asfortranarray(hist1[:, 0].copy()), np.asfortranarray(hist1[:, 3].copy()), 1, 6)
+        for k, v in (("deps", deps[:npt]), ("cgn", cgn[:npt]), ("hist", hist), ("cgn1", cgn1[:npt]), ("hist1", hist1), ("cep", cep[:npt])):
+            m01[k].append(np.ascontiguousarray(v).copy())
+        cgn, hist = cgn1, hist1
+    for k, v in m01.items():
+        out["mm01_" + k] = np.array(v)
+    out["mm01_props"] = np.array([69000.0, 0.33, 100.0, hp[0]])
+    out["mm01_beta"] = beta[:npt].copy()
 
     prov = "; ".join(f"{f} sha256 {hashlib.sha256(open(REF + f, 'rb').read()).hexdigest()[:16]}" for f in FILES)
     out["provenance"] = np.array("maranGit/CPFFT src: " + prov + "; executed by tools/fortran_subset.py (tools/make_reference_vectors.py)")
