@@ -207,6 +207,15 @@ class Oracle:
         return R.reshape(3, 3)
 
     @staticmethod
+    def kinematics_probe(Fn, Fn1, ur6):
+        a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (Fn, Fn1, ur6)]
+        R, uddt, P = np.zeros(9), np.zeros(6), np.zeros(9)
+        L = _lib()
+        L.orc_kinematics_probe.argtypes = [_DP] * 6
+        L.orc_kinematics_probe(_dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(R), _dp(uddt), _dp(P))
+        return R.reshape(3, 3), uddt, P
+
+    @staticmethod
     def getrm1(R, opt):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
         q = np.zeros(36)

@@ -705,6 +705,26 @@ extern "C" void orc_getrm1(const double* R9, int opt, double* q36) {
 extern "C" void orc_ddot42_point(const double* A81, const double* B9, double* C9) {
   ddot42_point([&](int col) { return A81[col]; }, B9, C9);
 }
+// the kinematics of do_nleps_block around the material call (drive_eps_sig.f:203-300), for tests/test_reference_vectors.py:
+// (Fn, Fn1) -> R of Fn1, unrotated strain increment uddt (rtcmp1, inv33, mul33, getrm1 opt 1, qmply1), and for an
+// unrotated stress ur6 the first Piola-Kirchhoff stress P (getrm1 opt 2, qmply1, inv33, cs2p); 3x3 row-major
+extern "C" void orc_kinematics_probe(const double* Fn9, const double* Fn19, const double* ur6, double* R9, double* uddt6, double* P9) {
+  M33 fn, fn1, fnh, dfn, rnh, R, fnhinv, fn1inv;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { fn[i][j] = Fn9[3 * i + j]; fn1[i][j] = Fn19[3 * i + j]; }
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { fnh[i][j] = 0.5 * (fn[i][j] + fn1[i][j]); dfn[i][j] = fn1[i][j] - fn[i][j]; }
+  rtcmp1(fnh, rnh); rtcmp1(fn1, R);
+  double detFh, detF, ddt[6], cs[6];
+  inv33(fnh, fnhinv, &detFh);
+  mul33(dfn, fnhinv, ddt);
+  M66 qnhalf, qtn1;
+  getrm1(qnhalf, rnh, 1);
+  qmply1(qnhalf, ddt, uddt6);
+  getrm1(qtn1, R, 2);
+  qmply1(qtn1, ur6, cs);
+  inv33(fn1, fn1inv, &detF);
+  cs2p(cs, fn1inv, detF, P9);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R9[3 * i + j] = R[i][j];
+}
 extern "C" void orc_cep2A(const double* Fn9, const double* Fn19, const double* t6, const double* cep36, double* A81) {
   M33 fn, fn1, fnh, rnh, R, fnhinv, fn1inv, t; M66 C;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { fn[i][j] = Fn9[3 * i + j]; fn1[i][j] = Fn19[3 * i + j]; fnh[i][j] = 0.5 * (fn[i][j] + fn1[i][j]); }

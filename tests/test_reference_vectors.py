@@ -222,3 +222,15 @@ def test_mm01_path_and_cnst1():
         assert rel(cep, V["mm01_cep"][step]) <= 1e-12
         nplastic += int(np.count_nonzero(ref_h[:, 3].view(np.int64) & 0xFFFFFFFF == 1))
     assert nplastic > 0                                                                         # the path did yield
+
+
+def test_kinematics_of_do_nleps_block():
+    """the kinematics around the material call (drive_eps_sig.f:203-300) with the reference's own rtcmp1, inv33, mul33, getrm1,
+    qmply1 and cs2p in the block driver's order: R of F_n+1, the unrotated strain increment fed to the material models, and the
+    first Piola-Kirchhoff stress of an unrotated Cauchy stress.  The polar noise band (test_polar_rtcmp1) enters through R."""
+    for Fn, Fn1, ur6, R, uddt, P, amp in zip(V["kin_Fn"], V["kin_Fn1"], V["kin_ur6"], V["kin_R"], V["kin_uddt"], V["kin_P"], V["kin_amp"]):
+        Ro, uo, Po = Oracle.kinematics_probe(Fn, Fn1, ur6)
+        band = 1e-14 + 3e-15 / amp ** 2
+        assert np.abs(Ro - R).max() <= band
+        assert np.abs(uo - uddt).max() <= 2.0 * band * np.abs(uddt).max() + 1e-18
+        assert np.abs(Po - P).max() <= band * np.abs(P).max()

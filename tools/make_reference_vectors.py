@@ -22,6 +22,7 @@ order and precision the source states.  Routines (reference file:line of the sub
                 line search, DGESV), mm10_tangent (:658), mm10_update_rotation (:3310), mm10_output (:3433)      -> M3, M7-M10
   FFT_init.f:272 formG                                                   Green operator table, odd N     -> G3
   G_K_dF.f:241  ddot42n                                                  K4 : x with its summation tree  -> G1
+  drive_eps_sig.f:1017 inv33, :1110 mul33, :1182 cs2p, qmply1.f:15 qmply1, in do_nleps_block's order (:203-300)   -> K1, K3
   mm01.f:28     mm01 (+ mm01_set_history, _init, _simple1, _sig_final, _plastic_work) and cnst1 (:1222)            -> M1
   G_K_dF.f:11   G_K_dF (+ fftfem3d :101, ifftfem3d :163, formfftshift FFT_init.f:355; DFTI by numpy)  the operator -> G2, G4, G5
 """
@@ -36,7 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import fortran_subset as F  # noqa: E402
 
 REF = "/root/reference/src/"
-FILES = ["param_def", "mod_crystals.f", "polar.f", "cep2A.f", "mm10_a.f", "mm10_b.f", "FFT_init.f", "G_K_dF.f", "mm01.f"]
+FILES = ["param_def", "mod_crystals.f", "polar.f", "cep2A.f", "mm10_a.f", "mm10_b.f", "FFT_init.f", "G_K_dF.f", "mm01.f", "drive_eps_sig.f", "qmply1.f"]
 
 
 def interpreter():
@@ -329,6 +330,39 @@ def main():
         out[f"GKdF_{N}_K4"], out[f"GKdF_{N}_F"] = np.ascontiguousarray(K4), np.ascontiguousarray(Fm)
         out[f"GKdF_{N}_with_K4"], out[f"GKdF_{N}_without_K4"] = res
         out[f"fftshift_{N}"] = np.array([np.ascontiguousarray(c1), np.ascontiguousarray(c2)])
+
+    # ---- the kinematics of do_nleps_block around the material call (drive_eps_sig.f:203-300): the call sequence is the
+    #      block driver's, every routine is the reference's: rtcmp1 (Fnh, Fn1), inv33, mul33, getrm1 opt 1, qmply1 -> uddt;
+    #      getrm1 opt 2, qmply1, inv33, cs2p -> P
+    it.load(open(REF + "drive_eps_sig.f").read()); it.load(open(REF + "qmply1.f").read())
+    kin = {k: [] for k in ("amp", "Fn", "Fn1", "ur6", "R", "uddt", "P", "detF")}
+    for amp in (1e-3, 1e-2, 0.1, 0.3):
+        for _ in range(3):
+            Fn = rand_rotation(rng) @ (np.eye(3) + amp * rng.standard_normal((3, 3))) if amp >= 0.1 else np.eye(3) + amp * rng.standard_normal((3, 3))
+            Fn1 = Fn + 0.3 * amp * rng.standard_normal((3, 3))
+            ur6 = 200.0 * rng.standard_normal(6)
+            B3 = lambda: np.zeros((mx, 3, 3), order="F")
+            fnb, fn1b, fnh, dfn, rnh, Rb, fnhinv, fn1inv = (B3() for _ in range(8))
+            fnb[0], fn1b[0] = Fn, Fn1
+            fnh[0] = 0.5 * (fnb[0] + fn1b[0]); dfn[0] = fn1b[0] - fnb[0]
+            it.call("rtcmp1", 1, fnh, rnh); it.call("rtcmp1", 1, fn1b, Rb)
+            detFh, detF = np.zeros(mx), np.zeros(mx)
+            it.call("inv33", 1, 1, fnh, fnhinv, detFh)
+            ddt, uddt, cs, urb = (np.zeros((mx, 6), order="F") for _ in range(4))
+            it.call("mul33", 1, 1, dfn, fnhinv, ddt, 6)
+            q1, q2 = np.zeros((mx, 6, 6), order="F"), np.zeros((mx, 6, 6), order="F")
+            it.call("getrm1", 1, q1, rnh, 1)
+            it.call("qmply1", 1, mx, 6, q1, ddt, uddt)
+            urb[0] = ur6
+            it.call("getrm1", 1, q2, Rb, 2)
+            it.call("qmply1", 1, mx, 6, q2, urb, cs)
+            it.call("inv33", 1, 1, fn1b, fn1inv, detF)
+            Pb = np.zeros((mx, 9), order="F")
+            it.call("cs2p", 1, 1, cs, fn1inv, detF, Pb)
+            for k, v in (("amp", amp), ("Fn", Fn), ("Fn1", Fn1), ("ur6", ur6), ("R", Rb[0].copy()), ("uddt", uddt[0].copy()), ("P", Pb[0].copy()), ("detF", detF[0])):
+                kin[k].append(v)
+    for k, v in kin.items():
+        out["kin_" + k] = np.array(v)
 
     # ---- mm01 (bilinear Mises plasticity, mixed hardening) + cnst1: a four-increment path (elastic, plastic, plastic in
     #      another direction, unloading) on 6 points with beta = 0, 0.5, 1; the history carries the packed state word
