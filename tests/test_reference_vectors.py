@@ -22,6 +22,13 @@ from oracle import binding as ob
 V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
 
 
+@pytest.fixture(scope="module")
+def libs(oracle_built):
+    from host_kernels import HostKernels, build
+    build()
+    return HostKernels, Oracle
+
+
 def rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
 
@@ -234,3 +241,79 @@ def test_kinematics_of_do_nleps_block():
         assert np.abs(Ro - R).max() <= band
         assert np.abs(uo - uddt).max() <= 2.0 * band * np.abs(uddt).max() + 1e-18
         assert np.abs(Po - P).max() <= band * np.abs(P).max()
+
+
+def _hist_layout(nslip, num_hard=1):
+    """cpf_hist_layout (cpfft_b200/csrc/material_types.h) = mm10_d.f:137-331"""
+    use_max = nslip == 48 or num_hard == 48
+    lc5 = 48 if use_max else nslip
+    l6, l7, l8, l9 = (48, 48, 48, 48) if use_max else (nslip, num_hard, 15, num_hard)
+    L = dict(work=72, slipsum=75)
+    L["c_stress"] = 75 + lc5; L["c_euler"] = L["c_stress"] + 6; L["c_Rp"] = L["c_euler"] + 3; L["c_D"] = L["c_Rp"] + 9
+    L["c_eps"] = L["c_D"] + 6; L["c_slipinc"] = L["c_eps"] + 6; L["c_tt"] = L["c_slipinc"] + l6; L["c_u"] = L["c_tt"] + l7
+    L["c_ttrate"] = L["c_u"] + l8
+    return L
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_kernel_source_voxel_against_reference(libs, k):
+    """THE PRODUCT'S KERNEL SOURCE (cpfft_b200/csrc/update.cuh, mm10.cuh, kin.cuh compiled for the host, the same text nvcc
+    compiles) and the oracle, against one voxel run end to end by the reference's own source the way do_nleps_block does it
+    (drive_eps_sig.f:203-300): (Fn, Fn1, loaded / rotated n state) -> rtcmp1, inv33, mul33, getrm1, qmply1 -> mm10_solve_crystal ->
+    getrm1, qmply1, cs2p -> P and cep2A_a -> dP/dF.  fcc Voce at 1 %, 3 % and 0.2 % strain, bcc48, and MTS.  Stress, P, the
+    81-entry tangent, tau_tilde, Rp, Euler angles, lattice strain and the local Newton iteration counts."""
+    from cpfft_b200.polycrystal import polycrystal
+    from cpfft_b200.problem import Crystal
+    HostKernels, OracleCls = libs
+    rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["voxel_params"][k]
+    cr = Crystal(slip_type=int(V["voxel_slip_type"][k]), elastic_type=1, h_type=int(V["voxel_h_type"][k]), e=e, nu=nu, mu=e / 2.0 / (1.0 + nu),
+                 harden_n=rate_n, theta_0=theta_0, tau_y=tau_y, tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+    if cr.h_type == 2:
+        for name, val in zip(V["crystal_mts_names"], V["crystal_mts_params"]):
+            if str(name) != "theta_0":
+                setattr(cr, str(name), float(val))
+    p = polycrystal(2, ngrains=1)
+    p.crystals = [cr]
+    p.angles = np.ascontiguousarray(np.tile(V["voxel_angles"][k], (p.N3, 1)))
+    nslip = 12 if cr.slip_type == 1 else 48
+    L = _hist_layout(nslip)
+    ns = V["voxel_n_state"][k]
+    Rp = ns[23:32].reshape(3, 3)
+    band = 3e-15 / 0.002 ** 2 if k == 2 else 1e-10          # polar noise band of the step (0.2 % strain in case 2)
+    for impl in (HostKernels(p), OracleCls(p, threads=1)):
+        is_host = isinstance(impl, HostKernels)
+        hist_n = impl.hist_n if is_host else impl.hist_n.T      # (H, N3) views of both layouts
+        impl.drive_eps_sig(1, 0)                               # allocates / initialises the state (step-1 virgin sweep)
+        hist_n[...] = 0.0
+        for q in range(6):
+            hist_n[L["c_stress"] + q] = ns[q]; hist_n[L["c_D"] + q] = ns[8 + q]; hist_n[L["c_eps"] + q] = ns[14 + q]
+        hist_n[L["c_tt"]] = ns[6]; hist_n[L["c_ttrate"]] = ns[7]
+        for q in range(3):
+            hist_n[L["c_euler"] + q] = ns[20 + q]
+        for i in range(3):
+            for j in range(3):
+                hist_n[L["c_Rp"] + 3 * j + i] = Rp[i, j]
+                hist_n[63 + 3 * j + i] = 1.0 if i == j else 0.0
+        if cr.h_type == 2:
+            hist_n[L["c_u"]] = -1.0; hist_n[L["c_u"] + 1] = -1.0
+        if is_host:
+            impl.urcs_n[...] = 0.0; impl.eps_n[...] = 0.0
+            impl.Fn[...] = V["voxel_Fn"][k].reshape(9, 1); impl.Fn1[...] = V["voxel_Fn1"][k].reshape(9, 1)
+        else:
+            impl.urcs_n[...] = 0.0
+            impl.Fn[...] = V["voxel_Fn"][k].reshape(9, 1); impl.Fn1[...] = V["voxel_Fn1"][k].reshape(9, 1)
+        assert impl.drive_eps_sig(2, 1) == 0
+        P = impl.Pn1[:, 0]
+        K4 = impl.K4[:, 0]
+        sig = impl.urcs_n1[:6, 0] if is_host else impl.urcs_n1[0, :6]
+        h1 = impl.hist_n1[:, 0] if is_host else impl.hist_n1[0]
+        tag = "kernel source" if is_host else "oracle"
+        assert rel(sig, V["voxel_stress"][k]) <= max(1e-10, band), tag
+        assert rel(P, V["voxel_P"][k]) <= max(1e-10, band), tag
+        assert rel(K4, V["voxel_dPdF"][k]) <= max(2e-10, band), tag      # measured 1e-13 .. 8e-11 (case 2)
+        assert abs(h1[L["c_tt"]] - V["voxel_tt"][k]) <= 1e-10 * V["voxel_tt"][k], tag
+        Rp1 = np.array([[h1[L["c_Rp"] + 3 * j + i] for j in range(3)] for i in range(3)])
+        assert np.abs(Rp1 - V["voxel_Rp"][k]).max() <= 1e-12, tag
+        assert np.abs(h1[L["c_euler"]:L["c_euler"] + 3] - V["voxel_euler"][k]).max() <= max(1e-9, 100.0 * band), tag
+        assert np.abs(h1[L["c_eps"]:L["c_eps"] + 6] - V["voxel_eps"][k]).max() <= max(1e-12, band), tag
+        assert list(impl.local_iters[0]) == list(V["voxel_iters"][k]), tag

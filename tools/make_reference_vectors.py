@@ -22,6 +22,7 @@ order and precision the source states.  Routines (reference file:line of the sub
                 line search, DGESV), mm10_tangent (:658), mm10_update_rotation (:3310), mm10_output (:3433)      -> M3, M7-M10
   FFT_init.f:272 formG                                                   Green operator table, odd N     -> G3
   G_K_dF.f:241  ddot42n                                                  K4 : x with its summation tree  -> G1
+  do_nleps_block end to end for one mm10 voxel: (Fn, Fn1, n state) -> kinematics -> mm10_solve_crystal -> cs2p, cep2A_a -> P, dP/dF
   drive_eps_sig.f:1017 inv33, :1110 mul33, :1182 cs2p, qmply1.f:15 qmply1, in do_nleps_block's order (:203-300)   -> K1, K3
   mm01.f:28     mm01 (+ mm01_set_history, _init, _simple1, _sig_final, _plastic_work) and cnst1 (:1222)            -> M1
   G_K_dF.f:11   G_K_dF (+ fftfem3d :101, ifftfem3d :163, formfftshift FFT_init.f:355; DFTI by numpy)  the operator -> G2, G4, G5
@@ -308,6 +309,106 @@ def main():
         out["crystal_" + k] = np.array(v)
     out["crystal_mts_params"] = np.array([MTS[k] for k in sorted(MTS)])
     out["crystal_mts_names"] = np.array(sorted(MTS))
+
+    # ---- one voxel end to end, the way do_nleps_block runs it (drive_eps_sig.f:203-300): (Fn, Fn1, n state) -> kinematics ->
+    #      mm10_solve_crystal -> rotation of the stress, cs2p -> P, cep2A_a -> dP/dF.  Every routine is the reference's; the few
+    #      assignments between them (Fnh, dFn, t33 from the stress vector) are do_nleps_block's / cep2A's.
+    it.load(open(REF + "drive_eps_sig.f").read()); it.load(open(REF + "qmply1.f").read())
+    vrec = {k: [] for k in ("h_type", "slip_type", "angles", "params", "Fn", "Fn1", "n_state", "R", "uddt", "stress", "tt", "tt_rate", "tangent", "Rp",
+                            "euler", "eps", "slip_incs", "P", "dPdF", "iters")}
+    rng_main, rng = rng, np.random.default_rng(20240608)        # own stream: the sections below keep their inputs
+    for (slip_type, mts_) in ((1, False), (1, False), (1, False), (8, False), (1, True)):
+        b, nrm = slip_vectors(slip_type)
+        nslip = len(b)
+        case = len(vrec["Fn"])
+        ang = rng.uniform(0.0, 360.0, 3)
+        e_mod, nu = 200000.0, 0.3
+        prm = dict(rate_n=20.0, theta_0=100.0 if not mts_ else MTS["theta_0"], tau_y=100.0, tau_v=100.0, voche_m=1.0, iD_v=0.0, e=e_mod, nu=nu)
+        Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
+        Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
+        Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+        g = np.zeros((3, 3), order="F")
+        it.call("mm10_rotation_matrix", ang.copy(), "kocks", "degrees", g, 6)
+        trot = np.asfortranarray(g.T)
+        RE = np.zeros((6, 6), order="F")
+        it.call("mm10_rt2rve", trot, RE)
+        props = NS(nslip=nslip, num_hard=1, h_type=2 if mts_ else 1, out=6, alter_mode=False, eps_dot_0_y=1.0e10, k_0=0.0, burgers=2.87e-7, cp_031=0.0,
+                   rate_n=prm["rate_n"], theta_0=prm["theta_0"], tau_y=prm["tau_y"], tau_v=prm["tau_v"], voche_m=prm["voche_m"],
+                   id_v=prm["iD_v"], stiffness=np.asfortranarray(RE @ Cc @ RE.T), ms=np.zeros((6, ms_max), order="F"),
+                   qs=np.zeros((3, ms_max), order="F"), ns=np.zeros((3, ms_max), order="F"), debug=False, gpall=False, gpp=0, solver=True,
+                   strategy=True, atol=1e-5, atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, miter=30, tang_calc=0,
+                   g=np.asfortranarray(g), init_angles=ang.copy(), angle_type=1, angle_convention=1)
+        if mts_:
+            props.burgers = MTS["burgers"]
+            for k_, v_ in MTS.items():
+                if k_ not in ("theta_0", "burgers"):
+                    setattr(props, k_.lower(), v_)
+        for s_ in range(nslip):
+            bs, ns_ = trot @ b[s_], trot @ nrm[s_]
+            A = np.outer(bs, ns_)
+            ev, wv = np.zeros(6), np.zeros(3)
+            it.call("mm10_et2ev", np.asfortranarray(0.5 * (A + A.T)), ev)
+            it.call("mm10_wt2wv", np.asfortranarray(0.5 * (A - A.T)), wv)
+            props.ms[:, s_], props.qs[:, s_], props.ns[:, s_] = ev, wv, ns_
+        # a loaded n state and a deformation step
+        n = new_state()
+        n.r[...] = np.eye(3); n.euler_angles[:] = ang
+        w = rng.standard_normal(3) * 0.02
+        Wm = np.array([[0, w[2], w[1]], [-w[2], 0, w[0]], [-w[1], -w[0], 0.0]])
+        q_, r_ = np.linalg.qr(np.eye(3) + Wm + 0.5 * Wm @ Wm)
+        n.rp[...] = q_ * np.sign(np.diag(r_))[None, :]
+        n.stress[:] = rng.standard_normal(6) * 80.0
+        n.tau_tilde[0] = (150.0 if mts_ else 100.0) + 15.0 * rng.random()
+        n.tt_rate[0] = 0.5 * rng.random()
+        n.d[:] = rng.standard_normal(6) * 1e-3
+        n.eps[:] = rng.standard_normal(6) * 1e-3
+        if mts_:
+            n.u[0] = n.u[1] = -1.0
+        amp = (0.01, 0.03, 0.002, 0.01, 0.01)[case]
+        Fn = np.eye(3) + amp * rng.standard_normal((3, 3))
+        Fn1 = Fn + 0.25 * amp * rng.standard_normal((3, 3))
+        B3 = lambda: np.zeros((mx, 3, 3), order="F")
+        fnb, fn1b, fnh, dfn, rnh, Rb, fnhinv, fn1inv = (B3() for _ in range(8))
+        fnb[0], fn1b[0] = Fn, Fn1
+        fnh[0] = 0.5 * (fnb[0] + fn1b[0]); dfn[0] = fn1b[0] - fnb[0]
+        it.call("rtcmp1", 1, fnh, rnh); it.call("rtcmp1", 1, fn1b, Rb)
+        detFh, detF = np.zeros(mx), np.zeros(mx)
+        it.call("inv33", 1, 1, fnh, fnhinv, detFh)
+        ddt, uddt, cs, urb = (np.zeros((mx, 6), order="F") for _ in range(4))
+        it.call("mul33", 1, 1, dfn, fnhinv, ddt, 6)
+        q1, q2 = np.zeros((mx, 6, 6), order="F"), np.zeros((mx, 6, 6), order="F")
+        it.call("getrm1", 1, q1, rnh, 1)
+        it.call("qmply1", 1, mx, 6, q1, ddt, uddt)
+        np1 = new_state()
+        np1.temp = 297.0
+        np1.r[...] = Rb[0]; np1.d[:] = uddt[0]
+        np1.tinc, np1.step, np1.iter, np1.elem, np1.gp = 1.0, 2, 1, 1, 1
+        n_state = np.concatenate([n.stress, [n.tau_tilde[0], n.tt_rate[0]], n.d, n.eps, n.euler_angles, np.asarray(n.rp).ravel(), np.asarray(n.r).ravel()])
+        it.calls.clear()
+        res = it.call("mm10_solve_crystal", props, np1, n, False, 6, False, 1, np.zeros(6), False)
+        assert not res.get("cut", False)
+        nj, nj11 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
+        urb[0] = np1.stress
+        it.call("getrm1", 1, q2, Rb, 2)
+        it.call("qmply1", 1, mx, 6, q2, urb, cs)
+        it.call("inv33", 1, 1, fn1b, fn1inv, detF)
+        Pb = np.zeros((mx, 9), order="F")
+        it.call("cs2p", 1, 1, cs, fn1inv, detF, Pb)
+        t6 = np1.stress
+        t33 = np.array([[t6[0], t6[3], t6[5]], [t6[3], t6[1], t6[4]], [t6[5], t6[4], t6[2]]])
+        dPdF = np.zeros(81)
+        it.call("cep2a_a", np.asfortranarray(Fn), np.asfortranarray(t33), np.asfortranarray(np1.tangent.copy()), np.asfortranarray(rnh[0].copy()),
+                float(detFh[0]), np.asfortranarray(fnhinv[0].copy()), np.asfortranarray(Rb[0].copy()), np.asfortranarray(Fn1),
+                np.asfortranarray(fn1inv[0].copy()), float(detF[0]), dPdF)
+        for k, v in (("h_type", props.h_type), ("slip_type", slip_type), ("angles", ang), ("params", [prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
+                     ("Fn", Fn), ("Fn1", Fn1), ("n_state", n_state), ("R", Rb[0].copy()), ("uddt", uddt[0].copy()), ("stress", np1.stress.copy()),
+                     ("tt", np1.tau_tilde[0]), ("tt_rate", np1.tt_rate[0]), ("tangent", np.ascontiguousarray(np1.tangent)), ("Rp", np.ascontiguousarray(np1.rp)),
+                     ("euler", np1.euler_angles.copy()), ("eps", np1.eps.copy()), ("slip_incs", np1.slip_incs[:48].copy()), ("P", Pb[0].copy()),
+                     ("dPdF", dPdF.copy()), ("iters", [nj11 - nj, nj])):
+            vrec[k].append(v)
+    for k, v in vrec.items():
+        out["voxel_" + k] = np.array(v)
+    rng = rng_main
 
     # ---- the spectral operator itself: G_K_dF (G_K_dF.f:11-87) = ddot42n with K4 -> fftfem3d (phase ramp of formfftshift,
     #      MKL DFTI forward, split real / imaginary storage) -> two ddot42n with Ghat4 -> ifftfem3d, for odd N.  DFTI is
