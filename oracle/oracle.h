@@ -25,9 +25,15 @@
  * mm10_symSW, formG (odd N), ddot42n and the whole operator G_K_dF (DFTI by
  * numpy), mm01 + cnst1, mm10_setup / mm10_formR / mm10_formJ, and
  * mm10_solve_crystal end to end (converged state, tangent, Newton iteration
- * counts, failure flags; Voce and MTS, fcc and bcc48).  UNPINNED: the block
- * drivers (drive_eps_sig, rstgp1, mm10) and the MKL RCI-based global loop
- * (FFT_nr3, fftPcg, tangent_homo); those are held by derived identities
+ * counts, failure flags; Voce and MTS, fcc and bcc48), one voxel through
+ * do_nleps_block's sequence, and A WHOLE JOB (tests/golden/reference_global.npz,
+ * tests/test_reference_global.py): FFT_nr3, fftPcg, NBC_update, tangent_homo,
+ * G_K_dF and the wrapper mm10 executed on a 3^3 polycrystal under mixed boundary
+ * conditions -- the oracle's solver reproduces it with the CG iteration count of
+ * every Newton-loop solve, the sweep and the outer-iteration counts identical.
+ * NOT the reference's text in that run: MKL's closed RCI CG (restated from its
+ * documentation) and the gather / scatter of the block driver.  Beyond the pin
+ * the oracle is held by derived identities
  * (tests/test_oracle_*.py, tests/test_py_mm10.py): Green-operator projection
  * identities, independent numpy restatements of G_K_dF and of the crystal
  * update, finite-difference checks of cep2A / cnst1 / the local Jacobian /

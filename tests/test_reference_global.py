@@ -1,0 +1,137 @@
+"""The global solver loop held to a run of the REFERENCE'S OWN SOURCE.
+
+tests/golden/reference_global.npz is a whole job -- a 3 x 3 x 3 fcc polycrystal (one orientation per voxel, Voce hardening)
+pulled in uniaxial tension under mixed boundary conditions (F_xx prescribed, P_yy = P_zz = 0, no mean shear) for three load
+steps into the plastic range -- run by maranGit/CPFFT's FFT_nr3, fftPcg, NBC_update, tangent_homo, G_K_dF and, per point,
+the crystal-plasticity wrapper mm10 with everything below it, executed statement by statement by tools/fortran_subset.py
+(generator and the exact list of what is and is not the reference's text: tools/make_reference_global.py; MKL's RCI CG is
+restated from its documentation).  Runs without /root/reference.
+
+What is compared, and how tightly: the trajectory of a Newton / CG solve is fixed by its tolerances (NR 1e-5, CG 1e-10, the
+shipped decks' values), two correct implementations agree in the converged fields to about the CG tolerance times the number
+of corrections -- measured here 1e-11 in F, 4e-9 (relative) in P -- and in every iteration count exactly."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import Oracle
+
+V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_global.npz"))
+N, NSTEP = int(V["N"]), int(V["nstep"])
+
+
+def problem():
+    from cpfft_b200.polycrystal import polycrystal
+    from cpfft_b200.problem import Crystal
+    rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["params"]
+    cr = Crystal(slip_type=1, elastic_type=1, h_type=1, e=e, nu=nu, mu=e / 2.0 / (1.0 + nu), harden_n=rate_n, theta_0=theta_0, tau_y=tau_y,
+                 tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+    p = polycrystal(N, ngrains=1)
+    p.crystals = [cr]
+    p.angles = np.ascontiguousarray(V["angles"])
+    p.FP_max, p.isNBC, p.mults = V["FP_max"].copy(), V["isNBC"].astype(np.int32), V["mults"].copy()
+    p.tolNR, p.tolPCG, p.maxIter = float(V["tolNR"]), float(V["tolPCG"]), int(V["maxIter"])
+    return p
+
+
+def reference_iterations():
+    """per load step: the CG iteration counts of the Newton-loop solves (tangent_homo's nine solves per call taken out), the
+    number of material sweeps and of tangent_homo calls"""
+    cg = V["cg"]
+    newton_cg, seen = [], {}
+    for k, (th, its) in enumerate(cg):
+        seen[th] = seen.get(th, 0) + 1
+        if seen[th] > 9:                               # the first nine solves after a tangent_homo call are its own
+            newton_cg.append((k, int(its)))
+    bounds = [0] + [int(x) for x in V["step_n_cg"]]
+    per_step_cg = [[its for k, its in newton_cg if bounds[s] <= k < bounds[s + 1]] for s in range(NSTEP)]
+    sweeps = [0] + [int(x) for x in V["step_n_sweeps"]]
+    per_step_sweeps = [sweeps[s + 1] - sweeps[s] - (1 if s == 0 else 0) for s in range(NSTEP)]     # the first sweep is FFT_finite_3d.f:145
+    th = [1] + [int(x) for x in V["step_n_tangent_homo"]]
+    return per_step_cg, per_step_sweeps, [th[s + 1] - th[s] for s in range(NSTEP)]
+
+
+def test_provenance_names_the_reference_sources():
+    p = str(V["provenance"])
+    for f in ("FFT_nr3.f", "tangent_homo.f", "G_K_dF.f", "mm10_a.f", "polar.f", "cep2A.f", "fortran_subset"):
+        assert f in p
+    assert int(V["step_n_tangent_homo"][-1]) > NSTEP          # the stress-controlled outer loop iterated
+
+
+def test_initial_tangent(oracle_built):
+    """drive_eps_sig(1, 0) at F = I (FFT_finite_3d.f:145): the elastic dP/dF of every voxel"""
+    o = Oracle(problem(), threads=1)
+    o.drive_eps_sig(1, 0)
+    assert np.abs(o.K4.T - V["K4_initial"]).max() <= 1e-14 * np.abs(V["K4_initial"]).max()
+
+
+@pytest.mark.parametrize("polar", ["double", "quad"])
+def test_oracle_solver_follows_the_reference_run(oracle_built, polar):
+    """FFT_nr3 of the oracle against FFT_nr3 of the reference: per load step the converged F and P fields, the mean
+    deformation gradient the stress-controlled loop arrives at, the mean stress, and -- exactly -- the CG iteration count of
+    every Newton-loop solve, the number of material sweeps and the number of outer (mean-stress) iterations."""
+    ref_cg, ref_sweeps, ref_outer = reference_iterations()
+    for k in range(1, NSTEP + 1):
+        o = Oracle(problem(), threads=1, polar=polar)
+        o.drive_eps_sig(1, 0)
+        res = o.FFT_nr3(k)
+        assert res["rc"] == 0
+        F1, P1 = V["step_Fn1"][k - 1], V["step_Pn1"][k - 1]
+        assert np.abs(o.Fn1.T - F1).max() <= 1e-10
+        assert np.abs(o.Pn1.T - P1).max() <= 2e-8 * np.abs(P1).max()
+        assert np.abs(res["Pbar"][k - 1] - P1.mean(axis=0)).max() <= 2e-8 * np.abs(P1).max()
+        assert np.abs(o.Fn1.mean(axis=1) - F1.mean(axis=0)).max() <= 1e-11
+        if k == NSTEP:
+            for s in range(NSTEP):
+                assert [int(x) for x in res["cg_iters"][s]] == ref_cg[s], (s, res["cg_iters"][s], ref_cg[s])
+            # Newton iterations + one closing sweep per outer iteration = the reference's material sweeps of the step
+            for s in range(NSTEP):
+                assert int(res["nr_iters"][s]) + ref_outer[s] + 1 == ref_sweeps[s], (s, res["nr_iters"], ref_outer, ref_sweeps)
+
+
+@pytest.fixture(scope="module")
+def host(oracle_built):
+    from host_kernels import HostKernels, build
+    build()
+    return HostKernels
+
+
+@pytest.mark.parametrize("k", range(1, NSTEP + 1))
+def test_kernel_source_sweep_on_the_reference_state(host, k):
+    """THE PRODUCT'S KERNEL SOURCE (host build, tests/native/material_host.cpp) on the state the reference run passed through:
+    history and stresses of step k-1 as the reference left them, F_n and the converged F_n+1 of step k -> the closing sweep of
+    the step.  P, the unrotated Cauchy stress, the hardening variable, Rp, the stored tangent and -- exactly -- the summed
+    local Newton counts of all 27 points against the reference's own sweep.  Uniaxial tension makes two principal stretches
+    nearly equal (0.99936 / 0.99909), where the reference's closed-form polar decomposition is at its noisiest (polar.f:224-307,
+    DESIGN.md section 4): R itself differs by 1e-9 .. 4e-9 between two evaluations of the same formulas, and everything rotated
+    by it follows; quantities that do not pass through R (Rp, lattice strain, tau_tilde) agree to 1e-11."""
+    p = problem()
+    h = host(p)
+    assert h.H == int(V["hist_size"])
+    h.drive_eps_sig(1, 0)
+    eye = np.eye(3).reshape(9, 1)
+    Fn = eye if k == 1 else V["step_Fn1"][k - 2].T
+    h.Fn[...] = Fn; h.Fn1[...] = V["step_Fn1"][k - 1].T
+    if k > 1:
+        h.hist_n[...] = V["step_hist"][k - 2].T
+        h.urcs_n[...] = V["step_urcs"][k - 2].T
+    last = [s for s in V["sweeps"] if s[0] == k][-1]
+    assert h.drive_eps_sig(k, int(last[1])) == 0
+    P1, H1, U1 = V["step_Pn1"][k - 1], V["step_hist"][k - 1], V["step_urcs"][k - 1]
+    hk = h.hist_n1.T
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    c0 = 75 + 12                                               # crystal block: stress 6, euler 3, Rp 9, D 6, eps 6, slip 12, tau_tilde
+    assert np.abs(hk[:, 63:72] - H1[:, 63:72]).max() <= 1e-8                  # R of F = R U as stored: measured 1.3e-9 .. 3.5e-9, the band
+    assert rel(h.Pn1.T, P1) <= 2e-8                                           # measured 3e-9 .. 5e-9
+    assert rel(h.urcs_n1.T[:, :6], U1[:, :6]) <= 5e-9                         # unrotated Cauchy stress, measured 2e-10 .. 7e-10
+    assert rel(h.urcs_n1.T[:, 6:9], U1[:, 6:9]) <= 2e-8                       # work densities, plastic strain
+    assert rel(hk[:, :36], H1[:, :36]) <= 5e-9                                # [D] as stored, measured 4e-10 .. 6e-10
+    assert rel(hk[:, c0:c0 + 6], H1[:, c0:c0 + 6]) <= 5e-9                    # crystal stress
+    assert np.abs(hk[:, c0 + 9:c0 + 18] - H1[:, c0 + 9:c0 + 18]).max() <= 1e-10          # Rp, measured 1e-12 .. 7e-12
+    assert np.abs(hk[:, c0 + 24:c0 + 30] - H1[:, c0 + 24:c0 + 30]).max() <= 1e-10        # lattice strain, measured 4e-12 .. 8e-12
+    assert rel(hk[:, c0 + 42], H1[:, c0 + 42]) <= 1e-9                        # tau_tilde, measured 5e-12 .. 2e-11
+    assert rel(hk[:, c0 + 30:c0 + 42], H1[:, c0 + 30:c0 + 42]) <= 2e-8        # slip increments, measured 5e-10 .. 2e-9
+    assert rel(hk[:, 75:87], H1[:, 75:87]) <= 2e-8                            # accumulated slip
+    it = np.asarray(h.local_iters)
+    assert (int(it[:, 0].sum()), int(it[:, 1].sum())) == (int(last[2]), int(last[3]))     # 164 / 85, 117 / 116, 103 / 100 Jacobians

@@ -35,6 +35,7 @@ INTRINSICS = {
     "dot_product": "_ftn_dot", "matmul": "np.matmul", "transpose": "np.transpose", "maxval": "np.max", "minval": "np.min",
     "isnan": "_ftn_isnan", "any": "np.any", "all": "np.all", "size": "np.size", "log10": "math.log10", "dlog10": "math.log10", "idint": "_ftn_int", "ifix": "_ftn_int", "dfloat": "float",
     "sinh": "math.sinh", "cosh": "math.cosh", "tanh": "math.tanh", "nint": "_ftn_nint", "float": "float",
+    "exponent": "(lambda x_: math.frexp(x_)[1])", "epsilon": "(lambda x_: 2.220446049250313e-16)",
 }
 
 
@@ -81,10 +82,33 @@ def _flat(a, *idx):
     return v[off:]
 
 
+def _flat0(a, *idx0):
+    """_flat with zero-based indices (the form the expression translator produces)"""
+    return _flat(a, *[int(i) + 1 for i in idx0])
+
+
+def _dnrm2(n, x, incx):                       # BLAS: Euclidean norm (unit stride)
+    n = int(n)
+    return float(math.sqrt(float(np.dot(x[:n], x[:n]))))
+
+
+def _ddot(n, x, incx, y, incy):               # BLAS: dot product (unit strides), accumulated in index order
+    n = int(n)
+    return float(np.dot(x[:n], y[:n]))
+
+
+def _dscal(n, alpha, x, incx):                # BLAS: x *= alpha
+    n = int(n); x[:n] = alpha * x[:n]
+
+
+ADDRESS_FUNCS = {"dnrm2": (1,), "ddot": (1, 3)}      # function arguments passed by address: array or first element of a run
+
+
 def _assign_whole(a, v):
     """a = v for a whole array.  A longer rank-1 right-hand side is cut to the extent of the left-hand side: what the
-    reference's compiler does with its one non-conforming assignment, work_vec1(7) = matmul(trans_J(14,7), R)
-    (mm10_a.f:3220, the first 7 entries are the intended J^T R)."""
+    reference's compiler does with its non-conforming assignments: work_vec1(7) = matmul(trans_J(14,7), R) (mm10_a.f:3220,
+    the first 7 entries are the intended J^T R) and n%slip_incs(1:len2-1) = history(1,sh:eh), n%u(1:len2-1) = history(1,sh:eh)
+    (mm10_a.f:2535, 2548: one element short, the last slip increment / user value of the n state is not loaded)."""
     if isinstance(v, np.ndarray) and v.ndim == 1 and a.ndim == 1 and v.size > a.size:
         a[...] = v[:a.size]
     else:
@@ -213,8 +237,8 @@ def _dcopy(n, x, incx, y, incy):
     n = int(n); y[:n] = x[:n]
 
 
-BUILTIN_SUBS.update({"dcopy": _dcopy, "omp_set_dynamic": lambda *a: None})
-BUILTIN_ARRAY_ARGS.update({"dcopy": (1, 3), "omp_set_dynamic": ()})
+BUILTIN_SUBS.update({"dcopy": _dcopy, "omp_set_dynamic": lambda *a: None, "dscal": _dscal})
+BUILTIN_ARRAY_ARGS.update({"dcopy": (1, 3), "omp_set_dynamic": (), "dscal": (2,)})
 
 
 # MKL DFTI as the reference uses it (G_K_dF.f:101-224): a 3-D complex transform on split real / imaginary arrays
@@ -243,7 +267,7 @@ def _dfti_compute(h, re_, im_, sign):
 BUILTIN_FUNCS = {
     "dfticreatedescriptor": _dfti_create, "dftisetvalue": _dfti_set, "dfticommitdescriptor": lambda h: 0, "dftifreedescriptor": lambda h: 0,
     "dfticomputeforward": lambda h, a, b: _dfti_compute(h, a, b, -1), "dfticomputebackward": lambda h, a, b: _dfti_compute(h, a, b, +1),
-    "omp_get_thread_num": lambda: 0,
+    "omp_get_thread_num": lambda: 0, "dnrm2": _dnrm2, "ddot": _ddot,
 }
 DFTI_CONSTS = {"dfti_double": "double", "dfti_complex": "complex", "dfti_complex_storage": "complex_storage", "dfti_real_real": "real_real",
                "dfti_placement": "placement", "dfti_inplace": "inplace", "dfti_input_strides": "input_strides",
@@ -408,7 +432,7 @@ def split_top(s, sep=","):
     return out
 
 
-TOKEN = re.compile(r"\s*(?:(\d+\.?\d*(?:[de][+-]?\d+)?|\.\d+(?:[de][+-]?\d+)?)|(\.[a-z]+\.)|('(?:[^']|'')*'|\"[^\"]*\")|(\w+(?:\s*%\s*\w+)*)|(\*\*|==|/=|<=|>=|\(/|/\)|[-+*/(),:<>=\[\]]))")
+TOKEN = re.compile(r"\s*(?:(\d+\.?\d*(?:[de][+-]?\d+)?|\.\d+(?:[de][+-]?\d+)?)|(\.[a-z]+\.)|('(?:[^']|'')*'|\"[^\"]*\")|(\w+(?:\s*%\s*\w+)*)|(%\s*\w+(?:\s*%\s*\w+)*)|(\*\*|==|/=|<=|>=|\(/|/\)|[-+*/(),:<>=\[\]]))")
 DOTOPS = {".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".and.": " and ", ".or.": " or ",
           ".not.": " not ", ".true.": "True", ".false.": "False", ".eqv.": "==", ".neqv.": "!="}
 
@@ -428,7 +452,7 @@ class Translator:
             m = TOKEN.match(s, pos)
             if not m or m.end() == pos:
                 raise FortranError(f"cannot tokenise: {s[pos:]!r} in {s!r}")
-            num, dot, string, name, op = m.groups()
+            num, dot, string, name, attr, op = m.groups()
             if num is not None:
                 out.append(("num", num))
             elif dot is not None:
@@ -437,6 +461,8 @@ class Translator:
                 out.append(("str", string))
             elif name is not None:
                 out.append(("name", name))
+            elif attr is not None:
+                out.append(("attr", attr))
             else:
                 out.append(("op", op))
             pos = m.end()
@@ -555,29 +581,29 @@ class Translator:
                 t = re.sub(r"\s*%\s*", ".", t)
             if self._peek() == ("op", "("):
                 self._take()
-                args = []
-                while True:
-                    parts = [""]
-                    while True:
-                        k2, t2 = self._peek()
-                        if (k2, t2) in (("op", ","), ("op", ")")):
-                            break
-                        if (k2, t2) == ("op", ":"):
-                            self._take(); parts.append("")
-                            continue
-                        parts[-1] = self._or()
-                    args.append(parts)
-                    if self._take() == ("op", ")"):
-                        break
+                args = self._arglist()
                 if t in self.units and self.units[t][2] == "function":
                     return f"_fcall({t!r}, {', '.join(a[0] for a in args)})"
+                if t in ADDRESS_FUNCS:
+                    pa = []
+                    for k_, a in enumerate(args):
+                        mm = re.match(r"^([\w.]+)\[(.+)\]$", a[0])
+                        pa.append(f"_flat0({mm.group(1)}, {mm.group(2)})" if k_ in ADDRESS_FUNCS[t] and mm else
+                                  f"_flat_any({a[0]})" if k_ in ADDRESS_FUNCS[t] else a[0])
+                    return f"_bfunc[{t!r}]({', '.join(pa)})"
                 if t in BUILTIN_FUNCS:
                     pa = [f"_flat_any({a[0]})" if a[0] in self.arrays else a[0] for a in args if a[0] != ""]
                     return f"_bfunc[{t!r}]({', '.join(pa)})"
                 if derived or t in self.arrays:
                     if all(len(a) == 1 and a[0] in self.arrays for a in args):      # vector subscripts c(iv, jv)
                         return f"{t}[np.ix_({', '.join(a[0] + ' - 1' for a in args)})]"
-                    return f"{t}[{', '.join(self._index(a) for a in args)}]"
+                    src = f"{t}[{', '.join(self._index(a) for a in args)}]"
+                    while self._peek()[0] == "attr":            # a%b(i, j)%c(k): component of an element of an array of objects
+                        src += re.sub(r"\s*%\s*", ".", self._take()[1])
+                        if self._peek() == ("op", "("):
+                            self._take()
+                            src += f"[{', '.join(self._index(a) for a in self._arglist())}]"
+                    return src
                 if t in INTRINSICS:
                     return f"{INTRINSICS[t]}({', '.join(a[0] for a in args)})"
                 raise FortranError(f"unknown function or undeclared array `{t}`")
@@ -585,6 +611,23 @@ class Translator:
                 return f"{t}[0]"
             return t
         raise FortranError(f"unexpected token {t!r}")
+
+    def _arglist(self):
+        args = []
+        while True:
+            parts = [""]
+            while True:
+                k2, t2 = self._peek()
+                if (k2, t2) in (("op", ","), ("op", ")")):
+                    break
+                if (k2, t2) == ("op", ":"):
+                    self._take(); parts.append("")
+                    continue
+                parts[-1] = self._or()
+            args.append(parts)
+            if self._take() == ("op", ")"):
+                break
+        return args
 
     @staticmethod
     def _index(parts):
@@ -611,6 +654,7 @@ class Interpreter:
         self.derived_factories = {}    # derived type name -> callable making a fresh object (types.SimpleNamespace) for locals
         self.calls = {}
         self.module_vars = {}          # variables of `use <module>` (arrays by reference, scalars read-only): set by the harness
+        self.module_members = {}       # module name -> names of module_vars a `use <module>` without an only-list brings in
 
     def load(self, text):
         self.units.update(split_units(logical_lines(text)))
@@ -623,6 +667,7 @@ class Interpreter:
         arrays, scalars, dims, data_init, local_consts, int_arrays, module_names = set(), set(), {}, [], {}, set(), set()
         scalar_types = {}
         stmts = []
+        use_all = set()
         for lab, st in body:
             m = re.match(r"use\s+\w+\s*,\s*only\s*:\s*(.*)$", st)
             if m:
@@ -632,6 +677,10 @@ class Interpreter:
                         raise FortranError(f"module variable {nm} not provided")
                     (arrays if isinstance(self.module_vars[nm], np.ndarray) else scalars).add(nm)
                     module_names.add(nm)
+                continue
+            m = re.match(r"use\s+(\w+)\s*$", st)
+            if m:
+                use_all |= set(self.module_members.get(m.group(1), ()))
                 continue
             m = re.match(r"type\s*\(\s*(\w+)\s*\)\s*(?:,[^:]*)?::\s*(.*)$", st)
             if m:
@@ -655,6 +704,9 @@ class Interpreter:
                 rest = m.group(1)
                 for names, vals in re.findall(r"([^/]+)/([^/]+)/", rest):
                     ns, vs = split_top(names.strip().strip(",")), split_top(vals)
+                    if len(ns) == 1 and len(vs) > 1:              # data a / v1, v2, ... /: an array filled in storage order
+                        data_init.append((ns[0].strip(), ("__data_array__", [v_.strip() for v_ in vs])))
+                        continue
                     for n_, v_ in zip(ns, vs):
                         data_init.append((n_.strip(), v_.strip()))
                 continue
@@ -693,6 +745,9 @@ class Interpreter:
                             data_init.append((item, init))
                 continue
             stmts.append((lab, st))
+        for nm in use_all - arrays - scalars - set(local_consts):        # `use module` without only: what the unit does not declare itself
+            (arrays if isinstance(self.module_vars[nm], np.ndarray) else scalars).add(nm)
+            module_names.add(nm)
         return arrays, scalars, dims, data_init, local_consts, int_arrays, module_names, scalar_types, stmts
 
     def compile(self, name):
@@ -717,6 +772,8 @@ class Interpreter:
                 break
         arrays, scalars, dims, data_init, local_consts, int_arrays, module_names, scalar_types, stmts = self._parse_decls(body)
         self._int_arrays = int_arrays
+        array_equiv = [(n_, v_[1]) for n_, v_ in data_init if isinstance(v_, tuple) and v_[0] == "__equiv__" and n_ in arrays and v_[1] in arrays]
+        data_init = [(n_, v_) for n_, v_ in data_init if not (isinstance(v_, tuple) and v_[0] == "__equiv__" and n_ in arrays and v_[1] in arrays)]
         tr.eq_scalars = {(n_ if n_ in scalar_types else v_[1]) for n_, v_ in data_init if isinstance(v_, tuple) and v_[0] == "__equiv__"}
         known = set(self.consts) | set(local_consts)
         py = [f"def {name}({', '.join(a + '_' if a in ('lambda',) else a for a in args)}):"]
@@ -728,6 +785,10 @@ class Interpreter:
                 continue
             shape = ", ".join(f"int({tr.expr(d, arrays, scalars | known)})" for d in dims[a])
             py.append(f"{ind}{a} = np.zeros(({shape},), order='F'{', dtype=np.int64' if a in int_arrays else ''})")
+        for a_, b_ in array_equiv:                            # equivalence( matrix, vector ): the vector is a view of the matrix
+            if len(dims[a_]) < len(dims[b_]):
+                a_, b_ = b_, a_
+            py.append(f"{ind}{b_} = {a_}.reshape(-1, order='F')")
         for a in args:
             if a in arrays and dims.get(a) and not any(":" in d for d in dims[a]) and not any(d.strip() == "*" for d in dims[a][:-1]):
                 shape = ", ".join("-1" if d.strip() == "*" else f"int({tr.expr(d, arrays, scalars | known)})" for d in dims[a])
@@ -745,6 +806,9 @@ class Interpreter:
                 py.append(f"{ind}{iname} = {dname}.view(np.int32)")
         for n_, v_ in data_init:
             if isinstance(v_, tuple) and v_[0] == "__equiv__":      # a double scalar and an integer(2) array sharing storage
+                continue
+            if isinstance(v_, tuple) and v_[0] == "__data_array__":
+                py.append(f"{ind}{n_}.T.reshape(-1)[:{len(v_[1])}] = [{', '.join(tr.expr(x_, arrays, scalars | known) for x_ in v_[1])}]")
                 continue
             if isinstance(v_, tuple):            # a local variable of derived type: made by the harness's factory
                 if n_ not in args:
@@ -786,7 +850,7 @@ class Interpreter:
         self.array_dummies[name] = [a in arrays for a in args]
         self.sources[name] = src
         glob = {"np": np, "math": math, "_ftn_sign": _ftn_sign, "_ftn_mod": _ftn_mod, "_ftn_int": _ftn_int, "_ftn_div": _ftn_div, "_ftn_pow": _ftn_pow,
-                "_ftn_dot": _ftn_dot, "_ftn_nint": _ftn_nint, "_ftn_dble": _ftn_dble, "_ftn_isnan": _ftn_isnan, "_flat": _flat, "_reshape_dummy": _reshape_dummy, "_call": self.call, "_fcall": self.call, "_first": _first, "_assign_whole": _assign_whole,
+                "_ftn_dot": _ftn_dot, "_ftn_nint": _ftn_nint, "_ftn_dble": _ftn_dble, "_ftn_isnan": _ftn_isnan, "_flat": _flat, "_flat0": _flat0, "_reshape_dummy": _reshape_dummy, "_call": self.call, "_fcall": self.call, "_first": _first, "_assign_whole": _assign_whole,
                 "_builtin": BUILTIN_SUBS, "_bfunc": BUILTIN_FUNCS, **DFTI_CONSTS, "_flat_any": _flat_any, "_new_derived": self.new_derived, **self.consts, **self.module_vars}
         exec(compile(src, f"<fortran {name}>", "exec"), glob)
         self.funcs[name] = glob[name]
@@ -941,9 +1005,13 @@ class Interpreter:
                 a = a.strip()
                 mm = re.match(r"(\w+(?:\s*%\s*\w+)*)\s*\(([^:]*)\)$", a)
                 is_arr_dummy = k < len(self.array_dummies.get(callee, [])) and self.array_dummies[callee][k]
-                if a in arrays:
+                mc = re.match(r"^(.*\))\s*%\s*(\w+)\s*\(([^:()]*)\)$", a)      # a%b(i, j)%c(k): a run starting at an element of a component
+                if mc and is_arr_dummy:
+                    base = tr.expr(mc.group(1) + "%" + mc.group(2), arrays, scalars)
+                    pyargs.append(f"_flat({base}, {', '.join(tr.expr(x, arrays, scalars) for x in split_top(mc.group(3)))})")
+                elif a in arrays:
                     pyargs.append(a)
-                elif mm and is_arr_dummy and (mm.group(1) in arrays or "%" in mm.group(1)) and ":" not in mm.group(2):
+                elif mm and "%" not in mm.group(2) and is_arr_dummy and (mm.group(1) in arrays or "%" in mm.group(1)) and ":" not in mm.group(2):
                     base = re.sub(r"\s*%\s*", ".", mm.group(1))
                     pyargs.append(f"_flat({base}, {', '.join(tr.expr(x, arrays, scalars) for x in split_top(mm.group(2)))})")
                 else:
@@ -974,7 +1042,10 @@ class Interpreter:
         rhs_py = tr.expr(rhs, arrays, scalars)
         if base in arrays and lhs == base:
             return [f"_assign_whole({base}, {rhs_py})"]
-        return [f"{tr.expr(lhs, arrays, scalars)} = {rhs_py}"]
+        lhs_py = tr.expr(lhs, arrays, scalars)
+        if ":" in lhs and "np.ix_" not in lhs_py:            # an array section: a view, assigned with _assign_whole's extent rule
+            return [f"_assign_whole({lhs_py}, {rhs_py})"]
+        return [f"{lhs_py} = {rhs_py}"]
 
 
 def _do_range(lo, hi, step=1):

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""A whole (small) job run by the reference's OWN source: the global Newton loop FFT_nr3 with its stress-controlled outer
+loop, fftPcg, tangent_homo, NBC_update, the operator G_K_dF and -- inside the Python stand-in for the block driver --
+the crystal-plasticity wrapper mm10 with everything below it, executed statement by statement by the Fortran-subset
+interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/golden/reference_global.npz.
+
+    python tools/make_reference_global.py            # needs /root/reference (this container); about ten minutes
+
+tests/test_reference_global.py (which needs neither /root/reference nor this script) holds the oracle's solver and the
+kernel source to it.  What is executed from the reference (file:line of the subroutine statement):
+
+  FFT_nr3.f:14    FFT_nr3      load steps, boundary-condition split, the Newton loop on the fluctuation, the outer loop on
+                                the prescribed mean stress, convergence tests, the commit of a step
+  FFT_nr3.f:214   fftPcg       right-hand side norm, tolerance checks, the RCI loop and its stopping test
+  FFT_nr3.f:375   NBC_update   the mixed 9 x 9 system for the mean deformation gradient (DGESV)
+  tangent_homo.f:11 tangent_homo  nine CG solves for d(dF)/d(Fbar), C_homo = <K4 : dF/dFbar>
+  G_K_dF.f:11     G_K_dF, ddot42n, fftfem3d, ifftfem3d; FFT_init.f:272 formG, :355 formfftshift
+  mm10_a.f:28     mm10         the per-point wrapper: history initialisation (mm10_init_general_hist, _uout_hist, _slip_hist,
+                                mm10_init_cc_hist0), mm10_init_cc_props, mm10_copy_cc_hist, mm10_setup_np1,
+                                mm10_solve_crystal (everything tools/make_reference_vectors.py lists), the crystal averages,
+                                mm10_store_cryhist and the common history block
+  polar.f:18 rtcmp1, :680 getrm1; drive_eps_sig.f:1017 inv33, :1110 mul33, :1182 cs2p; qmply1.f:15 qmply1; cep2A.f:14 cep2A
+
+What is NOT the reference's text, and why:
+  * MKL's reverse-communication CG (dcg_init / dcg_check / dcg / dcg_get) is a closed library: restated here from its
+    documented algorithm (plain CG on tmp(:,1..3) = direction, A x direction, residual; user stopping test, ipar(10) = 1).
+  * do_nleps_block / rstgp1 / dupstr_blocked / rplstr (drive_eps_sig.f:16-330, rstgp1.f) -- the gather / scatter between the
+    global arrays and the 128-point block work space -- are replaced by `drive_eps_sig` below, which calls the reference
+    routines listed above in do_nleps_block's order on one 27-point block.  drive_10_cnst's copy of history(1:36) into the
+    block tangent (gptns1.f:519-567) and update.f's n+1 -> n copies are one assignment each, done here.  rknstr_finish_cp (the
+    lattice-curvature fit) is not run: its output only enters through k_0, which is zero.
+  * mm10_set_cons returns at once for Voce hardening (mm10_a.f:383-388) and is skipped; mm10_set_history_locs
+    (mm10_d.f:25-331) writes module scalars, which the interpreter keeps read-only: the history layout is set here from the
+    same table (and is not what is compared).
+  * MKL DFTI is numpy's FFT (tools/fortran_subset.py).
+"""
+import hashlib
+import os
+import sys
+import time
+from types import SimpleNamespace as NS
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, ROOT)
+import fortran_subset as F  # noqa: E402
+import make_reference_vectors as G  # noqa: E402
+
+REF = G.REF
+FILES = G.FILES + ["FFT_nr3.f", "tangent_homo.f"]
+
+
+class Defaulting(NS):
+    """crystal_properties as the deck reader leaves it: every parameter the deck does not set is zero"""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return 0.0
+
+
+def mkl_rci_cg():
+    """MKL RCI CG (dcg_init, dcg_check, dcg, dcg_get), restated from the library's documented scheme: x_0 given, r = b - A x_0,
+    p = r, then alpha = (r.r)/(p.Ap), x += alpha p, r -= alpha Ap, beta = (r.r)_new/(r.r)_old, p = r + beta p; RCI_request 1 asks
+    for tmp(:,2) = A tmp(:,1), RCI_request 2 for the user's stopping test on tmp(:,3) = r (ipar(10) = 1, ipar(9) = 0), ipar(4) counts
+    the iterations."""
+    st = {}
+
+    def dcg_init(n, x, b, rci, ipar, dpar, tmp):
+        st.clear(); st.update(stage=0, it=0, rho=0.0)
+        return 0
+
+    def dcg_check(n, x, b, rci, ipar, dpar, tmp):
+        return 0
+
+    def dcg(n, x, b, rci, ipar, dpar, tmp):
+        n = int(n)
+        p, q, r = tmp[0:n], tmp[n:2 * n], tmp[2 * n:3 * n]
+        if st["stage"] == 0:                      # residual of the initial guess
+            p[:] = x[:n]; st["stage"] = 1
+            return 1
+        if st["stage"] == 1:
+            r[:] = b[:n] - q; st["stage"] = 2
+            return 2
+        if st["stage"] == 2:                      # the user's test did not stop the iteration: next direction
+            rho = float(np.dot(r, r))
+            if st["it"] == 0:
+                p[:] = r
+            else:
+                p[:] = r + (rho / st["rho"]) * p
+            st["rho"] = rho; st["stage"] = 3
+            return 1
+        alpha = st["rho"] / float(np.dot(p, q))
+        x[:n] = x[:n] + alpha * p
+        r[:] = r - alpha * q
+        st["it"] += 1; ipar[3] = st["it"]; st["stage"] = 2
+        if ipar[7] != 0 and st["it"] > ipar[4]:
+            return -1
+        return 2
+
+    def dcg_get(n, x, b, rci, ipar, dpar, tmp, itercount):
+        return st["it"]
+    return st, dcg_init, dcg_check, dcg, dcg_get
+
+
+def main():
+    t_start = time.time()
+    N, nstep = 3, int(os.environ.get("GLOBAL_NSTEP", "3"))
+    N3 = N ** 3
+    it = F.Interpreter()
+    it.add_constants(open(REF + "param_def").read())
+    mc_src = open(REF + "mod_crystals.f").read()
+    i0 = mc_src.index("      module mm10_constants")
+    it.add_constants(mc_src[i0:mc_src.index("      end module", i0)])
+    it.consts.setdefault("out", 6)
+    mx, ms_max, mu_ = it.consts["mxvl"], it.consts["max_slip_sys"], it.consts["max_uhard"]
+    rng = np.random.default_rng(20240609)
+
+    # ---- module fft: the arrays FFT_init allocates (FFT_init.f:141-172) and the solver parameters of the deck
+    Z = lambda *s: np.zeros(s, order="F")
+    fft = dict(n=N, nhalf=(N + 1) // 2, n3=N3, ndim1=3, ndim2=9, veclen=9 * N3, dims=np.array([N, N, N]), ghat4=Z(N3, 81), k4=Z(N3, 81),
+               coeffs1=Z(N, N, N), coeffs2=Z(N, N, N), real1=Z(N3, 9), real2=Z(N3, 9), real3=Z(N3, 9), b=Z(N3, 9), fn=Z(N3, 9), fn1=Z(N3, 9),
+               pn=Z(N3, 9), pn1=Z(N3, 9), dfm=Z(N3, 9), tmppcg=Z(9 * N3, 4), isnbc=np.zeros(9, dtype=bool), bc_all=Z(9, nstep),
+               straininc=0.0, tolpcg=1.0e-10, tolnr=1.0e-5, maxiter=10, nstep=nstep, out_step=np.zeros(nstep, dtype=bool))
+    FP_max = np.zeros(9); FP_max[0] = 0.002                  # uniaxial tension along x: F_xx prescribed, P_yy = P_zz = 0, no mean shear
+    fft["isnbc"][[4, 8]] = True
+    mults = np.ones(nstep)
+    bc = np.cumsum(np.outer(mults, FP_max), axis=0)           # inlod.f:57-63
+    for d in (0, 4, 8):
+        if not fft["isnbc"][d]:
+            bc[:, d] += 1.0
+    fft["bc_all"][...] = bc.T
+    fft["fn"][:, [0, 4, 8]] = 1.0; fft["fn1"][...] = fft["fn"]
+
+    # ---- module mm10_defs: the history layout mm10_set_history_locs computes for 12 slip systems, one hardening variable
+    nslip = 12
+    lcm = np.array([36, 27, 9, 3, nslip]); lcr = np.array([6, 3, 9, 6, 6, nslip, 1, 15, 1, 6, 6])
+    ic = np.zeros((5, 2), dtype=np.int64, order="F")
+    ic[:, 1] = np.cumsum(lcm); ic[:, 0] = ic[:, 1] - lcm + 1
+    ich = np.zeros((it.consts["max_crystals"], 11, 2), dtype=np.int64, order="F")
+    for c in range(ich.shape[0]):
+        start = ic[4, 1] + 1 + c * lcr.sum()
+        ich[c, :, 0] = start + np.cumsum(lcr) - lcr; ich[c, :, 1] = ich[c, :, 0] + lcr - 1
+    hist_sz = int(ic[4, 1] + lcr.sum())
+    mm10_defs = dict(indexes_common=ic, index_crys_hist=ich, length_comm_hist=lcm.astype(np.int64), length_crys_hist=lcr.astype(np.int64),
+                     num_common_indexes=5, num_crystal_terms=11, one_crystal_hist_size=int(lcr.sum()), common_hist_size=int(lcm.sum()),
+                     asymmetric_assembly=False)
+    it.module_vars.update(fft); it.module_vars.update(mm10_defs)
+    it.module_members.update(fft=set(fft), mm10_defs=set(mm10_defs))
+    for f in FILES[2:]:
+        it.load(open(REF + f).read())
+    del it.units["mm10_set_cons"]
+
+    def new_state():
+        return NS(r=Z(3, 3), rp=Z(3, 3), stress=np.zeros(6), d=np.zeros(6), eps=np.zeros(6), euler_angles=np.zeros(3), slip_incs=np.zeros(ms_max),
+                  tau_tilde=np.zeros(mu_), tt_rate=np.zeros(mu_), u=np.zeros(mu_), ep=np.zeros(6), ed=np.zeros(6), tangent=Z(6, 6), ms=Z(6, ms_max),
+                  qs=Z(3, ms_max), qc=Z(3, ms_max), tau_l=np.zeros(ms_max), gradfeinv=Z(3, 3, 3), dg=0.0, tinc=0.0, temp=0.0, mu_harden=0.0,
+                  work_inc=0.0, p_work_inc=0.0, p_strain_inc=0.0, step=0, elem=0, iter=0, gp=0, tau_v=0.0, tau_y=0.0)
+    it.derived_factories["crystal_state"] = new_state
+    it.derived_factories["crystal_props"] = lambda: NS(g=Z(3, 3), ms=Z(6, ms_max), qs=Z(3, ms_max), ns=Z(3, ms_max), stiffness=Z(6, 6),
+                                                       st_it=np.zeros(3, dtype=np.int64), init_angles=np.zeros(3), out=6)
+    it.derived_factories["dfti_descriptor"] = NS
+
+    # ---- one crystal per voxel, fcc, Voce hardening, its own orientation: crystal_properties the way setup_mm10_rknstr fills it
+    #      (drive_eps_sig.f:571-606, 975-986) with the reference's own mm10_rotation_matrix, mm10_RT2RVE, mm10_ET2EV, mm10_WT2WV
+    from oracle import Oracle
+    bvec, nvec = Oracle.slip_table(1)
+    e_mod, nu = 200000.0, 0.3
+    prm = dict(rate_n=20.0, theta_0=100.0, tau_y=100.0, tau_v=100.0, voche_m=1.0, iD_v=0.0, e=e_mod, nu=nu)
+    Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
+    Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
+    Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+    angles = rng.uniform(0.0, 360.0, (N3, 3))
+    c_props = np.empty((mx, 1), dtype=object)
+    for e in range(N3):
+        g = Z(3, 3)
+        it.call("mm10_rotation_matrix", angles[e].copy(), "kocks", "degrees", g, 6)
+        trot = np.asfortranarray(g.T)
+        RE = Z(6, 6)
+        it.call("mm10_rt2rve", trot, RE)
+        cp = Defaulting(raten=prm["rate_n"], theta_o=prm["theta_0"], tau_y=prm["tau_y"], tau_v=prm["tau_v"], voche_m=prm["voche_m"], id_v=prm["iD_v"],
+                        burgers=2.87e-7, eps_dot_o_y=1.0e10, solver=True, strategy=True, gpall=False, gpp=0, method=0, miter=30, atol=1e-5, atol1=1e-5,
+                        rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, alter_mode=False, nslip=nslip, h_type=1, num_hard=1, tang_calc=0, s_type=1, cnum=1,
+                        st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max), qs=Z(3, ms_max), ns=Z(3, ms_max),
+                        init_elast_stiff=np.asfortranarray(RE @ Cc @ RE.T), init_angles=angles[e].copy())
+        for s_ in range(nslip):
+            bs, ns_ = trot @ bvec[s_], trot @ nvec[s_]
+            A = np.outer(bs, ns_)
+            ev, wv = np.zeros(6), np.zeros(3)
+            it.call("mm10_et2ev", np.asfortranarray(0.5 * (A + A.T)), ev)
+            it.call("mm10_wt2wv", np.asfortranarray(0.5 * (A - A.T)), wv)
+            cp.ms[:, s_], cp.qs[:, s_], cp.ns[:, s_] = ev, wv, ns_
+        c_props[e, 0] = cp
+
+    # ---- the block work space and the global state the block driver gathers from / scatters to
+    lw = NS(dt=1.0, blk=1, span=N3, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False, debug_flag=np.zeros(mx, dtype=bool),
+            c_props=c_props, angle_type=np.ones(mx, dtype=np.int64), angle_convention=np.ones(mx, dtype=np.int64), fn=Z(mx, 3, 3), fn1=Z(mx, 3, 3),
+            urcs_blk_n=Z(mx, 9, 1), urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
+    hist_n, hist_n1 = Z(N3, hist_sz), Z(N3, hist_sz)
+    lw1 = NS(dt=1.0, blk=1, span=1, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False, debug_flag=np.zeros(mx, dtype=bool),
+             c_props=np.empty((mx, 1), dtype=object), angle_type=np.ones(mx, dtype=np.int64), angle_convention=np.ones(mx, dtype=np.int64),
+             urcs_blk_n=Z(mx, 9, 1), urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
+    h_n, h_n1, u1 = Z(1, hist_sz), Z(1, hist_sz), Z(mx, 6)
+    ncrystals = np.ones(mx, dtype=np.int64)
+    log = dict(sweeps=[], cg=[], steps=[])
+
+    def drive_eps_sig(step, iter_):
+        span = N3
+        lw.step, lw.iter, lw.material_cut_step = int(step), int(iter_), False
+        lw.fn[:span] = np.asarray(fft["fn"]).reshape(N3, 3, 3)           # Fn(e, 1..9) = F11, F12, F13, F21, ... (drive_eps_sig.f:190-214)
+        lw.fn1[:span] = np.asarray(fft["fn1"]).reshape(N3, 3, 3)
+        fnh, dfn, rnh, fnhinv, fn1inv = (Z(mx, 3, 3) for _ in range(5))
+        fnh[:span] = 0.5 * (lw.fn[:span] + lw.fn1[:span]); dfn[...] = lw.fn1 - lw.fn
+        it.call("rtcmp1", span, fnh, rnh); it.call("rtcmp1", span, lw.fn1, lw.rot_blk_n1)
+        detFh, detF = np.zeros(mx), np.zeros(mx)
+        it.call("inv33", span, 1, fnh, fnhinv, detFh)
+        ddt, uddt, cs = Z(mx, 6), Z(mx, 6), Z(mx, 6)
+        it.call("mul33", span, 1, dfn, fnhinv, ddt, 6)
+        qnhalf, qtn1 = Z(mx, 6, 6), Z(mx, 6, 6)
+        it.call("getrm1", span, qnhalf, rnh, 1)
+        it.call("qmply1", span, mx, 6, qnhalf, ddt, uddt)
+        hist_n1[...] = 0.0
+        lw.urcs_blk_n1[...] = 0.0
+        nj0, nj110 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
+        for e in range(span):              # one-point blocks: mm10 addresses the history through history(iloop, 1) with an assumed-size dummy,
+            lw1.step, lw1.iter, lw1.felem, lw1.material_cut_step = lw.step, lw.iter, e + 1, False      # which for span > 1 runs past whole columns
+            lw1.c_props[0, 0] = c_props[e, 0]
+            lw1.rot_blk_n1[0] = lw.rot_blk_n1[e]; lw1.urcs_blk_n[0] = lw.urcs_blk_n[e]; lw1.urcs_blk_n1[...] = 0.0
+            u1[0] = uddt[e]; h_n[0] = hist_n[e]; h_n1[...] = 0.0
+            it.call("mm10", 1, 1, ncrystals, hist_sz, h_n, h_n1, lw1, u1, np.full(mx, 297.0), np.zeros(mx), 6, False, False, Z(mx, 1), 1,
+                    int(iter_) == 0)                                     # rstgp1.f:862-880: iteration 0 is always the linear-elastic estimate
+            lw.material_cut_step = lw.material_cut_step or lw1.material_cut_step
+            hist_n1[e] = h_n1[0]; lw.urcs_blk_n1[e] = lw1.urcs_blk_n1[0]
+            if step == 1:
+                hist_n[e] = h_n[0]                                       # step 1 initialises the n history in place (mm10_a.f:73-78, 237-244)
+        if lw.material_cut_step:
+            raise RuntimeError("material_cut_step")
+        it.call("getrm1", span, qtn1, lw.rot_blk_n1, 2)
+        it.call("qmply1", span, mx, 6, qtn1, lw.urcs_blk_n1, cs)
+        it.call("inv33", span, 1, lw.fn1, fn1inv, detF)
+        P_blk, A_blk, cep = Z(mx, 9), Z(mx, 81), Z(mx, 6, 6)
+        it.call("cs2p", span, 1, cs, fn1inv, detF, P_blk)
+        for i in range(span):                                             # drive_10_cnst, gptns1.f:562-567
+            cep[i] = hist_n1[i, 0:36].reshape(6, 6, order="F")
+        it.call("cep2a", lw, cep, rnh, detF, detFh, fnhinv, fn1inv, A_blk)
+        fft["pn1"][...] = P_blk[:span]; fft["k4"][...] = A_blk[:span]
+        log["sweeps"].append((int(step), int(iter_), it.calls.get("mm10_formj11", 0) - nj110 - (it.calls.get("mm10_formj", 0) - nj0), it.calls.get("mm10_formj", 0) - nj0))
+        print(f"  sweep step {step} iter {iter_}: {time.time() - t_start:.0f} s", flush=True)
+
+    def update():
+        hist_n[...] = hist_n1; lw.urcs_blk_n[...] = lw.urcs_blk_n1            # update.f:85-93
+        log["steps"].append(dict(Fn1=np.ascontiguousarray(fft["fn1"]).copy(), Pn1=np.ascontiguousarray(fft["pn1"]).copy(), hist=np.ascontiguousarray(hist_n1).copy(),
+                                 urcs=np.ascontiguousarray(lw.urcs_blk_n1[:N3, :, 0]).copy(), n_sweeps=len(log["sweeps"]), n_cg=len(log["cg"]),
+                                 n_tangent_homo=it.calls.get("tangent_homo", 0)))
+
+    def die_abort(*a):
+        raise RuntimeError("die_abort")
+    st, dcg_init, dcg_check, dcg, dcg_get = mkl_rci_cg()
+
+    def thyme(a, b):
+        if int(b) == 1:
+            log["cg"].append([it.calls.get("tangent_homo", 0), 0])
+        else:
+            log["cg"][-1][1] = st.get("it", 0)
+    F.BUILTIN_SUBS.update(drive_eps_sig=drive_eps_sig, update=update, die_abort=die_abort, thyme=thyme, mkl_free_buffers=lambda *a: None,
+                          mm10_set_cons=lambda *a: None, dcg_init=dcg_init, dcg_check=dcg_check, dcg=dcg, dcg_get=dcg_get, ouresult=lambda *a: None)
+    F.BUILTIN_ARRAY_ARGS.update(drive_eps_sig=(), update=(), die_abort=(), thyme=(), mkl_free_buffers=(), mm10_set_cons=(), ouresult=(),
+                                dcg_init=(1, 2, 4, 5, 6), dcg_check=(1, 2, 4, 5, 6), dcg=(1, 2, 4, 5, 6), dcg_get=(1, 2, 4, 5, 6))
+    F.BUILTIN_INFO_ARG.update(dcg_init=3, dcg_check=3, dcg=3, dcg_get=7)
+    for name in ("drive_eps_sig", "update"):
+        it.units.pop(name, None)
+
+    it.call("formg"); it.call("formfftshift", fft["coeffs1"], fft["coeffs2"])
+    drive_eps_sig(1, 0)                                                  # FFT_finite_3d.f:145
+    K4_initial = np.ascontiguousarray(fft["k4"]).copy()
+    it.call("fft_nr3")                                                   # FFT_finite_3d.f:146
+
+    out = dict(N=N, nstep=nstep, angles=angles, params=np.array([prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
+               FP_max=FP_max, isNBC=fft["isnbc"].astype(np.int32), mults=mults, tolNR=fft["tolnr"], tolPCG=fft["tolpcg"], maxIter=fft["maxiter"],
+               K4_initial=K4_initial, hist_size=hist_sz)
+    for k in ("Fn1", "Pn1", "hist", "urcs", "n_sweeps", "n_cg", "n_tangent_homo"):
+        out["step_" + k] = np.array([s[k] for s in log["steps"]])
+    out["sweeps"] = np.array(log["sweeps"])                            # (step, global iteration, predictor Jacobians, update Jacobians) summed over the block
+    out["cg"] = np.array(log["cg"])                                    # (tangent_homo calls so far, CG iterations) per fftPcg call, in call order
+    h = hashlib.sha256()
+    for f in FILES + ["mm10_d.f"]:
+        h.update(open(REF + f, "rb").read())
+    out["provenance"] = ("maranGit/CPFFT src/{" + ", ".join(FILES) + "} executed by tools/fortran_subset.py (tools/make_reference_global.py); sha256 of the sources "
+                         + h.hexdigest() + "; interpreter sha256 " + hashlib.sha256(open(os.path.join(ROOT, "tools", "fortran_subset.py"), "rb").read()).hexdigest())
+    path = os.path.join(ROOT, "tests", "golden", "reference_global.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, f"{time.time() - t_start:.0f} s", {k: np.shape(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
