@@ -4,7 +4,10 @@ loop, fftPcg, tangent_homo, NBC_update, the operator G_K_dF and -- inside the Py
 the crystal-plasticity wrapper mm10 with everything below it, executed statement by statement by the Fortran-subset
 interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/golden/reference_global.npz.
 
-    python tools/make_reference_global.py            # needs /root/reference (this container); about ten minutes
+    python tools/make_reference_global.py            # needs /root/reference (this container); about two minutes
+
+A second set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
+point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
 
 tests/test_reference_global.py (which needs neither /root/reference nor this script) holds the oracle's solver and the
 kernel source to it.  What is executed from the reference (file:line of the subroutine statement):
@@ -104,21 +107,203 @@ def mkl_rci_cg():
     return st, dcg_init, dcg_check, dcg, dcg_get
 
 
+MTS = dict(theta_0=1500.0, tau_a=20.0, tau_hat_y=180.0, g_0_y=0.4, tau_hat_v=300.0, g_0_v=1.2, burgers=2.5e-7, mu_0=80000.0, D_0=3000.0,
+           T_0=200.0, p_y=0.5, q_y=2.0, p_v=0.5, q_v=2.0, boltzman=1.3806e-20, eps_dot_0_y=1.0e10, eps_dot_0_v=1.0e10)   # tests/golden/decks/mts_mm10.in
+MTS_FIELD = dict(theta_0="theta_o", tau_hat_y="tauhat_y", g_0_y="go_y", tau_hat_v="tauhat_v", g_0_v="go_v", mu_0="mu_o", D_0="d_o", T_0="t_o",
+                 eps_dot_0_y="eps_dot_o_y", eps_dot_0_v="eps_dot_o_v")         # crystal_properties spells them differently (mm10_a.f:1822-1845)
+PRM = dict(rate_n=20.0, theta_0=100.0, tau_y=100.0, tau_v=100.0, voche_m=1.0, iD_v=0.0, e=200000.0, nu=0.3)
+Z = lambda *s: np.zeros(s, order="F")
+
+
+def _die(*a):
+    raise RuntimeError("die_abort")
+
+
+class Harness:
+    """The material stage of npts points, one block-driver call at a time: the reference's routines in do_nleps_block's order
+    (drive_eps_sig.f:203-300), with its own interpreter because the history layout is module data.  slip_type 1 (fcc, 12
+    systems) or 8 (bcc48, which selects the maximum-size layout, mm10_d.f:136-141)."""
+
+    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES):
+        self.npts, self.slip_type, self.mts = npts, slip_type, mts
+        it = self.it = F.Interpreter()
+        it.add_constants(open(REF + "param_def").read())
+        mc_src = open(REF + "mod_crystals.f").read()
+        i0 = mc_src.index("      module mm10_constants")
+        it.add_constants(mc_src[i0:mc_src.index("      end module", i0)])
+        it.consts.setdefault("out", 6)
+        mx, ms_max, mu_ = it.consts["mxvl"], it.consts["max_slip_sys"], it.consts["max_uhard"]
+        self.mx = mx
+        angles = np.asarray(angles, dtype=np.float64).reshape(npts, -1, 3)
+        self.ncry = ncry = angles.shape[1]
+        from oracle import Oracle
+        bvec, nvec = Oracle.slip_table(slip_type)
+        nslip = self.nslip = len(bvec)
+
+        # module mm10_defs: the history layout mm10_set_history_locs computes (mm10_d.f:136-331)
+        use_max = nslip == ms_max
+        lcm = np.array([36, 27, 9, 3, ms_max if use_max else nslip])
+        lcr = np.array([6, 3, 9, 6, 6, ms_max, mu_, mu_, mu_, 6, 6] if use_max else [6, 3, 9, 6, 6, nslip, 1, 15, 1, 6, 6])
+        ic = np.zeros((5, 2), dtype=np.int64, order="F")
+        ic[:, 1] = np.cumsum(lcm); ic[:, 0] = ic[:, 1] - lcm + 1
+        ich = np.zeros((it.consts["max_crystals"], 11, 2), dtype=np.int64, order="F")
+        for c in range(ich.shape[0]):
+            start = ic[4, 1] + 1 + c * lcr.sum()
+            ich[c, :, 0] = start + np.cumsum(lcr) - lcr; ich[c, :, 1] = ich[c, :, 0] + lcr - 1
+        self.hist_sz = hist_sz = int(ic[4, 1] + ncry * lcr.sum())
+        self.crystal_start, self.crystal_len, self.lcr = int(ic[4, 1]), int(lcr.sum()), lcr
+        mm10_defs = dict(indexes_common=ic, index_crys_hist=ich, length_comm_hist=lcm.astype(np.int64), length_crys_hist=lcr.astype(np.int64),
+                         num_common_indexes=5, num_crystal_terms=11, one_crystal_hist_size=int(lcr.sum()), common_hist_size=int(lcm.sum()),
+                         asymmetric_assembly=False)
+        it.module_vars.update(mm10_defs); it.module_members["mm10_defs"] = set(mm10_defs)
+        if extra_module_vars:
+            it.module_vars.update(extra_module_vars); it.module_members["fft"] = set(extra_module_vars)
+        for f in files[2:]:
+            it.load(open(REF + f).read())
+        del it.units["mm10_set_cons"]                            # returns at once for Voce / MTS (mm10_a.f:383-388); its allocate(..., stat=) is not interpretable
+        F.BUILTIN_SUBS.setdefault("mm10_set_cons", lambda *a: None); F.BUILTIN_ARRAY_ARGS.setdefault("mm10_set_cons", ())
+        F.BUILTIN_SUBS.setdefault("die_abort", _die); F.BUILTIN_ARRAY_ARGS.setdefault("die_abort", ())
+        F.BUILTIN_SUBS.setdefault("die_gracefully", _die); F.BUILTIN_ARRAY_ARGS.setdefault("die_gracefully", ())
+        for name in ("drive_eps_sig", "update"):
+            it.units.pop(name, None)
+
+        def new_state():
+            return NS(r=Z(3, 3), rp=Z(3, 3), stress=np.zeros(6), d=np.zeros(6), eps=np.zeros(6), euler_angles=np.zeros(3), slip_incs=np.zeros(ms_max),
+                      tau_tilde=np.zeros(mu_), tt_rate=np.zeros(mu_), u=np.zeros(mu_), ep=np.zeros(6), ed=np.zeros(6), tangent=Z(6, 6), ms=Z(6, ms_max),
+                      qs=Z(3, ms_max), qc=Z(3, ms_max), tau_l=np.zeros(ms_max), gradfeinv=Z(3, 3, 3), dg=0.0, tinc=0.0, temp=0.0, mu_harden=0.0,
+                      work_inc=0.0, p_work_inc=0.0, p_strain_inc=0.0, step=0, elem=0, iter=0, gp=0, tau_v=0.0, tau_y=0.0)
+        it.derived_factories["crystal_state"] = new_state
+        it.derived_factories["crystal_props"] = lambda: NS(g=Z(3, 3), ms=Z(6, ms_max), qs=Z(3, ms_max), ns=Z(3, ms_max), stiffness=Z(6, 6),
+                                                           st_it=np.zeros(3, dtype=np.int64), init_angles=np.zeros(3), out=6)
+        it.derived_factories["dfti_descriptor"] = NS
+
+        # crystal_properties the way setup_mm10_rknstr fills it (drive_eps_sig.f:571-606, 975-986) with the reference's own
+        # mm10_rotation_matrix, mm10_RT2RVE, mm10_ET2EV, mm10_WT2WV; every parameter the deck does not set is zero
+        e_mod, nu = PRM["e"], PRM["nu"]
+        Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
+        Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
+        Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+        self.c_props = c_props = np.empty((npts, ncry), dtype=object)
+        for e in range(npts):
+            for c in range(ncry):
+                g = Z(3, 3)
+                it.call("mm10_rotation_matrix", angles[e, c].copy(), "kocks", "degrees", g, 6)
+                trot = np.asfortranarray(g.T)
+                RE = Z(6, 6)
+                it.call("mm10_rt2rve", trot, RE)
+                cp = Defaulting(raten=PRM["rate_n"], theta_o=PRM["theta_0"], tau_y=PRM["tau_y"], tau_v=PRM["tau_v"], voche_m=PRM["voche_m"], id_v=PRM["iD_v"],
+                                burgers=2.87e-7, eps_dot_o_y=1.0e10, solver=True, strategy=True, gpall=False, gpp=0, method=0, miter=30, atol=1e-5,
+                                atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, alter_mode=False, nslip=nslip, h_type=2 if mts else 1, num_hard=1,
+                                tang_calc=0, s_type=slip_type, cnum=1, st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max),
+                                qs=Z(3, ms_max), ns=Z(3, ms_max), init_elast_stiff=np.asfortranarray(RE @ Cc @ RE.T), init_angles=angles[e, c].copy())
+                if mts:
+                    for k_, v_ in MTS.items():
+                        setattr(cp, MTS_FIELD.get(k_, k_), v_)
+                for s_ in range(nslip):
+                    bs, ns_ = trot @ bvec[s_], trot @ nvec[s_]
+                    A = np.outer(bs, ns_)
+                    ev, wv = np.zeros(6), np.zeros(3)
+                    it.call("mm10_et2ev", np.asfortranarray(0.5 * (A + A.T)), ev)
+                    it.call("mm10_wt2wv", np.asfortranarray(0.5 * (A - A.T)), wv)
+                    cp.ms[:, s_], cp.qs[:, s_], cp.ns[:, s_] = ev, wv, ns_
+                c_props[e, c] = cp
+
+        # the block work space and the global state the block driver gathers from / scatters to
+        mk = lambda span: NS(dt=1.0, blk=1, span=span, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False,
+                             debug_flag=np.zeros(mx, dtype=bool), c_props=np.empty((mx, ncry), dtype=object), angle_type=np.ones(mx, dtype=np.int64),
+                             angle_convention=np.ones(mx, dtype=np.int64), fn=Z(mx, 3, 3), fn1=Z(mx, 3, 3), urcs_blk_n=Z(mx, 9, 1),
+                             urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
+        self.lw, self.lw1 = mk(npts), mk(1)
+        self.hist_n, self.hist_n1 = Z(npts, hist_sz), Z(npts, hist_sz)
+        self.h_n, self.h_n1, self.u1 = Z(1, hist_sz), Z(1, hist_sz), Z(mx, 6)
+        self.ncrystals = np.full(mx, ncry, dtype=np.int64)
+        self.sweeps = []
+
+    def sweep(self, step, iter_, Fn, Fn1):
+        """(npts, 9) row-major F_n, F_n+1 -> P (npts, 9), dP/dF (npts, 81); the n+1 history and stresses are kept in the harness"""
+        it, lw, lw1, mx, span = self.it, self.lw, self.lw1, self.mx, self.npts
+        lw.step, lw.iter, lw.material_cut_step = int(step), int(iter_), False
+        lw.fn[:span] = np.asarray(Fn).reshape(span, 3, 3)                # Fn(e, 1..9) = F11, F12, F13, F21, ... (drive_eps_sig.f:190-214)
+        lw.fn1[:span] = np.asarray(Fn1).reshape(span, 3, 3)
+        fnh, dfn, rnh, fnhinv, fn1inv = (Z(mx, 3, 3) for _ in range(5))
+        fnh[:span] = 0.5 * (lw.fn[:span] + lw.fn1[:span]); dfn[...] = lw.fn1 - lw.fn
+        it.call("rtcmp1", span, fnh, rnh); it.call("rtcmp1", span, lw.fn1, lw.rot_blk_n1)
+        detFh, detF = np.zeros(mx), np.zeros(mx)
+        it.call("inv33", span, 1, fnh, fnhinv, detFh)
+        ddt, uddt, cs = Z(mx, 6), Z(mx, 6), Z(mx, 6)
+        it.call("mul33", span, 1, dfn, fnhinv, ddt, 6)
+        qnhalf, qtn1 = Z(mx, 6, 6), Z(mx, 6, 6)
+        it.call("getrm1", span, qnhalf, rnh, 1)
+        it.call("qmply1", span, mx, 6, qnhalf, ddt, uddt)
+        self.hist_n1[...] = 0.0
+        lw.urcs_blk_n1[...] = 0.0
+        nj0, nj110 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
+        for e in range(span):              # one-point blocks: mm10 addresses the history through history(iloop, 1) with an assumed-size dummy,
+            lw1.step, lw1.iter, lw1.felem, lw1.material_cut_step = lw.step, lw.iter, e + 1, False      # which for span > 1 runs past whole columns
+            lw1.c_props[0, :] = self.c_props[e, :]
+            lw1.rot_blk_n1[0] = lw.rot_blk_n1[e]; lw1.urcs_blk_n[0] = lw.urcs_blk_n[e]; lw1.urcs_blk_n1[...] = 0.0
+            self.u1[0] = uddt[e]; self.h_n[0] = self.hist_n[e]; self.h_n1[...] = 0.0
+            it.call("mm10", 1, 1, self.ncrystals, self.hist_sz, self.h_n, self.h_n1, lw1, self.u1, np.full(mx, 297.0), np.zeros(mx), 6, False, False,
+                    Z(mx, 1), 1, int(iter_) == 0)                        # rstgp1.f:862-880: iteration 0 is always the linear-elastic estimate
+            lw.material_cut_step = lw.material_cut_step or lw1.material_cut_step
+            self.hist_n1[e] = self.h_n1[0]; lw.urcs_blk_n1[e] = lw1.urcs_blk_n1[0]
+            if step == 1:
+                self.hist_n[e] = self.h_n[0]                             # step 1 initialises the n history in place (mm10_a.f:73-78, 237-244)
+        if lw.material_cut_step:
+            raise RuntimeError("material_cut_step")
+        it.call("getrm1", span, qtn1, lw.rot_blk_n1, 2)
+        it.call("qmply1", span, mx, 6, qtn1, lw.urcs_blk_n1, cs)
+        it.call("inv33", span, 1, lw.fn1, fn1inv, detF)
+        P_blk, A_blk, cep = Z(mx, 9), Z(mx, 81), Z(mx, 6, 6)
+        it.call("cs2p", span, 1, cs, fn1inv, detF, P_blk)
+        for i in range(span):                                             # drive_10_cnst, gptns1.f:562-567
+            cep[i] = self.hist_n1[i, 0:36].reshape(6, 6, order="F")
+        it.call("cep2a", lw, cep, rnh, detF, detFh, fnhinv, fn1inv, A_blk)
+        nj, nj11 = it.calls.get("mm10_formj", 0) - nj0, it.calls.get("mm10_formj11", 0) - nj110
+        self.sweeps.append((int(step), int(iter_), nj11 - nj, nj))
+        return P_blk[:span].copy(), A_blk[:span].copy()
+
+    def update(self):
+        self.hist_n[...] = self.hist_n1; self.lw.urcs_blk_n[...] = self.lw.urcs_blk_n1            # update.f:85-93
+
+
+def wrapper_cases(out):
+    """the per-point wrapper mm10 on what the 3^3 job does not reach: polycrystalline points (three crystals, Taylor average,
+    mm10_a.f:112-197), MTS hardening with its history (mm10_init_mts, tau_y / mu_harden carried in u(1:2)), and the 48-system
+    layout.  Two load steps each: step 1 from the virgin state (iteration 0 = elastic estimate, then a plastic sweep), commit,
+    step 2."""
+    rng = np.random.default_rng(20240610)
+    for name, slip_type, mts, ncry in (("taylor", 1, False, 3), ("mts", 1, True, 1), ("bcc48", 8, False, 1)):
+        npts = 4
+        angles = rng.uniform(0.0, 360.0, (npts, ncry, 3))
+        H = Harness(npts, angles, slip_type=slip_type, mts=mts)
+        eye = np.tile(np.eye(3).reshape(9), (npts, 1))
+        F1 = eye + 0.0015 * rng.standard_normal((npts, 9))
+        F2 = F1 + 0.0012 * rng.standard_normal((npts, 9))
+        P0, K0 = H.sweep(1, 0, eye, eye)
+        rec = dict(angles=angles, F1=F1, F2=F2, K4_initial=K0, hist_size=H.hist_sz, slip_type=slip_type, h_type=2 if mts else 1, ncry=ncry)
+        for step, (Fa, Fb) in ((1, (eye, F1)), (2, (F1, F2))):
+            P, K = H.sweep(step, 1, Fa, Fb)
+            rec[f"P{step}"], rec[f"K4_{step}"] = P, K
+            rec[f"hist{step}"] = np.ascontiguousarray(H.hist_n1).copy()
+            rec[f"urcs{step}"] = np.ascontiguousarray(H.lw.urcs_blk_n1[:npts, :, 0]).copy()
+            rec[f"iters{step}"] = np.array(H.sweeps[-1][2:])
+            H.update()
+        for k, v in rec.items():
+            out[f"wrap_{name}_{k}"] = np.asarray(v)
+        print("wrapper case", name, "hist", H.hist_sz, "iters", rec["iters1"], rec["iters2"], flush=True)
+    out["mts_names"] = np.array(sorted(MTS)); out["mts_params"] = np.array([MTS[k] for k in sorted(MTS)])
+
+
 def main():
     t_start = time.time()
     N, nstep = 3, int(os.environ.get("GLOBAL_NSTEP", "3"))
     N3 = N ** 3
-    it = F.Interpreter()
-    it.add_constants(open(REF + "param_def").read())
-    mc_src = open(REF + "mod_crystals.f").read()
-    i0 = mc_src.index("      module mm10_constants")
-    it.add_constants(mc_src[i0:mc_src.index("      end module", i0)])
-    it.consts.setdefault("out", 6)
-    mx, ms_max, mu_ = it.consts["mxvl"], it.consts["max_slip_sys"], it.consts["max_uhard"]
     rng = np.random.default_rng(20240609)
+    out = {}
+    wrapper_cases(out)
 
     # ---- module fft: the arrays FFT_init allocates (FFT_init.f:141-172) and the solver parameters of the deck
-    Z = lambda *s: np.zeros(s, order="F")
     fft = dict(n=N, nhalf=(N + 1) // 2, n3=N3, ndim1=3, ndim2=9, veclen=9 * N3, dims=np.array([N, N, N]), ghat4=Z(N3, 81), k4=Z(N3, 81),
                coeffs1=Z(N, N, N), coeffs2=Z(N, N, N), real1=Z(N3, 9), real2=Z(N3, 9), real3=Z(N3, 9), b=Z(N3, 9), fn=Z(N3, 9), fn1=Z(N3, 9),
                pn=Z(N3, 9), pn1=Z(N3, 9), dfm=Z(N3, 9), tmppcg=Z(9 * N3, 4), isnbc=np.zeros(9, dtype=bool), bc_all=Z(9, nstep),
@@ -133,129 +318,22 @@ def main():
     fft["bc_all"][...] = bc.T
     fft["fn"][:, [0, 4, 8]] = 1.0; fft["fn1"][...] = fft["fn"]
 
-    # ---- module mm10_defs: the history layout mm10_set_history_locs computes for 12 slip systems, one hardening variable
-    nslip = 12
-    lcm = np.array([36, 27, 9, 3, nslip]); lcr = np.array([6, 3, 9, 6, 6, nslip, 1, 15, 1, 6, 6])
-    ic = np.zeros((5, 2), dtype=np.int64, order="F")
-    ic[:, 1] = np.cumsum(lcm); ic[:, 0] = ic[:, 1] - lcm + 1
-    ich = np.zeros((it.consts["max_crystals"], 11, 2), dtype=np.int64, order="F")
-    for c in range(ich.shape[0]):
-        start = ic[4, 1] + 1 + c * lcr.sum()
-        ich[c, :, 0] = start + np.cumsum(lcr) - lcr; ich[c, :, 1] = ich[c, :, 0] + lcr - 1
-    hist_sz = int(ic[4, 1] + lcr.sum())
-    mm10_defs = dict(indexes_common=ic, index_crys_hist=ich, length_comm_hist=lcm.astype(np.int64), length_crys_hist=lcr.astype(np.int64),
-                     num_common_indexes=5, num_crystal_terms=11, one_crystal_hist_size=int(lcr.sum()), common_hist_size=int(lcm.sum()),
-                     asymmetric_assembly=False)
-    it.module_vars.update(fft); it.module_vars.update(mm10_defs)
-    it.module_members.update(fft=set(fft), mm10_defs=set(mm10_defs))
-    for f in FILES[2:]:
-        it.load(open(REF + f).read())
-    del it.units["mm10_set_cons"]
-
-    def new_state():
-        return NS(r=Z(3, 3), rp=Z(3, 3), stress=np.zeros(6), d=np.zeros(6), eps=np.zeros(6), euler_angles=np.zeros(3), slip_incs=np.zeros(ms_max),
-                  tau_tilde=np.zeros(mu_), tt_rate=np.zeros(mu_), u=np.zeros(mu_), ep=np.zeros(6), ed=np.zeros(6), tangent=Z(6, 6), ms=Z(6, ms_max),
-                  qs=Z(3, ms_max), qc=Z(3, ms_max), tau_l=np.zeros(ms_max), gradfeinv=Z(3, 3, 3), dg=0.0, tinc=0.0, temp=0.0, mu_harden=0.0,
-                  work_inc=0.0, p_work_inc=0.0, p_strain_inc=0.0, step=0, elem=0, iter=0, gp=0, tau_v=0.0, tau_y=0.0)
-    it.derived_factories["crystal_state"] = new_state
-    it.derived_factories["crystal_props"] = lambda: NS(g=Z(3, 3), ms=Z(6, ms_max), qs=Z(3, ms_max), ns=Z(3, ms_max), stiffness=Z(6, 6),
-                                                       st_it=np.zeros(3, dtype=np.int64), init_angles=np.zeros(3), out=6)
-    it.derived_factories["dfti_descriptor"] = NS
-
-    # ---- one crystal per voxel, fcc, Voce hardening, its own orientation: crystal_properties the way setup_mm10_rknstr fills it
-    #      (drive_eps_sig.f:571-606, 975-986) with the reference's own mm10_rotation_matrix, mm10_RT2RVE, mm10_ET2EV, mm10_WT2WV
-    from oracle import Oracle
-    bvec, nvec = Oracle.slip_table(1)
-    e_mod, nu = 200000.0, 0.3
-    prm = dict(rate_n=20.0, theta_0=100.0, tau_y=100.0, tau_v=100.0, voche_m=1.0, iD_v=0.0, e=e_mod, nu=nu)
-    Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
-    Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
-    Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+    # ---- one crystal per voxel, fcc, Voce hardening, its own orientation
     angles = rng.uniform(0.0, 360.0, (N3, 3))
-    c_props = np.empty((mx, 1), dtype=object)
-    for e in range(N3):
-        g = Z(3, 3)
-        it.call("mm10_rotation_matrix", angles[e].copy(), "kocks", "degrees", g, 6)
-        trot = np.asfortranarray(g.T)
-        RE = Z(6, 6)
-        it.call("mm10_rt2rve", trot, RE)
-        cp = Defaulting(raten=prm["rate_n"], theta_o=prm["theta_0"], tau_y=prm["tau_y"], tau_v=prm["tau_v"], voche_m=prm["voche_m"], id_v=prm["iD_v"],
-                        burgers=2.87e-7, eps_dot_o_y=1.0e10, solver=True, strategy=True, gpall=False, gpp=0, method=0, miter=30, atol=1e-5, atol1=1e-5,
-                        rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, alter_mode=False, nslip=nslip, h_type=1, num_hard=1, tang_calc=0, s_type=1, cnum=1,
-                        st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max), qs=Z(3, ms_max), ns=Z(3, ms_max),
-                        init_elast_stiff=np.asfortranarray(RE @ Cc @ RE.T), init_angles=angles[e].copy())
-        for s_ in range(nslip):
-            bs, ns_ = trot @ bvec[s_], trot @ nvec[s_]
-            A = np.outer(bs, ns_)
-            ev, wv = np.zeros(6), np.zeros(3)
-            it.call("mm10_et2ev", np.asfortranarray(0.5 * (A + A.T)), ev)
-            it.call("mm10_wt2wv", np.asfortranarray(0.5 * (A - A.T)), wv)
-            cp.ms[:, s_], cp.qs[:, s_], cp.ns[:, s_] = ev, wv, ns_
-        c_props[e, 0] = cp
-
-    # ---- the block work space and the global state the block driver gathers from / scatters to
-    lw = NS(dt=1.0, blk=1, span=N3, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False, debug_flag=np.zeros(mx, dtype=bool),
-            c_props=c_props, angle_type=np.ones(mx, dtype=np.int64), angle_convention=np.ones(mx, dtype=np.int64), fn=Z(mx, 3, 3), fn1=Z(mx, 3, 3),
-            urcs_blk_n=Z(mx, 9, 1), urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
-    hist_n, hist_n1 = Z(N3, hist_sz), Z(N3, hist_sz)
-    lw1 = NS(dt=1.0, blk=1, span=1, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False, debug_flag=np.zeros(mx, dtype=bool),
-             c_props=np.empty((mx, 1), dtype=object), angle_type=np.ones(mx, dtype=np.int64), angle_convention=np.ones(mx, dtype=np.int64),
-             urcs_blk_n=Z(mx, 9, 1), urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
-    h_n, h_n1, u1 = Z(1, hist_sz), Z(1, hist_sz), Z(mx, 6)
-    ncrystals = np.ones(mx, dtype=np.int64)
-    log = dict(sweeps=[], cg=[], steps=[])
+    H = Harness(N3, angles, extra_module_vars=fft)
+    it, prm, hist_sz = H.it, PRM, H.hist_sz
+    log = dict(cg=[], steps=[])
 
     def drive_eps_sig(step, iter_):
-        span = N3
-        lw.step, lw.iter, lw.material_cut_step = int(step), int(iter_), False
-        lw.fn[:span] = np.asarray(fft["fn"]).reshape(N3, 3, 3)           # Fn(e, 1..9) = F11, F12, F13, F21, ... (drive_eps_sig.f:190-214)
-        lw.fn1[:span] = np.asarray(fft["fn1"]).reshape(N3, 3, 3)
-        fnh, dfn, rnh, fnhinv, fn1inv = (Z(mx, 3, 3) for _ in range(5))
-        fnh[:span] = 0.5 * (lw.fn[:span] + lw.fn1[:span]); dfn[...] = lw.fn1 - lw.fn
-        it.call("rtcmp1", span, fnh, rnh); it.call("rtcmp1", span, lw.fn1, lw.rot_blk_n1)
-        detFh, detF = np.zeros(mx), np.zeros(mx)
-        it.call("inv33", span, 1, fnh, fnhinv, detFh)
-        ddt, uddt, cs = Z(mx, 6), Z(mx, 6), Z(mx, 6)
-        it.call("mul33", span, 1, dfn, fnhinv, ddt, 6)
-        qnhalf, qtn1 = Z(mx, 6, 6), Z(mx, 6, 6)
-        it.call("getrm1", span, qnhalf, rnh, 1)
-        it.call("qmply1", span, mx, 6, qnhalf, ddt, uddt)
-        hist_n1[...] = 0.0
-        lw.urcs_blk_n1[...] = 0.0
-        nj0, nj110 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
-        for e in range(span):              # one-point blocks: mm10 addresses the history through history(iloop, 1) with an assumed-size dummy,
-            lw1.step, lw1.iter, lw1.felem, lw1.material_cut_step = lw.step, lw.iter, e + 1, False      # which for span > 1 runs past whole columns
-            lw1.c_props[0, 0] = c_props[e, 0]
-            lw1.rot_blk_n1[0] = lw.rot_blk_n1[e]; lw1.urcs_blk_n[0] = lw.urcs_blk_n[e]; lw1.urcs_blk_n1[...] = 0.0
-            u1[0] = uddt[e]; h_n[0] = hist_n[e]; h_n1[...] = 0.0
-            it.call("mm10", 1, 1, ncrystals, hist_sz, h_n, h_n1, lw1, u1, np.full(mx, 297.0), np.zeros(mx), 6, False, False, Z(mx, 1), 1,
-                    int(iter_) == 0)                                     # rstgp1.f:862-880: iteration 0 is always the linear-elastic estimate
-            lw.material_cut_step = lw.material_cut_step or lw1.material_cut_step
-            hist_n1[e] = h_n1[0]; lw.urcs_blk_n1[e] = lw1.urcs_blk_n1[0]
-            if step == 1:
-                hist_n[e] = h_n[0]                                       # step 1 initialises the n history in place (mm10_a.f:73-78, 237-244)
-        if lw.material_cut_step:
-            raise RuntimeError("material_cut_step")
-        it.call("getrm1", span, qtn1, lw.rot_blk_n1, 2)
-        it.call("qmply1", span, mx, 6, qtn1, lw.urcs_blk_n1, cs)
-        it.call("inv33", span, 1, lw.fn1, fn1inv, detF)
-        P_blk, A_blk, cep = Z(mx, 9), Z(mx, 81), Z(mx, 6, 6)
-        it.call("cs2p", span, 1, cs, fn1inv, detF, P_blk)
-        for i in range(span):                                             # drive_10_cnst, gptns1.f:562-567
-            cep[i] = hist_n1[i, 0:36].reshape(6, 6, order="F")
-        it.call("cep2a", lw, cep, rnh, detF, detFh, fnhinv, fn1inv, A_blk)
-        fft["pn1"][...] = P_blk[:span]; fft["k4"][...] = A_blk[:span]
-        log["sweeps"].append((int(step), int(iter_), it.calls.get("mm10_formj11", 0) - nj110 - (it.calls.get("mm10_formj", 0) - nj0), it.calls.get("mm10_formj", 0) - nj0))
+        P, K = H.sweep(step, iter_, fft["fn"], fft["fn1"])
+        fft["pn1"][...] = P; fft["k4"][...] = K
         print(f"  sweep step {step} iter {iter_}: {time.time() - t_start:.0f} s", flush=True)
 
     def update():
-        hist_n[...] = hist_n1; lw.urcs_blk_n[...] = lw.urcs_blk_n1            # update.f:85-93
-        log["steps"].append(dict(Fn1=np.ascontiguousarray(fft["fn1"]).copy(), Pn1=np.ascontiguousarray(fft["pn1"]).copy(), hist=np.ascontiguousarray(hist_n1).copy(),
-                                 urcs=np.ascontiguousarray(lw.urcs_blk_n1[:N3, :, 0]).copy(), n_sweeps=len(log["sweeps"]), n_cg=len(log["cg"]),
-                                 n_tangent_homo=it.calls.get("tangent_homo", 0)))
-
-    def die_abort(*a):
-        raise RuntimeError("die_abort")
+        H.update()
+        log["steps"].append(dict(Fn1=np.ascontiguousarray(fft["fn1"]).copy(), Pn1=np.ascontiguousarray(fft["pn1"]).copy(),
+                                 hist=np.ascontiguousarray(H.hist_n1).copy(), urcs=np.ascontiguousarray(H.lw.urcs_blk_n1[:N3, :, 0]).copy(),
+                                 n_sweeps=len(H.sweeps), n_cg=len(log["cg"]), n_tangent_homo=it.calls.get("tangent_homo", 0)))
     st, dcg_init, dcg_check, dcg, dcg_get = mkl_rci_cg()
 
     def thyme(a, b):
@@ -263,28 +341,26 @@ def main():
             log["cg"].append([it.calls.get("tangent_homo", 0), 0])
         else:
             log["cg"][-1][1] = st.get("it", 0)
-    F.BUILTIN_SUBS.update(drive_eps_sig=drive_eps_sig, update=update, die_abort=die_abort, thyme=thyme, mkl_free_buffers=lambda *a: None,
-                          mm10_set_cons=lambda *a: None, dcg_init=dcg_init, dcg_check=dcg_check, dcg=dcg, dcg_get=dcg_get, ouresult=lambda *a: None)
-    F.BUILTIN_ARRAY_ARGS.update(drive_eps_sig=(), update=(), die_abort=(), thyme=(), mkl_free_buffers=(), mm10_set_cons=(), ouresult=(),
+    F.BUILTIN_SUBS.update(drive_eps_sig=drive_eps_sig, update=update, thyme=thyme, mkl_free_buffers=lambda *a: None,
+                          dcg_init=dcg_init, dcg_check=dcg_check, dcg=dcg, dcg_get=dcg_get, ouresult=lambda *a: None)
+    F.BUILTIN_ARRAY_ARGS.update(drive_eps_sig=(), update=(), thyme=(), mkl_free_buffers=(), ouresult=(),
                                 dcg_init=(1, 2, 4, 5, 6), dcg_check=(1, 2, 4, 5, 6), dcg=(1, 2, 4, 5, 6), dcg_get=(1, 2, 4, 5, 6))
     F.BUILTIN_INFO_ARG.update(dcg_init=3, dcg_check=3, dcg=3, dcg_get=7)
-    for name in ("drive_eps_sig", "update"):
-        it.units.pop(name, None)
 
     it.call("formg"); it.call("formfftshift", fft["coeffs1"], fft["coeffs2"])
     drive_eps_sig(1, 0)                                                  # FFT_finite_3d.f:145
     K4_initial = np.ascontiguousarray(fft["k4"]).copy()
     it.call("fft_nr3")                                                   # FFT_finite_3d.f:146
 
-    out = dict(N=N, nstep=nstep, angles=angles, params=np.array([prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
+    out.update(N=N, nstep=nstep, angles=angles, params=np.array([prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
                FP_max=FP_max, isNBC=fft["isnbc"].astype(np.int32), mults=mults, tolNR=fft["tolnr"], tolPCG=fft["tolpcg"], maxIter=fft["maxiter"],
                K4_initial=K4_initial, hist_size=hist_sz)
     for k in ("Fn1", "Pn1", "hist", "urcs", "n_sweeps", "n_cg", "n_tangent_homo"):
         out["step_" + k] = np.array([s[k] for s in log["steps"]])
-    out["sweeps"] = np.array(log["sweeps"])                            # (step, global iteration, predictor Jacobians, update Jacobians) summed over the block
+    out["sweeps"] = np.array(H.sweeps)                            # (step, global iteration, predictor Jacobians, update Jacobians) summed over the block
     out["cg"] = np.array(log["cg"])                                    # (tangent_homo calls so far, CG iterations) per fftPcg call, in call order
     h = hashlib.sha256()
-    for f in FILES + ["mm10_d.f"]:
+    for f in FILES:
         h.update(open(REF + f, "rb").read())
     out["provenance"] = ("maranGit/CPFFT src/{" + ", ".join(FILES) + "} executed by tools/fortran_subset.py (tools/make_reference_global.py); sha256 of the sources "
                          + h.hexdigest() + "; interpreter sha256 " + hashlib.sha256(open(os.path.join(ROOT, "tools", "fortran_subset.py"), "rb").read()).hexdigest())
