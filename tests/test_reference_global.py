@@ -21,34 +21,41 @@ V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "
 N, NSTEP = int(V["N"]), int(V["nstep"])
 
 
-def problem():
+def problem(job=""):
     from cpfft_b200.polycrystal import polycrystal
-    from cpfft_b200.problem import Crystal
-    rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["params"]
-    cr = Crystal(slip_type=1, elastic_type=1, h_type=1, e=e, nu=nu, mu=e / 2.0 / (1.0 + nu), harden_n=rate_n, theta_0=theta_0, tau_y=tau_y,
-                 tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
-    p = polycrystal(N, ngrains=1)
-    p.crystals = [cr]
-    p.angles = np.ascontiguousarray(V["angles"])
-    p.FP_max, p.isNBC, p.mults = V["FP_max"].copy(), V["isNBC"].astype(np.int32), V["mults"].copy()
-    p.tolNR, p.tolPCG, p.maxIter = float(V["tolNR"]), float(V["tolPCG"]), int(V["maxIter"])
+    from cpfft_b200.problem import Crystal, Material, Problem
+    if job == "":
+        rate_n, theta_0, tau_y, tau_v, voche_m, iD_v, e, nu = V["params"]
+        cr = Crystal(slip_type=1, elastic_type=1, h_type=1, e=e, nu=nu, mu=e / 2.0 / (1.0 + nu), harden_n=rate_n, theta_0=theta_0, tau_y=tau_y,
+                     tau_v=tau_v, voche_m=voche_m, iD_v=iD_v)
+        p = polycrystal(N, ngrains=1)
+        p.crystals = [cr]
+        p.angles = np.ascontiguousarray(V["angles"])
+    else:                                                  # mm01: one material per distinct property set
+        props = np.stack([V[job + "prop_" + k] for k in ("e", "nu", "yld", "tan_e", "beta")], axis=1)
+        keys = sorted({tuple(r) for r in props})
+        mats = [Material(name=f"m{k}", type=1, e=t[0], nu=t[1], yld_pt=t[2], tan_e=t[3], beta=t[4]) for k, t in enumerate(keys)]
+        ml = np.array([keys.index(tuple(r)) + 1 for r in props], dtype=np.int32)
+        p = Problem(N=N, materials=mats, crystals=[], matlist=ml, angles=np.zeros((N ** 3, 3)))
+    p.FP_max, p.isNBC, p.mults = V[job + "FP_max"].copy(), V[job + "isNBC"].astype(np.int32), V[job + "mults"].copy()
+    p.tolNR, p.tolPCG, p.maxIter = float(V[job + "tolNR"]), float(V[job + "tolPCG"]), int(V[job + "maxIter"])
     return p
 
 
-def reference_iterations():
+def reference_iterations(job=""):
     """per load step: the CG iteration counts of the Newton-loop solves (tangent_homo's nine solves per call taken out), the
     number of material sweeps and of tangent_homo calls"""
-    cg = V["cg"]
+    cg = V[job + "cg"]
     newton_cg, seen = [], {}
     for k, (th, its) in enumerate(cg):
         seen[th] = seen.get(th, 0) + 1
         if seen[th] > 9:                               # the first nine solves after a tangent_homo call are its own
             newton_cg.append((k, int(its)))
-    bounds = [0] + [int(x) for x in V["step_n_cg"]]
+    bounds = [0] + [int(x) for x in V[job + "step_n_cg"]]
     per_step_cg = [[its for k, its in newton_cg if bounds[s] <= k < bounds[s + 1]] for s in range(NSTEP)]
-    sweeps = [0] + [int(x) for x in V["step_n_sweeps"]]
+    sweeps = [0] + [int(x) for x in V[job + "step_n_sweeps"]]
     per_step_sweeps = [sweeps[s + 1] - sweeps[s] - (1 if s == 0 else 0) for s in range(NSTEP)]     # the first sweep is FFT_finite_3d.f:145
-    th = [1] + [int(x) for x in V["step_n_tangent_homo"]]
+    th = [1] + [int(x) for x in V[job + "step_n_tangent_homo"]]
     return per_step_cg, per_step_sweeps, [th[s + 1] - th[s] for s in range(NSTEP)]
 
 
@@ -57,27 +64,30 @@ def test_provenance_names_the_reference_sources():
     for f in ("FFT_nr3.f", "tangent_homo.f", "G_K_dF.f", "mm10_a.f", "polar.f", "cep2A.f", "fortran_subset"):
         assert f in p
     assert int(V["step_n_tangent_homo"][-1]) > NSTEP          # the stress-controlled outer loop iterated
+    assert int(V["m01_step_n_tangent_homo"][-1]) == 1         # the strain-controlled job: only the initial tangent_homo
 
 
-def test_initial_tangent(oracle_built):
-    """drive_eps_sig(1, 0) at F = I (FFT_finite_3d.f:145): the elastic dP/dF of every voxel"""
-    o = Oracle(problem(), threads=1)
+@pytest.mark.parametrize("job", ["", "m01_"])
+def test_initial_tangent(oracle_built, job):
+    """drive_eps_sig(1, 0) at F = I (FFT_finite_3d.f:145): the elastic dP/dF of every voxel (mm01: from properties the
+    reference keeps in single precision, mod_fft.f:20)"""
+    o = Oracle(problem(job), threads=1)
     o.drive_eps_sig(1, 0)
-    assert np.abs(o.K4.T - V["K4_initial"]).max() <= 1e-14 * np.abs(V["K4_initial"]).max()
+    assert np.abs(o.K4.T - V[job + "K4_initial"]).max() <= 1e-14 * np.abs(V[job + "K4_initial"]).max()
 
 
-@pytest.mark.parametrize("polar", ["double", "quad"])
-def test_oracle_solver_follows_the_reference_run(oracle_built, polar):
+@pytest.mark.parametrize("job,polar", [("", "double"), ("", "quad"), ("m01_", "quad")])
+def test_oracle_solver_follows_the_reference_run(oracle_built, job, polar):
     """FFT_nr3 of the oracle against FFT_nr3 of the reference: per load step the converged F and P fields, the mean
     deformation gradient the stress-controlled loop arrives at, the mean stress, and -- exactly -- the CG iteration count of
     every Newton-loop solve, the number of material sweeps and the number of outer (mean-stress) iterations."""
-    ref_cg, ref_sweeps, ref_outer = reference_iterations()
+    ref_cg, ref_sweeps, ref_outer = reference_iterations(job)
     for k in range(1, NSTEP + 1):
-        o = Oracle(problem(), threads=1, polar=polar)
+        o = Oracle(problem(job), threads=1, polar=polar)
         o.drive_eps_sig(1, 0)
         res = o.FFT_nr3(k)
         assert res["rc"] == 0
-        F1, P1 = V["step_Fn1"][k - 1], V["step_Pn1"][k - 1]
+        F1, P1 = V[job + "step_Fn1"][k - 1], V[job + "step_Pn1"][k - 1]
         assert np.abs(o.Fn1.T - F1).max() <= 1e-10
         assert np.abs(o.Pn1.T - P1).max() <= 2e-8 * np.abs(P1).max()
         assert np.abs(res["Pbar"][k - 1] - P1.mean(axis=0)).max() <= 2e-8 * np.abs(P1).max()
@@ -190,3 +200,33 @@ def test_wrapper_cases(host, name, impl):
         assert (int(it[:npts, 0].sum()), int(it[:npts, 1].sum())) == tuple(int(x) for x in W(f"iters{step}"))
         m.Fn[...] = m.Fn1
         m.update()
+
+
+@pytest.mark.parametrize("k", range(1, NSTEP + 1))
+def test_kernel_source_mm01_sweep_on_the_reference_state(host, k):
+    """the same for the mm01 job (the two materials of examples/test_mm01.in scattered over the grid, kinematic / mixed /
+    isotropic hardening per voxel, 3 % strain per step, every point plastic): the kernel source's closing sweep of each step
+    on the reference's state -- P and the unrotated stress (measured 4e-10 in step 1, 1e-12 after), the energy densities, the
+    11-word history with the packed integer state word bit for bit."""
+    job = "m01_"
+    h = host(problem(job))
+    assert h.H == int(V[job + "hist_size"]) == 11
+    h.drive_eps_sig(1, 0)
+    h.Fn[...] = np.eye(3).reshape(9, 1) if k == 1 else V[job + "step_Fn1"][k - 2].T
+    h.Fn1[...] = V[job + "step_Fn1"][k - 1].T
+    if k > 1:
+        h.hist_n[...] = V[job + "step_hist"][k - 2].T
+        h.urcs_n[...] = V[job + "step_urcs"][k - 2].T
+    last = [s for s in V[job + "sweeps"] if s[0] == k][-1]
+    assert h.drive_eps_sig(k, int(last[1])) == 0
+    P1, H1, U1 = V[job + "step_Pn1"][k - 1], V[job + "step_hist"][k - 1], V[job + "step_urcs"][k - 1]
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    hk = h.hist_n1.T
+    assert rel(h.Pn1.T, P1) <= 2e-9
+    assert rel(h.urcs_n1.T[:, :6], U1[:, :6]) <= 2e-9
+    assert rel(h.urcs_n1.T[:, 6:], U1[:, 6:]) <= 2e-9
+    mask = np.ones(11, dtype=bool); mask[3] = False
+    assert rel(hk[:, mask], H1[:, mask]) <= 1e-11
+    word = lambda a: np.ascontiguousarray(a[:, 3]).view(np.int64)
+    assert np.array_equal(word(hk), word(H1))
+    assert np.count_nonzero(word(H1) & 0xFFFFFFFF == 1) >= 26              # the job is plastic almost everywhere

@@ -6,7 +6,8 @@ interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/g
 
     python tools/make_reference_global.py            # needs /root/reference (this container); about two minutes
 
-A second set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
+A second job (`m01_*`) is strain-controlled with mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450) as the
+material.  A further set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
 point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
 
 tests/test_reference_global.py (which needs neither /root/reference nor this script) holds the oracle's solver and the
@@ -124,8 +125,10 @@ class Harness:
     (drive_eps_sig.f:203-300), with its own interpreter because the history layout is module data.  slip_type 1 (fcc, 12
     systems) or 8 (bcc48, which selects the maximum-size layout, mm10_d.f:136-141)."""
 
-    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES):
-        self.npts, self.slip_type, self.mts = npts, slip_type, mts
+    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES, mm01=None):
+        self.npts, self.slip_type, self.mts, self.mm01 = npts, slip_type, mts, mm01
+        if angles is None:
+            angles = np.zeros((npts, 1, 3))
         it = self.it = F.Interpreter()
         it.add_constants(open(REF + "param_def").read())
         mc_src = open(REF + "mod_crystals.f").read()
@@ -214,6 +217,12 @@ class Harness:
                              angle_convention=np.ones(mx, dtype=np.int64), fn=Z(mx, 3, 3), fn1=Z(mx, 3, 3), urcs_blk_n=Z(mx, 9, 1),
                              urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
         self.lw, self.lw1 = mk(npts), mk(1)
+        if mm01 is not None:                      # mm01: 11 history words per point (mm01.f:219-262), properties per point
+            self.hist_sz = hist_sz = 11
+            pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(mx - npts)])
+            self.m1 = NS(e=pad(mm01["e"]), nu=pad(mm01["nu"]), beta=pad(mm01["beta"]), yld=pad(mm01["yld"]),
+                         h=pad(np.asarray(mm01["tan_e"]) * np.asarray(mm01["e"]) / (np.asarray(mm01["e"]) - np.asarray(mm01["tan_e"]))))
+            self.eps_n, self.eps_n1 = Z(npts, 6), Z(npts, 6)
         self.hist_n, self.hist_n1 = Z(npts, hist_sz), Z(npts, hist_sz)
         self.h_n, self.h_n1, self.u1 = Z(1, hist_sz), Z(1, hist_sz), Z(mx, 6)
         self.ncrystals = np.full(mx, ncry, dtype=np.int64)
@@ -238,7 +247,20 @@ class Harness:
         self.hist_n1[...] = 0.0
         lw.urcs_blk_n1[...] = 0.0
         nj0, nj110 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
-        for e in range(span):              # one-point blocks: mm10 addresses the history through history(iloop, 1) with an assumed-size dummy,
+        if self.mm01 is not None:          # drive_01_update (rstgp1.f:330-450): total strain, mm01, cnst1, [D] kept as its upper triangle
+            m1 = self.m1
+            self.eps_n1[...] = self.eps_n + uddt[:span]                  # rstgp1_update_strains
+            cgn1, rtse, cep = Z(mx, 9), Z(mx, 6), Z(mx, 6, 6)
+            it.call("mm01", span, 1, 1, int(step), int(iter_), m1.e, m1.nu, m1.beta, m1.h, np.zeros(mx), m1.yld, lw.urcs_blk_n, cgn1, uddt, self.hist_n,
+                    self.hist_n1, rtse, np.zeros(mx), m1.e, m1.nu, 6)
+            lw.urcs_blk_n1[:, :, 0] = cgn1
+            h1 = self.hist_n1
+            it.call("cnst1", span, cep, rtse, m1.nu, m1.e, np.asfortranarray(h1[:, 1].copy()), np.asfortranarray(h1[:, 4].copy()), m1.beta,
+                    np.asfortranarray(h1[:, 0].copy()), np.asfortranarray(h1[:, 3].copy()), 1, 6)
+            for i in range(span):                                         # rstgp1_store_cep keeps 21 terms, drive_01_cnst mirrors them
+                cep[i] = np.triu(cep[i]) + np.triu(cep[i], 1).T
+            self.cep_mm01 = cep
+        for e in range(span if self.mm01 is None else 0):              # one-point blocks: mm10 addresses the history through history(iloop, 1) with an assumed-size dummy,
             lw1.step, lw1.iter, lw1.felem, lw1.material_cut_step = lw.step, lw.iter, e + 1, False      # which for span > 1 runs past whole columns
             lw1.c_props[0, :] = self.c_props[e, :]
             lw1.rot_blk_n1[0] = lw.rot_blk_n1[e]; lw1.urcs_blk_n[0] = lw.urcs_blk_n[e]; lw1.urcs_blk_n1[...] = 0.0
@@ -257,7 +279,7 @@ class Harness:
         P_blk, A_blk, cep = Z(mx, 9), Z(mx, 81), Z(mx, 6, 6)
         it.call("cs2p", span, 1, cs, fn1inv, detF, P_blk)
         for i in range(span):                                             # drive_10_cnst, gptns1.f:562-567
-            cep[i] = self.hist_n1[i, 0:36].reshape(6, 6, order="F")
+            cep[i] = self.hist_n1[i, 0:36].reshape(6, 6, order="F") if self.mm01 is None else self.cep_mm01[i]
         it.call("cep2a", lw, cep, rnh, detF, detFh, fnhinv, fn1inv, A_blk)
         nj, nj11 = it.calls.get("mm10_formj", 0) - nj0, it.calls.get("mm10_formj11", 0) - nj110
         self.sweeps.append((int(step), int(iter_), nj11 - nj, nj))
@@ -265,6 +287,8 @@ class Harness:
 
     def update(self):
         self.hist_n[...] = self.hist_n1; self.lw.urcs_blk_n[...] = self.lw.urcs_blk_n1            # update.f:85-93
+        if self.mm01 is not None:
+            self.eps_n[...] = self.eps_n1
 
 
 def wrapper_cases(out):
@@ -295,21 +319,14 @@ def wrapper_cases(out):
     out["mts_names"] = np.array(sorted(MTS)); out["mts_params"] = np.array([MTS[k] for k in sorted(MTS)])
 
 
-def main():
-    t_start = time.time()
-    N, nstep = 3, int(os.environ.get("GLOBAL_NSTEP", "3"))
+def run_job(out, prefix, N, nstep, FP_max, isNBC, make_harness, t_start):
+    """FFT_init's state (FFT_init.f:141-172), the initial sweep and FFT_nr3 (FFT_finite_3d.f:145-146) for one job; results
+    under `prefix` in `out`"""
     N3 = N ** 3
-    rng = np.random.default_rng(20240609)
-    out = {}
-    wrapper_cases(out)
-
-    # ---- module fft: the arrays FFT_init allocates (FFT_init.f:141-172) and the solver parameters of the deck
     fft = dict(n=N, nhalf=(N + 1) // 2, n3=N3, ndim1=3, ndim2=9, veclen=9 * N3, dims=np.array([N, N, N]), ghat4=Z(N3, 81), k4=Z(N3, 81),
                coeffs1=Z(N, N, N), coeffs2=Z(N, N, N), real1=Z(N3, 9), real2=Z(N3, 9), real3=Z(N3, 9), b=Z(N3, 9), fn=Z(N3, 9), fn1=Z(N3, 9),
-               pn=Z(N3, 9), pn1=Z(N3, 9), dfm=Z(N3, 9), tmppcg=Z(9 * N3, 4), isnbc=np.zeros(9, dtype=bool), bc_all=Z(9, nstep),
+               pn=Z(N3, 9), pn1=Z(N3, 9), dfm=Z(N3, 9), tmppcg=Z(9 * N3, 4), isnbc=np.asarray(isNBC, dtype=bool), bc_all=Z(9, nstep),
                straininc=0.0, tolpcg=1.0e-10, tolnr=1.0e-5, maxiter=10, nstep=nstep, out_step=np.zeros(nstep, dtype=bool))
-    FP_max = np.zeros(9); FP_max[0] = 0.002                  # uniaxial tension along x: F_xx prescribed, P_yy = P_zz = 0, no mean shear
-    fft["isnbc"][[4, 8]] = True
     mults = np.ones(nstep)
     bc = np.cumsum(np.outer(mults, FP_max), axis=0)           # inlod.f:57-63
     for d in (0, 4, 8):
@@ -317,17 +334,14 @@ def main():
             bc[:, d] += 1.0
     fft["bc_all"][...] = bc.T
     fft["fn"][:, [0, 4, 8]] = 1.0; fft["fn1"][...] = fft["fn"]
-
-    # ---- one crystal per voxel, fcc, Voce hardening, its own orientation
-    angles = rng.uniform(0.0, 360.0, (N3, 3))
-    H = Harness(N3, angles, extra_module_vars=fft)
-    it, prm, hist_sz = H.it, PRM, H.hist_sz
+    H = make_harness(fft)
+    it = H.it
     log = dict(cg=[], steps=[])
 
     def drive_eps_sig(step, iter_):
         P, K = H.sweep(step, iter_, fft["fn"], fft["fn1"])
         fft["pn1"][...] = P; fft["k4"][...] = K
-        print(f"  sweep step {step} iter {iter_}: {time.time() - t_start:.0f} s", flush=True)
+        print(f"  {prefix}sweep step {step} iter {iter_}: {time.time() - t_start:.0f} s", flush=True)
 
     def update():
         H.update()
@@ -352,13 +366,46 @@ def main():
     K4_initial = np.ascontiguousarray(fft["k4"]).copy()
     it.call("fft_nr3")                                                   # FFT_finite_3d.f:146
 
-    out.update(N=N, nstep=nstep, angles=angles, params=np.array([prm[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]),
-               FP_max=FP_max, isNBC=fft["isnbc"].astype(np.int32), mults=mults, tolNR=fft["tolnr"], tolPCG=fft["tolpcg"], maxIter=fft["maxiter"],
-               K4_initial=K4_initial, hist_size=hist_sz)
+    res = dict(N=N, nstep=nstep, FP_max=FP_max, isNBC=fft["isnbc"].astype(np.int32), mults=mults, tolNR=fft["tolnr"], tolPCG=fft["tolpcg"],
+               maxIter=fft["maxiter"], K4_initial=K4_initial, hist_size=H.hist_sz)
     for k in ("Fn1", "Pn1", "hist", "urcs", "n_sweeps", "n_cg", "n_tangent_homo"):
-        out["step_" + k] = np.array([s[k] for s in log["steps"]])
-    out["sweeps"] = np.array(H.sweeps)                            # (step, global iteration, predictor Jacobians, update Jacobians) summed over the block
-    out["cg"] = np.array(log["cg"])                                    # (tangent_homo calls so far, CG iterations) per fftPcg call, in call order
+        res["step_" + k] = np.array([s[k] for s in log["steps"]])
+    res["sweeps"] = np.array(H.sweeps)                            # (step, global iteration, predictor Jacobians, update Jacobians) summed over the block
+    res["cg"] = np.array(log["cg"])                                    # (tangent_homo calls so far, CG iterations) per fftPcg call, in call order
+    for k, v in res.items():
+        out[prefix + k] = v
+    return H
+
+
+def main():
+    t_start = time.time()
+    N, nstep = 3, int(os.environ.get("GLOBAL_NSTEP", "3"))
+    N3 = N ** 3
+    rng = np.random.default_rng(20240609)
+    out = {}
+    wrapper_cases(out)
+
+    # ---- job 1: one fcc crystal per voxel, Voce hardening, its own orientation; uniaxial tension along x under mixed boundary
+    #      conditions: F_xx prescribed, P_yy = P_zz = 0, no mean shear
+    angles = rng.uniform(0.0, 360.0, (N3, 3))
+    FP_max = np.zeros(9); FP_max[0] = 0.002
+    isNBC = np.zeros(9, dtype=bool); isNBC[[4, 8]] = True
+    run_job(out, "", N, nstep, FP_max, isNBC, lambda fft: Harness(N3, angles, extra_module_vars=fft), t_start)
+    out.update(angles=angles, params=np.array([PRM[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]))
+
+    # ---- job 2: mm01 (bilinear Mises plasticity), the two materials of the shipped deck examples/test_mm01.in scattered over the
+    #      grid with kinematic / mixed / isotropic hardening per voxel, strain-controlled (all nine mean components prescribed):
+    #      the deck's 3 % tension with lateral contraction per step plus a shear component
+    rng = np.random.default_rng(20240611)
+    incl = rng.random(N3) < 0.4
+    m01 = dict(e=np.where(incl, 24000.0, 12000.0), nu=np.full(N3, 0.3), yld=np.where(incl, 200.0, 100.0), tan_e=np.full(N3, 1000.0),
+               beta=rng.choice([0.0, 0.5, 1.0], N3))
+    m01_single = {k: np.asarray(v, dtype=np.float32).astype(np.float64) for k, v in m01.items()}      # matprp is single precision (mod_fft.f:20)
+    FP_max = np.array([0.03, 0.005, 0.0, 0.0, -0.01, 0.0, 0.0, 0.0, -0.01])
+    run_job(out, "m01_", N, nstep, FP_max, np.zeros(9, dtype=bool), lambda fft: Harness(N3, None, extra_module_vars=fft, mm01=m01_single), t_start)
+    for k, v in m01.items():
+        out["m01_prop_" + k] = np.asarray(v, dtype=np.float64)
+
     h = hashlib.sha256()
     for f in FILES:
         h.update(open(REF + f, "rb").read())
