@@ -18,11 +18,16 @@ class _KernelSourceSolver:
     def drive_eps_sig(self, step, it):
         return self.k.drive_eps_sig(step, it)
 
-    def upload(self, name, F):
-        getattr(self.k, {"FN1": "Fn1", "FN": "Fn"}[name])[:] = F
+    FIELDS = {"FN1": "Fn1", "FN": "Fn", "PN1": "Pn1", "K4": "K4", "HIST_N": "hist_n", "HIST_N1": "hist_n1", "URCS_N": "urcs_n",
+              "URCS_N1": "urcs_n1", "EPS_N": "eps_n", "EPS_N1": "eps_n1"}
 
-    def download(self, name):
-        return np.array(getattr(self.k, {"PN1": "Pn1", "K4": "K4"}[name]))
+    def upload(self, name, F):
+        f = getattr(self.k, self.FIELDS[name])
+        f[:] = np.asarray(F).reshape(f.shape)
+
+    def download(self, name, layout=0):
+        a = np.array(getattr(self.k, self.FIELDS[name]))
+        return np.ascontiguousarray(a.T) if layout == 1 else a
 
     def local_iters(self):
         return np.array(self.k.local_iters)
@@ -63,3 +68,30 @@ def test_body_of_the_gpu_variant_test(oracle_built, kind):
 
 def test_body_of_the_gpu_spectral_test(oracle_built):
     T.test_fast_path_matches_plain_fft_statement((_OracleSolver, None), 16)
+
+
+# ---- tests/test_zzz_gpu_reference_fixtures.py: the reference-executed fixtures through the Solver interface
+
+import test_zzz_gpu_reference_fixtures as R
+
+
+@pytest.fixture(scope="module")
+def kernel_source_solver(oracle_built):
+    from host_kernels import build
+    build()
+    return _KernelSourceSolver
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_body_of_the_gpu_voxel_test(kernel_source_solver, k):
+    R.voxel_case(kernel_source_solver, k)
+
+
+@pytest.mark.parametrize("name", ["taylor", "mts", "bcc48"])
+def test_body_of_the_gpu_wrapper_test(kernel_source_solver, name):
+    R.wrapper_case(kernel_source_solver, name)
+
+
+@pytest.mark.parametrize("job,k", [("", 1), ("", 2), ("", 3), ("m01_", 1), ("m01_", 2), ("m01_", 3)])
+def test_body_of_the_gpu_job_sweep_test(kernel_source_solver, job, k):
+    R.job_sweep(kernel_source_solver, job, k)
