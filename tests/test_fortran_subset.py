@@ -298,3 +298,66 @@ def test_arithmetic_is_not_contracted():
     r = np.zeros(1)
     run(src, "fma", a, b, c, r)
     assert r[0] == (a * b) + c == 0.0                   # the product rounds to 1 - 2^-60 -> 1.0; a fused operation would give -2^-60
+
+
+def test_variables_that_begin_with_a_keyword():
+    """use_max = .true. is an assignment, not a use statement (nor are save_it, stop_now, format_id, write_flag statements of
+    those keywords) -- found when the reference's mm10_set_history_locs came out with the small history layout for 48 systems"""
+    src = """
+      subroutine kw( r )
+      implicit none
+      double precision :: r(5)
+      logical :: use_max
+      integer :: save_it, stop_now, format_id, write_flag
+      use_max = .false.
+      if( r(1) .gt. 0.0d0 ) then
+        use_max = .true.
+      end if
+      save_it = 2
+      stop_now = 3
+      format_id = 4
+      write_flag = 5
+      r(1) = 0.0d0
+      if( use_max ) r(1) = 1.0d0
+      r(2) = save_it
+      r(3) = stop_now
+      r(4) = format_id
+      r(5) = write_flag
+      return
+      end
+"""
+    r = np.ones(5)
+    run(src, "kw", r)
+    assert list(r) == [1.0, 2.0, 3.0, 4.0, 5.0]
+
+
+def test_module_scalars_written_by_a_unit_reach_the_harness():
+    """a unit that assigns module scalars hands them back; units compiled afterwards see the new values; allocate of a module
+    array the harness provides is a shape check"""
+    src = """
+      subroutine setit
+      use sizes, only : ntotal, table
+      implicit none
+      integer :: i
+      if( .not. allocated( table ) ) allocate( table(3) )
+      ntotal = 0
+      do i = 1, 3
+        table(i) = 10 * i
+        ntotal = ntotal + table(i)
+      end do
+      return
+      end
+      subroutine readit( r )
+      use sizes, only : ntotal
+      implicit none
+      double precision :: r(1)
+      r(1) = ntotal
+      return
+      end
+"""
+    table = np.zeros(3, dtype=np.int64)
+    it, _ = run(src, "setit", module_vars=dict(ntotal=-1, table=table))
+    assert it.module_vars["ntotal"] == 60 and list(table) == [10, 20, 30]
+    r = np.zeros(1)
+    it.call("readit", r)
+    assert r[0] == 60.0

@@ -230,3 +230,24 @@ def test_kernel_source_mm01_sweep_on_the_reference_state(host, k):
     word = lambda a: np.ascontiguousarray(a[:, 3]).view(np.int64)
     assert np.array_equal(word(hk), word(H1))
     assert np.count_nonzero(word(H1) & 0xFFFFFFFF == 1) >= 26              # the job is plastic almost everywhere
+
+
+@pytest.mark.parametrize("name", ["taylor", "mts", "bcc48"])
+def test_history_layout_is_the_references(host, name):
+    """mm10_set_history_locs (mm10_d.f:25-331), executed: start / end of the common blocks and of every crystal block for 12
+    systems (158 words, 300 with three crystals) and for the 48-system maximum-size layout (357) -- the table the kernels'
+    cpf_hist_layout (cpfft_b200/csrc/material_types.h) and tests/helpers.mm10_layout restate"""
+    from helpers import mm10_layout
+    W = lambda k: V[f"wrap_{name}_{k}"]
+    ncry, nslip = int(W("ncry")), 12 if int(W("slip_type")) == 1 else 48
+    L = mm10_layout(nslip)
+    common = W("layout_common")                              # (5, 2): 1-based first / last index of cep, gradfe, R, work, slipsum
+    for row, key in enumerate(("cep", "gradfe", "R", "work", "slipsum")):
+        assert (int(common[row, 0]) - 1, int(common[row, 1])) == tuple(L[key])
+    per = L["total"] - L["stress"][0]
+    assert [int(x) for x in W("layout_sizes")] == [L["stress"][0], per]
+    crystal = W("layout_crystal")                            # (ncry, 11, 2)
+    for c in range(ncry):
+        for row, key in enumerate(("stress", "euler", "Rp", "D", "eps", "slipinc", "tau_tilde", "u", "tt_rate", "ep", "ed")):
+            assert (int(crystal[c, row, 0]) - 1, int(crystal[c, row, 1])) == (L[key][0] + c * per, L[key][1] + c * per)
+    assert int(W("hist_size")) == L["stress"][0] + ncry * per == {("taylor"): 300, "mts": 158, "bcc48": 357}[name]

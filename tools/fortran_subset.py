@@ -35,7 +35,7 @@ INTRINSICS = {
     "dot_product": "_ftn_dot", "matmul": "np.matmul", "transpose": "np.transpose", "maxval": "np.max", "minval": "np.min",
     "isnan": "_ftn_isnan", "any": "np.any", "all": "np.all", "size": "np.size", "log10": "math.log10", "dlog10": "math.log10", "idint": "_ftn_int", "ifix": "_ftn_int", "dfloat": "float",
     "sinh": "math.sinh", "cosh": "math.cosh", "tanh": "math.tanh", "nint": "_ftn_nint", "float": "float",
-    "exponent": "(lambda x_: math.frexp(x_)[1])", "epsilon": "(lambda x_: 2.220446049250313e-16)",
+    "exponent": "(lambda x_: math.frexp(x_)[1])", "allocated": "(lambda a_: a_ is not None)", "epsilon": "(lambda x_: 2.220446049250313e-16)",
 }
 
 
@@ -102,6 +102,11 @@ def _dscal(n, alpha, x, incx):                # BLAS: x *= alpha
 
 
 ADDRESS_FUNCS = {"dnrm2": (1,), "ddot": (1, 3)}      # function arguments passed by address: array or first element of a run
+
+
+def _check_allocated(a, shape, name):
+    if tuple(a.shape) != tuple(shape):
+        raise FortranError(f"allocate({name}{tuple(shape)}): the module array provided by the harness has shape {a.shape}")
 
 
 def _assign_whole(a, v):
@@ -687,7 +692,8 @@ class Interpreter:
                 for nm in split_top(m.group(2)):
                     data_init.append((nm.strip(), ("__derived__", m.group(1))))
                 continue
-            if re.match(r"(implicit|use|include|intent|save|external|format|!dir|deallocate|type\s*\()", st) or st.startswith("c!dir"):
+            if (re.match(r"(implicit|use|include|intent|save|external|format|deallocate)\b(?!\s*=)", st) or re.match(r"(!dir|type\s*\()", st)
+                    or st.startswith("c!dir")):       # keywords, not variables that begin with one (use_max = .true.)
                 continue
             m = re.match(r"equivalence\s*\(\s*(\w+)\s*,\s*(\w+)\s*\)\s*$", st)
             if m:
@@ -841,17 +847,26 @@ class Interpreter:
             py.append(f"{ind}{ind}return")
             assigned |= {v for v in iassigned if v in args}
         body_py = self._block(stmts, tr, arrays, scalars | known, args, assigned, 1)
-        py += body_py
         outs = [a for a in args if a in assigned and a not in arrays]
         ret = name if kind == "function" else f"{{{', '.join(repr(o) + ': ' + o for o in outs)}}}"
-        py.append(f"{ind}return {ret}")
+        written = sorted(v for v in assigned if v in module_names and v not in arrays and v not in args)
+        if written:                     # module scalars this unit sets: handed back to the harness's table when the unit returns
+            py[1:1] = [f"{ind}{v} = _mv[{v!r}]" for v in written]
+            py.append(f"{ind}try:")
+            py += self._block(stmts, tr, arrays, scalars | known, args, set(), 2)
+            py.append(f"{ind}{ind}return {ret}")
+            py.append(f"{ind}finally:")
+            py += [f"{ind}{ind}_mv[{v!r}] = {v}" for v in written]
+        else:
+            py += body_py
+            py.append(f"{ind}return {ret}")
         src = "\n".join(py)
         src = src.replace("return _RET_", f"return {ret}")
         self.array_dummies[name] = [a in arrays for a in args]
         self.sources[name] = src
         glob = {"np": np, "math": math, "_ftn_sign": _ftn_sign, "_ftn_mod": _ftn_mod, "_ftn_int": _ftn_int, "_ftn_div": _ftn_div, "_ftn_pow": _ftn_pow,
                 "_ftn_dot": _ftn_dot, "_ftn_nint": _ftn_nint, "_ftn_dble": _ftn_dble, "_ftn_isnan": _ftn_isnan, "_flat": _flat, "_flat0": _flat0, "_reshape_dummy": _reshape_dummy, "_call": self.call, "_fcall": self.call, "_first": _first, "_assign_whole": _assign_whole,
-                "_builtin": BUILTIN_SUBS, "_bfunc": BUILTIN_FUNCS, **DFTI_CONSTS, "_flat_any": _flat_any, "_new_derived": self.new_derived, **self.consts, **self.module_vars}
+                "_builtin": BUILTIN_SUBS, "_bfunc": BUILTIN_FUNCS, **DFTI_CONSTS, "_flat_any": _flat_any, "_new_derived": self.new_derived, "_mv": self.module_vars, "_check_allocated": _check_allocated, **self.consts, **self.module_vars}
         exec(compile(src, f"<fortran {name}>", "exec"), glob)
         self.funcs[name] = glob[name]
         self.funcs[name]._outs = outs
@@ -947,7 +962,7 @@ class Interpreter:
         return py
 
     def _simple(self, st, tr, arrays, scalars, args, assigned):
-        if re.match(r"(write|print|format|continue)\b", st):
+        if re.match(r"(write|print|format|continue)\b(?!\s*=)", st):
             return ["pass"]
         if re.match(r"return\s*$", st):
             return ["return _RET_"]
@@ -955,7 +970,7 @@ class Interpreter:
             return ["break"]
         if re.match(r"cycle\s*$", st):
             return ["continue"]
-        if re.match(r"(go\s*to|goto|stop|call\s+die)", st):
+        if re.match(r"(go\s*to\b|goto\b|stop\b|call\s+die)(?!\s*=)", st):
             return [f"raise RuntimeError({st!r})"]
         m = re.match(r"allocate\s*\((.*)\)\s*$", st)
         if m:
@@ -963,6 +978,9 @@ class Interpreter:
             for item in split_top(m.group(1)):
                 mm = re.match(r"(\w+)\s*\((.*)\)$", item.strip())
                 shape = ", ".join(f"int({tr.expr(d, arrays, scalars)})" for d in split_top(mm.group(2)))
+                if mm.group(1) in self.module_vars:        # a module array: the harness owns it, it must already have the requested shape
+                    lines.append(f"_check_allocated({mm.group(1)}, ({shape},), {mm.group(1)!r})")
+                    continue
                 lines.append(f"{mm.group(1)} = np.zeros(({shape},), order='F'{', dtype=np.int64' if mm.group(1) in self._int_arrays else ''})")
                 assigned.add(mm.group(1))
             return lines

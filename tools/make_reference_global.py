@@ -33,9 +33,8 @@ What is NOT the reference's text, and why:
     routines listed above in do_nleps_block's order on one 27-point block.  drive_10_cnst's copy of history(1:36) into the
     block tangent (gptns1.f:519-567) and update.f's n+1 -> n copies are one assignment each, done here.  rknstr_finish_cp (the
     lattice-curvature fit) is not run: its output only enters through k_0, which is zero.
-  * mm10_set_cons returns at once for Voce hardening (mm10_a.f:383-388) and is skipped; mm10_set_history_locs
-    (mm10_d.f:25-331) writes module scalars, which the interpreter keeps read-only: the history layout is set here from the
-    same table (and is not what is compared).
+  * mm10_set_cons returns at once for Voce / MTS hardening (mm10_a.f:383-388) and is skipped.  The history layout is computed by
+    the reference's mm10_set_history_locs (mm10_d.f:25-331) from hand-filled material tables (one CP material, one crystal type).
   * MKL DFTI is numpy's FFT (tools/fortran_subset.py).
 """
 import hashlib
@@ -52,7 +51,7 @@ import fortran_subset as F  # noqa: E402
 import make_reference_vectors as G  # noqa: E402
 
 REF = G.REF
-FILES = G.FILES + ["FFT_nr3.f", "tangent_homo.f"]
+FILES = G.FILES + ["FFT_nr3.f", "tangent_homo.f", "mm10_d.f"]
 
 
 class Defaulting(NS):
@@ -143,26 +142,32 @@ class Harness:
         bvec, nvec = Oracle.slip_table(slip_type)
         nslip = self.nslip = len(bvec)
 
-        # module mm10_defs: the history layout mm10_set_history_locs computes (mm10_d.f:136-331)
-        use_max = nslip == ms_max
-        lcm = np.array([36, 27, 9, 3, ms_max if use_max else nslip])
-        lcr = np.array([6, 3, 9, 6, 6, ms_max, mu_, mu_, mu_, 6, 6] if use_max else [6, 3, 9, 6, 6, nslip, 1, 15, 1, 6, 6])
-        ic = np.zeros((5, 2), dtype=np.int64, order="F")
-        ic[:, 1] = np.cumsum(lcm); ic[:, 0] = ic[:, 1] - lcm + 1
-        ich = np.zeros((it.consts["max_crystals"], 11, 2), dtype=np.int64, order="F")
-        for c in range(ich.shape[0]):
-            start = ic[4, 1] + 1 + c * lcr.sum()
-            ich[c, :, 0] = start + np.cumsum(lcr) - lcr; ich[c, :, 1] = ich[c, :, 0] + lcr - 1
-        self.hist_sz = hist_sz = int(ic[4, 1] + ncry * lcr.sum())
-        self.crystal_start, self.crystal_len, self.lcr = int(ic[4, 1]), int(lcr.sum()), lcr
-        mm10_defs = dict(indexes_common=ic, index_crys_hist=ich, length_comm_hist=lcm.astype(np.int64), length_crys_hist=lcr.astype(np.int64),
-                         num_common_indexes=5, num_crystal_terms=11, one_crystal_hist_size=int(lcr.sum()), common_hist_size=int(lcm.sum()),
-                         asymmetric_assembly=False)
-        it.module_vars.update(mm10_defs); it.module_members["mm10_defs"] = set(mm10_defs)
+        # module mm10_defs: the history layout, computed by the reference's own mm10_set_history_locs (mm10_d.f:25-331) from the
+        # material / crystal tables a deck with one crystal-plasticity material of `ncry` crystals per point leaves behind
+        mcr = it.consts["max_crystals"]
+        mm10_defs = dict(indexes_common=np.zeros((5, 2), dtype=np.int64, order="F"), index_crys_hist=np.zeros((mcr, 11, 2), dtype=np.int64, order="F"),
+                         length_comm_hist=np.zeros(5, dtype=np.int64), length_crys_hist=np.zeros(11, dtype=np.int64), num_common_indexes=0,
+                         num_crystal_terms=0, one_crystal_hist_size=0, common_hist_size=0, asymmetric_assembly=False)
+        matprp = np.zeros((300, 500), order="F"); matprp[8, 0] = 10                      # matprp(9, 1): material model 10
+        imatprp = np.zeros((300, 500), dtype=np.int64, order="F")
+        imatprp[100, 0], imatprp[103, 0], imatprp[104, 0] = ncry, 1, 1                     # imatprp(101 / 104 / 105, 1): crystals per point, one crystal type, its number
+        c_array = np.empty(mcr, dtype=object); c_array[0] = NS(nslip=nslip, num_hard=1)
+        tables = dict(matprp=matprp, imatprp=imatprp, matlist=np.ones(npts, dtype=np.int64), c_array=c_array,
+                      crystal_input=np.zeros((1, 1), dtype=np.int64), data_offset=np.zeros(npts, dtype=np.int64))
+        it.consts.update(nummat=1, noelem=npts)
+        it.module_vars.update(mm10_defs); it.module_vars.update(tables)
+        it.load(open(REF + "mm10_d.f").read())
+        it.call("mm10_set_history_locs")
+        for k_ in tables:
+            del it.module_vars[k_]
+        ic, lcr = it.module_vars["indexes_common"], it.module_vars["length_crys_hist"]
+        self.hist_sz = hist_sz = int(ic[4, 1] + ncry * it.module_vars["one_crystal_hist_size"])
+        it.module_members["mm10_defs"] = set(mm10_defs)
         if extra_module_vars:
             it.module_vars.update(extra_module_vars); it.module_members["fft"] = set(extra_module_vars)
         for f in files[2:]:
-            it.load(open(REF + f).read())
+            if f != "mm10_d.f":
+                it.load(open(REF + f).read())
         del it.units["mm10_set_cons"]                            # returns at once for Voce / MTS (mm10_a.f:383-388); its allocate(..., stat=) is not interpretable
         F.BUILTIN_SUBS.setdefault("mm10_set_cons", lambda *a: None); F.BUILTIN_ARRAY_ARGS.setdefault("mm10_set_cons", ())
         F.BUILTIN_SUBS.setdefault("die_abort", _die); F.BUILTIN_ARRAY_ARGS.setdefault("die_abort", ())
@@ -305,7 +310,10 @@ def wrapper_cases(out):
         F1 = eye + 0.0015 * rng.standard_normal((npts, 9))
         F2 = F1 + 0.0012 * rng.standard_normal((npts, 9))
         P0, K0 = H.sweep(1, 0, eye, eye)
-        rec = dict(angles=angles, F1=F1, F2=F2, K4_initial=K0, hist_size=H.hist_sz, slip_type=slip_type, h_type=2 if mts else 1, ncry=ncry)
+        mv = H.it.module_vars
+        rec = dict(angles=angles, F1=F1, F2=F2, K4_initial=K0, hist_size=H.hist_sz, slip_type=slip_type, h_type=2 if mts else 1, ncry=ncry,
+                   layout_common=mv["indexes_common"].copy(), layout_crystal=mv["index_crys_hist"][:ncry].copy(),      # mm10_set_history_locs' tables
+                   layout_sizes=np.array([mv["common_hist_size"], mv["one_crystal_hist_size"]]))
         for step, (Fa, Fb) in ((1, (eye, F1)), (2, (F1, F2))):
             P, K = H.sweep(step, 1, Fa, Fb)
             rec[f"P{step}"], rec[f"K4_{step}"] = P, K
