@@ -4,8 +4,9 @@ loop, fftPcg, tangent_homo, NBC_update, the operator G_K_dF and -- inside the Py
 the crystal-plasticity wrapper mm10 with everything below it, executed statement by statement by the Fortran-subset
 interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/golden/reference_global.npz.
 
-    python tools/make_reference_global.py            # needs /root/reference (this container); about two minutes
+    python tools/make_reference_global.py            # needs /root/reference (this container); about twelve minutes (GLOBAL_DECK_STEPS=0: two)
 
+A third job (`deck_*`) is the reference's shipped deck examples/test_mm10.in, all ten load steps (7^3, bcc48, three blocks).
 A second job (`m01_*`) is strain-controlled with mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450) as the
 material.  A further set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
 point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
@@ -124,8 +125,9 @@ class Harness:
     (drive_eps_sig.f:203-300), with its own interpreter because the history layout is module data.  slip_type 1 (fcc, 12
     systems) or 8 (bcc48, which selects the maximum-size layout, mm10_d.f:136-141)."""
 
-    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES, mm01=None):
+    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES, mm01=None, prm=None, dt=1.0):
         self.npts, self.slip_type, self.mts, self.mm01 = npts, slip_type, mts, mm01
+        PRM = {**globals()["PRM"], "alter_mode": False, "eps_dot_0_y": 1.0e10, **(prm or {})}
         if angles is None:
             angles = np.zeros((npts, 1, 3))
         it = self.it = F.Interpreter()
@@ -200,8 +202,8 @@ class Harness:
                 RE = Z(6, 6)
                 it.call("mm10_rt2rve", trot, RE)
                 cp = Defaulting(raten=PRM["rate_n"], theta_o=PRM["theta_0"], tau_y=PRM["tau_y"], tau_v=PRM["tau_v"], voche_m=PRM["voche_m"], id_v=PRM["iD_v"],
-                                burgers=2.87e-7, eps_dot_o_y=1.0e10, solver=True, strategy=True, gpall=False, gpp=0, method=0, miter=30, atol=1e-5,
-                                atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, alter_mode=False, nslip=nslip, h_type=2 if mts else 1, num_hard=1,
+                                burgers=2.87e-7, eps_dot_o_y=PRM["eps_dot_0_y"], solver=True, strategy=True, gpall=False, gpp=0, method=0, miter=30, atol=1e-5,
+                                atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, alter_mode=bool(PRM["alter_mode"]), nslip=nslip, h_type=2 if mts else 1, num_hard=1,
                                 tang_calc=0, s_type=slip_type, cnum=1, st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max),
                                 qs=Z(3, ms_max), ns=Z(3, ms_max), init_elast_stiff=np.asfortranarray(RE @ Cc @ RE.T), init_angles=angles[e, c].copy())
                 if mts:
@@ -217,14 +219,15 @@ class Harness:
                 c_props[e, c] = cp
 
         # the block work space and the global state the block driver gathers from / scatters to
-        mk = lambda span: NS(dt=1.0, blk=1, span=span, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False,
+        mk = lambda span: NS(dt=float(dt), blk=1, span=span, felem=1, gpn=1, step=1, iter=0, iout=6, mat_type=10, material_cut_step=False,
                              debug_flag=np.zeros(mx, dtype=bool), c_props=np.empty((mx, ncry), dtype=object), angle_type=np.ones(mx, dtype=np.int64),
                              angle_convention=np.ones(mx, dtype=np.int64), fn=Z(mx, 3, 3), fn1=Z(mx, 3, 3), urcs_blk_n=Z(mx, 9, 1),
                              urcs_blk_n1=Z(mx, 9, 1), rot_blk_n1=Z(mx, 9, 1))
-        self.lw, self.lw1 = mk(npts), mk(1)
+        self.lw, self.lw1 = mk(min(npts, mx)), mk(1)
+        self.urcs_n, self.urcs_n1 = np.zeros((npts, 9)), np.zeros((npts, 9))
         if mm01 is not None:                      # mm01: 11 history words per point (mm01.f:219-262), properties per point
             self.hist_sz = hist_sz = 11
-            pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(mx - npts)])
+            pad = lambda a: np.asarray(a, dtype=np.float64)
             self.m1 = NS(e=pad(mm01["e"]), nu=pad(mm01["nu"]), beta=pad(mm01["beta"]), yld=pad(mm01["yld"]),
                          h=pad(np.asarray(mm01["tan_e"]) * np.asarray(mm01["e"]) / (np.asarray(mm01["e"]) - np.asarray(mm01["tan_e"]))))
             self.eps_n, self.eps_n1 = Z(npts, 6), Z(npts, 6)
@@ -234,11 +237,26 @@ class Harness:
         self.sweeps = []
 
     def sweep(self, step, iter_, Fn, Fn1):
-        """(npts, 9) row-major F_n, F_n+1 -> P (npts, 9), dP/dF (npts, 81); the n+1 history and stresses are kept in the harness"""
-        it, lw, lw1, mx, span = self.it, self.lw, self.lw1, self.mx, self.npts
-        lw.step, lw.iter, lw.material_cut_step = int(step), int(iter_), False
-        lw.fn[:span] = np.asarray(Fn).reshape(span, 3, 3)                # Fn(e, 1..9) = F11, F12, F13, F21, ... (drive_eps_sig.f:190-214)
-        lw.fn1[:span] = np.asarray(Fn1).reshape(span, 3, 3)
+        """(npts, 9) row-major F_n, F_n+1 -> P (npts, 9), dP/dF (npts, 81); the n+1 history and stresses are kept in the harness.
+        Blocks of at most mxvl = 128 points, as the reference's automatic blocking makes them (FFT_init.f:449-475)."""
+        Fn, Fn1 = np.asarray(Fn), np.asarray(Fn1)
+        P, K = np.zeros((self.npts, 9)), np.zeros((self.npts, 81))
+        self.hist_n1[...] = 0.0; self.urcs_n1[...] = 0.0
+        nj0, nj110 = self.it.calls.get("mm10_formj", 0), self.it.calls.get("mm10_formj11", 0)
+        for e0 in range(0, self.npts, self.mx):
+            span = min(self.mx, self.npts - e0)
+            P[e0:e0 + span], K[e0:e0 + span] = self._sweep_block(step, iter_, Fn[e0:e0 + span], Fn1[e0:e0 + span], e0, span)
+        nj, nj11 = self.it.calls.get("mm10_formj", 0) - nj0, self.it.calls.get("mm10_formj11", 0) - nj110
+        self.sweeps.append((int(step), int(iter_), nj11 - nj, nj))
+        return P, K
+
+    def _sweep_block(self, step, iter_, Fn, Fn1, e0, span):
+        it, lw, lw1, mx = self.it, self.lw, self.lw1, self.mx
+        lw.step, lw.iter, lw.material_cut_step, lw.span, lw.felem = int(step), int(iter_), False, span, e0 + 1
+        lw.fn[...] = 0.0; lw.fn1[...] = 0.0
+        lw.fn[:span] = Fn.reshape(span, 3, 3)                            # Fn(e, 1..9) = F11, F12, F13, F21, ... (drive_eps_sig.f:190-214)
+        lw.fn1[:span] = Fn1.reshape(span, 3, 3)
+        lw.urcs_blk_n[...] = 0.0; lw.urcs_blk_n[:span, :, 0] = self.urcs_n[e0:e0 + span]
         fnh, dfn, rnh, fnhinv, fn1inv = (Z(mx, 3, 3) for _ in range(5))
         fnh[:span] = 0.5 * (lw.fn[:span] + lw.fn1[:span]); dfn[...] = lw.fn1 - lw.fn
         it.call("rtcmp1", span, fnh, rnh); it.call("rtcmp1", span, lw.fn1, lw.rot_blk_n1)
@@ -249,49 +267,51 @@ class Harness:
         qnhalf, qtn1 = Z(mx, 6, 6), Z(mx, 6, 6)
         it.call("getrm1", span, qnhalf, rnh, 1)
         it.call("qmply1", span, mx, 6, qnhalf, ddt, uddt)
-        self.hist_n1[...] = 0.0
         lw.urcs_blk_n1[...] = 0.0
-        nj0, nj110 = it.calls.get("mm10_formj", 0), it.calls.get("mm10_formj11", 0)
         if self.mm01 is not None:          # drive_01_update (rstgp1.f:330-450): total strain, mm01, cnst1, [D] kept as its upper triangle
             m1 = self.m1
-            self.eps_n1[...] = self.eps_n + uddt[:span]                  # rstgp1_update_strains
+            blk = lambda a: np.concatenate([a[e0:e0 + span], np.zeros(mx - span)])
+            e_, nu_, beta_, h_, yld_ = blk(m1.e), blk(m1.nu), blk(m1.beta), blk(m1.h), blk(m1.yld)
+            self.eps_n1[e0:e0 + span] = self.eps_n[e0:e0 + span] + uddt[:span]        # rstgp1_update_strains
             cgn1, rtse, cep = Z(mx, 9), Z(mx, 6), Z(mx, 6, 6)
-            it.call("mm01", span, 1, 1, int(step), int(iter_), m1.e, m1.nu, m1.beta, m1.h, np.zeros(mx), m1.yld, lw.urcs_blk_n, cgn1, uddt, self.hist_n,
-                    self.hist_n1, rtse, np.zeros(mx), m1.e, m1.nu, 6)
+            hn, h1 = np.asfortranarray(self.hist_n[e0:e0 + span]), Z(span, 11)
+            it.call("mm01", span, e0 + 1, 1, int(step), int(iter_), e_, nu_, beta_, h_, np.zeros(mx), yld_, lw.urcs_blk_n, cgn1, uddt, hn, h1, rtse,
+                    np.zeros(mx), e_, nu_, 6)
             lw.urcs_blk_n1[:, :, 0] = cgn1
-            h1 = self.hist_n1
-            it.call("cnst1", span, cep, rtse, m1.nu, m1.e, np.asfortranarray(h1[:, 1].copy()), np.asfortranarray(h1[:, 4].copy()), m1.beta,
-                    np.asfortranarray(h1[:, 0].copy()), np.asfortranarray(h1[:, 3].copy()), 1, 6)
+            self.hist_n1[e0:e0 + span] = h1
+            self.hist_n[e0:e0 + span] = hn                               # step 1 initialises the n history in place (mm01_set_history)
+            it.call("cnst1", span, cep, rtse, nu_, e_, np.asfortranarray(h1[:, 1].copy()), np.asfortranarray(h1[:, 4].copy()), beta_,
+                    np.asfortranarray(h1[:, 0].copy()), np.asfortranarray(h1[:, 3].copy()), e0 + 1, 6)
             for i in range(span):                                         # rstgp1_store_cep keeps 21 terms, drive_01_cnst mirrors them
                 cep[i] = np.triu(cep[i]) + np.triu(cep[i], 1).T
             self.cep_mm01 = cep
-        for e in range(span if self.mm01 is None else 0):              # one-point blocks: mm10 addresses the history through history(iloop, 1) with an assumed-size dummy,
-            lw1.step, lw1.iter, lw1.felem, lw1.material_cut_step = lw.step, lw.iter, e + 1, False      # which for span > 1 runs past whole columns
-            lw1.c_props[0, :] = self.c_props[e, :]
+        for e in range(span if self.mm01 is None else 0):              # one-point blocks: mm10 addresses the history through history(iloop, 1)
+            g = e0 + e                                                   # with an assumed-size dummy, which for span > 1 runs past whole columns
+            lw1.step, lw1.iter, lw1.felem, lw1.material_cut_step = lw.step, lw.iter, g + 1, False
+            lw1.c_props[0, :] = self.c_props[g, :]
             lw1.rot_blk_n1[0] = lw.rot_blk_n1[e]; lw1.urcs_blk_n[0] = lw.urcs_blk_n[e]; lw1.urcs_blk_n1[...] = 0.0
-            self.u1[0] = uddt[e]; self.h_n[0] = self.hist_n[e]; self.h_n1[...] = 0.0
+            self.u1[0] = uddt[e]; self.h_n[0] = self.hist_n[g]; self.h_n1[...] = 0.0
             it.call("mm10", 1, 1, self.ncrystals, self.hist_sz, self.h_n, self.h_n1, lw1, self.u1, np.full(mx, 297.0), np.zeros(mx), 6, False, False,
                     Z(mx, 1), 1, int(iter_) == 0)                        # rstgp1.f:862-880: iteration 0 is always the linear-elastic estimate
             lw.material_cut_step = lw.material_cut_step or lw1.material_cut_step
-            self.hist_n1[e] = self.h_n1[0]; lw.urcs_blk_n1[e] = lw1.urcs_blk_n1[0]
+            self.hist_n1[g] = self.h_n1[0]; lw.urcs_blk_n1[e] = lw1.urcs_blk_n1[0]
             if step == 1:
-                self.hist_n[e] = self.h_n[0]                             # step 1 initialises the n history in place (mm10_a.f:73-78, 237-244)
+                self.hist_n[g] = self.h_n[0]                             # step 1 initialises the n history in place (mm10_a.f:73-78, 237-244)
         if lw.material_cut_step:
             raise RuntimeError("material_cut_step")
+        self.urcs_n1[e0:e0 + span] = lw.urcs_blk_n1[:span, :, 0]
         it.call("getrm1", span, qtn1, lw.rot_blk_n1, 2)
         it.call("qmply1", span, mx, 6, qtn1, lw.urcs_blk_n1, cs)
         it.call("inv33", span, 1, lw.fn1, fn1inv, detF)
         P_blk, A_blk, cep = Z(mx, 9), Z(mx, 81), Z(mx, 6, 6)
         it.call("cs2p", span, 1, cs, fn1inv, detF, P_blk)
         for i in range(span):                                             # drive_10_cnst, gptns1.f:562-567
-            cep[i] = self.hist_n1[i, 0:36].reshape(6, 6, order="F") if self.mm01 is None else self.cep_mm01[i]
+            cep[i] = self.hist_n1[e0 + i, 0:36].reshape(6, 6, order="F") if self.mm01 is None else self.cep_mm01[i]
         it.call("cep2a", lw, cep, rnh, detF, detFh, fnhinv, fn1inv, A_blk)
-        nj, nj11 = it.calls.get("mm10_formj", 0) - nj0, it.calls.get("mm10_formj11", 0) - nj110
-        self.sweeps.append((int(step), int(iter_), nj11 - nj, nj))
         return P_blk[:span].copy(), A_blk[:span].copy()
 
     def update(self):
-        self.hist_n[...] = self.hist_n1; self.lw.urcs_blk_n[...] = self.lw.urcs_blk_n1            # update.f:85-93
+        self.hist_n[...] = self.hist_n1; self.urcs_n[...] = self.urcs_n1            # update.f:85-93
         if self.mm01 is not None:
             self.eps_n[...] = self.eps_n1
 
@@ -318,7 +338,7 @@ def wrapper_cases(out):
             P, K = H.sweep(step, 1, Fa, Fb)
             rec[f"P{step}"], rec[f"K4_{step}"] = P, K
             rec[f"hist{step}"] = np.ascontiguousarray(H.hist_n1).copy()
-            rec[f"urcs{step}"] = np.ascontiguousarray(H.lw.urcs_blk_n1[:npts, :, 0]).copy()
+            rec[f"urcs{step}"] = H.urcs_n1.copy()
             rec[f"iters{step}"] = np.array(H.sweeps[-1][2:])
             H.update()
         for k, v in rec.items():
@@ -327,15 +347,15 @@ def wrapper_cases(out):
     out["mts_names"] = np.array(sorted(MTS)); out["mts_params"] = np.array([MTS[k] for k in sorted(MTS)])
 
 
-def run_job(out, prefix, N, nstep, FP_max, isNBC, make_harness, t_start):
+def run_job(out, prefix, N, nstep, FP_max, isNBC, make_harness, t_start, mults=None, maxiter=10):
     """FFT_init's state (FFT_init.f:141-172), the initial sweep and FFT_nr3 (FFT_finite_3d.f:145-146) for one job; results
     under `prefix` in `out`"""
     N3 = N ** 3
     fft = dict(n=N, nhalf=(N + 1) // 2, n3=N3, ndim1=3, ndim2=9, veclen=9 * N3, dims=np.array([N, N, N]), ghat4=Z(N3, 81), k4=Z(N3, 81),
                coeffs1=Z(N, N, N), coeffs2=Z(N, N, N), real1=Z(N3, 9), real2=Z(N3, 9), real3=Z(N3, 9), b=Z(N3, 9), fn=Z(N3, 9), fn1=Z(N3, 9),
                pn=Z(N3, 9), pn1=Z(N3, 9), dfm=Z(N3, 9), tmppcg=Z(9 * N3, 4), isnbc=np.asarray(isNBC, dtype=bool), bc_all=Z(9, nstep),
-               straininc=0.0, tolpcg=1.0e-10, tolnr=1.0e-5, maxiter=10, nstep=nstep, out_step=np.zeros(nstep, dtype=bool))
-    mults = np.ones(nstep)
+               straininc=0.0, tolpcg=1.0e-10, tolnr=1.0e-5, maxiter=maxiter, nstep=nstep, out_step=np.zeros(nstep, dtype=bool))
+    mults = np.ones(nstep) if mults is None else np.asarray(mults, dtype=np.float64)[:nstep]
     bc = np.cumsum(np.outer(mults, FP_max), axis=0)           # inlod.f:57-63
     for d in (0, 4, 8):
         if not fft["isnbc"][d]:
@@ -354,7 +374,7 @@ def run_job(out, prefix, N, nstep, FP_max, isNBC, make_harness, t_start):
     def update():
         H.update()
         log["steps"].append(dict(Fn1=np.ascontiguousarray(fft["fn1"]).copy(), Pn1=np.ascontiguousarray(fft["pn1"]).copy(),
-                                 hist=np.ascontiguousarray(H.hist_n1).copy(), urcs=np.ascontiguousarray(H.lw.urcs_blk_n1[:N3, :, 0]).copy(),
+                                 hist=np.ascontiguousarray(H.hist_n1).copy(), urcs=H.urcs_n1.copy(),
                                  n_sweeps=len(H.sweeps), n_cg=len(log["cg"]), n_tangent_homo=it.calls.get("tangent_homo", 0)))
     st, dcg_init, dcg_check, dcg, dcg_get = mkl_rci_cg()
 
@@ -413,6 +433,21 @@ def main():
     run_job(out, "m01_", N, nstep, FP_max, np.zeros(9, dtype=bool), lambda fft: Harness(N3, None, extra_module_vars=fft, mm01=m01_single), t_start)
     for k, v in m01.items():
         out["m01_prop_" + k] = np.asarray(v, dtype=np.float64)
+
+    # ---- job 3: the reference's shipped deck examples/test_mm10.in as it stands (7^3, bcc48, Voce with alter_mode on, orientations
+    #      from angle_bc.in, F_xx 0.03 / F_yy = F_zz -0.01 in ten steps, time step 10): its first load steps.  The deck is read by
+    #      this repository's reader (cpfft_b200/deck.py); everything from the crystal properties on is the reference's text.
+    nd = int(os.environ.get("GLOBAL_DECK_STEPS", "10"))
+    if nd > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import deck
+        pd = deck("test_mm10.in")
+        cd = pd.crystals[0]
+        prm = dict(rate_n=cd.harden_n, theta_0=cd.theta_0, tau_y=cd.tau_y, tau_v=cd.tau_v, voche_m=cd.voche_m, iD_v=cd.iD_v, e=cd.e, nu=cd.nu,
+                   alter_mode=bool(cd.alter_mode), eps_dot_0_y=cd.eps_dot_0_y)
+        run_job(out, "deck_", pd.N, nd, np.asarray(pd.FP_max, dtype=np.float64), np.asarray(pd.isNBC, dtype=bool),
+                lambda fft: Harness(pd.N3, np.asarray(pd.angles), slip_type=cd.slip_type, extra_module_vars=fft, prm=prm, dt=pd.tstep), t_start,
+                mults=pd.mults, maxiter=pd.maxIter)
 
     h = hashlib.sha256()
     for f in FILES:
