@@ -406,41 +406,52 @@ def run_job(out, prefix, N, nstep, FP_max, isNBC, make_harness, t_start, mults=N
 
 
 def main():
+    """GLOBAL_ONLY=<comma list of wrap, job1, m01, deck, deck01>: regenerate only those parts and keep the rest of the existing fixture"""
     t_start = time.time()
     N, nstep = 3, int(os.environ.get("GLOBAL_NSTEP", "3"))
     N3 = N ** 3
-    rng = np.random.default_rng(20240609)
+    path = os.path.join(ROOT, "tests", "golden", "reference_global.npz")
+    only = [x for x in os.environ.get("GLOBAL_ONLY", "").split(",") if x]
+    want = lambda name: not only or name in only
     out = {}
-    wrapper_cases(out)
+    if only:
+        old = np.load(path)
+        out.update({k: old[k] for k in old.files})
+    if want("wrap"):
+        wrapper_cases(out)
 
     # ---- job 1: one fcc crystal per voxel, Voce hardening, its own orientation; uniaxial tension along x under mixed boundary
     #      conditions: F_xx prescribed, P_yy = P_zz = 0, no mean shear
-    angles = rng.uniform(0.0, 360.0, (N3, 3))
-    FP_max = np.zeros(9); FP_max[0] = 0.002
-    isNBC = np.zeros(9, dtype=bool); isNBC[[4, 8]] = True
-    run_job(out, "", N, nstep, FP_max, isNBC, lambda fft: Harness(N3, angles, extra_module_vars=fft), t_start)
-    out.update(angles=angles, params=np.array([PRM[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]))
+    if want("job1"):
+        rng = np.random.default_rng(20240609)
+        angles = rng.uniform(0.0, 360.0, (N3, 3))
+        FP_max = np.zeros(9); FP_max[0] = 0.002
+        isNBC = np.zeros(9, dtype=bool); isNBC[[4, 8]] = True
+        run_job(out, "", N, nstep, FP_max, isNBC, lambda fft: Harness(N3, angles, extra_module_vars=fft), t_start)
+        out.update(angles=angles, params=np.array([PRM[q] for q in ("rate_n", "theta_0", "tau_y", "tau_v", "voche_m", "iD_v", "e", "nu")]))
 
     # ---- job 2: mm01 (bilinear Mises plasticity), the two materials of the shipped deck examples/test_mm01.in scattered over the
     #      grid with kinematic / mixed / isotropic hardening per voxel, strain-controlled (all nine mean components prescribed):
     #      the deck's 3 % tension with lateral contraction per step plus a shear component
-    rng = np.random.default_rng(20240611)
-    incl = rng.random(N3) < 0.4
-    m01 = dict(e=np.where(incl, 24000.0, 12000.0), nu=np.full(N3, 0.3), yld=np.where(incl, 200.0, 100.0), tan_e=np.full(N3, 1000.0),
-               beta=rng.choice([0.0, 0.5, 1.0], N3))
-    m01_single = {k: np.asarray(v, dtype=np.float32).astype(np.float64) for k, v in m01.items()}      # matprp is single precision (mod_fft.f:20)
-    FP_max = np.array([0.03, 0.005, 0.0, 0.0, -0.01, 0.0, 0.0, 0.0, -0.01])
-    run_job(out, "m01_", N, nstep, FP_max, np.zeros(9, dtype=bool), lambda fft: Harness(N3, None, extra_module_vars=fft, mm01=m01_single), t_start)
-    for k, v in m01.items():
-        out["m01_prop_" + k] = np.asarray(v, dtype=np.float64)
+    single = lambda d: {k: np.asarray(v, dtype=np.float32).astype(np.float64) for k, v in d.items()}      # matprp is single precision (mod_fft.f:20)
+    if want("m01"):
+        rng = np.random.default_rng(20240611)
+        incl = rng.random(N3) < 0.4
+        m01 = dict(e=np.where(incl, 24000.0, 12000.0), nu=np.full(N3, 0.3), yld=np.where(incl, 200.0, 100.0), tan_e=np.full(N3, 1000.0),
+                   beta=rng.choice([0.0, 0.5, 1.0], N3))
+        FP_max = np.array([0.03, 0.005, 0.0, 0.0, -0.01, 0.0, 0.0, 0.0, -0.01])
+        run_job(out, "m01_", N, nstep, FP_max, np.zeros(9, dtype=bool), lambda fft: Harness(N3, None, extra_module_vars=fft, mm01=single(m01)), t_start)
+        for k, v in m01.items():
+            out["m01_prop_" + k] = np.asarray(v, dtype=np.float64)
 
-    # ---- job 3: the reference's shipped deck examples/test_mm10.in as it stands (7^3, bcc48, Voce with alter_mode on, orientations
-    #      from angle_bc.in, F_xx 0.03 / F_yy = F_zz -0.01 in ten steps, time step 10): its first load steps.  The deck is read by
-    #      this repository's reader (cpfft_b200/deck.py); everything from the crystal properties on is the reference's text.
+    # ---- jobs 3, 4: the reference's shipped decks examples/test_mm10.in (7^3, bcc48, Voce with alter_mode on, orientations from
+    #      angle_bc.in, F_xx 0.03 / F_yy = F_zz -0.01 in ten steps, time step 10) and examples/test_mm01.in (7^3, two bilinear materials,
+    #      F_xx 0.3 / F_yy = F_zz -0.1 in ten steps) as they stand, all load steps.  The decks are read by this repository's reader
+    #      (cpfft_b200/deck.py); everything from the material properties on is the reference's text.
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import deck
     nd = int(os.environ.get("GLOBAL_DECK_STEPS", "10"))
-    if nd > 0:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from helpers import deck
+    if want("deck") and nd > 0:
         pd = deck("test_mm10.in")
         cd = pd.crystals[0]
         prm = dict(rate_n=cd.harden_n, theta_0=cd.theta_0, tau_y=cd.tau_y, tau_v=cd.tau_v, voche_m=cd.voche_m, iD_v=cd.iD_v, e=cd.e, nu=cd.nu,
@@ -448,13 +459,36 @@ def main():
         run_job(out, "deck_", pd.N, nd, np.asarray(pd.FP_max, dtype=np.float64), np.asarray(pd.isNBC, dtype=bool),
                 lambda fft: Harness(pd.N3, np.asarray(pd.angles), slip_type=cd.slip_type, extra_module_vars=fft, prm=prm, dt=pd.tstep), t_start,
                 mults=pd.mults, maxiter=pd.maxIter)
+    if want("deck01") and nd > 0:
+        pd1 = deck("test_mm01.in")
+        mat = [pd1.materials[m - 1] for m in pd1.matlist]
+        d01 = dict(e=[m.e for m in mat], nu=[m.nu for m in mat], yld=[m.yld_pt for m in mat], tan_e=[m.tan_e for m in mat], beta=[m.beta for m in mat])
+        run_job(out, "deck01_", pd1.N, nd, np.asarray(pd1.FP_max, dtype=np.float64), np.asarray(pd1.isNBC, dtype=bool),
+                lambda fft: Harness(pd1.N3, None, extra_module_vars=fft, mm01=single(d01), dt=pd1.tstep), t_start, mults=pd1.mults, maxiter=pd1.maxIter)
+
+    # ---- jobs 5, 6: the derived mixed decks of SURVEY.md 8d -- the shipped decks with F_xx driven and P_yy = P_zz = 0 (tests/helpers.py
+    #      stress_bc_variant): the outer loop on the mean stress with tangent_homo / NBC_update on the shipped materials
+    from helpers import stress_bc_variant
+    if want("deck01nbc") and nd > 0:
+        pn = stress_bc_variant(deck("test_mm01.in"))
+        mat = [pn.materials[m - 1] for m in pn.matlist]
+        d01 = dict(e=[m.e for m in mat], nu=[m.nu for m in mat], yld=[m.yld_pt for m in mat], tan_e=[m.tan_e for m in mat], beta=[m.beta for m in mat])
+        run_job(out, "deck01nbc_", pn.N, min(nd, 3), np.asarray(pn.FP_max, dtype=np.float64), np.asarray(pn.isNBC, dtype=bool),
+                lambda fft: Harness(pn.N3, None, extra_module_vars=fft, mm01=single(d01), dt=pn.tstep), t_start, mults=pn.mults, maxiter=pn.maxIter)
+    if want("deck10nbc") and nd > 0:
+        pn = stress_bc_variant(deck("test_mm10.in"))
+        cd = pn.crystals[0]
+        prm = dict(rate_n=cd.harden_n, theta_0=cd.theta_0, tau_y=cd.tau_y, tau_v=cd.tau_v, voche_m=cd.voche_m, iD_v=cd.iD_v, e=cd.e, nu=cd.nu,
+                   alter_mode=bool(cd.alter_mode), eps_dot_0_y=cd.eps_dot_0_y)
+        run_job(out, "deck10nbc_", pn.N, min(nd, 2), np.asarray(pn.FP_max, dtype=np.float64), np.asarray(pn.isNBC, dtype=bool),
+                lambda fft: Harness(pn.N3, np.asarray(pn.angles), slip_type=cd.slip_type, extra_module_vars=fft, prm=prm, dt=pn.tstep), t_start,
+                mults=pn.mults, maxiter=pn.maxIter)
 
     h = hashlib.sha256()
     for f in FILES:
         h.update(open(REF + f, "rb").read())
     out["provenance"] = ("maranGit/CPFFT src/{" + ", ".join(FILES) + "} executed by tools/fortran_subset.py (tools/make_reference_global.py); sha256 of the sources "
                          + h.hexdigest() + "; interpreter sha256 " + hashlib.sha256(open(os.path.join(ROOT, "tools", "fortran_subset.py"), "rb").read()).hexdigest())
-    path = os.path.join(ROOT, "tests", "golden", "reference_global.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, f"{time.time() - t_start:.0f} s", {k: np.shape(v) for k, v in out.items()})
 
