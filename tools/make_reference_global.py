@@ -4,9 +4,10 @@ loop, fftPcg, tangent_homo, NBC_update, the operator G_K_dF and -- inside the Py
 the crystal-plasticity wrapper mm10 with everything below it, executed statement by statement by the Fortran-subset
 interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/golden/reference_global.npz.
 
-    python tools/make_reference_global.py            # needs /root/reference (this container); about twelve minutes (GLOBAL_DECK_STEPS=0: two)
+    python tools/make_reference_global.py            # needs /root/reference (this container); about twenty minutes (GLOBAL_DECK_STEPS=0: two; GLOBAL_ONLY=<jobs> regenerates single jobs)
 
-A third job (`deck_*`) is the reference's shipped deck examples/test_mm10.in, all ten load steps (7^3, bcc48, three blocks).
+Further jobs are the reference's shipped decks as they stand, all ten load steps (`deck_*`: examples/test_mm10.in, 7^3, bcc48, three
+blocks; `deck01_*`: examples/test_mm01.in), and their derived mixed variants with P_yy = P_zz = 0 (`deck01nbc_*`, `deck10nbc_*`).
 A second job (`m01_*`) is strain-controlled with mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450) as the
 material.  A further set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
 point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
