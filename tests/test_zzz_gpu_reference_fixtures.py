@@ -196,3 +196,50 @@ def job_sweep(Solver, job, k):
 @pytest.mark.parametrize("job,k", [("", 1), ("", 2), ("", 3), ("m01_", 1), ("m01_", 2), ("m01_", 3)])
 def test_job_sweeps_through_the_c_abi(solver, job, k):
     job_sweep(solver, job, k)
+
+
+def deck_sweep(Solver, deck_name, job, k):
+    """the closing sweep of load step k of a shipped deck as the reference ran it (all 343 points at once, the deck's own grid):
+    examples/test_mm10.in exercises bcc48 with alter_mode on, examples/test_mm01.in the bilinear Mises update at 3 % strain per step"""
+    from helpers import deck, mm10_layout
+    import test_reference_global as G
+    V = G.V
+    p = deck(deck_name)
+    n = p.N3
+    F1, H1, U1, P1 = V[job + "step_Fn1"][k - 1], V[job + "step_hist"][k - 1], V[job + "step_urcs"][k - 1], V[job + "step_Pn1"][k - 1]
+    Fn = np.tile(np.eye(3).reshape(9), (n, 1)) if k == 1 else V[job + "step_Fn1"][k - 2]
+    last = [r for r in V[job + "sweeps"] if r[0] == k][-1]
+    H = int(V[job + "hist_size"])
+    s = Solver(p)
+    assert s.H == H
+    s.drive_eps_sig(1, 0)
+    s.upload("FN", Fn.T); s.upload("FN1", F1.T)
+    if k > 1:
+        s.upload("HIST_N", V[job + "step_hist"][k - 2].T)
+        s.upload("URCS_N", V[job + "step_urcs"][k - 2].T)
+    s.drive_eps_sig(k, int(last[1]))
+    hk = s.download("HIST_N1", 1)[:, :H]
+    ur = s.download("URCS_N1", 1)
+    assert rel(s.download("PN1").T, P1) <= 2e-8
+    assert rel(ur[:, :6], U1[:, :6]) <= 2e-8
+    if job == "deck_":
+        L = mm10_layout(48)
+        for key, tol in (("cep", 2e-8), ("stress", 2e-8), ("tau_tilde", 1e-9), ("slipinc", 5e-8)):
+            a, b = hk[:, L[key][0]:L[key][1]], H1[:, L[key][0]:L[key][1]]
+            assert rel(a, b) <= tol, (key, rel(a, b))
+        a, b = hk[:, L["Rp"][0]:L["Rp"][1]], H1[:, L["Rp"][0]:L["Rp"][1]]
+        assert np.abs(a - b).max() <= 1e-9
+        it = s.local_iters()
+        got = (int(it[:, 0].sum()), int(it[:, 1].sum()))
+        assert abs(got[0] - int(last[2])) <= slack(last[2]) and abs(got[1] - int(last[3])) <= slack(last[3]), (got, last)
+    else:
+        mask = np.ones(11, dtype=bool); mask[3] = False
+        assert rel(hk[:, mask], H1[:, mask]) <= 1e-10
+        word = lambda a: np.ascontiguousarray(a[:, 3]).view(np.int64)
+        assert np.array_equal(word(hk), word(H1))
+
+
+@pytest.mark.parametrize("deck_name,job,k", [("test_mm10.in", "deck_", 1), ("test_mm10.in", "deck_", 3), ("test_mm10.in", "deck_", 10),
+                                             ("test_mm01.in", "deck01_", 1), ("test_mm01.in", "deck01_", 10)])
+def test_shipped_deck_sweeps_through_the_c_abi(solver, deck_name, job, k):
+    deck_sweep(solver, deck_name, job, k)
