@@ -7,7 +7,7 @@ interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/g
     python tools/make_reference_global.py            # needs /root/reference (this container); about twenty minutes (GLOBAL_DECK_STEPS=0: two; GLOBAL_ONLY=<jobs> regenerates single jobs)
 
 Further jobs are the reference's shipped decks as they stand, all ten load steps (`deck_*`: examples/test_mm10.in, 7^3, bcc48, three
-blocks; `deck01_*`: examples/test_mm01.in), and their derived mixed variants with P_yy = P_zz = 0 (`deck01nbc_*`, `deck10nbc_*`).
+blocks; `deck01_*`: examples/test_mm01.in), their derived mixed variants with P_yy = P_zz = 0 (`deck01nbc_*`, `deck10nbc_*`), and the derived MTS deck (`deckmts_*`).
 A second job (`m01_*`) is strain-controlled with mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450) as the
 material.  A further set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
 point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
@@ -208,7 +208,7 @@ class Harness:
                                 tang_calc=0, s_type=slip_type, cnum=1, st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max),
                                 qs=Z(3, ms_max), ns=Z(3, ms_max), init_elast_stiff=np.asfortranarray(RE @ Cc @ RE.T), init_angles=angles[e, c].copy())
                 if mts:
-                    for k_, v_ in MTS.items():
+                    for k_, v_ in (mts if isinstance(mts, dict) else MTS).items():
                         setattr(cp, MTS_FIELD.get(k_, k_), v_)
                 for s_ in range(nslip):
                     bs, ns_ = trot @ bvec[s_], trot @ nvec[s_]
@@ -484,6 +484,18 @@ def main():
         run_job(out, "deck10nbc_", pn.N, min(nd, 2), np.asarray(pn.FP_max, dtype=np.float64), np.asarray(pn.isNBC, dtype=bool),
                 lambda fft: Harness(pn.N3, np.asarray(pn.angles), slip_type=cd.slip_type, extra_module_vars=fft, prm=prm, dt=pn.tstep), t_start,
                 mults=pn.mults, maxiter=pn.maxIter)
+
+    # ---- job 7: the derived MTS deck tests/golden/decks/mts_mm10.in (5^3 fcc polycrystal, MTS hardening, 0.1 % strain per step,
+    #      four steps): the mechanical-threshold-stress law through the whole loop
+    if want("deckmts") and nd > 0:
+        pm = deck("mts_mm10.in")
+        cm = pm.crystals[0]
+        prm = dict(rate_n=cm.harden_n, theta_0=cm.theta_0, tau_y=cm.tau_y, tau_v=cm.tau_v, voche_m=cm.voche_m, iD_v=cm.iD_v, e=cm.e, nu=cm.nu,
+                   alter_mode=bool(cm.alter_mode), eps_dot_0_y=cm.eps_dot_0_y)
+        mts = {k: getattr(cm, k) for k in MTS}
+        run_job(out, "deckmts_", pm.N, min(nd, pm.nstep), np.asarray(pm.FP_max, dtype=np.float64), np.asarray(pm.isNBC, dtype=bool),
+                lambda fft: Harness(pm.N3, np.asarray(pm.angles), slip_type=cm.slip_type, mts=mts, extra_module_vars=fft, prm=prm, dt=pm.tstep), t_start,
+                mults=pm.mults, maxiter=pm.maxIter)
 
     h = hashlib.sha256()
     for f in FILES:
