@@ -278,7 +278,7 @@ def test_shipped_deck_run_by_the_reference_source(oracle_built, deck_name, job, 
         ref_cg.append([int(x) for x in cg[lo:bounds[s + 1], 1]])
         ref_sweeps.append(sweeps[s + 1] - sweeps[s] - (1 if s == 0 else 0))
     assert int(V[job + "step_n_tangent_homo"][-1]) == 1           # strain-controlled: no outer loop
-    o = Oracle(p, threads=0)
+    o = Oracle(p, threads=1)
     o.drive_eps_sig(1, 0)
     res = o.FFT_nr3(nd)
     assert res["rc"] == 0
@@ -309,7 +309,7 @@ def test_derived_stress_bc_deck_run_by_the_reference_source(oracle_built, deck_n
     ref_cg, ref_sweeps, ref_outer = reference_iterations(job)
     assert sum(ref_outer) > 0                                      # the outer loop iterated
     p = stress_bc_variant(deck(deck_name))
-    o = Oracle(p, threads=0)
+    o = Oracle(p, threads=1)
     o.drive_eps_sig(1, 0)
     res = o.FFT_nr3(nd)
     assert res["rc"] == 0
