@@ -7,7 +7,7 @@ interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/g
     python tools/make_reference_global.py            # needs /root/reference (this container); about twenty minutes (GLOBAL_DECK_STEPS=0: two; GLOBAL_ONLY=<jobs> regenerates single jobs)
 
 Further jobs are the reference's shipped decks as they stand, all ten load steps (`deck_*`: examples/test_mm10.in, 7^3, bcc48, three
-blocks; `deck01_*`: examples/test_mm01.in), their derived mixed variants with P_yy = P_zz = 0 (`deck01nbc_*`, `deck10nbc_*`), and the derived MTS deck (`deckmts_*`).
+blocks; `deck01_*`: examples/test_mm01.in), their derived mixed variants with P_yy = P_zz = 0 (`deck01nbc_*`, `deck10nbc_*`), and the derived MTS and Taylor (two crystal types per point) decks (`deckmts_*`, `decktaylor_*`).
 A second job (`m01_*`) is strain-controlled with mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450) as the
 material.  A further set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
 point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
@@ -126,7 +126,9 @@ class Harness:
     (drive_eps_sig.f:203-300), with its own interpreter because the history layout is module data.  slip_type 1 (fcc, 12
     systems) or 8 (bcc48, which selects the maximum-size layout, mm10_d.f:136-141)."""
 
-    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES, mm01=None, prm=None, dt=1.0):
+    def __init__(self, npts, angles, slip_type=1, mts=False, extra_module_vars=None, files=FILES, mm01=None, prm=None, dt=1.0, types=None, ids=None):
+        """types / ids: several crystal types (list of dict(slip_type=, prm=)) and the 1-based type of every crystal of every point
+        (`crystal_input file`); otherwise one type (slip_type, prm, mts) for all"""
         self.npts, self.slip_type, self.mts, self.mm01 = npts, slip_type, mts, mm01
         PRM = {**globals()["PRM"], "alter_mode": False, "eps_dot_0_y": 1.0e10, **(prm or {})}
         if angles is None:
@@ -142,8 +144,10 @@ class Harness:
         angles = np.asarray(angles, dtype=np.float64).reshape(npts, -1, 3)
         self.ncry = ncry = angles.shape[1]
         from oracle import Oracle
-        bvec, nvec = Oracle.slip_table(slip_type)
-        nslip = self.nslip = len(bvec)
+        if types is None:
+            types, ids = [dict(slip_type=slip_type, prm=prm)], np.ones((npts, ncry), dtype=np.int64)
+        tables = [Oracle.slip_table(t["slip_type"]) for t in types]
+        nslip = self.nslip = max(len(t[0]) for t in tables)
 
         # module mm10_defs: the history layout, computed by the reference's own mm10_set_history_locs (mm10_d.f:25-331) from the
         # material / crystal tables a deck with one crystal-plasticity material of `ncry` crystals per point leaves behind
@@ -153,15 +157,17 @@ class Harness:
                          num_crystal_terms=0, one_crystal_hist_size=0, common_hist_size=0, asymmetric_assembly=False)
         matprp = np.zeros((300, 500), order="F"); matprp[8, 0] = 10                      # matprp(9, 1): material model 10
         imatprp = np.zeros((300, 500), dtype=np.int64, order="F")
-        imatprp[100, 0], imatprp[103, 0], imatprp[104, 0] = ncry, 1, 1                     # imatprp(101 / 104 / 105, 1): crystals per point, one crystal type, its number
-        c_array = np.empty(mcr, dtype=object); c_array[0] = NS(nslip=nslip, num_hard=1)
-        tables = dict(matprp=matprp, imatprp=imatprp, matlist=np.ones(npts, dtype=np.int64), c_array=c_array,
-                      crystal_input=np.zeros((1, 1), dtype=np.int64), data_offset=np.zeros(npts, dtype=np.int64))
+        imatprp[100, 0], imatprp[103, 0], imatprp[104, 0] = ncry, (1 if len(types) == 1 else 2), 1   # imatprp(101 / 104 / 105, 1): crystals per point,
+        c_array = np.empty(mcr, dtype=object)                                                        # crystal type single / from file, its number
+        for k_, tb in enumerate(tables):
+            c_array[k_] = NS(nslip=len(tb[0]), num_hard=1)
+        tables_mod = dict(matprp=matprp, imatprp=imatprp, matlist=np.ones(npts, dtype=np.int64), c_array=c_array,
+                          crystal_input=np.asfortranarray(np.asarray(ids, dtype=np.int64)), data_offset=np.arange(1, npts + 1, dtype=np.int64))
         it.consts.update(nummat=1, noelem=npts)
-        it.module_vars.update(mm10_defs); it.module_vars.update(tables)
+        it.module_vars.update(mm10_defs); it.module_vars.update(tables_mod)
         it.load(open(REF + "mm10_d.f").read())
         it.call("mm10_set_history_locs")
-        for k_ in tables:
+        for k_ in tables_mod:
             del it.module_vars[k_]
         ic, lcr = it.module_vars["indexes_common"], it.module_vars["length_crys_hist"]
         self.hist_sz = hist_sz = int(ic[4, 1] + ncry * it.module_vars["one_crystal_hist_size"])
@@ -190,13 +196,19 @@ class Harness:
 
         # crystal_properties the way setup_mm10_rknstr fills it (drive_eps_sig.f:571-606, 975-986) with the reference's own
         # mm10_rotation_matrix, mm10_RT2RVE, mm10_ET2EV, mm10_WT2WV; every parameter the deck does not set is zero
-        e_mod, nu = PRM["e"], PRM["nu"]
-        Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
-        Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
-        Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
+        base_prm = PRM
         self.c_props = c_props = np.empty((npts, ncry), dtype=object)
         for e in range(npts):
             for c in range(ncry):
+                ty = types[int(ids[e][c]) - 1]
+                PRM = {**base_prm, **(ty.get("prm") or {})}
+                slip_type_c = ty["slip_type"]
+                bvec, nvec = tables[int(ids[e][c]) - 1]
+                nslip = len(bvec)
+                e_mod, nu = PRM["e"], PRM["nu"]
+                Sf = np.zeros((6, 6)); Sf[:3, :3] = -nu / e_mod
+                Sf[np.arange(3), np.arange(3)] = 1.0 / e_mod; Sf[np.arange(3, 6), np.arange(3, 6)] = 2.0 * (1.0 + nu) / e_mod
+                Cc = np.linalg.inv(Sf); Cc = 0.5 * (Cc + Cc.T)
                 g = Z(3, 3)
                 it.call("mm10_rotation_matrix", angles[e, c].copy(), "kocks", "degrees", g, 6)
                 trot = np.asfortranarray(g.T)
@@ -205,7 +217,7 @@ class Harness:
                 cp = Defaulting(raten=PRM["rate_n"], theta_o=PRM["theta_0"], tau_y=PRM["tau_y"], tau_v=PRM["tau_v"], voche_m=PRM["voche_m"], id_v=PRM["iD_v"],
                                 burgers=2.87e-7, eps_dot_o_y=PRM["eps_dot_0_y"], solver=True, strategy=True, gpall=False, gpp=0, method=0, miter=30, atol=1e-5,
                                 atol1=1e-5, rtol=5e-5, rtol1=1e-5, xtol=1e-4, xtol1=1e-4, alter_mode=bool(PRM["alter_mode"]), nslip=nslip, h_type=2 if mts else 1, num_hard=1,
-                                tang_calc=0, s_type=slip_type, cnum=1, st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max),
+                                tang_calc=0, s_type=slip_type_c, cnum=int(ids[e][c]), st_it=np.zeros(3, dtype=np.int64), rotation_g=np.asfortranarray(g), ms=Z(6, ms_max),
                                 qs=Z(3, ms_max), ns=Z(3, ms_max), init_elast_stiff=np.asfortranarray(RE @ Cc @ RE.T), init_angles=angles[e, c].copy())
                 if mts:
                     for k_, v_ in (mts if isinstance(mts, dict) else MTS).items():
@@ -496,6 +508,16 @@ def main():
         run_job(out, "deckmts_", pm.N, min(nd, pm.nstep), np.asarray(pm.FP_max, dtype=np.float64), np.asarray(pm.isNBC, dtype=bool),
                 lambda fft: Harness(pm.N3, np.asarray(pm.angles), slip_type=cm.slip_type, mts=mts, extra_module_vars=fft, prm=prm, dt=pm.tstep), t_start,
                 mults=pm.mults, maxiter=pm.maxIter)
+
+    # ---- job 8: the derived Taylor deck tests/golden/decks/taylor_mm10.in (5^3, two crystals per material point -- bcc48 and fcc, crystal
+    #      numbers and orientations from a flat file --, Taylor average, five steps)
+    if want("decktaylor") and nd > 0:
+        pt = deck("taylor_mm10.in")
+        types = [dict(slip_type=c.slip_type, prm=dict(rate_n=c.harden_n, theta_0=c.theta_0, tau_y=c.tau_y, tau_v=c.tau_v, voche_m=c.voche_m, iD_v=c.iD_v,
+                                                      e=c.e, nu=c.nu, alter_mode=bool(c.alter_mode), eps_dot_0_y=c.eps_dot_0_y)) for c in pt.crystals]
+        run_job(out, "decktaylor_", pt.N, min(nd, pt.nstep), np.asarray(pt.FP_max, dtype=np.float64), np.asarray(pt.isNBC, dtype=bool),
+                lambda fft: Harness(pt.N3, np.asarray(pt.angles), extra_module_vars=fft, dt=pt.tstep, types=types, ids=np.asarray(pt.crystal_ids)), t_start,
+                mults=pt.mults, maxiter=pt.maxIter)
 
     h = hashlib.sha256()
     for f in FILES:
