@@ -98,7 +98,9 @@ def test_body_of_the_gpu_job_sweep_test(kernel_source_solver, job, k):
 
 
 @pytest.mark.parametrize("deck_name,job,k", [("test_mm10.in", "deck_", 1), ("test_mm10.in", "deck_", 3), ("test_mm10.in", "deck_", 10),
-                                             ("test_mm01.in", "deck01_", 1), ("test_mm01.in", "deck01_", 10)])
+                                             ("test_mm01.in", "deck01_", 1), ("test_mm01.in", "deck01_", 10),
+                                             ("mts_mm10.in", "deckmts_", 2), ("mts_mm10.in", "deckmts_", 4),
+                                             ("taylor_mm10.in", "decktaylor_", 2), ("taylor_mm10.in", "decktaylor_", 5)])
 def test_kernel_source_on_the_shipped_decks_as_the_reference_ran_them(kernel_source_solver, deck_name, job, k):
     """the body of tests/test_zzz_gpu_reference_fixtures.py::test_shipped_deck_sweeps_through_the_c_abi with the host build of the
     kernel source: the kernels' own text on the state the REFERENCE'S source passed through when it ran its shipped decks"""

@@ -222,7 +222,15 @@ def deck_sweep(Solver, deck_name, job, k):
     ur = s.download("URCS_N1", 1)
     assert rel(s.download("PN1").T, P1) <= 2e-8
     assert rel(ur[:, :6], U1[:, :6]) <= 2e-8
-    if job == "deck_":
+    if job in ("deckmts_", "decktaylor_"):                     # MTS hardening; two crystal types (bcc48 + fcc) per point
+        from helpers import compare_mm10_history
+        ncry = max(m.n_crystals for m in p.materials)
+        nslip = 48 if any(c.slip_type == 8 for c in p.crystals) else 12
+        assert compare_mm10_history(hk, H1, nslip, 5e-8, ncry)
+        it = s.local_iters()
+        got = (int(it[:, 0].sum()), int(it[:, 1].sum()))
+        assert abs(got[0] - int(last[2])) <= slack(last[2]) and abs(got[1] - int(last[3])) <= slack(last[3]), (got, last)
+    elif job == "deck_":
         L = mm10_layout(48)
         for key, tol in (("cep", 2e-8), ("stress", 2e-8), ("tau_tilde", 1e-9), ("slipinc", 5e-8)):
             a, b = hk[:, L[key][0]:L[key][1]], H1[:, L[key][0]:L[key][1]]
@@ -240,6 +248,8 @@ def deck_sweep(Solver, deck_name, job, k):
 
 
 @pytest.mark.parametrize("deck_name,job,k", [("test_mm10.in", "deck_", 1), ("test_mm10.in", "deck_", 3), ("test_mm10.in", "deck_", 10),
-                                             ("test_mm01.in", "deck01_", 1), ("test_mm01.in", "deck01_", 10)])
+                                             ("test_mm01.in", "deck01_", 1), ("test_mm01.in", "deck01_", 10),
+                                             ("mts_mm10.in", "deckmts_", 2), ("mts_mm10.in", "deckmts_", 4),
+                                             ("taylor_mm10.in", "decktaylor_", 2), ("taylor_mm10.in", "decktaylor_", 5)])
 def test_shipped_deck_sweeps_through_the_c_abi(solver, deck_name, job, k):
     deck_sweep(solver, deck_name, job, k)
