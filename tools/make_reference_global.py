@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""A whole (small) job run by the reference's OWN source: the global Newton loop FFT_nr3 with its stress-controlled outer
-loop, fftPcg, tangent_homo, NBC_update, the operator G_K_dF and -- inside the Python stand-in for the block driver --
-the crystal-plasticity wrapper mm10 with everything below it, executed statement by statement by the Fortran-subset
-interpreter tools/fortran_subset.py on a 3 x 3 x 3 polycrystal.  Output: tests/golden/reference_global.npz.
+"""Whole jobs run by the reference's OWN source: the global Newton loop FFT_nr3 with its stress-controlled outer loop, fftPcg,
+tangent_homo, NBC_update, the operator G_K_dF and -- inside the Python stand-in for the block driver -- the material routines
+(the crystal-plasticity wrapper mm10 with everything below it, or mm01 + cnst1), executed statement by statement by the
+Fortran-subset interpreter tools/fortran_subset.py.  Output: tests/golden/reference_global.npz.
 
-    python tools/make_reference_global.py            # needs /root/reference (this container); about twenty minutes (GLOBAL_DECK_STEPS=0: two; GLOBAL_ONLY=<jobs> regenerates single jobs)
+    python tools/make_reference_global.py     # needs /root/reference (this container); about twenty-five minutes
+    GLOBAL_ONLY=deck,deckmts python ...       # regenerate single jobs, keep the rest of the fixture; GLOBAL_DECK_STEPS=0: no deck jobs
 
-Further jobs are the reference's shipped decks as they stand, all ten load steps (`deck_*`: examples/test_mm10.in, 7^3, bcc48, three
-blocks; `deck01_*`: examples/test_mm01.in), their derived mixed variants with P_yy = P_zz = 0 (`deck01nbc_*`, `deck10nbc_*`), and the derived MTS and Taylor (two crystal types per point) decks (`deckmts_*`, `decktaylor_*`).
-A second job (`m01_*`) is strain-controlled with mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450) as the
-material.  A further set of cases (`wrap_*`) runs the same block-driver sequence and mm10 on polycrystalline points (three crystals per
-point, Taylor average), MTS hardening and the 48-system layout, two load steps each.
+Jobs (key prefix in the fixture):
+  ""            3^3 fcc polycrystal, Voce hardening, uniaxial tension under mixed boundary conditions (F_xx, P_yy = P_zz = 0), 3 steps
+  m01_          3^3, mm01 + cnst1 (mm01.f) in drive_01_update's sequence (rstgp1.f:330-450), strain-controlled, 3 steps
+  deck_         the shipped deck examples/test_mm10.in as it stands (7^3, bcc48, alter_mode on, three blocks), all ten load steps
+  deck01_       the shipped deck examples/test_mm01.in as it stands (7^3, two bilinear materials), all ten load steps
+  deck01nbc_, deck10nbc_   the shipped decks with F_xx driven and P_yy = P_zz = 0, 3 / 2 steps
+  deckmts_      tests/golden/decks/mts_mm10.in (5^3, MTS hardening), 4 steps
+  decktaylor_   tests/golden/decks/taylor_mm10.in (5^3, bcc48 + fcc crystal per point from a flat file, Taylor average), 5 steps
+  wrap_*        the block-driver sequence and mm10 on polycrystalline points (three crystals per point), MTS hardening and the
+                48-system layout, two load steps each, with mm10_set_history_locs' layout tables
 
 tests/test_reference_global.py (which needs neither /root/reference nor this script) holds the oracle's solver and the
 kernel source to it.  What is executed from the reference (file:line of the subroutine statement):
@@ -32,11 +38,12 @@ What is NOT the reference's text, and why:
     documented algorithm (plain CG on tmp(:,1..3) = direction, A x direction, residual; user stopping test, ipar(10) = 1).
   * do_nleps_block / rstgp1 / dupstr_blocked / rplstr (drive_eps_sig.f:16-330, rstgp1.f) -- the gather / scatter between the
     global arrays and the 128-point block work space -- are replaced by `drive_eps_sig` below, which calls the reference
-    routines listed above in do_nleps_block's order on one 27-point block.  drive_10_cnst's copy of history(1:36) into the
+    routines listed above in do_nleps_block's order on blocks of at most 128 points.  drive_10_cnst's copy of history(1:36) into the
     block tangent (gptns1.f:519-567) and update.f's n+1 -> n copies are one assignment each, done here.  rknstr_finish_cp (the
     lattice-curvature fit) is not run: its output only enters through k_0, which is zero.
   * mm10_set_cons returns at once for Voce / MTS hardening (mm10_a.f:383-388) and is skipped.  The history layout is computed by
-    the reference's mm10_set_history_locs (mm10_d.f:25-331) from hand-filled material tables (one CP material, one crystal type).
+    the reference's mm10_set_history_locs (mm10_d.f:25-331) from hand-filled material tables (one CP material; one crystal type, or
+    the crystal numbers per point of `crystal_input file`).
   * MKL DFTI is numpy's FFT (tools/fortran_subset.py).
 """
 import hashlib
